@@ -1,0 +1,302 @@
+/* marxb200.h -- C ABI of the B200-native MARX ray-trace path.
+ *
+ * This is the drop-in boundary: plain C, plain pointers and sizes, no C++/torch types.  The host
+ * side of MARX stays C (marx/src/marx.c driver, pfile, jdfits); its module functions call the entry
+ * points below.  Each entry point cites the reference interface it replaces (paths relative to the
+ * MARX 5.5.3 tree).  INTEGRATION.md shows the binding a MARX maintainer would add.
+ *
+ * Conventions (same as the reference, marx/libsrc/marxerr.c:26-54): every function returns 0 on
+ * success and -1 on error; the message is retrievable with marxb200_last_error().  There is no CPU
+ * fallback: if no CUDA device is usable, marxb200_create fails.
+ *
+ * Data model.  The reference's array-of-structs Marx_Photon_Attr_Type (136 B, marx/libsrc/marx.h:51-100)
+ * becomes a structure-of-arrays photon buffer in HBM owned by the context.  Stage calls compact the
+ * live list (the reference's marx_prune_photons, marx/libsrc/photon.c:40-63) in arrival order.
+ * Random draws are counter based: draw k of (ray, stage) is lane k&3 of
+ * Philox4x32-10(key = seed, counter = (ray_lo, ray_hi, k>>2, stage)) mapped to [0,1] as
+ * u32 * (1/4294967295.0)  (jdmath/src/random.c:151-154), so results do not depend on batch size,
+ * launch geometry or GPU count.
+ */
+#ifndef MARXB200_H
+#define MARXB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MARXB200_ABI_VERSION 1
+#define MARXB200_NUM_SHELLS 4          /* MARX_NUM_MIRRORS, marx/libsrc/_marx.h:46 */
+#define MARXB200_MAX_CHIPS 6           /* _MARX_NUM_ACIS_S_CHIPS, _marx.h:41 */
+#define MARXB200_MAX_CONTAM_LAYERS 5   /* MAX_LAYERS, marx/libsrc/aciscontam.c:76 */
+
+typedef struct marxb200_ctx marxb200_ctx;
+
+/* RNG sub-stream ids (counter word 3) */
+enum { MARXB200_STAGE_SOURCE = 0, MARXB200_STAGE_MIRROR = 1, MARXB200_STAGE_GRATING = 2, MARXB200_STAGE_DETECTOR = 3 };
+
+/* photon flags: identical to marx/libsrc/marx.h:65-75 */
+#define MARXB200_PHOTON_UNDETECTED       0x01
+#define MARXB200_PHOTON_UNREFLECTED      0x02
+#define MARXB200_PHOTON_UNDIFFRACTED     0x04
+#define MARXB200_PHOTON_MISSED_DETECTOR  0x08
+#define MARXB200_PHOTON_MIRROR_VBLOCKED  0x10
+#define MARXB200_PHOTON_DRAKE_BLOCKED    0x20
+#define MARXB200_PHOTON_GRATING_VBLOCKED 0x40
+#define MARXB200_BAD_PHOTON_MASK         0xFF
+#define MARXB200_PHOTON_ACIS_STREAKED    0x200
+
+/* Byte-compatible image of Marx_Photon_Attr_Type (marx/libsrc/marx.h:51-100; sizeof == 136 on x86-64).
+ * Used only at the host boundary (upload / download); never stored in HBM. */
+typedef struct
+{
+   double energy;
+   double x[3];
+   double p[3];
+   double arrival_time;
+   uint32_t flags;
+   float y_pixel, z_pixel, u_pixel, v_pixel;
+   float dither_ra, dither_dec, dither_roll, dither_dy, dither_dz, dither_dtheta;
+   float pi;
+   int16_t pulse_height;
+   uint32_t mirror_shell;
+   int8_t ccd_num;
+   int8_t detector_region;
+   int8_t order;
+   int8_t support_orders[4];
+   uint32_t tag;
+}
+marxb200_photon_attr;
+
+/* ------------------------------------------------------------------------------------------------
+ * Module descriptors.  All pointers are HOST pointers; the library copies what it needs to the
+ * device during the call, the caller keeps ownership.  Field meanings are those of the reference
+ * statics they are filled from (cited per field group).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* source + spectrum + arrival times: marx/libsrc/source.c:136-215,260-264 ; spectrum.c:138-181 */
+typedef struct
+{
+   int32_t source_type;            /* 0 = POINT (s-point.c:59-83) */
+   int32_t spectrum_type;          /* 1 = FLAT, 2 = FILE (MARX_*_SPECTRUM, marx.h) */
+   double p[3];                    /* unit vector FROM source TO origin (Marx_Source_Type.p) */
+   double p_normal[3];
+   double distance;                /* mm; <= 0: infinity */
+   double emin, emax;              /* FLAT */
+   const double *spec_energies;    /* FILE: inverse-CDF table (prob.c:46-58) */
+   const double *spec_cum_flux;
+   uint32_t spec_num;
+   double total_flux;              /* photons/s/cm^2 */
+   double geometric_area;          /* Marx_Mirror_Geometric_Area, cm^2 (hrma.c:736) */
+}
+marxb200_source_desc;
+
+/* aspect dither: marx/libsrc/dither.c:50-72,167-182,508-547 (angles already in radians) */
+typedef struct
+{
+   int32_t mode;                   /* 0 = NONE, 1 = INTERNAL */
+   double ra_amp, dec_amp, roll_amp;
+   double ra_period, dec_period, roll_period;
+   double ra_phase, dec_phase, roll_phase;
+   double nominal_roll;
+   double aspect_blur;
+}
+marxb200_dither_desc;
+
+/* one WFOLD scattering table (marx/libsrc/wfold.c:42-60): arrays sorted by e_alpha */
+typedef struct
+{
+   uint32_t num_arrays;
+   const double *e_alpha, *p_min, *delta_p, *p_max, *pow_law_norm, *pow_law_expon;  /* [num_arrays] */
+   const uint32_t *num_theta;      /* [num_arrays] */
+   const uint32_t *theta_offset;   /* [num_arrays] offset of each array in theta_values */
+   const float *theta_values;      /* concatenated */
+   uint32_t total_theta;
+}
+marxb200_wfold_table;
+
+/* one HRMA shell: derived fields of HRMA_Type (marx/libsrc/hrma.c:51-128,551-602,671-745,842-897) */
+typedef struct
+{
+   uint32_t mirror_number;
+   uint32_t shutter_bitmap;
+   double conic_a_p, conic_b_p, conic_c_p, conic_xmin_p, conic_xmax_p;
+   double conic_a_h, conic_b_h, conic_c_h, conic_xmin_h, conic_xmax_h;
+   double to_osac_p[3], to_osac_h[3];
+   double front_position;
+   double area_fraction;           /* cumulative, normalised */
+   double min_radius, max_radius;
+   double p_blur, h_blur;          /* arcsec */
+   double p_scat_factor, h_scat_factor;
+   double fwd_matrix_p[9], bwd_matrix_p[9], fwd_matrix_h[9], bwd_matrix_h[9];
+   const float *corr_energies, *corr_factors;   /* hrma/corr_<n>.dat */
+   uint32_t num_corr;
+   marxb200_wfold_table p_wfold, h_wfold;
+}
+marxb200_hrma_shell;
+
+typedef struct
+{
+   marxb200_hrma_shell shells[MARXB200_NUM_SHELLS];
+   double vignetting_factor;       /* HRMAVig */
+   double cap_position;            /* _Marx_HRMA_Cap_Position */
+   int32_t is_ideal, use_blur, use_wfold, use_struts, use_scale_factors;
+   const float *opt_energies, *opt_betas, *opt_deltas;  /* hrma/iridium.dat */
+   uint32_t num_opt;
+}
+marxb200_hrma_desc;
+
+/* gratings: Grating_Type / Grating_Sector_Type (marx/libsrc/diffract.c:51-91) */
+typedef struct
+{
+   uint32_t num_orders;
+   const int32_t *order_list;      /* [num_orders] */
+   uint32_t num_energies;
+   const float *energies;          /* [num_energies] */
+   const float *cum_eff;           /* [num_orders][num_energies], cumulative */
+   double dispersion_angle;        /* radians */
+   double period;                  /* um */
+   double dp_over_p;
+   double theta_blur;              /* radians */
+   double vig;
+   uint32_t num_sectors;           /* 0: statistical blur (diffract.c:771-777) */
+   const double *sec_min_angle, *sec_max_angle, *sec_dtheta, *sec_dtheta_blur, *sec_dpp, *sec_dpp_blur;
+}
+marxb200_grating_shell;
+
+typedef struct
+{
+   int32_t type;                   /* 0 none, 1 HETG, 2 LETG (MARX_GRATING_*, marx.h:364-376) */
+   marxb200_grating_shell shells[MARXB200_NUM_SHELLS];
+   double rowland[MARXB200_NUM_SHELLS];   /* diameter per shell (diffract.c:885-904) */
+}
+marxb200_grating_desc;
+
+/* one FEF region function: Fef_Type (marx/libsrc/acis_fef.c:87-106) */
+typedef struct
+{
+   uint32_t num_gaussians, num_energies;
+   const float *energies, *channels;   /* [num_energies] */
+   const float *gauss;                 /* [num_energies][num_gaussians][3] = (amp, center, sigma) */
+}
+marxb200_fef;
+
+/* one ACIS chip: Marx_Detector_Geometry_Type (marx.h:398-425) + _Marx_Acis_Chip_Type QE (_marx.h:53-)
+ * + Single_Component_Contam_Type (aciscontam.c:76-91) + FEF region map (acis_fef.c:108-115) */
+typedef struct
+{
+   int32_t id;
+   double x_ll[3], xhat[3], yhat[3], normal[3];
+   double xlen, ylen, x_pixel_size, y_pixel_size, xpixel_offset, ypixel_offset;
+   uint32_t qe_num; const float *qe_energies, *qe;
+   uint32_t filter_num; const float *filter_energies, *filter_qe;
+   uint32_t contam_num_layers;
+   double contam_tau0[MARXB200_MAX_CONTAM_LAYERS], contam_tau1[MARXB200_MAX_CONTAM_LAYERS];
+   uint32_t contam_num_mu[MARXB200_MAX_CONTAM_LAYERS];
+   const float *contam_energies[MARXB200_MAX_CONTAM_LAYERS], *contam_mus[MARXB200_MAX_CONTAM_LAYERS];
+   int32_t contam_fxy_mode;        /* 0: table fxy_vals; 1: fxy_acis_i(x0,y0); 2: fxy_acis456789 (aciscontam.c:141-187) */
+   double contam_x0, contam_y0;
+   uint32_t contam_blocking;       /* FXYBLK */
+   const float *contam_fxy[MARXB200_MAX_CONTAM_LAYERS];   /* [(1024/blk)^2] */
+   const int32_t *fef_map;         /* [32][32] -> index into marxb200_acis_desc.fefs, -1: none (i = x/32 major) */
+}
+marxb200_acis_chip;
+
+typedef struct
+{
+   int32_t detector_type;          /* MARX_DETECTOR_ACIS_S = 2 ... ; 0 = none */
+   int32_t num_chips;
+   marxb200_acis_chip chips[MARXB200_MAX_CHIPS];   /* facet-list order = intersection priority */
+   uint32_t num_fefs;
+   const marxb200_fef *fefs;
+   double det_offset[3];           /* _Marx_Det_XForm_Matrix.dx,dy,dz (detector.c:40-54) */
+   double det_matrix[9];
+   int32_t det_ideal, det_extend;
+   double focal_length;            /* Marx_Focal_Length */
+   double exposure_time, frame_transfer_time, frame_time;   /* acis-i.c:171-200 */
+   int32_t dither_mode;            /* _Marx_Dither_Mode != 0: detector dither applied (detector.c:275-295) */
+}
+marxb200_acis_desc;
+
+/* ------------------------------------------------------------------------------------------------ */
+/* life cycle                                                                                        */
+int marxb200_abi_version (void);
+const char *marxb200_last_error (void);
+/* device_ordinal: CUDA device; seed: RandomSeed (marx.c:846-849, JDMsrandom). */
+int marxb200_create (marxb200_ctx **ctxp, int device_ordinal, uint64_t seed);
+int marxb200_destroy (marxb200_ctx *ctx);
+/* use an externally owned cudaStream_t (e.g. the harness's timing stream); NULL = library stream */
+int marxb200_set_stream (marxb200_ctx *ctx, void *cuda_stream);
+
+/* on (default): every stage compacts survivors, in arrival order, into the other SoA buffer.
+ * off: stages work in place and keep dead rays with their flags (parity tests compare slot by slot). */
+int marxb200_set_compaction (marxb200_ctx *ctx, int on);
+
+/* table upload: called once after the stock *_init functions have loaded the calibration files
+ * (marx_mirror_init/marx_grating_init/marx_detector_init/marx_create_source, marx.h:287,354-362) */
+int marxb200_set_source (marxb200_ctx *ctx, const marxb200_source_desc *d);
+int marxb200_set_dither (marxb200_ctx *ctx, const marxb200_dither_desc *d);
+int marxb200_set_hrma (marxb200_ctx *ctx, const marxb200_hrma_desc *d);
+int marxb200_set_grating (marxb200_ctx *ctx, const marxb200_grating_desc *d);
+int marxb200_set_acis (marxb200_ctx *ctx, const marxb200_acis_desc *d);
+/* convenience: read a calibration pack (tools/ + DESIGN.md "calpack") and call the setters above */
+int marxb200_load_calpack (marxb200_ctx *ctx, const char *path);
+
+/* photon buffer: marx_alloc_photon_type / marx_dealloc_photon_type (photon.c:67-106) */
+int marxb200_alloc_photons (marxb200_ctx *ctx, uint64_t max_photons);
+
+/* marx_create_photons (source.c:268-384): generate n rays with global ray indices
+ * [first_ray, first_ray+n): energies, directions, Poisson arrival times (running sum continued from the
+ * previous call, source.c:285,326), dither.  No energy sort is needed (draws are per-ray).
+ * time_base_in < 0: continue from the context's running time; otherwise restart the sum there. */
+int marxb200_create_photons (marxb200_ctx *ctx, uint64_t first_ray, uint64_t n, double time_base_in);
+/* Multi-GPU time base: sums of the arrival-time increments of rays [first_ray, first_ray+n) per
+ * super-tile of 65536 rays, in canonical order.  Ranks all-gather these (tiny) vectors and add them
+ * sequentially to obtain the time_base_in of their block, which makes arrival times independent of
+ * the number of GPUs (the reference's analogue: marxcat's time-ordered merge, marx/src/marxcat.c:505-535). */
+int marxb200_time_sums (marxb200_ctx *ctx, uint64_t first_ray, uint64_t n, double *sums_host, uint64_t max_sums, uint64_t *n_sums);
+/* marx_mirror_reflect (mirror.c:93 -> hrma.c:1161-1341) */
+int marxb200_mirror_reflect (marxb200_ctx *ctx);
+/* marx_grating_diffract (grating.c:87 -> diffract.c:974-1130) */
+int marxb200_grating_diffract (marxb200_ctx *ctx);
+/* marx_detect (detector.c:361-379 -> acis-s.c:177-248) */
+int marxb200_detect (marxb200_ctx *ctx);
+/* all of the above for one batch, device resident (marx.c:569 + process_photons :240-273) */
+int marxb200_trace (marxb200_ctx *ctx, uint64_t first_ray, uint64_t n);
+
+/* number of live photons / generated rays / running time after the last stage (synchronises) */
+int marxb200_get_counts (marxb200_ctx *ctx, uint64_t *n_generated, uint64_t *n_live, double *total_time);
+/* per-stage live counts of the last batch: [generated, after mirror, after grating, detected]
+ * (the reference's PRINT_STATS_ARRAY, marx.c:68,236-271) */
+int marxb200_get_stage_counts (marxb200_ctx *ctx, uint64_t counts[4]);
+
+/* host boundary.  download: live photons, arrival order, into AoS records (what marx_write_photons,
+ * marxio.c:403-476, and the pipe/rayfile writers consume).  upload: inject photons at a stage boundary
+ * (the reference's RAYFILE channel, s-rayfile.c:188-221); tags are the ray indices used for draws. */
+int marxb200_download (marxb200_ctx *ctx, marxb200_photon_attr *out, uint64_t max_out, uint64_t *n_out);
+int marxb200_upload (marxb200_ctx *ctx, const marxb200_photon_attr *in, uint64_t n, const uint64_t *ray_ids);
+/* debug/parity: download EVERY photon slot of the last stage call, dead ones included (flags say why) */
+int marxb200_download_all (marxb200_ctx *ctx, marxb200_photon_attr *out, uint64_t max_out, uint64_t *n_out);
+
+/* column download of the live list without the AoS detour (bulk egress).
+ * Any pointer may be NULL.  Arrays must hold marxb200_get_counts().n_live entries. */
+typedef struct
+{
+   double *energy, *time, *xpos, *ypos, *zpos, *xcos, *ycos, *zcos;
+   float *chipx, *chipy, *pi;
+   int16_t *pha;
+   int8_t *ccd, *order, *shell;
+   uint64_t *ray;
+}
+marxb200_columns;
+int marxb200_download_columns (marxb200_ctx *ctx, const marxb200_columns *cols, uint64_t max_out, uint64_t *n_out);
+
+/* kernel launch counter (bench.py "gpu_launches") */
+int marxb200_get_launch_count (marxb200_ctx *ctx, uint64_t *n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

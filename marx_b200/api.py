@@ -1,0 +1,228 @@
+"""ctypes host mirror of include/marxb200.h.
+
+Method names follow the reference's module API (marx/libsrc/marx.h:287-293,354-362):
+``create_photons`` / ``mirror_reflect`` / ``grating_diffract`` / ``detect`` over a photon list that
+lives in HBM; ``download`` returns the live list as records laid out exactly like the reference's
+``Marx_Photon_Attr_Type`` (marx.h:51-100).  Error behaviour mirrors the reference: the C calls return
+-1 and a message; here that raises ``MarxB200Error``.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+STAGE_SOURCE, STAGE_MIRROR, STAGE_GRATING, STAGE_DETECTOR = 0, 1, 2, 3
+
+# every symbol include/marxb200.h declares (checked by tests/test_abi.py)
+EXPORTED_SYMBOLS = [
+    "marxb200_abi_version", "marxb200_last_error", "marxb200_create", "marxb200_destroy", "marxb200_set_stream",
+    "marxb200_set_compaction", "marxb200_set_source", "marxb200_set_dither", "marxb200_set_hrma",
+    "marxb200_set_grating", "marxb200_set_acis", "marxb200_load_calpack", "marxb200_alloc_photons",
+    "marxb200_create_photons", "marxb200_time_sums", "marxb200_mirror_reflect", "marxb200_grating_diffract",
+    "marxb200_detect", "marxb200_trace", "marxb200_get_counts", "marxb200_get_stage_counts", "marxb200_download",
+    "marxb200_upload", "marxb200_download_all", "marxb200_download_columns", "marxb200_get_launch_count",
+]
+
+# Marx_Photon_Attr_Type, marx/libsrc/marx.h:51-100 (136 bytes; offsets probed in SURVEY.md 8a1)
+PHOTON_DTYPE = np.dtype({
+    "names": ["energy", "x", "p", "arrival_time", "flags", "y_pixel", "z_pixel", "u_pixel", "v_pixel",
+              "dither", "pi", "pulse_height", "mirror_shell", "ccd_num", "detector_region", "order",
+              "support_orders", "tag"],
+    "formats": ["<f8", ("<f8", 3), ("<f8", 3), "<f8", "<u4", "<f4", "<f4", "<f4", "<f4",
+                ("<f4", 6), "<f4", "<i2", "<u4", "i1", "i1", "i1", ("i1", 4), "<u4"],
+    "offsets": [0, 8, 32, 56, 64, 68, 72, 76, 80, 84, 108, 112, 116, 120, 121, 122, 123, 128],
+    "itemsize": 136,
+})
+
+
+class MarxB200Error(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmarxb200.so")
+
+
+def caldata_path(name):
+    """Path of a calibration pack shipped with the package (marx_b200/caldata/<name>.calpack)."""
+    if not name.endswith(".calpack"):
+        name += ".calpack"
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "caldata", name)
+
+
+_LIB = None
+
+
+def load_library():
+    """dlopen libmarxb200.so (built in-tree by __graft_entry__.build()).  Fails loudly if absent."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise MarxB200Error("libmarxb200.so not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                            "There is no CPU fallback." % path)
+    lib = C.CDLL(path)
+    u64, i32, vp, dbl = C.c_uint64, C.c_int, C.c_void_p, C.c_double
+    lib.marxb200_abi_version.restype = i32
+    lib.marxb200_last_error.restype = C.c_char_p
+    sigs = {
+        "marxb200_create": [C.POINTER(vp), i32, u64],
+        "marxb200_destroy": [vp],
+        "marxb200_set_stream": [vp, vp],
+        "marxb200_set_compaction": [vp, i32],
+        "marxb200_load_calpack": [vp, C.c_char_p],
+        "marxb200_alloc_photons": [vp, u64],
+        "marxb200_create_photons": [vp, u64, u64, dbl],
+        "marxb200_time_sums": [vp, u64, u64, C.POINTER(dbl), u64, C.POINTER(u64)],
+        "marxb200_mirror_reflect": [vp],
+        "marxb200_grating_diffract": [vp],
+        "marxb200_detect": [vp],
+        "marxb200_trace": [vp, u64, u64],
+        "marxb200_get_counts": [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(dbl)],
+        "marxb200_get_stage_counts": [vp, C.POINTER(u64)],
+        "marxb200_download": [vp, vp, u64, C.POINTER(u64)],
+        "marxb200_download_all": [vp, vp, u64, C.POINTER(u64)],
+        "marxb200_upload": [vp, vp, u64, vp],
+        "marxb200_download_columns": [vp, vp, u64, C.POINTER(u64)],
+        "marxb200_get_launch_count": [vp, C.POINTER(u64)],
+    }
+    for name, args in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = i32
+    _LIB = lib
+    return lib
+
+
+class _Columns(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ["energy", "time", "xpos", "ypos", "zpos", "xcos", "ycos", "zcos", "chipx", "chipy", "pi",
+                 "pha", "ccd", "order", "shell", "ray"]]
+
+
+_COLUMN_DTYPES = {"energy": "<f8", "time": "<f8", "xpos": "<f8", "ypos": "<f8", "zpos": "<f8", "xcos": "<f8",
+                  "ycos": "<f8", "zcos": "<f8", "chipx": "<f4", "chipy": "<f4", "pi": "<f4", "pha": "<i2",
+                  "ccd": "i1", "order": "i1", "shell": "i1", "ray": "<u8"}
+
+
+class MarxB200:
+    """One context = one GPU = one photon list (the reference's single Marx_Photon_Type, marx.c:444)."""
+
+    def __init__(self, calpack, device=0, seed=1, max_photons=1 << 20, stream=None):
+        self._lib = load_library()
+        self._ctx = C.c_void_p()
+        self._check(self._lib.marxb200_create(C.byref(self._ctx), int(device), int(seed)))
+        try:
+            if stream is not None:
+                self._check(self._lib.marxb200_set_stream(self._ctx, C.c_void_p(int(stream))))
+            path = calpack if os.path.exists(calpack) else caldata_path(calpack)
+            self._check(self._lib.marxb200_load_calpack(self._ctx, path.encode()))
+            self._check(self._lib.marxb200_alloc_photons(self._ctx, int(max_photons)))
+        except Exception:
+            self.close()
+            raise
+        self.max_photons = int(max_photons)
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise MarxB200Error(self._lib.marxb200_last_error().decode(errors="replace"))
+
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._lib.marxb200_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- the module API ------------------------------------------------------------------------
+    def set_compaction(self, on):
+        self._check(self._lib.marxb200_set_compaction(self._ctx, 1 if on else 0))
+
+    def create_photons(self, first_ray, n, time_base=-1.0):
+        """marx_create_photons (source.c:268-384) for global ray indices [first_ray, first_ray+n)."""
+        self._check(self._lib.marxb200_create_photons(self._ctx, int(first_ray), int(n), float(time_base)))
+
+    def time_sums(self, first_ray, n):
+        cap = n // 65536 + 2
+        buf = (C.c_double * cap)()
+        ns = C.c_uint64()
+        self._check(self._lib.marxb200_time_sums(self._ctx, int(first_ray), int(n), buf, cap, C.byref(ns)))
+        return np.frombuffer(buf, dtype=np.float64, count=ns.value).copy()
+
+    def mirror_reflect(self):
+        self._check(self._lib.marxb200_mirror_reflect(self._ctx))
+
+    def grating_diffract(self):
+        self._check(self._lib.marxb200_grating_diffract(self._ctx))
+
+    def detect(self):
+        self._check(self._lib.marxb200_detect(self._ctx))
+
+    def trace(self, first_ray, n):
+        """create -> mirror -> grating -> detect for one batch, device resident (marx.c:569, :240-273)."""
+        self._check(self._lib.marxb200_trace(self._ctx, int(first_ray), int(n)))
+
+    # -- results -------------------------------------------------------------------------------
+    def counts(self):
+        g, l, t = C.c_uint64(), C.c_uint64(), C.c_double()
+        self._check(self._lib.marxb200_get_counts(self._ctx, C.byref(g), C.byref(l), C.byref(t)))
+        return g.value, l.value, t.value
+
+    def stage_counts(self):
+        a = (C.c_uint64 * 4)()
+        self._check(self._lib.marxb200_get_stage_counts(self._ctx, a))
+        return [int(v) for v in a]
+
+    def launch_count(self):
+        n = C.c_uint64()
+        self._check(self._lib.marxb200_get_launch_count(self._ctx, C.byref(n)))
+        return n.value
+
+    def download(self, all_slots=False, out=None):
+        """Live photons in arrival order as Marx_Photon_Attr_Type records (all slots if compaction is off)."""
+        _, live, _ = self.counts()
+        n = max(int(live), 1)
+        if out is None:
+            out = np.zeros(n, dtype=PHOTON_DTYPE)
+        got = C.c_uint64()
+        fn = self._lib.marxb200_download_all if all_slots else self._lib.marxb200_download
+        self._check(fn(self._ctx, out.ctypes.data_as(C.c_void_p), len(out), C.byref(got)))
+        return out[:got.value]
+
+    def upload(self, photons, ray_ids=None):
+        """Inject photons at a stage boundary (the reference's RAYFILE channel, s-rayfile.c:188-221)."""
+        photons = np.ascontiguousarray(photons, dtype=PHOTON_DTYPE)
+        ids = None
+        if ray_ids is not None:
+            ids = np.ascontiguousarray(ray_ids, dtype=np.uint64)
+        self._check(self._lib.marxb200_upload(self._ctx, photons.ctypes.data_as(C.c_void_p), len(photons),
+                                              ids.ctypes.data_as(C.c_void_p) if ids is not None else None))
+
+    def download_columns(self, names=("energy", "time", "chipx", "chipy", "pha", "ccd", "order", "ray"), out=None):
+        _, live, _ = self.counts()
+        n = max(int(live), 1)
+        cols = _Columns()
+        arrays = {}
+        for name in names:
+            if out is not None and name in out:
+                arr = out[name]
+            else:
+                arr = np.empty(n, dtype=_COLUMN_DTYPES[name])
+            arrays[name] = arr
+            setattr(cols, name, arr.ctypes.data)
+        got = C.c_uint64()
+        cap = min(len(a) for a in arrays.values()) if arrays else 0
+        self._check(self._lib.marxb200_download_columns(self._ctx, C.byref(cols), cap, C.byref(got)))
+        return {k: v[:got.value] for k, v in arrays.items()}

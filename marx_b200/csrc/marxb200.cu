@@ -1,0 +1,624 @@
+// marxb200.cu -- context, table upload and the C ABI declared in include/marxb200.h.
+// Thin by design: everything per-photon happens in kernels.cu.  No CPU fallback exists: every entry
+// point needs a CUDA device and fails with -1 otherwise.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <map>
+#include "../../include/marxb200.h"
+#include "../../include/marxb200_calpack.h"
+#include "mx_tables.h"
+#include "mx_kernels.cuh"
+#include "tables_build.hpp"
+
+static_assert (sizeof (marxb200_photon_attr) == 136, "must match sizeof(Marx_Photon_Attr_Type), SURVEY.md 8a1");
+static_assert (offsetof (marxb200_photon_attr, flags) == 64, "layout");
+static_assert (offsetof (marxb200_photon_attr, pi) == 108, "layout");
+static_assert (offsetof (marxb200_photon_attr, pulse_height) == 112, "layout");
+static_assert (offsetof (marxb200_photon_attr, mirror_shell) == 116, "layout");
+static_assert (offsetof (marxb200_photon_attr, ccd_num) == 120, "layout");
+static_assert (offsetof (marxb200_photon_attr, tag) == 128, "layout");
+
+using namespace mx;
+
+static thread_local char g_err[512] = "";
+static int fail (const char *fmt, ...)
+{
+   va_list ap;
+   va_start (ap, fmt);
+   vsnprintf (g_err, sizeof (g_err), fmt, ap);
+   va_end (ap);
+   return -1;
+}
+#define CUDA_OK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return fail ("%s: %s", #expr, cudaGetErrorString (e_)); } while (0)
+
+struct marxb200_ctx
+{
+   int device = 0;
+   int num_sms = 0;
+   uint64_t seed = 0;
+   cudaStream_t stream = nullptr;
+   bool own_stream = false;
+   int compact = 1;
+
+   // photon buffers
+   uint64_t capacity = 0;
+   void *slab[2] = {nullptr, nullptr};
+   PhotonSoA buf[2];
+   int cur = 0;
+
+   // device scalars: counts[0..3] + ticket + total_time
+   unsigned long long *d_counts = nullptr;      // [4]
+   unsigned long long *d_ticket = nullptr;
+   unsigned long long *d_tile_status = nullptr; // [capacity/kTile + 1]
+   double *d_tile_sums = nullptr, *d_tile_base = nullptr, *d_super_sums = nullptr, *d_total_time = nullptr;
+   int stage_done = -1;                          // index into d_counts of the latest valid count
+   uint64_t n_generated = 0;
+   double batch_start_time = 0.0;                // pt->start_time of the current batch
+   double running_time = 0.0;                    // absolute time after the last generated ray
+   bool running_time_dirty = false;
+
+   // tables
+   std::vector<void *> allocs;                   // every cudaMalloc'd table (freed in destroy)
+   SourceDev S; DitherDev D;
+   bool have_source = false, have_dither = false, have_hrma = false, have_grating = false, have_acis = false;
+   int grating_type = 0, detector_type = 0;
+   double source_distance = 0.0;
+   void *blob1 = nullptr, *blob2 = nullptr, *blob3 = nullptr;
+   uint32_t blob1_bytes = 0, blob2_bytes = 0, blob3_bytes = 0;
+   int grid1 = 0, grid2 = 0, grid3 = 0;
+
+   // host boundary staging
+   void *d_aos = nullptr; uint64_t d_aos_cap = 0;
+   void *h_pinned = nullptr; size_t h_pinned_bytes = 0;
+
+   uint64_t launches = 0;
+};
+
+// ---------------------------------------------------------------------------------------------
+static int dev_upload (marxb200_ctx *c, const void *host, size_t bytes, void **out)
+{
+   void *d = nullptr;
+   if (bytes == 0) bytes = 16;
+   size_t padded = (bytes + 255) & ~(size_t) 255;
+   CUDA_OK (cudaMalloc (&d, padded));
+   CUDA_OK (cudaMemsetAsync (d, 0, padded, c->stream));
+   if (host != nullptr) CUDA_OK (cudaMemcpyAsync (d, host, bytes, cudaMemcpyHostToDevice, c->stream));
+   CUDA_OK (cudaStreamSynchronize (c->stream));
+   c->allocs.push_back (d);
+   *out = d;
+   return 0;
+}
+template <class T> static int dev_upload_t (marxb200_ctx *c, const T *host, size_t n, const T **out)
+{
+   void *d;
+   if (-1 == dev_upload (c, host, n * sizeof (T), &d)) return -1;
+   *out = (const T *) d;
+   return 0;
+}
+static size_t align16 (size_t x) { return (x + 15) & ~(size_t) 15; }
+
+static int ensure_pinned (marxb200_ctx *c, size_t bytes)
+{
+   if (c->h_pinned_bytes >= bytes) return 0;
+   if (c->h_pinned) cudaFreeHost (c->h_pinned);
+   c->h_pinned = nullptr; c->h_pinned_bytes = 0;
+   CUDA_OK (cudaMallocHost (&c->h_pinned, bytes));
+   c->h_pinned_bytes = bytes;
+   return 0;
+}
+static int ensure_aos (marxb200_ctx *c, uint64_t n)
+{
+   if (c->d_aos_cap >= n) return 0;
+   if (c->d_aos) cudaFree (c->d_aos);
+   c->d_aos = nullptr; c->d_aos_cap = 0;
+   CUDA_OK (cudaMalloc (&c->d_aos, (size_t) n * sizeof (marxb200_photon_attr)));
+   c->d_aos_cap = n;
+   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int marxb200_abi_version (void) { return MARXB200_ABI_VERSION; }
+extern "C" const char *marxb200_last_error (void) { return g_err; }
+
+extern "C" int marxb200_create (marxb200_ctx **ctxp, int device_ordinal, uint64_t seed)
+{
+   if (ctxp == nullptr) return fail ("marxb200_create: NULL ctxp");
+   *ctxp = nullptr;
+   int ndev = 0;
+   cudaError_t e = cudaGetDeviceCount (&ndev);
+   if ((e != cudaSuccess) || (ndev == 0))
+     return fail ("marxb200_create: no CUDA device available (%s); there is no CPU fallback", cudaGetErrorString (e));
+   if ((device_ordinal < 0) || (device_ordinal >= ndev)) return fail ("marxb200_create: bad device ordinal %d", device_ordinal);
+   CUDA_OK (cudaSetDevice (device_ordinal));
+   marxb200_ctx *c = new marxb200_ctx ();
+   c->device = device_ordinal;
+   c->seed = seed;
+   cudaDeviceProp prop;
+   CUDA_OK (cudaGetDeviceProperties (&prop, device_ordinal));
+   c->num_sms = prop.multiProcessorCount;
+   CUDA_OK (cudaStreamCreateWithFlags (&c->stream, cudaStreamNonBlocking));
+   c->own_stream = true;
+   CUDA_OK (cudaMalloc (&c->d_counts, 4 * sizeof (unsigned long long)));
+   CUDA_OK (cudaMalloc (&c->d_ticket, sizeof (unsigned long long)));
+   CUDA_OK (cudaMalloc (&c->d_total_time, sizeof (double)));
+   CUDA_OK (cudaMemset (c->d_counts, 0, 4 * sizeof (unsigned long long)));
+   CUDA_OK (cudaMemset (c->d_total_time, 0, sizeof (double)));
+   memset (&c->S, 0, sizeof (c->S));
+   memset (&c->D, 0, sizeof (c->D));
+   *ctxp = c;
+   return 0;
+}
+
+extern "C" int marxb200_destroy (marxb200_ctx *c)
+{
+   if (c == nullptr) return -1;
+   cudaSetDevice (c->device);
+   cudaDeviceSynchronize ();
+   for (void *p : c->allocs) cudaFree (p);
+   for (int i = 0; i < 2; i++) if (c->slab[i]) cudaFree (c->slab[i]);
+   cudaFree (c->d_counts); cudaFree (c->d_ticket); cudaFree (c->d_total_time);
+   if (c->d_tile_status) cudaFree (c->d_tile_status);
+   if (c->d_tile_sums) cudaFree (c->d_tile_sums);
+   if (c->d_tile_base) cudaFree (c->d_tile_base);
+   if (c->d_super_sums) cudaFree (c->d_super_sums);
+   if (c->d_aos) cudaFree (c->d_aos);
+   if (c->h_pinned) cudaFreeHost (c->h_pinned);
+   if (c->own_stream && c->stream) cudaStreamDestroy (c->stream);
+   delete c;
+   return 0;
+}
+
+extern "C" int marxb200_set_stream (marxb200_ctx *c, void *cuda_stream)
+{
+   if (c == nullptr) return fail ("NULL ctx");
+   CUDA_OK (cudaStreamSynchronize (c->stream));
+   if (cuda_stream == nullptr)
+     {
+        if (!c->own_stream)
+          {
+             CUDA_OK (cudaStreamCreateWithFlags (&c->stream, cudaStreamNonBlocking));
+             c->own_stream = true;
+          }
+        return 0;
+     }
+   if (c->own_stream) cudaStreamDestroy (c->stream);
+   c->own_stream = false;
+   c->stream = (cudaStream_t) cuda_stream;
+   return 0;
+}
+
+extern "C" int marxb200_set_compaction (marxb200_ctx *c, int on)
+{
+   if (c == nullptr) return fail ("NULL ctx");
+   c->compact = on ? 1 : 0;
+   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// table setters
+// ---------------------------------------------------------------------------------------------
+extern "C" int marxb200_set_source (marxb200_ctx *c, const marxb200_source_desc *d)
+{
+   if ((c == nullptr) || (d == nullptr)) return fail ("marxb200_set_source: NULL argument");
+   if (d->source_type != 0) return fail ("marxb200_set_source: only POINT sources are implemented (type %d)", d->source_type);
+   if ((d->spectrum_type != 1) && (d->spectrum_type != 2)) return fail ("marxb200_set_source: unknown spectrum type %d", d->spectrum_type);
+   CUDA_OK (cudaSetDevice (c->device));
+   SourceDev &S = c->S;
+   memset (&S, 0, sizeof (S));
+   S.source_type = d->source_type; S.spectrum_type = d->spectrum_type;
+   for (int i = 0; i < 3; i++) { S.p[i] = d->p[i]; S.p_normal[i] = d->p_normal[i]; }
+   S.distance = d->distance; S.emin = d->emin; S.emax = d->emax;
+   if (d->spectrum_type == 2)
+     {
+        if ((d->spec_num < 2) || !d->spec_energies || !d->spec_cum_flux) return fail ("marxb200_set_source: FILE spectrum needs a table");
+        if (-1 == dev_upload_t (c, d->spec_energies, d->spec_num, &S.spec_energies)) return -1;
+        if (-1 == dev_upload_t (c, d->spec_cum_flux, d->spec_num, &S.spec_cum_flux)) return -1;
+        S.spec_num = d->spec_num;
+     }
+   // compute_mean_time, source.c:260-264
+   S.mean_time = (d->total_flux <= 0.0) ? 0.0 : 1.0 / d->total_flux / d->geometric_area;
+   c->source_distance = d->distance;
+   c->have_source = true;
+   return 0;
+}
+
+extern "C" int marxb200_set_dither (marxb200_ctx *c, const marxb200_dither_desc *d)
+{
+   if ((c == nullptr) || (d == nullptr)) return fail ("marxb200_set_dither: NULL argument");
+   if ((d->mode != 0) && (d->mode != 1)) return fail ("marxb200_set_dither: only NONE and INTERNAL models are implemented (mode %d)", d->mode);
+   DitherDev &D = c->D;
+   D.mode = d->mode;
+   D.ra_amp = d->ra_amp; D.dec_amp = d->dec_amp; D.roll_amp = d->roll_amp;
+   D.ra_period = d->ra_period; D.dec_period = d->dec_period; D.roll_period = d->roll_period;
+   D.ra_phase = d->ra_phase; D.dec_phase = d->dec_phase; D.roll_phase = d->roll_phase;
+   D.nominal_roll = d->nominal_roll; D.aspect_blur = d->aspect_blur;
+   c->have_dither = true;
+   return 0;
+}
+
+struct CudaUploader
+{
+   marxb200_ctx *c;
+   std::string err;
+   const void *operator() (const void *host, size_t bytes)
+   {
+      void *d = nullptr;
+      if (-1 == dev_upload (c, host, bytes, &d)) { err = g_err; return nullptr; }
+      return d;
+   }
+};
+
+extern "C" int marxb200_set_hrma (marxb200_ctx *c, const marxb200_hrma_desc *d)
+{
+   if ((c == nullptr) || (d == nullptr)) return fail ("marxb200_set_hrma: NULL argument");
+   CUDA_OK (cudaSetDevice (c->device));
+   CudaUploader up{c};
+   std::vector<unsigned char> blob;
+   std::string err;
+   if (-1 == mx::build_hrma_blob (up, d, blob, err)) return fail ("marxb200_set_hrma: %s", err.c_str ());
+   if (-1 == dev_upload (c, blob.data (), blob.size (), &c->blob1)) return -1;
+   c->blob1_bytes = (uint32_t) blob.size ();
+   c->grid1 = stage_grid_size (1, c->num_sms, c->blob1_bytes);
+   c->have_hrma = true;
+   return 0;
+}
+
+extern "C" int marxb200_set_grating (marxb200_ctx *c, const marxb200_grating_desc *d)
+{
+   if ((c == nullptr) || (d == nullptr)) return fail ("marxb200_set_grating: NULL argument");
+   CUDA_OK (cudaSetDevice (c->device));
+   c->grating_type = d->type;
+   c->have_grating = true;
+   if (d->type == 0) return 0;
+   CudaUploader up{c};
+   std::vector<unsigned char> blob;
+   std::string err;
+   if (-1 == mx::build_grating_blob (up, d, blob, err)) { c->have_grating = false; return fail ("marxb200_set_grating: %s", err.c_str ()); }
+   if (-1 == dev_upload (c, blob.data (), blob.size (), &c->blob2)) return -1;
+   c->blob2_bytes = (uint32_t) blob.size ();
+   c->grid2 = stage_grid_size (2, c->num_sms, c->blob2_bytes);
+   return 0;
+}
+
+extern "C" int marxb200_set_acis (marxb200_ctx *c, const marxb200_acis_desc *d)
+{
+   if ((c == nullptr) || (d == nullptr)) return fail ("marxb200_set_acis: NULL argument");
+   CUDA_OK (cudaSetDevice (c->device));
+   c->detector_type = d->detector_type;
+   c->have_acis = true;
+   if (d->detector_type == 0) return 0;
+   CudaUploader up{c};
+   std::vector<unsigned char> blob;
+   std::string err;
+   if (-1 == mx::build_acis_blob (up, d, blob, err)) { c->have_acis = false; return fail ("marxb200_set_acis: %s", err.c_str ()); }
+   if (-1 == dev_upload (c, blob.data (), blob.size (), &c->blob3)) return -1;
+   c->blob3_bytes = (uint32_t) blob.size ();
+   c->grid3 = stage_grid_size (3, c->num_sms, c->blob3_bytes);
+   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// photon buffers
+// ---------------------------------------------------------------------------------------------
+static size_t carve (PhotonSoA &b, unsigned char *base, uint64_t n)
+{
+   size_t off = 0;
+   auto take = [&] (size_t elem) { size_t o = off; off = (off + elem * n + 255) & ~(size_t) 255; return base ? base + o : (unsigned char *) nullptr; };
+   b.energy = (double *) take (8);
+   b.x0 = (double *) take (8); b.x1 = (double *) take (8); b.x2 = (double *) take (8);
+   b.p0 = (double *) take (8); b.p1 = (double *) take (8); b.p2 = (double *) take (8);
+   b.time = (double *) take (8);
+   b.ray = (uint64_t *) take (8);
+   b.flags = (uint32_t *) take (4);
+   b.dra = (float *) take (4); b.ddec = (float *) take (4); b.droll = (float *) take (4);
+   b.chipx = (float *) take (4); b.chipy = (float *) take (4); b.pi = (float *) take (4);
+   b.pha = (int16_t *) take (2);
+   b.shell = (uint8_t *) take (1);
+   b.order = (int8_t *) take (1); b.ccd = (int8_t *) take (1);
+   return off;
+}
+
+extern "C" int marxb200_alloc_photons (marxb200_ctx *c, uint64_t max_photons)
+{
+   if (c == nullptr) return fail ("NULL ctx");
+   if (max_photons == 0) return fail ("marxb200_alloc_photons: max_photons must be > 0");
+   CUDA_OK (cudaSetDevice (c->device));
+   CUDA_OK (cudaStreamSynchronize (c->stream));
+   for (int i = 0; i < 2; i++) if (c->slab[i]) { cudaFree (c->slab[i]); c->slab[i] = nullptr; }
+   if (c->d_tile_status) cudaFree (c->d_tile_status);
+   if (c->d_tile_sums) cudaFree (c->d_tile_sums);
+   if (c->d_tile_base) cudaFree (c->d_tile_base);
+   if (c->d_super_sums) cudaFree (c->d_super_sums);
+   PhotonSoA tmp;
+   size_t bytes = carve (tmp, nullptr, max_photons);
+   for (int i = 0; i < 2; i++)
+     {
+        CUDA_OK (cudaMalloc (&c->slab[i], bytes));
+        CUDA_OK (cudaMemsetAsync (c->slab[i], 0, bytes, c->stream));
+        carve (c->buf[i], (unsigned char *) c->slab[i], max_photons);
+     }
+   uint64_t n_tiles = (max_photons + kTile - 1) / kTile + 1;
+   uint64_t n_super = (n_tiles + kSuperTile - 1) / kSuperTile + 1;
+   CUDA_OK (cudaMalloc (&c->d_tile_status, n_tiles * sizeof (unsigned long long)));
+   CUDA_OK (cudaMalloc (&c->d_tile_sums, n_tiles * sizeof (double)));
+   CUDA_OK (cudaMalloc (&c->d_tile_base, n_tiles * sizeof (double)));
+   CUDA_OK (cudaMalloc (&c->d_super_sums, n_super * sizeof (double)));
+   CUDA_OK (cudaStreamSynchronize (c->stream));
+   c->capacity = max_photons;
+   c->cur = 0; c->stage_done = -1; c->n_generated = 0;
+   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stages
+// ---------------------------------------------------------------------------------------------
+static void fill_source_args (marxb200_ctx *c, SourceArgs &a, uint64_t first_ray, uint64_t n, double time_base)
+{
+   a.out = c->buf[0];
+   a.first_ray = first_ray; a.n = n; a.seed = c->seed;
+   a.S = c->S; a.D = c->D;
+   a.time_base = time_base;
+   a.tile_sums = c->d_tile_sums; a.tile_base = c->d_tile_base; a.supertile_sums = c->d_super_sums;
+   a.total_time = c->d_total_time;
+   a.n_out = c->d_counts + 0;
+}
+
+static int sync_running_time (marxb200_ctx *c)
+{
+   if (!c->running_time_dirty) return 0;
+   CUDA_OK (cudaMemcpyAsync (&c->running_time, c->d_total_time, sizeof (double), cudaMemcpyDeviceToHost, c->stream));
+   CUDA_OK (cudaStreamSynchronize (c->stream));
+   c->running_time_dirty = false;
+   return 0;
+}
+
+extern "C" int marxb200_create_photons (marxb200_ctx *c, uint64_t first_ray, uint64_t n, double time_base_in)
+{
+   if (c == nullptr) return fail ("NULL ctx");
+   if (!c->have_source) return fail ("marxb200_create_photons: no source set");
+   if (n > c->capacity) return fail ("marxb200_create_photons: n=%llu exceeds the allocated capacity %llu", (unsigned long long) n, (unsigned long long) c->capacity);
+   CUDA_OK (cudaSetDevice (c->device));
+   SourceArgs a;
+   if (time_base_in >= 0.0)
+     {
+        fill_source_args (c, a, first_ray, n, time_base_in);
+        c->batch_start_time = time_base_in;
+     }
+   else
+     {
+        // continue the running sum without a host round trip: the device scalar holds the end time
+        if (-1 == sync_running_time (c)) return -1;
+        fill_source_args (c, a, first_ray, n, c->running_time);
+        c->batch_start_time = c->running_time;
+     }
+   launch_time_sums (a, c->stream);
+   launch_time_scan (a, c->stream);
+   launch_source (a, c->stream);
+   c->launches += 3;
+   CUDA_OK (cudaGetLastError ());
+   c->running_time_dirty = true;
+   c->cur = 0; c->stage_done = 0; c->n_generated = n;
+   return 0;
+}
+
+// super-tile sums of the arrival-time increments of rays [first_ray, first_ray+n) -- the quantity ranks
+// exchange (all-gather) to give every GPU its time base (DESIGN.md "multi-GPU").
+extern "C" int marxb200_time_sums (marxb200_ctx *c, uint64_t first_ray, uint64_t n, double *sums_host, uint64_t max_sums, uint64_t *n_sums)
+{
+   if (c == nullptr) return fail ("NULL ctx");
+   if (!c->have_source) return fail ("marxb200_time_sums: no source set");
+   if (n > c->capacity) return fail ("marxb200_time_sums: n exceeds capacity");
+   CUDA_OK (cudaSetDevice (c->device));
+   SourceArgs a;
+   fill_source_args (c, a, first_ray, n, 0.0);
+   launch_time_sums (a, c->stream);
+   launch_time_scan (a, c->stream);
+   c->launches += 2;
+   uint64_t n_tiles = (n + kTile - 1) / kTile, ns = (n_tiles + kSuperTile - 1) / kSuperTile;
+   if (ns > max_sums) return fail ("marxb200_time_sums: need room for %llu sums", (unsigned long long) ns);
+   CUDA_OK (cudaMemcpyAsync (sums_host, c->d_super_sums, ns * sizeof (double), cudaMemcpyDeviceToHost, c->stream));
+   CUDA_OK (cudaStreamSynchronize (c->stream));
+   if (n_sums) *n_sums = ns;
+   return 0;
+}
+
+static int run_stage (marxb200_ctx *c, int stage)
+{
+   StageArgs a;
+   memset (&a, 0, sizeof (a));
+   if (c->stage_done < 0) return fail ("stage %d: no photons (call marxb200_create_photons or marxb200_upload first)", stage);
+   a.in = c->buf[c->cur];
+   a.out = c->compact ? c->buf[1 - c->cur] : c->buf[c->cur];
+   a.n_in = c->d_counts + c->stage_done;
+   a.n_out = c->d_counts + stage;
+   a.ticket = c->d_ticket;
+   a.tile_status = c->d_tile_status;
+   a.seed = c->seed;
+   a.compact = c->compact;
+   a.source_distance = c->source_distance;
+   uint64_t n_tiles = (c->n_generated + kTile - 1) / kTile + 1;
+   CUDA_OK (cudaMemsetAsync (c->d_ticket, 0, sizeof (unsigned long long), c->stream));
+   if (c->compact) CUDA_OK (cudaMemsetAsync (c->d_tile_status, 0, n_tiles * sizeof (unsigned long long), c->stream));
+   switch (stage)
+     {
+      case 1: a.blob = c->blob1; a.blob_bytes = c->blob1_bytes; launch_hrma (a, c->grid1, c->stream); break;
+      case 2: a.blob = c->blob2; a.blob_bytes = c->blob2_bytes; launch_grating (a, c->grid2, c->stream); break;
+      case 3: a.blob = c->blob3; a.blob_bytes = c->blob3_bytes; launch_acis (a, c->grid3, c->stream); break;
+     }
+   c->launches += 1;
+   CUDA_OK (cudaGetLastError ());
+   if (c->compact) c->cur = 1 - c->cur;
+   c->stage_done = stage;
+   return 0;
+}
+
+extern "C" int marxb200_mirror_reflect (marxb200_ctx *c)
+{
+   if (c == nullptr) return fail ("NULL ctx");
+   if (!c->have_hrma) return fail ("marxb200_mirror_reflect: no HRMA tables set");
+   CUDA_OK (cudaSetDevice (c->device));
+   return run_stage (c, 1);
+}
+extern "C" int marxb200_grating_diffract (marxb200_ctx *c)
+{
+   if (c == nullptr) return fail ("NULL ctx");
+   if (!c->have_grating) return fail ("marxb200_grating_diffract: no grating set");
+   CUDA_OK (cudaSetDevice (c->device));
+   if (c->grating_type == 0)
+     {
+        // GratingType=NONE: the stage is the identity (grating.c:87-110); carry the count forward
+        if (c->stage_done < 0) return fail ("marxb200_grating_diffract: no photons");
+        CUDA_OK (cudaMemcpyAsync (c->d_counts + 2, c->d_counts + c->stage_done, sizeof (unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
+        c->stage_done = 2;
+        return 0;
+     }
+   return run_stage (c, 2);
+}
+extern "C" int marxb200_detect (marxb200_ctx *c)
+{
+   if (c == nullptr) return fail ("NULL ctx");
+   if (!c->have_acis) return fail ("marxb200_detect: no detector set");
+   CUDA_OK (cudaSetDevice (c->device));
+   if (c->detector_type == 0)
+     {
+        if (c->stage_done < 0) return fail ("marxb200_detect: no photons");
+        CUDA_OK (cudaMemcpyAsync (c->d_counts + 3, c->d_counts + c->stage_done, sizeof (unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
+        c->stage_done = 3;
+        return 0;
+     }
+   return run_stage (c, 3);
+}
+
+extern "C" int marxb200_trace (marxb200_ctx *c, uint64_t first_ray, uint64_t n)
+{
+   if (-1 == marxb200_create_photons (c, first_ray, n, -1.0)) return -1;
+   if (-1 == marxb200_mirror_reflect (c)) return -1;
+   if (-1 == marxb200_grating_diffract (c)) return -1;
+   if (-1 == marxb200_detect (c)) return -1;
+   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// counts and host boundary
+// ---------------------------------------------------------------------------------------------
+extern "C" int marxb200_get_stage_counts (marxb200_ctx *c, uint64_t counts[4])
+{
+   if (c == nullptr) return fail ("NULL ctx");
+   CUDA_OK (cudaSetDevice (c->device));
+   unsigned long long h[4];
+   CUDA_OK (cudaMemcpyAsync (h, c->d_counts, sizeof (h), cudaMemcpyDeviceToHost, c->stream));
+   CUDA_OK (cudaStreamSynchronize (c->stream));
+   for (int i = 0; i < 4; i++) counts[i] = (i <= c->stage_done) ? h[i] : 0;
+   return 0;
+}
+
+extern "C" int marxb200_get_counts (marxb200_ctx *c, uint64_t *n_generated, uint64_t *n_live, double *total_time)
+{
+   if (c == nullptr) return fail ("NULL ctx");
+   uint64_t cnt[4];
+   if (-1 == marxb200_get_stage_counts (c, cnt)) return -1;
+   if (-1 == sync_running_time (c)) return -1;
+   if (n_generated) *n_generated = c->n_generated;
+   if (n_live) *n_live = (c->stage_done >= 0) ? cnt[c->stage_done] : 0;
+   if (total_time) *total_time = c->running_time;
+   return 0;
+}
+
+static int download_impl (marxb200_ctx *c, marxb200_photon_attr *out, uint64_t max_out, uint64_t *n_out)
+{
+   if ((c == nullptr) || (out == nullptr)) return fail ("download: NULL argument");
+   if (c->stage_done < 0) { if (n_out) *n_out = 0; return 0; }
+   CUDA_OK (cudaSetDevice (c->device));
+   unsigned long long n = 0;
+   CUDA_OK (cudaMemcpyAsync (&n, c->d_counts + c->stage_done, sizeof (n), cudaMemcpyDeviceToHost, c->stream));
+   CUDA_OK (cudaStreamSynchronize (c->stream));
+   if (n > max_out) n = max_out;
+   if (n_out) *n_out = n;
+   if (n == 0) return 0;
+   if (-1 == ensure_aos (c, n)) return -1;
+   launch_soa_to_aos (c->buf[c->cur], c->d_counts + c->stage_done, n, c->d_aos, c->batch_start_time, c->stream);
+   c->launches += 1;
+   CUDA_OK (cudaMemcpyAsync (out, c->d_aos, (size_t) n * sizeof (marxb200_photon_attr), cudaMemcpyDeviceToHost, c->stream));
+   CUDA_OK (cudaStreamSynchronize (c->stream));
+   return 0;
+}
+
+extern "C" int marxb200_download (marxb200_ctx *c, marxb200_photon_attr *out, uint64_t max_out, uint64_t *n_out)
+{
+   if (c && !c->compact) return fail ("marxb200_download: compaction is off; use marxb200_download_all");
+   return download_impl (c, out, max_out, n_out);
+}
+extern "C" int marxb200_download_all (marxb200_ctx *c, marxb200_photon_attr *out, uint64_t max_out, uint64_t *n_out)
+{
+   return download_impl (c, out, max_out, n_out);
+}
+
+extern "C" int marxb200_upload (marxb200_ctx *c, const marxb200_photon_attr *in, uint64_t n, const uint64_t *ray_ids)
+{
+   if ((c == nullptr) || (in == nullptr)) return fail ("marxb200_upload: NULL argument");
+   if (n > c->capacity) return fail ("marxb200_upload: n exceeds capacity");
+   CUDA_OK (cudaSetDevice (c->device));
+   if (-1 == ensure_aos (c, n ? n : 1)) return -1;
+   CUDA_OK (cudaMemcpyAsync (c->d_aos, in, (size_t) n * sizeof (marxb200_photon_attr), cudaMemcpyHostToDevice, c->stream));
+   uint64_t *d_ids = nullptr;
+   if (ray_ids)
+     {
+        CUDA_OK (cudaMalloc (&d_ids, (n ? n : 1) * sizeof (uint64_t)));
+        CUDA_OK (cudaMemcpyAsync (d_ids, ray_ids, n * sizeof (uint64_t), cudaMemcpyHostToDevice, c->stream));
+     }
+   c->cur = 0;
+   c->batch_start_time = 0.0;
+   launch_aos_to_soa (c->d_aos, d_ids, n, c->buf[0], 0.0, c->stream);
+   c->launches += 1;
+   unsigned long long nn = n;
+   CUDA_OK (cudaMemcpyAsync (c->d_counts + 0, &nn, sizeof (nn), cudaMemcpyHostToDevice, c->stream));
+   CUDA_OK (cudaStreamSynchronize (c->stream));
+   if (d_ids) cudaFree (d_ids);
+   c->stage_done = 0; c->n_generated = n;
+   return 0;
+}
+
+extern "C" int marxb200_download_columns (marxb200_ctx *c, const marxb200_columns *cols, uint64_t max_out, uint64_t *n_out)
+{
+   if ((c == nullptr) || (cols == nullptr)) return fail ("marxb200_download_columns: NULL argument");
+   if (c->stage_done < 0) { if (n_out) *n_out = 0; return 0; }
+   CUDA_OK (cudaSetDevice (c->device));
+   unsigned long long n = 0;
+   CUDA_OK (cudaMemcpyAsync (&n, c->d_counts + c->stage_done, sizeof (n), cudaMemcpyDeviceToHost, c->stream));
+   CUDA_OK (cudaStreamSynchronize (c->stream));
+   if (n > max_out) n = max_out;
+   if (n_out) *n_out = n;
+   if (n == 0) return 0;
+   const PhotonSoA &b = c->buf[c->cur];
+#define COL(dst, src, T) if (cols->dst) CUDA_OK (cudaMemcpyAsync (cols->dst, b.src, (size_t) n * sizeof (T), cudaMemcpyDeviceToHost, c->stream))
+   COL (energy, energy, double); COL (time, time, double);
+   COL (xpos, x0, double); COL (ypos, x1, double); COL (zpos, x2, double);
+   COL (xcos, p0, double); COL (ycos, p1, double); COL (zcos, p2, double);
+   COL (chipx, chipx, float); COL (chipy, chipy, float); COL (pi, pi, float);
+   COL (pha, pha, int16_t); COL (ccd, ccd, int8_t); COL (order, order, int8_t); COL (shell, shell, int8_t);
+   COL (ray, ray, uint64_t);
+#undef COL
+   CUDA_OK (cudaStreamSynchronize (c->stream));
+   return 0;
+}
+
+extern "C" int marxb200_get_launch_count (marxb200_ctx *c, uint64_t *n)
+{
+   if ((c == nullptr) || (n == nullptr)) return fail ("NULL argument");
+   *n = c->launches;
+   return 0;
+}
+
+extern "C" int marxb200_load_calpack_impl (marxb200_ctx *ctx, const char *path, char *errbuf, size_t errlen);
+extern "C" int marxb200_load_calpack (marxb200_ctx *c, const char *path)
+{
+   if ((c == nullptr) || (path == nullptr)) return fail ("marxb200_load_calpack: NULL argument");
+   char buf[512]; buf[0] = 0;
+   if (-1 == marxb200_load_calpack_impl (c, path, buf, sizeof (buf))) return fail ("%s", buf);
+   return 0;
+}

@@ -1,0 +1,306 @@
+// mx_acis.cuh -- K3: ACIS chip-plane intersection, QE x OBF x contamination, FEF pulse height, streak.
+// Reference: marx/libsrc/acis-s.c:177-248 (_marx_acis_s_detect), :138-175 (_marx_acis_apply_qe_and_pha);
+// detector.c:56-168 (plane intersection), trans.c:40-90; aciscontam.c:93-187; acis_fef.c:380-579,
+// :910-1079 (find_fef, normalize_gaussians, mixture sampling, marx_apply_acis_rmf); acis-i.c:60-89 (streak).
+// Draw order on sub-stream MARXB200_STAGE_DETECTOR: QE U; FEF { component U; 1..100 G | tail 2 U / iter }
+// [+ 1 U per negative-amplitude rejection trial]; PI U; streak U (transfer window only).
+#pragma once
+#include "mx_common.cuh"
+#include "mx_tables.h"
+
+namespace mx {
+
+// rotate_vector / rotate_vector_inv, trans.c:40-64
+MX_HD Vec3 m3_mul_t (const double *m, const Vec3 &v)
+{
+   Vec3 b;
+   b.x = m[0] * v.x + m[3] * v.y + m[6] * v.z;
+   b.y = m[1] * v.x + m[4] * v.y + m[7] * v.z;
+   b.z = m[2] * v.x + m[5] * v.y + m[8] * v.z;
+   return b;
+}
+
+// intersect_with_detector_plane (must_hit = 1), detector.c:56-109
+MX_HD int chip_intersect (const AcisChipDev &g, const Vec3 &x0, const Vec3 &p, Vec3 &x, double &dx, double &dy)
+{
+   Vec3 normal = v_make (g.normal[0], g.normal[1], g.normal[2]);
+   double pdotn = v_dot (p, normal);
+   if (pdotn == 0) return -1;
+   Vec3 x_ll = v_make (g.x_ll[0], g.x_ll[1], g.x_ll[2]);
+   Vec3 r = v_diff (x0, x_ll);
+   r = v_ax1_bx2 (1.0, r, -1.0 * v_dot (r, normal) / pdotn, p);
+   double rx = v_dot (r, v_make (g.xhat[0], g.xhat[1], g.xhat[2]));
+   if ((rx < 0.0) || (rx >= g.xlen)) return 0;
+   double ry = v_dot (r, v_make (g.yhat[0], g.yhat[1], g.yhat[2]));
+   if ((ry < 0.0) || (ry >= g.ylen)) return 0;
+   x = v_sum (r, x_ll);
+   dx = rx; dy = ry;
+   return 1;
+}
+
+// compute_contamination, aciscontam.c:93-136, with the analytic f(x,y) of :141-187
+MX_HD double acis_contamination (const AcisChipDev &c, double en, double cx, double cy)
+{
+   if (c.contam_num_layers == 0) return 1.0;
+   float ef = (float) en;
+   double v = 0.0;
+   if (c.contam_fxy_mode != 0)
+     {
+        double fxy;
+        if (c.contam_fxy_mode == 1)
+          {
+             double ddx = cx - c.contam_x0, ddy = cy - c.contam_y0;
+             double r = (8.0 / 1024.0) * sqrt (ddx * ddx + ddy * ddy);
+             r /= 8.07;
+             fxy = 1.29 * r * r;
+          }
+        else
+          {
+             const double y_0 = 512.0;
+             if (cy <= 512.0) fxy = pow (fabs ((cy - y_0) / (64.0 - y_0)), 5.5);
+             else fxy = pow (fabs ((cy - y_0) / (964.0 - y_0)), 4.5);
+          }
+        for (uint32_t i = 0; i < c.contam_num_layers; i++)
+          {
+             double mu = interp_f (ef, c.contam_energies[i], c.contam_mus[i], c.contam_num_mu[i]);
+             v += mu * (c.contam_tau0[i] + c.contam_tau1[i] * fxy);
+          }
+     }
+   else
+     {
+        if ((cx < 0) || (cx >= 1024) || (cy < 0) || (cy >= 1024)) return 0.0;
+        cx /= c.contam_blocking;
+        cy /= c.contam_blocking;
+        uint32_t ofs = (1024 / c.contam_blocking) * (uint32_t) cy + (uint32_t) cx;
+        for (uint32_t i = 0; i < c.contam_num_layers; i++)
+          {
+             double mu = interp_f (ef, c.contam_energies[i], c.contam_mus[i], c.contam_num_mu[i]);
+             double fxy = c.contam_fxy[i][ofs];
+             v += mu * (c.contam_tau0[i] + c.contam_tau1[i] * fxy);
+          }
+     }
+   return exp (-v);
+}
+
+struct GaussParm { float amp, center, sigma, cum_area; int use_tail_dist; };   // acis_fef.c:87-96
+
+// normalize_gaussians, acis_fef.c:509-579.  gaussian_integral(0,+inf) and (-inf,0) share one erf:
+// erf((+-1e37 - x0)/sigma) is exactly +-1 for every representable table value.
+MX_HD int fef_normalize (GaussParm *g, uint32_t num)
+{
+   const double SQRT_2 = 1.4142135623730951, SQRT_2PI = 2.5066282746310002;
+   double total_pos_area = 0.0, total_neg_area = 0.0;
+   int flags = 0;
+   for (uint32_t k = 0; k < num; k++)
+     {
+        double area1 = 0.0, area2 = 0.0;
+        double sigma = g[k].sigma * SQRT_2;
+        if (sigma != 0.0)
+          {
+             double x0 = g[k].center;
+             double e0 = erf ((0 - x0) / sigma);
+             area1 = 0.5 * g[k].amp * (1.0 - e0) * (SQRT_2PI * g[k].sigma);
+             area2 = 0.5 * g[k].amp * (e0 - (-1.0)) * (SQRT_2PI * g[k].sigma);
+          }
+        g[k].use_tail_dist = 0;
+        if (area2 > area1)
+          {
+             double ratio = area1 / area2;
+             if (ratio < 0.1) g[k].use_tail_dist = 1;
+          }
+        if (area1 >= 0) total_pos_area += area1;
+        else total_neg_area -= area1;
+        g[k].cum_area = (float) total_pos_area;
+     }
+   if (total_pos_area <= total_neg_area) flags |= 4;      // HAS_TOTAL_NEG_AREA
+   if (total_neg_area != 0.0) flags |= 1;                 // HAS_NEG_AMP_GAUSSIANS
+   if (total_pos_area > 0)
+     for (uint32_t k = 0; k < num; k++)
+       g[k].cum_area = (float) (g[k].cum_area / total_pos_area);
+   return flags;
+}
+
+// compute_pha_with_pos_amps, acis_fef.c:408-468.  The reference loops until a value is found; the cap
+// only bounds pathological tables (it is never reached with a valid FEF).
+MX_HD int fef_pha_pos (const GaussParm *g, uint32_t num, double &phap, Rng &rng)
+{
+   for (int guard = 0; guard < 4096; guard++)
+     {
+        double r = rng.uniform ();
+        for (uint32_t k = 0; k < num; k++)
+          {
+             double pha;
+             if (g[k].cum_area <= r) continue;
+             if (g[k].use_tail_dist == 0)
+               {
+                  unsigned int count = 0;
+                  do
+                    {
+                       pha = g[k].center + g[k].sigma * rng.gaussian ();
+                       count++;
+                    }
+                  while ((pha < 0) && (count < 100));
+               }
+             else
+               {
+                  // truncated-tail sampler adapted from GSL (acis_fef.c:440-456)
+                  double u, v, x;
+                  double s = (0 - g[k].center) / g[k].sigma;      // float arithmetic, as in the reference
+                  do
+                    {
+                       u = rng.uniform ();
+                       do v = rng.uniform (); while (v == 0.0);
+                       x = sqrt (s * s - 2 * log (v));
+                    }
+                  while (x * u > s);
+                  pha = g[k].center + x * g[k].sigma;
+               }
+             if (pha < 0) break;          // "Failed to find a pha value": draw a new r
+             phap = pha;
+             return 0;
+          }
+     }
+   return -1;
+}
+
+// compute_pha_with_neg_amps, acis_fef.c:471-503
+MX_HD int fef_pha_neg (const GaussParm *g, uint32_t num, double &phap, Rng &rng)
+{
+   int count = 0;
+   while (count < 100)
+     {
+        double pha;
+        if (-1 == fef_pha_pos (g, num, pha, rng)) return -1;
+        double pos_sum = 0.0, sum = 0.0;
+        for (uint32_t k = 0; k < num; k++)
+          {
+             double sigma = g[k].sigma, dsum = 0.0;
+             if (sigma != 0.0)
+               {
+                  double xx = (pha - g[k].center) / sigma;
+                  dsum = g[k].amp * exp (-0.5 * xx * xx);
+               }
+             sum += dsum;
+             if (dsum > 0) pos_sum += dsum;
+          }
+        if (rng.uniform () * pos_sum < sum) { phap = pha; return 0; }
+        count++;
+     }
+   return -1;
+}
+
+// marx_apply_acis_rmf, acis_fef.c:967-1079 (+ find_fef :910-965).  x, y are the float chip pixels.
+MX_HD int acis_apply_fef (const AcisDev &A, const AcisChipDev &chip, float x, float y, double energy,
+                          float &pi, int16_t &pha_out, Rng &rng)
+{
+   if ((x < 0) || (x >= 1024) || (y < 0) || (y >= 1024)) return -1;    // DetExtendFlag=no
+   uint32_t i = (uint32_t) (x / 32), j = (uint32_t) (y / 32);
+   if ((i >= 32) || (j >= 32)) return -1;
+   int fi = chip.fef_map[i * 32 + j];
+   if (fi < 0) return -1;
+   const FefDev &f = A.fefs[fi];
+   uint32_t ng = f.num_gaussians, ne = f.num_energies;
+   if (ng > (uint32_t) kMaxGauss) return -1;
+
+   i = bsearch_f ((float) energy, f.energies, ne);
+   if (i == 0) i++;
+   if (i == ne) i--;
+   double t = (energy - f.energies[i - 1]) / (f.energies[i] - f.energies[i - 1]);
+   const float *g0 = f.gauss + (size_t) (i - 1) * ng * 3;
+   const float *g1 = g0 + (size_t) ng * 3;
+   GaussParm G[kMaxGauss];
+   for (uint32_t k = 0; k < ng; k++)
+     {
+        float a0 = g0[3 * k], c0 = g0[3 * k + 1], s0 = g0[3 * k + 2];
+        float a1 = g1[3 * k], c1 = g1[3 * k + 1], s1 = g1[3 * k + 2];
+        G[k].center = (float) (c0 + t * (c1 - c0));
+        double v = s0 + t * (s1 - s0);
+        if (v <= 0.0) { G[k].sigma = 0.0f; G[k].amp = 0.0f; }
+        else
+          {
+             G[k].sigma = (float) v;
+             v = a0 + t * (a1 - a0);
+             if ((v < 0.0) && ((a1 > 0.0f) || (a0 > 0.0f))) v = 0.0;
+             G[k].amp = (float) v;
+          }
+     }
+   int flags = fef_normalize (G, ng);
+   if (flags & 4) return -1;
+   double pha;
+   int status = (flags == 0) ? fef_pha_pos (G, ng, pha, rng) : fef_pha_neg (G, ng, pha, rng);
+   if (status == -1) return -1;
+   int16_t ipha = (int16_t) pha;                   // truncation, acis_fef.c:1065
+   pha_out = ipha;
+   pha = ipha - rng.uniform ();
+   pi = interp_f ((float) pha, f.channels, f.energies, ne);
+   if (pi < 0) return -1;
+   return 0;
+}
+
+// _marx_acis_s_detect for one ray.  t_abs = pt->start_time + arrival_time.  Returns flags (0 alive,
+// possibly with PHOTON_ACIS_STREAKED set, which is not a "dead" bit).
+MX_HD uint32_t acis_detect (const AcisDev &A, double energy, double t_abs, Vec3 &x, Vec3 &p,
+                            int &ccd, float &chipx, float &chipy, int16_t &pha, float &pi, Rng &rng)
+{
+   const uint32_t UNDETECTED = 0x01, MISSED = 0x08, STREAKED = 0x200;
+   uint32_t flags = 0;
+   // _marx_transform_ray, trans.c:66-77 (detector dither offsets are zero for the INTERNAL model, dither.c:177-179)
+   x.x -= A.det_offset[0]; x.y -= A.det_offset[1]; x.z -= A.det_offset[2];
+   x = m3_mul (A.det_matrix, x);
+   p = m3_mul (A.det_matrix, p);
+
+   int hit = -1;
+   double dx = 0, dy = 0;
+   Vec3 xh = x;
+   for (int k = 0; k < A.num_chips; k++)
+     if (1 == chip_intersect (A.chip[k], x, p, xh, dx, dy)) { hit = k; break; }
+   if (hit < 0)
+     {
+        ccd = -1;
+        return MISSED;
+     }
+   const AcisChipDev &d = A.chip[hit];
+   x = xh;
+   ccd = d.id;
+   chipx = (float) (dx / d.x_pixel_size);
+   chipy = (float) (dy / d.y_pixel_size);
+
+   // _marx_acis_apply_qe_and_pha, acis-s.c:138-175
+   if (A.det_ideal == 0)
+     {
+        double r = rng.uniform ();
+        float ef = (float) energy;
+        double qe = (d.qe_num != 0) ? (double) interp_f (ef, d.qe_energies, d.qe, d.qe_num) : 1.0;
+        double qe_filter = (d.filter_num != 0) ? (double) interp_f (ef, d.filter_energies, d.filter_qe, d.filter_num) : 1.0;
+        double qe_contam = acis_contamination (d, energy, chipx, chipy);
+        if (r >= qe * qe_filter * qe_contam) return UNDETECTED;
+     }
+   if (-1 == acis_apply_fef (A, d, chipx, chipy, energy, pi, pha, rng))
+     {
+        pha = -1; pi = 0;
+        return UNDETECTED;
+     }
+   // _marx_acis_apply_streak, acis-i.c:60-89
+   if (A.frame_transfer_time > 0.0)
+     {
+        double t = fmod (t_abs, A.frame_time);
+        if (t > A.exposure_time)
+          {
+             chipy = (float) (1.0 + 1022.0 * rng.uniform ());
+             double xpixel = (chipx - d.xpixel_offset) * d.x_pixel_size;
+             double ypixel = (chipy - d.ypixel_offset) * d.y_pixel_size;
+             Vec3 ddx = v_ax1_bx2 (xpixel, v_make (d.xhat[0], d.xhat[1], d.xhat[2]), ypixel, v_make (d.yhat[0], d.yhat[1], d.yhat[2]));
+             x = v_sum (v_make (d.x_ll[0], d.x_ll[1], d.x_ll[2]), ddx);
+             p = v_diff (x, v_make (A.focal_length, 0, 0));
+             v_normalize (p);
+             flags |= STREAKED;
+          }
+     }
+   // _marx_transform_ray_reverse, trans.c:79-90
+   p = m3_mul_t (A.det_matrix, p);
+   x = m3_mul_t (A.det_matrix, x);
+   x.x += A.det_offset[0]; x.y += A.det_offset[1]; x.z += A.det_offset[2];
+   return flags;
+}
+
+}  // namespace mx

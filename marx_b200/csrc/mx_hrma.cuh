@@ -1,0 +1,360 @@
+// mx_hrma.cuh -- K1: HRMA Wolter-I shell pair, per ray.
+// Reference: marx/libsrc/hrma.c:1161-1341 (_marx_hrma_mirror_reflect), :984-1050 (project_photon_to_hrma),
+// :411-478 (compute_conic_intersection), :488-545 (reflect_from_conic), :1054-1093 (blur_normal),
+// :928-968 (intersects_struts); reflect.c:39-77 (marx_reflectivity, with jdmath/src/complex.c);
+// wfold.c:304-369 (scatter table lookup); jdmath/src/qroot.c:36-68.
+// Draw order on sub-stream MARXB200_STAGE_MIRROR: vignetting U; shell U; radius U;
+// azimuth U (retry on closed shutter); then per conic: blur U + G, reflect U, scatter U, sign U.
+//
+// Deliberate difference from the reference, invisible in its output: a ray that is blocked or absorbed
+// stops here with the flag of the FIRST cause (the reference keeps tracing strut-blocked rays, hrma.c:1214,
+// only to discard them; marx_write_photons never emits a flagged ray).
+#pragma once
+#include "mx_common.cuh"
+#include "mx_tables.h"
+
+namespace mx {
+
+struct Cplx { double r, i; };
+// JDMc_mul / JDMc_div / JDMc_abs / JDMc_sqrt, jdmath/src/complex.c:38-227
+MX_HD Cplx c_mul (Cplx a, Cplx b) { Cplx z; z.r = a.r * b.r - a.i * b.i; z.i = a.r * b.i + a.i * b.r; return z; }
+MX_HD Cplx c_div (Cplx z1, Cplx z2)
+{
+   Cplx z;
+   double r1 = z1.r, i1 = z1.i, r2 = z2.r, i2 = z2.i, ratio, denom;
+   if (fabs (r2) > fabs (i2))
+     {
+        ratio = i2 / r2;
+        denom = r2 + i2 * ratio;
+        z.r = (r1 + ratio * i1) / denom;
+        z.i = (i1 - r1 * ratio) / denom;
+     }
+   else
+     {
+        ratio = r2 / i2;
+        denom = r2 * ratio + i2;
+        z.r = (r1 * ratio + i1) / denom;
+        z.i = (i1 * ratio - r1) / denom;
+     }
+   return z;
+}
+MX_HD double c_abs (Cplx z)
+{
+   double fr = fabs (z.r), fi = fabs (z.i), ratio;
+   if (fr > fi) { ratio = z.i / z.r; return fr * sqrt (1.0 + ratio * ratio); }
+   if (fi == 0.0) return 0.0;
+   ratio = z.r / z.i;
+   return fi * sqrt (1.0 + ratio * ratio);
+}
+MX_HD Cplx c_sqrt (Cplx a)
+{
+   double r = c_abs (a);
+   if (r == 0.0) return a;
+   if (a.r >= 0.0)
+     {
+        a.r = sqrt (0.5 * (r + a.r));
+        a.i = 0.5 * a.i / a.r;
+     }
+   else
+     {
+        r = sqrt (0.5 * (r - a.r));
+        a.r = 0.5 * a.i / r;
+        a.i = r;
+        if (a.r < 0.0) { a.r = -a.r; a.i = -a.i; }
+     }
+   return a;
+}
+// JDMc_a_bz: a + b z ; JDMc_az1_bz2: a z1 + b z2 (complex.c:148-166)
+MX_HD Cplx c_a_bz (double a, double b, Cplx z1) { Cplx z; z.r = a + b * z1.r; z.i = b * z1.i; return z; }
+MX_HD Cplx c_az1_bz2 (double a, Cplx z1, double b, Cplx z2) { Cplx z; z.r = a * z1.r + b * z2.r; z.i = a * z1.i + b * z2.i; return z; }
+
+// marx_reflectivity, reflect.c:39-77: polarisation-averaged Fresnel reflectivity, cos_theta >= 0
+MX_HD double reflectivity (double cos_theta, double beta, double delta)
+{
+   Cplx n, root, nsqr, e_perp, e_par, num, den;
+   n.r = (1.0 - delta);
+   n.i = beta;
+   double sin_theta = sqrt (1.0 - cos_theta * cos_theta);
+   nsqr = c_mul (n, n);
+   root = c_sqrt (c_a_bz (-sin_theta * sin_theta, 1.0, nsqr));
+   num = c_a_bz (cos_theta, -1.0, root);
+   den = c_a_bz (cos_theta, 1.0, root);
+   e_perp = c_div (num, den);
+   num = c_az1_bz2 (cos_theta, nsqr, -1.0, root);
+   den = c_az1_bz2 (cos_theta, nsqr, 1.0, root);
+   e_par = c_div (num, den);
+   return 0.5 * (e_par.r * e_par.r + e_par.i * e_par.i + e_perp.r * e_perp.r + e_perp.i * e_perp.i);
+}
+
+// JDMquadratic_root, qroot.c:36-68 (a != 0 here); returns 1 real / 0 complex
+MX_HD int quadratic_root (double a, double b, double c, double &rplus, double &rminus)
+{
+   double bsqr = b * b;
+   double ac4 = a * c * 4;
+   double neg_b_over_2a = -b / (2.0 * a);
+   if (bsqr > ac4)
+     {
+        double factor = 1.0 + sqrt (1.0 - ac4 / bsqr);
+        rplus = -2.0 * c / (b * factor);
+        rminus = neg_b_over_2a * factor;
+        return 1;
+     }
+   if (bsqr == ac4) { rplus = rminus = neg_b_over_2a; return 1; }
+   return 0;
+}
+
+// compute_conic_intersection, hrma.c:411-478.  conic = {a, b, c, xmin, xmax}.  Line (not ray)
+// intersection; of two in-range roots the one with the larger x wins.
+MX_HD int conic_intersection (const double *conic, Vec3 &x0, const Vec3 &p, Vec3 &normal)
+{
+   double a = conic[0], b = conic[1], c = conic[2], xmin = conic[3], xmax = conic[4];
+   double t_plus, t_minus;
+   t_plus = -x0.x / p.x;
+   double x_y = x0.y + t_plus * p.y;
+   double x_z = x0.z + t_plus * p.z;
+   double alpha = a * p.x * p.x - 1.0;
+   double beta = b * p.x - 2.0 * (p.y * x_y + p.z * x_z);
+   double gamma = c - x_z * x_z - x_y * x_y;
+   if (alpha == 0.0)
+     {
+        if (beta == 0.0) return -1;
+        t_plus = t_minus = -gamma / beta;
+     }
+   else if (0 >= quadratic_root (alpha, beta, gamma, t_plus, t_minus))
+     return -1;
+   double x_plus = p.x * t_plus, x_minus = p.x * t_minus;
+   if ((x_plus >= xmin) && (x_plus < xmax))
+     {
+        if ((x_minus >= xmin) && (x_minus < xmax) && (x_minus > x_plus))
+          { x0.x = x_minus; x0.y = x_y + p.y * t_minus; x0.z = x_z + p.z * t_minus; }
+        else
+          { x0.x = x_plus; x0.y = x_y + p.y * t_plus; x0.z = x_z + p.z * t_plus; }
+     }
+   else if ((x_minus >= xmin) && (x_minus < xmax))
+     { x0.x = x_minus; x0.y = x_y + p.y * t_minus; x0.z = x_z + p.z * t_minus; }
+   else return -1;
+   normal.x = (a - 1) * x0.x + 0.5 * b;
+   normal.y = -x0.y;
+   normal.z = -x0.z;
+   v_normalize (normal);
+   return 0;
+}
+
+// blur_normal, hrma.c:1054-1093
+MX_HD void blur_normal (Vec3 &n, double blur, Rng &rng)
+{
+   double n_y = n.y, n_z = n.z;
+   double len = sqrt (n_y * n_y + n_z * n_z);
+   Vec3 perp = v_make (0.0, n_z / len, -n_y / len);
+   double phi = (2.0 * kPI) * rng.uniform ();
+   perp = v_rotate_unit (perp, n, phi);
+   phi = blur * (1.0 / 3600.0 * kPI / 180.0);
+   phi = phi * rng.gaussian ();
+   n = v_rotate_unit (n, perp, phi);
+}
+
+// interpolate_theta, wfold.c:304-332, for array k of table w
+MX_HD double wfold_theta (const WfoldDev &w, uint32_t k, double p)
+{
+   const double *h = w.hdr + 6 * k;
+   double p_min = h[1], delta_p = h[2], p_max = h[3];
+   if (p < p_min) return 0.0;
+   if (p > p_max) return pow (h[4] * (1.0 - p), h[5]);
+   const float *t = w.theta + w.theta_offset[k];
+   uint32_t nt = w.num_theta[k];
+   double delta_i = (p - p_min) / delta_p;
+   uint32_t i = (uint32_t) delta_i;
+   if (i + 1 >= nt) return (double) t[nt - 1];
+   delta_i -= (double) i;
+   return (1.0 - delta_i) * t[i] + delta_i * t[i + 1];
+}
+// marx_wfold_table_interp, wfold.c:334-369
+MX_HD double wfold_interp (const WfoldDev &w, double energy, double sin_alpha, double r)
+{
+   if (w.num_arrays == 0) return 0.0;
+   if (w.num_arrays == 1) return wfold_theta (w, 0, r);
+   double e_alpha = energy * sin_alpha;
+   // JDMbinary_search_d over the e_alpha column (stride 6 doubles)
+   uint32_t n = w.num_arrays, n0 = 0, n1 = n, n2, i;
+   while (n1 > n0 + 1)
+     {
+        n2 = (n0 + n1) / 2;
+        double v = w.hdr[6 * n2];
+        if (v >= e_alpha)
+          {
+             if (v == e_alpha) { n1 = n2; n0 = n2; break; }
+             n1 = n2;
+          }
+        else n0 = n2;
+     }
+   if (n0 == n1) i = n1;                       // equality short-circuit
+   else if (e_alpha >= w.hdr[6 * n0]) i = n1;
+   else i = n0;
+   if (i == n) i--;
+   if (i == 0) i++;
+   double theta_0 = wfold_theta (w, i - 1, r);
+   double theta_1 = wfold_theta (w, i, r);
+   double e0 = w.hdr[6 * (i - 1)], e1 = w.hdr[6 * i];
+   return theta_0 + (theta_1 - theta_0) * (e_alpha - e0) / (e1 - e0);
+}
+
+// reflect_from_conic, hrma.c:488-545.  returns 0 ok, -1 absorbed, -2 missed
+MX_HD int reflect_from_conic (const HrmaDev &H, const double *conic, const WfoldDev &wfold, double scat_factor,
+                              double blur, double energy, double beta, double delta, double corr,
+                              Vec3 &x, Vec3 &p, Rng &rng)
+{
+   Vec3 normal;
+   if (-1 == conic_intersection (conic, x, p, normal)) return -2;
+   if (H.use_blur) blur_normal (normal, blur, rng);
+   double p_dot_n = v_dot (p, normal);
+   if (H.is_ideal == 0)
+     {
+        double r = rng.uniform ();
+        double rfl = reflectivity (fabs (p_dot_n), beta, delta);
+        if (r >= rfl * corr) return -1;
+     }
+   p = v_ax1_bx2 (1.0, p, -2.0 * p_dot_n, normal);
+   if (H.use_wfold == 0) return 0;
+   double sin_grazing = -p_dot_n;
+   double r = rng.uniform ();
+   double delta_grazing = wfold_interp (wfold, energy, sin_grazing, r);
+   delta_grazing *= scat_factor;
+   if (delta_grazing > kPI / 4) return -1;
+   if (rng.uniform () < 0.5) delta_grazing = -delta_grazing;
+   p = v_rotate_unit (p, v_cross (p, normal), delta_grazing);
+   return 0;
+}
+
+// intersects_struts, hrma.c:928-968.  struts = {xpos0, half_width0, xpos1, half_width1}
+MX_HD int intersects_struts (const Vec3 &x0, const Vec3 &p0, double cap_position, const double *struts)
+{
+   const double theta = 30.0 * (kPI / 180.0);
+   const double cos_theta = cos (theta), sin_theta = sin (theta);
+   for (int s = 0; s < 2; s++)
+     {
+        double half_width = struts[2 * s + 1];
+        double x = x0.x, y = x0.y, z = x0.z;
+        double t = (struts[2 * s] + cap_position - x) / p0.x;
+        y += p0.y * t; z += p0.z * t;
+        for (int i = 0; i < 3; i++)
+          {
+             if (i != 0)
+               {
+                  double tmp = cos_theta * y - sin_theta * z;
+                  z = sin_theta * y + cos_theta * z;
+                  y = tmp;
+               }
+             if (((-half_width < y) && (y < half_width)) || ((-half_width < z) && (z < half_width)))
+               return 1;
+          }
+     }
+   return 0;
+}
+
+// hrma.c:908-926 (compile-time constants of the reference, not parameters)
+#define MX_PRECOL_STRUTS  {1492.060, 0.5 * 0.5 * 25.4, 942.266, 0.5 * 0.5 * 25.4}
+#define MX_CAP_STRUTS     {0.5 * 1.965 * 25.4, 0.5 * 0.75 * 25.4, -0.5 * 1.965 * 25.4, 0.5 * 0.75 * 25.4}
+#define MX_POSTCOL_STRUTS {-1050.353, 0.5 * 0.5 * 25.4, -1271.333, 0.5 * 0.5 * 25.4}
+
+// _marx_hrma_mirror_reflect for one ray.  In: energy, p (from the source), source distance.
+// Out: x, p at the exit of the mirror pair, shell index 0..3.  Returns the photon flags (0 = alive).
+// opt_* / corr_* may point to shared memory copies of H.opt_* / H.corr_*.
+MX_HD uint32_t hrma_reflect (const HrmaDev &H, const float *opt_e, const float *opt_b, const float *opt_d,
+                             const float *corr_e, const float *corr_f,
+                             double source_distance, double energy, Vec3 &x, Vec3 &p, uint32_t &shell_out, Rng &rng)
+{
+   const uint32_t VBLOCKED = 0x10, UNREFLECTED = 0x02;
+   // vignetting, hrma.c:1183-1192
+   if (H.is_ideal == 0)
+     {
+        if (rng.uniform () > H.vig) return VBLOCKED;
+     }
+   // project_photon_to_hrma, hrma.c:984-1050
+   uint32_t shell = 0;
+   bool found = false;
+   while (!found)
+     {
+        double r = rng.uniform ();
+        for (uint32_t i = 0; i < (uint32_t) kNumShells; i++)
+          if (r < H.shell[i].area_fraction) { shell = i; found = true; break; }
+     }
+   const HrmaShellDev &h = H.shell[shell];
+   shell_out = shell;
+   {
+      double radius = h.min_radius + (h.max_radius - h.min_radius) * rng.uniform ();
+      double theta;
+      uint32_t quad;
+      do
+        {
+           theta = rng.uniform ();
+           quad = (uint32_t) (4.0 * theta);
+        }
+      while (0 == (h.shutter_bitmap & (1u << quad)));
+      theta = (2.0 * kPI) * (theta - 1.0 / 8.0);
+      x.z = radius * cos (theta);
+      x.y = radius * sin (theta);
+      x.x = h.front_position;
+      x.z -= h.to_osac_p[2];
+      x.y -= h.to_osac_p[1];
+      if (source_distance > 0.0)
+        {
+           p = v_ax1_bx2 (1.0, x, source_distance, p);
+           v_normalize (p);
+        }
+   }
+   if (H.use_struts)
+     {
+        const double st[4] = MX_PRECOL_STRUTS;
+        if (intersects_struts (x, p, H.cap_position, st)) return VBLOCKED;
+     }
+   // to OSAC P frame, hrma.c:1222-1235
+   const Vec3 to_p = v_make (h.to_osac_p[0], h.to_osac_p[1], h.to_osac_p[2]);
+   const Vec3 to_h = v_make (h.to_osac_h[0], h.to_osac_h[1], h.to_osac_h[2]);
+   x = v_sum (x, to_p);
+   x = m3_mul (h.fwd_p, x);
+   p = m3_mul (h.fwd_p, p);
+
+   // optical constants and effective-area correction, hrma.c:1239-1262
+   double beta = 0.0, delta = 1.0, corr = 1.0;
+   if (H.num_opt != 0)
+     {
+        float ef = (float) energy;
+        beta = interp_f (ef, opt_e, opt_b, H.num_opt);
+        delta = interp_f (ef, opt_e, opt_d, H.num_opt);
+        if (H.use_scale)
+          {
+             corr = interp_f (ef, corr_e + h.corr_offset, corr_f + h.corr_offset, h.num_corr);
+             corr = sqrt (corr);
+          }
+     }
+
+   int status = reflect_from_conic (H, h.conic_p, h.wfold_p, h.p_scat, h.p_blur, energy, beta, delta, corr, x, p, rng);
+   if (status != 0) return UNREFLECTED;
+
+   p = m3_mul (h.bwd_p, p);
+   x = m3_mul (h.bwd_p, x);
+   x = v_diff (x, to_p);
+   if (H.use_struts)
+     {
+        const double st[4] = MX_CAP_STRUTS;
+        if (intersects_struts (x, p, H.cap_position, st)) return VBLOCKED;
+     }
+   x = v_sum (x, to_h);
+   p = m3_mul (h.fwd_h, p);
+   x = m3_mul (h.fwd_h, x);
+
+   status = reflect_from_conic (H, h.conic_h, h.wfold_h, h.h_scat, h.h_blur, energy, beta, delta, corr, x, p, rng);
+   if (status != 0) return UNREFLECTED;
+
+   p = m3_mul (h.bwd_h, p);
+   x = m3_mul (h.bwd_h, x);
+   x = v_diff (x, to_h);
+   if (H.use_struts)
+     {
+        const double st[4] = MX_POSTCOL_STRUTS;
+        if (intersects_struts (x, p, H.cap_position, st)) return VBLOCKED;
+     }
+   return 0;
+}
+
+}  // namespace mx

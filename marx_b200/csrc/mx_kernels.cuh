@@ -1,0 +1,89 @@
+// mx_kernels.cuh -- launch-side view of the stage kernels (kernels.cu) used by the C ABI (marxb200.cu).
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "mx_tables.h"
+
+namespace mx {
+
+constexpr int kTile = 256;               // rays per tile == threads per CTA
+constexpr int kSuperTile = 256;          // tiles per super-tile of the canonical arrival-time sum
+
+// Structure-of-arrays photon buffer in HBM (replaces Marx_Photon_Attr_Type[], marx.h:51-100).
+struct PhotonSoA
+{
+   double *energy;
+   double *x0, *x1, *x2;
+   double *p0, *p1, *p2;
+   double *time;                         // absolute: pt->start_time + arrival_time
+   uint64_t *ray;                        // global ray index (RNG counter; low 32 bits = tag)
+   uint32_t *flags;
+   float *dra, *ddec, *droll;            // Marx_Dither_Type ra/dec/roll (dy,dz,dtheta are 0 for INTERNAL)
+   float *chipx, *chipy, *pi;
+   int16_t *pha;
+   uint8_t *shell;
+   int8_t *order, *ccd;
+};
+
+// Blob staged into shared memory by K1 with one TMA bulk copy.
+struct K1Blob
+{
+   HrmaDev H;
+   uint32_t off_opt_e, off_opt_b, off_opt_d, off_corr_e, off_corr_f, total_bytes, pad0, pad1;
+};
+struct K2Blob
+{
+   GratingDev G;
+   uint32_t off_sectors[kNumShells];     // byte offsets of each shell's [6][num_sectors] doubles
+   uint32_t total_bytes, pad0, pad1, pad2;
+};
+struct K3Blob
+{
+   AcisDev A;
+   uint32_t total_bytes, pad0, pad1, pad2;
+};
+
+struct StageArgs
+{
+   PhotonSoA in, out;
+   const unsigned long long *n_in;       // device: number of input slots
+   unsigned long long *n_out;            // device: number of output photons (compact) / == n_in (in place)
+   unsigned long long *ticket;           // device: tile ticket counter (zeroed before launch)
+   unsigned long long *tile_status;      // device: decoupled look-back words (zeroed before launch)
+   uint64_t seed;
+   int compact;                          // 1: order-preserving compaction into `out`; 0: in place, dead rays kept
+   double source_distance;
+   const void *blob;                     // K1Blob / K2Blob / K3Blob in global memory
+   uint32_t blob_bytes;
+};
+
+struct SourceArgs
+{
+   PhotonSoA out;
+   uint64_t first_ray, n;
+   uint64_t seed;
+   SourceDev S;
+   DitherDev D;
+   double time_base;                     // absolute time of the batch start
+   double *tile_sums;                    // [n_tiles]
+   double *tile_base;                    // [n_tiles]
+   double *supertile_sums;               // [n_supertiles]
+   double *total_time;                   // device scalar: absolute time after the last ray
+   unsigned long long *n_out;            // device: count[0] = n
+};
+
+void launch_time_sums (const SourceArgs &a, cudaStream_t s);
+void launch_time_scan (const SourceArgs &a, cudaStream_t s);
+void launch_source (const SourceArgs &a, cudaStream_t s);
+void launch_hrma (const StageArgs &a, int grid, cudaStream_t s);
+void launch_grating (const StageArgs &a, int grid, cudaStream_t s);
+void launch_acis (const StageArgs &a, int grid, cudaStream_t s);
+int stage_grid_size (int stage, int num_sms, uint32_t blob_bytes);
+
+// host boundary helpers (AoS <-> SoA); `aos` is a device buffer of 136-byte records
+void launch_soa_to_aos (const PhotonSoA &in, const unsigned long long *n, uint64_t max_n, void *aos, double start_time,
+                        cudaStream_t s);
+void launch_aos_to_soa (const void *aos, const uint64_t *ray_ids, uint64_t n, const PhotonSoA &out, double start_time,
+                        cudaStream_t s);
+
+}  // namespace mx

@@ -1,0 +1,65 @@
+// mx_source.cuh -- K0: source draw, Poisson arrival increment, aspect dither (per ray).
+// Reference: marx/libsrc/source.c:268-384, s-point.c:59-83, spectrum.c:138-147,184-189, prob.c:46-58,
+// dither.c:167-182 (get_internal_dither), :551-581 (apply_dither), :609-628 (dither_ray).
+// Draw order on sub-stream MARXB200_STAGE_SOURCE: energy U; [direction draws];
+// time E; dither 2 G.
+#pragma once
+#include "mx_common.cuh"
+#include "mx_tables.h"
+
+namespace mx {
+
+// energy + direction.  POINT source: direction is the source vector (s-point.c:76).
+MX_HD void source_draw (const SourceDev &s, Rng &rng, double &energy, Vec3 &p)
+{
+   if (s.spectrum_type == 2)      // MARX_FILE_SPECTRUM: inverse CDF (prob.c:55-56)
+     {
+        double r = rng.uniform ();
+        energy = interp_d (r, s.spec_cum_flux, s.spec_energies, s.spec_num);
+     }
+   else                           // MARX_FLAT_SPECTRUM (spectrum.c:140-145)
+     {
+        double emin = s.emin;
+        double de = s.emax - emin;
+        energy = emin + de * rng.uniform ();
+     }
+   p = v_make (s.p[0], s.p[1], s.p[2]);
+}
+
+// arrival-time increment: mt * Exp(1)  (source.c:326)
+MX_HD double source_time_increment (const SourceDev &s, Rng &rng)
+{
+   return s.mean_time * rng.expn ();
+}
+
+// apply_dither, dither.c:551-581
+MX_HD Vec3 apply_dither (double ra, double dec, double roll, Vec3 p)
+{
+   p = v_rotate_unit (p, v_make (1, 0, 0), -roll);
+   double cos_ra = cos (ra), sin_ra = sin (ra);
+   double cos_dec = cos (dec), sin_dec = sin (dec);
+   double cos_theta = cos_dec * cos_ra;
+   Vec3 n = v_make (0, sin_dec, -cos_dec * sin_ra);
+   double sin_theta = v_length (n);
+   if (sin_theta <= 1e-20) return p;
+   n.x /= sin_theta; n.y /= sin_theta; n.z /= sin_theta;
+   return v_rotate_unit1 (p, n, cos_theta, sin_theta);
+}
+
+// dither_ray + get_internal_dither.  t is the absolute time (pt->start_time + arrival_time).
+// The three angles are stored through float fields before use (dither.c:173-175); that rounding is
+// part of the result.
+MX_HD void dither_ray (const DitherDev &d, Rng &rng, double t, Vec3 &p, float &f_ra, float &f_dec, float &f_roll)
+{
+   if (d.mode == 0) { f_ra = f_dec = f_roll = 0.0f; return; }
+   t = (2.0 * kPI) * t;
+   f_ra = (float) (d.ra_amp * sin (t / d.ra_period + d.ra_phase));
+   f_dec = (float) (d.dec_amp * sin (t / d.dec_period + d.dec_phase));
+   f_roll = (float) (d.nominal_roll + d.roll_amp * sin (t / d.roll_period + d.roll_phase));
+   double ra = f_ra, dec = f_dec, roll = f_roll;
+   double delta_ra = d.aspect_blur * rng.gaussian ();
+   double delta_dec = d.aspect_blur * rng.gaussian ();
+   p = apply_dither (ra + delta_ra, dec + delta_dec, roll, p);
+}
+
+}  // namespace mx

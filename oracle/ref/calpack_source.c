@@ -1,0 +1,39 @@
+/* Serialises source / spectrum / dither state (marx/libsrc/dither.c statics + public Marx_Source_Type).
+ * oracle/_ref build only. */
+#include <dither.c>
+#include "calpack_io.h"
+
+int calpack_dump_dither (mxcp_writer *w)
+{
+   double v[12];
+   v[0] = _Marx_Dither_Mode;
+   v[1] = Ra_Amp; v[2] = Dec_Amp; v[3] = Roll_Amp;
+   v[4] = Ra_Period; v[5] = Dec_Period; v[6] = Roll_Period;
+   v[7] = Ra_Phase; v[8] = Dec_Phase; v[9] = Roll_Phase;
+   v[10] = Nominal_Roll; v[11] = Aspect_Blur;
+   if (Get_Dither_Function == get_zeroamp_internal_dither) v[1] = v[2] = v[3] = 0.0;
+   return CP_F64 (w, "dither.params", v, 12);
+}
+
+int calpack_dump_source (mxcp_writer *w, void *marx_source)
+{
+   Marx_Source_Type *st = (Marx_Source_Type *) marx_source;
+   double v[13];
+   v[0] = 0;  /* POINT; other source types are not packed yet */
+   v[1] = st->spectrum.type;
+   v[2] = st->p.x; v[3] = st->p.y; v[4] = st->p.z;
+   v[5] = st->p_normal.x; v[6] = st->p_normal.y; v[7] = st->p_normal.z;
+   v[8] = st->distance;
+   v[9] = v[10] = 0.0;
+   if (st->spectrum.type == MARX_FLAT_SPECTRUM)
+     { v[9] = st->spectrum.s.flat.emin; v[10] = st->spectrum.s.flat.emax; }
+   v[11] = st->spectrum.total_flux;
+   v[12] = Marx_Mirror_Geometric_Area;
+   CP_F64 (w, "source.params", v, 13);
+   if (st->spectrum.type == MARX_FILE_SPECTRUM)
+     {
+	CP_F64 (w, "source.spec_energies", st->spectrum.s.file.energies, st->spectrum.s.file.num);
+	CP_F64 (w, "source.spec_cum_flux", st->spectrum.s.file.cum_flux, st->spectrum.s.file.num);
+     }
+   return 0;
+}
