@@ -21,6 +21,16 @@ def rel(a, b):
     return np.where(s > 0, d / np.where(s > 0, s, 1), 0.0)
 
 
+def vrel(a, b):
+    """per-photon relative error of a 3-vector: max|a-b| / max|b| (component-wise ratios are meaningless
+    for components that cancel to ~0, e.g. x on the x=0 Rowland plane or on the chip plane)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    s = np.abs(b).max(axis=-1)
+    d = np.abs(a - b).max(axis=-1)
+    return np.where(s > 0, d / np.where(s > 0, s, 1), d)
+
+
 def compare_stage(mine, ref, stage, check_time_abs=None):
     """mine/ref: PHOTON_DTYPE arrays of the same rays after `stage` (0..3).  Returns a dict of findings."""
     out = {}
@@ -37,7 +47,7 @@ def compare_stage(mine, ref, stage, check_time_abs=None):
     out["energy_max_rel"] = float(rel(a["energy"], b["energy"]).max()) if len(a) else 0.0
     out["p_max_abs"] = float(np.abs(a["p"] - b["p"]).max()) if len(a) else 0.0
     if stage >= 1:
-        out["x_max_rel"] = float(rel(a["x"], b["x"]).max()) if len(a) else 0.0
+        out["x_max_rel"] = float(vrel(a["x"], b["x"]).max()) if len(a) else 0.0
         out["shell_mismatch"] = int((a["mirror_shell"] != b["mirror_shell"]).sum())
     if stage >= 2:
         out["order_mismatch"] = int((a["order"] != b["order"]).sum())
