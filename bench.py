@@ -1,0 +1,349 @@
+#!/usr/bin/env python3
+"""bench.py -- rays/sec of the MARX ray-trace hot path (HRMA -> HETG -> ACIS-S with dither).
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA path (one process per GPU)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU implementation, all host cores
+
+A "step" is one batch of 2**24 generated rays per GPU of BASELINE.json configs[1]
+(point source, flat 0.3-8 keV, HETG + ACIS-S, INTERNAL dither): marx_create_photons ->
+marx_mirror_reflect -> marx_grating_diffract -> marx_detect, i.e. the body of marx.c:545-608 without the
+file output.  The photon SoA of one batch is ~1.7 GB, far larger than the 126 MB L2, so no L2 flush is
+needed between steps (stated in config.l2).  ACIS calibration is synthetic (the FEF/contamination blobs
+are absent from the reference checkout); both arms load the same files.
+
+Prints ONE JSON line (rank 0).  `value` = generated rays/s with everything resident in HBM;
+`e2e` = the same through the C ABI with the event list copied to pinned host memory every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "rays/sec HRMA+HETG+ACIS-S"
+UNIT = "rays/s"
+WORKLOAD = ("BASELINE.json configs[1]: point source, flat 0.3-8 keV, HETG+ACIS-S, INTERNAL dither; "
+            "one step = one batch of 2^24 generated rays per GPU (synthetic ACIS FEF/contamination)")
+REF_ARGS = ["ExposureTime=0", "Verbose=0", "SourceFlux=0.003", "TStart=2023.5", "SourceType=POINT",
+            "SpectrumType=FLAT", "MinEnergy=0.3", "MaxEnergy=8.0", "GratingType=HETG", "DetectorType=ACIS-S",
+            "DitherModel=INTERNAL", "dNumRays=1000000"]
+
+# algorithmic bytes per input ray of each staged kernel (SURVEY.md 8d / DESIGN.md "roofline")
+BYTES_PER_RAY = {"K0": 56.0, "K1": 89.0, "K2": 114.0, "K3": 147.0}
+# FP64 flop-equivalents per input ray (SURVEY.md 8d contract figures)
+FLOPEQ_PER_RAY = {"K0": 530.0, "K1": 860.0, "K2": 700.0, "K3": 850.0}
+
+
+# ------------------------------------------------------------------------------------------------
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def ref_paths():
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    return ref, os.path.join(ref, "marx_trace_bench"), os.path.join(ref, "par", "marx.par"), os.path.join(ref, "data")
+
+
+def run_reference_sample(nrays_per_proc, nprocs, seed0=1):
+    """nprocs concurrent single-threaded reference processes (the reference's own multi-core mode:
+    N independent `marx` runs); returns (total rays, wall seconds of the trace loops)."""
+    ref, exe, par, data = ref_paths()
+    if not os.path.exists(exe):
+        raise RuntimeError("oracle/_ref/marx_trace_bench not built (run __graft_entry__.build() where /root/reference exists)")
+    env = dict(os.environ, MARX_DATA_DIR=data)
+    t0 = time.time()
+    procs = [subprocess.Popen([exe, str(nrays_per_proc), "@@" + par, "RandomSeed=%d" % (seed0 + k)] + REF_ARGS,
+                              stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, env=env) for k in range(nprocs)]
+    outs = [p.communicate()[0] for p in procs]
+    wall = time.time() - t0
+    rays, secs = 0, 0.0
+    for p, o in zip(procs, outs):
+        if p.returncode != 0:
+            raise RuntimeError("reference process failed")
+        j = json.loads(o.decode().strip().splitlines()[-1])
+        rays += j["rays"]
+        secs = max(secs, j["seconds"])
+    return rays, secs, wall
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], None, [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2]); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "samples": len(sm),
+                "power_w_max": max(power) if power else None, "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    per_proc = args.ref_rays_per_proc
+    # warm-up (page cache, CPU clocks), then K bounded samples on all host cores
+    for _ in range(args.warmup):
+        run_reference_sample(max(per_proc // 10, 20000), cores)
+    rays_tot, t_tot = 0, 0.0
+    for s in range(args.steps):
+        rays, secs, wall = run_reference_sample(per_proc, cores, seed0=1 + s * cores)
+        rays_tot += rays
+        t_tot += secs
+    value = rays_tot / t_tot
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": "%d rays per process x %d processes per step" % (per_proc, cores)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                         "sample": "%d steps x %d processes x %d rays, stock MARX stages + stock RNG, trace loop only "
+                                   "(oracle/_ref/marx_trace_bench, gcc -O2)" % (args.steps, cores, per_proc)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def cuda_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import marx_b200
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = args.rays_per_step
+    assert n % 65536 == 0, "rays per step must be a multiple of 65536 (super-tile aligned time sums)"
+    stream = torch.cuda.Stream(device=dev)
+    m = marx_b200.MarxB200(args.calpack, device=local_rank, seed=args.seed, max_photons=n, stream=stream.cuda_stream)
+
+    # pinned host buffers for the e2e leg: event columns of marxio.c:292-322 (E T x y z cosines chip pha pi order ...)
+    col_names = ("energy", "time", "xpos", "ypos", "zpos", "xcos", "ycos", "zcos", "chipx", "chipy", "pi", "pha",
+                 "ccd", "order", "shell", "ray")
+    cap = n // 8
+    from marx_b200.api import _COLUMN_DTYPES
+    pinned = {k: torch.empty(cap, dtype=getattr(torch, {"<f8": "float64", "<f4": "float32", "<i2": "int16", "i1": "int8",
+                                                            "<u8": "int64"}[_COLUMN_DTYPES[k]]), pin_memory=True)
+              for k in col_names}
+    pinned_np = {k: v.numpy().view(_COLUMN_DTYPES[k]) for k, v in pinned.items()}
+    bytes_per_event = sum(np.dtype(_COLUMN_DTYPES[k]).itemsize for k in col_names)
+
+    def time_base_for(step):
+        """multi-GPU: canonical time base of this rank's block = running end time + the super-tile sums of the
+        lower ranks' blocks added sequentially (all-gather over NCCL); single GPU: continue on device."""
+        first = (step * world + rank) * n
+        if world == 1:
+            return first, -1.0
+        from marx_b200.dist import exchange_time_base
+        base, time_base_for.running = exchange_time_base(m.time_sums(first, n), rank, world, time_base_for.running, device=dev)
+        return first, base
+    time_base_for.running = 0.0
+
+    stage_events = []
+
+    def one_step(step, record=False, e2e=False):
+        first, base = time_base_for(step)
+        with torch.cuda.stream(stream):
+            if record:
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+                ev[0].record(stream)
+                m.create_photons(first, n, base); ev[1].record(stream)
+                m.mirror_reflect(); ev[2].record(stream)
+                m.grating_diffract(); ev[3].record(stream)
+                m.detect(); ev[4].record(stream)
+                stage_events.append(ev)
+            else:
+                m.create_photons(first, n, base)
+                m.mirror_reflect(); m.grating_diffract(); m.detect()
+            if e2e:
+                cols = m.download_columns(col_names, out=pinned_np)      # D2H into pinned memory; synchronises
+                return len(cols["energy"])
+        return None
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def timed(K, e2e):
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        launches0 = m.launch_count()
+        t0.record(stream)
+        n_events = 0
+        for s in range(K):
+            r = one_step(timed.step, record=not e2e, e2e=e2e)
+            timed.step += 1
+            if r is not None:
+                n_events += r
+        t1.record(stream)
+        barrier()
+        ms = t0.elapsed_time(t1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, m.launch_count() - launches0, n_events
+    timed.step = 0
+
+    for _ in range(max(args.warmup, 3)):
+        one_step(timed.step); timed.step += 1
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, launches, _ = timed(args.steps, e2e=False)
+    clocks = sampler.stop() if rank == 0 else None
+    counts = m.stage_counts()
+    # per-kernel durations from the SAME timed steps (CUDA events on the launching stream)
+    stage_ms = [sum(ev[k].elapsed_time(ev[k + 1]) for ev in stage_events) / len(stage_events) for k in range(4)]
+    # e2e leg
+    for _ in range(2):
+        one_step(timed.step, e2e=True); timed.step += 1
+    ms_e2e, _, n_events = timed(args.steps, e2e=True)
+
+    total_rays = float(n) * world * args.steps
+    value = total_rays / (ms * 1e-3)
+    e2e_value = total_rays / (ms_e2e * 1e-3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    k1_ms = stage_ms[1]
+    achieved = BYTES_PER_RAY["K1"] * n / (k1_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    fp64_peak = float(peaks.get("fp64_tflops", 37.0))
+    frac_in = [1.0, 1.0, counts[1] / max(counts[0], 1), counts[2] / max(counts[0], 1)]
+    kernels = {}
+    for k, name in enumerate(["K0", "K1", "K2", "K3"]):
+        n_in = n * frac_in[k]
+        kernels[name] = {"ms": stage_ms[k], "share": stage_ms[k] / sum(stage_ms), "input_rays": n_in,
+                         "hbm_gbs": BYTES_PER_RAY[name] * n_in / (stage_ms[k] * 1e-3) / 1e9 if stage_ms[k] > 0 else None,
+                         "fp64_tflopeq": FLOPEQ_PER_RAY[name] * n_in / (stage_ms[k] * 1e-3) / 1e12 if stage_ms[k] > 0 else None}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": n, "calpack": args.calpack, "seed": args.seed,
+                   "l2": "inputs (1.7 GB photon SoA per batch) exceed the 126 MB L2; no flush needed",
+                   "stage_counts_last_step_rank0": counts},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 24,
+                "d2h_bytes_per_step": int(bytes_per_event * n_events / args.steps) + 8,
+                "note": "C ABI trace + marxb200_download_columns into pinned host memory each step; the only per-step "
+                        "host input of this path is the batch descriptor (first ray, count, time base)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "k1_hrma", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": BYTES_PER_RAY["K1"] * n, "avg_launch_ms": k1_ms,
+                     "fp64": {"achieved_tflopeq": FLOPEQ_PER_RAY["K1"] * n / (k1_ms * 1e-3) / 1e12, "peak_tflops": fp64_peak,
+                              "frac": FLOPEQ_PER_RAY["K1"] * n / (k1_ms * 1e-3) / 1e12 / fp64_peak,
+                              "peak_source": "measured" if "fp64_tflops" in peaks else "datasheet (not in MEASURED_PEAKS.json)"},
+                     "kernels": kernels},
+    }
+    # CPU baseline beside it (N=1 only): the compiled reference on ONE core, bounded sample
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            rays, secs, _ = run_reference_sample(args.cpu_baseline_rays, 1)
+            line["cpu_baseline"] = {"value": rays / secs, "unit": UNIT, "cores": 1, "kind": "reference",
+                                    "sample": "%d rays, stock MARX 5.5.3 stages + stock RNG, trace loop only "
+                                              "(oracle/_ref/marx_trace_bench, gcc -O2), %.1f s" % (rays, secs)}
+        except Exception as e:  # noqa: BLE001
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "unavailable: %s" % e}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--rays-per-step", type=int, default=1 << 24)
+    ap.add_argument("--calpack", default="c2_hetg_acis_s")
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--cpu-baseline-rays", type=int, default=6000000)
+    ap.add_argument("--ref-rays-per-proc", type=int, default=1000000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        cuda_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -232,14 +232,15 @@ __global__ void __launch_bounds__ (kTile) k0_time_scan (const __grid_constant__ 
    __syncthreads ();
    if (threadIdx.x == 0)
      {
-        double acc = a.time_base;
+        double acc = a.use_dev_base ? a.dev_times[1] : a.time_base;
+        a.dev_times[0] = acc;
         for (uint64_t s = 0; s < n_super; s++)
           {
              double v = a.supertile_sums[s];
              a.tile_base[s * kSuperTile] = acc;          // base of the first tile of the super-tile
              acc += v;
           }
-        *a.total_time = acc;
+        a.dev_times[1] = acc;
      }
    __syncthreads ();
    for (uint64_t s = threadIdx.x; s < n_super; s += blockDim.x)
@@ -498,9 +499,10 @@ __global__ void __launch_bounds__ (kTile) k3_acis (const __grid_constant__ Stage
 // host boundary: SoA <-> 136-byte AoS records (marxb200_photon_attr == Marx_Photon_Attr_Type)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__ (256) soa_to_aos (PhotonSoA in, const unsigned long long *n_ptr, uint64_t max_n,
-                                                    marxb200_photon_attr *aos, double start_time)
+                                                    marxb200_photon_attr *aos, const double *dev_start_time)
 {
    const uint64_t n = min ((uint64_t) *n_ptr, max_n);
+   const double start_time = *dev_start_time;
    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x)
      {
         marxb200_photon_attr r;
@@ -596,12 +598,12 @@ void launch_hrma (const StageArgs &a, int grid, cudaStream_t s) { k1_hrma<<<grid
 void launch_grating (const StageArgs &a, int grid, cudaStream_t s) { k2_grating<<<grid, kTile, a.blob_bytes, s>>> (a); }
 void launch_acis (const StageArgs &a, int grid, cudaStream_t s) { k3_acis<<<grid, kTile, a.blob_bytes, s>>> (a); }
 
-void launch_soa_to_aos (const PhotonSoA &in, const unsigned long long *n, uint64_t max_n, void *aos, double start_time,
-                        cudaStream_t s)
+void launch_soa_to_aos (const PhotonSoA &in, const unsigned long long *n, uint64_t max_n, void *aos,
+                        const double *dev_start_time, cudaStream_t s)
 {
    if (max_n == 0) return;
    unsigned int grid = (unsigned int) min ((uint64_t) 148 * 8, (max_n + 255) / 256);
-   soa_to_aos<<<grid, 256, 0, s>>> (in, n, max_n, (marxb200_photon_attr *) aos, start_time);
+   soa_to_aos<<<grid, 256, 0, s>>> (in, n, max_n, (marxb200_photon_attr *) aos, dev_start_time);
 }
 void launch_aos_to_soa (const void *aos, const uint64_t *ray_ids, uint64_t n, const PhotonSoA &out, double start_time,
                         cudaStream_t s)

@@ -55,12 +55,9 @@ struct marxb200_ctx
    unsigned long long *d_counts = nullptr;      // [4]
    unsigned long long *d_ticket = nullptr;
    unsigned long long *d_tile_status = nullptr; // [capacity/kTile + 1]
-   double *d_tile_sums = nullptr, *d_tile_base = nullptr, *d_super_sums = nullptr, *d_total_time = nullptr;
+   double *d_tile_sums = nullptr, *d_tile_base = nullptr, *d_super_sums = nullptr, *d_times = nullptr;   // d_times: [batch start, running end]
    int stage_done = -1;                          // index into d_counts of the latest valid count
    uint64_t n_generated = 0;
-   double batch_start_time = 0.0;                // pt->start_time of the current batch
-   double running_time = 0.0;                    // absolute time after the last generated ray
-   bool running_time_dirty = false;
 
    // tables
    std::vector<void *> allocs;                   // every cudaMalloc'd table (freed in destroy)
@@ -145,9 +142,9 @@ extern "C" int marxb200_create (marxb200_ctx **ctxp, int device_ordinal, uint64_
    c->own_stream = true;
    CUDA_OK (cudaMalloc (&c->d_counts, 4 * sizeof (unsigned long long)));
    CUDA_OK (cudaMalloc (&c->d_ticket, sizeof (unsigned long long)));
-   CUDA_OK (cudaMalloc (&c->d_total_time, sizeof (double)));
+   CUDA_OK (cudaMalloc (&c->d_times, 2 * sizeof (double)));
    CUDA_OK (cudaMemset (c->d_counts, 0, 4 * sizeof (unsigned long long)));
-   CUDA_OK (cudaMemset (c->d_total_time, 0, sizeof (double)));
+   CUDA_OK (cudaMemset (c->d_times, 0, 2 * sizeof (double)));
    memset (&c->S, 0, sizeof (c->S));
    memset (&c->D, 0, sizeof (c->D));
    *ctxp = c;
@@ -161,7 +158,7 @@ extern "C" int marxb200_destroy (marxb200_ctx *c)
    cudaDeviceSynchronize ();
    for (void *p : c->allocs) cudaFree (p);
    for (int i = 0; i < 2; i++) if (c->slab[i]) cudaFree (c->slab[i]);
-   cudaFree (c->d_counts); cudaFree (c->d_ticket); cudaFree (c->d_total_time);
+   cudaFree (c->d_counts); cudaFree (c->d_ticket); cudaFree (c->d_times);
    if (c->d_tile_status) cudaFree (c->d_tile_status);
    if (c->d_tile_sums) cudaFree (c->d_tile_sums);
    if (c->d_tile_base) cudaFree (c->d_tile_base);
@@ -362,19 +359,11 @@ static void fill_source_args (marxb200_ctx *c, SourceArgs &a, uint64_t first_ray
    a.out = c->buf[0];
    a.first_ray = first_ray; a.n = n; a.seed = c->seed;
    a.S = c->S; a.D = c->D;
-   a.time_base = time_base;
+   a.time_base = (time_base >= 0.0) ? time_base : 0.0;
+   a.use_dev_base = (time_base >= 0.0) ? 0 : 1;
+   a.dev_times = c->d_times;
    a.tile_sums = c->d_tile_sums; a.tile_base = c->d_tile_base; a.supertile_sums = c->d_super_sums;
-   a.total_time = c->d_total_time;
    a.n_out = c->d_counts + 0;
-}
-
-static int sync_running_time (marxb200_ctx *c)
-{
-   if (!c->running_time_dirty) return 0;
-   CUDA_OK (cudaMemcpyAsync (&c->running_time, c->d_total_time, sizeof (double), cudaMemcpyDeviceToHost, c->stream));
-   CUDA_OK (cudaStreamSynchronize (c->stream));
-   c->running_time_dirty = false;
-   return 0;
 }
 
 extern "C" int marxb200_create_photons (marxb200_ctx *c, uint64_t first_ray, uint64_t n, double time_base_in)
@@ -384,24 +373,13 @@ extern "C" int marxb200_create_photons (marxb200_ctx *c, uint64_t first_ray, uin
    if (n > c->capacity) return fail ("marxb200_create_photons: n=%llu exceeds the allocated capacity %llu", (unsigned long long) n, (unsigned long long) c->capacity);
    CUDA_OK (cudaSetDevice (c->device));
    SourceArgs a;
-   if (time_base_in >= 0.0)
-     {
-        fill_source_args (c, a, first_ray, n, time_base_in);
-        c->batch_start_time = time_base_in;
-     }
-   else
-     {
-        // continue the running sum without a host round trip: the device scalar holds the end time
-        if (-1 == sync_running_time (c)) return -1;
-        fill_source_args (c, a, first_ray, n, c->running_time);
-        c->batch_start_time = c->running_time;
-     }
+   // time_base_in < 0: continue the running sum from the device scalar (no host round trip)
+   fill_source_args (c, a, first_ray, n, time_base_in);
    launch_time_sums (a, c->stream);
    launch_time_scan (a, c->stream);
    launch_source (a, c->stream);
    c->launches += 3;
    CUDA_OK (cudaGetLastError ());
-   c->running_time_dirty = true;
    c->cur = 0; c->stage_done = 0; c->n_generated = n;
    return 0;
 }
@@ -416,9 +394,13 @@ extern "C" int marxb200_time_sums (marxb200_ctx *c, uint64_t first_ray, uint64_t
    CUDA_OK (cudaSetDevice (c->device));
    SourceArgs a;
    fill_source_args (c, a, first_ray, n, 0.0);
+   double saved[2];
+   CUDA_OK (cudaMemcpyAsync (saved, c->d_times, sizeof (saved), cudaMemcpyDeviceToHost, c->stream));
    launch_time_sums (a, c->stream);
    launch_time_scan (a, c->stream);
    c->launches += 2;
+   CUDA_OK (cudaStreamSynchronize (c->stream));
+   CUDA_OK (cudaMemcpyAsync (c->d_times, saved, sizeof (saved), cudaMemcpyHostToDevice, c->stream));
    uint64_t n_tiles = (n + kTile - 1) / kTile, ns = (n_tiles + kSuperTile - 1) / kSuperTile;
    if (ns > max_sums) return fail ("marxb200_time_sums: need room for %llu sums", (unsigned long long) ns);
    CUDA_OK (cudaMemcpyAsync (sums_host, c->d_super_sums, ns * sizeof (double), cudaMemcpyDeviceToHost, c->stream));
@@ -522,10 +504,12 @@ extern "C" int marxb200_get_counts (marxb200_ctx *c, uint64_t *n_generated, uint
    if (c == nullptr) return fail ("NULL ctx");
    uint64_t cnt[4];
    if (-1 == marxb200_get_stage_counts (c, cnt)) return -1;
-   if (-1 == sync_running_time (c)) return -1;
+   double times[2];
+   CUDA_OK (cudaMemcpyAsync (times, c->d_times, sizeof (times), cudaMemcpyDeviceToHost, c->stream));
+   CUDA_OK (cudaStreamSynchronize (c->stream));
    if (n_generated) *n_generated = c->n_generated;
    if (n_live) *n_live = (c->stage_done >= 0) ? cnt[c->stage_done] : 0;
-   if (total_time) *total_time = c->running_time;
+   if (total_time) *total_time = times[1];
    return 0;
 }
 
@@ -541,7 +525,7 @@ static int download_impl (marxb200_ctx *c, marxb200_photon_attr *out, uint64_t m
    if (n_out) *n_out = n;
    if (n == 0) return 0;
    if (-1 == ensure_aos (c, n)) return -1;
-   launch_soa_to_aos (c->buf[c->cur], c->d_counts + c->stage_done, n, c->d_aos, c->batch_start_time, c->stream);
+   launch_soa_to_aos (c->buf[c->cur], c->d_counts + c->stage_done, n, c->d_aos, c->d_times, c->stream);
    c->launches += 1;
    CUDA_OK (cudaMemcpyAsync (out, c->d_aos, (size_t) n * sizeof (marxb200_photon_attr), cudaMemcpyDeviceToHost, c->stream));
    CUDA_OK (cudaStreamSynchronize (c->stream));
@@ -572,7 +556,7 @@ extern "C" int marxb200_upload (marxb200_ctx *c, const marxb200_photon_attr *in,
         CUDA_OK (cudaMemcpyAsync (d_ids, ray_ids, n * sizeof (uint64_t), cudaMemcpyHostToDevice, c->stream));
      }
    c->cur = 0;
-   c->batch_start_time = 0.0;
+   CUDA_OK (cudaMemsetAsync (c->d_times, 0, sizeof (double), c->stream));   // uploaded arrival times are absolute
    launch_aos_to_soa (c->d_aos, d_ids, n, c->buf[0], 0.0, c->stream);
    c->launches += 1;
    unsigned long long nn = n;

@@ -64,11 +64,12 @@ struct SourceArgs
    uint64_t seed;
    SourceDev S;
    DitherDev D;
-   double time_base;                     // absolute time of the batch start
+   double time_base;                     // absolute time of the batch start (used when use_dev_base == 0)
+   int use_dev_base;                     // 1: continue from dev_times[1] (end of the previous batch), no host round trip
+   double *dev_times;                    // device: [0] = start time of the current batch, [1] = running end time
    double *tile_sums;                    // [n_tiles]
    double *tile_base;                    // [n_tiles]
    double *supertile_sums;               // [n_supertiles]
-   double *total_time;                   // device scalar: absolute time after the last ray
    unsigned long long *n_out;            // device: count[0] = n
 };
 
@@ -81,8 +82,8 @@ void launch_acis (const StageArgs &a, int grid, cudaStream_t s);
 int stage_grid_size (int stage, int num_sms, uint32_t blob_bytes);
 
 // host boundary helpers (AoS <-> SoA); `aos` is a device buffer of 136-byte records
-void launch_soa_to_aos (const PhotonSoA &in, const unsigned long long *n, uint64_t max_n, void *aos, double start_time,
-                        cudaStream_t s);
+void launch_soa_to_aos (const PhotonSoA &in, const unsigned long long *n, uint64_t max_n, void *aos,
+                        const double *dev_start_time, cudaStream_t s);
 void launch_aos_to_soa (const void *aos, const uint64_t *ray_ids, uint64_t n, const PhotonSoA &out, double start_time,
                         cudaStream_t s);
 

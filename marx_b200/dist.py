@@ -1,0 +1,72 @@
+"""Multi-GPU plumbing (torch.distributed; NCCL over NVLink on the GPU box, gloo in the CPU tests).
+
+The path shards trivially: rank r traces the contiguous block of global ray indices
+[(step*G + r)*n, (step*G + r + 1)*n) with the same counter-based draw streams, so every event is
+identical for any GPU count.  Two small exchanges remain:
+
+* arrival times are a running sum over ALL rays (source.c:326): ranks all-gather the per-super-tile
+  sums of their block (n/65536 doubles) and add the lower ranks' sums sequentially -> `block_time_bases`;
+* the per-GPU event lists are merged on demand: blocks are contiguous in ray index and arrival time, so
+  the time-ordered merge the reference's marxcat performs (marx/src/marxcat.c:505-535) degenerates to a
+  concatenation in rank order -> `gather_event_columns`.
+"""
+import numpy as np
+
+
+def block_time_bases(sums_per_rank, running):
+    """sums_per_rank[r] = super-tile sums of rank r's block (canonical order).  Returns (bases, end):
+    bases[r] = absolute time at the start of rank r's block, end = time after the last block.  The
+    additions are strictly sequential over super-tiles, exactly what a single GPU tracing all blocks does."""
+    bases = []
+    acc = float(running)
+    for sums in sums_per_rank:
+        bases.append(acc)
+        for v in np.asarray(sums, dtype=np.float64):
+            acc = acc + float(v)
+    return bases, acc
+
+
+def exchange_time_base(time_sums, rank, world, running, device=None):
+    """all-gather the super-tile sums (tiny) and return (time base of this rank's block, new running time)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.as_tensor(np.asarray(time_sums, dtype=np.float64))
+    if device is not None:
+        t = t.to(device)
+    gathered = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(gathered, t)
+    sums = [g.cpu().numpy() for g in gathered]
+    bases, end = block_time_bases(sums, running)
+    return bases[rank], end
+
+
+def gather_event_columns(cols, rank, world, dst=0, device=None):
+    """cols: dict name -> 1-D numpy array (this rank's events, arrival order).  On `dst` returns the merged
+    dict (rank order == arrival-time order); elsewhere None.  Variable lengths are handled by an all-gather of
+    the counts followed by padded gathers."""
+    import torch
+    import torch.distributed as dist
+    names = sorted(cols)
+    n_local = len(cols[names[0]]) if names else 0
+    cnt = torch.tensor([n_local], dtype=torch.int64)
+    if device is not None:
+        cnt = cnt.to(device)
+    counts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(counts, cnt)
+    counts = [int(c.item()) for c in counts]
+    nmax = max(max(counts), 1)
+    out = {} if rank == dst else None
+    for name in names:
+        a = np.ascontiguousarray(cols[name])
+        raw = a.view(np.uint8).reshape(n_local, a.dtype.itemsize) if n_local else np.zeros((0, a.dtype.itemsize), np.uint8)
+        pad = np.zeros((nmax, a.dtype.itemsize), dtype=np.uint8)
+        pad[:n_local] = raw
+        t = torch.from_numpy(pad)
+        if device is not None:
+            t = t.to(device)
+        bufs = [torch.empty_like(t) for _ in range(world)] if rank == dst else None
+        dist.gather(t, bufs, dst=dst)
+        if rank == dst:
+            parts = [bufs[r][:counts[r]].cpu().numpy().reshape(-1).view(a.dtype) for r in range(world)]
+            out[name] = np.concatenate(parts)
+    return out

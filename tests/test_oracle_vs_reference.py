@@ -1,0 +1,85 @@
+"""Pins the CPU restatement (oracle/marx_oracle.c) to the reference itself.
+
+1. Against the committed fixtures: per-stage FP64 photon records produced by the UNMODIFIED MARX 5.5.3
+   stage functions (oracle/_ref/marx_replay, see tests/golden/make_golden.py) -- required BIT-EXACT.
+2. Where oracle/_ref exists (the build container), against freshly generated replays with other seeds,
+   ray ranges and parameter overrides -- also bit-exact.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.oracle_lib import Oracle
+from tests.replay_io import read_replay
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REF = os.path.join(ROOT, "oracle", "_ref")
+HAVE_REF = os.path.exists(os.path.join(REF, "marx_replay")) and os.path.exists(os.path.join(REF, "calpack_dump"))
+
+LIVE_FIELDS = ["energy", "x", "p", "flags", "y_pixel", "z_pixel", "dither", "pi", "pulse_height", "mirror_shell",
+               "ccd_num", "order", "tag"]
+
+
+def check_bit_exact(mine, ref_stages, start_times):
+    """mine: oracle records [4][n] with absolute times; ref_stages: replay records [n][4]."""
+    n = mine.shape[1]
+    for s in range(4):
+        a, b = mine[s], ref_stages[:, s]
+        a_alive = (a["flags"] & 0xFF) == 0
+        b_alive = (b["flags"] & 0xFF) == 0
+        assert (a_alive == b_alive).all(), "stage %d: live sets differ" % s
+        # dead rays: first cause reported by the restatement must be among the reference's bits
+        dead = ~a_alive
+        assert ((a["flags"][dead] & b["flags"][dead] & 0xFF) == (a["flags"][dead] & 0xFF)).all()
+        for f in LIVE_FIELDS:
+            if s == 0 and f == "x":
+                continue
+            assert (a[f][a_alive] == b[f][a_alive]).all(), "stage %d field %s differs" % (s, f)
+    # absolute arrival times: reference (batch size 1) = running start_time + arrival_time
+    t_ref = start_times + ref_stages[:, 0]["arrival_time"]
+    assert np.abs(mine[0]["arrival_time"] - t_ref).max() <= 1e-9 * max(t_ref.max(), 1.0)
+    assert n == len(ref_stages)
+
+
+@pytest.mark.parametrize("config", ["c1_acis_s", "c2_hetg_acis_s"])
+def test_oracle_matches_committed_reference_replay(config):
+    z = np.load(os.path.join(GOLDEN, config + "_replay.npz"))
+    o = Oracle(config, int(z["seed"]))
+    st, _, nd = o.trace(int(z["first_ray"]), len(z["stages"]))
+    check_bit_exact(st, z["stages"], z["start_time"])
+    assert nd == int(((z["stages"][:, 3]["flags"] & 0xFF) == 0).sum())
+
+
+CASES = [
+    ("hetg_mid_stream", ["MinEnergy=0.3", "MaxEnergy=8.0", "GratingType=HETG", "DetectorType=ACIS-S", "DitherModel=INTERNAL"], 3, 5000000, 30000),
+    ("soft_no_grating_dither", ["MinEnergy=0.1", "MaxEnergy=1.0", "GratingType=NONE", "DetectorType=ACIS-S", "DitherModel=INTERNAL"], 9, 0, 20000),
+    ("hard_hetg_nodither", ["MinEnergy=5.0", "MaxEnergy=11.5", "GratingType=HETG", "DetectorType=ACIS-S", "DitherModel=NONE"], 21, 123456, 20000),
+    ("ideal_mirror", ["MinEnergy=1.0", "MaxEnergy=2.0", "GratingType=HETG", "DetectorType=ACIS-S", "DitherModel=INTERNAL", "HRMA_Ideal=yes"], 4, 0, 10000),
+    ("no_wfold_no_struts_offset_detector", ["MinEnergy=0.5", "MaxEnergy=6.0", "GratingType=HETG", "DetectorType=ACIS-S", "DitherModel=INTERNAL",
+                                             "HRMA_Use_WFold=no", "HRMA_Use_Struts=no", "DetOffsetX=0.5", "DetOffsetZ=-3.0"], 5, 77, 10000),
+    ("finite_distance_shutters", ["MinEnergy=0.5", "MaxEnergy=4.0", "GratingType=NONE", "DetectorType=ACIS-S", "DitherModel=NONE",
+                                  "SourceDistance=537.0", "Shutters1=0110", "Shutters4=1000"], 6, 0, 10000),
+    ("sector_files_off_unit_order", ["MinEnergy=0.8", "MaxEnergy=3.0", "GratingType=HETG", "DetectorType=ACIS-S", "DitherModel=INTERNAL",
+                                     "Use_HETG_Sector_Files=no"], 8, 1000, 10000),
+]
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref (compiled reference) not present on this box")
+@pytest.mark.parametrize("name,args,seed,first,n", CASES, ids=[c[0] for c in CASES])
+def test_oracle_matches_fresh_reference_replay(tmp_path, name, args, seed, first, n):
+    par = "@@" + os.path.join(REF, "par", "marx.par")
+    common = ["ExposureTime=0", "Verbose=0", "SourceFlux=0.003", "TStart=2023.5", "SourceType=POINT", "SpectrumType=FLAT"]
+    env = dict(os.environ, MARX_DATA_DIR=os.path.join(REF, "data"))
+    pack = str(tmp_path / (name + ".calpack"))
+    dump = str(tmp_path / (name + ".bin"))
+    subprocess.check_call([os.path.join(REF, "calpack_dump"), pack, par] + common + args, env=env,
+                          stdout=subprocess.DEVNULL)
+    subprocess.check_call([os.path.join(REF, "marx_replay"), dump, str(n), str(seed), str(first), par] + common + args,
+                          env=env, stdout=subprocess.DEVNULL)
+    hdr, recs = read_replay(dump)
+    o = Oracle(pack, seed)
+    st, _, _ = o.trace(first, n)
+    check_bit_exact(st, recs["st"], recs["start"])
