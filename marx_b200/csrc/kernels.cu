@@ -306,6 +306,13 @@ __device__ __forceinline__ void stage_loop (const StageArgs &a, TileShared &ts, 
 }
 
 // K1 ------------------------------------------------------------------------------------------
+// The mirror stage is three kernels (HRMA phases A, B, C of mx_hrma.cuh), each with its own fused
+// compaction, so that every phase starts with full warps although 52 % / 43 % / 33 % of its rays die.
+// State handed from phase to phase through otherwise unused SoA columns:
+//   pha  (i16)  draws consumed so far on the MIRROR sub-stream | 0x4000 if a Box-Muller spare is cached
+//   aux  (f64)  the cached spare
+//   chipx, chipy, pi (f32)  beta, delta, effective-area correction (float-valued table lookups)
+template <int PHASE>
 __global__ void __launch_bounds__ (kTile) k1_hrma (const __grid_constant__ StageArgs a)
 {
    extern __shared__ __align__ (128) unsigned char smem[];
@@ -314,11 +321,6 @@ __global__ void __launch_bounds__ (kTile) k1_hrma (const __grid_constant__ Stage
    stage_blob (smem, a.blob, a.blob_bytes, &bar);
    const K1Blob &B = *reinterpret_cast<const K1Blob *> (smem);
    const HrmaDev &H = B.H;
-   const float *opt_e = reinterpret_cast<const float *> (smem + B.off_opt_e);
-   const float *opt_b = reinterpret_cast<const float *> (smem + B.off_opt_b);
-   const float *opt_d = reinterpret_cast<const float *> (smem + B.off_opt_d);
-   const float *corr_e = reinterpret_cast<const float *> (smem + B.off_corr_e);
-   const float *corr_f = reinterpret_cast<const float *> (smem + B.off_corr_f);
 
    stage_loop (a, ts, [&] (unsigned long long tile, unsigned long long i, bool valid, bool last_tile)
      {
@@ -326,44 +328,78 @@ __global__ void __launch_bounds__ (kTile) k1_hrma (const __grid_constant__ Stage
         uint32_t flags = 0xFFu;
         double energy = 0.0; Vec3 x = v_make (0, 0, 0), p = v_make (0, 0, 0);
         uint32_t shell = 0; uint64_t ray = 0;
+        float beta = 0.f, delta = 1.f, corr = 1.f;
+        Rng rng;
         bool active = valid;
         if (valid && !a.compact) active = ((in.flags[i] & 0xFFu) == 0);
         if (active)
           {
-             energy = in.energy[i];
-             p = v_make (in.p0[i], in.p1[i], in.p2[i]);
              ray = in.ray[i];
-             Rng rng; rng.init (a.seed, ray, MARXB200_STAGE_MIRROR);
-             flags = hrma_reflect (H, opt_e, opt_b, opt_d, corr_e, corr_f, a.source_distance, energy, x, p, shell, rng);
+             p = v_make (in.p0[i], in.p1[i], in.p2[i]);
+             rng.init (a.seed, ray, MARXB200_STAGE_MIRROR);
+             if (PHASE == 0)
+               flags = hrma_phase_a (H, a.source_distance, x, p, shell, rng);
+             else
+               {
+                  x = v_make (in.x0[i], in.x1[i], in.x2[i]);
+                  energy = in.energy[i];
+                  shell = in.shell[i];
+                  const int st = in.pha[i];
+                  rng.resume ((uint32_t) (st & 0x3FFF), (st & 0x4000) ? 1 : 0, (st & 0x4000) ? in.aux[i] : 0.0);
+                  if (PHASE == 1)
+                    {
+                       hrma_optical_constants (H, H.shell[shell],
+                                               reinterpret_cast<const float *> (smem + B.off_opt_e),
+                                               reinterpret_cast<const float *> (smem + B.off_opt_b),
+                                               reinterpret_cast<const float *> (smem + B.off_opt_d),
+                                               reinterpret_cast<const float *> (smem + B.off_corr_e),
+                                               reinterpret_cast<const float *> (smem + B.off_corr_f),
+                                               energy, beta, delta, corr);
+                       flags = hrma_phase_b (H, shell, energy, beta, delta, corr, x, p, rng);
+                    }
+                  else
+                    {
+                       beta = in.chipx[i]; delta = in.chipy[i]; corr = in.pi[i];
+                       flags = hrma_phase_c (H, shell, energy, beta, delta, corr, x, p, rng);
+                    }
+               }
           }
+        const int16_t rng_state = (int16_t) ((rng.draw & 0x3FFFu) | (rng.have_spare ? 0x4000u : 0u));
+        unsigned long long j = i;
+        bool write = active;
         if (a.compact)
           {
              const bool alive = active && (flags == 0);
              uint32_t aggregate;
              uint32_t rank = block_rank (alive, ts, aggregate);
              unsigned long long excl = tile_exclusive_prefix (a.tile_status, tile, aggregate, ts);
+             j = excl + rank;
+             write = alive;
              if (alive)
                {
-                  const unsigned long long j = excl + rank;
-                  out.energy[j] = energy;
-                  out.x0[j] = x.x; out.x1[j] = x.y; out.x2[j] = x.z;
-                  out.p0[j] = p.x; out.p1[j] = p.y; out.p2[j] = p.z;
+                  // payload carried through the stage untouched
                   out.time[j] = in.time[i];
                   out.ray[j] = ray;
-                  out.flags[j] = 0;
                   out.dra[j] = in.dra[i]; out.ddec[j] = in.ddec[i]; out.droll[j] = in.droll[i];
+                  out.energy[j] = (PHASE == 0) ? in.energy[i] : energy;
                   out.shell[j] = (uint8_t) shell;
                }
              if (last_tile && (threadIdx.x == 0)) *a.n_out = excl + aggregate;
           }
-        else if (active)
+        else if (last_tile && (threadIdx.x == 0)) *a.n_out = *a.n_in;
+        if (write)
           {
-             out.x0[i] = x.x; out.x1[i] = x.y; out.x2[i] = x.z;
-             out.p0[i] = p.x; out.p1[i] = p.y; out.p2[i] = p.z;
-             out.flags[i] = flags;
-             out.shell[i] = (uint8_t) shell;
+             out.x0[j] = x.x; out.x1[j] = x.y; out.x2[j] = x.z;
+             out.p0[j] = p.x; out.p1[j] = p.y; out.p2[j] = p.z;
+             out.flags[j] = flags;
+             if ((PHASE == 0) && !a.compact) out.shell[j] = (uint8_t) shell;
+             if (PHASE < 2)
+               {
+                  out.pha[j] = rng_state;
+                  if (rng.have_spare) out.aux[j] = rng.spare;
+               }
+             if (PHASE == 1) { out.chipx[j] = beta; out.chipy[j] = delta; out.pi[j] = corr; }
           }
-        if (!a.compact && last_tile && (threadIdx.x == 0)) *a.n_out = *a.n_in;
      });
 }
 
@@ -588,13 +624,23 @@ int stage_grid_size (int stage, int num_sms, uint32_t blob_bytes)
 {
    switch (stage)
      {
-      case 1: return occupancy_grid (k1_hrma, num_sms, blob_bytes);
+      case 10: return occupancy_grid (k1_hrma<0>, num_sms, blob_bytes);
+      case 11: return occupancy_grid (k1_hrma<1>, num_sms, blob_bytes);
+      case 12: return occupancy_grid (k1_hrma<2>, num_sms, blob_bytes);
       case 2: return occupancy_grid (k2_grating, num_sms, blob_bytes);
       case 3: return occupancy_grid (k3_acis, num_sms, blob_bytes);
      }
    return num_sms;
 }
-void launch_hrma (const StageArgs &a, int grid, cudaStream_t s) { k1_hrma<<<grid, kTile, a.blob_bytes, s>>> (a); }
+void launch_hrma (const StageArgs &a, int phase, int grid, cudaStream_t s)
+{
+   switch (phase)
+     {
+      case 0: k1_hrma<0><<<grid, kTile, a.blob_bytes, s>>> (a); break;
+      case 1: k1_hrma<1><<<grid, kTile, a.blob_bytes, s>>> (a); break;
+      default: k1_hrma<2><<<grid, kTile, a.blob_bytes, s>>> (a); break;
+     }
+}
 void launch_grating (const StageArgs &a, int grid, cudaStream_t s) { k2_grating<<<grid, kTile, a.blob_bytes, s>>> (a); }
 void launch_acis (const StageArgs &a, int grid, cudaStream_t s) { k3_acis<<<grid, kTile, a.blob_bytes, s>>> (a); }
 

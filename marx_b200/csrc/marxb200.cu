@@ -52,9 +52,10 @@ struct marxb200_ctx
    int cur = 0;
 
    // device scalars: counts[0..3] + ticket + total_time
-   unsigned long long *d_counts = nullptr;      // [4]
-   unsigned long long *d_ticket = nullptr;
-   unsigned long long *d_tile_status = nullptr; // [capacity/kTile + 1]
+   unsigned long long *d_counts = nullptr;      // [8]: generated, after mirror, after grating, detected, after k1a, after k1b
+   unsigned long long *d_ticket = nullptr;      // [4]: one ticket counter per kernel of a stage call
+   unsigned long long *d_tile_status = nullptr; // [3][n_status]: look-back words, one array per kernel of a stage call
+   uint64_t n_status = 0;
    double *d_tile_sums = nullptr, *d_tile_base = nullptr, *d_super_sums = nullptr, *d_times = nullptr;   // d_times: [batch start, running end]
    int stage_done = -1;                          // index into d_counts of the latest valid count
    uint64_t n_generated = 0;
@@ -67,7 +68,7 @@ struct marxb200_ctx
    double source_distance = 0.0;
    void *blob1 = nullptr, *blob2 = nullptr, *blob3 = nullptr;
    uint32_t blob1_bytes = 0, blob2_bytes = 0, blob3_bytes = 0;
-   int grid1 = 0, grid2 = 0, grid3 = 0;
+   int grid1[3] = {0, 0, 0}, grid2 = 0, grid3 = 0;
 
    // host boundary staging
    void *d_aos = nullptr; uint64_t d_aos_cap = 0;
@@ -140,10 +141,10 @@ extern "C" int marxb200_create (marxb200_ctx **ctxp, int device_ordinal, uint64_
    c->num_sms = prop.multiProcessorCount;
    CUDA_OK (cudaStreamCreateWithFlags (&c->stream, cudaStreamNonBlocking));
    c->own_stream = true;
-   CUDA_OK (cudaMalloc (&c->d_counts, 4 * sizeof (unsigned long long)));
-   CUDA_OK (cudaMalloc (&c->d_ticket, sizeof (unsigned long long)));
+   CUDA_OK (cudaMalloc (&c->d_counts, 8 * sizeof (unsigned long long)));
+   CUDA_OK (cudaMalloc (&c->d_ticket, 4 * sizeof (unsigned long long)));
    CUDA_OK (cudaMalloc (&c->d_times, 2 * sizeof (double)));
-   CUDA_OK (cudaMemset (c->d_counts, 0, 4 * sizeof (unsigned long long)));
+   CUDA_OK (cudaMemset (c->d_counts, 0, 8 * sizeof (unsigned long long)));
    CUDA_OK (cudaMemset (c->d_times, 0, 2 * sizeof (double)));
    memset (&c->S, 0, sizeof (c->S));
    memset (&c->D, 0, sizeof (c->D));
@@ -260,7 +261,7 @@ extern "C" int marxb200_set_hrma (marxb200_ctx *c, const marxb200_hrma_desc *d)
    if (-1 == mx::build_hrma_blob (up, d, blob, err)) return fail ("marxb200_set_hrma: %s", err.c_str ());
    if (-1 == dev_upload (c, blob.data (), blob.size (), &c->blob1)) return -1;
    c->blob1_bytes = (uint32_t) blob.size ();
-   c->grid1 = stage_grid_size (1, c->num_sms, c->blob1_bytes);
+   for (int ph = 0; ph < 3; ph++) c->grid1[ph] = stage_grid_size (10 + ph, c->num_sms, c->blob1_bytes);
    c->have_hrma = true;
    return 0;
 }
@@ -310,6 +311,7 @@ static size_t carve (PhotonSoA &b, unsigned char *base, uint64_t n)
    b.x0 = (double *) take (8); b.x1 = (double *) take (8); b.x2 = (double *) take (8);
    b.p0 = (double *) take (8); b.p1 = (double *) take (8); b.p2 = (double *) take (8);
    b.time = (double *) take (8);
+   b.aux = (double *) take (8);
    b.ray = (uint64_t *) take (8);
    b.flags = (uint32_t *) take (4);
    b.dra = (float *) take (4); b.ddec = (float *) take (4); b.droll = (float *) take (4);
@@ -341,7 +343,8 @@ extern "C" int marxb200_alloc_photons (marxb200_ctx *c, uint64_t max_photons)
      }
    uint64_t n_tiles = (max_photons + kTile - 1) / kTile + 1;
    uint64_t n_super = (n_tiles + kSuperTile - 1) / kSuperTile + 1;
-   CUDA_OK (cudaMalloc (&c->d_tile_status, n_tiles * sizeof (unsigned long long)));
+   c->n_status = n_tiles;
+   CUDA_OK (cudaMalloc (&c->d_tile_status, 3 * n_tiles * sizeof (unsigned long long)));
    CUDA_OK (cudaMalloc (&c->d_tile_sums, n_tiles * sizeof (double)));
    CUDA_OK (cudaMalloc (&c->d_tile_base, n_tiles * sizeof (double)));
    CUDA_OK (cudaMalloc (&c->d_super_sums, n_super * sizeof (double)));
@@ -414,27 +417,37 @@ static int run_stage (marxb200_ctx *c, int stage)
    StageArgs a;
    memset (&a, 0, sizeof (a));
    if (c->stage_done < 0) return fail ("stage %d: no photons (call marxb200_create_photons or marxb200_upload first)", stage);
-   a.in = c->buf[c->cur];
-   a.out = c->compact ? c->buf[1 - c->cur] : c->buf[c->cur];
-   a.n_in = c->d_counts + c->stage_done;
-   a.n_out = c->d_counts + stage;
-   a.ticket = c->d_ticket;
-   a.tile_status = c->d_tile_status;
    a.seed = c->seed;
    a.compact = c->compact;
    a.source_distance = c->source_distance;
+   // the mirror stage runs as three kernels (HRMA phases A, B, C, mx_hrma.cuh) with a compaction after each
+   const int n_kernels = (stage == 1) ? 3 : 1;
    uint64_t n_tiles = (c->n_generated + kTile - 1) / kTile + 1;
-   CUDA_OK (cudaMemsetAsync (c->d_ticket, 0, sizeof (unsigned long long), c->stream));
-   if (c->compact) CUDA_OK (cudaMemsetAsync (c->d_tile_status, 0, n_tiles * sizeof (unsigned long long), c->stream));
-   switch (stage)
+   if (n_tiles > c->n_status) n_tiles = c->n_status;
+   CUDA_OK (cudaMemsetAsync (c->d_ticket, 0, 4 * sizeof (unsigned long long), c->stream));
+   if (c->compact)
+     for (int k = 0; k < n_kernels; k++)
+       CUDA_OK (cudaMemsetAsync (c->d_tile_status + k * c->n_status, 0, n_tiles * sizeof (unsigned long long), c->stream));
+   const unsigned long long *n_in = c->d_counts + c->stage_done;
+   for (int k = 0; k < n_kernels; k++)
      {
-      case 1: a.blob = c->blob1; a.blob_bytes = c->blob1_bytes; launch_hrma (a, c->grid1, c->stream); break;
-      case 2: a.blob = c->blob2; a.blob_bytes = c->blob2_bytes; launch_grating (a, c->grid2, c->stream); break;
-      case 3: a.blob = c->blob3; a.blob_bytes = c->blob3_bytes; launch_acis (a, c->grid3, c->stream); break;
+        a.in = c->buf[c->cur];
+        a.out = c->compact ? c->buf[1 - c->cur] : c->buf[c->cur];
+        a.n_in = n_in;
+        a.n_out = (k == n_kernels - 1) ? c->d_counts + stage : c->d_counts + 4 + k;
+        a.ticket = c->d_ticket + k;
+        a.tile_status = c->d_tile_status + k * c->n_status;
+        switch (stage)
+          {
+           case 1: a.blob = c->blob1; a.blob_bytes = c->blob1_bytes; launch_hrma (a, k, c->grid1[k], c->stream); break;
+           case 2: a.blob = c->blob2; a.blob_bytes = c->blob2_bytes; launch_grating (a, c->grid2, c->stream); break;
+           case 3: a.blob = c->blob3; a.blob_bytes = c->blob3_bytes; launch_acis (a, c->grid3, c->stream); break;
+          }
+        c->launches += 1;
+        CUDA_OK (cudaGetLastError ());
+        if (c->compact) c->cur = 1 - c->cur;
+        n_in = a.n_out;
      }
-   c->launches += 1;
-   CUDA_OK (cudaGetLastError ());
-   if (c->compact) c->cur = 1 - c->cur;
    c->stage_done = stage;
    return 0;
 }

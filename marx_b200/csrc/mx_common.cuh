@@ -132,6 +132,12 @@ struct Rng
       stage = stg; draw = 0; have_spare = 0; spare = 0.0;
       b0 = b1 = b2 = b3 = 0;
    }
+   // continue a stream that another kernel left after `d` draws (sub-stage kernels of one MARX stage share a stream)
+   MX_HD void resume (uint32_t d, int has_spare, double spare_value)
+   {
+      draw = d; have_spare = has_spare; spare = spare_value;
+      if ((d & 3u) != 0u) refill (d >> 2);
+   }
    MX_HD void refill (uint32_t block)
    {
       uint32_t x0 = c0, x1 = c1, x2 = block, x3 = stage, ka = k0, kb = k1;

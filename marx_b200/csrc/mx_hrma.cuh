@@ -198,33 +198,6 @@ MX_HD double wfold_interp (const WfoldDev &w, double energy, double sin_alpha, d
    return theta_0 + (theta_1 - theta_0) * (e_alpha - e0) / (e1 - e0);
 }
 
-// reflect_from_conic, hrma.c:488-545.  returns 0 ok, -1 absorbed, -2 missed
-MX_HD int reflect_from_conic (const HrmaDev &H, const double *conic, const WfoldDev &wfold, double scat_factor,
-                              double blur, double energy, double beta, double delta, double corr,
-                              Vec3 &x, Vec3 &p, Rng &rng)
-{
-   Vec3 normal;
-   if (-1 == conic_intersection (conic, x, p, normal)) return -2;
-   if (H.use_blur) blur_normal (normal, blur, rng);
-   double p_dot_n = v_dot (p, normal);
-   if (H.is_ideal == 0)
-     {
-        double r = rng.uniform ();
-        double rfl = reflectivity (fabs (p_dot_n), beta, delta);
-        if (r >= rfl * corr) return -1;
-     }
-   p = v_ax1_bx2 (1.0, p, -2.0 * p_dot_n, normal);
-   if (H.use_wfold == 0) return 0;
-   double sin_grazing = -p_dot_n;
-   double r = rng.uniform ();
-   double delta_grazing = wfold_interp (wfold, energy, sin_grazing, r);
-   delta_grazing *= scat_factor;
-   if (delta_grazing > kPI / 4) return -1;
-   if (rng.uniform () < 0.5) delta_grazing = -delta_grazing;
-   p = v_rotate_unit (p, v_cross (p, normal), delta_grazing);
-   return 0;
-}
-
 // intersects_struts, hrma.c:928-968.  struts = {xpos0, half_width0, xpos1, half_width1}
 MX_HD int intersects_struts (const Vec3 &x0, const Vec3 &p0, double cap_position, const double *struts)
 {
@@ -256,12 +229,56 @@ MX_HD int intersects_struts (const Vec3 &x0, const Vec3 &p0, double cap_position
 #define MX_CAP_STRUTS     {0.5 * 1.965 * 25.4, 0.5 * 0.75 * 25.4, -0.5 * 1.965 * 25.4, 0.5 * 0.75 * 25.4}
 #define MX_POSTCOL_STRUTS {-1050.353, 0.5 * 0.5 * 25.4, -1271.333, 0.5 * 0.5 * 25.4}
 
-// _marx_hrma_mirror_reflect for one ray.  In: energy, p (from the source), source distance.
-// Out: x, p at the exit of the mirror pair, shell index 0..3.  Returns the photon flags (0 = alive).
-// opt_* / corr_* may point to shared memory copies of H.opt_* / H.corr_*.
-MX_HD uint32_t hrma_reflect (const HrmaDev &H, const float *opt_e, const float *opt_b, const float *opt_d,
-                             const float *corr_e, const float *corr_f,
-                             double source_distance, double energy, Vec3 &x, Vec3 &p, uint32_t &shell_out, Rng &rng)
+// _marx_hrma_mirror_reflect for one ray, cut at the two points where most rays die so that the GPU can
+// re-pack the survivors into full warps between the pieces (kernels k1a/k1b/k1c):
+//   phase A  vignetting, shell + aperture point, precollimator struts, OSAC-P transform, P-conic intersection
+//            (47.6 % of the rays of the C2 workload reach the end of A)
+//   phase B  optical constants, P blur/reflect/scatter, back transform, CAP struts, OSAC-H transform, H-conic
+//            intersection (27.3 % reach the end of B)
+//   phase C  H blur/reflect/scatter, back transform, postcollimator struts (18.4 % survive)
+// The conic normal is a pure function of the stored intersection point, so B and C recompute it from x
+// bit-identically instead of carrying it.  hrma_reflect() = A;B;C is what the host-side checks step.
+
+// inward unit normal of a conic at surface point x (tail of compute_conic_intersection, hrma.c:471-476)
+MX_HD Vec3 conic_normal (const double *conic, const Vec3 &x)
+{
+   Vec3 n;
+   n.x = (conic[0] - 1) * x.x + 0.5 * conic[1];
+   n.y = -x.y;
+   n.z = -x.z;
+   v_normalize (n);
+   return n;
+}
+
+// reflect_from_conic after the intersection test, hrma.c:499-544.  returns 0 ok, -1 absorbed
+MX_HD int reflect_at_point (const HrmaDev &H, const double *conic, const WfoldDev &wfold, double scat_factor,
+                            double blur, double energy, double beta, double delta, double corr,
+                            const Vec3 &x, Vec3 &p, Rng &rng)
+{
+   Vec3 normal = conic_normal (conic, x);
+   if (H.use_blur) blur_normal (normal, blur, rng);
+   double p_dot_n = v_dot (p, normal);
+   if (H.is_ideal == 0)
+     {
+        double r = rng.uniform ();
+        double rfl = reflectivity (fabs (p_dot_n), beta, delta);
+        if (r >= rfl * corr) return -1;
+     }
+   p = v_ax1_bx2 (1.0, p, -2.0 * p_dot_n, normal);
+   if (H.use_wfold == 0) return 0;
+   double sin_grazing = -p_dot_n;
+   double r = rng.uniform ();
+   double delta_grazing = wfold_interp (wfold, energy, sin_grazing, r);
+   delta_grazing *= scat_factor;
+   if (delta_grazing > kPI / 4) return -1;
+   if (rng.uniform () < 0.5) delta_grazing = -delta_grazing;
+   p = v_rotate_unit (p, v_cross (p, normal), delta_grazing);
+   return 0;
+}
+
+// phase A.  In: energy-independent; p from the source.  Out: x, p in the OSAC-P frame AT the P-conic
+// intersection, shell.  Returns flags (0 = still alive).
+MX_HD uint32_t hrma_phase_a (const HrmaDev &H, double source_distance, Vec3 &x, Vec3 &p, uint32_t &shell_out, Rng &rng)
 {
    const uint32_t VBLOCKED = 0x10, UNREFLECTED = 0x02;
    // vignetting, hrma.c:1183-1192
@@ -291,8 +308,14 @@ MX_HD uint32_t hrma_reflect (const HrmaDev &H, const float *opt_e, const float *
         }
       while (0 == (h.shutter_bitmap & (1u << quad)));
       theta = (2.0 * kPI) * (theta - 1.0 / 8.0);
-      x.z = radius * cos (theta);
-      x.y = radius * sin (theta);
+      double st, ct;
+#if defined(__CUDA_ARCH__)
+      sincos (theta, &st, &ct);
+#else
+      st = sin (theta); ct = cos (theta);
+#endif
+      x.z = radius * ct;
+      x.y = radius * st;
       x.x = h.front_position;
       x.z -= h.to_osac_p[2];
       x.y -= h.to_osac_p[1];
@@ -308,29 +331,41 @@ MX_HD uint32_t hrma_reflect (const HrmaDev &H, const float *opt_e, const float *
         if (intersects_struts (x, p, H.cap_position, st)) return VBLOCKED;
      }
    // to OSAC P frame, hrma.c:1222-1235
-   const Vec3 to_p = v_make (h.to_osac_p[0], h.to_osac_p[1], h.to_osac_p[2]);
-   const Vec3 to_h = v_make (h.to_osac_h[0], h.to_osac_h[1], h.to_osac_h[2]);
-   x = v_sum (x, to_p);
+   x = v_sum (x, v_make (h.to_osac_p[0], h.to_osac_p[1], h.to_osac_p[2]));
    x = m3_mul (h.fwd_p, x);
    p = m3_mul (h.fwd_p, p);
+   Vec3 normal;
+   if (-1 == conic_intersection (h.conic_p, x, p, normal)) return UNREFLECTED;
+   return 0;
+}
 
-   // optical constants and effective-area correction, hrma.c:1239-1262
-   double beta = 0.0, delta = 1.0, corr = 1.0;
+// optical constants and effective-area correction, hrma.c:1239-1262.  beta/delta/corr are float-valued
+// table interpolations (finterpo.c:59-85); the square root of corr is taken at use (hrma.c:1258-1259).
+MX_HD void hrma_optical_constants (const HrmaDev &H, const HrmaShellDev &h, const float *opt_e, const float *opt_b,
+                                   const float *opt_d, const float *corr_e, const float *corr_f, double energy,
+                                   float &beta, float &delta, float &corr)
+{
+   beta = 0.0f; delta = 1.0f; corr = 1.0f;
    if (H.num_opt != 0)
      {
         float ef = (float) energy;
         beta = interp_f (ef, opt_e, opt_b, H.num_opt);
         delta = interp_f (ef, opt_e, opt_d, H.num_opt);
-        if (H.use_scale)
-          {
-             corr = interp_f (ef, corr_e + h.corr_offset, corr_f + h.corr_offset, h.num_corr);
-             corr = sqrt (corr);
-          }
+        if (H.use_scale) corr = interp_f (ef, corr_e + h.corr_offset, corr_f + h.corr_offset, h.num_corr);
      }
+}
 
-   int status = reflect_from_conic (H, h.conic_p, h.wfold_p, h.p_scat, h.p_blur, energy, beta, delta, corr, x, p, rng);
-   if (status != 0) return UNREFLECTED;
-
+// phase B.  In: x, p at the P intersection (OSAC-P frame).  Out: x, p at the H intersection (OSAC-H frame).
+MX_HD uint32_t hrma_phase_b (const HrmaDev &H, uint32_t shell, double energy, float beta, float delta, float corr_f32,
+                             Vec3 &x, Vec3 &p, Rng &rng)
+{
+   const uint32_t VBLOCKED = 0x10, UNREFLECTED = 0x02;
+   const HrmaShellDev &h = H.shell[shell];
+   double corr = (H.num_opt != 0 && H.use_scale) ? sqrt ((double) corr_f32) : 1.0;
+   if (0 != reflect_at_point (H, h.conic_p, h.wfold_p, h.p_scat, h.p_blur, energy, beta, delta, corr, x, p, rng))
+     return UNREFLECTED;
+   const Vec3 to_p = v_make (h.to_osac_p[0], h.to_osac_p[1], h.to_osac_p[2]);
+   const Vec3 to_h = v_make (h.to_osac_h[0], h.to_osac_h[1], h.to_osac_h[2]);
    p = m3_mul (h.bwd_p, p);
    x = m3_mul (h.bwd_p, x);
    x = v_diff (x, to_p);
@@ -342,19 +377,43 @@ MX_HD uint32_t hrma_reflect (const HrmaDev &H, const float *opt_e, const float *
    x = v_sum (x, to_h);
    p = m3_mul (h.fwd_h, p);
    x = m3_mul (h.fwd_h, x);
+   Vec3 normal;
+   if (-1 == conic_intersection (h.conic_h, x, p, normal)) return UNREFLECTED;
+   return 0;
+}
 
-   status = reflect_from_conic (H, h.conic_h, h.wfold_h, h.h_scat, h.h_blur, energy, beta, delta, corr, x, p, rng);
-   if (status != 0) return UNREFLECTED;
-
+// phase C.  In: x, p at the H intersection (OSAC-H frame).  Out: x, p in MARX coordinates behind the mirror.
+MX_HD uint32_t hrma_phase_c (const HrmaDev &H, uint32_t shell, double energy, float beta, float delta, float corr_f32,
+                             Vec3 &x, Vec3 &p, Rng &rng)
+{
+   const uint32_t VBLOCKED = 0x10, UNREFLECTED = 0x02;
+   const HrmaShellDev &h = H.shell[shell];
+   double corr = (H.num_opt != 0 && H.use_scale) ? sqrt ((double) corr_f32) : 1.0;
+   if (0 != reflect_at_point (H, h.conic_h, h.wfold_h, h.h_scat, h.h_blur, energy, beta, delta, corr, x, p, rng))
+     return UNREFLECTED;
    p = m3_mul (h.bwd_h, p);
    x = m3_mul (h.bwd_h, x);
-   x = v_diff (x, to_h);
+   x = v_diff (x, v_make (h.to_osac_h[0], h.to_osac_h[1], h.to_osac_h[2]));
    if (H.use_struts)
      {
         const double st[4] = MX_POSTCOL_STRUTS;
         if (intersects_struts (x, p, H.cap_position, st)) return VBLOCKED;
      }
    return 0;
+}
+
+// the whole stage for one ray (A;B;C) -- used by the developer host check; the kernels call the phases
+MX_HD uint32_t hrma_reflect (const HrmaDev &H, const float *opt_e, const float *opt_b, const float *opt_d,
+                             const float *corr_e, const float *corr_f,
+                             double source_distance, double energy, Vec3 &x, Vec3 &p, uint32_t &shell_out, Rng &rng)
+{
+   uint32_t flags = hrma_phase_a (H, source_distance, x, p, shell_out, rng);
+   if (flags) return flags;
+   float beta, delta, corr;
+   hrma_optical_constants (H, H.shell[shell_out], opt_e, opt_b, opt_d, corr_e, corr_f, energy, beta, delta, corr);
+   flags = hrma_phase_b (H, shell_out, energy, beta, delta, corr, x, p, rng);
+   if (flags) return flags;
+   return hrma_phase_c (H, shell_out, energy, beta, delta, corr, x, p, rng);
 }
 
 }  // namespace mx

@@ -16,6 +16,7 @@ struct PhotonSoA
    double *x0, *x1, *x2;
    double *p0, *p1, *p2;
    double *time;                         // absolute: pt->start_time + arrival_time
+   double *aux;                          // scratch between the HRMA sub-kernels (cached Box-Muller spare)
    uint64_t *ray;                        // global ray index (RNG counter; low 32 bits = tag)
    uint32_t *flags;
    float *dra, *ddec, *droll;            // Marx_Dither_Type ra/dec/roll (dy,dz,dtheta are 0 for INTERNAL)
@@ -76,7 +77,7 @@ struct SourceArgs
 void launch_time_sums (const SourceArgs &a, cudaStream_t s);
 void launch_time_scan (const SourceArgs &a, cudaStream_t s);
 void launch_source (const SourceArgs &a, cudaStream_t s);
-void launch_hrma (const StageArgs &a, int grid, cudaStream_t s);
+void launch_hrma (const StageArgs &a, int phase, int grid, cudaStream_t s);   // phase 0,1,2 = k1a,k1b,k1c
 void launch_grating (const StageArgs &a, int grid, cudaStream_t s);
 void launch_acis (const StageArgs &a, int grid, cudaStream_t s);
 int stage_grid_size (int stage, int num_sms, uint32_t blob_bytes);

@@ -123,8 +123,11 @@ def test_seed_and_offset_independence():
     import marx_b200
     n = 1 << 18
     with marx_b200.MarxB200("c2_hetg_acis_s", seed=7, max_photons=n) as m:
-        m.trace(0, n); a = m.download().copy()
-        m.create_photons(n // 2, n // 2, time_base=0.0); m.mirror_reflect(); m.grating_diffract(); m.detect()
+        m.create_photons(0, n, time_base=0.0); m.mirror_reflect(); m.grating_diffract(); m.detect()
+        a = m.download().copy()
+        # same rays as two batches: the second continues the running arrival time of the first (dither depends on it)
+        m.create_photons(0, n // 2, time_base=0.0)
+        m.trace(n // 2, n // 2)
         b = m.download().copy()
     with marx_b200.MarxB200("c2_hetg_acis_s", seed=8, max_photons=n) as m:
         m.trace(0, n); c = m.download().copy()
