@@ -204,16 +204,17 @@ def cuda_arm(args):
         first, base = time_base_for(step)
         with torch.cuda.stream(stream):
             if record:
-                ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
                 ev[0].record(stream)
                 m.create_photons(first, n, base); ev[1].record(stream)
                 m.mirror_reflect(); ev[2].record(stream)
                 m.grating_diffract(); ev[3].record(stream)
                 m.detect(); ev[4].record(stream)
+                m.restore_order(); ev[5].record(stream)
                 stage_events.append(ev)
             else:
                 m.create_photons(first, n, base)
-                m.mirror_reflect(); m.grating_diffract(); m.detect()
+                m.mirror_reflect(); m.grating_diffract(); m.detect(); m.restore_order()
             if e2e:
                 cols = m.download_columns(col_names, out=pinned_np)      # D2H into pinned memory; synchronises
                 return len(cols["energy"])
@@ -255,7 +256,7 @@ def cuda_arm(args):
     clocks = sampler.stop() if rank == 0 else None
     counts = m.stage_counts()
     # per-kernel durations from the SAME timed steps (CUDA events on the launching stream)
-    stage_ms = [sum(ev[k].elapsed_time(ev[k + 1]) for ev in stage_events) / len(stage_events) for k in range(4)]
+    stage_ms = [sum(ev[k].elapsed_time(ev[k + 1]) for ev in stage_events) / len(stage_events) for k in range(5)]
     # e2e leg
     for _ in range(2):
         one_step(timed.step, e2e=True); timed.step += 1
@@ -291,6 +292,7 @@ def cuda_arm(args):
         kernels[name] = {"ms": stage_ms[k], "share": stage_ms[k] / sum(stage_ms), "input_rays": n_in,
                          "hbm_gbs": BYTES_PER_RAY[name] * n_in / (stage_ms[k] * 1e-3) / 1e9 if stage_ms[k] > 0 else None,
                          "fp64_tflopeq": FLOPEQ_PER_RAY[name] * n_in / (stage_ms[k] * 1e-3) / 1e12 if stage_ms[k] > 0 else None}
+    kernels["order_restore"] = {"ms": stage_ms[4], "share": stage_ms[4] / sum(stage_ms), "input_rays": counts[3]}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

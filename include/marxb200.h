@@ -263,6 +263,10 @@ int marxb200_mirror_reflect (marxb200_ctx *ctx);
 int marxb200_grating_diffract (marxb200_ctx *ctx);
 /* marx_detect (detector.c:361-379 -> acis-s.c:177-248) */
 int marxb200_detect (marxb200_ctx *ctx);
+/* The compacting stage kernels emit survivors in completion order; this puts the live list back into
+ * arrival order (what marx_prune_photons preserves, photon.c:40-63).  Called implicitly by marxb200_trace
+ * and by every download; exposed so that a caller timing individual stages can account for it. */
+int marxb200_restore_order (marxb200_ctx *ctx);
 /* all of the above for one batch, device resident (marx.c:569 + process_photons :240-273) */
 int marxb200_trace (marxb200_ctx *ctx, uint64_t first_ray, uint64_t n);
 

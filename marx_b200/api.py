@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "marxb200_set_compaction", "marxb200_set_source", "marxb200_set_dither", "marxb200_set_hrma",
     "marxb200_set_grating", "marxb200_set_acis", "marxb200_load_calpack", "marxb200_alloc_photons",
     "marxb200_create_photons", "marxb200_time_sums", "marxb200_mirror_reflect", "marxb200_grating_diffract",
-    "marxb200_detect", "marxb200_trace", "marxb200_get_counts", "marxb200_get_stage_counts", "marxb200_download",
+    "marxb200_detect", "marxb200_restore_order", "marxb200_trace", "marxb200_get_counts", "marxb200_get_stage_counts", "marxb200_download",
     "marxb200_upload", "marxb200_download_all", "marxb200_download_columns", "marxb200_get_launch_count",
 ]
 
@@ -40,6 +40,8 @@ class MarxB200Error(RuntimeError):
 
 
 def lib_path():
+    if os.environ.get("MARXB200_LIB"):          # developer A/B builds; the default is the in-tree library
+        return os.environ["MARXB200_LIB"]
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmarxb200.so")
 
 
@@ -78,6 +80,7 @@ def load_library():
         "marxb200_mirror_reflect": [vp],
         "marxb200_grating_diffract": [vp],
         "marxb200_detect": [vp],
+        "marxb200_restore_order": [vp],
         "marxb200_trace": [vp, u64, u64],
         "marxb200_get_counts": [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(dbl)],
         "marxb200_get_stage_counts": [vp, C.POINTER(u64)],
@@ -169,6 +172,10 @@ class MarxB200:
 
     def detect(self):
         self._check(self._lib.marxb200_detect(self._ctx))
+
+    def restore_order(self):
+        """put the live list back into arrival order (implicit in trace() and download*())"""
+        self._check(self._lib.marxb200_restore_order(self._ctx))
 
     def trace(self, first_ray, n):
         """create -> mirror -> grating -> detect for one batch, device resident (marx.c:569, :240-273)."""

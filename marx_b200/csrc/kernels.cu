@@ -83,87 +83,6 @@ __device__ __forceinline__ void stage_blob (unsigned char *smem, const void *blo
 }
 
 // ---------------------------------------------------------------------------------------------
-// tile bookkeeping: ticket, block prefix, decoupled look-back
-// ---------------------------------------------------------------------------------------------
-constexpr unsigned long long kFlagAgg = 1ULL << 62, kFlagPrefix = 2ULL << 62, kValueMask = (1ULL << 62) - 1;
-
-struct TileShared
-{
-   unsigned long long tile;
-   unsigned long long excl;
-   uint32_t warp_count[kTile / 32];
-};
-
-// Exclusive rank of this thread's survivor within the tile and the tile aggregate.
-__device__ __forceinline__ uint32_t block_rank (bool alive, TileShared &ts, uint32_t &aggregate)
-{
-   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-   uint32_t ballot = __ballot_sync (0xffffffffu, alive);
-   uint32_t rank = __popc (ballot & ((1u << lane) - 1u));
-   if (lane == 0) ts.warp_count[warp] = __popc (ballot);
-   __syncthreads ();
-   uint32_t off = 0, total = 0;
-#pragma unroll
-   for (int w = 0; w < kTile / 32; w++)
-     {
-        uint32_t c = ts.warp_count[w];
-        if (w < (int) warp) off += c;
-        total += c;
-     }
-   aggregate = total;
-   return off + rank;
-}
-
-// Publish this tile's aggregate and return the number of survivors in all earlier tiles
-// (warp 0 walks back 32 tiles at a time; Merrill & Garland decoupled look-back).
-__device__ __forceinline__ unsigned long long tile_exclusive_prefix (unsigned long long *status, unsigned long long tile,
-                                                                     uint32_t aggregate, TileShared &ts)
-{
-   if (threadIdx.x < 32)
-     {
-        const uint32_t lane = threadIdx.x;
-        unsigned long long excl = 0;
-        if (tile == 0)
-          {
-             if (lane == 0) st_relaxed (status, kFlagPrefix | aggregate);
-          }
-        else
-          {
-             if (lane == 0) st_relaxed (status + tile, kFlagAgg | aggregate);
-             long long j = (long long) tile - 1 - lane;          // this lane inspects tile j
-             while (true)
-               {
-                  unsigned long long w = kFlagPrefix;             // tiles before 0 behave like an empty prefix
-                  if (j >= 0)
-                    {
-                       do w = ld_relaxed (status + j); while ((w >> 62) == 0);
-                    }
-                  uint32_t is_prefix = __ballot_sync (0xffffffffu, (w >> 62) == 2);
-                  unsigned long long v = w & kValueMask;
-                  if (is_prefix)
-                    {
-                       // add aggregates of lanes closer than the first prefix, plus that prefix
-                       uint32_t first = __ffs (is_prefix) - 1;
-                       if (lane > first) v = 0;
-#pragma unroll
-                       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync (0xffffffffu, v, o);
-                       excl += v;
-                       break;
-                    }
-#pragma unroll
-                  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync (0xffffffffu, v, o);
-                  excl += v;
-                  j -= 32;
-               }
-             if (lane == 0) st_relaxed (status + tile, kFlagPrefix | (excl + aggregate));
-          }
-        if (lane == 0) ts.excl = excl;
-     }
-   __syncthreads ();
-   return ts.excl;
-}
-
-// ---------------------------------------------------------------------------------------------
 // K0: source, arrival times, dither
 // ---------------------------------------------------------------------------------------------
 // deterministic inclusive scan of one double per thread over the 256-thread tile; returns the tile total
@@ -274,141 +193,202 @@ __global__ void __launch_bounds__ (kTile) k0_source (const __grid_constant__ Sou
    o.p0[i] = p.x; o.p1[i] = p.y; o.p2[i] = p.z;
    o.time[i] = t;
    o.ray[i] = a.first_ray + i;
+   o.slot[i] = (uint32_t) i;
    o.flags[i] = 0;
    o.dra[i] = dra; o.ddec[i] = ddec; o.droll[i] = droll;
 }
 
 // ---------------------------------------------------------------------------------------------
-// shared skeleton of the persistent stage kernels
+// skeleton of the persistent stage kernels: autonomous warps + warp-private re-packing queues
 // ---------------------------------------------------------------------------------------------
-struct Carry { double time; float dra, ddec, droll; uint8_t shell; int8_t order; };
+// Every warp pulls chunks of a.chunk_tiles 32-ray tiles from a ticket counter and traces one ray per
+// lane.  Survivors are ranked with a ballot and appended to the warp's PRIVATE ring buffer in shared
+// memory; whenever 32 or more are queued the warp reserves 32 output slots with one atomicAdd and writes a
+// FULL, coalesced row of the output SoA (the carried columns are gathered from the input SoA through
+// the staged source index).  There is no block barrier and no waiting on other tiles anywhere in the
+// loop: rays die at very different depths, and in the first version (ordered decoupled look-back + block
+// barrier per tile) 20-35 % of all stall samples sat on those two waits (profiles/README.md).
+// The price is that a stage's output is no longer in arrival order; the order is restored once, by
+// restore_order below, when the list is observed (download) or at the end of marxb200_trace.
+template <int ND, int NU> struct WarpQueue { double d[ND][kQueueCap]; uint32_t u[NU][kQueueCap]; };
 
-template <class Body>
-__device__ __forceinline__ void stage_loop (const StageArgs &a, TileShared &ts, Body body)
+template <int ND, int NU, class Trace, class FlushEntry, class InPlace>
+__device__ __forceinline__ void run_stage (const StageArgs &a, WarpQueue<ND, NU> &q, Trace trace, FlushEntry flush_entry,
+                                           InPlace store_in_place)
 {
+   const uint32_t lane = threadIdx.x & 31;
    const unsigned long long n_in = *a.n_in;
+   uint32_t head = 0, count = 0;
+
+   auto flush = [&] (uint32_t n_flush)
+     {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd (a.n_out, (unsigned long long) n_flush);
+        base = __shfl_sync (0xffffffffu, base, 0);
+        if (lane < n_flush) flush_entry ((head + lane) & (kQueueCap - 1), base + lane);
+        head = (head + n_flush) & (kQueueCap - 1);
+        count -= n_flush;
+        __syncwarp ();
+     };
+
    while (true)
      {
-        __syncthreads ();
-        if (threadIdx.x == 0) ts.tile = atomicAdd (a.ticket, 1ULL);
-        __syncthreads ();
-        const unsigned long long tile = ts.tile;
-        const unsigned long long base = tile * kTile;
-        if (base >= n_in)
+        unsigned long long chunk = 0;
+        if (lane == 0) chunk = atomicAdd (a.ticket, 1ULL);
+        chunk = __shfl_sync (0xffffffffu, chunk, 0);
+        const unsigned long long base0 = chunk * (unsigned long long) (a.chunk_tiles * kWarpTile);
+        if (base0 >= n_in)
           {
-             if ((tile == 0) && (threadIdx.x == 0)) *a.n_out = 0;
+             if (!a.compact && (chunk == 0) && (lane == 0)) *a.n_out = n_in;     // n_in == 0
              break;
           }
-        const unsigned long long i = base + threadIdx.x;
-        const bool valid = i < n_in;
-        body (tile, i, valid, (base + kTile >= n_in));
+        if (!a.compact && (chunk == 0) && (lane == 0)) *a.n_out = n_in;
+#pragma unroll 1
+        for (int t = 0; t < a.chunk_tiles; t++)
+          {
+             const unsigned long long base = base0 + (unsigned long long) t * kWarpTile;
+             if (base >= n_in) break;
+             const unsigned long long i = base + lane;
+             bool active = i < n_in;
+             if (active && !a.compact) active = ((a.in.flags[i] & 0xFFu) == 0);
+             double d[ND]; uint32_t u[NU];
+             uint32_t flags = 0xFFu;
+             if (active) flags = trace (i, d, u);
+             if (a.compact)
+               {
+                  const bool alive = active && ((flags & 0xFFu) == 0);
+                  const uint32_t ballot = __ballot_sync (0xffffffffu, alive);
+                  if (alive)
+                    {
+                       const uint32_t pos = (head + count + __popc (ballot & ((1u << lane) - 1u))) & (kQueueCap - 1);
+#pragma unroll
+                       for (int k = 0; k < ND; k++) q.d[k][pos] = d[k];
+#pragma unroll
+                       for (int k = 0; k < NU; k++) q.u[k][pos] = u[k];
+                    }
+                  count += __popc (ballot);
+                  __syncwarp ();
+                  if (count >= 32) flush (32);
+               }
+             else if (active) store_in_place (i, d, u, flags);
+          }
      }
+   if (a.compact && (count > 0)) flush (count);
+}
+
+// columns a stage does not touch, gathered from the input list when a queue row is flushed
+__device__ __forceinline__ void copy_carried (const PhotonSoA &in, uint32_t src, const PhotonSoA &out, unsigned long long j)
+{
+   out.energy[j] = in.energy[src];
+   out.time[j] = in.time[src];
+   out.ray[j] = in.ray[src];
+   out.slot[j] = in.slot[src];
+   out.dra[j] = in.dra[src]; out.ddec[j] = in.ddec[src]; out.droll[j] = in.droll[src];
+}
+
+template <int ND, int NU>
+__device__ __forceinline__ WarpQueue<ND, NU> &my_queue (unsigned char *smem, uint32_t blob_bytes)
+{
+   return reinterpret_cast<WarpQueue<ND, NU> *> (smem + ((blob_bytes + 127u) & ~127u))[threadIdx.x >> 5];
 }
 
 // K1 ------------------------------------------------------------------------------------------
-// The mirror stage is three kernels (HRMA phases A, B, C of mx_hrma.cuh), each with its own fused
-// compaction, so that every phase starts with full warps although 52 % / 43 % / 33 % of its rays die.
-// State handed from phase to phase through otherwise unused SoA columns:
+// The mirror stage is three kernels (HRMA phases A, B, C of mx_hrma.cuh) so that every phase starts with
+// full warps although 52 % / 43 % / 33 % of its rays die.  State handed from phase to phase through
+// otherwise unused SoA columns:
 //   pha  (i16)  draws consumed so far on the MIRROR sub-stream | 0x4000 if a Box-Muller spare is cached
 //   aux  (f64)  the cached spare
 //   chipx, chipy, pi (f32)  beta, delta, effective-area correction (float-valued table lookups)
+template <int PHASE> struct K1Shape { static constexpr int ND = (PHASE == 1) ? 7 : 6, NU = (PHASE == 1) ? 5 : 2; };
+
 template <int PHASE>
-__global__ void __launch_bounds__ (kTile) k1_hrma (const __grid_constant__ StageArgs a)
+__global__ void __launch_bounds__ (kStageThreads) k1_hrma (const __grid_constant__ StageArgs a)
 {
+   constexpr int ND = K1Shape<PHASE>::ND, NU = K1Shape<PHASE>::NU;
    extern __shared__ __align__ (128) unsigned char smem[];
    __shared__ __align__ (8) unsigned long long bar;
-   __shared__ TileShared ts;
    stage_blob (smem, a.blob, a.blob_bytes, &bar);
    const K1Blob &B = *reinterpret_cast<const K1Blob *> (smem);
    const HrmaDev &H = B.H;
+   WarpQueue<ND, NU> &q = my_queue<ND, NU> (smem, a.blob_bytes);
+   const PhotonSoA &in = a.in, &out = a.out;
 
-   stage_loop (a, ts, [&] (unsigned long long tile, unsigned long long i, bool valid, bool last_tile)
+   auto trace = [&] (unsigned long long i, double *d, uint32_t *u) -> uint32_t
      {
-        const PhotonSoA &in = a.in, &out = a.out;
-        uint32_t flags = 0xFFu;
-        double energy = 0.0; Vec3 x = v_make (0, 0, 0), p = v_make (0, 0, 0);
-        uint32_t shell = 0; uint64_t ray = 0;
+        Vec3 x = v_make (0, 0, 0), p = v_make (in.p0[i], in.p1[i], in.p2[i]);
+        uint32_t shell = 0, flags;
         float beta = 0.f, delta = 1.f, corr = 1.f;
         Rng rng;
-        bool active = valid;
-        if (valid && !a.compact) active = ((in.flags[i] & 0xFFu) == 0);
-        if (active)
+        rng.init (a.seed, in.ray[i], MARXB200_STAGE_MIRROR);
+        if (PHASE == 0)
+          flags = hrma_phase_a (H, a.source_distance, x, p, shell, rng);
+        else
           {
-             ray = in.ray[i];
-             p = v_make (in.p0[i], in.p1[i], in.p2[i]);
-             rng.init (a.seed, ray, MARXB200_STAGE_MIRROR);
-             if (PHASE == 0)
-               flags = hrma_phase_a (H, a.source_distance, x, p, shell, rng);
+             x = v_make (in.x0[i], in.x1[i], in.x2[i]);
+             const double energy = in.energy[i];
+             shell = in.shell[i];
+             const int st = in.pha[i];
+             rng.resume ((uint32_t) (st & 0x3FFF), (st & 0x4000) ? 1 : 0, (st & 0x4000) ? in.aux[i] : 0.0);
+             if (PHASE == 1)
+               {
+                  hrma_optical_constants (H, H.shell[shell],
+                                          reinterpret_cast<const float *> (smem + B.off_opt_e),
+                                          reinterpret_cast<const float *> (smem + B.off_opt_b),
+                                          reinterpret_cast<const float *> (smem + B.off_opt_d),
+                                          reinterpret_cast<const float *> (smem + B.off_corr_e),
+                                          reinterpret_cast<const float *> (smem + B.off_corr_f),
+                                          energy, beta, delta, corr);
+                  flags = hrma_phase_b (H, shell, energy, beta, delta, corr, x, p, rng);
+               }
              else
                {
-                  x = v_make (in.x0[i], in.x1[i], in.x2[i]);
-                  energy = in.energy[i];
-                  shell = in.shell[i];
-                  const int st = in.pha[i];
-                  rng.resume ((uint32_t) (st & 0x3FFF), (st & 0x4000) ? 1 : 0, (st & 0x4000) ? in.aux[i] : 0.0);
-                  if (PHASE == 1)
-                    {
-                       hrma_optical_constants (H, H.shell[shell],
-                                               reinterpret_cast<const float *> (smem + B.off_opt_e),
-                                               reinterpret_cast<const float *> (smem + B.off_opt_b),
-                                               reinterpret_cast<const float *> (smem + B.off_opt_d),
-                                               reinterpret_cast<const float *> (smem + B.off_corr_e),
-                                               reinterpret_cast<const float *> (smem + B.off_corr_f),
-                                               energy, beta, delta, corr);
-                       flags = hrma_phase_b (H, shell, energy, beta, delta, corr, x, p, rng);
-                    }
-                  else
-                    {
-                       beta = in.chipx[i]; delta = in.chipy[i]; corr = in.pi[i];
-                       flags = hrma_phase_c (H, shell, energy, beta, delta, corr, x, p, rng);
-                    }
+                  beta = in.chipx[i]; delta = in.chipy[i]; corr = in.pi[i];
+                  flags = hrma_phase_c (H, shell, energy, beta, delta, corr, x, p, rng);
                }
           }
-        const int16_t rng_state = (int16_t) ((rng.draw & 0x3FFFu) | (rng.have_spare ? 0x4000u : 0u));
-        unsigned long long j = i;
-        bool write = active;
-        if (a.compact)
+        d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = p.x; d[4] = p.y; d[5] = p.z;
+        u[0] = (uint32_t) i;
+        u[1] = shell | (((rng.draw & 0x3FFFu) | (rng.have_spare ? 0x4000u : 0u)) << 8);
+        if (PHASE == 1)
           {
-             const bool alive = active && (flags == 0);
-             uint32_t aggregate;
-             uint32_t rank = block_rank (alive, ts, aggregate);
-             unsigned long long excl = tile_exclusive_prefix (a.tile_status, tile, aggregate, ts);
-             j = excl + rank;
-             write = alive;
-             if (alive)
-               {
-                  // payload carried through the stage untouched
-                  out.time[j] = in.time[i];
-                  out.ray[j] = ray;
-                  out.dra[j] = in.dra[i]; out.ddec[j] = in.ddec[i]; out.droll[j] = in.droll[i];
-                  out.energy[j] = (PHASE == 0) ? in.energy[i] : energy;
-                  out.shell[j] = (uint8_t) shell;
-               }
-             if (last_tile && (threadIdx.x == 0)) *a.n_out = excl + aggregate;
+             d[ND - 1] = rng.spare;
+             u[NU - 3] = __float_as_uint (beta); u[NU - 2] = __float_as_uint (delta); u[NU - 1] = __float_as_uint (corr);
           }
-        else if (last_tile && (threadIdx.x == 0)) *a.n_out = *a.n_in;
-        if (write)
+        return flags;
+     };
+   auto write_row = [&] (unsigned long long j, const double *d, const uint32_t *u, uint32_t flags)
+     {
+        out.x0[j] = d[0]; out.x1[j] = d[1]; out.x2[j] = d[2];
+        out.p0[j] = d[3]; out.p1[j] = d[4]; out.p2[j] = d[5];
+        out.flags[j] = flags;
+        out.shell[j] = (uint8_t) (u[1] & 0xFFu);
+        if (PHASE < 2) out.pha[j] = (int16_t) (u[1] >> 8);
+        if (PHASE == 1)
           {
-             out.x0[j] = x.x; out.x1[j] = x.y; out.x2[j] = x.z;
-             out.p0[j] = p.x; out.p1[j] = p.y; out.p2[j] = p.z;
-             out.flags[j] = flags;
-             if ((PHASE == 0) && !a.compact) out.shell[j] = (uint8_t) shell;
-             if (PHASE < 2)
-               {
-                  out.pha[j] = rng_state;
-                  if (rng.have_spare) out.aux[j] = rng.spare;
-               }
-             if (PHASE == 1) { out.chipx[j] = beta; out.chipy[j] = delta; out.pi[j] = corr; }
+             out.aux[j] = d[ND - 1];
+             out.chipx[j] = __uint_as_float (u[NU - 3]); out.chipy[j] = __uint_as_float (u[NU - 2]); out.pi[j] = __uint_as_float (u[NU - 1]);
           }
-     });
+     };
+   auto flush_entry = [&] (uint32_t pos, unsigned long long j)
+     {
+        double d[ND]; uint32_t u[NU];
+#pragma unroll
+        for (int k = 0; k < ND; k++) d[k] = q.d[k][pos];
+#pragma unroll
+        for (int k = 0; k < NU; k++) u[k] = q.u[k][pos];
+        write_row (j, d, u, 0);
+        copy_carried (in, u[0], out, j);
+     };
+   auto in_place = [&] (unsigned long long i, const double *d, const uint32_t *u, uint32_t flags) { write_row (i, d, u, flags); };
+   run_stage<ND, NU> (a, q, trace, flush_entry, in_place);
 }
 
 // K2 ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__ (kTile) k2_grating (const __grid_constant__ StageArgs a)
+__global__ void __launch_bounds__ (kStageThreads) k2_grating (const __grid_constant__ StageArgs a)
 {
+   constexpr int ND = 6, NU = 2;
    extern __shared__ __align__ (128) unsigned char smem[];
    __shared__ __align__ (8) unsigned long long bar;
-   __shared__ TileShared ts;
    stage_blob (smem, a.blob, a.blob_bytes, &bar);
    // the shell descriptors hold global pointers for the big tables; sector tables are re-pointed to smem
    K2Blob &B = *reinterpret_cast<K2Blob *> (smem);
@@ -416,119 +396,171 @@ __global__ void __launch_bounds__ (kTile) k2_grating (const __grid_constant__ St
      B.G.shell[threadIdx.x].sectors = reinterpret_cast<const double *> (smem + B.off_sectors[threadIdx.x]);
    __syncthreads ();
    const GratingDev &G = B.G;
+   WarpQueue<ND, NU> &q = my_queue<ND, NU> (smem, a.blob_bytes);
+   const PhotonSoA &in = a.in, &out = a.out;
 
-   stage_loop (a, ts, [&] (unsigned long long tile, unsigned long long i, bool valid, bool last_tile)
+   auto trace = [&] (unsigned long long i, double *d, uint32_t *u) -> uint32_t
      {
-        const PhotonSoA &in = a.in, &out = a.out;
-        uint32_t flags = 0xFFu;
-        double energy = 0.0; Vec3 x = v_make (0, 0, 0), p = v_make (0, 0, 0);
-        uint32_t shell = 0; uint64_t ray = 0; int order = 0;
-        bool active = valid;
-        if (valid && !a.compact) active = ((in.flags[i] & 0xFFu) == 0);
-        if (active)
-          {
-             energy = in.energy[i];
-             x = v_make (in.x0[i], in.x1[i], in.x2[i]);
-             p = v_make (in.p0[i], in.p1[i], in.p2[i]);
-             shell = in.shell[i];
-             ray = in.ray[i];
-             Rng rng; rng.init (a.seed, ray, MARXB200_STAGE_GRATING);
-             flags = grating_diffract (G, shell, energy, x, p, order, rng);
-          }
-        if (a.compact)
-          {
-             const bool alive = active && (flags == 0);
-             uint32_t aggregate;
-             uint32_t rank = block_rank (alive, ts, aggregate);
-             unsigned long long excl = tile_exclusive_prefix (a.tile_status, tile, aggregate, ts);
-             if (alive)
-               {
-                  const unsigned long long j = excl + rank;
-                  out.energy[j] = energy;
-                  out.x0[j] = x.x; out.x1[j] = x.y; out.x2[j] = x.z;
-                  out.p0[j] = p.x; out.p1[j] = p.y; out.p2[j] = p.z;
-                  out.time[j] = in.time[i];
-                  out.ray[j] = ray;
-                  out.flags[j] = 0;
-                  out.dra[j] = in.dra[i]; out.ddec[j] = in.ddec[i]; out.droll[j] = in.droll[i];
-                  out.shell[j] = (uint8_t) shell;
-                  out.order[j] = (int8_t) order;
-               }
-             if (last_tile && (threadIdx.x == 0)) *a.n_out = excl + aggregate;
-          }
-        else if (active)
-          {
-             out.x0[i] = x.x; out.x1[i] = x.y; out.x2[i] = x.z;
-             out.p0[i] = p.x; out.p1[i] = p.y; out.p2[i] = p.z;
-             out.flags[i] = flags;
-             out.order[i] = (int8_t) order;
-          }
-        if (!a.compact && last_tile && (threadIdx.x == 0)) *a.n_out = *a.n_in;
-     });
+        Vec3 x = v_make (in.x0[i], in.x1[i], in.x2[i]), p = v_make (in.p0[i], in.p1[i], in.p2[i]);
+        int order = 0;
+        Rng rng;
+        rng.init (a.seed, in.ray[i], MARXB200_STAGE_GRATING);
+        uint32_t flags = grating_diffract (G, in.shell[i], in.energy[i], x, p, order, rng);
+        d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = p.x; d[4] = p.y; d[5] = p.z;
+        u[0] = (uint32_t) i;
+        u[1] = (uint32_t) (order & 0xFF);
+        return flags;
+     };
+   auto write_row = [&] (unsigned long long j, const double *d, const uint32_t *u, uint32_t flags)
+     {
+        out.x0[j] = d[0]; out.x1[j] = d[1]; out.x2[j] = d[2];
+        out.p0[j] = d[3]; out.p1[j] = d[4]; out.p2[j] = d[5];
+        out.flags[j] = flags;
+        out.order[j] = (int8_t) (u[1] & 0xFFu);
+     };
+   auto flush_entry = [&] (uint32_t pos, unsigned long long j)
+     {
+        double d[ND]; uint32_t u[NU];
+#pragma unroll
+        for (int k = 0; k < ND; k++) d[k] = q.d[k][pos];
+#pragma unroll
+        for (int k = 0; k < NU; k++) u[k] = q.u[k][pos];
+        write_row (j, d, u, 0);
+        copy_carried (in, u[0], out, j);
+        out.shell[j] = in.shell[u[0]];
+     };
+   auto in_place = [&] (unsigned long long i, const double *d, const uint32_t *u, uint32_t flags) { write_row (i, d, u, flags); };
+   run_stage<ND, NU> (a, q, trace, flush_entry, in_place);
 }
 
 // K3 ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__ (kTile) k3_acis (const __grid_constant__ StageArgs a)
+__global__ void __launch_bounds__ (kStageThreads) k3_acis (const __grid_constant__ StageArgs a)
 {
+   constexpr int ND = 6, NU = 6;
    extern __shared__ __align__ (128) unsigned char smem[];
    __shared__ __align__ (8) unsigned long long bar;
-   __shared__ TileShared ts;
    stage_blob (smem, a.blob, a.blob_bytes, &bar);
    const AcisDev &A = reinterpret_cast<const K3Blob *> (smem)->A;
+   WarpQueue<ND, NU> &q = my_queue<ND, NU> (smem, a.blob_bytes);
+   const PhotonSoA &in = a.in, &out = a.out;
 
-   stage_loop (a, ts, [&] (unsigned long long tile, unsigned long long i, bool valid, bool last_tile)
+   auto trace = [&] (unsigned long long i, double *d, uint32_t *u) -> uint32_t
      {
-        const PhotonSoA &in = a.in, &out = a.out;
-        uint32_t flags = 0xFFu;
-        double energy = 0.0, t_abs = 0.0; Vec3 x = v_make (0, 0, 0), p = v_make (0, 0, 0);
-        uint64_t ray = 0; int ccd = -1; float chipx = 0, chipy = 0, pi = 0; int16_t pha = 0;
-        bool active = valid;
-        if (valid && !a.compact) active = ((in.flags[i] & 0xFFu) == 0);
-        if (active)
-          {
-             energy = in.energy[i];
-             x = v_make (in.x0[i], in.x1[i], in.x2[i]);
-             p = v_make (in.p0[i], in.p1[i], in.p2[i]);
-             t_abs = in.time[i];
-             ray = in.ray[i];
-             Rng rng; rng.init (a.seed, ray, MARXB200_STAGE_DETECTOR);
-             flags = acis_detect (A, energy, t_abs, x, p, ccd, chipx, chipy, pha, pi, rng);
-          }
-        if (a.compact)
-          {
-             const bool alive = active && ((flags & 0xFFu) == 0);
-             uint32_t aggregate;
-             uint32_t rank = block_rank (alive, ts, aggregate);
-             unsigned long long excl = tile_exclusive_prefix (a.tile_status, tile, aggregate, ts);
-             if (alive)
-               {
-                  const unsigned long long j = excl + rank;
-                  out.energy[j] = energy;
-                  out.x0[j] = x.x; out.x1[j] = x.y; out.x2[j] = x.z;
-                  out.p0[j] = p.x; out.p1[j] = p.y; out.p2[j] = p.z;
-                  out.time[j] = t_abs;
-                  out.ray[j] = ray;
-                  out.flags[j] = flags;
-                  out.dra[j] = in.dra[i]; out.ddec[j] = in.ddec[i]; out.droll[j] = in.droll[i];
-                  out.shell[j] = in.shell[i];
-                  out.order[j] = in.order[i];
-                  out.ccd[j] = (int8_t) ccd;
-                  out.chipx[j] = chipx; out.chipy[j] = chipy;
-                  out.pha[j] = pha; out.pi[j] = pi;
-               }
-             if (last_tile && (threadIdx.x == 0)) *a.n_out = excl + aggregate;
-          }
-        else if (active)
-          {
-             out.x0[i] = x.x; out.x1[i] = x.y; out.x2[i] = x.z;
-             out.p0[i] = p.x; out.p1[i] = p.y; out.p2[i] = p.z;
-             out.flags[i] = flags;
-             out.ccd[i] = (int8_t) ccd;
-             out.chipx[i] = chipx; out.chipy[i] = chipy;
-             out.pha[i] = pha; out.pi[i] = pi;
-          }
-        if (!a.compact && last_tile && (threadIdx.x == 0)) *a.n_out = *a.n_in;
-     });
+        Vec3 x = v_make (in.x0[i], in.x1[i], in.x2[i]), p = v_make (in.p0[i], in.p1[i], in.p2[i]);
+        int ccd = -1; float chipx = 0, chipy = 0, pi = 0; int16_t pha = 0;
+        Rng rng;
+        rng.init (a.seed, in.ray[i], MARXB200_STAGE_DETECTOR);
+        uint32_t flags = acis_detect (A, in.energy[i], in.time[i], x, p, ccd, chipx, chipy, pha, pi, rng);
+        d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = p.x; d[4] = p.y; d[5] = p.z;
+        u[0] = (uint32_t) i;
+        u[1] = flags;
+        u[2] = ((uint32_t) (ccd & 0xFF)) | (((uint32_t) (uint16_t) pha) << 8);
+        u[3] = __float_as_uint (chipx); u[4] = __float_as_uint (chipy); u[5] = __float_as_uint (pi);
+        return flags;
+     };
+   auto write_row = [&] (unsigned long long j, const double *d, const uint32_t *u)
+     {
+        out.x0[j] = d[0]; out.x1[j] = d[1]; out.x2[j] = d[2];
+        out.p0[j] = d[3]; out.p1[j] = d[4]; out.p2[j] = d[5];
+        out.flags[j] = u[1];
+        out.ccd[j] = (int8_t) (u[2] & 0xFFu);
+        out.pha[j] = (int16_t) (uint16_t) (u[2] >> 8);
+        out.chipx[j] = __uint_as_float (u[3]); out.chipy[j] = __uint_as_float (u[4]); out.pi[j] = __uint_as_float (u[5]);
+     };
+   auto flush_entry = [&] (uint32_t pos, unsigned long long j)
+     {
+        double d[ND]; uint32_t u[NU];
+#pragma unroll
+        for (int k = 0; k < ND; k++) d[k] = q.d[k][pos];
+#pragma unroll
+        for (int k = 0; k < NU; k++) u[k] = q.u[k][pos];
+        write_row (j, d, u);
+        copy_carried (in, u[0], out, j);
+        out.shell[j] = in.shell[u[0]];
+        out.order[j] = in.order[u[0]];
+     };
+   auto in_place = [&] (unsigned long long i, const double *d, const uint32_t *u, uint32_t) { write_row (i, d, u); };
+   run_stage<ND, NU> (a, q, trace, flush_entry, in_place);
+}
+
+// ---------------------------------------------------------------------------------------------
+// arrival-order restoration: the live list's `slot` keys are distinct indices into the batch, so the rank
+// of a photon is the number of set bits below its slot in a bitmap of the live slots.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__ (256) order_mark (OrderArgs a)
+{
+   const unsigned long long n = *a.n_live;
+   for (unsigned long long s = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (unsigned long long) gridDim.x * blockDim.x)
+     {
+        const uint32_t key = a.in.slot[s];
+        atomicOr (a.bitmap + (key >> 5), 1u << (key & 31u));
+     }
+}
+// one block per 1024 bitmap words: exclusive popcount prefix inside the block + the block total
+__global__ void __launch_bounds__ (256) order_scan_words (OrderArgs a, uint32_t n_words)
+{
+   __shared__ uint32_t warp_tot[8];
+   const uint32_t w0 = blockIdx.x * 1024u + threadIdx.x * 4u;
+   uint32_t c[4], sum = 0;
+#pragma unroll
+   for (int k = 0; k < 4; k++) { c[k] = (w0 + k < n_words) ? __popc (a.bitmap[w0 + k]) : 0u; sum += c[k]; }
+   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+   uint32_t incl = sum;
+#pragma unroll
+   for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync (0xffffffffu, incl, o); if (lane >= (uint32_t) o) incl += v; }
+   if (lane == 31) warp_tot[warp] = incl;
+   __syncthreads ();
+   uint32_t off = 0, tot = 0;
+#pragma unroll
+   for (int w = 0; w < 8; w++) { if (w < (int) warp) off += warp_tot[w]; tot += warp_tot[w]; }
+   uint32_t run = off + incl - sum;
+#pragma unroll
+   for (int k = 0; k < 4; k++) { if (w0 + k < n_words) a.word_prefix[w0 + k] = run; run += c[k]; }
+   if (threadIdx.x == 0) a.block_prefix[blockIdx.x] = tot;
+}
+// one block: exclusive scan of the block totals (sequential chunks per thread, then a warp/block scan)
+__global__ void __launch_bounds__ (1024) order_scan_blocks (OrderArgs a, uint32_t n_blocks)
+{
+   __shared__ uint32_t part[1024];
+   const uint32_t per = (n_blocks + 1023u) / 1024u;
+   const uint32_t b0 = threadIdx.x * per;
+   uint32_t sum = 0;
+   for (uint32_t k = 0; k < per; k++) if (b0 + k < n_blocks) sum += a.block_prefix[b0 + k];
+   part[threadIdx.x] = sum;
+   __syncthreads ();
+   if (threadIdx.x == 0) { uint32_t acc = 0; for (int t = 0; t < 1024; t++) { uint32_t v = part[t]; part[t] = acc; acc += v; } }
+   __syncthreads ();
+   uint32_t acc = part[threadIdx.x];
+   for (uint32_t k = 0; k < per; k++) if (b0 + k < n_blocks) { uint32_t v = a.block_prefix[b0 + k]; a.block_prefix[b0 + k] = acc; acc += v; }
+}
+__global__ void __launch_bounds__ (256) order_scatter (OrderArgs a)
+{
+   const unsigned long long n = *a.n_live;
+   const PhotonSoA &in = a.in, &out = a.out;
+   for (unsigned long long s = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (unsigned long long) gridDim.x * blockDim.x)
+     {
+        const uint32_t key = in.slot[s], w = key >> 5;
+        const unsigned long long j = (unsigned long long) a.block_prefix[w >> 10] + a.word_prefix[w]
+                                     + __popc (a.bitmap[w] & ((1u << (key & 31u)) - 1u));
+        out.energy[j] = in.energy[s];
+        out.x0[j] = in.x0[s]; out.x1[j] = in.x1[s]; out.x2[j] = in.x2[s];
+        out.p0[j] = in.p0[s]; out.p1[j] = in.p1[s]; out.p2[j] = in.p2[s];
+        out.time[j] = in.time[s]; out.aux[j] = in.aux[s];
+        out.ray[j] = in.ray[s]; out.slot[j] = key; out.flags[j] = in.flags[s];
+        out.dra[j] = in.dra[s]; out.ddec[j] = in.ddec[s]; out.droll[j] = in.droll[s];
+        out.chipx[j] = in.chipx[s]; out.chipy[j] = in.chipy[s]; out.pi[j] = in.pi[s];
+        out.pha[j] = in.pha[s]; out.shell[j] = in.shell[s]; out.order[j] = in.order[s]; out.ccd[j] = in.ccd[s];
+     }
+}
+void launch_restore_order (const OrderArgs &a, int num_sms, cudaStream_t s, int *n_launches)
+{
+   const uint32_t n_words = (uint32_t) (a.n_slots / 32 + 1), n_blocks = (n_words + 1023u) / 1024u;
+   const int grid = num_sms * 8;
+   order_mark<<<grid, 256, 0, s>>> (a);
+   order_scan_words<<<n_blocks, 256, 0, s>>> (a, n_words);
+   order_scan_blocks<<<1, 1024, 0, s>>> (a, n_blocks);
+   order_scatter<<<grid, 256, 0, s>>> (a);
+   if (n_launches) *n_launches = 4;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -581,6 +613,7 @@ __global__ void __launch_bounds__ (256) aos_to_soa (const marxb200_photon_attr *
         out.p0[i] = r.p[0]; out.p1[i] = r.p[1]; out.p2[i] = r.p[2];
         out.time[i] = r.arrival_time + start_time;
         out.ray[i] = ray_ids ? ray_ids[i] : (uint64_t) r.tag;
+        out.slot[i] = (uint32_t) i;
         out.flags[i] = r.flags;
         out.dra[i] = r.dither_ra; out.ddec[i] = r.dither_dec; out.droll[i] = r.dither_roll;
         out.chipx[i] = r.y_pixel; out.chipy[i] = r.z_pixel; out.pi[i] = r.pi;
@@ -611,38 +644,53 @@ void launch_source (const SourceArgs &a, cudaStream_t s)
    k0_source<<<n_tiles_of (a.n), kTile, 0, s>>> (a);
 }
 
+uint32_t stage_smem_bytes (int stage, uint32_t blob_bytes)
+{
+   const uint32_t warps = kStageThreads / 32, base = (blob_bytes + 127u) & ~127u;
+   switch (stage)
+     {
+      case 10: return base + warps * (uint32_t) sizeof (WarpQueue<K1Shape<0>::ND, K1Shape<0>::NU>);
+      case 11: return base + warps * (uint32_t) sizeof (WarpQueue<K1Shape<1>::ND, K1Shape<1>::NU>);
+      case 12: return base + warps * (uint32_t) sizeof (WarpQueue<K1Shape<2>::ND, K1Shape<2>::NU>);
+      case 2: return base + warps * (uint32_t) sizeof (WarpQueue<6, 2>);
+      case 3: return base + warps * (uint32_t) sizeof (WarpQueue<6, 6>);
+     }
+   return base;
+}
 template <class K>
 static int occupancy_grid (K kernel, int num_sms, uint32_t smem_bytes)
 {
    int per_sm = 1;
    cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes);
-   cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, kernel, kTile, smem_bytes);
+   cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, kernel, kStageThreads, smem_bytes);
    if (per_sm < 1) per_sm = 1;
    return per_sm * num_sms;
 }
 int stage_grid_size (int stage, int num_sms, uint32_t blob_bytes)
 {
+   const uint32_t smem = stage_smem_bytes (stage, blob_bytes);
    switch (stage)
      {
-      case 10: return occupancy_grid (k1_hrma<0>, num_sms, blob_bytes);
-      case 11: return occupancy_grid (k1_hrma<1>, num_sms, blob_bytes);
-      case 12: return occupancy_grid (k1_hrma<2>, num_sms, blob_bytes);
-      case 2: return occupancy_grid (k2_grating, num_sms, blob_bytes);
-      case 3: return occupancy_grid (k3_acis, num_sms, blob_bytes);
+      case 10: return occupancy_grid (k1_hrma<0>, num_sms, smem);
+      case 11: return occupancy_grid (k1_hrma<1>, num_sms, smem);
+      case 12: return occupancy_grid (k1_hrma<2>, num_sms, smem);
+      case 2: return occupancy_grid (k2_grating, num_sms, smem);
+      case 3: return occupancy_grid (k3_acis, num_sms, smem);
      }
    return num_sms;
 }
 void launch_hrma (const StageArgs &a, int phase, int grid, cudaStream_t s)
 {
+   const uint32_t smem = stage_smem_bytes (10 + phase, a.blob_bytes);
    switch (phase)
      {
-      case 0: k1_hrma<0><<<grid, kTile, a.blob_bytes, s>>> (a); break;
-      case 1: k1_hrma<1><<<grid, kTile, a.blob_bytes, s>>> (a); break;
-      default: k1_hrma<2><<<grid, kTile, a.blob_bytes, s>>> (a); break;
+      case 0: k1_hrma<0><<<grid, kStageThreads, smem, s>>> (a); break;
+      case 1: k1_hrma<1><<<grid, kStageThreads, smem, s>>> (a); break;
+      default: k1_hrma<2><<<grid, kStageThreads, smem, s>>> (a); break;
      }
 }
-void launch_grating (const StageArgs &a, int grid, cudaStream_t s) { k2_grating<<<grid, kTile, a.blob_bytes, s>>> (a); }
-void launch_acis (const StageArgs &a, int grid, cudaStream_t s) { k3_acis<<<grid, kTile, a.blob_bytes, s>>> (a); }
+void launch_grating (const StageArgs &a, int grid, cudaStream_t s) { k2_grating<<<grid, kStageThreads, stage_smem_bytes (2, a.blob_bytes), s>>> (a); }
+void launch_acis (const StageArgs &a, int grid, cudaStream_t s) { k3_acis<<<grid, kStageThreads, stage_smem_bytes (3, a.blob_bytes), s>>> (a); }
 
 void launch_soa_to_aos (const PhotonSoA &in, const unsigned long long *n, uint64_t max_n, void *aos,
                         const double *dev_start_time, cudaStream_t s)

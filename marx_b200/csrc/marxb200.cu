@@ -54,8 +54,9 @@ struct marxb200_ctx
    // device scalars: counts[0..3] + ticket + total_time
    unsigned long long *d_counts = nullptr;      // [8]: generated, after mirror, after grating, detected, after k1a, after k1b
    unsigned long long *d_ticket = nullptr;      // [4]: one ticket counter per kernel of a stage call
-   unsigned long long *d_tile_status = nullptr; // [3][n_status]: look-back words, one array per kernel of a stage call
-   uint64_t n_status = 0;
+   uint32_t *d_bitmap = nullptr, *d_word_prefix = nullptr, *d_block_prefix = nullptr;   // order restoration scratch
+   uint64_t n_words = 0;
+   bool ordered = true;                          // live list is in arrival order
    double *d_tile_sums = nullptr, *d_tile_base = nullptr, *d_super_sums = nullptr, *d_times = nullptr;   // d_times: [batch start, running end]
    int stage_done = -1;                          // index into d_counts of the latest valid count
    uint64_t n_generated = 0;
@@ -160,7 +161,9 @@ extern "C" int marxb200_destroy (marxb200_ctx *c)
    for (void *p : c->allocs) cudaFree (p);
    for (int i = 0; i < 2; i++) if (c->slab[i]) cudaFree (c->slab[i]);
    cudaFree (c->d_counts); cudaFree (c->d_ticket); cudaFree (c->d_times);
-   if (c->d_tile_status) cudaFree (c->d_tile_status);
+   if (c->d_bitmap) cudaFree (c->d_bitmap);
+   if (c->d_word_prefix) cudaFree (c->d_word_prefix);
+   if (c->d_block_prefix) cudaFree (c->d_block_prefix);
    if (c->d_tile_sums) cudaFree (c->d_tile_sums);
    if (c->d_tile_base) cudaFree (c->d_tile_base);
    if (c->d_super_sums) cudaFree (c->d_super_sums);
@@ -313,6 +316,7 @@ static size_t carve (PhotonSoA &b, unsigned char *base, uint64_t n)
    b.time = (double *) take (8);
    b.aux = (double *) take (8);
    b.ray = (uint64_t *) take (8);
+   b.slot = (uint32_t *) take (4);
    b.flags = (uint32_t *) take (4);
    b.dra = (float *) take (4); b.ddec = (float *) take (4); b.droll = (float *) take (4);
    b.chipx = (float *) take (4); b.chipy = (float *) take (4); b.pi = (float *) take (4);
@@ -329,7 +333,9 @@ extern "C" int marxb200_alloc_photons (marxb200_ctx *c, uint64_t max_photons)
    CUDA_OK (cudaSetDevice (c->device));
    CUDA_OK (cudaStreamSynchronize (c->stream));
    for (int i = 0; i < 2; i++) if (c->slab[i]) { cudaFree (c->slab[i]); c->slab[i] = nullptr; }
-   if (c->d_tile_status) cudaFree (c->d_tile_status);
+   if (c->d_bitmap) cudaFree (c->d_bitmap);
+   if (c->d_word_prefix) cudaFree (c->d_word_prefix);
+   if (c->d_block_prefix) cudaFree (c->d_block_prefix);
    if (c->d_tile_sums) cudaFree (c->d_tile_sums);
    if (c->d_tile_base) cudaFree (c->d_tile_base);
    if (c->d_super_sums) cudaFree (c->d_super_sums);
@@ -343,14 +349,16 @@ extern "C" int marxb200_alloc_photons (marxb200_ctx *c, uint64_t max_photons)
      }
    uint64_t n_tiles = (max_photons + kTile - 1) / kTile + 1;
    uint64_t n_super = (n_tiles + kSuperTile - 1) / kSuperTile + 1;
-   c->n_status = n_tiles;
-   CUDA_OK (cudaMalloc (&c->d_tile_status, 3 * n_tiles * sizeof (unsigned long long)));
+   c->n_words = max_photons / 32 + 1;
+   CUDA_OK (cudaMalloc (&c->d_bitmap, c->n_words * sizeof (uint32_t)));
+   CUDA_OK (cudaMalloc (&c->d_word_prefix, c->n_words * sizeof (uint32_t)));
+   CUDA_OK (cudaMalloc (&c->d_block_prefix, (c->n_words / 1024 + 2) * sizeof (uint32_t)));
    CUDA_OK (cudaMalloc (&c->d_tile_sums, n_tiles * sizeof (double)));
    CUDA_OK (cudaMalloc (&c->d_tile_base, n_tiles * sizeof (double)));
    CUDA_OK (cudaMalloc (&c->d_super_sums, n_super * sizeof (double)));
    CUDA_OK (cudaStreamSynchronize (c->stream));
    c->capacity = max_photons;
-   c->cur = 0; c->stage_done = -1; c->n_generated = 0;
+   c->cur = 0; c->stage_done = -1; c->n_generated = 0; c->ordered = true;
    return 0;
 }
 
@@ -383,7 +391,7 @@ extern "C" int marxb200_create_photons (marxb200_ctx *c, uint64_t first_ray, uin
    launch_source (a, c->stream);
    c->launches += 3;
    CUDA_OK (cudaGetLastError ());
-   c->cur = 0; c->stage_done = 0; c->n_generated = n;
+   c->cur = 0; c->stage_done = 0; c->n_generated = n; c->ordered = true;
    return 0;
 }
 
@@ -420,14 +428,15 @@ static int run_stage (marxb200_ctx *c, int stage)
    a.seed = c->seed;
    a.compact = c->compact;
    a.source_distance = c->source_distance;
-   // the mirror stage runs as three kernels (HRMA phases A, B, C, mx_hrma.cuh) with a compaction after each
+   // the mirror stage runs as three kernels (HRMA phases A, B, C, mx_hrma.cuh), each re-packing its survivors
    const int n_kernels = (stage == 1) ? 3 : 1;
-   uint64_t n_tiles = (c->n_generated + kTile - 1) / kTile + 1;
-   if (n_tiles > c->n_status) n_tiles = c->n_status;
    CUDA_OK (cudaMemsetAsync (c->d_ticket, 0, 4 * sizeof (unsigned long long), c->stream));
    if (c->compact)
-     for (int k = 0; k < n_kernels; k++)
-       CUDA_OK (cudaMemsetAsync (c->d_tile_status + k * c->n_status, 0, n_tiles * sizeof (unsigned long long), c->stream));
+     {
+        // output counters grow by atomics: zero them (d_counts[4], [5] = after k1a, k1b; d_counts[stage] = stage output)
+        CUDA_OK (cudaMemsetAsync (c->d_counts + stage, 0, sizeof (unsigned long long), c->stream));
+        if (stage == 1) CUDA_OK (cudaMemsetAsync (c->d_counts + 4, 0, 2 * sizeof (unsigned long long), c->stream));
+     }
    const unsigned long long *n_in = c->d_counts + c->stage_done;
    for (int k = 0; k < n_kernels; k++)
      {
@@ -436,7 +445,8 @@ static int run_stage (marxb200_ctx *c, int stage)
         a.n_in = n_in;
         a.n_out = (k == n_kernels - 1) ? c->d_counts + stage : c->d_counts + 4 + k;
         a.ticket = c->d_ticket + k;
-        a.tile_status = c->d_tile_status + k * c->n_status;
+        // big inputs amortise the ticket atomic over several tiles; small ones need fine-grained balancing
+        a.chunk_tiles = (stage == 1 && k == 0) ? 4 : ((stage == 1 && k == 1) ? 2 : 1);
         switch (stage)
           {
            case 1: a.blob = c->blob1; a.blob_bytes = c->blob1_bytes; launch_hrma (a, k, c->grid1[k], c->stream); break;
@@ -448,7 +458,28 @@ static int run_stage (marxb200_ctx *c, int stage)
         if (c->compact) c->cur = 1 - c->cur;
         n_in = a.n_out;
      }
+   if (c->compact) c->ordered = false;
    c->stage_done = stage;
+   return 0;
+}
+
+// Bring the live list back into arrival order (the compacting stage kernels emit survivors in completion
+// order).  Called lazily before the list is observed and at the end of marxb200_trace.
+static int ensure_order (marxb200_ctx *c)
+{
+   if (c->ordered || (c->stage_done <= 0)) { c->ordered = true; return 0; }
+   OrderArgs o;
+   o.in = c->buf[c->cur]; o.out = c->buf[1 - c->cur];
+   o.n_live = c->d_counts + c->stage_done;
+   o.n_slots = c->n_generated;
+   o.bitmap = c->d_bitmap; o.word_prefix = c->d_word_prefix; o.block_prefix = c->d_block_prefix;
+   CUDA_OK (cudaMemsetAsync (c->d_bitmap, 0, (c->n_generated / 32 + 1) * sizeof (uint32_t), c->stream));
+   int nl = 0;
+   launch_restore_order (o, c->num_sms, c->stream, &nl);
+   c->launches += nl;
+   CUDA_OK (cudaGetLastError ());
+   c->cur = 1 - c->cur;
+   c->ordered = true;
    return 0;
 }
 
@@ -489,13 +520,20 @@ extern "C" int marxb200_detect (marxb200_ctx *c)
    return run_stage (c, 3);
 }
 
+extern "C" int marxb200_restore_order (marxb200_ctx *c)
+{
+   if (c == nullptr) return fail ("NULL ctx");
+   CUDA_OK (cudaSetDevice (c->device));
+   return ensure_order (c);
+}
+
 extern "C" int marxb200_trace (marxb200_ctx *c, uint64_t first_ray, uint64_t n)
 {
    if (-1 == marxb200_create_photons (c, first_ray, n, -1.0)) return -1;
    if (-1 == marxb200_mirror_reflect (c)) return -1;
    if (-1 == marxb200_grating_diffract (c)) return -1;
    if (-1 == marxb200_detect (c)) return -1;
-   return 0;
+   return ensure_order (c);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -531,6 +569,7 @@ static int download_impl (marxb200_ctx *c, marxb200_photon_attr *out, uint64_t m
    if ((c == nullptr) || (out == nullptr)) return fail ("download: NULL argument");
    if (c->stage_done < 0) { if (n_out) *n_out = 0; return 0; }
    CUDA_OK (cudaSetDevice (c->device));
+   if (-1 == ensure_order (c)) return -1;
    unsigned long long n = 0;
    CUDA_OK (cudaMemcpyAsync (&n, c->d_counts + c->stage_done, sizeof (n), cudaMemcpyDeviceToHost, c->stream));
    CUDA_OK (cudaStreamSynchronize (c->stream));
@@ -576,7 +615,7 @@ extern "C" int marxb200_upload (marxb200_ctx *c, const marxb200_photon_attr *in,
    CUDA_OK (cudaMemcpyAsync (c->d_counts + 0, &nn, sizeof (nn), cudaMemcpyHostToDevice, c->stream));
    CUDA_OK (cudaStreamSynchronize (c->stream));
    if (d_ids) cudaFree (d_ids);
-   c->stage_done = 0; c->n_generated = n;
+   c->stage_done = 0; c->n_generated = n; c->ordered = true;
    return 0;
 }
 
@@ -585,6 +624,7 @@ extern "C" int marxb200_download_columns (marxb200_ctx *c, const marxb200_column
    if ((c == nullptr) || (cols == nullptr)) return fail ("marxb200_download_columns: NULL argument");
    if (c->stage_done < 0) { if (n_out) *n_out = 0; return 0; }
    CUDA_OK (cudaSetDevice (c->device));
+   if (-1 == ensure_order (c)) return -1;
    unsigned long long n = 0;
    CUDA_OK (cudaMemcpyAsync (&n, c->d_counts + c->stage_done, sizeof (n), cudaMemcpyDeviceToHost, c->stream));
    CUDA_OK (cudaStreamSynchronize (c->stream));

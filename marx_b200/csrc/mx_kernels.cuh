@@ -6,7 +6,13 @@
 
 namespace mx {
 
-constexpr int kTile = 256;               // rays per tile == threads per CTA
+constexpr int kTile = 256;               // K0: rays per tile == threads per CTA (also the unit of the canonical time sum)
+#ifndef MX_STAGE_THREADS
+#define MX_STAGE_THREADS 256
+#endif
+constexpr int kStageThreads = MX_STAGE_THREADS;   // K1..K3: threads per persistent CTA (warps are autonomous)
+constexpr int kWarpTile = 32;            // rays per warp tile
+constexpr int kQueueCap = 64;            // entries of a warp's staging queue
 constexpr int kSuperTile = 256;          // tiles per super-tile of the canonical arrival-time sum
 
 // Structure-of-arrays photon buffer in HBM (replaces Marx_Photon_Attr_Type[], marx.h:51-100).
@@ -18,6 +24,7 @@ struct PhotonSoA
    double *time;                         // absolute: pt->start_time + arrival_time
    double *aux;                          // scratch between the HRMA sub-kernels (cached Box-Muller spare)
    uint64_t *ray;                        // global ray index (RNG counter; low 32 bits = tag)
+   uint32_t *slot;                       // index of the ray inside its batch: the key that restores arrival order
    uint32_t *flags;
    float *dra, *ddec, *droll;            // Marx_Dither_Type ra/dec/roll (dy,dz,dtheta are 0 for INTERNAL)
    float *chipx, *chipy, *pi;
@@ -48,10 +55,10 @@ struct StageArgs
 {
    PhotonSoA in, out;
    const unsigned long long *n_in;       // device: number of input slots
-   unsigned long long *n_out;            // device: number of output photons (compact) / == n_in (in place)
-   unsigned long long *ticket;           // device: tile ticket counter (zeroed before launch)
-   unsigned long long *tile_status;      // device: decoupled look-back words (zeroed before launch)
+   unsigned long long *n_out;            // device: number of output photons; compact: zeroed before launch, grown by atomics
+   unsigned long long *ticket;           // device: chunk ticket counter (zeroed before launch)
    uint64_t seed;
+   int chunk_tiles;                      // 32-ray warp tiles handed out per ticket
    int compact;                          // 1: order-preserving compaction into `out`; 0: in place, dead rays kept
    double source_distance;
    const void *blob;                     // K1Blob / K2Blob / K3Blob in global memory
@@ -81,6 +88,20 @@ void launch_hrma (const StageArgs &a, int phase, int grid, cudaStream_t s);   //
 void launch_grating (const StageArgs &a, int grid, cudaStream_t s);
 void launch_acis (const StageArgs &a, int grid, cudaStream_t s);
 int stage_grid_size (int stage, int num_sms, uint32_t blob_bytes);
+uint32_t stage_smem_bytes (int stage, uint32_t blob_bytes);
+
+// arrival-order restoration of an unordered live list (DESIGN.md "compaction"): bitmap over batch slots ->
+// popcount prefix -> scatter
+struct OrderArgs
+{
+   PhotonSoA in, out;
+   const unsigned long long *n_live;
+   uint64_t n_slots;                     // slots of the batch (= generated rays)
+   uint32_t *bitmap;                     // [n_slots/32 + 1], zeroed before launch
+   uint32_t *word_prefix;                // [n_words]
+   uint32_t *block_prefix;               // [n_words/1024 + 1]
+};
+void launch_restore_order (const OrderArgs &a, int num_sms, cudaStream_t s, int *n_launches);
 
 // host boundary helpers (AoS <-> SoA); `aos` is a device buffer of 136-byte records
 void launch_soa_to_aos (const PhotonSoA &in, const unsigned long long *n, uint64_t max_n, void *aos,

@@ -13,10 +13,10 @@ reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 stream = torch.cuda.Stream()
 with torch.cuda.stream(stream):
     m = marx_b200.MarxB200(cfg, seed=1, max_photons=n, stream=stream.cuda_stream)
-    names = ["create", "mirror", "grating", "detect"]
-    calls = [lambda i: m.create_photons(i * n, n), m.mirror_reflect, m.grating_diffract, m.detect]
+    names = ["create", "mirror", "grating", "detect", "order"]
+    calls = [lambda i: m.create_photons(i * n, n), m.mirror_reflect, m.grating_diffract, m.detect, m.restore_order]
     for rep in range(reps):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
         ev[0].record(stream)
         for k, c in enumerate(calls):
             if k == 0:
@@ -25,7 +25,7 @@ with torch.cuda.stream(stream):
                 c()
             ev[k + 1].record(stream)
         stream.synchronize()
-        ts = [ev[k].elapsed_time(ev[k + 1]) for k in range(4)]
+        ts = [ev[k].elapsed_time(ev[k + 1]) for k in range(5)]
         tot = sum(ts)
         print("rep %d: " % rep + "  ".join("%s %.3f ms" % (a, b) for a, b in zip(names, ts)),
               " total %.3f ms  -> %.3e rays/s" % (tot, n / tot * 1e3), m.stage_counts())
