@@ -302,7 +302,7 @@ __device__ __forceinline__ WarpQueue<ND, NU> &my_queue (unsigned char *smem, uin
 template <int PHASE> struct K1Shape { static constexpr int ND = (PHASE == 1) ? 7 : 6, NU = (PHASE == 1) ? 5 : 2; };
 
 template <int PHASE>
-__global__ void __launch_bounds__ (kStageThreads) k1_hrma (const __grid_constant__ StageArgs a)
+__global__ void __launch_bounds__ (kStageThreads, (PHASE == 1) ? 3 : 1) k1_hrma (const __grid_constant__ StageArgs a)
 {
    constexpr int ND = K1Shape<PHASE>::ND, NU = K1Shape<PHASE>::NU;
    extern __shared__ __align__ (128) unsigned char smem[];
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__ (kStageThreads) k1_hrma (const __grid_constant
 }
 
 // K2 ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__ (kStageThreads) k2_grating (const __grid_constant__ StageArgs a)
+__global__ void __launch_bounds__ (kStageThreads, 3) k2_grating (const __grid_constant__ StageArgs a)
 {
    constexpr int ND = 6, NU = 2;
    extern __shared__ __align__ (128) unsigned char smem[];

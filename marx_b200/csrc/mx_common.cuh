@@ -40,9 +40,14 @@ MX_HD Vec3 v_cross (const Vec3 &a, const Vec3 &b)
    return c;
 }
 // JDMv_length, vector.c:78-97 (scaled to avoid overflow; the scaling changes rounding, so keep it)
-// MX_RECIP_NORMALIZE (build option, off by default): divide once and multiply -- a/len becomes a*(1/len),
-// which can differ from the reference's three divisions by one ulp (1e-16 relative; parity tests still
-// hold at 1e-9) and saves four of the six FP64 divisions of a normalisation.
+// Device builds divide once and multiply: a/len becomes a*(1/len), which can differ from the reference's
+// three divisions by one ulp (1e-16 relative, the same size as the libm differences between glibc and
+// libdevice; the parity tests hold at 1e-9 with exact integer outputs) and saves four of the six FP64
+// divisions of a normalisation (~5 % of the whole trace).  -DMX_STRICT_DIV restores the three divisions;
+// host builds (tools/hostcheck) always use them and stay bit-identical to the reference.
+#if defined(__CUDA_ARCH__) && !defined(MX_STRICT_DIV)
+#define MX_RECIP_NORMALIZE 1
+#endif
 MX_HD double v_length (const Vec3 &a)
 {
    double x = fabs (a.x), y = fabs (a.y), z = fabs (a.z), tmp;
@@ -96,15 +101,21 @@ MX_HD Vec3 v_rotate_unit1 (const Vec3 &p, const Vec3 &n, double cos_theta, doubl
    v_normalize (u);
    return u;
 }
-// JDMv_rotate_unit_vector, vector.c:204-208
-MX_HD Vec3 v_rotate_unit (const Vec3 &p, const Vec3 &n, double theta)
+// sin and cos of one angle: one argument reduction on the device (libdevice sincos returns the values
+// of its sin and cos), the two libm calls of the reference on the host
+MX_HD void sin_cos (double theta, double &s, double &c)
 {
-   double s, c;
 #if defined(__CUDA_ARCH__)
    sincos (theta, &s, &c);
 #else
    s = sin (theta); c = cos (theta);
 #endif
+}
+// JDMv_rotate_unit_vector, vector.c:204-208
+MX_HD Vec3 v_rotate_unit (const Vec3 &p, const Vec3 &n, double theta)
+{
+   double s, c;
+   sin_cos (theta, s, c);
    return v_rotate_unit1 (p, n, c, s);
 }
 // JDM3m_vector_mul, jdmath/src/rotate.c:121-131 (row-major 3x3)
@@ -254,6 +265,21 @@ MX_HD float interp_f (float x, const float *xp, const float *yp, uint32_t n)
    if (x1 == x0) return yp[n1];
    float dy = yp[n1] - yp[n0];
    return (float) (yp[n0] + dy / (x1 - x0) * (x - x0));
+}
+// two JDMinterpolate_f calls on the SAME abscissa grid (beta and delta of hrma.c:1250-1251) share one search
+MX_HD void interp_f2 (float x, const float *xp, const float *yp1, const float *yp2, uint32_t n, float &y1, float &y2)
+{
+   if (n == 1) { y1 = yp1[0]; y2 = yp2[0]; return; }
+   uint32_t n1 = bsearch_f (x, xp, n);
+   uint32_t n0 = n1 - 1;
+   if ((n1 < n) && (x == xp[n1])) { y1 = yp1[n1]; y2 = yp2[n1]; return; }
+   if (n1 == n) { n1--; n0--; }
+   if (n1 == 0) n0 = 1;
+   double x0 = xp[n0], x1 = xp[n1];
+   if (x1 == x0) { y1 = yp1[n1]; y2 = yp2[n1]; return; }
+   float dy1 = yp1[n1] - yp1[n0], dy2 = yp2[n1] - yp2[n0];
+   y1 = (float) (yp1[n0] + dy1 / (x1 - x0) * (x - x0));
+   y2 = (float) (yp2[n0] + dy2 / (x1 - x0) * (x - x0));
 }
 // JDMinterpolate_d, jdmath/src/dinterpo.c (all double)
 MX_HD double interp_d (double x, const double *xp, const double *yp, uint32_t n)

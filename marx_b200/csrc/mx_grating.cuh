@@ -14,7 +14,8 @@ namespace mx {
 // rotate about the x axis, diffract.c:689-700
 MX_HD Vec3 rotate_x (Vec3 a, double theta)
 {
-   double c = cos (theta), s = sin (theta);
+   double c, s;
+   sin_cos (theta, s, c);
    double ay = a.y, az = a.z;
    a.y = c * ay - s * az;
    a.z = s * ay + c * az;
@@ -102,7 +103,8 @@ MX_HD int diffract_photon (const GratingShellDev &g, double theta, double energy
    if (theta != 0.0)
      {
         Vec3 l_tmp = l, d_tmp = d;
-        double c = cos (theta), s = sin (theta);
+        double c, s;
+        sin_cos (theta, s, c);
         l = v_ax1_bx2 (c, l_tmp, s, d_tmp);
         d = v_ax1_bx2 (-s, l_tmp, c, d_tmp);
      }

@@ -309,11 +309,7 @@ MX_HD uint32_t hrma_phase_a (const HrmaDev &H, double source_distance, Vec3 &x, 
       while (0 == (h.shutter_bitmap & (1u << quad)));
       theta = (2.0 * kPI) * (theta - 1.0 / 8.0);
       double st, ct;
-#if defined(__CUDA_ARCH__)
-      sincos (theta, &st, &ct);
-#else
-      st = sin (theta); ct = cos (theta);
-#endif
+      sin_cos (theta, st, ct);
       x.z = radius * ct;
       x.y = radius * st;
       x.x = h.front_position;
@@ -349,8 +345,7 @@ MX_HD void hrma_optical_constants (const HrmaDev &H, const HrmaShellDev &h, cons
    if (H.num_opt != 0)
      {
         float ef = (float) energy;
-        beta = interp_f (ef, opt_e, opt_b, H.num_opt);
-        delta = interp_f (ef, opt_e, opt_d, H.num_opt);
+        interp_f2 (ef, opt_e, opt_b, opt_d, H.num_opt, beta, delta);
         if (H.use_scale) corr = interp_f (ef, corr_e + h.corr_offset, corr_f + h.corr_offset, h.num_corr);
      }
 }

@@ -36,8 +36,9 @@ MX_HD double source_time_increment (const SourceDev &s, Rng &rng)
 MX_HD Vec3 apply_dither (double ra, double dec, double roll, Vec3 p)
 {
    p = v_rotate_unit (p, v_make (1, 0, 0), -roll);
-   double cos_ra = cos (ra), sin_ra = sin (ra);
-   double cos_dec = cos (dec), sin_dec = sin (dec);
+   double cos_ra, sin_ra, cos_dec, sin_dec;
+   sin_cos (ra, sin_ra, cos_ra);
+   sin_cos (dec, sin_dec, cos_dec);
    double cos_theta = cos_dec * cos_ra;
    Vec3 n = v_make (0, sin_dec, -cos_dec * sin_ra);
    double sin_theta = v_length (n);
@@ -53,9 +54,11 @@ MX_HD void dither_ray (const DitherDev &d, Rng &rng, double t, Vec3 &p, float &f
 {
    if (d.mode == 0) { f_ra = f_dec = f_roll = 0.0f; return; }
    t = (2.0 * kPI) * t;
-   f_ra = (float) (d.ra_amp * sin (t / d.ra_period + d.ra_phase));
-   f_dec = (float) (d.dec_amp * sin (t / d.dec_period + d.dec_phase));
-   f_roll = (float) (d.nominal_roll + d.roll_amp * sin (t / d.roll_period + d.roll_phase));
+   // amp * sin(..) is exactly +-0 when the amplitude is 0 (default DitherAmp_Roll): skip the sine then
+   f_ra = (d.ra_amp == 0.0) ? 0.0f : (float) (d.ra_amp * sin (t / d.ra_period + d.ra_phase));
+   f_dec = (d.dec_amp == 0.0) ? 0.0f : (float) (d.dec_amp * sin (t / d.dec_period + d.dec_phase));
+   f_roll = (d.roll_amp == 0.0) ? (float) d.nominal_roll
+                                : (float) (d.nominal_roll + d.roll_amp * sin (t / d.roll_period + d.roll_phase));
    double ra = f_ra, dec = f_dec, roll = f_roll;
    double delta_ra = d.aspect_blur * rng.gaussian ();
    double delta_dec = d.aspect_blur * rng.gaussian ();
