@@ -84,6 +84,20 @@ MX_HD double acis_contamination (const AcisChipDev &c, double en, double cx, dou
 
 struct GaussParm { float amp, center, sigma, cum_area; int use_tail_dist; };   // acis_fef.c:87-96
 
+// fmod(t, T) for t >= 0, T > 0 -- EXACT, like the libm routine, without its bit-serial long division:
+// with q = floor(t/T) (possibly off by one) the remainder t - q*T is a multiple of ulp(T) smaller than 2T in
+// magnitude, hence representable, and a single fused multiply-add delivers it without rounding.
+MX_HD double fmod_pos (double t, double T)
+{
+   if (!(t >= T)) return (t >= 0.0) ? t : fmod (t, T);
+   if (t > 4.0e15 * T) return fmod (t, T);        // quotient beyond 2^53: leave it to libm
+   double q = floor (t / T);
+   double r = fma (-q, T, t);
+   if (r < 0.0) r += T;
+   else if (r >= T) r -= T;
+   return r;
+}
+
 // normalize_gaussians, acis_fef.c:509-579.  gaussian_integral(0,+inf) and (-inf,0) share one erf:
 // erf((+-1e37 - x0)/sigma) is exactly +-1 for every representable table value.
 MX_HD int fef_normalize (GaussParm *g, uint32_t num)
@@ -120,45 +134,47 @@ MX_HD int fef_normalize (GaussParm *g, uint32_t num)
    return flags;
 }
 
-// compute_pha_with_pos_amps, acis_fef.c:408-468.  The reference loops until a value is found; the cap
-// only bounds pathological tables (it is never reached with a valid FEF).
+// compute_pha_with_pos_amps, acis_fef.c:408-468.  Same draws in the same order as the reference; the
+// component search is separated from the sampling so that the lanes of a warp reconverge before the
+// expensive part (in the reference's loop shape every lane would sample inside a different iteration).
+// The reference loops until a value is found; the cap only bounds pathological tables.
 MX_HD int fef_pha_pos (const GaussParm *g, uint32_t num, double &phap, Rng &rng)
 {
    for (int guard = 0; guard < 4096; guard++)
      {
         double r = rng.uniform ();
-        for (uint32_t k = 0; k < num; k++)
+        uint32_t k = 0;
+        while ((k < num) && (g[k].cum_area <= r)) k++;
+        if (k == num) continue;                  // r above every cumulative area: draw again (acis_fef.c:411-424)
+        const float center = g[k].center, sigma = g[k].sigma;
+        double pha;
+        if (g[k].use_tail_dist == 0)
           {
-             double pha;
-             if (g[k].cum_area <= r) continue;
-             if (g[k].use_tail_dist == 0)
+             unsigned int count = 0;
+             do
                {
-                  unsigned int count = 0;
-                  do
-                    {
-                       pha = g[k].center + g[k].sigma * rng.gaussian ();
-                       count++;
-                    }
-                  while ((pha < 0) && (count < 100));
+                  pha = center + sigma * rng.gaussian ();
+                  count++;
                }
-             else
-               {
-                  // truncated-tail sampler adapted from GSL (acis_fef.c:440-456)
-                  double u, v, x;
-                  double s = (0 - g[k].center) / g[k].sigma;      // float arithmetic, as in the reference
-                  do
-                    {
-                       u = rng.uniform ();
-                       do v = rng.uniform (); while (v == 0.0);
-                       x = sqrt (s * s - 2 * log (v));
-                    }
-                  while (x * u > s);
-                  pha = g[k].center + x * g[k].sigma;
-               }
-             if (pha < 0) break;          // "Failed to find a pha value": draw a new r
-             phap = pha;
-             return 0;
+             while ((pha < 0) && (count < 100));
           }
+        else
+          {
+             // truncated-tail sampler adapted from GSL (acis_fef.c:440-456)
+             double u, v, x;
+             double s = (0 - center) / sigma;      // float arithmetic, as in the reference
+             do
+               {
+                  u = rng.uniform ();
+                  do v = rng.uniform (); while (v == 0.0);
+                  x = sqrt (s * s - 2 * log (v));
+               }
+             while (x * u > s);
+             pha = center + x * sigma;
+          }
+        if (pha < 0) continue;                   // "Failed to find a pha value": draw a new r
+        phap = pha;
+        return 0;
      }
    return -1;
 }
@@ -283,7 +299,7 @@ MX_HD uint32_t acis_detect (const AcisDev &A, double energy, double t_abs, Vec3 
    // _marx_acis_apply_streak, acis-i.c:60-89
    if (A.frame_transfer_time > 0.0)
      {
-        double t = fmod (t_abs, A.frame_time);
+        double t = fmod_pos (t_abs, A.frame_time);
         if (t > A.exposure_time)
           {
              chipy = (float) (1.0 + 1022.0 * rng.uniform ());
