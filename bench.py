@@ -80,7 +80,7 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.first = index, None, [], 0
 
     def start(self):
         try:
@@ -96,9 +96,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        self.first = len(self.lines)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)                      # make sure at least one sample falls after the timed region started
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -106,7 +110,8 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, power, reasons = [], None, [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        time.sleep(0.15)
+        for ln in self.lines[self.first:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -247,11 +252,14 @@ def cuda_arm(args):
         return ms, m.launch_count() - launches0, n_events
     timed.step = 0
 
-    for _ in range(max(args.warmup, 3)):
-        one_step(timed.step); timed.step += 1
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(1.0)                       # let nvidia-smi come up; it samples every 100 ms from then on
+    for _ in range(max(args.warmup, 3)):
+        one_step(timed.step); timed.step += 1
+    if rank == 0:
+        sampler.mark()                        # only samples taken from here on count
     ms, launches, _ = timed(args.steps, e2e=False)
     clocks = sampler.stop() if rank == 0 else None
     counts = m.stage_counts()
@@ -331,7 +339,7 @@ def cuda_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--rays-per-step", type=int, default=1 << 24)
