@@ -79,7 +79,8 @@ marxb200_photon_attr;
 /* source + spectrum + arrival times: marx/libsrc/source.c:136-215,260-264 ; spectrum.c:138-181 */
 typedef struct
 {
-   int32_t source_type;            /* 0 = POINT (s-point.c:59-83) */
+   int32_t source_type;            /* 0 POINT (s-point.c:59-83), 1 GAUSS (s-gauss.c:78-141), 2 BETA (s-beta.c:81-139),
+                                      3 DISK (s-disk.c:63-109) */
    int32_t spectrum_type;          /* 1 = FLAT, 2 = FILE (MARX_*_SPECTRUM, marx.h) */
    double p[3];                    /* unit vector FROM source TO origin (Marx_Source_Type.p) */
    double p_normal[3];
@@ -90,6 +91,8 @@ typedef struct
    uint32_t spec_num;
    double total_flux;              /* photons/s/cm^2 */
    double geometric_area;          /* Marx_Mirror_Geometric_Area, cm^2 (hrma.c:736) */
+   double shape[3];                /* GAUSS: sigma (rad); BETA: core radius (rad), 1/(1-alpha) with alpha = 3 beta - 1/2;
+                                      DISK: theta_max (rad), x0 = (theta_min/theta_max)^2, x1 = 1 - x0 */
 }
 marxb200_source_desc;
 

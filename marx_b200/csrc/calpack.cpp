@@ -3,7 +3,7 @@
 // written by oracle/ref/calpack_*.c (the file-writing twin of the upload calls shown in INTEGRATION.md):
 //
 //   meta                      f64[8]  mirror, grating, detector module ids, tstart yrs, tstart secs, seed, numrays, exposure
-//   source.params             f64[13] source_type, spectrum_type, p[3], p_normal[3], distance, emin, emax, total_flux, geometric_area
+//   source.params             f64[16] source_type, spectrum_type, p[3], p_normal[3], distance, emin, emax, total_flux, geometric_area, shape[3]
 //   source.spec_energies/.spec_cum_flux  f64[n]   (FILE spectrum only)
 //   dither.params             f64[12] mode, amp ra/dec/roll, period ra/dec/roll, phase ra/dec/roll, nominal_roll, aspect_blur
 //   hrma.params               f64[7]  vig, cap_position, is_ideal, use_blur, use_wfold, use_struts, use_scale_factors
@@ -103,6 +103,7 @@ extern "C" int marxb200_load_calpack_impl (marxb200_ctx *ctx, const char *path, 
       d.source_type = (int32_t) v[0]; d.spectrum_type = (int32_t) v[1];
       for (int i = 0; i < 3; i++) { d.p[i] = v[2 + i]; d.p_normal[i] = v[5 + i]; }
       d.distance = v[8]; d.emin = v[9]; d.emax = v[10]; d.total_flux = v[11]; d.geometric_area = v[12];
+      if (e->count >= 16) for (int i = 0; i < 3; i++) d.shape[i] = v[13 + i];
       if (d.spectrum_type == 2)
         {
            GET (se, "source.spec_energies", MXCP_F64, 2);

@@ -206,7 +206,7 @@ extern "C" int marxb200_set_compaction (marxb200_ctx *c, int on)
 extern "C" int marxb200_set_source (marxb200_ctx *c, const marxb200_source_desc *d)
 {
    if ((c == nullptr) || (d == nullptr)) return fail ("marxb200_set_source: NULL argument");
-   if (d->source_type != 0) return fail ("marxb200_set_source: only POINT sources are implemented (type %d)", d->source_type);
+   if ((d->source_type < 0) || (d->source_type > 3)) return fail ("marxb200_set_source: source type %d is not implemented (POINT, GAUSS, BETA, DISK are)", d->source_type);
    if ((d->spectrum_type != 1) && (d->spectrum_type != 2)) return fail ("marxb200_set_source: unknown spectrum type %d", d->spectrum_type);
    CUDA_OK (cudaSetDevice (c->device));
    SourceDev &S = c->S;
@@ -214,6 +214,7 @@ extern "C" int marxb200_set_source (marxb200_ctx *c, const marxb200_source_desc 
    S.source_type = d->source_type; S.spectrum_type = d->spectrum_type;
    for (int i = 0; i < 3; i++) { S.p[i] = d->p[i]; S.p_normal[i] = d->p_normal[i]; }
    S.distance = d->distance; S.emin = d->emin; S.emax = d->emax;
+   for (int i = 0; i < 3; i++) S.shape[i] = d->shape[i];
    if (d->spectrum_type == 2)
      {
         if ((d->spec_num < 2) || !d->spec_energies || !d->spec_cum_flux) return fail ("marxb200_set_source: FILE spectrum needs a table");

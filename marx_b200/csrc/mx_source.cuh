@@ -24,6 +24,24 @@ MX_HD void source_draw (const SourceDev &s, Rng &rng, double &energy, Vec3 &p)
         energy = emin + de * rng.uniform ();
      }
    p = v_make (s.p[0], s.p[1], s.p[2]);
+   if (s.source_type == 0) return;
+   // GAUSS / BETA / DISK share one construction (s-gauss.c:96-137): rotate the normal to p about p by a
+   // uniform angle, then rotate p about that normal by a source-specific polar angle.  The reference keeps
+   // rotating ONE normal from photon to photon (statistically a fresh uniform azimuth every time); per-ray
+   // draws restart from st->p_normal, which is what the reference does at the start of every batch.
+   Vec3 normal = v_make (s.p_normal[0], s.p_normal[1], s.p_normal[2]);
+   normal = v_rotate_unit (normal, p, 2.0 * kPI * rng.uniform ());
+   double theta;
+   if (s.source_type == 3)        // DISK, s-disk.c:104
+     theta = s.shape[0] * sqrt (s.shape[1] + s.shape[2] * rng.uniform ());
+   else
+     {
+        double rnd;
+        do rnd = rng.uniform (); while (rnd == 0.0);
+        if (s.source_type == 1) theta = s.shape[0] * sqrt (-log (rnd));                 // GAUSS, s-gauss.c:126-136
+        else theta = s.shape[0] * sqrt (pow (rnd, s.shape[1]) - 1.0);                  // BETA, s-beta.c:116-125
+     }
+   p = v_rotate_unit (p, normal, theta);
 }
 
 // arrival-time increment: mt * Exp(1)  (source.c:326)

@@ -21,6 +21,7 @@ struct SourceDev
    const double *spec_energies, *spec_cum_flux;
    uint32_t spec_num;
    double mean_time;               // 1/flux/area, source.c:260-264
+   double shape[3];                // extended-source parameters (marxb200_source_desc.shape)
 };
 
 struct DitherDev

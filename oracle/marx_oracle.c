@@ -365,6 +365,22 @@ static void stage_source (oracle_t *o, uint64_t first, uint64_t n, double *time_
         if ((int) s[1] == 2) at->energy = interp_d (rng_uniform (&r), o->spec_c, o->spec_e, o->nspec);   /* prob.c:55 */
         else { double emin = s[9], de = s[10] - emin; at->energy = emin + de * rng_uniform (&r); }       /* spectrum.c:140-145 */
         at->p[0] = s[2]; at->p[1] = s[3]; at->p[2] = s[4];                                               /* s-point.c:76 */
+        if ((int) s[0] != 0)
+          {
+             /* GAUSS / BETA / DISK: s-gauss.c:96-137, s-beta.c:100-125, s-disk.c:86-106 (normal restarts from
+              * st->p_normal for every ray, as the reference does at the start of every batch) */
+             double nrm[3], src[3], theta, rnd;
+             nrm[0] = s[5]; nrm[1] = s[6]; nrm[2] = s[7]; src[0] = s[2]; src[1] = s[3]; src[2] = s[4];
+             rot_unit (nrm, src, 2.0 * PI * rng_uniform (&r));
+             if ((int) s[0] == 3) theta = s[13] * sqrt (s[14] + s[15] * rng_uniform (&r));
+             else
+               {
+                  do rnd = rng_uniform (&r); while (rnd == 0.0);
+                  if ((int) s[0] == 1) theta = s[13] * sqrt (-log (rnd));
+                  else theta = s[13] * sqrt (pow (rnd, s[14]) - 1.0);
+               }
+             rot_unit (at->p, nrm, theta);
+          }
         t += mt * rng_expn (&r);                                                                          /* source.c:326 */
         at->arrival_time = t;
         at->tag = (uint32_t) (first + i);

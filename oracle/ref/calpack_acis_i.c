@@ -1,11 +1,10 @@
-/* Serialises ACIS-S detector state: chip geometry + QE (marx/libsrc/acis-s.c statics), detector
- * transform (detector.c globals), frame timing (acis-i.c globals).  oracle/_ref build only. */
-#include <acis-s.c>
+/* Serialises ACIS-I detector state (marx/libsrc/acis-i.c statics); same layout as calpack_acis.c.
+ * oracle/_ref build only. */
+#include <acis-i.c>
 #include "calpack_io.h"
 
-extern double Frame_Time, Exposure_Time, Frame_Transfer_Time;   /* acis-i.c:54-56 */
 
-int calpack_dump_acis_s (mxcp_writer *w, int detector_module)
+int calpack_dump_acis_i (mxcp_writer *w, int detector_module)
 {
    char name[MARXB200_CALPACK_NAMELEN];
    double v[32];
@@ -14,21 +13,20 @@ int calpack_dump_acis_s (mxcp_writer *w, int detector_module)
    static int fef_map[10][1024];
 
    v[n++] = detector_module;
-   v[n++] = (detector_module == MARX_DETECTOR_ACIS_S) ? _MARX_NUM_ACIS_S_CHIPS : 0;
+   v[n++] = (detector_module == MARX_DETECTOR_ACIS_I) ? _MARX_NUM_ACIS_I_CHIPS : 0;
    v[n++] = _Marx_Det_XForm_Matrix.dx; v[n++] = _Marx_Det_XForm_Matrix.dy; v[n++] = _Marx_Det_XForm_Matrix.dz;
    for (i = 0; i < 9; i++) v[n++] = _Marx_Det_XForm_Matrix.matrix[i];
    v[n++] = _Marx_Det_Ideal_Flag; v[n++] = _Marx_Det_Extend_Flag; v[n++] = Marx_Focal_Length;
    v[n++] = Exposure_Time; v[n++] = Frame_Transfer_Time; v[n++] = Frame_Time;
    v[n++] = _Marx_Dither_Mode;
-   if (detector_module == MARX_DETECTOR_ACIS_I) return calpack_dump_acis_i (w, detector_module);
    CP_F64 (w, "acis.params", v, n);
-   if (detector_module != MARX_DETECTOR_ACIS_S) return 0;
+   if (detector_module != MARX_DETECTOR_ACIS_I) return 0;
 
-   if (-1 == calpack_dump_fef (w, 4, 9, &fef_map[0][0])) return -1;
+   if (-1 == calpack_dump_fef (w, 0, 3, &fef_map[0][0])) return -1;
 
-   for (k = 0, d = ACIS_S_Chips; d != NULL; d = d->next, k++)
+   for (k = 0, d = ACIS_I_Chips; d != NULL; d = d->next, k++)
      {
-	_Marx_Acis_Chip_Type *c = &Acis_CCDS[d->id - 4];
+	_Marx_Acis_Chip_Type *c = &Acis_CCDS[d->id];
 	double gm[19];
 	n = 0;
 	gm[n++] = d->id;

@@ -18,6 +18,12 @@ static inline void cp_name (char *buf, const char *fmt, ...)
 
 int calpack_dump_source (mxcp_writer *w, void *marx_source);
 int calpack_dump_dither (mxcp_writer *w);
+int calpack_source_shape (void *marx_source, double *shape);
+int calpack_is_gauss (void *st, double *shape);
+int calpack_is_beta (void *st, double *shape);
+int calpack_is_disk (void *st, double *shape);
+int calpack_is_point (void *st);
+int calpack_dump_acis_i (mxcp_writer *w, int detector_module);
 int calpack_dump_hrma (mxcp_writer *w);
 int calpack_dump_wfold (mxcp_writer *w, const char *prefix, void *table);
 int calpack_dump_grating (mxcp_writer *w, int grating_module);

@@ -1,0 +1,9 @@
+/* BETA source statics (marx/libsrc/s-beta.c).  oracle/_ref build only. */
+#include <s-beta.c>
+#include "calpack_io.h"
+int calpack_is_beta (void *st, double *shape)
+{
+   if (((Marx_Source_Type *) st)->create_photons != beta_create_photons) return 0;
+   shape[0] = Core_Radius; shape[1] = 1.0 / (1.0 - Alpha); shape[2] = 0.0;
+   return 1;
+}

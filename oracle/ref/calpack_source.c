@@ -18,8 +18,12 @@ int calpack_dump_dither (mxcp_writer *w)
 int calpack_dump_source (mxcp_writer *w, void *marx_source)
 {
    Marx_Source_Type *st = (Marx_Source_Type *) marx_source;
-   double v[13];
-   v[0] = 0;  /* POINT; other source types are not packed yet */
+   double v[16];
+   int type;
+   memset (v, 0, sizeof (v));
+   type = calpack_source_shape (st, v + 13);       /* 0 POINT, 1 GAUSS, 2 BETA, 3 DISK, -1 unsupported */
+   if (type < 0) return -1;
+   v[0] = type;
    v[1] = st->spectrum.type;
    v[2] = st->p.x; v[3] = st->p.y; v[4] = st->p.z;
    v[5] = st->p_normal.x; v[6] = st->p_normal.y; v[7] = st->p_normal.z;
@@ -29,7 +33,7 @@ int calpack_dump_source (mxcp_writer *w, void *marx_source)
      { v[9] = st->spectrum.s.flat.emin; v[10] = st->spectrum.s.flat.emax; }
    v[11] = st->spectrum.total_flux;
    v[12] = Marx_Mirror_Geometric_Area;
-   CP_F64 (w, "source.params", v, 13);
+   CP_F64 (w, "source.params", v, 16);
    if (st->spectrum.type == MARX_FILE_SPECTRUM)
      {
 	CP_F64 (w, "source.spec_energies", st->spectrum.s.file.energies, st->spectrum.s.file.num);

@@ -19,14 +19,18 @@ REF = os.path.join(ROOT, "oracle", "_ref")
 sys.path.insert(0, ROOT)
 from tests.replay_io import read_replay  # noqa: E402
 
-COMMON = ["ExposureTime=0", "Verbose=0", "SourceFlux=0.003", "TStart=2023.5", "SourceType=POINT", "SpectrumType=FLAT"]
+COMMON = ["ExposureTime=0", "Verbose=0", "SourceFlux=0.003", "TStart=2023.5", "SpectrumType=FLAT"]
 CONFIGS = {
     # BASELINE.json configs[0]
-    "c1_acis_s": dict(args=["MinEnergy=1.5", "MaxEnergy=1.5", "GratingType=NONE", "DetectorType=ACIS-S", "DitherModel=NONE"],
+    "c1_acis_s": dict(args=["SourceType=POINT", "MinEnergy=1.5", "MaxEnergy=1.5", "GratingType=NONE", "DetectorType=ACIS-S", "DitherModel=NONE"],
                       nrays=8192, seed=11),
     # BASELINE.json configs[1] (the bench workload)
-    "c2_hetg_acis_s": dict(args=["MinEnergy=0.3", "MaxEnergy=8.0", "GratingType=HETG", "DetectorType=ACIS-S",
+    "c2_hetg_acis_s": dict(args=["SourceType=POINT", "MinEnergy=0.3", "MaxEnergy=8.0", "GratingType=HETG", "DetectorType=ACIS-S",
                                  "DitherModel=INTERNAL"], nrays=16384, seed=7),
+    # BASELINE.json configs[3]: extended BETA source 10 arcmin off axis, ACIS-I, dither
+    "c4_beta_acis_i": dict(args=["SourceType=BETA", "S-BetaCoreRadius=10", "S-BetaBeta=0.7", "SourceDEC=-53.92410480125",
+                                 "MinEnergy=0.5", "MaxEnergy=7.0", "GratingType=NONE", "DetectorType=ACIS-I",
+                                 "DitherModel=INTERNAL"], nrays=16384, seed=13),
 }
 
 

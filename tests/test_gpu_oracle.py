@@ -54,7 +54,7 @@ def test_cuda_matches_oracle_slot_by_slot(config, seed, first, n):
     assert int(alive.sum()) == n_det
 
 
-@pytest.mark.parametrize("config,seed,n", [("c2_hetg_acis_s", 31, 1 << 19), ("c1_acis_s", 32, 1 << 18)])
+@pytest.mark.parametrize("config,seed,n", [("c2_hetg_acis_s", 31, 1 << 19), ("c1_acis_s", 32, 1 << 18), ("c4_beta_acis_i", 33, 1 << 18)])
 def test_stage_injection_parity(config, seed, n):
     """Pure replay parity per stage: upload the oracle's photons at a stage boundary (the reference's RAYFILE
     channel, s-rayfile.c:188-221), run ONE stage on the GPU, compare with the oracle's next stage."""

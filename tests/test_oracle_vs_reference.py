@@ -44,7 +44,7 @@ def check_bit_exact(mine, ref_stages, start_times):
     assert n == len(ref_stages)
 
 
-@pytest.mark.parametrize("config", ["c1_acis_s", "c2_hetg_acis_s"])
+@pytest.mark.parametrize("config", ["c1_acis_s", "c2_hetg_acis_s", "c4_beta_acis_i"])
 def test_oracle_matches_committed_reference_replay(config):
     z = np.load(os.path.join(GOLDEN, config + "_replay.npz"))
     o = Oracle(config, int(z["seed"]))
@@ -62,6 +62,13 @@ CASES = [
                                              "HRMA_Use_WFold=no", "HRMA_Use_Struts=no", "DetOffsetX=0.5", "DetOffsetZ=-3.0"], 5, 77, 10000),
     ("finite_distance_shutters", ["MinEnergy=0.5", "MaxEnergy=4.0", "GratingType=NONE", "DetectorType=ACIS-S", "DitherModel=NONE",
                                   "SourceDistance=537.0", "Shutters1=0110", "Shutters4=1000"], 6, 0, 10000),
+    ("gauss_source_acis_i", ["SourceType=GAUSS", "S-GaussSigma=45", "MinEnergy=0.5", "MaxEnergy=5.0", "GratingType=NONE",
+                             "DetectorType=ACIS-I", "DitherModel=INTERNAL"], 15, 0, 10000),
+    ("disk_source_hetg", ["SourceType=DISK", "S-DiskTheta0=20", "S-DiskTheta1=90", "MinEnergy=0.8", "MaxEnergy=2.5", "GratingType=HETG",
+                          "DetectorType=ACIS-S", "DitherModel=NONE"], 16, 4096, 10000),
+    ("beta_source_off_axis_acis_i", ["SourceType=BETA", "S-BetaCoreRadius=25", "S-BetaBeta=0.9", "SourceRA=249.9316", "MinEnergy=0.5",
+                                     "MaxEnergy=7.0", "GratingType=NONE", "DetectorType=ACIS-I", "DitherModel=INTERNAL"], 17, 0, 10000),
+    ("file_spectrum", ["SpectrumType=FILE", "SpectrumFile=%SPECFILE%", "GratingType=HETG", "DetectorType=ACIS-S", "DitherModel=INTERNAL"], 18, 0, 10000),
     ("sector_files_off_unit_order", ["MinEnergy=0.8", "MaxEnergy=3.0", "GratingType=HETG", "DetectorType=ACIS-S", "DitherModel=INTERNAL",
                                      "Use_HETG_Sector_Files=no"], 8, 1000, 10000),
 ]
@@ -71,8 +78,16 @@ CASES = [
 @pytest.mark.parametrize("name,args,seed,first,n", CASES, ids=[c[0] for c in CASES])
 def test_oracle_matches_fresh_reference_replay(tmp_path, name, args, seed, first, n):
     par = "@@" + os.path.join(REF, "par", "marx.par")
-    common = ["ExposureTime=0", "Verbose=0", "SourceFlux=0.003", "TStart=2023.5", "SourceType=POINT", "SpectrumType=FLAT"]
+    common = ["ExposureTime=0", "Verbose=0", "SourceFlux=0.003", "TStart=2023.5", "SpectrumType=FLAT"]
     env = dict(os.environ, MARX_DATA_DIR=os.path.join(REF, "data"))
+    if any("%SPECFILE%" in a for a in args):
+        # a FILE spectrum (spectrum.c:214-273): two columns, energy [keV] and flux density
+        spec = tmp_path / "spec.dat"
+        e = np.linspace(0.4, 9.0, 400)
+        spec.write_text("".join("%.6f %.6e\n" % (x, x ** -1.7 * (1 + 3 * np.exp(-0.5 * ((x - 6.4) / 0.05) ** 2))) for x in e))
+        args = [a.replace("%SPECFILE%", str(spec)) for a in args]
+    if not any(a.startswith("SourceType=") for a in args):
+        args = ["SourceType=POINT"] + args
     pack = str(tmp_path / (name + ".calpack"))
     dump = str(tmp_path / (name + ".bin"))
     subprocess.check_call([os.path.join(REF, "calpack_dump"), pack, par] + common + args, env=env,

@@ -45,6 +45,7 @@ extern "C" int marxb200_set_source (marxb200_ctx *, const marxb200_source_desc *
    gS.source_type = d->source_type; gS.spectrum_type = d->spectrum_type;
    for (int i = 0; i < 3; i++) { gS.p[i] = d->p[i]; gS.p_normal[i] = d->p_normal[i]; }
    gS.distance = d->distance; gS.emin = d->emin; gS.emax = d->emax;
+   for (int i = 0; i < 3; i++) gS.shape[i] = d->shape[i];
    gS.spec_energies = d->spec_energies; gS.spec_cum_flux = d->spec_cum_flux; gS.spec_num = d->spec_num;
    gS.mean_time = (d->total_flux <= 0.0) ? 0.0 : 1.0 / d->total_flux / d->geometric_area;
    return 0;
