@@ -46,6 +46,7 @@ enum { MARXB200_STAGE_SOURCE = 0, MARXB200_STAGE_MIRROR = 1, MARXB200_STAGE_GRAT
 #define MARXB200_PHOTON_DRAKE_BLOCKED    0x20
 #define MARXB200_PHOTON_GRATING_VBLOCKED 0x40
 #define MARXB200_BAD_PHOTON_MASK         0xFF
+#define MARXB200_PHOTON_DRAKE_REFLECTED  0x100
 #define MARXB200_PHOTON_ACIS_STREAKED    0x200
 
 /* Byte-compatible image of Marx_Photon_Attr_Type (marx/libsrc/marx.h:51-100; sizeof == 136 on x86-64).
@@ -174,6 +175,9 @@ typedef struct
    int32_t type;                   /* 0 none, 1 HETG, 2 LETG (MARX_GRATING_*, marx.h:364-376) */
    marxb200_grating_shell shells[MARXB200_NUM_SHELLS];
    double rowland[MARXB200_NUM_SHELLS];   /* diameter per shell (diffract.c:885-904) */
+   /* LETG only: fine [0] and coarse [1] support gratings (diffract.c:917-970, :1098-1118); num_orders == 0: absent.
+    * Their efficiencies are tabulated on the 1024-point grid of diffract.c:108-110. */
+   marxb200_grating_shell support[2];
 }
 marxb200_grating_desc;
 
@@ -223,6 +227,41 @@ typedef struct
 }
 marxb200_acis_desc;
 
+/* HRC-S (marx/libsrc/hrc-s.c, hrc_s_geom.c, hrcblur.c, hrc-i.c:66-85) with the HESF "Drake flat" (drake.c) */
+typedef struct
+{
+   int32_t id;                     /* MCP id 1..3 */
+   double x_ll[3], xhat[3], yhat[3], normal[3], xlen, ylen;
+   uint32_t qe_num; const float *qe_energies, *qe;      /* MCP_QEs[Mcp_Id_Mapping[id]] (hrc-s.c:44-56) */
+   double u_start, v_start, u_0, v_0, cx_0, cy_0;       /* _marx_hrc_s_compute_pixel constants (hrc_s_geom.c:344-394) */
+}
+marxb200_hrc_mcp;
+
+typedef struct
+{
+   double a[3], e1[3], e2[3], normal[3], len1, len2;    /* Rectangle_Type, drake.c:60-69 */
+}
+marxb200_hesf_plate;
+
+typedef struct
+{
+   int32_t detector_type;          /* MARX_DETECTOR_HRC_S */
+   int32_t num_mcps;
+   marxb200_hrc_mcp mcps[3];       /* facet-list order */
+   uint32_t filter_num[4]; const float *filter_energies[4], *filter_qe[4];   /* UV/ion shield regions 0..3 */
+   double shield_t, shield_l, shield_r, shield_x, shield_sl, shield_sr, shield_sl_gap, shield_sr_gap;
+   double shield_y_center, shield_z_center;              /* hrc-s.c:66-83,431-441 */
+   double blur[13];                /* Marx_HRC_Blur_Parm_Type after fixup_blur_parms (hrcblur.c:52-70) */
+   double u_pixel_size, v_pixel_size;
+   double det_offset[3], det_matrix[9];
+   int32_t det_ideal, det_extend;
+   int32_t use_hesf, hesf_num_plates;                    /* rectangles: 2 * hesf_num_plates (drake.c:233-262) */
+   marxb200_hesf_plate hesf[8];
+   double hesf_cr_width;
+   uint32_t c_num, cr_num; const float *c_energies, *c_betas, *c_deltas, *cr_energies, *cr_betas, *cr_deltas;
+}
+marxb200_hrc_s_desc;
+
 /* ------------------------------------------------------------------------------------------------ */
 /* life cycle                                                                                        */
 int marxb200_abi_version (void);
@@ -244,6 +283,7 @@ int marxb200_set_dither (marxb200_ctx *ctx, const marxb200_dither_desc *d);
 int marxb200_set_hrma (marxb200_ctx *ctx, const marxb200_hrma_desc *d);
 int marxb200_set_grating (marxb200_ctx *ctx, const marxb200_grating_desc *d);
 int marxb200_set_acis (marxb200_ctx *ctx, const marxb200_acis_desc *d);
+int marxb200_set_hrc_s (marxb200_ctx *ctx, const marxb200_hrc_s_desc *d);
 /* convenience: read a calibration pack (tools/ + DESIGN.md "calpack") and call the setters above */
 int marxb200_load_calpack (marxb200_ctx *ctx, const char *path);
 
@@ -264,7 +304,7 @@ int marxb200_time_sums (marxb200_ctx *ctx, uint64_t first_ray, uint64_t n, doubl
 int marxb200_mirror_reflect (marxb200_ctx *ctx);
 /* marx_grating_diffract (grating.c:87 -> diffract.c:974-1130) */
 int marxb200_grating_diffract (marxb200_ctx *ctx);
-/* marx_detect (detector.c:361-379 -> acis-s.c:177-248) */
+/* marx_detect (detector.c:361-379 -> acis-s.c:177-248 | acis-i.c:96-166 | hrc-s.c:236-312 with drake.c:317-372) */
 int marxb200_detect (marxb200_ctx *ctx);
 /* The compacting stage kernels emit survivors in completion order; this puts the live list back into
  * arrival order (what marx_prune_photons preserves, photon.c:40-63).  Called implicitly by marxb200_trace

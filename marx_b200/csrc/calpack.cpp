@@ -14,6 +14,9 @@
 //   grating.params            f64[5]  type, rowland[4]
 //   grating.shell<k>.params   f64[5]  dispersion_angle, period, dp_over_p, theta_blur, vig
 //   grating.shell<k>.order_list i32, .energies f32, .cum_eff f32[orders][energies], .sectors f64[n][6]
+//   grating.support<k>.*      LETG fine (0) / coarse (1) support gratings, same entries as a shell without sectors
+//   hrc.params f64[44]; hrc.mcp<k>.geom f64[21], .qe_energies, .qe; hrc.filter<r>.energies, .qe; hrc.hesf f64[2n][14];
+//   hrc.hesf_c_{energies,betas,deltas}, hrc.hesf_cr_{...}        (HRC-S packs carry no acis.* entries)
 //   acis.params               f64[21] detector_type, num_chips, det_offset[3], det_matrix[9], det_ideal, det_extend,
 //                                     focal_length, exposure_time, frame_transfer_time, frame_time, dither_mode
 //   acis.num_fefs u32[1]; acis.fef<j>.dims u32[2] (num_gaussians, num_energies), .energies, .channels, .gauss f32
@@ -223,8 +226,78 @@ extern "C" int marxb200_load_calpack_impl (marxb200_ctx *ctx, const char *path, 
              s.sec_dtheta = sec_cols[c0 + 2].data (); s.sec_dtheta_blur = sec_cols[c0 + 3].data ();
              s.sec_dpp = sec_cols[c0 + 4].data (); s.sec_dpp_blur = sec_cols[c0 + 5].data ();
           }
+      if (d.type == 2)
+        for (int k = 0; k < 2; k++)
+          {
+             if (!P.has (nm ("grating.support%d.params", k))) continue;
+             GET (gp, nm ("grating.support%d.params", k), MXCP_F64, 5);
+             GET (ol, nm ("grating.support%d.order_list", k), MXCP_I32, 0);
+             GET (en, nm ("grating.support%d.energies", k), MXCP_F32, 2);
+             GET (ce, nm ("grating.support%d.cum_eff", k), MXCP_F32, ol->count * en->count);
+             const double *g = (const double *) gp->data;
+             marxb200_grating_shell &s = d.support[k];
+             s.dispersion_angle = g[0]; s.period = g[1]; s.dp_over_p = g[2]; s.theta_blur = g[3]; s.vig = g[4];
+             s.num_orders = (uint32_t) ol->count; s.order_list = (const int32_t *) ol->data;
+             s.num_energies = (uint32_t) en->count; s.energies = (const float *) en->data;
+             s.cum_eff = (const float *) ce->data;
+          }
       if (-1 == marxb200_set_grating (ctx, &d)) return bail (marxb200_last_error ());
    }
+   // ---- HRC-S ----
+   if (P.has ("hrc.params"))
+     {
+        GET (e, "hrc.params", MXCP_F64, 44);
+        const double *v = (const double *) e->data;
+        marxb200_hrc_s_desc d; memset (&d, 0, sizeof (d));
+        int n = 0;
+        d.detector_type = (int32_t) v[n++]; d.num_mcps = (int32_t) v[n++];
+        for (int i = 0; i < 3; i++) d.det_offset[i] = v[n++];
+        for (int i = 0; i < 9; i++) d.det_matrix[i] = v[n++];
+        d.det_ideal = (int32_t) v[n++]; d.det_extend = (int32_t) v[n++];
+        d.shield_t = v[n++]; d.shield_l = v[n++]; d.shield_r = v[n++]; d.shield_x = v[n++]; d.shield_sl = v[n++]; d.shield_sr = v[n++];
+        d.shield_sl_gap = v[n++]; d.shield_sr_gap = v[n++]; d.shield_y_center = v[n++]; d.shield_z_center = v[n++];
+        for (int i = 0; i < 13; i++) d.blur[i] = v[n++];
+        d.u_pixel_size = v[n++]; d.v_pixel_size = v[n++];
+        d.use_hesf = (int32_t) v[n++]; d.hesf_num_plates = (int32_t) v[n++]; d.hesf_cr_width = v[n++];
+        if ((d.num_mcps > 3) || (d.hesf_num_plates > 4)) return bail ("bad HRC pack");
+        for (int k = 0; k < d.num_mcps; k++)
+          {
+             GET (gm, nm ("hrc.mcp%d.geom", k), MXCP_F64, 21);
+             const double *g = (const double *) gm->data;
+             marxb200_hrc_mcp &c = d.mcps[k];
+             int m = 0;
+             c.id = (int32_t) g[m++];
+             for (int i = 0; i < 3; i++) c.x_ll[i] = g[m++];
+             for (int i = 0; i < 3; i++) c.xhat[i] = g[m++];
+             for (int i = 0; i < 3; i++) c.yhat[i] = g[m++];
+             for (int i = 0; i < 3; i++) c.normal[i] = g[m++];
+             c.xlen = g[m++]; c.ylen = g[m++];
+             c.u_start = g[m++]; c.v_start = g[m++]; c.u_0 = g[m++]; c.v_0 = g[m++]; c.cx_0 = g[m++]; c.cy_0 = g[m++];
+             GET (qe_e, nm ("hrc.mcp%d.qe_energies", k), MXCP_F32, 0); GET (qe_v, nm ("hrc.mcp%d.qe", k), MXCP_F32, qe_e->count);
+             c.qe_num = (uint32_t) qe_e->count; c.qe_energies = (const float *) qe_e->data; c.qe = (const float *) qe_v->data;
+          }
+        for (int r = 0; r < 4; r++)
+          {
+             GET (fe, nm ("hrc.filter%d.energies", r), MXCP_F32, 0); GET (fq, nm ("hrc.filter%d.qe", r), MXCP_F32, fe->count);
+             d.filter_num[r] = (uint32_t) fe->count; d.filter_energies[r] = (const float *) fe->data; d.filter_qe[r] = (const float *) fq->data;
+          }
+        GET (hp, "hrc.hesf", MXCP_F64, 14ull * 2 * d.hesf_num_plates);
+        const double *h = (const double *) hp->data;
+        for (int k = 0; k < 2 * d.hesf_num_plates; k++)
+          {
+             marxb200_hesf_plate &pl = d.hesf[k];
+             const double *q = h + 14 * k;
+             for (int i = 0; i < 3; i++) { pl.a[i] = q[i]; pl.e1[i] = q[3 + i]; pl.e2[i] = q[6 + i]; pl.normal[i] = q[9 + i]; }
+             pl.len1 = q[12]; pl.len2 = q[13];
+          }
+        GET (ce, "hrc.hesf_c_energies", MXCP_F32, 0); GET (cb, "hrc.hesf_c_betas", MXCP_F32, ce->count); GET (cd, "hrc.hesf_c_deltas", MXCP_F32, ce->count);
+        GET (re, "hrc.hesf_cr_energies", MXCP_F32, 0); GET (rb, "hrc.hesf_cr_betas", MXCP_F32, re->count); GET (rd, "hrc.hesf_cr_deltas", MXCP_F32, re->count);
+        d.c_num = (uint32_t) ce->count; d.c_energies = (const float *) ce->data; d.c_betas = (const float *) cb->data; d.c_deltas = (const float *) cd->data;
+        d.cr_num = (uint32_t) re->count; d.cr_energies = (const float *) re->data; d.cr_betas = (const float *) rb->data; d.cr_deltas = (const float *) rd->data;
+        if (-1 == marxb200_set_hrc_s (ctx, &d)) return bail (marxb200_last_error ());
+        rc = 0;
+        return 0;
+     }
    // ---- ACIS ----
    std::vector<marxb200_fef> fefs;
    {

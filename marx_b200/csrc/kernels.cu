@@ -22,6 +22,7 @@
 #include "mx_hrma.cuh"
 #include "mx_grating.cuh"
 #include "mx_acis.cuh"
+#include "mx_hrc.cuh"
 #include "mx_kernels.cuh"
 #include "../../include/marxb200.h"
 
@@ -195,6 +196,7 @@ __global__ void __launch_bounds__ (kTile) k0_source (const __grid_constant__ Sou
    o.ray[i] = a.first_ray + i;
    o.slot[i] = (uint32_t) i;
    o.flags[i] = 0;
+   o.order[i] = 0; o.sorders[i] = 0;      // stay 0 when GratingType=NONE (memset of source.c:287)
    o.dra[i] = dra; o.ddec[i] = ddec; o.droll[i] = droll;
 }
 
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__ (kStageThreads, (PHASE == 1) ? 3 : 1) k1_hrma 
 // K2 ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__ (kStageThreads, 3) k2_grating (const __grid_constant__ StageArgs a)
 {
-   constexpr int ND = 6, NU = 2;
+   constexpr int ND = 6, NU = 3;
    extern __shared__ __align__ (128) unsigned char smem[];
    __shared__ __align__ (8) unsigned long long bar;
    stage_blob (smem, a.blob, a.blob_bytes, &bar);
@@ -403,12 +405,14 @@ __global__ void __launch_bounds__ (kStageThreads, 3) k2_grating (const __grid_co
      {
         Vec3 x = v_make (in.x0[i], in.x1[i], in.x2[i]), p = v_make (in.p0[i], in.p1[i], in.p2[i]);
         int order = 0;
+        uint32_t sorders = 0;
         Rng rng;
         rng.init (a.seed, in.ray[i], MARXB200_STAGE_GRATING);
-        uint32_t flags = grating_diffract (G, in.shell[i], in.energy[i], x, p, order, rng);
+        uint32_t flags = grating_diffract (G, in.shell[i], in.energy[i], x, p, order, sorders, rng);
         d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = p.x; d[4] = p.y; d[5] = p.z;
         u[0] = (uint32_t) i;
         u[1] = (uint32_t) (order & 0xFF);
+        u[2] = sorders;
         return flags;
      };
    auto write_row = [&] (unsigned long long j, const double *d, const uint32_t *u, uint32_t flags)
@@ -417,6 +421,7 @@ __global__ void __launch_bounds__ (kStageThreads, 3) k2_grating (const __grid_co
         out.p0[j] = d[3]; out.p1[j] = d[4]; out.p2[j] = d[5];
         out.flags[j] = flags;
         out.order[j] = (int8_t) (u[1] & 0xFFu);
+        out.sorders[j] = u[2];
      };
    auto flush_entry = [&] (uint32_t pos, unsigned long long j)
      {
@@ -465,6 +470,7 @@ __global__ void __launch_bounds__ (kStageThreads) k3_acis (const __grid_constant
         out.flags[j] = u[1];
         out.ccd[j] = (int8_t) (u[2] & 0xFFu);
         out.pha[j] = (int16_t) (uint16_t) (u[2] >> 8);
+        out.region[j] = 0; out.upix[j] = 0.f; out.vpix[j] = 0.f;
         out.chipx[j] = __uint_as_float (u[3]); out.chipy[j] = __uint_as_float (u[4]); out.pi[j] = __uint_as_float (u[5]);
      };
    auto flush_entry = [&] (uint32_t pos, unsigned long long j)
@@ -478,6 +484,62 @@ __global__ void __launch_bounds__ (kStageThreads) k3_acis (const __grid_constant
         copy_carried (in, u[0], out, j);
         out.shell[j] = in.shell[u[0]];
         out.order[j] = in.order[u[0]];
+        out.sorders[j] = in.sorders[u[0]];
+     };
+   auto in_place = [&] (unsigned long long i, const double *d, const uint32_t *u, uint32_t) { write_row (i, d, u); };
+   run_stage<ND, NU> (a, q, trace, flush_entry, in_place);
+}
+
+// K3 (HRC-S) -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__ (kStageThreads) k3_hrc (const __grid_constant__ StageArgs a)
+{
+   constexpr int ND = 6, NU = 7;
+   extern __shared__ __align__ (128) unsigned char smem[];
+   __shared__ __align__ (8) unsigned long long bar;
+   stage_blob (smem, a.blob, a.blob_bytes, &bar);
+   const HrcDev &D = reinterpret_cast<const K3HrcBlob *> (smem)->D;
+   WarpQueue<ND, NU> &q = my_queue<ND, NU> (smem, a.blob_bytes);
+   const PhotonSoA &in = a.in, &out = a.out;
+
+   auto trace = [&] (unsigned long long i, double *d, uint32_t *u) -> uint32_t
+     {
+        Vec3 x = v_make (in.x0[i], in.x1[i], in.x2[i]), p = v_make (in.p0[i], in.p1[i], in.p2[i]);
+        int ccd = -1, region = 0; float ypix = 0, zpix = 0, upix = 0, vpix = 0; int16_t pha = 0;
+        Rng rng;
+        rng.init (a.seed, in.ray[i], MARXB200_STAGE_DETECTOR);
+        uint32_t flags = hrc_s_detect (D, in.energy[i], x, p, ccd, region, ypix, zpix, upix, vpix, pha, rng);
+        d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = p.x; d[4] = p.y; d[5] = p.z;
+        u[0] = (uint32_t) i;
+        u[1] = flags;
+        u[2] = ((uint32_t) (ccd & 0xFF)) | (((uint32_t) (uint16_t) pha) << 8) | (((uint32_t) (region & 0xFF)) << 24);
+        u[3] = __float_as_uint (ypix); u[4] = __float_as_uint (zpix);
+        u[5] = __float_as_uint (upix); u[6] = __float_as_uint (vpix);
+        return flags;
+     };
+   auto write_row = [&] (unsigned long long j, const double *d, const uint32_t *u)
+     {
+        out.x0[j] = d[0]; out.x1[j] = d[1]; out.x2[j] = d[2];
+        out.p0[j] = d[3]; out.p1[j] = d[4]; out.p2[j] = d[5];
+        out.flags[j] = u[1];
+        out.ccd[j] = (int8_t) (u[2] & 0xFFu);
+        out.pha[j] = (int16_t) (uint16_t) ((u[2] >> 8) & 0xFFFFu);
+        out.region[j] = (int8_t) (u[2] >> 24);
+        out.chipx[j] = __uint_as_float (u[3]); out.chipy[j] = __uint_as_float (u[4]);
+        out.upix[j] = __uint_as_float (u[5]); out.vpix[j] = __uint_as_float (u[6]);
+        out.pi[j] = 0.f;
+     };
+   auto flush_entry = [&] (uint32_t pos, unsigned long long j)
+     {
+        double d[ND]; uint32_t u[NU];
+#pragma unroll
+        for (int k = 0; k < ND; k++) d[k] = q.d[k][pos];
+#pragma unroll
+        for (int k = 0; k < NU; k++) u[k] = q.u[k][pos];
+        write_row (j, d, u);
+        copy_carried (in, u[0], out, j);
+        out.shell[j] = in.shell[u[0]];
+        out.order[j] = in.order[u[0]];
+        out.sorders[j] = in.sorders[u[0]];
      };
    auto in_place = [&] (unsigned long long i, const double *d, const uint32_t *u, uint32_t) { write_row (i, d, u); };
    run_stage<ND, NU> (a, q, trace, flush_entry, in_place);
@@ -550,6 +612,7 @@ __global__ void __launch_bounds__ (256) order_scatter (OrderArgs a)
         out.dra[j] = in.dra[s]; out.ddec[j] = in.ddec[s]; out.droll[j] = in.droll[s];
         out.chipx[j] = in.chipx[s]; out.chipy[j] = in.chipy[s]; out.pi[j] = in.pi[s];
         out.pha[j] = in.pha[s]; out.shell[j] = in.shell[s]; out.order[j] = in.order[s]; out.ccd[j] = in.ccd[s];
+        out.upix[j] = in.upix[s]; out.vpix[j] = in.vpix[s]; out.sorders[j] = in.sorders[s]; out.region[j] = in.region[s];
      }
 }
 void launch_restore_order (const OrderArgs &a, int num_sms, cudaStream_t s, int *n_launches)
@@ -579,16 +642,18 @@ __global__ void __launch_bounds__ (256) soa_to_aos (PhotonSoA in, const unsigned
         r.p[0] = in.p0[i]; r.p[1] = in.p1[i]; r.p[2] = in.p2[i];
         r.arrival_time = in.time[i] - start_time;
         r.flags = in.flags[i];
-        r.y_pixel = in.chipx[i]; r.z_pixel = in.chipy[i]; r.u_pixel = 0.f; r.v_pixel = 0.f;
+        r.y_pixel = in.chipx[i]; r.z_pixel = in.chipy[i]; r.u_pixel = in.upix[i]; r.v_pixel = in.vpix[i];
         r.dither_ra = in.dra[i]; r.dither_dec = in.ddec[i]; r.dither_roll = in.droll[i];
         r.dither_dy = 0.f; r.dither_dz = 0.f; r.dither_dtheta = 0.f;
         r.pi = in.pi[i];
         r.pulse_height = in.pha[i];
         r.mirror_shell = in.shell[i];
         r.ccd_num = in.ccd[i];
-        r.detector_region = 0;
+        r.detector_region = in.region[i];
         r.order = in.order[i];
-        r.support_orders[0] = r.support_orders[1] = r.support_orders[2] = r.support_orders[3] = 0;
+        const uint32_t so = in.sorders[i];
+        r.support_orders[0] = (int8_t) (so & 0xFFu); r.support_orders[1] = (int8_t) ((so >> 8) & 0xFFu);
+        r.support_orders[2] = (int8_t) ((so >> 16) & 0xFFu); r.support_orders[3] = (int8_t) (so >> 24);
         r.tag = (uint32_t) in.ray[i];
         // 17 aligned 8-byte stores per record
         const uint64_t *src = reinterpret_cast<const uint64_t *> (&r);
@@ -621,6 +686,10 @@ __global__ void __launch_bounds__ (256) aos_to_soa (const marxb200_photon_attr *
         out.shell[i] = (uint8_t) r.mirror_shell;
         out.order[i] = r.order;
         out.ccd[i] = r.ccd_num;
+        out.region[i] = r.detector_region;
+        out.upix[i] = r.u_pixel; out.vpix[i] = r.v_pixel;
+        out.sorders[i] = ((uint32_t) (uint8_t) r.support_orders[0]) | (((uint32_t) (uint8_t) r.support_orders[1]) << 8)
+                         | (((uint32_t) (uint8_t) r.support_orders[2]) << 16) | (((uint32_t) (uint8_t) r.support_orders[3]) << 24);
      }
 }
 
@@ -652,8 +721,9 @@ uint32_t stage_smem_bytes (int stage, uint32_t blob_bytes)
       case 10: return base + warps * (uint32_t) sizeof (WarpQueue<K1Shape<0>::ND, K1Shape<0>::NU>);
       case 11: return base + warps * (uint32_t) sizeof (WarpQueue<K1Shape<1>::ND, K1Shape<1>::NU>);
       case 12: return base + warps * (uint32_t) sizeof (WarpQueue<K1Shape<2>::ND, K1Shape<2>::NU>);
-      case 2: return base + warps * (uint32_t) sizeof (WarpQueue<6, 2>);
+      case 2: return base + warps * (uint32_t) sizeof (WarpQueue<6, 3>);
       case 3: return base + warps * (uint32_t) sizeof (WarpQueue<6, 6>);
+      case 4: return base + warps * (uint32_t) sizeof (WarpQueue<6, 7>);
      }
    return base;
 }
@@ -676,6 +746,7 @@ int stage_grid_size (int stage, int num_sms, uint32_t blob_bytes)
       case 12: return occupancy_grid (k1_hrma<2>, num_sms, smem);
       case 2: return occupancy_grid (k2_grating, num_sms, smem);
       case 3: return occupancy_grid (k3_acis, num_sms, smem);
+      case 4: return occupancy_grid (k3_hrc, num_sms, smem);
      }
    return num_sms;
 }
@@ -691,6 +762,7 @@ void launch_hrma (const StageArgs &a, int phase, int grid, cudaStream_t s)
 }
 void launch_grating (const StageArgs &a, int grid, cudaStream_t s) { k2_grating<<<grid, kStageThreads, stage_smem_bytes (2, a.blob_bytes), s>>> (a); }
 void launch_acis (const StageArgs &a, int grid, cudaStream_t s) { k3_acis<<<grid, kStageThreads, stage_smem_bytes (3, a.blob_bytes), s>>> (a); }
+void launch_hrc (const StageArgs &a, int grid, cudaStream_t s) { k3_hrc<<<grid, kStageThreads, stage_smem_bytes (4, a.blob_bytes), s>>> (a); }
 
 void launch_soa_to_aos (const PhotonSoA &in, const unsigned long long *n, uint64_t max_n, void *aos,
                         const double *dev_start_time, cudaStream_t s)

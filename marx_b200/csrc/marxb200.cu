@@ -70,6 +70,7 @@ struct marxb200_ctx
    void *blob1 = nullptr, *blob2 = nullptr, *blob3 = nullptr;
    uint32_t blob1_bytes = 0, blob2_bytes = 0, blob3_bytes = 0;
    int grid1[3] = {0, 0, 0}, grid2 = 0, grid3 = 0;
+   bool detector_is_hrc = false;
 
    // host boundary staging
    void *d_aos = nullptr; uint64_t d_aos_cap = 0;
@@ -301,6 +302,25 @@ extern "C" int marxb200_set_acis (marxb200_ctx *c, const marxb200_acis_desc *d)
    if (-1 == dev_upload (c, blob.data (), blob.size (), &c->blob3)) return -1;
    c->blob3_bytes = (uint32_t) blob.size ();
    c->grid3 = stage_grid_size (3, c->num_sms, c->blob3_bytes);
+   c->detector_is_hrc = false;
+   return 0;
+}
+
+extern "C" int marxb200_set_hrc_s (marxb200_ctx *c, const marxb200_hrc_s_desc *d)
+{
+   if ((c == nullptr) || (d == nullptr)) return fail ("marxb200_set_hrc_s: NULL argument");
+   CUDA_OK (cudaSetDevice (c->device));
+   c->detector_type = d->detector_type;
+   c->have_acis = true;
+   if (d->detector_type == 0) return 0;
+   CudaUploader up{c};
+   std::vector<unsigned char> blob;
+   std::string err;
+   if (-1 == mx::build_hrc_blob (up, d, blob, err)) { c->have_acis = false; return fail ("marxb200_set_hrc_s: %s", err.c_str ()); }
+   if (-1 == dev_upload (c, blob.data (), blob.size (), &c->blob3)) return -1;
+   c->blob3_bytes = (uint32_t) blob.size ();
+   c->grid3 = stage_grid_size (4, c->num_sms, c->blob3_bytes);
+   c->detector_is_hrc = true;
    return 0;
 }
 
@@ -321,9 +341,11 @@ static size_t carve (PhotonSoA &b, unsigned char *base, uint64_t n)
    b.flags = (uint32_t *) take (4);
    b.dra = (float *) take (4); b.ddec = (float *) take (4); b.droll = (float *) take (4);
    b.chipx = (float *) take (4); b.chipy = (float *) take (4); b.pi = (float *) take (4);
+   b.upix = (float *) take (4); b.vpix = (float *) take (4);
+   b.sorders = (uint32_t *) take (4);
    b.pha = (int16_t *) take (2);
    b.shell = (uint8_t *) take (1);
-   b.order = (int8_t *) take (1); b.ccd = (int8_t *) take (1);
+   b.order = (int8_t *) take (1); b.ccd = (int8_t *) take (1); b.region = (int8_t *) take (1);
    return off;
 }
 
@@ -452,7 +474,9 @@ static int run_stage (marxb200_ctx *c, int stage)
           {
            case 1: a.blob = c->blob1; a.blob_bytes = c->blob1_bytes; launch_hrma (a, k, c->grid1[k], c->stream); break;
            case 2: a.blob = c->blob2; a.blob_bytes = c->blob2_bytes; launch_grating (a, c->grid2, c->stream); break;
-           case 3: a.blob = c->blob3; a.blob_bytes = c->blob3_bytes; launch_acis (a, c->grid3, c->stream); break;
+           case 3: a.blob = c->blob3; a.blob_bytes = c->blob3_bytes;
+                   if (c->detector_is_hrc) launch_hrc (a, c->grid3, c->stream); else launch_acis (a, c->grid3, c->stream);
+                   break;
           }
         c->launches += 1;
         CUDA_OK (cudaGetLastError ());

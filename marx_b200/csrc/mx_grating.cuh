@@ -170,9 +170,12 @@ MX_HD int diffract_from_grating (const GratingShellDev &g, double theta, double 
    return -1;
 }
 
-// diffract() for one ray of shell `shell` (HETG / primary LETG grating).  Returns flags (0 alive).
+// diffract() for one ray of shell `shell`.  HETG: the primary grating; LETG: the primary grating followed by the
+// fine support grating (facet rotated by pi/2) and three passes through the coarse support grating (pi/3,
+// 2pi/3, 0), diffract.c:1098-1118.  support_orders packs the four support orders (one signed byte each).
+// Returns flags (0 alive).
 MX_HD uint32_t grating_diffract (const GratingDev &G, uint32_t shell, double energy, Vec3 &x, Vec3 &p,
-                                 int &order_out, Rng &rng)
+                                 int &order_out, uint32_t &support_orders, Rng &rng)
 {
    const uint32_t VBLOCKED = 0x10, UNDIFFRACTED = 0x04;
    const GratingShellDev &g = G.shell[shell];
@@ -183,6 +186,20 @@ MX_HD uint32_t grating_diffract (const GratingDev &G, uint32_t shell, double ene
    p = rotate_x (p, theta);
    if (-1 == torus_intersect (x, p, g.rowland)) return UNDIFFRACTED;
    if (-1 == diffract_from_grating (g, 0.0, energy, x, p, order_out, g.num_sectors != 0, rng)) return UNDIFFRACTED;
+   support_orders = 0;
+   if (G.type == 2)
+     {
+        const double pass_theta[4] = {kPI / 2.0, kPI / 3.0, 2.0 * kPI / 3.0, 0.0};
+        for (int pass = 0; pass < 4; pass++)
+          {
+             const GratingShellDev &sg = G.support[pass == 0 ? 0 : 1];
+             if (sg.num_orders == 0) continue;
+             int so = 0;
+             int rc = diffract_from_grating (sg, pass_theta[pass], energy, x, p, so, false, rng);
+             support_orders |= ((uint32_t) (so & 0xFF)) << (8 * pass);
+             if (rc == -1) return UNDIFFRACTED;
+          }
+     }
    theta = 1 * g.dispersion_angle;
    x = rotate_x (x, theta);
    p = rotate_x (p, theta);

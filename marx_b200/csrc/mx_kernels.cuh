@@ -28,9 +28,11 @@ struct PhotonSoA
    uint32_t *flags;
    float *dra, *ddec, *droll;            // Marx_Dither_Type ra/dec/roll (dy,dz,dtheta are 0 for INTERNAL)
    float *chipx, *chipy, *pi;
+   float *upix, *vpix;                   // HRC u/v pixels
+   uint32_t *sorders;                    // LETG support-grating orders, one signed byte per pass
    int16_t *pha;
    uint8_t *shell;
-   int8_t *order, *ccd;
+   int8_t *order, *ccd, *region;
 };
 
 // Blob staged into shared memory by K1 with one TMA bulk copy.
@@ -48,6 +50,11 @@ struct K2Blob
 struct K3Blob
 {
    AcisDev A;
+   uint32_t total_bytes, pad0, pad1, pad2;
+};
+struct K3HrcBlob
+{
+   HrcDev D;
    uint32_t total_bytes, pad0, pad1, pad2;
 };
 
@@ -87,6 +94,7 @@ void launch_source (const SourceArgs &a, cudaStream_t s);
 void launch_hrma (const StageArgs &a, int phase, int grid, cudaStream_t s);   // phase 0,1,2 = k1a,k1b,k1c
 void launch_grating (const StageArgs &a, int grid, cudaStream_t s);
 void launch_acis (const StageArgs &a, int grid, cudaStream_t s);
+void launch_hrc (const StageArgs &a, int grid, cudaStream_t s);
 int stage_grid_size (int stage, int num_sms, uint32_t blob_bytes);
 uint32_t stage_smem_bytes (int stage, uint32_t blob_bytes);
 

@@ -79,6 +79,7 @@ struct GratingDev
 {
    int type;
    GratingShellDev shell[kNumShells];
+   GratingShellDev support[2];     // LETG fine / coarse support gratings (num_orders == 0: absent)
 };
 
 struct FefDev
@@ -114,6 +115,31 @@ struct AcisDev
    double det_offset[3], det_matrix[9];
    int det_ideal, det_extend, dither_mode, pad;
    double focal_length, exposure_time, frame_transfer_time, frame_time;
+};
+
+struct HrcMcpDev
+{
+   int id; uint32_t qe_num;
+   double x_ll[3], xhat[3], yhat[3], normal[3], xlen, ylen;
+   const float *qe_energies, *qe;
+   double u_start, v_start, u_0, v_0, cx_0, cy_0;
+};
+struct HesfPlateDev { double a[3], e1[3], e2[3], normal[3], len1, len2; };
+struct HrcDev
+{
+   int detector_type, num_mcps;
+   HrcMcpDev mcp[3];
+   uint32_t filter_num[4];
+   const float *filter_energies[4], *filter_qe[4];
+   double shield_t, shield_l, shield_r, shield_x, shield_sl, shield_sr, shield_sl_gap, shield_sr_gap, shield_y_center, shield_z_center;
+   double blur[13];
+   double u_pixel_size, v_pixel_size;
+   double det_offset[3], det_matrix[9];
+   int det_ideal, det_extend, use_hesf, hesf_num_plates;
+   HesfPlateDev hesf[8];
+   double hesf_cr_width;
+   uint32_t c_num, cr_num;
+   const float *c_energies, *c_betas, *c_deltas, *cr_energies, *cr_betas, *cr_deltas;
 };
 
 }  // namespace mx

@@ -102,9 +102,27 @@ template <class Up> int build_hrma_blob (Up &up, const marxb200_hrma_desc *d, st
    return 0;
 }
 
+template <class Up> int build_grating_shell (Up &up, const marxb200_grating_shell &s, GratingShellDev &g, double rowland, std::string &err)
+{
+   if ((s.num_orders == 0) || (s.num_energies < 2)) { err = "a grating has an empty efficiency table"; return -1; }
+   g.num_orders = s.num_orders; g.num_energies = s.num_energies; g.num_sectors = s.num_sectors;
+   if (-1 == tb_up (up, s.order_list, s.num_orders, &g.order_list, err)) return -1;
+   if (-1 == tb_up (up, s.energies, s.num_energies, &g.energies, err)) return -1;
+   // transpose [order][energy] -> [energy][order] (mx_grating.cuh diffract_from_grating)
+   std::vector<float> t ((size_t) s.num_orders * s.num_energies);
+   for (uint32_t o = 0; o < s.num_orders; o++)
+     for (uint32_t e = 0; e < s.num_energies; e++)
+       t[(size_t) e * s.num_orders + o] = s.cum_eff[(size_t) o * s.num_energies + e];
+   if (-1 == tb_up (up, t.data (), t.size (), &g.cum_eff, err)) return -1;
+   g.dispersion_angle = s.dispersion_angle; g.period = s.period; g.dp_over_p = s.dp_over_p;
+   g.theta_blur = s.theta_blur; g.vig = s.vig; g.rowland = rowland;
+   g.sectors = nullptr;
+   return 0;
+}
+
 template <class Up> int build_grating_blob (Up &up, const marxb200_grating_desc *d, std::vector<unsigned char> &blob, std::string &err)
 {
-   if (d->type != 1) { err = "only HETG (type 1) is implemented"; return -1; }
+   if ((d->type != 1) && (d->type != 2)) { err = "only HETG (1) and LETG (2) are implemented"; return -1; }
    size_t off = tb_align16 (sizeof (K2Blob));
    size_t off_sec[kNumShells];
    for (int k = 0; k < kNumShells; k++) { off_sec[k] = off; off = tb_align16 (off + 6 * 8 * (size_t) d->shells[k].num_sectors); }
@@ -116,18 +134,7 @@ template <class Up> int build_grating_blob (Up &up, const marxb200_grating_desc 
      {
         const marxb200_grating_shell &s = d->shells[k];
         GratingShellDev &g = B->G.shell[k];
-        if ((s.num_orders == 0) || (s.num_energies < 2)) { err = "a shell has an empty efficiency table"; return -1; }
-        g.num_orders = s.num_orders; g.num_energies = s.num_energies; g.num_sectors = s.num_sectors;
-        if (-1 == tb_up (up, s.order_list, s.num_orders, &g.order_list, err)) return -1;
-        if (-1 == tb_up (up, s.energies, s.num_energies, &g.energies, err)) return -1;
-        // transpose [order][energy] -> [energy][order] (mx_grating.cuh diffract_from_grating)
-        std::vector<float> t ((size_t) s.num_orders * s.num_energies);
-        for (uint32_t o = 0; o < s.num_orders; o++)
-          for (uint32_t e = 0; e < s.num_energies; e++)
-            t[(size_t) e * s.num_orders + o] = s.cum_eff[(size_t) o * s.num_energies + e];
-        if (-1 == tb_up (up, t.data (), t.size (), &g.cum_eff, err)) return -1;
-        g.dispersion_angle = s.dispersion_angle; g.period = s.period; g.dp_over_p = s.dp_over_p;
-        g.theta_blur = s.theta_blur; g.vig = s.vig; g.rowland = d->rowland[k];
+        if (-1 == build_grating_shell (up, s, g, d->rowland[k], err)) return -1;
         double *sec = reinterpret_cast<double *> (blob.data () + off_sec[k]);
         for (uint32_t i = 0; i < s.num_sectors; i++)
           {
@@ -135,9 +142,68 @@ template <class Up> int build_grating_blob (Up &up, const marxb200_grating_desc 
              sec[2 * s.num_sectors + i] = s.sec_dtheta[i]; sec[3 * s.num_sectors + i] = s.sec_dtheta_blur[i];
              sec[4 * s.num_sectors + i] = s.sec_dpp[i]; sec[5 * s.num_sectors + i] = s.sec_dpp_blur[i];
           }
-        g.sectors = nullptr;     // re-pointed into shared memory by the kernel
         B->off_sectors[k] = (uint32_t) off_sec[k];
      }
+   for (int k = 0; k < 2; k++)
+     {
+        memset (&B->G.support[k], 0, sizeof (GratingShellDev));
+        if ((d->type == 2) && (d->support[k].num_orders != 0))
+          {
+             if (-1 == build_grating_shell (up, d->support[k], B->G.support[k], 0.0, err)) return -1;
+             B->G.support[k].num_sectors = 0;
+          }
+     }
+   B->total_bytes = (uint32_t) total;
+   return 0;
+}
+
+template <class Up> int build_hrc_blob (Up &up, const marxb200_hrc_s_desc *d, std::vector<unsigned char> &blob, std::string &err)
+{
+   if ((d->num_mcps < 1) || (d->num_mcps > 3)) { err = "bad MCP count"; return -1; }
+   if (d->det_extend) { err = "DetExtendFlag=yes is not implemented"; return -1; }
+   if ((d->hesf_num_plates < 0) || (d->hesf_num_plates > 4)) { err = "bad HESF plate count"; return -1; }
+   const size_t total = tb_align16 (sizeof (K3HrcBlob));
+   blob.assign (total, 0);
+   K3HrcBlob *B = reinterpret_cast<K3HrcBlob *> (blob.data ());
+   HrcDev &D = B->D;
+   D.detector_type = d->detector_type; D.num_mcps = d->num_mcps;
+   for (int k = 0; k < d->num_mcps; k++)
+     {
+        const marxb200_hrc_mcp &s = d->mcps[k];
+        HrcMcpDev &g = D.mcp[k];
+        g.id = s.id; g.qe_num = s.qe_num;
+        for (int i = 0; i < 3; i++) { g.x_ll[i] = s.x_ll[i]; g.xhat[i] = s.xhat[i]; g.yhat[i] = s.yhat[i]; g.normal[i] = s.normal[i]; }
+        g.xlen = s.xlen; g.ylen = s.ylen;
+        if (s.qe_num && ((-1 == tb_up (up, s.qe_energies, s.qe_num, &g.qe_energies, err)) || (-1 == tb_up (up, s.qe, s.qe_num, &g.qe, err)))) return -1;
+        g.u_start = s.u_start; g.v_start = s.v_start; g.u_0 = s.u_0; g.v_0 = s.v_0; g.cx_0 = s.cx_0; g.cy_0 = s.cy_0;
+     }
+   for (int r = 0; r < 4; r++)
+     {
+        D.filter_num[r] = d->filter_num[r];
+        if (d->filter_num[r] && ((-1 == tb_up (up, d->filter_energies[r], d->filter_num[r], &D.filter_energies[r], err))
+                                 || (-1 == tb_up (up, d->filter_qe[r], d->filter_num[r], &D.filter_qe[r], err)))) return -1;
+     }
+   D.shield_t = d->shield_t; D.shield_l = d->shield_l; D.shield_r = d->shield_r; D.shield_x = d->shield_x;
+   D.shield_sl = d->shield_sl; D.shield_sr = d->shield_sr; D.shield_sl_gap = d->shield_sl_gap; D.shield_sr_gap = d->shield_sr_gap;
+   D.shield_y_center = d->shield_y_center; D.shield_z_center = d->shield_z_center;
+   for (int i = 0; i < 13; i++) D.blur[i] = d->blur[i];
+   D.u_pixel_size = d->u_pixel_size; D.v_pixel_size = d->v_pixel_size;
+   for (int i = 0; i < 3; i++) D.det_offset[i] = d->det_offset[i];
+   for (int i = 0; i < 9; i++) D.det_matrix[i] = d->det_matrix[i];
+   D.det_ideal = d->det_ideal; D.det_extend = d->det_extend;
+   D.use_hesf = d->use_hesf; D.hesf_num_plates = d->hesf_num_plates; D.hesf_cr_width = d->hesf_cr_width;
+   for (int k = 0; k < 2 * d->hesf_num_plates; k++)
+     {
+        const marxb200_hesf_plate &s = d->hesf[k];
+        HesfPlateDev &h = D.hesf[k];
+        for (int i = 0; i < 3; i++) { h.a[i] = s.a[i]; h.e1[i] = s.e1[i]; h.e2[i] = s.e2[i]; h.normal[i] = s.normal[i]; }
+        h.len1 = s.len1; h.len2 = s.len2;
+     }
+   D.c_num = d->c_num; D.cr_num = d->cr_num;
+   if (d->c_num && ((-1 == tb_up (up, d->c_energies, d->c_num, &D.c_energies, err)) || (-1 == tb_up (up, d->c_betas, d->c_num, &D.c_betas, err))
+                    || (-1 == tb_up (up, d->c_deltas, d->c_num, &D.c_deltas, err)))) return -1;
+   if (d->cr_num && ((-1 == tb_up (up, d->cr_energies, d->cr_num, &D.cr_energies, err)) || (-1 == tb_up (up, d->cr_betas, d->cr_num, &D.cr_betas, err))
+                     || (-1 == tb_up (up, d->cr_deltas, d->cr_num, &D.cr_deltas, err)))) return -1;
    B->total_bytes = (uint32_t) total;
    return 0;
 }

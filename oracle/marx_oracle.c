@@ -68,6 +68,8 @@ chip_t;
 
 typedef struct { uint32_t ng, ne; const float *energies, *channels, *gauss; } fef_t;
 
+typedef struct { const double *geom; const float *qe_e, *qe; uint32_t nqe; } mcp_t;
+
 struct oracle
 {
    unsigned char *bytes; entry_t *entries; uint32_t nentries;
@@ -79,6 +81,10 @@ struct oracle
    gshell_t gshell[NUM_SHELLS];
    chip_t chip[MAX_CHIPS]; int nchips;
    fef_t *fefs; uint32_t nfefs;
+   gshell_t support[2];                 /* LETG fine / coarse support gratings */
+   const double *hrc, *hesf; mcp_t mcp[3]; int nmcps;
+   const float *filt_e[4], *filt_q[4]; uint32_t nfilt[4];
+   const float *hc_e, *hc_b, *hc_d, *hcr_e, *hcr_b, *hcr_d; uint32_t nhc, nhcr;
 };
 
 static const entry_t *find (oracle_t *o, const char *name)
@@ -144,8 +150,9 @@ oracle_t *oracle_open (const char *path, uint64_t seed)
    o->dith = (const double *) need (o, "dither.params", NULL);
    o->hrma = (const double *) need (o, "hrma.params", NULL);
    o->grat = (const double *) need (o, "grating.params", NULL);
-   o->acis = (const double *) need (o, "acis.params", NULL);
-   if (!o->src || !o->dith || !o->hrma || !o->grat || !o->acis) { oracle_close (o); return NULL; }
+   o->hrc = find (o, "hrc.params") ? (const double *) need (o, "hrc.params", NULL) : NULL;
+   o->acis = o->hrc ? NULL : (const double *) need (o, "acis.params", NULL);
+   if (!o->src || !o->dith || !o->hrma || !o->grat || (!o->acis && !o->hrc)) { oracle_close (o); return NULL; }
    if ((int) o->src[1] == 2)
      {
         o->spec_e = (const double *) need (o, "source.spec_energies", &c); o->nspec = (uint32_t) c;
@@ -173,7 +180,39 @@ oracle_t *oracle_open (const char *path, uint64_t seed)
           g->sectors = (const double *) needf (o, &c, "grating.shell%d.sectors", k, 0); g->nsectors = (uint32_t) (c / 6);
           if (!g->prm || !g->orders || !g->energies || !g->cum_eff) { oracle_close (o); return NULL; }
        }
-   if ((int) o->acis[0] != 0)
+   if ((int) o->grat[0] == 2)
+     for (k = 0; k < 2; k++)
+       {
+          gshell_t *g = &o->support[k]; char nm[MARXB200_CALPACK_NAMELEN];
+          snprintf (nm, sizeof nm, "grating.support%d.params", k);
+          if (!find (o, nm)) continue;
+          g->prm = (const double *) needf (o, &c, "grating.support%d.params", k, 0);
+          g->orders = (const int32_t *) needf (o, &c, "grating.support%d.order_list", k, 0); g->norders = (uint32_t) c;
+          g->energies = (const float *) needf (o, &c, "grating.support%d.energies", k, 0); g->nenergies = (uint32_t) c;
+          g->cum_eff = (const float *) needf (o, &c, "grating.support%d.cum_eff", k, 0);
+          g->nsectors = 0;
+       }
+   if (o->hrc)
+     {
+        o->nmcps = (int) o->hrc[1];
+        for (k = 0; k < o->nmcps; k++)
+          {
+             o->mcp[k].geom = (const double *) needf (o, &c, "hrc.mcp%d.geom", k, 0);
+             o->mcp[k].qe_e = (const float *) needf (o, &c, "hrc.mcp%d.qe_energies", k, 0); o->mcp[k].nqe = (uint32_t) c;
+             o->mcp[k].qe = (const float *) needf (o, &c, "hrc.mcp%d.qe", k, 0);
+          }
+        for (k = 0; k < 4; k++)
+          {
+             o->filt_e[k] = (const float *) needf (o, &c, "hrc.filter%d.energies", k, 0); o->nfilt[k] = (uint32_t) c;
+             o->filt_q[k] = (const float *) needf (o, &c, "hrc.filter%d.qe", k, 0);
+          }
+        o->hesf = (const double *) need (o, "hrc.hesf", &c);
+        o->hc_e = (const float *) need (o, "hrc.hesf_c_energies", &c); o->nhc = (uint32_t) c;
+        o->hc_b = (const float *) need (o, "hrc.hesf_c_betas", &c); o->hc_d = (const float *) need (o, "hrc.hesf_c_deltas", &c);
+        o->hcr_e = (const float *) need (o, "hrc.hesf_cr_energies", &c); o->nhcr = (uint32_t) c;
+        o->hcr_b = (const float *) need (o, "hrc.hesf_cr_betas", &c); o->hcr_d = (const float *) need (o, "hrc.hesf_cr_deltas", &c);
+     }
+   if (o->acis && ((int) o->acis[0] != 0))
      {
         const uint32_t *nf = (const uint32_t *) need (o, "acis.num_fefs", NULL);
         uint32_t j;
@@ -647,36 +686,56 @@ static int facet_diffract (const gshell_t *g, double theta, oracle_photon *at, i
    norm3 (at->p);
    return 0;
 }
+/* diffract_photon_from_grating with the per-photon row of JDMinterpolate_n_fvector (finterpo.c:134-189) */
+static int order_and_diffract (const gshell_t *g, double theta, oracle_photon *at, int8_t *order_out, rng_t *r, int use_sectors)
+{
+   double u = rng_uniform (r), xe = (double) (float) at->energy, x0, x1, dx; uint32_t c = 1, k;
+   gshell_t tmp = *g;
+   if (!use_sectors) tmp.nsectors = 0;
+   while ((c < g->nenergies - 1) && (xe > g->energies[c])) c++;
+   x0 = g->energies[c - 1]; x1 = g->energies[c]; dx = x1 - x0;
+   for (k = 0; k < g->norders; k++)
+     {
+        float ce;
+        if (dx == 0.0) ce = g->cum_eff[(size_t) k * g->nenergies + c - 1];
+        else
+          {
+             double y0 = g->cum_eff[(size_t) k * g->nenergies + c - 1], y1 = g->cum_eff[(size_t) k * g->nenergies + c];
+             ce = (float) (y0 + (y1 - y0) * (xe - x0) / dx);
+          }
+        if (u <= ce) { *order_out = (int8_t) g->orders[k]; return facet_diffract (&tmp, theta, at, g->orders[k], r); }
+     }
+   return -1;
+}
+
 static void stage_grating (oracle_t *o, uint64_t n, oracle_photon *ph)
 {
    uint64_t i;
    if ((int) o->grat[0] == 0) return;
    for (i = 0; i < n; i++)
      {
-        oracle_photon *at = ph + i; rng_t r; const gshell_t *g; double u, xe, x0, x1, dx; uint32_t c, k; int rc = -1;
+        oracle_photon *at = ph + i; rng_t r; const gshell_t *g; int rc = -1;
         if (at->flags & 0xFF) continue;
         g = &o->gshell[at->mirror_shell];
         rng_set (&r, o->seed, at->tag, 2);
         if (rng_uniform (&r) > g->prm[4]) { at->flags |= F_VBLOCKED; continue; }                        /* :994-1001 */
         rot_x (at->x, -1 * g->prm[0]); rot_x (at->p, -1 * g->prm[0]);                                   /* :1013 */
         if (-1 == torus_hit (at->x, at->p, o->grat[1 + at->mirror_shell])) { at->flags |= F_UNDIFFRACTED; continue; }
-        u = rng_uniform (&r);                                                                            /* :837 */
-        xe = (double) (float) at->energy;                                                               /* :1047 */
-        /* JDMinterpolate_n_fvector for one abscissa, finterpo.c:134-189 */
-        c = 1; while ((c < g->nenergies - 1) && (xe > g->energies[c])) c++;
-        x0 = g->energies[c - 1]; x1 = g->energies[c]; dx = x1 - x0;
-        for (k = 0; k < g->norders; k++)
-          {
-             float ce;
-             if (dx == 0.0) ce = g->cum_eff[(size_t) k * g->nenergies + c - 1];
-             else
-               {
-                  double y0 = g->cum_eff[(size_t) k * g->nenergies + c - 1], y1 = g->cum_eff[(size_t) k * g->nenergies + c];
-                  ce = (float) (y0 + (y1 - y0) * (xe - x0) / dx);
-               }
-             if (u <= ce) { at->order = (int8_t) g->orders[k]; rc = facet_diffract (g, 0.0, at, g->orders[k], &r); break; }
-          }
+        rc = order_and_diffract (g, 0.0, at, &at->order, &r, 1);                                         /* :1024-1079 */
         if (rc == -1) { at->flags |= F_UNDIFFRACTED; continue; }
+        if ((int) o->grat[0] == 2)                                                                       /* LETG support gratings, :1083-1123 */
+          {
+             static const double pass_theta[4] = {PI / 2.0, PI / 3.0, 2.0 * PI / 3.0, 0.0};
+             int pass;
+             for (pass = 0; pass < 4; pass++)
+               {
+                  const gshell_t *sg = &o->support[pass == 0 ? 0 : 1];
+                  if (sg->norders == 0) continue;
+                  if (-1 == order_and_diffract (sg, pass_theta[pass], at, &at->support_orders[pass], &r, 0))
+                    { at->flags |= F_UNDIFFRACTED; break; }
+               }
+             if (at->flags & 0xFF) continue;
+          }
         rot_x (at->x, 1 * g->prm[0]); rot_x (at->p, 1 * g->prm[0]);                                     /* :1127 */
      }
 }
@@ -818,6 +877,92 @@ static int plane_hit (const double *g, const double *x0, const double *p, double
    *dx = rx; *dy = ry;
    return 1;
 }
+/* stage 3 (HRC-S): _marx_drake_reflect (drake.c:317-372) + _marx_hrc_s_detect (hrc-s.c:236-312) */
+static void stage_detect_hrc (oracle_t *o, uint64_t n, oracle_photon *ph)
+{
+   const double *H = o->hrc; const double *off = H + 2, *M = H + 5, *S = H + 16, *B = H + 26;
+   int ideal = (int) H[14], extend = (int) H[15], use_hesf = (int) H[41], nplates = (int) H[42];
+   double upix = H[39], vpix = H[40], crw = H[43];
+   uint64_t i;
+   for (i = 0; i < n; i++)
+     {
+        oracle_photon *at = ph + i; rng_t r; int k, hit = -1; double dx = 0, dy = 0, xh[3]; const double *g = NULL; const mcp_t *m;
+        double t, y, z, u, v; int region;
+        if (at->flags & 0xFF) continue;
+        rng_set (&r, o->seed, at->tag, 3);
+        if (use_hesf)
+          for (k = 0; k < 2 * nplates; k++)                                                              /* drake.c:268-313 */
+            {
+               const double *q = o->hesf + 14 * k; double pdn = dot3 (at->p, q + 9), dd[3], nx[3], xp[3], xx, yy, rfl = 1.0; int cr;
+               if (0.0 == pdn) continue;
+               dd[0] = q[0] - at->x[0]; dd[1] = q[1] - at->x[1]; dd[2] = q[2] - at->x[2];
+               t = dot3 (dd, q + 9) / pdn;
+               nx[0] = 1.0 * at->x[0] + t * at->p[0]; nx[1] = 1.0 * at->x[1] + t * at->p[1]; nx[2] = 1.0 * at->x[2] + t * at->p[2];
+               xp[0] = nx[0] - q[0]; xp[1] = nx[1] - q[1]; xp[2] = nx[2] - q[2];
+               xx = dot3 (xp, q + 3); if ((xx < 0.0) || (xx >= q[12])) continue;
+               yy = dot3 (xp, q + 6); if ((yy < 0.0) || (yy >= q[13])) continue;
+               cr = (xx < crw);
+               at->x[0] = nx[0]; at->x[1] = nx[1]; at->x[2] = nx[2];
+               if (cr ? o->nhcr : o->nhc)                                                                /* reflect.c:81-92 */
+                 {
+                    float b = interp_f (at->energy, cr ? o->hcr_e : o->hc_e, cr ? o->hcr_b : o->hc_b, cr ? o->nhcr : o->nhc);
+                    float d = interp_f (at->energy, cr ? o->hcr_e : o->hc_e, cr ? o->hcr_d : o->hc_d, cr ? o->nhcr : o->nhc);
+                    rfl = reflectivity (fabs (pdn), b, d);
+                 }
+               if (rfl < rng_uniform (&r)) { at->flags |= 0x20; break; }
+               { double f = -2.0 * pdn; at->p[0] = 1.0 * at->p[0] + f * q[9]; at->p[1] = 1.0 * at->p[1] + f * q[10]; at->p[2] = 1.0 * at->p[2] + f * q[11]; }
+               at->flags |= 0x100;
+               break;
+            }
+        if (at->flags & 0xFF) continue;
+        at->x[0] -= off[0]; at->x[1] -= off[1]; at->x[2] -= off[2];
+        mat3 (M, at->x); mat3 (M, at->p);
+        for (k = 0; k < o->nmcps; k++) if (1 == plane_hit (o->mcp[k].geom, at->x, at->p, xh, &dx, &dy)) { hit = k; break; }
+        if (hit < 0) { at->flags |= F_MISSED; at->ccd_num = -1; continue; }
+        m = &o->mcp[hit]; g = m->geom;
+        at->x[0] = xh[0]; at->x[1] = xh[1]; at->x[2] = xh[2];
+        /* apply_hrc_qe, hrc-s.c:192-234 */
+        if (m->nqe && (rng_uniform (&r) >= interp_f ((float) at->energy, m->qe_e, m->qe, m->nqe))) { at->flags |= F_UNDETECTED; at->ccd_num = -1; continue; }
+        t = (S[3] - at->x[0]) / at->p[0]; y = at->x[1] + t * at->p[1]; z = at->x[2] + t * at->p[2];
+        y -= S[8]; z -= S[9];                                                                            /* get_filter_region :136-188 */
+        {
+           double o1, sl, slg;
+           if (y < 0) { y = -y; o1 = S[1]; sl = S[4]; slg = S[6]; } else { o1 = S[2]; sl = S[5]; slg = S[7]; }
+           if (y < o1) region = 0;
+           else if (y < sl) region = (z >= S[0]) ? 0 : 1;
+           else if (y >= slg) region = (z >= S[0]) ? 2 : 3;
+           else region = -1;
+        }
+        if (region < 0) { at->flags |= F_UNDETECTED; at->ccd_num = -1; continue; }
+        if (o->nfilt[region] && (rng_uniform (&r) >= interp_f ((float) at->energy, o->filt_e[region], o->filt_q[region], o->nfilt[region])))
+          { at->flags |= F_UNDETECTED; at->ccd_num = -1; continue; }
+        at->detector_region = (int8_t) region;
+        {                                                                                                /* hrc-i.c:66-85 */
+           double e = at->energy;
+           if (e <= 0.5) e = 141.582 * sqrt (e); else if (e < 2.0) e = 107.299 * pow (e, 0.1); else e = 115.0;
+           e = e * (1.0 + 0.424661 * rng_gauss (&r));
+           if (e < 0.0) e = 0.0;
+           at->pulse_height = (short) e;
+        }
+        if (!ideal)                                                                                      /* hrcblur.c:260-298 */
+          {
+             double rr = rng_uniform (&r), x_0, y_0, th;
+             if (rr < B[3]) { double c; do c = rng_uniform (&r); while (c == 0.0); rr = B[0] * sqrt (-2 * log (c)); x_0 = B[1]; y_0 = B[2]; }
+             else if (rr < B[3] + B[7]) { double c; do c = rng_uniform (&r); while (c == 0.0); rr = B[4] * sqrt (-2 * log (c)); x_0 = B[5]; y_0 = B[6]; }
+             else { double c = rng_uniform (&r), rmax = B[11] / B[8]; rr = B[8] * sqrt (expm1 (c * log1p (rmax * rmax))); x_0 = B[9]; y_0 = B[10]; }
+             th = (2.0 * PI) * rng_uniform (&r);
+             dx += x_0 + rr * cos (th); dy += y_0 + rr * sin (th);
+             if (!extend) { if (dx < 0.0) dx = 0.0; if (dy < 0.0) dy = 0.0; }
+          }
+        at->ccd_num = (int8_t) g[0];
+        u = g[15] + dx / upix; v = g[16] + dy / vpix;                                                    /* hrc_s_geom.c:344-394 */
+        at->u_pixel = u; at->v_pixel = v;
+        at->y_pixel = g[19] + (u - g[17]); at->z_pixel = g[20] + (v - g[18]);
+        mat3t (M, at->p); mat3t (M, at->x);
+        at->x[0] += off[0]; at->x[1] += off[1]; at->x[2] += off[2];
+     }
+}
+
 static void stage_detect (oracle_t *o, uint64_t n, oracle_photon *ph)
 {
    const double *A = o->acis; const double *off = A + 2, *M = A + 5;
@@ -881,7 +1026,7 @@ long oracle_trace (oracle_t *o, uint64_t first_ray, uint64_t n, double *time_bas
    if (st1) memcpy (st1, work, n * sizeof (oracle_photon));
    stage_grating (o, n, work);
    if (st2) memcpy (st2, work, n * sizeof (oracle_photon));
-   stage_detect (o, n, work);
+   if (o->hrc) stage_detect_hrc (o, n, work); else stage_detect (o, n, work);
    if (st3) memcpy (st3, work, n * sizeof (oracle_photon));
    for (i = 0; i < n; i++) if ((work[i].flags & 0xFF) == 0) detected++;
    free (work);

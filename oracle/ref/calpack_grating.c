@@ -43,5 +43,22 @@ int calpack_dump_grating (mxcp_writer *w, int grating_module)
 	cp_name (name, "grating.shell%u.sectors", k); CP_F64 (w, name, sec, 6 * ns);
 	free (sec);
      }
+   if (Sim_Use_LETG)
+     for (k = 0; k < 2; k++)
+       {
+	  /* support gratings are looked up on the global computed-efficiency grid (diffract.c:941-944) */
+	  Grating_Type *gt = (k == 0) ? LEG_Fine_Grating : LEG_Coarse_Grating;
+	  double v[5]; float *ce; unsigned int i;
+	  if ((gt == NULL) || (gt->num_orders == 0)) continue;
+	  v[0] = gt->dispersion_angle; v[1] = gt->period; v[2] = gt->dp_over_p; v[3] = gt->theta_blur; v[4] = gt->vig;
+	  cp_name (name, "grating.support%u.params", k); CP_F64 (w, name, v, 5);
+	  cp_name (name, "grating.support%u.order_list", k); CP_I32 (w, name, gt->order_list, gt->num_orders);
+	  cp_name (name, "grating.support%u.energies", k); CP_F32 (w, name, Energies, Num_Energies);
+	  ce = (float *) malloc (sizeof (float) * gt->num_orders * Num_Energies);
+	  for (i = 0; i < gt->num_orders; i++)
+	    memcpy (ce + i * Num_Energies, gt->cum_efficiencies[i], sizeof (float) * Num_Energies);
+	  cp_name (name, "grating.support%u.cum_eff", k); CP_F32 (w, name, ce, (uint64_t) gt->num_orders * Num_Energies);
+	  free (ce);
+       }
    return 0;
 }

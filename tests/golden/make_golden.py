@@ -27,6 +27,9 @@ CONFIGS = {
     # BASELINE.json configs[1] (the bench workload)
     "c2_hetg_acis_s": dict(args=["SourceType=POINT", "MinEnergy=0.3", "MaxEnergy=8.0", "GratingType=HETG", "DetectorType=ACIS-S",
                                  "DitherModel=INTERNAL"], nrays=16384, seed=7),
+    # BASELINE.json configs[2]: LETG + HRC-S (HESF on, fine + coarse support gratings)
+    "c3_letg_hrc_s": dict(args=["SourceType=POINT", "MinEnergy=0.1", "MaxEnergy=2.0", "GratingType=LETG", "DetectorType=HRC-S",
+                                "DitherModel=INTERNAL"], nrays=16384, seed=9),
     # BASELINE.json configs[3]: extended BETA source 10 arcmin off axis, ACIS-I, dither
     "c4_beta_acis_i": dict(args=["SourceType=BETA", "S-BetaCoreRadius=10", "S-BetaBeta=0.7", "SourceDEC=-53.92410480125",
                                  "MinEnergy=0.5", "MaxEnergy=7.0", "GratingType=NONE", "DetectorType=ACIS-I",

@@ -50,7 +50,7 @@ def compare_stage(mine, ref, stage, check_time_abs=None):
         out["x_max_rel"] = float(vrel(a["x"], b["x"]).max()) if len(a) else 0.0
         out["shell_mismatch"] = int((a["mirror_shell"] != b["mirror_shell"]).sum())
     if stage >= 2:
-        out["order_mismatch"] = int((a["order"] != b["order"]).sum())
+        out["order_mismatch"] = int((a["order"] != b["order"]).sum() + (a["support_orders"] != b["support_orders"]).sum())
     if stage >= 3:
         out["ccd_mismatch"] = int((a["ccd_num"] != b["ccd_num"]).sum())
         out["pha_mismatch"] = int((a["pulse_height"] != b["pulse_height"]).sum())
@@ -58,6 +58,8 @@ def compare_stage(mine, ref, stage, check_time_abs=None):
         out["int_pixel_mismatch"] = int((np.floor(a["y_pixel"]) != np.floor(b["y_pixel"])).sum()
                                         + (np.floor(a["z_pixel"]) != np.floor(b["z_pixel"])).sum())
         out["pi_max_rel"] = float(rel(a["pi"], b["pi"]).max()) if len(a) else 0.0
+        out["region_mismatch"] = int((a["detector_region"] != b["detector_region"]).sum())
+        out["uv_max_rel"] = float(max(rel(a["u_pixel"], b["u_pixel"]).max(), rel(a["v_pixel"], b["v_pixel"]).max())) if len(a) else 0.0
     # dither angles are float roundings of FP64 values (dither.c:173-175): a 1e-16 difference in the arrival-time
     # sum can flip the last float bit, so they are compared to a float ulp, not exactly
     # (absolute 1e-11 rad ~ one float ulp at the 16 arcsec dither amplitude, plus a relative float ulp for the roll)
@@ -79,5 +81,6 @@ def assert_stage_ok(f, stage):
         assert f["order_mismatch"] == 0, f
     if stage >= 3:
         assert f["ccd_mismatch"] == 0 and f["pha_mismatch"] == 0 and f["int_pixel_mismatch"] == 0, f
-        assert f["pixel_max_rel"] <= F32_RTOL and f["pi_max_rel"] <= F32_RTOL, f
+        assert f["pixel_max_rel"] <= F32_RTOL and f["pi_max_rel"] <= F32_RTOL and f["uv_max_rel"] <= F32_RTOL, f
+        assert f["region_mismatch"] == 0, f
     assert f["dither_excess"] <= 1e-11, f

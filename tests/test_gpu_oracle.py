@@ -26,6 +26,8 @@ def _gpu_all_stages(config, seed, first, n, compact):
     ("c2_hetg_acis_s", 12345, 0, 1 << 20),
     ("c2_hetg_acis_s", 2, (1 << 33) + 65536 * 3, 1 << 18),      # 64-bit ray indices (beyond the reference's int NumRays)
     ("c1_acis_s", 99, 7 * 65536, 1 << 19),
+    ("c3_letg_hrc_s", 5, 0, 1 << 20),
+    ("c4_beta_acis_i", 6, 65536, 1 << 19),
 ])
 def test_cuda_matches_oracle_slot_by_slot(config, seed, first, n):
     from tests.oracle_lib import Oracle
@@ -54,7 +56,7 @@ def test_cuda_matches_oracle_slot_by_slot(config, seed, first, n):
     assert int(alive.sum()) == n_det
 
 
-@pytest.mark.parametrize("config,seed,n", [("c2_hetg_acis_s", 31, 1 << 19), ("c1_acis_s", 32, 1 << 18), ("c4_beta_acis_i", 33, 1 << 18)])
+@pytest.mark.parametrize("config,seed,n", [("c2_hetg_acis_s", 31, 1 << 19), ("c1_acis_s", 32, 1 << 18), ("c4_beta_acis_i", 33, 1 << 18), ("c3_letg_hrc_s", 34, 1 << 19)])
 def test_stage_injection_parity(config, seed, n):
     """Pure replay parity per stage: upload the oracle's photons at a stage boundary (the reference's RAYFILE
     channel, s-rayfile.c:188-221), run ONE stage on the GPU, compare with the oracle's next stage."""

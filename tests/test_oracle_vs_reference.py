@@ -19,8 +19,8 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 REF = os.path.join(ROOT, "oracle", "_ref")
 HAVE_REF = os.path.exists(os.path.join(REF, "marx_replay")) and os.path.exists(os.path.join(REF, "calpack_dump"))
 
-LIVE_FIELDS = ["energy", "x", "p", "flags", "y_pixel", "z_pixel", "dither", "pi", "pulse_height", "mirror_shell",
-               "ccd_num", "order", "tag"]
+LIVE_FIELDS = ["energy", "x", "p", "flags", "y_pixel", "z_pixel", "u_pixel", "v_pixel", "dither", "pi", "pulse_height",
+               "mirror_shell", "ccd_num", "detector_region", "order", "support_orders", "tag"]
 
 
 def check_bit_exact(mine, ref_stages, start_times):
@@ -44,7 +44,7 @@ def check_bit_exact(mine, ref_stages, start_times):
     assert n == len(ref_stages)
 
 
-@pytest.mark.parametrize("config", ["c1_acis_s", "c2_hetg_acis_s", "c4_beta_acis_i"])
+@pytest.mark.parametrize("config", ["c1_acis_s", "c2_hetg_acis_s", "c3_letg_hrc_s", "c4_beta_acis_i"])
 def test_oracle_matches_committed_reference_replay(config):
     z = np.load(os.path.join(GOLDEN, config + "_replay.npz"))
     o = Oracle(config, int(z["seed"]))
@@ -69,6 +69,12 @@ CASES = [
     ("beta_source_off_axis_acis_i", ["SourceType=BETA", "S-BetaCoreRadius=25", "S-BetaBeta=0.9", "SourceRA=249.9316", "MinEnergy=0.5",
                                      "MaxEnergy=7.0", "GratingType=NONE", "DetectorType=ACIS-I", "DitherModel=INTERNAL"], 17, 0, 10000),
     ("file_spectrum", ["SpectrumType=FILE", "SpectrumFile=%SPECFILE%", "GratingType=HETG", "DetectorType=ACIS-S", "DitherModel=INTERNAL"], 18, 0, 10000),
+    ("letg_hrc_s_no_hesf", ["MinEnergy=0.08", "MaxEnergy=3.0", "GratingType=LETG", "DetectorType=HRC-S", "DitherModel=INTERNAL",
+                            "HRC-HESF=no"], 19, 0, 20000),
+    ("hetg_hrc_s_hesf", ["MinEnergy=0.3", "MaxEnergy=8.0", "GratingType=HETG", "DetectorType=HRC-S", "DitherModel=NONE"], 20, 0, 20000),
+    ("letg_acis_s", ["MinEnergy=0.3", "MaxEnergy=4.0", "GratingType=LETG", "DetectorType=ACIS-S", "DitherModel=INTERNAL"], 22, 0, 10000),
+    ("letg_computed_efficiencies", ["MinEnergy=0.2", "MaxEnergy=2.0", "GratingType=LETG", "DetectorType=HRC-S", "DitherModel=INTERNAL",
+                                    "UseGratingEffFiles=no"], 23, 0, 10000),
     ("sector_files_off_unit_order", ["MinEnergy=0.8", "MaxEnergy=3.0", "GratingType=HETG", "DetectorType=ACIS-S", "DitherModel=INTERNAL",
                                      "Use_HETG_Sector_Files=no"], 8, 1000, 10000),
 ]

@@ -76,6 +76,7 @@ extern "C" int marxb200_set_acis (marxb200_ctx *, const marxb200_acis_desc *d)
    gDetType = d->detector_type; if (d->detector_type == 0) return 0;
    HostUploader up; std::string e; int r = build_acis_blob (up, d, gB3, e); snprintf (gErr, sizeof gErr, "%s", e.c_str ()); return r;
 }
+extern "C" int marxb200_set_hrc_s (marxb200_ctx *, const marxb200_hrc_s_desc *) { snprintf (gErr, sizeof gErr, "hostcheck: HRC-S not wired"); return -1; }
 extern "C" int marxb200_load_calpack_impl (marxb200_ctx *ctx, const char *path, char *errbuf, size_t errlen);
 
 #pragma pack(push, 1)
@@ -153,7 +154,8 @@ int main (int argc, char **argv)
           {
              const GratingDev &G = ((const K2Blob *) gB2.data ())->G;
              rng.init (seed, ray, 2);
-             flags = grating_diffract (G, shell, energy, x, p, order, rng);
+             uint32_t sorders = 0;
+             flags = grating_diffract (G, shell, energy, x, p, order, sorders, rng);
              const marxb200_photon_attr &a2 = r.st[2];
              ref_alive = (a2.flags & 0xFF) == 0; my_alive = (flags & 0xFF) == 0;
              if (ref_alive != my_alive || (!my_alive && ((a2.flags & flags) != flags)))
