@@ -151,8 +151,14 @@ MX_HD int diffract_from_grating (const GratingShellDev &g, double theta, double 
    double dx_10 = x_1 - x_0;
    const float *row0 = g.cum_eff + (size_t) (c - 1) * g.num_orders;
    const float *row1 = g.cum_eff + (size_t) c * g.num_orders;
-   for (uint32_t k = 0; k < g.num_orders; k++)
+   // The reference scans the orders linearly for the first k with r <= cum_eff[k] (diffract.c:839-847).  The
+   // interpolated cumulative efficiencies are non-decreasing in k (a convex combination of two non-decreasing
+   // table rows, then a monotone rounding to float), so a bisection finds the same k in log2(num_orders)
+   // interpolations instead of num_orders/2 -- 7 instead of ~60 for the 121-order LETG coarse support grating.
+   uint32_t lo = 0, hi = g.num_orders;
+   while (lo < hi)
      {
+        const uint32_t k = (lo + hi) >> 1;
         float ce;
         if (dx_10 == 0.0) ce = row0[k];
         else
@@ -160,14 +166,12 @@ MX_HD int diffract_from_grating (const GratingShellDev &g, double theta, double 
              double y_0 = row0[k], y_1 = row1[k];
              ce = (float) (y_0 + (y_1 - y_0) * (xe - x_0) / dx_10);
           }
-        if (r <= ce)
-          {
-             int order = g.order_list[k];
-             order_out = order;
-             return diffract_photon (g, theta, energy, x, p, order, use_sectors, rng);
-          }
+        if (r <= ce) hi = k; else lo = k + 1;
      }
-   return -1;
+   if (lo == g.num_orders) return -1;
+   int order = g.order_list[lo];
+   order_out = order;
+   return diffract_photon (g, theta, energy, x, p, order, use_sectors, rng);
 }
 
 // diffract() for one ray of shell `shell`.  HETG: the primary grating; LETG: the primary grating followed by the
