@@ -312,12 +312,25 @@ int marxb200_detect (marxb200_ctx *ctx);
 int marxb200_restore_order (marxb200_ctx *ctx);
 /* all of the above for one batch, device resident (marx.c:569 + process_photons :240-273) */
 int marxb200_trace (marxb200_ctx *ctx, uint64_t first_ray, uint64_t n);
+/* same with an explicit time base (multi-GPU blocks, see marxb200_time_sums); time_base_in < 0: continue */
+int marxb200_trace_from (marxb200_ctx *ctx, uint64_t first_ray, uint64_t n, double time_base_in);
+
+/* Per-kernel device times (CUDA events on the launching stream), for roofline bookkeeping.  When enabled, an
+ * event is recorded after every kernel launch; marxb200_get_kernel_ms synchronises, returns the accumulated
+ * milliseconds and launch counts per kernel class since the last call, and resets them.  Classes:
+ * 0 k0_time_sums, 1 k0_time_scan, 2 k0_source, 3 k01_source_hrma (fused), 4 k1_hrma<0>, 5 k1_hrma<1>, 6 k1_hrma<2>,
+ * 7 k2_grating, 8 k3 (acis or hrc), 9 order restoration (4 kernels). */
+#define MARXB200_NUM_KERNEL_CLASSES 10
+int marxb200_set_profiling (marxb200_ctx *ctx, int on);
+int marxb200_get_kernel_ms (marxb200_ctx *ctx, double ms[MARXB200_NUM_KERNEL_CLASSES], uint64_t launches[MARXB200_NUM_KERNEL_CLASSES]);
 
 /* number of live photons / generated rays / running time after the last stage (synchronises) */
 int marxb200_get_counts (marxb200_ctx *ctx, uint64_t *n_generated, uint64_t *n_live, double *total_time);
 /* per-stage live counts of the last batch: [generated, after mirror, after grating, detected]
  * (the reference's PRINT_STATS_ARRAY, marx.c:68,236-271) */
 int marxb200_get_stage_counts (marxb200_ctx *ctx, uint64_t counts[4]);
+/* same plus the counts between the HRMA sub-kernels: [4] after phase A, [5] after phase B ([6],[7] reserved) */
+int marxb200_get_internal_counts (marxb200_ctx *ctx, uint64_t counts[8]);
 
 /* host boundary.  download: live photons, arrival order, into AoS records (what marx_write_photons,
  * marxio.c:403-476, and the pipe/rayfile writers consume).  upload: inject photons at a stage boundary

@@ -17,9 +17,9 @@ STAGE_SOURCE, STAGE_MIRROR, STAGE_GRATING, STAGE_DETECTOR = 0, 1, 2, 3
 EXPORTED_SYMBOLS = [
     "marxb200_abi_version", "marxb200_last_error", "marxb200_create", "marxb200_destroy", "marxb200_set_stream",
     "marxb200_set_compaction", "marxb200_set_source", "marxb200_set_dither", "marxb200_set_hrma",
-    "marxb200_set_grating", "marxb200_set_acis", "marxb200_load_calpack", "marxb200_alloc_photons",
+    "marxb200_set_grating", "marxb200_set_acis", "marxb200_set_hrc_s", "marxb200_load_calpack", "marxb200_alloc_photons",
     "marxb200_create_photons", "marxb200_time_sums", "marxb200_mirror_reflect", "marxb200_grating_diffract",
-    "marxb200_detect", "marxb200_restore_order", "marxb200_trace", "marxb200_get_counts", "marxb200_get_stage_counts", "marxb200_download",
+    "marxb200_detect", "marxb200_restore_order", "marxb200_trace", "marxb200_trace_from", "marxb200_set_profiling", "marxb200_get_kernel_ms", "marxb200_get_counts", "marxb200_get_stage_counts", "marxb200_get_internal_counts", "marxb200_download",
     "marxb200_upload", "marxb200_download_all", "marxb200_download_columns", "marxb200_get_launch_count",
 ]
 
@@ -82,8 +82,12 @@ def load_library():
         "marxb200_detect": [vp],
         "marxb200_restore_order": [vp],
         "marxb200_trace": [vp, u64, u64],
+        "marxb200_trace_from": [vp, u64, u64, dbl],
+        "marxb200_set_profiling": [vp, i32],
+        "marxb200_get_kernel_ms": [vp, C.POINTER(dbl), C.POINTER(u64)],
         "marxb200_get_counts": [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(dbl)],
         "marxb200_get_stage_counts": [vp, C.POINTER(u64)],
+        "marxb200_get_internal_counts": [vp, C.POINTER(u64)],
         "marxb200_download": [vp, vp, u64, C.POINTER(u64)],
         "marxb200_download_all": [vp, vp, u64, C.POINTER(u64)],
         "marxb200_upload": [vp, vp, u64, vp],
@@ -177,9 +181,22 @@ class MarxB200:
         """put the live list back into arrival order (implicit in trace() and download*())"""
         self._check(self._lib.marxb200_restore_order(self._ctx))
 
-    def trace(self, first_ray, n):
+    def trace(self, first_ray, n, time_base=-1.0):
         """create -> mirror -> grating -> detect for one batch, device resident (marx.c:569, :240-273)."""
-        self._check(self._lib.marxb200_trace(self._ctx, int(first_ray), int(n)))
+        self._check(self._lib.marxb200_trace_from(self._ctx, int(first_ray), int(n), float(time_base)))
+
+    KERNEL_CLASSES = ("k0_time_sums", "k0_time_scan", "k0_source", "k01_source_hrma", "k1_hrma<0>", "k1_hrma<1>",
+                      "k1_hrma<2>", "k2_grating", "k3_detect", "order_restore")
+
+    def set_profiling(self, on):
+        self._check(self._lib.marxb200_set_profiling(self._ctx, 1 if on else 0))
+
+    def kernel_ms(self):
+        """accumulated device milliseconds and launch counts per kernel class since the last call"""
+        ms = (C.c_double * 10)()
+        nl = (C.c_uint64 * 10)()
+        self._check(self._lib.marxb200_get_kernel_ms(self._ctx, ms, nl))
+        return {k: (float(ms[i]), int(nl[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
 
     # -- results -------------------------------------------------------------------------------
     def counts(self):
@@ -190,6 +207,12 @@ class MarxB200:
     def stage_counts(self):
         a = (C.c_uint64 * 4)()
         self._check(self._lib.marxb200_get_stage_counts(self._ctx, a))
+        return [int(v) for v in a]
+
+    def internal_counts(self):
+        """[generated, after mirror, after grating, detected, after HRMA phase A, after HRMA phase B] of the last batch"""
+        a = (C.c_uint64 * 8)()
+        self._check(self._lib.marxb200_get_internal_counts(self._ctx, a))
         return [int(v) for v in a]
 
     def launch_count(self):

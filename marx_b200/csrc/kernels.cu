@@ -304,15 +304,17 @@ __device__ __forceinline__ WarpQueue<ND, NU> &my_queue (unsigned char *smem, uin
 template <int PHASE> struct K1Shape { static constexpr int ND = (PHASE == 1) ? 7 : 6, NU = (PHASE == 1) ? 5 : 2; };
 
 template <int PHASE>
-__global__ void __launch_bounds__ (kStageThreads, (PHASE == 1) ? 3 : 1) k1_hrma (const __grid_constant__ StageArgs a)
+__global__ void __launch_bounds__ (kStageThreads, 3) k1_hrma (const __grid_constant__ StageArgs a)
 {
    constexpr int ND = K1Shape<PHASE>::ND, NU = K1Shape<PHASE>::NU;
    extern __shared__ __align__ (128) unsigned char smem[];
    __shared__ __align__ (8) unsigned long long bar;
-   stage_blob (smem, a.blob, a.blob_bytes, &bar);
+   // only phase B needs the optical-constant tables behind the header
+   const uint32_t staged = (PHASE == 1) ? a.blob_bytes : (uint32_t) sizeof (K1Blob);
+   stage_blob (smem, a.blob, staged, &bar);
    const K1Blob &B = *reinterpret_cast<const K1Blob *> (smem);
    const HrmaDev &H = B.H;
-   WarpQueue<ND, NU> &q = my_queue<ND, NU> (smem, a.blob_bytes);
+   WarpQueue<ND, NU> &q = my_queue<ND, NU> (smem, staged);
    const PhotonSoA &in = a.in, &out = a.out;
 
    auto trace = [&] (unsigned long long i, double *d, uint32_t *u) -> uint32_t
@@ -545,6 +547,82 @@ __global__ void __launch_bounds__ (kStageThreads) k3_hrc (const __grid_constant_
    run_stage<ND, NU> (a, q, trace, flush_entry, in_place);
 }
 
+// K0 + K1a fused -------------------------------------------------------------------------------
+// marxb200_trace's first kernel: source draw, arrival time, dither AND HRMA phase A for one ray per thread, so
+// that the 52 % of the rays that miss the paraboloid never touch HBM (the separate k0_source / k1_hrma<0>
+// pair writes 77 B and re-reads 36 B for every generated ray).  Persistent 256-thread CTAs walk the 256-ray
+// tiles of the canonical time sum (k0_time_sums / k0_time_scan must have run); survivors go through the
+// warp-private re-packing queue straight into the list that k1_hrma<1> consumes.
+__global__ void __launch_bounds__ (kTile, 3) k01_source_hrma (const __grid_constant__ SourceArgs a, const __grid_constant__ StageArgs st)
+{
+   constexpr int ND = 8, NU = 5;
+   extern __shared__ __align__ (128) unsigned char smem[];
+   __shared__ __align__ (8) unsigned long long bar;
+   stage_blob (smem, st.blob, (uint32_t) sizeof (K1Blob), &bar);
+   const HrmaDev &H = reinterpret_cast<const K1Blob *> (smem)->H;
+   WarpQueue<ND, NU> &q = my_queue<ND, NU> (smem, (uint32_t) sizeof (K1Blob));
+   const PhotonSoA &out = st.out;
+   const uint32_t lane = threadIdx.x & 31;
+   uint32_t head = 0, count = 0;
+
+   auto flush = [&] (uint32_t n_flush)
+     {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd (st.n_out, (unsigned long long) n_flush);
+        base = __shfl_sync (0xffffffffu, base, 0);
+        if (lane < n_flush)
+          {
+             const uint32_t pos = (head + lane) & (kQueueCap - 1);
+             const unsigned long long j = base + lane;
+             out.x0[j] = q.d[0][pos]; out.x1[j] = q.d[1][pos]; out.x2[j] = q.d[2][pos];
+             out.p0[j] = q.d[3][pos]; out.p1[j] = q.d[4][pos]; out.p2[j] = q.d[5][pos];
+             out.energy[j] = q.d[6][pos]; out.time[j] = q.d[7][pos];
+             const uint32_t slot = q.u[0][pos], pk = q.u[1][pos];
+             out.slot[j] = slot; out.ray[j] = a.first_ray + slot;
+             out.shell[j] = (uint8_t) (pk & 0xFFu); out.pha[j] = (int16_t) (pk >> 8);
+             out.dra[j] = __uint_as_float (q.u[2][pos]); out.ddec[j] = __uint_as_float (q.u[3][pos]); out.droll[j] = __uint_as_float (q.u[4][pos]);
+             out.flags[j] = 0; out.order[j] = 0; out.sorders[j] = 0;
+          }
+        head = (head + n_flush) & (kQueueCap - 1);
+        count -= n_flush;
+        __syncwarp ();
+     };
+
+   const uint64_t n_tiles = (a.n + kTile - 1) / kTile;
+   for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+     {
+        const uint64_t i = tile * kTile + threadIdx.x;
+        const bool valid = i < a.n;
+        Rng rng; double energy = 0.0, dt = 0.0; Vec3 p = v_make (0, 0, 0);
+        if (valid) k0_draw (a, i, rng, energy, p, dt);
+        double total;
+        const double t = tile_inclusive_scan (dt, total) + a.tile_base[tile];
+        bool alive = false;
+        Vec3 x = v_make (0, 0, 0); uint32_t shell = 0; float dra = 0.f, ddec = 0.f, droll = 0.f;
+        if (valid)
+          {
+             dither_ray (a.D, rng, t, p, dra, ddec, droll);
+             rng.init (a.seed, a.first_ray + i, MARXB200_STAGE_MIRROR);
+             alive = (0 == hrma_phase_a (H, st.source_distance, x, p, shell, rng));
+          }
+        const uint32_t ballot = __ballot_sync (0xffffffffu, alive);
+        if (alive)
+          {
+             const uint32_t pos = (head + count + __popc (ballot & ((1u << lane) - 1u))) & (kQueueCap - 1);
+             q.d[0][pos] = x.x; q.d[1][pos] = x.y; q.d[2][pos] = x.z;
+             q.d[3][pos] = p.x; q.d[4][pos] = p.y; q.d[5][pos] = p.z;
+             q.d[6][pos] = energy; q.d[7][pos] = t;
+             q.u[0][pos] = (uint32_t) i;
+             q.u[1][pos] = shell | ((rng.draw & 0x3FFFu) << 8);
+             q.u[2][pos] = __float_as_uint (dra); q.u[3][pos] = __float_as_uint (ddec); q.u[4][pos] = __float_as_uint (droll);
+          }
+        count += __popc (ballot);
+        __syncwarp ();
+        if (count >= 32) flush (32);
+     }
+   if (count > 0) flush (count);
+}
+
 // ---------------------------------------------------------------------------------------------
 // arrival-order restoration: the live list's `slot` keys are distinct indices into the batch, so the rank
 // of a photon is the number of set bits below its slot in a bitmap of the live slots.
@@ -716,11 +794,13 @@ void launch_source (const SourceArgs &a, cudaStream_t s)
 uint32_t stage_smem_bytes (int stage, uint32_t blob_bytes)
 {
    const uint32_t warps = kStageThreads / 32, base = (blob_bytes + 127u) & ~127u;
+   const uint32_t hdr = ((uint32_t) sizeof (K1Blob) + 127u) & ~127u;
    switch (stage)
      {
-      case 10: return base + warps * (uint32_t) sizeof (WarpQueue<K1Shape<0>::ND, K1Shape<0>::NU>);
+      case 10: return hdr + warps * (uint32_t) sizeof (WarpQueue<K1Shape<0>::ND, K1Shape<0>::NU>);
       case 11: return base + warps * (uint32_t) sizeof (WarpQueue<K1Shape<1>::ND, K1Shape<1>::NU>);
-      case 12: return base + warps * (uint32_t) sizeof (WarpQueue<K1Shape<2>::ND, K1Shape<2>::NU>);
+      case 12: return hdr + warps * (uint32_t) sizeof (WarpQueue<K1Shape<2>::ND, K1Shape<2>::NU>);
+      case 13: return hdr + (kTile / 32) * (uint32_t) sizeof (WarpQueue<8, 5>);
       case 2: return base + warps * (uint32_t) sizeof (WarpQueue<6, 3>);
       case 3: return base + warps * (uint32_t) sizeof (WarpQueue<6, 6>);
       case 4: return base + warps * (uint32_t) sizeof (WarpQueue<6, 7>);
@@ -749,6 +829,19 @@ int stage_grid_size (int stage, int num_sms, uint32_t blob_bytes)
       case 4: return occupancy_grid (k3_hrc, num_sms, smem);
      }
    return num_sms;
+}
+int fused_source_grid (int num_sms)
+{
+   int per_sm = 1;
+   const uint32_t smem = stage_smem_bytes (13, 0);
+   cudaFuncSetAttribute (k01_source_hrma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+   cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, k01_source_hrma, kTile, smem);
+   return (per_sm < 1 ? 1 : per_sm) * num_sms;
+}
+void launch_source_hrma (const SourceArgs &a, const StageArgs &st, int grid, cudaStream_t s)
+{
+   if (a.n == 0) return;
+   k01_source_hrma<<<grid, kTile, stage_smem_bytes (13, 0), s>>> (a, st);
 }
 void launch_hrma (const StageArgs &a, int phase, int grid, cudaStream_t s)
 {

@@ -69,15 +69,62 @@ struct marxb200_ctx
    double source_distance = 0.0;
    void *blob1 = nullptr, *blob2 = nullptr, *blob3 = nullptr;
    uint32_t blob1_bytes = 0, blob2_bytes = 0, blob3_bytes = 0;
-   int grid1[3] = {0, 0, 0}, grid2 = 0, grid3 = 0;
+   int grid1[3] = {0, 0, 0}, grid2 = 0, grid3 = 0, grid01 = 0;
    bool detector_is_hrc = false;
+   int first_mirror_kernel = 0;                  // 1: phase A already ran fused with the source (marxb200_trace)
 
    // host boundary staging
    void *d_aos = nullptr; uint64_t d_aos_cap = 0;
    void *h_pinned = nullptr; size_t h_pinned_bytes = 0;
 
    uint64_t launches = 0;
+
+   // optional per-kernel timing
+   bool profiling = false;
+   cudaEvent_t ev_prev = nullptr;
+   std::vector<std::pair<cudaEvent_t, int>> ev_marks;   // (event recorded after a kernel, class)
+   std::vector<cudaEvent_t> ev_pool;
+   double prof_ms[MARXB200_NUM_KERNEL_CLASSES] = {0};
+   uint64_t prof_n[MARXB200_NUM_KERNEL_CLASSES] = {0};
 };
+
+static cudaEvent_t prof_event (marxb200_ctx *c)
+{
+   cudaEvent_t e;
+   if (!c->ev_pool.empty ()) { e = c->ev_pool.back (); c->ev_pool.pop_back (); return e; }
+   cudaEventCreate (&e);
+   return e;
+}
+// call before the first kernel of a sequence (begin) and after each kernel (mark)
+static void prof_begin (marxb200_ctx *c)
+{
+   if (!c->profiling) return;
+   cudaEvent_t e = prof_event (c);
+   cudaEventRecord (e, c->stream);
+   c->ev_marks.push_back (std::make_pair (e, -1));
+}
+static void prof_mark (marxb200_ctx *c, int cls)
+{
+   if (!c->profiling) return;
+   cudaEvent_t e = prof_event (c);
+   cudaEventRecord (e, c->stream);
+   c->ev_marks.push_back (std::make_pair (e, cls));
+}
+static void prof_collect (marxb200_ctx *c)
+{
+   if (c->ev_marks.empty ()) return;
+   cudaEventSynchronize (c->ev_marks.back ().first);
+   for (size_t i = 1; i < c->ev_marks.size (); i++)
+     {
+        const int cls = c->ev_marks[i].second;
+        if (cls < 0) continue;
+        float ms = 0.f;
+        cudaEventElapsedTime (&ms, c->ev_marks[i - 1].first, c->ev_marks[i].first);
+        c->prof_ms[cls] += ms; c->prof_n[cls] += 1;
+     }
+   for (auto &m : c->ev_marks) c->ev_pool.push_back (m.first);
+   c->ev_marks.clear ();
+}
 
 // ---------------------------------------------------------------------------------------------
 static int dev_upload (marxb200_ctx *c, const void *host, size_t bytes, void **out)
@@ -159,6 +206,8 @@ extern "C" int marxb200_destroy (marxb200_ctx *c)
    if (c == nullptr) return -1;
    cudaSetDevice (c->device);
    cudaDeviceSynchronize ();
+   prof_collect (c);
+   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy (e);
    for (void *p : c->allocs) cudaFree (p);
    for (int i = 0; i < 2; i++) if (c->slab[i]) cudaFree (c->slab[i]);
    cudaFree (c->d_counts); cudaFree (c->d_ticket); cudaFree (c->d_times);
@@ -267,6 +316,7 @@ extern "C" int marxb200_set_hrma (marxb200_ctx *c, const marxb200_hrma_desc *d)
    if (-1 == dev_upload (c, blob.data (), blob.size (), &c->blob1)) return -1;
    c->blob1_bytes = (uint32_t) blob.size ();
    for (int ph = 0; ph < 3; ph++) c->grid1[ph] = stage_grid_size (10 + ph, c->num_sms, c->blob1_bytes);
+   c->grid01 = fused_source_grid (c->num_sms);
    c->have_hrma = true;
    return 0;
 }
@@ -409,12 +459,13 @@ extern "C" int marxb200_create_photons (marxb200_ctx *c, uint64_t first_ray, uin
    SourceArgs a;
    // time_base_in < 0: continue the running sum from the device scalar (no host round trip)
    fill_source_args (c, a, first_ray, n, time_base_in);
-   launch_time_sums (a, c->stream);
-   launch_time_scan (a, c->stream);
-   launch_source (a, c->stream);
+   prof_begin (c);
+   launch_time_sums (a, c->stream); prof_mark (c, 0);
+   launch_time_scan (a, c->stream); prof_mark (c, 1);
+   launch_source (a, c->stream); prof_mark (c, 2);
    c->launches += 3;
    CUDA_OK (cudaGetLastError ());
-   c->cur = 0; c->stage_done = 0; c->n_generated = n; c->ordered = true;
+   c->cur = 0; c->stage_done = 0; c->n_generated = n; c->ordered = true; c->first_mirror_kernel = 0;
    return 0;
 }
 
@@ -453,15 +504,17 @@ static int run_stage (marxb200_ctx *c, int stage)
    a.source_distance = c->source_distance;
    // the mirror stage runs as three kernels (HRMA phases A, B, C, mx_hrma.cuh), each re-packing its survivors
    const int n_kernels = (stage == 1) ? 3 : 1;
+   const int k_first = (stage == 1) ? c->first_mirror_kernel : 0;
    CUDA_OK (cudaMemsetAsync (c->d_ticket, 0, 4 * sizeof (unsigned long long), c->stream));
    if (c->compact)
      {
         // output counters grow by atomics: zero them (d_counts[4], [5] = after k1a, k1b; d_counts[stage] = stage output)
         CUDA_OK (cudaMemsetAsync (c->d_counts + stage, 0, sizeof (unsigned long long), c->stream));
-        if (stage == 1) CUDA_OK (cudaMemsetAsync (c->d_counts + 4, 0, 2 * sizeof (unsigned long long), c->stream));
+        if (stage == 1) CUDA_OK (cudaMemsetAsync (c->d_counts + 4 + k_first, 0, (2 - k_first) * sizeof (unsigned long long), c->stream));
      }
-   const unsigned long long *n_in = c->d_counts + c->stage_done;
-   for (int k = 0; k < n_kernels; k++)
+   const unsigned long long *n_in = (k_first == 1) ? c->d_counts + 4 : c->d_counts + c->stage_done;
+   c->first_mirror_kernel = 0;
+   for (int k = k_first; k < n_kernels; k++)
      {
         a.in = c->buf[c->cur];
         a.out = c->compact ? c->buf[1 - c->cur] : c->buf[c->cur];
@@ -470,12 +523,14 @@ static int run_stage (marxb200_ctx *c, int stage)
         a.ticket = c->d_ticket + k;
         // big inputs amortise the ticket atomic over several tiles; small ones need fine-grained balancing
         a.chunk_tiles = (stage == 1 && k == 0) ? 4 : ((stage == 1 && k == 1) ? 2 : 1);
+        prof_begin (c);
         switch (stage)
           {
-           case 1: a.blob = c->blob1; a.blob_bytes = c->blob1_bytes; launch_hrma (a, k, c->grid1[k], c->stream); break;
-           case 2: a.blob = c->blob2; a.blob_bytes = c->blob2_bytes; launch_grating (a, c->grid2, c->stream); break;
+           case 1: a.blob = c->blob1; a.blob_bytes = c->blob1_bytes; launch_hrma (a, k, c->grid1[k], c->stream); prof_mark (c, 4 + k); break;
+           case 2: a.blob = c->blob2; a.blob_bytes = c->blob2_bytes; launch_grating (a, c->grid2, c->stream); prof_mark (c, 7); break;
            case 3: a.blob = c->blob3; a.blob_bytes = c->blob3_bytes;
                    if (c->detector_is_hrc) launch_hrc (a, c->grid3, c->stream); else launch_acis (a, c->grid3, c->stream);
+                   prof_mark (c, 8);
                    break;
           }
         c->launches += 1;
@@ -500,7 +555,9 @@ static int ensure_order (marxb200_ctx *c)
    o.bitmap = c->d_bitmap; o.word_prefix = c->d_word_prefix; o.block_prefix = c->d_block_prefix;
    CUDA_OK (cudaMemsetAsync (c->d_bitmap, 0, (c->n_generated / 32 + 1) * sizeof (uint32_t), c->stream));
    int nl = 0;
+   prof_begin (c);
    launch_restore_order (o, c->num_sms, c->stream, &nl);
+   prof_mark (c, 9);
    c->launches += nl;
    CUDA_OK (cudaGetLastError ());
    c->cur = 1 - c->cur;
@@ -552,9 +609,66 @@ extern "C" int marxb200_restore_order (marxb200_ctx *c)
    return ensure_order (c);
 }
 
-extern "C" int marxb200_trace (marxb200_ctx *c, uint64_t first_ray, uint64_t n)
+// marx_create_photons + HRMA phase A in one kernel (only the compacting path; the in-place parity mode and the
+// stage-by-stage API keep the separate kernels)
+static int create_and_enter_mirror (marxb200_ctx *c, uint64_t first_ray, uint64_t n, double time_base_in)
 {
-   if (-1 == marxb200_create_photons (c, first_ray, n, -1.0)) return -1;
+   if (!c->have_source) return fail ("marxb200_trace: no source set");
+   if (!c->have_hrma) return fail ("marxb200_trace: no HRMA tables set");
+   if (n > c->capacity) return fail ("marxb200_trace: n=%llu exceeds the allocated capacity %llu", (unsigned long long) n, (unsigned long long) c->capacity);
+   CUDA_OK (cudaSetDevice (c->device));
+   SourceArgs a;
+   fill_source_args (c, a, first_ray, n, time_base_in);
+   prof_begin (c);
+   launch_time_sums (a, c->stream); prof_mark (c, 0);
+   launch_time_scan (a, c->stream); prof_mark (c, 1);    // also sets d_counts[0] = n
+   StageArgs st;
+   memset (&st, 0, sizeof (st));
+   st.out = c->buf[1];
+   st.n_out = c->d_counts + 4;
+   st.seed = c->seed; st.compact = 1; st.source_distance = c->source_distance;
+   st.blob = c->blob1; st.blob_bytes = c->blob1_bytes;
+   CUDA_OK (cudaMemsetAsync (c->d_counts + 4, 0, sizeof (unsigned long long), c->stream));
+   prof_begin (c);
+   launch_source_hrma (a, st, c->grid01, c->stream); prof_mark (c, 3);
+   c->launches += 3;
+   CUDA_OK (cudaGetLastError ());
+   c->cur = 1; c->stage_done = 0; c->n_generated = n; c->ordered = false;
+   c->first_mirror_kernel = 1;
+   return 0;
+}
+
+extern "C" int marxb200_set_profiling (marxb200_ctx *c, int on)
+{
+   if (c == nullptr) return fail ("NULL ctx");
+   prof_collect (c);
+   c->profiling = (on != 0);
+   return 0;
+}
+extern "C" int marxb200_get_kernel_ms (marxb200_ctx *c, double ms[MARXB200_NUM_KERNEL_CLASSES], uint64_t launches[MARXB200_NUM_KERNEL_CLASSES])
+{
+   if (c == nullptr) return fail ("NULL ctx");
+   CUDA_OK (cudaSetDevice (c->device));
+   prof_collect (c);
+   for (int i = 0; i < MARXB200_NUM_KERNEL_CLASSES; i++)
+     {
+        if (ms) ms[i] = c->prof_ms[i];
+        if (launches) launches[i] = c->prof_n[i];
+        c->prof_ms[i] = 0.0; c->prof_n[i] = 0;
+     }
+   return 0;
+}
+
+extern "C" int marxb200_trace (marxb200_ctx *c, uint64_t first_ray, uint64_t n) { return marxb200_trace_from (c, first_ray, n, -1.0); }
+
+extern "C" int marxb200_trace_from (marxb200_ctx *c, uint64_t first_ray, uint64_t n, double time_base_in)
+{
+   if (c == nullptr) return fail ("NULL ctx");
+   if (c->compact)
+     {
+        if (-1 == create_and_enter_mirror (c, first_ray, n, time_base_in)) return -1;
+     }
+   else if (-1 == marxb200_create_photons (c, first_ray, n, time_base_in)) return -1;
    if (-1 == marxb200_mirror_reflect (c)) return -1;
    if (-1 == marxb200_grating_diffract (c)) return -1;
    if (-1 == marxb200_detect (c)) return -1;
@@ -572,6 +686,17 @@ extern "C" int marxb200_get_stage_counts (marxb200_ctx *c, uint64_t counts[4])
    CUDA_OK (cudaMemcpyAsync (h, c->d_counts, sizeof (h), cudaMemcpyDeviceToHost, c->stream));
    CUDA_OK (cudaStreamSynchronize (c->stream));
    for (int i = 0; i < 4; i++) counts[i] = (i <= c->stage_done) ? h[i] : 0;
+   return 0;
+}
+
+extern "C" int marxb200_get_internal_counts (marxb200_ctx *c, uint64_t counts[8])
+{
+   if (c == nullptr) return fail ("NULL ctx");
+   CUDA_OK (cudaSetDevice (c->device));
+   unsigned long long h[8];
+   CUDA_OK (cudaMemcpyAsync (h, c->d_counts, sizeof (h), cudaMemcpyDeviceToHost, c->stream));
+   CUDA_OK (cudaStreamSynchronize (c->stream));
+   for (int i = 0; i < 8; i++) counts[i] = h[i];
    return 0;
 }
 
@@ -640,7 +765,7 @@ extern "C" int marxb200_upload (marxb200_ctx *c, const marxb200_photon_attr *in,
    CUDA_OK (cudaMemcpyAsync (c->d_counts + 0, &nn, sizeof (nn), cudaMemcpyHostToDevice, c->stream));
    CUDA_OK (cudaStreamSynchronize (c->stream));
    if (d_ids) cudaFree (d_ids);
-   c->stage_done = 0; c->n_generated = n; c->ordered = true;
+   c->stage_done = 0; c->n_generated = n; c->ordered = true; c->first_mirror_kernel = 0;
    return 0;
 }
 

@@ -36,27 +36,29 @@ struct PhotonSoA
 };
 
 // Blob staged into shared memory by K1 with one TMA bulk copy.
-struct K1Blob
+struct alignas (16) K1Blob
 {
    HrmaDev H;
    uint32_t off_opt_e, off_opt_b, off_opt_d, off_corr_e, off_corr_f, total_bytes, pad0, pad1;
 };
-struct K2Blob
+struct alignas (16) K2Blob
 {
    GratingDev G;
    uint32_t off_sectors[kNumShells];     // byte offsets of each shell's [6][num_sectors] doubles
    uint32_t total_bytes, pad0, pad1, pad2;
 };
-struct K3Blob
+struct alignas (16) K3Blob
 {
    AcisDev A;
    uint32_t total_bytes, pad0, pad1, pad2;
 };
-struct K3HrcBlob
+struct alignas (16) K3HrcBlob
 {
    HrcDev D;
    uint32_t total_bytes, pad0, pad1, pad2;
 };
+
+static_assert (sizeof (K1Blob) % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
 
 struct StageArgs
 {
@@ -91,7 +93,9 @@ struct SourceArgs
 void launch_time_sums (const SourceArgs &a, cudaStream_t s);
 void launch_time_scan (const SourceArgs &a, cudaStream_t s);
 void launch_source (const SourceArgs &a, cudaStream_t s);
-void launch_hrma (const StageArgs &a, int phase, int grid, cudaStream_t s);   // phase 0,1,2 = k1a,k1b,k1c
+void launch_hrma (const StageArgs &a, int phase, int grid, cudaStream_t s);
+int fused_source_grid (int num_sms);
+void launch_source_hrma (const SourceArgs &a, const StageArgs &st, int grid, cudaStream_t s);   // k0_source + k1_hrma<0> in one kernel   // phase 0,1,2 = k1a,k1b,k1c
 void launch_grating (const StageArgs &a, int grid, cudaStream_t s);
 void launch_acis (const StageArgs &a, int grid, cudaStream_t s);
 void launch_hrc (const StageArgs &a, int grid, cudaStream_t s);
