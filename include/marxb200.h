@@ -353,6 +353,13 @@ typedef struct
 marxb200_columns;
 int marxb200_download_columns (marxb200_ctx *ctx, const marxb200_columns *cols, uint64_t max_out, uint64_t *n_out);
 
+/* Pipelined egress: marxb200_egress_begin restores arrival order, snapshots up to max_out live
+ * photons into a device staging area and returns at once, so the next batch can be launched; marxb200_egress_end
+ * waits for that snapshot, copies the requested columns to the caller's (ideally pinned) host arrays on a private
+ * copy stream -- overlapping the next batch's kernels -- and blocks until they have landed. */
+int marxb200_egress_begin (marxb200_ctx *ctx, uint64_t max_out);
+int marxb200_egress_end (marxb200_ctx *ctx, const marxb200_columns *cols, uint64_t *n_out);
+
 /* kernel launch counter (bench.py "gpu_launches") */
 int marxb200_get_launch_count (marxb200_ctx *ctx, uint64_t *n);
 

@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = [
     "marxb200_set_grating", "marxb200_set_acis", "marxb200_set_hrc_s", "marxb200_load_calpack", "marxb200_alloc_photons",
     "marxb200_create_photons", "marxb200_time_sums", "marxb200_mirror_reflect", "marxb200_grating_diffract",
     "marxb200_detect", "marxb200_restore_order", "marxb200_trace", "marxb200_trace_from", "marxb200_set_profiling", "marxb200_get_kernel_ms", "marxb200_get_counts", "marxb200_get_stage_counts", "marxb200_get_internal_counts", "marxb200_download",
-    "marxb200_upload", "marxb200_download_all", "marxb200_download_columns", "marxb200_get_launch_count",
+    "marxb200_upload", "marxb200_download_all", "marxb200_download_columns", "marxb200_egress_begin", "marxb200_egress_end", "marxb200_get_launch_count",
 ]
 
 # Marx_Photon_Attr_Type, marx/libsrc/marx.h:51-100 (136 bytes; offsets probed in SURVEY.md 8a1)
@@ -93,6 +93,8 @@ def load_library():
         "marxb200_upload": [vp, vp, u64, vp],
         "marxb200_download_columns": [vp, vp, u64, C.POINTER(u64)],
         "marxb200_get_launch_count": [vp, C.POINTER(u64)],
+        "marxb200_egress_begin": [vp, u64],
+        "marxb200_egress_end": [vp, vp, C.POINTER(u64)],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -239,6 +241,19 @@ class MarxB200:
             ids = np.ascontiguousarray(ray_ids, dtype=np.uint64)
         self._check(self._lib.marxb200_upload(self._ctx, photons.ctypes.data_as(C.c_void_p), len(photons),
                                               ids.ctypes.data_as(C.c_void_p) if ids is not None else None))
+
+    def egress_begin(self, max_out):
+        """snapshot the ordered live list on the device and return at once (see include/marxb200.h)"""
+        self._check(self._lib.marxb200_egress_begin(self._ctx, int(max_out)))
+
+    def egress_end(self, out):
+        """out: dict name -> (pinned) numpy array; blocks until the snapshot has been copied; returns views"""
+        cols = _Columns()
+        for name, arr in out.items():
+            setattr(cols, name, arr.ctypes.data)
+        got = C.c_uint64()
+        self._check(self._lib.marxb200_egress_end(self._ctx, C.byref(cols), C.byref(got)))
+        return {k: v[:got.value] for k, v in out.items()}
 
     def download_columns(self, names=("energy", "time", "chipx", "chipy", "pha", "ccd", "order", "ray"), out=None):
         _, live, _ = self.counts()

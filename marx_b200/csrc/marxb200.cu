@@ -79,6 +79,13 @@ struct marxb200_ctx
 
    uint64_t launches = 0;
 
+   // pipelined egress
+   cudaStream_t copy_stream = nullptr;
+   cudaEvent_t ev_staged = nullptr, ev_copied = nullptr;
+   void *egress_slab = nullptr; uint64_t egress_cap = 0; PhotonSoA egress;
+   unsigned long long *h_egress_count = nullptr;      // pinned
+   bool egress_pending = false;
+
    // optional per-kernel timing
    bool profiling = false;
    cudaEvent_t ev_prev = nullptr;
@@ -218,6 +225,11 @@ extern "C" int marxb200_destroy (marxb200_ctx *c)
    if (c->d_tile_base) cudaFree (c->d_tile_base);
    if (c->d_super_sums) cudaFree (c->d_super_sums);
    if (c->d_aos) cudaFree (c->d_aos);
+   if (c->egress_slab) cudaFree (c->egress_slab);
+   if (c->h_egress_count) cudaFreeHost (c->h_egress_count);
+   if (c->ev_staged) cudaEventDestroy (c->ev_staged);
+   if (c->ev_copied) cudaEventDestroy (c->ev_copied);
+   if (c->copy_stream) cudaStreamDestroy (c->copy_stream);
    if (c->h_pinned) cudaFreeHost (c->h_pinned);
    if (c->own_stream && c->stream) cudaStreamDestroy (c->stream);
    delete c;
@@ -791,6 +803,72 @@ extern "C" int marxb200_download_columns (marxb200_ctx *c, const marxb200_column
    COL (ray, ray, uint64_t);
 #undef COL
    CUDA_OK (cudaStreamSynchronize (c->stream));
+   return 0;
+}
+
+static size_t carve (PhotonSoA &b, unsigned char *base, uint64_t n);
+
+extern "C" int marxb200_egress_begin (marxb200_ctx *c, uint64_t max_out)
+{
+   if (c == nullptr) return fail ("NULL ctx");
+   if (c->stage_done < 0) return fail ("marxb200_egress_begin: no photons");
+   if (max_out == 0) return fail ("marxb200_egress_begin: max_out must be > 0");
+   CUDA_OK (cudaSetDevice (c->device));
+   if (c->copy_stream == nullptr)
+     {
+        CUDA_OK (cudaStreamCreateWithFlags (&c->copy_stream, cudaStreamNonBlocking));
+        CUDA_OK (cudaEventCreateWithFlags (&c->ev_staged, cudaEventDisableTiming));
+        CUDA_OK (cudaEventCreateWithFlags (&c->ev_copied, cudaEventDisableTiming));
+        CUDA_OK (cudaMallocHost (&c->h_egress_count, sizeof (unsigned long long)));
+     }
+   if (c->egress_cap < max_out)
+     {
+        CUDA_OK (cudaStreamSynchronize (c->copy_stream));
+        if (c->egress_slab) cudaFree (c->egress_slab);
+        PhotonSoA tmp;
+        size_t bytes = carve (tmp, nullptr, max_out);
+        CUDA_OK (cudaMalloc (&c->egress_slab, bytes));
+        carve (c->egress, (unsigned char *) c->egress_slab, max_out);
+        c->egress_cap = max_out;
+     }
+   if (c->egress_pending) return fail ("marxb200_egress_begin: the previous egress was not ended");
+   if (-1 == ensure_order (c)) return -1;
+   const PhotonSoA &b = c->buf[c->cur], &e = c->egress;
+   const uint64_t n = (max_out < c->capacity) ? max_out : c->capacity;
+   // the staging area may still be read by the previous copy: make the main stream wait for it
+   CUDA_OK (cudaStreamWaitEvent (c->stream, c->ev_copied, 0));
+#define STAGE(col, T) CUDA_OK (cudaMemcpyAsync (e.col, b.col, (size_t) n * sizeof (T), cudaMemcpyDeviceToDevice, c->stream))
+   STAGE (energy, double); STAGE (time, double); STAGE (x0, double); STAGE (x1, double); STAGE (x2, double);
+   STAGE (p0, double); STAGE (p1, double); STAGE (p2, double); STAGE (chipx, float); STAGE (chipy, float); STAGE (pi, float);
+   STAGE (pha, int16_t); STAGE (ccd, int8_t); STAGE (order, int8_t); STAGE (shell, uint8_t); STAGE (ray, uint64_t);
+#undef STAGE
+   CUDA_OK (cudaMemcpyAsync (c->h_egress_count, c->d_counts + c->stage_done, sizeof (unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+   CUDA_OK (cudaEventRecord (c->ev_staged, c->stream));
+   c->egress_pending = true;
+   return 0;
+}
+
+extern "C" int marxb200_egress_end (marxb200_ctx *c, const marxb200_columns *cols, uint64_t *n_out)
+{
+   if ((c == nullptr) || (cols == nullptr)) return fail ("marxb200_egress_end: NULL argument");
+   if (!c->egress_pending) return fail ("marxb200_egress_end: no egress in flight");
+   CUDA_OK (cudaSetDevice (c->device));
+   CUDA_OK (cudaEventSynchronize (c->ev_staged));
+   unsigned long long n = *c->h_egress_count;
+   if (n > c->egress_cap) n = c->egress_cap;
+   const PhotonSoA &e = c->egress;
+#define COL(dst, src, T) if (cols->dst) CUDA_OK (cudaMemcpyAsync (cols->dst, e.src, (size_t) n * sizeof (T), cudaMemcpyDeviceToHost, c->copy_stream))
+   COL (energy, energy, double); COL (time, time, double);
+   COL (xpos, x0, double); COL (ypos, x1, double); COL (zpos, x2, double);
+   COL (xcos, p0, double); COL (ycos, p1, double); COL (zcos, p2, double);
+   COL (chipx, chipx, float); COL (chipy, chipy, float); COL (pi, pi, float);
+   COL (pha, pha, int16_t); COL (ccd, ccd, int8_t); COL (order, order, int8_t); COL (shell, shell, int8_t);
+   COL (ray, ray, uint64_t);
+#undef COL
+   CUDA_OK (cudaEventRecord (c->ev_copied, c->copy_stream));
+   CUDA_OK (cudaStreamSynchronize (c->copy_stream));
+   c->egress_pending = false;
+   if (n_out) *n_out = n;
    return 0;
 }
 

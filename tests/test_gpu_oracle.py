@@ -138,3 +138,28 @@ def test_seed_and_offset_independence():
     for k in ("tag", "energy", "pulse_height", "ccd_num", "order", "y_pixel", "z_pixel"):
         assert (second_half[k] == b[k]).all(), k
     assert len(c) != len(a) or (c["pulse_height"] != a["pulse_height"]).any()
+
+
+def test_pipelined_egress_matches_download():
+    """marxb200_egress_begin/_end (copy overlapped with the next batch) returns exactly what download_columns returns"""
+    import marx_b200
+    n = 1 << 20
+    names = ("energy", "time", "chipx", "chipy", "pha", "ccd", "order", "ray", "xpos", "zcos", "pi", "shell")
+    from marx_b200.api import _COLUMN_DTYPES
+    with marx_b200.MarxB200("c2_hetg_acis_s", seed=11, max_photons=n) as m:
+        ref = []
+        for b in range(3):
+            m.trace(b * n, n)
+            ref.append({k: v.copy() for k, v in m.download_columns(names).items()})
+    with marx_b200.MarxB200("c2_hetg_acis_s", seed=11, max_photons=n) as m:
+        bufs = [{k: np.empty(n // 4, dtype=_COLUMN_DTYPES[k]) for k in names} for _ in range(2)]
+        got = []
+        for b in range(3):
+            m.trace(b * n, n)
+            if b > 0:
+                got.append({k: v.copy() for k, v in m.egress_end(bufs[(b - 1) & 1]).items()})
+            m.egress_begin(n // 4)
+        got.append({k: v.copy() for k, v in m.egress_end(bufs[0]).items()})
+    for a, b in zip(got, ref):
+        for k in names:
+            assert len(a[k]) == len(b[k]) and (a[k] == b[k]).all(), k
