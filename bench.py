@@ -192,16 +192,30 @@ def cuda_arm(args):
     pinned_np = [{k: v.numpy().view(_COLUMN_DTYPES[k]) for k, v in p.items()} for p in pinned]
     bytes_per_event = sum(np.dtype(_COLUMN_DTYPES[k]).itemsize for k in col_names)
 
-    def time_base_for(step):
-        """multi-GPU: canonical time base of this rank's block = running end time + the super-tile sums of the
-        lower ranks' blocks added sequentially (all-gather over NCCL); single GPU: continue on device."""
-        first = (step * world + rank) * n
+    bases = {}
+
+    def plan_time_bases(step0, K):
+        """multi-GPU: arrival times are one running sum over ALL rays (source.c:326).  Each rank reduces the time
+        increments of its K blocks to super-tile sums (marxb200_time_sums), ONE all-gather over NCCL exchanges them,
+        and every rank adds them up in global ray order -- exactly the additions a single GPU performs -- to get the
+        absolute time base of each of its blocks.  Single GPU: the running sum simply continues on the device."""
         if world == 1:
-            return first, -1.0
-        from marx_b200.dist import exchange_time_base
-        base, time_base_for.running = exchange_time_base(m.time_sums(first, n), rank, world, time_base_for.running, device=dev)
-        return first, base
-    time_base_for.running = 0.0
+            for s in range(step0, step0 + K):
+                bases[s] = -1.0
+            return
+        from marx_b200.dist import block_time_bases
+        mine = np.stack([m.time_sums((s * world + rank) * n, n) for s in range(step0, step0 + K)])      # [K, n_super]
+        t = torch.from_numpy(mine).to(dev)
+        gathered = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        allsums = torch.stack(gathered).cpu().numpy()                                                      # [world, K, n_super]
+        for k in range(K):
+            b, plan_time_bases.running = block_time_bases([allsums[r, k] for r in range(world)], plan_time_bases.running)
+            bases[step0 + k] = b[rank]
+    plan_time_bases.running = 0.0
+
+    def time_base_for(step):
+        return (step * world + rank) * n, bases[step]
 
     def one_step(step):
         first, base = time_base_for(step)
@@ -219,6 +233,7 @@ def cuda_arm(args):
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
         launches0 = m.launch_count()
         t0.record(stream)
+        plan_time_bases(timed.step, K)        # inside the timed region
         n_events = 0
         for s in range(K):
             one_step(timed.step)
@@ -244,6 +259,7 @@ def cuda_arm(args):
     if rank == 0:
         sampler.start()
         time.sleep(1.0)                       # let nvidia-smi come up; it samples every 100 ms from then on
+    plan_time_bases(timed.step, max(args.warmup, 3))
     for _ in range(max(args.warmup, 3)):
         one_step(timed.step); timed.step += 1
     if rank == 0:

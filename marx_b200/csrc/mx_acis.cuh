@@ -109,7 +109,8 @@ MX_HD int fef_normalize (GaussParm *g, uint32_t num)
      {
         double area1 = 0.0, area2 = 0.0;
         double sigma = g[k].sigma * SQRT_2;
-        if (sigma != 0.0)
+        // amp == 0 makes both areas exactly zero whatever erf returns: skip the erf (identical results)
+        if ((sigma != 0.0) && (g[k].amp != 0.0f))
           {
              double x0 = g[k].center;
              double e0 = erf ((0 - x0) / sigma);

@@ -16,8 +16,17 @@
 
 #if defined(__CUDACC__)
 #define MX_HD __host__ __device__ __forceinline__
+// Large helpers called from several places.  ncu attributes ~25 % of k1_hrma<1>'s stall samples to "no
+// instruction" (the fully inlined kernel exceeds the instruction cache), but keeping these helpers out of line
+// (-DMX_OUTLINE_BIG) measured 10 % SLOWER on B200 (call/ABI overhead, lost scheduling freedom), so they are inlined.
+#ifdef MX_OUTLINE_BIG
+#define MX_HD_BIG __host__ __device__ __noinline__
+#else
+#define MX_HD_BIG __host__ __device__ __forceinline__
+#endif
 #else
 #define MX_HD inline
+#define MX_HD_BIG inline
 #endif
 
 namespace mx {
@@ -112,7 +121,7 @@ MX_HD void sin_cos (double theta, double &s, double &c)
 #endif
 }
 // JDMv_rotate_unit_vector, vector.c:204-208
-MX_HD Vec3 v_rotate_unit (const Vec3 &p, const Vec3 &n, double theta)
+MX_HD_BIG Vec3 v_rotate_unit (const Vec3 &p, const Vec3 &n, double theta)
 {
    double s, c;
    sin_cos (theta, s, c);
@@ -253,7 +262,7 @@ MX_HD uint32_t bsearch_d (double x, const double *xp, uint32_t n)
 // takes float); (yp[n1]-yp[n0]) is a float subtraction, the rest is double, the result is a float.
 // The reference reads xp[n] one past the end when x exceeds the grid (finterpo.c:68); that compare
 // is guarded here.
-MX_HD float interp_f (float x, const float *xp, const float *yp, uint32_t n)
+MX_HD_BIG float interp_f (float x, const float *xp, const float *yp, uint32_t n)
 {
    if (n == 1) return yp[0];
    uint32_t n1 = bsearch_f (x, xp, n);

@@ -69,7 +69,7 @@ MX_HD Cplx c_a_bz (double a, double b, Cplx z1) { Cplx z; z.r = a + b * z1.r; z.
 MX_HD Cplx c_az1_bz2 (double a, Cplx z1, double b, Cplx z2) { Cplx z; z.r = a * z1.r + b * z2.r; z.i = a * z1.i + b * z2.i; return z; }
 
 // marx_reflectivity, reflect.c:39-77: polarisation-averaged Fresnel reflectivity, cos_theta >= 0
-MX_HD double reflectivity (double cos_theta, double beta, double delta)
+MX_HD_BIG double reflectivity (double cos_theta, double beta, double delta)
 {
    Cplx n, root, nsqr, e_perp, e_par, num, den;
    n.r = (1.0 - delta);
@@ -169,7 +169,7 @@ MX_HD double wfold_theta (const WfoldDev &w, uint32_t k, double p)
    return (1.0 - delta_i) * t[i] + delta_i * t[i + 1];
 }
 // marx_wfold_table_interp, wfold.c:334-369
-MX_HD double wfold_interp (const WfoldDev &w, double energy, double sin_alpha, double r)
+MX_HD_BIG double wfold_interp (const WfoldDev &w, double energy, double sin_alpha, double r)
 {
    if (w.num_arrays == 0) return 0.0;
    if (w.num_arrays == 1) return wfold_theta (w, 0, r);
@@ -199,7 +199,7 @@ MX_HD double wfold_interp (const WfoldDev &w, double energy, double sin_alpha, d
 }
 
 // intersects_struts, hrma.c:928-968.  struts = {xpos0, half_width0, xpos1, half_width1}
-MX_HD int intersects_struts (const Vec3 &x0, const Vec3 &p0, double cap_position, const double *struts)
+MX_HD_BIG int intersects_struts (const Vec3 &x0, const Vec3 &p0, double cap_position, const double *struts)
 {
    const double theta = 30.0 * (kPI / 180.0);
    const double cos_theta = cos (theta), sin_theta = sin (theta);
