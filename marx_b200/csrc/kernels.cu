@@ -588,6 +588,11 @@ __global__ void __launch_bounds__ (kTile, 3) k01_source_hrma (const __grid_const
         __syncwarp ();
      };
 
+   // POINT source, no roll dither: the rolled source direction is one vector for the whole run
+   const bool const_roll = dither_roll_is_constant (a.S, a.D);
+   Vec3 rolled = v_make (0, 0, 0);
+   if (const_roll) rolled = dither_roll ((double) (float) a.D.nominal_roll, v_make (a.S.p[0], a.S.p[1], a.S.p[2]));
+
    const uint64_t n_tiles = (a.n + kTile - 1) / kTile;
    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
      {
@@ -601,7 +606,7 @@ __global__ void __launch_bounds__ (kTile, 3) k01_source_hrma (const __grid_const
         Vec3 x = v_make (0, 0, 0); uint32_t shell = 0; float dra = 0.f, ddec = 0.f, droll = 0.f;
         if (valid)
           {
-             dither_ray (a.D, rng, t, p, dra, ddec, droll);
+             dither_ray (a.D, rng, t, p, dra, ddec, droll, const_roll ? &rolled : nullptr);
              rng.init (a.seed, a.first_ray + i, MARXB200_STAGE_MIRROR);
              alive = (0 == hrma_phase_a (H, st.source_distance, x, p, shell, rng));
           }

@@ -50,10 +50,12 @@ MX_HD double source_time_increment (const SourceDev &s, Rng &rng)
    return s.mean_time * rng.expn ();
 }
 
-// apply_dither, dither.c:551-581
-MX_HD Vec3 apply_dither (double ra, double dec, double roll, Vec3 p)
+// apply_dither, dither.c:551-581.  p_rolled: p after the roll about the x axis (first statement of apply_dither);
+// for a POINT source with DitherAmp_Roll = 0 it is the same vector for every ray, so persistent kernels compute
+// it once per thread with the same operations (dither_roll_is_constant / dither_roll).
+MX_HD Vec3 dither_roll (double roll, const Vec3 &p) { return v_rotate_unit (p, v_make (1, 0, 0), -roll); }
+MX_HD Vec3 apply_dither_rolled (double ra, double dec, Vec3 p)
 {
-   p = v_rotate_unit (p, v_make (1, 0, 0), -roll);
    double cos_ra, sin_ra, cos_dec, sin_dec;
    sin_cos (ra, sin_ra, cos_ra);
    sin_cos (dec, sin_dec, cos_dec);
@@ -64,11 +66,21 @@ MX_HD Vec3 apply_dither (double ra, double dec, double roll, Vec3 p)
    n.x /= sin_theta; n.y /= sin_theta; n.z /= sin_theta;
    return v_rotate_unit1 (p, n, cos_theta, sin_theta);
 }
+MX_HD Vec3 apply_dither (double ra, double dec, double roll, Vec3 p)
+{
+   return apply_dither_rolled (ra, dec, dither_roll (roll, p));
+}
+MX_HD bool dither_roll_is_constant (const SourceDev &s, const DitherDev &d)
+{
+   return (d.mode != 0) && (d.roll_amp == 0.0) && (s.source_type == 0);
+}
 
 // dither_ray + get_internal_dither.  t is the absolute time (pt->start_time + arrival_time).
 // The three angles are stored through float fields before use (dither.c:173-175); that rounding is
 // part of the result.
-MX_HD void dither_ray (const DitherDev &d, Rng &rng, double t, Vec3 &p, float &f_ra, float &f_dec, float &f_roll)
+// rolled != nullptr: the caller supplies dither_roll ((float) nominal_roll, source p) (see above)
+MX_HD void dither_ray (const DitherDev &d, Rng &rng, double t, Vec3 &p, float &f_ra, float &f_dec, float &f_roll,
+                       const Vec3 *rolled = nullptr)
 {
    if (d.mode == 0) { f_ra = f_dec = f_roll = 0.0f; return; }
    t = (2.0 * kPI) * t;
@@ -80,7 +92,8 @@ MX_HD void dither_ray (const DitherDev &d, Rng &rng, double t, Vec3 &p, float &f
    double ra = f_ra, dec = f_dec, roll = f_roll;
    double delta_ra = d.aspect_blur * rng.gaussian ();
    double delta_dec = d.aspect_blur * rng.gaussian ();
-   p = apply_dither (ra + delta_ra, dec + delta_dec, roll, p);
+   if (rolled != nullptr) p = apply_dither_rolled (ra + delta_ra, dec + delta_dec, *rolled);
+   else p = apply_dither (ra + delta_ra, dec + delta_dec, roll, p);
 }
 
 }  // namespace mx

@@ -38,6 +38,7 @@ struct WfoldDev
    const uint32_t *num_theta;      // [num_arrays]
    const uint32_t *theta_offset;   // [num_arrays]
    const float *theta;
+   double min_p_min;               // smallest p_min of the table: below it no array scatters (wfold.c:311-312)
 };
 
 struct HrmaShellDev

@@ -34,6 +34,8 @@ template <class Up> int build_wfold (Up &up, const marxb200_wfold_table *w, Wfol
         hdr[6 * i + 0] = w->e_alpha[i]; hdr[6 * i + 1] = w->p_min[i]; hdr[6 * i + 2] = w->delta_p[i];
         hdr[6 * i + 3] = w->p_max[i]; hdr[6 * i + 4] = w->pow_law_norm[i]; hdr[6 * i + 5] = w->pow_law_expon[i];
      }
+   out->min_p_min = w->p_min[0];
+   for (uint32_t i = 1; i < w->num_arrays; i++) if (w->p_min[i] < out->min_p_min) out->min_p_min = w->p_min[i];
    if (-1 == tb_up (up, hdr.data (), hdr.size (), &out->hdr, err)) return -1;
    if (-1 == tb_up (up, w->num_theta, w->num_arrays, &out->num_theta, err)) return -1;
    if (-1 == tb_up (up, w->theta_offset, w->num_arrays, &out->theta_offset, err)) return -1;
