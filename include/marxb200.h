@@ -295,6 +295,11 @@ int marxb200_alloc_photons (marxb200_ctx *ctx, uint64_t max_photons);
  * previous call, source.c:285,326), dither.  No energy sort is needed (draws are per-ray).
  * time_base_in < 0: continue from the context's running time; otherwise restart the sum there. */
 int marxb200_create_photons (marxb200_ctx *ctx, uint64_t first_ray, uint64_t n, double time_base_in);
+/* ExposureTime handling of marx_create_photons (source.c:323-334, marx.c:545-556): call directly after
+ * marxb200_create_photons.  Keeps the rays up to AND INCLUDING the first one whose arrival time, counted from the
+ * start of this batch, is >= exposure_left; later rays are dropped and the running end time is set to the last kept
+ * ray's arrival time.  *n_kept is the reference's *num_collected. */
+int marxb200_truncate_exposure (marxb200_ctx *ctx, double exposure_left, uint64_t *n_kept);
 /* Multi-GPU time base: sums of the arrival-time increments of rays [first_ray, first_ray+n) per
  * super-tile of 65536 rays, in canonical order.  Ranks all-gather these (tiny) vectors and add them
  * sequentially to obtain the time_base_in of their block, which makes arrival times independent of
@@ -359,6 +364,40 @@ int marxb200_download_columns (marxb200_ctx *ctx, const marxb200_columns *cols, 
  * copy stream -- overlapping the next batch's kernels -- and blocks until they have landed. */
 int marxb200_egress_begin (marxb200_ctx *ctx, uint64_t max_out);
 int marxb200_egress_end (marxb200_ctx *ctx, const marxb200_columns *cols, uint64_t *n_out);
+
+/* Bulk event-file egress: marx_write_photons (marxio.c:403-476) for the live list on the device.
+ * Writes/appends the column files of the reference's output directory (energy.dat, time.dat, xpixel.dat, ... -- the
+ * table at marxio.c:292-322), byte-compatible with the reference's writer so that marx2fits, marxcat and marxpileup read
+ * them unchanged: 32-byte header (marxio.c:151-205) + big-endian float32/int16/int32/int8 data, row count patched at
+ * offset 20 on every call.  Columns are converted and byte-swapped on the device and appended with one fwrite per file.
+ *   write_mask  the columns to write: the caller's OutputVectors mask ANDed with the photon history, exactly the value
+ *               marxio.c:409-414 computes (bits below = MARX_*_OK, marx.h:126-147)
+ *   open_mode   1: create the files (first batch), 0: append (marx.c:585-588)
+ *   total_time  the driver's accumulated time before this batch; TIME = arrival_time + total_time (marxio.c:246) */
+#define MARXB200_ENERGY_OK        0x00000001
+#define MARXB200_TIME_OK          0x00000002
+#define MARXB200_X_VECTOR_OK      0x00000004
+#define MARXB200_P_VECTOR_OK      0x00000008
+#define MARXB200_TAG_OK           0x00000010
+#define MARXB200_PULSEHEIGHT_OK   0x00000020
+#define MARXB200_PI_OK            0x00000040
+#define MARXB200_DET_PIXEL_OK     0x00000080
+#define MARXB200_DET_NUM_OK       0x00000100
+#define MARXB200_DET_REGION_OK    0x00000200
+#define MARXB200_DET_UV_PIXEL_OK  0x00000400
+#define MARXB200_MIRROR_SHELL_OK  0x00000800
+#define MARXB200_SKY_DITHER_OK    0x00001000
+#define MARXB200_DET_DITHER_OK    0x00002000
+#define MARXB200_ORDER_OK         0x00100000
+#define MARXB200_ORDER1_OK        0x00200000
+#define MARXB200_ORDER2_OK        0x00400000
+#define MARXB200_ORDER3_OK        0x00800000
+#define MARXB200_ORDER4_OK        0x01000000
+int marxb200_write_photons (marxb200_ctx *ctx, const char *dir, uint64_t write_mask, int open_mode, double total_time);
+
+/* FP64 roofline denominator measured on this GPU: best of 5 runs of a DFMA-chain kernel (8 independent chains per
+ * thread, 8 x 256-thread CTAs per SM), in TFLOP/s counting an FMA as 2 flops.  Diagnostic; leaves the photon list alone. */
+int marxb200_measure_fp64_peak (marxb200_ctx *ctx, double *tflops);
 
 /* kernel launch counter (bench.py "gpu_launches") */
 int marxb200_get_launch_count (marxb200_ctx *ctx, uint64_t *n);

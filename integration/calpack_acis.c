@@ -1,5 +1,5 @@
 /* Serialises ACIS-S detector state: chip geometry + QE (marx/libsrc/acis-s.c statics), detector
- * transform (detector.c globals), frame timing (acis-i.c globals).  oracle/_ref build only. */
+ * transform (detector.c globals), frame timing (acis-i.c globals).  Reference-side binding (integration/): compiled against the MARX tree, never into libmarxb200.so. */
 #include <acis-s.c>
 #include "calpack_io.h"
 

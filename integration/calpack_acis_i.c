@@ -1,5 +1,5 @@
 /* Serialises ACIS-I detector state (marx/libsrc/acis-i.c statics); same layout as calpack_acis.c.
- * oracle/_ref build only. */
+ * Reference-side binding (integration/): compiled against the MARX tree, never into libmarxb200.so. */
 #include <acis-i.c>
 #include "calpack_io.h"
 

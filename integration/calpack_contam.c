@@ -1,4 +1,4 @@
-/* Serialises marx/libsrc/aciscontam.c's per-CCD contamination model.  oracle/_ref build only. */
+/* Serialises marx/libsrc/aciscontam.c's per-CCD contamination model.  Reference-side binding (integration/): compiled against the MARX tree, never into libmarxb200.so. */
 #include <aciscontam.c>
 #include "calpack_io.h"
 

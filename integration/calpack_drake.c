@@ -1,4 +1,4 @@
-/* HESF "Drake flat" plates and optical constants (marx/libsrc/drake.c statics).  oracle/_ref build only. */
+/* HESF "Drake flat" plates and optical constants (marx/libsrc/drake.c statics).  Reference-side binding (integration/): compiled against the MARX tree, never into libmarxb200.so. */
 #include <drake.c>
 #include "calpack_io.h"
 int calpack_dump_hesf (mxcp_writer *w, int *n_plates, double *cr_width)

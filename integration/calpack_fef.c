@@ -1,4 +1,4 @@
-/* Serialises the FEF region map of marx/libsrc/acis_fef.c (static Fef_Maps).  oracle/_ref build only. */
+/* Serialises the FEF region map of marx/libsrc/acis_fef.c (static Fef_Maps).  Reference-side binding (integration/): compiled against the MARX tree, never into libmarxb200.so. */
 #include <acis_fef.c>
 #include "calpack_io.h"
 

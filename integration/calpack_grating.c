@@ -1,4 +1,4 @@
-/* Serialises the post-init state of marx/libsrc/diffract.c.  oracle/_ref build only. */
+/* Serialises the post-init state of marx/libsrc/diffract.c.  Reference-side binding (integration/): compiled against the MARX tree, never into libmarxb200.so. */
 #include <diffract.c>
 #include "calpack_io.h"
 

@@ -1,4 +1,4 @@
-/* HRC-S pixel-mapping constants (marx/libsrc/hrc_s_geom.c statics).  oracle/_ref build only. */
+/* HRC-S pixel-mapping constants (marx/libsrc/hrc_s_geom.c statics).  Reference-side binding (integration/): compiled against the MARX tree, never into libmarxb200.so. */
 #include <hrc_s_geom.c>
 #include "calpack_io.h"
 

@@ -1,4 +1,4 @@
-/* Serialises HRC-S detector state (marx/libsrc/hrc-s.c statics + detector.c globals).  oracle/_ref build only. */
+/* Serialises HRC-S detector state (marx/libsrc/hrc-s.c statics + detector.c globals).  Reference-side binding (integration/): compiled against the MARX tree, never into libmarxb200.so. */
 #include <hrc-s.c>
 #include "calpack_io.h"
 

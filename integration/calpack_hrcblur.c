@@ -1,4 +1,4 @@
-/* HRC blur parameters after fixup (marx/libsrc/hrcblur.c; the struct is opaque elsewhere).  oracle/_ref build only. */
+/* HRC blur parameters after fixup (marx/libsrc/hrcblur.c; the struct is opaque elsewhere).  Reference-side binding (integration/): compiled against the MARX tree, never into libmarxb200.so. */
 #include <hrcblur.c>
 #include "calpack_io.h"
 int calpack_hrc_blur (void *p, double *b)

@@ -1,5 +1,5 @@
 /* Serialises the post-init state of the reference's HRMA module (file-scope statics of
- * marx/libsrc/hrma.c) by compiling that file INTO this unit.  oracle/_ref build only. */
+ * marx/libsrc/hrma.c) by compiling that file INTO this unit.  Reference-side binding (integration/): compiled against the MARX tree, never into libmarxb200.so. */
 #include <hrma.c>
 #include "calpack_io.h"
 

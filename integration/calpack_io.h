@@ -1,8 +1,8 @@
-/* helpers shared by the calpack_*.c dump units.  TEST/INTEGRATION TOOLING (oracle/_ref build only). */
+/* helpers shared by the calpack_*.c dump units.  TEST/INTEGRATION TOOLING (reference-side binding, compiled against the MARX tree). */
 #ifndef ORACLE_CALPACK_IO_H
 #define ORACLE_CALPACK_IO_H
 #include <stdarg.h>
-#include "../../include/marxb200_calpack.h"
+#include <marxb200_calpack.h>
 
 static inline void cp_name (char *buf, const char *fmt, ...)
 {

@@ -1,4 +1,4 @@
-/* BETA source statics (marx/libsrc/s-beta.c).  oracle/_ref build only. */
+/* BETA source statics (marx/libsrc/s-beta.c).  Reference-side binding (integration/): compiled against the MARX tree, never into libmarxb200.so. */
 #include <s-beta.c>
 #include "calpack_io.h"
 int calpack_is_beta (void *st, double *shape)

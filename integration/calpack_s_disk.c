@@ -1,4 +1,4 @@
-/* DISK source statics (marx/libsrc/s-disk.c).  oracle/_ref build only. */
+/* DISK source statics (marx/libsrc/s-disk.c).  Reference-side binding (integration/): compiled against the MARX tree, never into libmarxb200.so. */
 #include <s-disk.c>
 #include "calpack_io.h"
 int calpack_is_disk (void *st, double *shape)

@@ -1,4 +1,4 @@
-/* GAUSS source statics (marx/libsrc/s-gauss.c).  oracle/_ref build only. */
+/* GAUSS source statics (marx/libsrc/s-gauss.c).  Reference-side binding (integration/): compiled against the MARX tree, never into libmarxb200.so. */
 #include <s-gauss.c>
 #include "calpack_io.h"
 int calpack_is_gauss (void *st, double *shape)

@@ -1,4 +1,4 @@
-/* POINT source (marx/libsrc/s-point.c).  oracle/_ref build only. */
+/* POINT source (marx/libsrc/s-point.c).  Reference-side binding (integration/): compiled against the MARX tree, never into libmarxb200.so. */
 #include <s-point.c>
 #include "calpack_io.h"
 int calpack_is_point (void *st) { return ((Marx_Source_Type *) st)->create_photons == point_create_photons; }

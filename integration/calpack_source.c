@@ -1,5 +1,5 @@
 /* Serialises source / spectrum / dither state (marx/libsrc/dither.c statics + public Marx_Source_Type).
- * oracle/_ref build only. */
+ * Reference-side binding (integration/): compiled against the MARX tree, never into libmarxb200.so. */
 #include <dither.c>
 #include "calpack_io.h"
 

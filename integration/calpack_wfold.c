@@ -1,4 +1,4 @@
-/* WFOLD table accessor: the table type is opaque outside marx/libsrc/wfold.c.  oracle/_ref build only. */
+/* WFOLD table accessor: the table type is opaque outside marx/libsrc/wfold.c.  Reference-side binding (integration/): compiled against the MARX tree, never into libmarxb200.so. */
 #include <wfold.c>
 #include "calpack_io.h"
 

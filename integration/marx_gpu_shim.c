@@ -1,0 +1,271 @@
+/* marx_gpu_shim.c -- reference-side binding of libmarxb200.so into the UNMODIFIED marx driver.
+ *
+ * The stock marx/src/marx.c is linked with
+ *    -Wl,--wrap=JDMsrandom,--wrap=marx_mirror_init,--wrap=marx_grating_init,--wrap=marx_detector_init,
+ *        --wrap=marx_create_photons,--wrap=marx_mirror_reflect,--wrap=marx_grating_diffract,--wrap=marx_detect,
+ *        --wrap=marx_write_photons,--wrap=marx_prune_photons,--wrap=marx_dump_to_rayfile,--wrap=marx_dealloc_photon_type
+ * so that its calls (marx.c:245,254,263,569) reach the __wrap_* functions below while pfile parameter handling,
+ * the stock *_init functions (calibration file readers), obs.par and the marxio/jdfits writers stay what they are
+ * (option ii).  Per-photon work happens on the GPU only: if the configuration is not covered by the
+ * CUDA path the run stops with an error -- there is no CPU fallback in here.
+ *
+ * Data flow per iteration of the driver loop (marx.c:545-608):
+ *   marx_create_photons   -> marxb200_create_photons (+ marxb200_truncate_exposure when ExposureTime > 0)
+ *   marx_mirror_reflect   -> marxb200_mirror_reflect        (photons stay in HBM)
+ *   marx_grating_diffract -> marxb200_grating_diffract
+ *   marx_detect           -> marxb200_detect
+ *   marx_write_photons    -> marxb200_write_photons: the column files of the output directory are produced from the
+ *                            device-resident event list (converted + byte-swapped on the GPU, one fwrite per file),
+ *                            byte-identical to the stock writer's (marxio.c:403-476).  MARXB200_EGRESS=stock selects the
+ *                            stock writer instead (survivors are first copied into pt->attributes).
+ *   anything else that looks at pt->attributes (the pipe and rayfile writers, marx.c:191,220,1247) first gets the
+ *   survivors via marxb200_download (Marx_Photon_Attr_Type == marxb200_photon_attr, 136 B).
+ * Bookkeeping of Marx_Photon_Type follows source.c:268-384 (start_time, total_time, tag_start, history).
+ *
+ * Table upload: on the first marx_create_photons the post-init statics of the stock modules are serialised by the
+ * calpack_*.c units (the field mappings of INTEGRATION.md section 2) and handed to marxb200_load_calpack.
+ * Environment: MARXB200_DEVICE (CUDA ordinal, default 0), MARXB200_EGRESS (bulk [default] | stock).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+#include <marx.h>
+#include <marxb200.h>
+
+extern int _Marx_Dither_Mode;          /* marx/libsrc/_marx.h:144-145 (library-private header) */
+#define DITHER_MODE_NONE 0
+#include "calpack_io.h"
+
+extern void __real_JDMsrandom (unsigned long);
+extern int __real_marx_mirror_init (Param_File_Type *);
+extern int __real_marx_grating_init (Param_File_Type *);
+extern int __real_marx_detector_init (Param_File_Type *);
+extern int __real_marx_write_photons (Marx_Photon_Type *, unsigned long, char *, int, double);
+extern void __real_marx_prune_photons (Marx_Photon_Type *);
+extern int __real_marx_dump_to_rayfile (char *, int, Marx_Photon_Type *, double);
+extern int __real_marx_dealloc_photon_type (Marx_Photon_Type *);
+
+static marxb200_ctx *Ctx;
+static unsigned long Seed = 1;
+static int Mirror_Id = -1, Grating_Id = -1, Detector_Id = -1;
+static uint64_t Next_Ray;              /* 64-bit global ray index = RNG counter; low 32 bits = the reference's tag */
+static int Host_Is_Stale;              /* photons of the current batch live in HBM only */
+static int Have_Support_Orders;
+static int Stock_Egress;               /* MARXB200_EGRESS=stock */
+static int Bulk_Written;               /* the current batch went to the output directory straight from the device */
+
+static int gpu_error (const char *what)
+{
+   marx_error ("marxb200: %s: %s", what, marxb200_last_error ());
+   return -1;
+}
+
+void __wrap_JDMsrandom (unsigned long seed)       /* marx.c:846-849: RandomSeed becomes the Philox key */
+{
+   Seed = seed;
+   __real_JDMsrandom (seed);
+}
+int __wrap_marx_mirror_init (Param_File_Type *p) { return Mirror_Id = __real_marx_mirror_init (p); }
+int __wrap_marx_grating_init (Param_File_Type *p) { return Grating_Id = __real_marx_grating_init (p); }
+int __wrap_marx_detector_init (Param_File_Type *p) { return Detector_Id = __real_marx_detector_init (p); }
+
+static int gpu_init (Marx_Source_Type *st, Marx_Photon_Type *pt)
+{
+   char path[] = "/tmp/marxb200_XXXXXX";
+   mxcp_writer w;
+   double meta[8];
+   const char *dev = getenv ("MARXB200_DEVICE");
+   int fd, status = -1;
+
+   if (Mirror_Id != MARX_MIRROR_HRMA)
+     { marx_error ("marxb200: MirrorType must be HRMA for the GPU path"); return -1; }
+   if ((Grating_Id != 0) && (Grating_Id != MARX_GRATING_HETG) && (Grating_Id != MARX_GRATING_LETG))
+     { marx_error ("marxb200: GratingType must be NONE, HETG or LETG for the GPU path"); return -1; }
+   if ((Detector_Id != 0) && (Detector_Id != MARX_DETECTOR_ACIS_S) && (Detector_Id != MARX_DETECTOR_ACIS_I)
+       && (Detector_Id != MARX_DETECTOR_HRC_S))
+     { marx_error ("marxb200: DetectorType must be NONE, ACIS-S, ACIS-I or HRC-S for the GPU path"); return -1; }
+
+   if (-1 == marxb200_create (&Ctx, dev ? atoi (dev) : 0, (uint64_t) Seed))
+     return gpu_error ("marxb200_create");
+
+   if (-1 == (fd = mkstemp (path)))
+     { marx_error ("marxb200: cannot create a temporary file"); return -1; }
+   close (fd);
+   if (-1 == mxcp_open_write (&w, path))
+     { marx_error ("marxb200: cannot write %s", path); return -1; }
+   memset (meta, 0, sizeof (meta));
+   meta[0] = Mirror_Id; meta[1] = Grating_Id; meta[2] = Detector_Id; meta[5] = (double) Seed;
+   CP_F64 (&w, "meta", meta, 8);
+   if (-1 == calpack_dump_source (&w, st))
+     marx_error ("marxb200: SourceType must be POINT, GAUSS, BETA or DISK for the GPU path");
+   else if ((-1 == calpack_dump_dither (&w))
+	    || (-1 == calpack_dump_hrma (&w))
+	    || (-1 == calpack_dump_grating (&w, Grating_Id))
+	    || (-1 == ((Detector_Id == MARX_DETECTOR_HRC_S) ? calpack_dump_hrc_s (&w, Detector_Id)
+		       : calpack_dump_acis_s (&w, Detector_Id))))
+     marx_error ("marxb200: could not serialise the module tables");
+   else status = 0;
+   mxcp_close_write (&w);
+   if ((status == 0) && (-1 == marxb200_load_calpack (Ctx, path)))
+     status = gpu_error ("table upload");
+   (void) unlink (path);
+   if (status == -1) return -1;
+
+   if (-1 == marxb200_alloc_photons (Ctx, pt->max_n_photons))
+     return gpu_error ("marxb200_alloc_photons");
+
+   Have_Support_Orders = (Grating_Id == MARX_GRATING_LETG);
+   Stock_Egress = ((NULL != getenv ("MARXB200_EGRESS")) && (0 == strcmp (getenv ("MARXB200_EGRESS"), "stock")));
+   marx_message ("marxb200: ray trace on CUDA device %d, Philox key %lu\n", dev ? atoi (dev) : 0, Seed);
+   return 0;
+}
+
+/* survivors of the current batch -> pt->attributes, arrival order (marxio.c:422-435) */
+static int sync_host (Marx_Photon_Type *pt)
+{
+   uint64_t n_live = 0, i;
+   unsigned int *idx;
+
+   if (Host_Is_Stale == 0) return 0;
+   if (-1 == marxb200_download (Ctx, (marxb200_photon_attr *) pt->attributes, pt->max_n_photons, &n_live))
+     return gpu_error ("marxb200_download");
+
+   if (pt->sorted_index != NULL) JDMfree_integer_vector ((int *) pt->sorted_index);
+   if (NULL == (idx = (unsigned int *) JDMinteger_vector ((unsigned int) (n_live ? n_live : 1))))
+     return -1;
+   for (i = 0; i < n_live; i++)
+     {
+	idx[i] = (unsigned int) i;
+	pt->sorted_energies[i] = pt->attributes[i].energy;
+     }
+   pt->sorted_index = idx;
+   pt->n_photons = pt->num_sorted = (unsigned int) n_live;
+   Host_Is_Stale = 0;
+   return 0;
+}
+
+int __wrap_marx_create_photons (Marx_Source_Type *st, Marx_Photon_Type *pt, unsigned int num,
+				unsigned int *num_collected, double *exposure_time)
+{
+   uint64_t n = num;
+   double t_end;
+
+   *num_collected = 0;
+   if ((st == NULL) || (pt == NULL)) return -1;
+   if ((Ctx == NULL) && (-1 == gpu_init (st, pt))) return -1;
+   if (num > pt->max_n_photons)
+     { marx_error ("marxb200: batch of %u rays exceeds the photon buffer", num); return -1; }
+
+   pt->source_distance = st->distance;                    /* source.c:282-285 */
+   pt->history = 0;
+   pt->start_time += pt->total_time;
+
+   /* time base < 0: the running sum of arrival times continues on the device (source.c:285,326) */
+   if (-1 == marxb200_create_photons (Ctx, Next_Ray, n, -1.0))
+     return gpu_error ("marxb200_create_photons");
+   if ((exposure_time != NULL)                            /* source.c:323-334 */
+       && (-1 == marxb200_truncate_exposure (Ctx, *exposure_time, &n)))
+     return gpu_error ("marxb200_truncate_exposure");
+   if (-1 == marxb200_get_counts (Ctx, NULL, NULL, &t_end))
+     return gpu_error ("marxb200_get_counts");
+
+   pt->history |= (MARX_ENERGY_OK | MARX_TIME_OK | MARX_X_VECTOR_OK | MARX_P_VECTOR_OK | MARX_TAG_OK);
+   pt->tag_start += (unsigned int) n;                     /* source.c:346-355 */
+   Next_Ray += n;
+   pt->num_sorted = pt->n_photons = (unsigned int) n;
+   pt->total_time = (n == 0) ? 0.0 : (t_end - pt->start_time);   /* source.c:377-381 */
+   *num_collected = (unsigned int) n;
+   Host_Is_Stale = 1;
+   Bulk_Written = 0;
+   return 0;
+}
+
+int __wrap_marx_mirror_reflect (Marx_Photon_Type *pt, int verbose)
+{
+   if (pt->history & MARX_MIRROR_SHELL_OK) return 0;      /* hrma.c:1171-1173 */
+   pt->history |= MARX_MIRROR_SHELL_OK;
+   if (verbose > 0) marx_message ("Reflecting from HRMA [B200]\n");
+   if (-1 == marxb200_mirror_reflect (Ctx)) return gpu_error ("marxb200_mirror_reflect");
+   return 0;
+}
+
+int __wrap_marx_grating_diffract (Marx_Photon_Type *pt, int verbose)
+{
+   if (Grating_Id == 0) return 0;                         /* grating.c:87-: no grating */
+   if (pt->history & MARX_ORDER_OK) return 0;             /* diffract.c:982-984 */
+   pt->history |= MARX_ORDER_OK;
+   if (Have_Support_Orders)                               /* diffract.c:1098-1118 */
+     pt->history |= (MARX_ORDER1_OK | MARX_ORDER2_OK | MARX_ORDER3_OK | MARX_ORDER4_OK);
+   if (verbose > 0) marx_message ("Diffracting from %s [B200]\n", (Grating_Id == MARX_GRATING_LETG) ? "LETG" : "HETG");
+   if (-1 == marxb200_grating_diffract (Ctx)) return gpu_error ("marxb200_grating_diffract");
+   return 0;
+}
+
+int __wrap_marx_detect (Marx_Photon_Type *pt, int verbose)
+{
+   if ((Detector_Id != 0) && (0 == (pt->history & MARX_DET_NUM_OK)))   /* acis-s.c:186-190, hrc-s.c:242-248 */
+     {
+	if (Detector_Id == MARX_DETECTOR_HRC_S)
+	  pt->history |= (MARX_DET_REGION_OK | MARX_PULSEHEIGHT_OK | MARX_DET_PIXEL_OK | MARX_DET_NUM_OK | MARX_DET_UV_PIXEL_OK);
+	else
+	  pt->history |= (MARX_DET_PIXEL_OK | MARX_DET_NUM_OK | MARX_PULSEHEIGHT_OK | MARX_PI_OK);
+	if (verbose > 0) marx_message ("Detecting [B200]\n");
+	if (-1 == marxb200_detect (Ctx)) return gpu_error ("marxb200_detect");
+     }
+   return 0;
+}
+
+int __wrap_marx_write_photons (Marx_Photon_Type *pt, unsigned long write_mask, char *dir, int open_mode, double total_time)
+{
+   if ((Ctx == NULL) || Stock_Egress || (Host_Is_Stale == 0))
+     {
+	if ((Ctx != NULL) && (-1 == sync_host (pt))) return -1;
+	return __real_marx_write_photons (pt, write_mask, dir, open_mode, total_time);
+     }
+   /* marxio.c:409-414 */
+   if (_Marx_Dither_Mode != DITHER_MODE_NONE)
+     write_mask &= (pt->history | MARX_SKY_DITHER_OK | MARX_DET_DITHER_OK);
+   else
+     write_mask &= pt->history;
+   if (-1 == marxb200_write_photons (Ctx, dir, (uint64_t) write_mask, open_mode, total_time))
+     return gpu_error ("marxb200_write_photons");
+   Bulk_Written = 1;
+   return 0;
+}
+
+void __wrap_marx_prune_photons (Marx_Photon_Type *pt)
+{
+   if ((Ctx != NULL) && Host_Is_Stale)
+     {
+	uint64_t n_live = 0;
+	if (Bulk_Written && (0 == marxb200_get_counts (Ctx, NULL, &n_live, NULL)))
+	  {
+	     /* marx.c:593 only needs the number of survivors; they were written from the device */
+	     pt->num_sorted = (unsigned int) n_live;
+	     return;
+	  }
+	if (-1 == sync_host (pt)) return;
+     }
+   __real_marx_prune_photons (pt);
+}
+
+int __wrap_marx_dump_to_rayfile (char *file, int new_file, Marx_Photon_Type *pt, double total_time)
+{
+   if (-1 == sync_host (pt)) return -1;                   /* DumpToRayFile=yes skips process_photons (marx.c:582) */
+   return __real_marx_dump_to_rayfile (file, new_file, pt, total_time);
+}
+
+int __wrap_marx_dealloc_photon_type (Marx_Photon_Type *pt)
+{
+   if (Ctx != NULL)
+     {
+	uint64_t stage[4];
+	if (0 == marxb200_get_stage_counts (Ctx, stage))
+	  marx_message ("marxb200: last batch: %lu generated, %lu reflected, %lu diffracted, %lu detected\n",
+			(unsigned long) stage[0], (unsigned long) stage[1], (unsigned long) stage[2], (unsigned long) stage[3]);
+	(void) marxb200_destroy (Ctx);
+	Ctx = NULL;
+     }
+   return __real_marx_dealloc_photon_type (pt);
+}

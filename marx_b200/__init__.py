@@ -7,7 +7,8 @@ fallback: importing works without a GPU, every compute call raises if the librar
 missing.
 """
 from .api import (MarxB200, MarxB200Error, PHOTON_DTYPE, caldata_path, lib_path, load_library,
-                  STAGE_SOURCE, STAGE_MIRROR, STAGE_GRATING, STAGE_DETECTOR, EXPORTED_SYMBOLS)
+                  STAGE_SOURCE, STAGE_MIRROR, STAGE_GRATING, STAGE_DETECTOR, EXPORTED_SYMBOLS, HISTORY, read_marx_column)
 
 __all__ = ["MarxB200", "MarxB200Error", "PHOTON_DTYPE", "caldata_path", "lib_path", "load_library",
-           "STAGE_SOURCE", "STAGE_MIRROR", "STAGE_GRATING", "STAGE_DETECTOR", "EXPORTED_SYMBOLS"]
+           "STAGE_SOURCE", "STAGE_MIRROR", "STAGE_GRATING", "STAGE_DETECTOR", "EXPORTED_SYMBOLS", "HISTORY",
+           "read_marx_column"]

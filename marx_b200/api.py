@@ -18,9 +18,9 @@ EXPORTED_SYMBOLS = [
     "marxb200_abi_version", "marxb200_last_error", "marxb200_create", "marxb200_destroy", "marxb200_set_stream",
     "marxb200_set_compaction", "marxb200_set_source", "marxb200_set_dither", "marxb200_set_hrma",
     "marxb200_set_grating", "marxb200_set_acis", "marxb200_set_hrc_s", "marxb200_load_calpack", "marxb200_alloc_photons",
-    "marxb200_create_photons", "marxb200_time_sums", "marxb200_mirror_reflect", "marxb200_grating_diffract",
+    "marxb200_create_photons", "marxb200_truncate_exposure", "marxb200_time_sums", "marxb200_mirror_reflect", "marxb200_grating_diffract",
     "marxb200_detect", "marxb200_restore_order", "marxb200_trace", "marxb200_trace_from", "marxb200_set_profiling", "marxb200_get_kernel_ms", "marxb200_get_counts", "marxb200_get_stage_counts", "marxb200_get_internal_counts", "marxb200_download",
-    "marxb200_upload", "marxb200_download_all", "marxb200_download_columns", "marxb200_egress_begin", "marxb200_egress_end", "marxb200_get_launch_count",
+    "marxb200_upload", "marxb200_download_all", "marxb200_download_columns", "marxb200_egress_begin", "marxb200_egress_end", "marxb200_write_photons", "marxb200_measure_fp64_peak", "marxb200_get_launch_count",
 ]
 
 # Marx_Photon_Attr_Type, marx/libsrc/marx.h:51-100 (136 bytes; offsets probed in SURVEY.md 8a1)
@@ -33,6 +33,30 @@ PHOTON_DTYPE = np.dtype({
     "offsets": [0, 8, 32, 56, 64, 68, 72, 76, 80, 84, 108, 112, 116, 120, 121, 122, 123, 128],
     "itemsize": 136,
 })
+
+
+# history / write-mask bits, marx/libsrc/marx.h:126-147
+HISTORY = {"ENERGY": 0x1, "TIME": 0x2, "X_VECTOR": 0x4, "P_VECTOR": 0x8, "TAG": 0x10, "PULSEHEIGHT": 0x20, "PI": 0x40,
+           "DET_PIXEL": 0x80, "DET_NUM": 0x100, "DET_REGION": 0x200, "DET_UV_PIXEL": 0x400, "MIRROR_SHELL": 0x800,
+           "SKY_DITHER": 0x1000, "DET_DITHER": 0x2000, "ORDER": 0x100000, "ORDER1": 0x200000, "ORDER2": 0x400000,
+           "ORDER3": 0x800000, "ORDER4": 0x1000000}
+
+
+def read_marx_column(path):
+    """Read one column file of a MARX output directory (format: marxio.c:151-205 header + big-endian data).
+    Returns (column name, numpy array in native byte order)."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    if len(raw) < 32 or raw[:4] != bytes([0x83, 0x13, 0x89, 0x8D]):
+        raise MarxB200Error("%s: not a MARX column file" % path)
+    kind = chr(raw[4])
+    name = raw[5:20].split(b"\0")[0].decode()
+    rows = int.from_bytes(raw[20:24], "big", signed=True)
+    dt = {"E": ">f4", "D": ">f8", "J": ">i4", "I": ">i2", "A": "i1"}[kind]
+    data = np.frombuffer(raw, dtype=dt, offset=32)
+    if len(data) != rows:
+        raise MarxB200Error("%s: header says %d rows, file holds %d" % (path, rows, len(data)))
+    return name, data.astype(data.dtype.newbyteorder("="))
 
 
 class MarxB200Error(RuntimeError):
@@ -76,6 +100,7 @@ def load_library():
         "marxb200_load_calpack": [vp, C.c_char_p],
         "marxb200_alloc_photons": [vp, u64],
         "marxb200_create_photons": [vp, u64, u64, dbl],
+        "marxb200_truncate_exposure": [vp, dbl, C.POINTER(u64)],
         "marxb200_time_sums": [vp, u64, u64, C.POINTER(dbl), u64, C.POINTER(u64)],
         "marxb200_mirror_reflect": [vp],
         "marxb200_grating_diffract": [vp],
@@ -95,6 +120,8 @@ def load_library():
         "marxb200_get_launch_count": [vp, C.POINTER(u64)],
         "marxb200_egress_begin": [vp, u64],
         "marxb200_egress_end": [vp, vp, C.POINTER(u64)],
+        "marxb200_write_photons": [vp, C.c_char_p, u64, i32, dbl],
+        "marxb200_measure_fp64_peak": [vp, C.POINTER(dbl)],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -163,6 +190,12 @@ class MarxB200:
         """marx_create_photons (source.c:268-384) for global ray indices [first_ray, first_ray+n)."""
         self._check(self._lib.marxb200_create_photons(self._ctx, int(first_ray), int(n), float(time_base)))
 
+    def truncate_exposure(self, exposure_left):
+        """ExposureTime handling of marx_create_photons (source.c:323-334); returns the number of rays kept."""
+        n = C.c_uint64()
+        self._check(self._lib.marxb200_truncate_exposure(self._ctx, float(exposure_left), C.byref(n)))
+        return n.value
+
     def time_sums(self, first_ray, n):
         cap = n // 65536 + 2
         buf = (C.c_double * cap)()
@@ -217,6 +250,12 @@ class MarxB200:
         self._check(self._lib.marxb200_get_internal_counts(self._ctx, a))
         return [int(v) for v in a]
 
+    def measure_fp64_peak(self):
+        """measured FP64 peak of this GPU in TFLOP/s (DFMA chains; the FP64 roofline denominator)"""
+        t = C.c_double()
+        self._check(self._lib.marxb200_measure_fp64_peak(self._ctx, C.byref(t)))
+        return t.value
+
     def launch_count(self):
         n = C.c_uint64()
         self._check(self._lib.marxb200_get_launch_count(self._ctx, C.byref(n)))
@@ -254,6 +293,12 @@ class MarxB200:
         got = C.c_uint64()
         self._check(self._lib.marxb200_egress_end(self._ctx, C.byref(cols), C.byref(got)))
         return {k: v[:got.value] for k, v in out.items()}
+
+    def write_photons(self, directory, write_mask, open_mode, total_time):
+        """marx_write_photons (marxio.c:403-476): create/append the column files of an output directory from the
+        device-resident live list; write_mask uses the MARX_*_OK bits (HISTORY below)."""
+        self._check(self._lib.marxb200_write_photons(self._ctx, os.fsencode(directory), int(write_mask),
+                                                     1 if open_mode else 0, float(total_time)))
 
     def download_columns(self, names=("energy", "time", "chipx", "chipy", "pha", "ccd", "order", "ray"), out=None):
         _, live, _ = self.counts()

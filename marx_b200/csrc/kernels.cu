@@ -777,6 +777,122 @@ __global__ void __launch_bounds__ (256) aos_to_soa (const marxb200_photon_attr *
 }
 
 // ---------------------------------------------------------------------------------------------
+// ExposureTime truncation (source.c:323-334): keep rays up to and including the first one whose arrival time,
+// counted from the batch start, reaches the exposure left.  Arrival times are a running sum, hence monotone: one
+// thread bisects.  Updates the generated count and the running end time (pt->total_time, source.c:377-381).
+// ---------------------------------------------------------------------------------------------
+__global__ void exposure_truncate (const double *time, unsigned long long *n_ptr, double *dev_times, double exposure_left)
+{
+   if ((blockIdx.x != 0) || (threadIdx.x != 0)) return;
+   const unsigned long long n = *n_ptr;
+   if (n == 0) return;
+   const double start = dev_times[0];
+   unsigned long long lo = 0, hi = n;            // first index with time - start >= exposure_left, or n
+   while (lo < hi)
+     {
+        const unsigned long long mid = lo + (hi - lo) / 2;
+        if (time[mid] - start >= exposure_left) hi = mid; else lo = mid + 1;
+     }
+   const unsigned long long keep = (lo < n) ? lo + 1 : n;
+   *n_ptr = keep;
+   dev_times[1] = time[keep - 1];
+}
+void launch_exposure_truncate (const PhotonSoA &buf, unsigned long long *n, double *dev_times, double exposure_left, cudaStream_t s)
+{
+   exposure_truncate<<<1, 32, 0, s>>> (buf.time, n, dev_times, exposure_left);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bulk event egress in the reference's on-disk column format (marxio.c:217-322): each selected column of the live
+// list is converted to its file type (float32 / int16 / int32 / int8, the casts of the MAKE_WRITE_*_FUNC macros) and
+// byte-swapped to big endian (JDMwrite_float32/int16/int32) on the device, so that the host only appends the packed
+// images to the column files.  One thread per (photon, column) pair would waste the SoA locality; instead each
+// thread handles one photon and walks the (uniform) column list, so that every store instruction of a warp hits
+// consecutive elements of one packed column.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bswap32 (uint32_t v) { return __byte_perm (v, 0u, 0x0123); }
+__device__ __forceinline__ uint16_t bswap16 (uint16_t v) { return (uint16_t) ((v << 8) | (v >> 8)); }
+
+__global__ void __launch_bounds__ (256) egress_pack (PhotonSoA in, const unsigned long long *n_ptr, uint64_t max_n, EgressPlan plan,
+                                                     unsigned char *dst, const double *dev_start_time, double total_time)
+{
+   const uint64_t n = min ((uint64_t) *n_ptr, max_n);
+   const double start_time = *dev_start_time;
+   for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x)
+     {
+        for (int c = 0; c < plan.num_cols; c++)
+          {
+             unsigned char *base = dst + plan.offset[c];
+             float f = 0.0f;
+             switch (plan.kind[c])
+               {
+                case EGRESS_PI: f = in.pi[i]; break;
+                case EGRESS_ENERGY: f = (float) in.energy[i]; break;
+                // write_time: (float) (at->arrival_time + total_time) with arrival_time = time - batch start (soa_to_aos)
+                case EGRESS_TIME: f = (float) ((in.time[i] - start_time) + total_time); break;
+                case EGRESS_XPOS: f = (float) in.x0[i]; break;
+                case EGRESS_YPOS: f = (float) in.x1[i]; break;
+                case EGRESS_ZPOS: f = (float) in.x2[i]; break;
+                case EGRESS_XCOS: f = (float) in.p0[i]; break;
+                case EGRESS_YCOS: f = (float) in.p1[i]; break;
+                case EGRESS_ZCOS: f = (float) in.p2[i]; break;
+                case EGRESS_CHIPX: f = in.chipx[i]; break;
+                case EGRESS_CHIPY: f = in.chipy[i]; break;
+                case EGRESS_HRC_U: f = in.upix[i]; break;
+                case EGRESS_HRC_V: f = in.vpix[i]; break;
+                case EGRESS_SKY_RA: f = in.dra[i]; break;
+                case EGRESS_SKY_DEC: f = in.ddec[i]; break;
+                case EGRESS_SKY_ROLL: f = in.droll[i]; break;
+                case EGRESS_ZERO_F32: f = 0.0f; break;
+                case EGRESS_TAG:
+                  reinterpret_cast<uint32_t *> (base)[i] = bswap32 ((uint32_t) in.ray[i]); continue;
+                case EGRESS_PHA:
+                  reinterpret_cast<uint16_t *> (base)[i] = bswap16 ((uint16_t) in.pha[i]); continue;
+                case EGRESS_MIRROR:
+                  reinterpret_cast<uint16_t *> (base)[i] = bswap16 ((uint16_t) in.shell[i]); continue;
+                case EGRESS_CCD: base[i] = (unsigned char) in.ccd[i]; continue;
+                case EGRESS_REGION: base[i] = (unsigned char) in.region[i]; continue;
+                case EGRESS_ORDER: base[i] = (unsigned char) in.order[i]; continue;
+                case EGRESS_ORDER1: base[i] = (unsigned char) (in.sorders[i] & 0xFFu); continue;
+                case EGRESS_ORDER2: base[i] = (unsigned char) ((in.sorders[i] >> 8) & 0xFFu); continue;
+                case EGRESS_ORDER3: base[i] = (unsigned char) ((in.sorders[i] >> 16) & 0xFFu); continue;
+                case EGRESS_ORDER4: base[i] = (unsigned char) (in.sorders[i] >> 24); continue;
+                default: continue;
+               }
+             reinterpret_cast<uint32_t *> (base)[i] = bswap32 (__float_as_uint (f));
+          }
+     }
+}
+void launch_egress_pack (const PhotonSoA &in, const unsigned long long *n, uint64_t max_n, const EgressPlan &plan, void *dst,
+                         const double *dev_start_time, double total_time, cudaStream_t s)
+{
+   if ((max_n == 0) || (plan.num_cols == 0)) return;
+   unsigned int grid = (unsigned int) min ((uint64_t) 148 * 8, (max_n + 255) / 256);
+   egress_pack<<<grid, 256, 0, s>>> (in, n, max_n, plan, (unsigned char *) dst, dev_start_time, total_time);
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64 roofline denominator: a DFMA-chain microbenchmark (SURVEY.md 8d asks for the FP64 peak to be MEASURED on the
+// box; MEASURED_PEAKS.json only holds HBM and bf16).  8 independent chains per thread hide the DFMA latency.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__ (256) fp64_peak_kernel (double *sink, int iters, double a, double b)
+{
+   double x0 = threadIdx.x * 1e-3, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0, x4 = x0 + 4.0, x5 = x0 + 5.0, x6 = x0 + 6.0, x7 = x0 + 7.0;
+   for (int i = 0; i < iters; i++)
+     {
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          {
+             x0 = __fma_rn (x0, a, b); x1 = __fma_rn (x1, a, b); x2 = __fma_rn (x2, a, b); x3 = __fma_rn (x3, a, b);
+             x4 = __fma_rn (x4, a, b); x5 = __fma_rn (x5, a, b); x6 = __fma_rn (x6, a, b); x7 = __fma_rn (x7, a, b);
+          }
+     }
+   const double r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+   if (r == 123.456) sink[0] = r;        // never true: keeps the chains alive
+}
+void launch_fp64_peak (double *sink, int grid, int iters, cudaStream_t s) { fp64_peak_kernel<<<grid, 256, 0, s>>> (sink, iters, 0.999999, 1e-9); }
+
+// ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
 static inline unsigned int n_tiles_of (uint64_t n) { return (unsigned int) ((n + kTile - 1) / kTile); }

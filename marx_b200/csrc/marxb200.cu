@@ -78,6 +78,7 @@ struct marxb200_ctx
    void *h_pinned = nullptr; size_t h_pinned_bytes = 0;
 
    uint64_t launches = 0;
+   uint64_t egress_rows[32] = {0};               // cumulative rows per column file (marxio.c File_Pointers[].num_rows)
 
    // pipelined egress
    cudaStream_t copy_stream = nullptr;
@@ -481,6 +482,23 @@ extern "C" int marxb200_create_photons (marxb200_ctx *c, uint64_t first_ray, uin
    return 0;
 }
 
+// ExposureTime handling of marx_create_photons (source.c:323-334): valid directly after marxb200_create_photons.
+extern "C" int marxb200_truncate_exposure (marxb200_ctx *c, double exposure_left, uint64_t *n_kept)
+{
+   if (c == nullptr) return fail ("NULL ctx");
+   if (c->stage_done != 0) return fail ("marxb200_truncate_exposure: call it directly after marxb200_create_photons");
+   CUDA_OK (cudaSetDevice (c->device));
+   launch_exposure_truncate (c->buf[c->cur], c->d_counts + 0, c->d_times, exposure_left, c->stream);
+   c->launches += 1;
+   unsigned long long n = 0;
+   CUDA_OK (cudaMemcpyAsync (&n, c->d_counts + 0, sizeof (n), cudaMemcpyDeviceToHost, c->stream));
+   CUDA_OK (cudaStreamSynchronize (c->stream));
+   CUDA_OK (cudaGetLastError ());
+   c->n_generated = n;
+   if (n_kept) *n_kept = n;
+   return 0;
+}
+
 // super-tile sums of the arrival-time increments of rays [first_ray, first_ray+n) -- the quantity ranks
 // exchange (all-gather) to give every GPU its time base (DESIGN.md "multi-GPU").
 extern "C" int marxb200_time_sums (marxb200_ctx *c, uint64_t first_ray, uint64_t n, double *sums_host, uint64_t max_sums, uint64_t *n_sums)
@@ -806,6 +824,121 @@ extern "C" int marxb200_download_columns (marxb200_ctx *c, const marxb200_column
    return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// marx_write_photons (marxio.c:403-476) for the device-resident live list: bulk column files, byte-compatible with
+// the reference's (32-byte header marxio.c:151-205 + big-endian column data), without the AoS detour and without one
+// fwrite per photon per column.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct EgressCol { uint64_t mask; const char *file, *colname; char type; int kind; int size; };
+// Outfile_Info_Table, marxio.c:292-322 (same files, names, type letters)
+const EgressCol kEgressCols[] = {
+   {MARXB200_PI_OK, "b_energy.dat", "B_ENERGY", 'E', EGRESS_PI, 4},
+   {MARXB200_ENERGY_OK, "energy.dat", "ENERGY", 'E', EGRESS_ENERGY, 4},
+   {MARXB200_TIME_OK, "time.dat", "TIME", 'E', EGRESS_TIME, 4},
+   {MARXB200_TAG_OK, "tag.dat", "TAG", 'J', EGRESS_TAG, 4},
+   {MARXB200_X_VECTOR_OK, "xpos.dat", "XPOS", 'E', EGRESS_XPOS, 4},
+   {MARXB200_X_VECTOR_OK, "ypos.dat", "YPOS", 'E', EGRESS_YPOS, 4},
+   {MARXB200_X_VECTOR_OK, "zpos.dat", "ZPOS", 'E', EGRESS_ZPOS, 4},
+   {MARXB200_P_VECTOR_OK, "xcos.dat", "COSX", 'E', EGRESS_XCOS, 4},
+   {MARXB200_P_VECTOR_OK, "ycos.dat", "COSY", 'E', EGRESS_YCOS, 4},
+   {MARXB200_P_VECTOR_OK, "zcos.dat", "COSZ", 'E', EGRESS_ZCOS, 4},
+   {MARXB200_PULSEHEIGHT_OK, "pha.dat", "PHA", 'I', EGRESS_PHA, 2},
+   {MARXB200_DET_NUM_OK, "detector.dat", "CCDID", 'A', EGRESS_CCD, 1},
+   {MARXB200_DET_PIXEL_OK, "xpixel.dat", "CHIPX", 'E', EGRESS_CHIPX, 4},
+   {MARXB200_DET_PIXEL_OK, "ypixel.dat", "CHIPY", 'E', EGRESS_CHIPY, 4},
+   {MARXB200_DET_UV_PIXEL_OK, "hrc_u.dat", "U", 'E', EGRESS_HRC_U, 4},
+   {MARXB200_DET_UV_PIXEL_OK, "hrc_v.dat", "V", 'E', EGRESS_HRC_V, 4},
+   {MARXB200_MIRROR_SHELL_OK, "mirror.dat", "MIRROR", 'I', EGRESS_MIRROR, 2},
+   {MARXB200_DET_REGION_OK, "hrcregion.dat", "HRCREGION", 'A', EGRESS_REGION, 1},
+   {MARXB200_ORDER_OK, "order.dat", "ORDER", 'A', EGRESS_ORDER, 1},
+   {MARXB200_ORDER1_OK, "ofine.dat", "FINE", 'A', EGRESS_ORDER1, 1},
+   {MARXB200_ORDER2_OK, "ocoarse1.dat", "COARSE1", 'A', EGRESS_ORDER2, 1},
+   {MARXB200_ORDER3_OK, "ocoarse2.dat", "COARSE2", 'A', EGRESS_ORDER3, 1},
+   {MARXB200_ORDER4_OK, "ocoarse3.dat", "COARSE3", 'A', EGRESS_ORDER4, 1},
+   {MARXB200_SKY_DITHER_OK, "sky_ra.dat", "RA", 'E', EGRESS_SKY_RA, 4},
+   {MARXB200_SKY_DITHER_OK, "sky_dec.dat", "DEC", 'E', EGRESS_SKY_DEC, 4},
+   {MARXB200_SKY_DITHER_OK, "sky_roll.dat", "ROLL", 'E', EGRESS_SKY_ROLL, 4},
+   {MARXB200_DET_DITHER_OK, "det_dy.dat", "DET_DY", 'E', EGRESS_ZERO_F32, 4},     // 0 for INTERNAL dither (dither.c:167-182)
+   {MARXB200_DET_DITHER_OK, "det_dz.dat", "DET_DZ", 'E', EGRESS_ZERO_F32, 4},
+   {MARXB200_DET_DITHER_OK, "det_theta.dat", "DET_THETA", 'E', EGRESS_ZERO_F32, 4},
+};
+constexpr int kNumEgressCols = (int) (sizeof (kEgressCols) / sizeof (kEgressCols[0]));
+static_assert (kNumEgressCols <= kMaxEgressCols, "EgressPlan too small");
+
+void put_be32 (unsigned char *b, uint32_t v) { b[0] = (unsigned char) (v >> 24); b[1] = (unsigned char) (v >> 16); b[2] = (unsigned char) (v >> 8); b[3] = (unsigned char) v; }
+}
+
+extern "C" int marxb200_write_photons (marxb200_ctx *c, const char *dir, uint64_t write_mask, int open_mode, double total_time)
+{
+   if ((c == nullptr) || (dir == nullptr)) return fail ("marxb200_write_photons: NULL argument");
+   if (c->stage_done < 0) return fail ("marxb200_write_photons: no photons");
+   CUDA_OK (cudaSetDevice (c->device));
+   if (-1 == ensure_order (c)) return -1;
+   unsigned long long n = 0;
+   CUDA_OK (cudaMemcpyAsync (&n, c->d_counts + c->stage_done, sizeof (n), cudaMemcpyDeviceToHost, c->stream));
+   CUDA_OK (cudaStreamSynchronize (c->stream));
+
+   EgressPlan plan;
+   memset (&plan, 0, sizeof (plan));
+   int which[kMaxEgressCols];
+   uint64_t total = 0;
+   for (int k = 0; k < kNumEgressCols; k++)
+     {
+        if (0 == (kEgressCols[k].mask & write_mask)) continue;
+        which[plan.num_cols] = k;
+        plan.kind[plan.num_cols] = kEgressCols[k].kind;
+        plan.offset[plan.num_cols] = total;
+        plan.num_cols++;
+        total += (uint64_t) align16 ((size_t) n * kEgressCols[k].size);
+     }
+   if (n && plan.num_cols)
+     {
+        // the AoS staging buffer (136 B per photon) is always large enough: at most 29 columns x 4 B = 116 B per row
+        if (-1 == ensure_aos (c, n + 16)) return -1;
+        if (-1 == ensure_pinned (c, (size_t) total)) return -1;
+        launch_egress_pack (c->buf[c->cur], c->d_counts + c->stage_done, n, plan, c->d_aos, c->d_times, total_time, c->stream);
+        c->launches += 1;
+        CUDA_OK (cudaMemcpyAsync (c->h_pinned, c->d_aos, (size_t) total, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK (cudaStreamSynchronize (c->stream));
+        CUDA_OK (cudaGetLastError ());
+     }
+   for (int j = 0; j < plan.num_cols; j++)
+     {
+        const EgressCol &col = kEgressCols[which[j]];
+        std::string path = std::string (dir) + "/" + col.file;
+        FILE *fp;
+        if (open_mode)
+          {
+             // marx_create_write_dump_file, marxio.c:151-205: magic, type letter, column name zero-padded to offset 20,
+             // num_rows, num_cols (big-endian int32), 4 reserved bytes
+             unsigned char hdr[32];
+             static const unsigned char magic[4] = {0x83, 0x13, 0x89, 0x8D};
+             memset (hdr, 0, sizeof (hdr));
+             memcpy (hdr, magic, 4);
+             hdr[4] = (unsigned char) col.type;
+             strncpy ((char *) hdr + 5, col.colname, 15);
+             if ((nullptr == (fp = fopen (path.c_str (), "w+b"))) || (32 != fwrite (hdr, 1, 32, fp)))
+               { if (fp) fclose (fp); return fail ("marxb200_write_photons: unable to create %s", path.c_str ()); }
+             c->egress_rows[which[j]] = 0;
+          }
+        else
+          {
+             // "r+b" + seek to the end, as the reference does (marxio.c:336-340,378-386)
+             if ((nullptr == (fp = fopen (path.c_str (), "r+b"))) || (0 != fseek (fp, 0, SEEK_END)))
+               { if (fp) fclose (fp); return fail ("marxb200_write_photons: unable to open %s", path.c_str ()); }
+          }
+        const size_t bytes = (size_t) n * col.size;
+        unsigned char rows_be[4];
+        c->egress_rows[which[j]] += n;
+        put_be32 (rows_be, (uint32_t) c->egress_rows[which[j]]);
+        bool ok = (bytes == 0) || (bytes == fwrite ((const unsigned char *) c->h_pinned + plan.offset[j], 1, bytes, fp));
+        ok = ok && (0 == fseek (fp, 20, SEEK_SET)) && (4 == fwrite (rows_be, 1, 4, fp));   // marx_close_write_dump_file :82-126
+        if ((0 != fclose (fp)) || !ok) return fail ("marxb200_write_photons: write error on %s", path.c_str ());
+     }
+   return 0;
+}
+
 static size_t carve (PhotonSoA &b, unsigned char *base, uint64_t n);
 
 extern "C" int marxb200_egress_begin (marxb200_ctx *c, uint64_t max_out)
@@ -869,6 +1002,32 @@ extern "C" int marxb200_egress_end (marxb200_ctx *c, const marxb200_columns *col
    CUDA_OK (cudaStreamSynchronize (c->copy_stream));
    c->egress_pending = false;
    if (n_out) *n_out = n;
+   return 0;
+}
+
+// measured FP64 peak of this GPU (DFMA chains), the denominator of the FP64 roofline
+extern "C" int marxb200_measure_fp64_peak (marxb200_ctx *c, double *tflops)
+{
+   if ((c == nullptr) || (tflops == nullptr)) return fail ("marxb200_measure_fp64_peak: NULL argument");
+   CUDA_OK (cudaSetDevice (c->device));
+   const int grid = c->num_sms * 8, iters = 4096;
+   cudaEvent_t e0, e1;
+   CUDA_OK (cudaEventCreate (&e0)); CUDA_OK (cudaEventCreate (&e1));
+   double best = 0.0;
+   for (int rep = 0; rep < 6; rep++)     // rep 0 warms up
+     {
+        CUDA_OK (cudaEventRecord (e0, c->stream));
+        launch_fp64_peak (c->d_times + 1, grid, iters, c->stream);   // the sink is never written
+        CUDA_OK (cudaEventRecord (e1, c->stream));
+        CUDA_OK (cudaEventSynchronize (e1));
+        float ms = 0.f;
+        CUDA_OK (cudaEventElapsedTime (&ms, e0, e1));
+        const double tf = 2.0 * 64.0 * iters * 256.0 * grid / (ms * 1e-3) * 1e-12;
+        if ((rep > 0) && (tf > best)) best = tf;
+     }
+   cudaEventDestroy (e0); cudaEventDestroy (e1);
+   CUDA_OK (cudaGetLastError ());
+   *tflops = best;
    return 0;
 }
 

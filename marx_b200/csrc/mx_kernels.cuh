@@ -93,6 +93,7 @@ struct SourceArgs
 void launch_time_sums (const SourceArgs &a, cudaStream_t s);
 void launch_time_scan (const SourceArgs &a, cudaStream_t s);
 void launch_source (const SourceArgs &a, cudaStream_t s);
+void launch_exposure_truncate (const PhotonSoA &buf, unsigned long long *n, double *dev_times, double exposure_left, cudaStream_t s);
 void launch_hrma (const StageArgs &a, int phase, int grid, cudaStream_t s);
 int fused_source_grid (int num_sms);
 void launch_source_hrma (const SourceArgs &a, const StageArgs &st, int grid, cudaStream_t s);   // k0_source + k1_hrma<0> in one kernel   // phase 0,1,2 = k1a,k1b,k1c
@@ -120,5 +121,24 @@ void launch_soa_to_aos (const PhotonSoA &in, const unsigned long long *n, uint64
                         const double *dev_start_time, cudaStream_t s);
 void launch_aos_to_soa (const void *aos, const uint64_t *ray_ids, uint64_t n, const PhotonSoA &out, double start_time,
                         cudaStream_t s);
+
+// bulk egress in the reference's column-file format (marxio.c:292-322): which packed columns to produce
+enum EgressKind
+{
+   EGRESS_PI = 0, EGRESS_ENERGY, EGRESS_TIME, EGRESS_TAG, EGRESS_XPOS, EGRESS_YPOS, EGRESS_ZPOS, EGRESS_XCOS, EGRESS_YCOS,
+   EGRESS_ZCOS, EGRESS_PHA, EGRESS_CCD, EGRESS_CHIPX, EGRESS_CHIPY, EGRESS_HRC_U, EGRESS_HRC_V, EGRESS_MIRROR, EGRESS_REGION,
+   EGRESS_ORDER, EGRESS_ORDER1, EGRESS_ORDER2, EGRESS_ORDER3, EGRESS_ORDER4, EGRESS_SKY_RA, EGRESS_SKY_DEC, EGRESS_SKY_ROLL,
+   EGRESS_ZERO_F32, EGRESS_NUM_KINDS
+};
+constexpr int kMaxEgressCols = 32;
+struct EgressPlan
+{
+   int num_cols;
+   int kind[kMaxEgressCols];
+   uint64_t offset[kMaxEgressCols];      // byte offset of each packed column in the staging buffer (4-byte aligned)
+};
+void launch_fp64_peak (double *sink, int grid, int iters, cudaStream_t s);   // 64 DFMA per thread per iteration
+void launch_egress_pack (const PhotonSoA &in, const unsigned long long *n, uint64_t max_n, const EgressPlan &plan, void *dst,
+                         const double *dev_start_time, double total_time, cudaStream_t s);
 
 }  // namespace mx

@@ -1,0 +1,182 @@
+"""The drop-in boundary end to end: the UNMODIFIED reference driver (marx/src/marx.c) linked against libmarxb200.so
+through integration/marx_gpu_shim.c (-Wl,--wrap), run as a user runs `marx`, on the GPU box.
+
+  * its output directory equals what the C ABI produces for the same seed / rays (batching, running arrival time,
+    tags and the ExposureTime cut survive the Marx_Photon_Type bookkeeping of the shim);
+  * the bulk column writer (marxb200_write_photons) is byte-identical to the reference's own marx_write_photons
+    (marxio.c:403-476) fed with the same photons (MARXB200_EGRESS=stock routes them through the stock writer);
+  * the detected fraction agrees with the stock CPU `marx` (own RNG) within Poisson noise.
+"""
+import filecmp
+import glob
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import marx_b200
+from marx_b200 import HISTORY, read_marx_column
+from tests.golden.make_golden import COMMON, CONFIGS
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MARX_GPU = os.path.join(ROOT, "integration", "_build", "marx_gpu")
+REF = os.path.join(ROOT, "oracle", "_ref")
+
+
+def run_marx(exe, outdir, args, env_extra=None, check=True):
+    env = dict(os.environ, MARX_DATA_DIR=os.path.join(REF, "data"))
+    env.update(env_extra or {})
+    cmd = [exe, "@@" + os.path.join(REF, "par", "marx.par"), "OutputDir=" + str(outdir), "OutputVectors=#ETXYZ123DxyMPOabcdSrB"] + args
+    p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    if check:
+        assert p.returncode == 0, p.stdout[-2000:]
+    return p
+
+
+def read_dir(d):
+    cols = {}
+    for f in sorted(glob.glob(os.path.join(str(d), "*.dat"))):
+        name, data = read_marx_column(f)
+        cols[os.path.basename(f)] = data
+    return cols
+
+
+needs_driver = pytest.mark.skipif(not os.path.exists(MARX_GPU), reason="integration/_build/marx_gpu not built")
+
+
+@needs_driver
+def test_marx_gpu_fails_loudly_without_a_gpu(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    p = run_marx(MARX_GPU, tmp_path / "out", COMMON + CONFIGS["c1_acis_s"]["args"] + ["NumRays=1000", "dNumRays=1000"], check=False)
+    assert "no CPU fallback" in p.stdout
+    assert not glob.glob(str(tmp_path / "out" / "*.dat"))
+
+
+@pytest.mark.gpu
+@needs_driver
+@pytest.mark.parametrize("config", ["c1_acis_s", "c2_hetg_acis_s", "c3_letg_hrc_s", "c4_beta_acis_i"])
+def test_marx_gpu_output_equals_c_abi(config, tmp_path):
+    cfg = CONFIGS[config]
+    # the reference's loop always collects whole batches (marx.c:545-608): NumRays=250000 -> 3 x 100000 rays
+    n_par, dn, seed = 250000, 100000, 5
+    n = 3 * dn
+    p = run_marx(MARX_GPU, tmp_path / "out", COMMON + cfg["args"] + ["NumRays=%d" % n_par, "dNumRays=%d" % dn, "RandomSeed=%d" % seed,
+                                                                      "Verbose=1"])
+    assert "marxb200: ray trace on CUDA device" in p.stdout
+    got = read_dir(tmp_path / "out")
+    want = []
+    with marx_b200.MarxB200(config, seed=seed, max_photons=dn) as m:
+        first = 0
+        while first < n:
+            k = min(dn, n - first)
+            m.trace(first, k)
+            want.append(m.download().copy())
+            first += k
+    ph = np.concatenate(want)
+    assert len(got["energy.dat"]) == len(ph) > 0
+    assert (got["tag.dat"].astype(np.uint32) == ph["tag"]).all()
+    assert (got["energy.dat"] == ph["energy"].astype(np.float32)).all()
+    for k, f in enumerate(("xpos.dat", "ypos.dat", "zpos.dat")):
+        assert (got[f] == ph["x"][:, k].astype(np.float32)).all(), f
+    for k, f in enumerate(("xcos.dat", "ycos.dat", "zcos.dat")):
+        assert (got[f] == ph["p"][:, k].astype(np.float32)).all(), f
+    assert (got["mirror.dat"] == ph["mirror_shell"].astype(np.int16)).all()
+    assert (got["detector.dat"] == ph["ccd_num"]).all()
+    assert (got["xpixel.dat"] == ph["y_pixel"]).all() and (got["ypixel.dat"] == ph["z_pixel"]).all()
+    assert (got["pha.dat"] == ph["pulse_height"]).all()
+    if "b_energy.dat" in got:
+        assert (got["b_energy.dat"] == ph["pi"]).all()
+    if "order.dat" in got:
+        assert (got["order.dat"] == ph["order"]).all()
+    if config == "c3_letg_hrc_s":
+        assert (got["hrc_u.dat"] == ph["u_pixel"]).all() and (got["hrc_v.dat"] == ph["v_pixel"]).all()
+        assert (got["hrcregion.dat"] == ph["detector_region"]).all()
+        for k, f in enumerate(("ofine.dat", "ocoarse1.dat", "ocoarse2.dat", "ocoarse3.dat")):
+            assert (got[f] == ph["support_orders"][:, k]).all(), f
+    if "DitherModel=INTERNAL" in cfg["args"]:
+        assert (got["sky_ra.dat"] == ph["dither"][:, 0]).all() and (got["sky_dec.dat"] == ph["dither"][:, 1]).all()
+        assert (got["det_dy.dat"] == 0).all()
+    else:
+        assert "sky_ra.dat" not in got
+    # TIME is monotone over the batch boundaries and continues the running sum
+    t = got["time.dat"].astype(np.float64)
+    assert (np.diff(t) >= 0).all()
+    tot, det = re.findall(r"Total photons: (\d+), Total Photons detected: (\d+)", p.stdout)[-1]
+    assert int(tot) == n and int(det) == len(ph)
+
+
+@pytest.mark.gpu
+@needs_driver
+@pytest.mark.parametrize("config", ["c1_acis_s", "c2_hetg_acis_s", "c3_letg_hrc_s"])
+def test_bulk_writer_is_byte_identical_to_the_stock_writer(config, tmp_path):
+    args = COMMON + CONFIGS[config]["args"] + ["NumRays=120000", "dNumRays=50000", "RandomSeed=3"]
+    run_marx(MARX_GPU, tmp_path / "bulk", args)
+    run_marx(MARX_GPU, tmp_path / "stock", args, env_extra={"MARXB200_EGRESS": "stock"})
+    files = sorted(os.path.basename(f) for f in glob.glob(str(tmp_path / "stock" / "*.dat")))
+    assert len(files) >= 15 and files == sorted(os.path.basename(f) for f in glob.glob(str(tmp_path / "bulk" / "*.dat")))
+    match, mismatch, errors = filecmp.cmpfiles(str(tmp_path / "bulk"), str(tmp_path / "stock"), files, shallow=False)
+    assert not mismatch and not errors, (mismatch, errors)
+    assert os.path.getsize(tmp_path / "bulk" / "energy.dat") > 32 + 4 * 1000
+
+
+@pytest.mark.gpu
+@needs_driver
+def test_write_photons_abi_matches_download(tmp_path):
+    """the same writer through the C ABI alone (no driver): two batches appended, columns vs download()"""
+    mask = sum(HISTORY[k] for k in ("ENERGY", "TIME", "TAG", "DET_PIXEL", "DET_NUM", "PULSEHEIGHT", "PI", "ORDER", "MIRROR_SHELL"))
+    parts, total = [], 0.0
+    os.makedirs(tmp_path / "o")
+    with marx_b200.MarxB200("c2_hetg_acis_s", seed=2, max_photons=1 << 18) as m:
+        for b in range(2):
+            m.trace(b << 18, 1 << 18)
+            m.write_photons(tmp_path / "o", mask, b == 0, total)
+            parts.append((m.download().copy(), total))
+            total = m.counts()[2]           # the driver's accumulated total_time = running end of the arrival-time sum
+    got = read_dir(tmp_path / "o")
+    assert sorted(got) == ["b_energy.dat", "detector.dat", "energy.dat", "mirror.dat", "order.dat", "pha.dat", "tag.dat",
+                           "time.dat", "xpixel.dat", "ypixel.dat"]
+    ph = np.concatenate([p for p, _ in parts])
+    assert (got["tag.dat"].astype(np.uint32) == ph["tag"]).all()
+    assert (got["pha.dat"] == ph["pulse_height"]).all() and (got["xpixel.dat"] == ph["y_pixel"]).all()
+    t = np.concatenate([(p["arrival_time"] + t0).astype(np.float32) for p, t0 in parts])
+    assert (got["time.dat"] == t).all()
+
+
+@pytest.mark.gpu
+@needs_driver
+def test_marx_gpu_exposure_time_cut(tmp_path):
+    """ExposureTime > 0 (the marx.par default): the loop ends on the first ray at or beyond the exposure (source.c:323-334)"""
+    cfg = CONFIGS["c1_acis_s"]
+    common = [a for a in COMMON if not a.startswith("ExposureTime")]
+    expo, dn, seed = 20000.0, 40000, 4
+    p = run_marx(MARX_GPU, tmp_path / "out", common + cfg["args"] + ["ExposureTime=%g" % expo, "NumRays=100000000", "dNumRays=%d" % dn,
+                                                                      "RandomSeed=%d" % seed, "Verbose=1"])
+    total = int(re.findall(r"Total photons: (\d+)", p.stdout)[-1])
+    got = read_dir(tmp_path / "out")
+    # the same through the C ABI
+    collected, t_total = 0, 0.0
+    with marx_b200.MarxB200("c1_acis_s", seed=seed, max_photons=dn) as m:
+        while True:
+            left = expo - t_total
+            if left <= 0:
+                break
+            m.create_photons(collected, dn)
+            k = m.truncate_exposure(left)
+            _, _, t_end = m.counts()
+            collected += k
+            t_total = t_end
+            if k != dn:
+                break
+    assert total == collected and total % dn != 0
+    t = got["time.dat"]
+    assert t.max() <= expo * 1.001 and t.max() > 0.9 * expo
+    # statistical check against the stock CPU driver (own RNG): detected counts within 5 sigma
+    q = run_marx(os.path.join(REF, "marx"), tmp_path / "cpu", common + cfg["args"] + ["ExposureTime=%g" % expo, "NumRays=100000000",
+                                                                                      "dNumRays=%d" % dn, "RandomSeed=%d" % seed, "Verbose=1"])
+    n_cpu = len(read_dir(tmp_path / "cpu")["energy.dat"])
+    n_gpu = len(got["energy.dat"])
+    assert abs(n_cpu - n_gpu) < 5.0 * np.sqrt(n_cpu + n_gpu), (n_cpu, n_gpu)
