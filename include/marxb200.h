@@ -81,7 +81,7 @@ marxb200_photon_attr;
 typedef struct
 {
    int32_t source_type;            /* 0 POINT (s-point.c:59-83), 1 GAUSS (s-gauss.c:78-141), 2 BETA (s-beta.c:81-139),
-                                      3 DISK (s-disk.c:63-109) */
+                                      3 DISK (s-disk.c:63-109), 4 LINE (s-line.c:62-104), 5 IMAGE (s-image.c:287-362) */
    int32_t spectrum_type;          /* 1 = FLAT, 2 = FILE (MARX_*_SPECTRUM, marx.h) */
    double p[3];                    /* unit vector FROM source TO origin (Marx_Source_Type.p) */
    double p_normal[3];
@@ -93,7 +93,14 @@ typedef struct
    double total_flux;              /* photons/s/cm^2 */
    double geometric_area;          /* Marx_Mirror_Geometric_Area, cm^2 (hrma.c:736) */
    double shape[3];                /* GAUSS: sigma (rad); BETA: core radius (rad), 1/(1-alpha) with alpha = 3 beta - 1/2;
-                                      DISK: theta_max (rad), x0 = (theta_min/theta_max)^2, x1 = 1 - x0 */
+                                      DISK: theta_max (rad), x0 = (theta_min/theta_max)^2, x1 = 1 - x0;
+                                      LINE: S-LineTheta (rad), cos and sin of S-LinePhi */
+   /* LINE and IMAGE build the ray in a frame centred on (-1,0,0) and rotate it to p: axis and angle of that
+    * rotation (JDMv_find_rotation_axis, s-line.c:77; s-image.c:303-319) */
+   double rot_axis[3], rot_angle;
+   const float *image_cdf;         /* IMAGE: normalised cumulative image, f32, [image_ny][image_nx] (s-image.c:138-148) */
+   uint32_t image_nx, image_ny;
+   double rad_per_xpixel, rad_per_ypixel;
 }
 marxb200_source_desc;
 

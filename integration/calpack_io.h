@@ -18,7 +18,10 @@ static inline void cp_name (char *buf, const char *fmt, ...)
 
 int calpack_dump_source (mxcp_writer *w, void *marx_source);
 int calpack_dump_dither (mxcp_writer *w);
-int calpack_source_shape (void *marx_source, double *shape);
+int calpack_source_shape (void *marx_source, double *shape, double *rot, double *img);
+int calpack_is_line (void *st, double *shape, double *rot);
+int calpack_is_image (void *st, double *rot, double *img);
+int calpack_dump_image (mxcp_writer *w);
 int calpack_is_gauss (void *st, double *shape);
 int calpack_is_beta (void *st, double *shape);
 int calpack_is_disk (void *st, double *shape);

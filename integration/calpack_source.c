@@ -18,10 +18,10 @@ int calpack_dump_dither (mxcp_writer *w)
 int calpack_dump_source (mxcp_writer *w, void *marx_source)
 {
    Marx_Source_Type *st = (Marx_Source_Type *) marx_source;
-   double v[16];
+   double v[16], rot[4], img[4];
    int type;
    memset (v, 0, sizeof (v));
-   type = calpack_source_shape (st, v + 13);       /* 0 POINT, 1 GAUSS, 2 BETA, 3 DISK, -1 unsupported */
+   type = calpack_source_shape (st, v + 13, rot, img);       /* 0 POINT, 1 GAUSS, 2 BETA, 3 DISK, 4 LINE, 5 IMAGE, -1 unsupported */
    if (type < 0) return -1;
    v[0] = type;
    v[1] = st->spectrum.type;
@@ -34,6 +34,12 @@ int calpack_dump_source (mxcp_writer *w, void *marx_source)
    v[11] = st->spectrum.total_flux;
    v[12] = Marx_Mirror_Geometric_Area;
    CP_F64 (w, "source.params", v, 16);
+   if (type >= 4) CP_F64 (w, "source.rotation", rot, 4);      /* axis + angle taking (-1,0,0) to p */
+   if (type == 5)
+     {
+	CP_F64 (w, "source.image_params", img, 4);           /* nx, ny, rad per x pixel, rad per y pixel */
+	calpack_dump_image (w);
+     }
    if (st->spectrum.type == MARX_FILE_SPECTRUM)
      {
 	CP_F64 (w, "source.spec_energies", st->spectrum.s.file.energies, st->spectrum.s.file.num);

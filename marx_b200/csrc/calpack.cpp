@@ -5,6 +5,8 @@
 //   meta                      f64[8]  mirror, grating, detector module ids, tstart yrs, tstart secs, seed, numrays, exposure
 //   source.params             f64[16] source_type, spectrum_type, p[3], p_normal[3], distance, emin, emax, total_flux, geometric_area, shape[3]
 //   source.spec_energies/.spec_cum_flux  f64[n]   (FILE spectrum only)
+//   source.rotation           f64[4]  LINE / IMAGE: axis[3] + angle of the rotation taking (-1,0,0) to p
+//   source.image_params       f64[4]  IMAGE: nx, ny, rad per x pixel, rad per y pixel;  source.image_cdf f32[ny*nx]
 //   dither.params             f64[12] mode, amp ra/dec/roll, period ra/dec/roll, phase ra/dec/roll, nominal_roll, aspect_blur
 //   hrma.params               f64[7]  vig, cap_position, is_ideal, use_blur, use_wfold, use_struts, use_scale_factors
 //   hrma.opt_energies/.opt_betas/.opt_deltas  f32[n]
@@ -112,6 +114,21 @@ extern "C" int marxb200_load_calpack_impl (marxb200_ctx *ctx, const char *path, 
            GET (se, "source.spec_energies", MXCP_F64, 2);
            GET (sc, "source.spec_cum_flux", MXCP_F64, 2);
            d.spec_energies = (const double *) se->data; d.spec_cum_flux = (const double *) sc->data; d.spec_num = (uint32_t) se->count;
+        }
+      if (d.source_type >= 4)       // LINE, IMAGE: rotation taking (-1,0,0) to p
+        {
+           GET (r, "source.rotation", MXCP_F64, 4);
+           const double *rv = (const double *) r->data;
+           for (int i = 0; i < 3; i++) d.rot_axis[i] = rv[i];
+           d.rot_angle = rv[3];
+        }
+      if (d.source_type == 5)
+        {
+           GET (ip, "source.image_params", MXCP_F64, 4);
+           const double *iv = (const double *) ip->data;
+           d.image_nx = (uint32_t) iv[0]; d.image_ny = (uint32_t) iv[1]; d.rad_per_xpixel = iv[2]; d.rad_per_ypixel = iv[3];
+           GET (ic, "source.image_cdf", MXCP_F32, (uint64_t) d.image_nx * d.image_ny);
+           d.image_cdf = (const float *) ic->data;
         }
       if (-1 == marxb200_set_source (ctx, &d)) return bail (marxb200_last_error ());
    }

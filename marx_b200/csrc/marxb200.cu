@@ -269,7 +269,7 @@ extern "C" int marxb200_set_compaction (marxb200_ctx *c, int on)
 extern "C" int marxb200_set_source (marxb200_ctx *c, const marxb200_source_desc *d)
 {
    if ((c == nullptr) || (d == nullptr)) return fail ("marxb200_set_source: NULL argument");
-   if ((d->source_type < 0) || (d->source_type > 3)) return fail ("marxb200_set_source: source type %d is not implemented (POINT, GAUSS, BETA, DISK are)", d->source_type);
+   if ((d->source_type < 0) || (d->source_type > 5)) return fail ("marxb200_set_source: source type %d is not implemented (POINT, GAUSS, BETA, DISK, LINE, IMAGE are)", d->source_type);
    if ((d->spectrum_type != 1) && (d->spectrum_type != 2)) return fail ("marxb200_set_source: unknown spectrum type %d", d->spectrum_type);
    CUDA_OK (cudaSetDevice (c->device));
    SourceDev &S = c->S;
@@ -284,6 +284,16 @@ extern "C" int marxb200_set_source (marxb200_ctx *c, const marxb200_source_desc 
         if (-1 == dev_upload_t (c, d->spec_energies, d->spec_num, &S.spec_energies)) return -1;
         if (-1 == dev_upload_t (c, d->spec_cum_flux, d->spec_num, &S.spec_cum_flux)) return -1;
         S.spec_num = d->spec_num;
+     }
+   for (int i = 0; i < 3; i++) S.rot_axis[i] = d->rot_axis[i];
+   S.rot_angle = d->rot_angle;
+   if (d->source_type == 5)
+     {
+        const uint64_t npix = (uint64_t) d->image_nx * d->image_ny;
+        if ((npix == 0) || (npix > 0xFFFFFFFFull) || !d->image_cdf) return fail ("marxb200_set_source: IMAGE source needs a cumulative image");
+        if (-1 == dev_upload_t (c, d->image_cdf, (size_t) npix, &S.image_cdf)) return -1;
+        S.image_size = (uint32_t) npix; S.image_nx = d->image_nx; S.image_ny = d->image_ny;
+        S.rad_per_xpixel = d->rad_per_xpixel; S.rad_per_ypixel = d->rad_per_ypixel;
      }
    // compute_mean_time, source.c:260-264
    S.mean_time = (d->total_flux <= 0.0) ? 0.0 : 1.0 / d->total_flux / d->geometric_area;

@@ -25,6 +25,35 @@ MX_HD void source_draw (const SourceDev &s, Rng &rng, double &energy, Vec3 &p)
      }
    p = v_make (s.p[0], s.p[1], s.p[2]);
    if (s.source_type == 0) return;
+   if (s.source_type >= 4)
+     {
+        // LINE / IMAGE: build the ray about (-1,0,0), then rotate it onto the source direction
+        Vec3 q;
+        if (s.source_type == 4)   // s-line.c:86-98
+          {
+             double theta = s.shape[0] * (-1.0 + 2.0 * rng.uniform ());
+             double sn, cs;
+             sin_cos (theta, sn, cs);
+             double sin_theta = -sn;
+             q = v_make (-cs, sin_theta * s.shape[1], sin_theta * s.shape[2]);
+          }
+        else                      // s-image.c:330-356
+          {
+             uint32_t ofs = bsearch_f ((float) rng.uniform (), s.image_cdf, s.image_size);
+             double y = (double) (ofs / s.image_nx);
+             double x = (double) (ofs % s.image_nx);
+             y += -0.5 * s.image_ny + (rng.uniform () - 0.5);
+             x += -0.5 * s.image_nx + (rng.uniform () - 0.5);
+             y = y * s.rad_per_ypixel;
+             x = x * s.rad_per_xpixel;
+             double sy, cy, sx, cx;
+             sin_cos (y, sy, cy);
+             sin_cos (x, sx, cx);
+             q = v_make (-cy * cx, cy * sx, -sy);
+          }
+        p = v_rotate_unit (q, v_make (s.rot_axis[0], s.rot_axis[1], s.rot_axis[2]), s.rot_angle);
+        return;
+     }
    // GAUSS / BETA / DISK share one construction (s-gauss.c:96-137): rotate the normal to p about p by a
    // uniform angle, then rotate p about that normal by a source-specific polar angle.  The reference keeps
    // rotating ONE normal from photon to photon (statistically a fresh uniform azimuth every time); per-ray

@@ -22,6 +22,10 @@ struct SourceDev
    uint32_t spec_num;
    double mean_time;               // 1/flux/area, source.c:260-264
    double shape[3];                // extended-source parameters (marxb200_source_desc.shape)
+   double rot_axis[3], rot_angle;  // LINE / IMAGE: rotation taking (-1,0,0) to p
+   const float *image_cdf;         // IMAGE: cumulative image (HBM; 1 MB for 512^2, L2 resident)
+   uint32_t image_size, image_nx, image_ny;
+   double rad_per_xpixel, rad_per_ypixel;
 };
 
 struct DitherDev

@@ -76,6 +76,7 @@ struct oracle
    uint64_t seed;
    const double *src, *dith, *hrma, *grat, *acis;
    const double *spec_e, *spec_c; uint32_t nspec;
+   const double *src_rot, *img_prm; const float *img_cdf; uint32_t nimg;   /* LINE / IMAGE sources */
    const float *opt_e, *opt_b, *opt_d; uint32_t nopt;
    shell_t shell[NUM_SHELLS];
    gshell_t gshell[NUM_SHELLS];
@@ -157,6 +158,17 @@ oracle_t *oracle_open (const char *path, uint64_t seed)
      {
         o->spec_e = (const double *) need (o, "source.spec_energies", &c); o->nspec = (uint32_t) c;
         o->spec_c = (const double *) need (o, "source.spec_cum_flux", &c);
+     }
+   if ((int) o->src[0] >= 4)
+     {
+        o->src_rot = (const double *) need (o, "source.rotation", NULL);
+        if (!o->src_rot) { oracle_close (o); return NULL; }
+     }
+   if ((int) o->src[0] == 5)
+     {
+        o->img_prm = (const double *) need (o, "source.image_params", NULL);
+        o->img_cdf = (const float *) need (o, "source.image_cdf", &c); o->nimg = (uint32_t) c;
+        if (!o->img_prm || !o->img_cdf) { oracle_close (o); return NULL; }
      }
    o->opt_e = (const float *) need (o, "hrma.opt_energies", &c); o->nopt = (uint32_t) c;
    o->opt_b = (const float *) need (o, "hrma.opt_betas", &c);
@@ -404,7 +416,33 @@ static void stage_source (oracle_t *o, uint64_t first, uint64_t n, double *time_
         if ((int) s[1] == 2) at->energy = interp_d (rng_uniform (&r), o->spec_c, o->spec_e, o->nspec);   /* prob.c:55 */
         else { double emin = s[9], de = s[10] - emin; at->energy = emin + de * rng_uniform (&r); }       /* spectrum.c:140-145 */
         at->p[0] = s[2]; at->p[1] = s[3]; at->p[2] = s[4];                                               /* s-point.c:76 */
-        if ((int) s[0] != 0)
+        if ((int) s[0] >= 4)
+          {
+             /* LINE (s-line.c:86-98) / IMAGE (s-image.c:330-356): ray about (-1,0,0), rotated onto the source direction */
+             double q[3], axis[3];
+             if ((int) s[0] == 4)
+               {
+                  double theta = s[13] * (-1.0 + 2.0 * rng_uniform (&r));
+                  double sin_theta = -sin (theta);
+                  q[0] = -cos (theta); q[1] = sin_theta * s[14]; q[2] = sin_theta * s[15];
+               }
+             else
+               {
+                  unsigned int nx = (unsigned int) o->img_prm[0], ny = (unsigned int) o->img_prm[1];
+                  unsigned int ofs = bsearch_f ((float) rng_uniform (&r), o->img_cdf, o->nimg);
+                  double y = (double) (ofs / nx), x = (double) (ofs % nx), cos_y;
+                  y += -0.5 * ny + (rng_uniform (&r) - 0.5);
+                  x += -0.5 * nx + (rng_uniform (&r) - 0.5);
+                  y = y * o->img_prm[3];
+                  x = x * o->img_prm[2];
+                  cos_y = cos (y);
+                  q[0] = -cos_y * cos (x); q[1] = cos_y * sin (x); q[2] = -sin (y);
+               }
+             axis[0] = o->src_rot[0]; axis[1] = o->src_rot[1]; axis[2] = o->src_rot[2];
+             rot_unit (q, axis, o->src_rot[3]);
+             at->p[0] = q[0]; at->p[1] = q[1]; at->p[2] = q[2];
+          }
+        else if ((int) s[0] != 0)
           {
              /* GAUSS / BETA / DISK: s-gauss.c:96-137, s-beta.c:100-125, s-disk.c:86-106 (normal restarts from
               * st->p_normal for every ray, as the reference does at the start of every batch) */

@@ -19,6 +19,26 @@ REF = os.path.join(ROOT, "oracle", "_ref")
 sys.path.insert(0, ROOT)
 from tests.replay_io import read_replay  # noqa: E402
 
+IMAGE_FITS = "/tmp/marxb200_beta_image.fits"
+
+
+def write_beta_image_fits(path=IMAGE_FITS, n=256, cdelt_arcsec=0.5, core_arcsec=10.0, beta=0.7):
+    """synthetic IMAGE source: an n x n float32 beta-model surface-brightness map as a primary
+    FITS HDU with CDELT1/2, the keywords s-image.c:200-262 reads."""
+    yy, xx = np.mgrid[0:n, 0:n]
+    r2 = ((xx - n / 2) ** 2 + (yy - n / 2) ** 2) * cdelt_arcsec ** 2
+    img = (1.0 + r2 / core_arcsec ** 2) ** (-3.0 * beta + 0.5)
+    cards = [("SIMPLE", "T"), ("BITPIX", "-32"), ("NAXIS", "2"), ("NAXIS1", str(n)), ("NAXIS2", str(n)),
+             ("CDELT1", "%.12E" % (-cdelt_arcsec / 3600.0)), ("CDELT2", "%.12E" % (cdelt_arcsec / 3600.0))]
+    hdr = "".join(("%-8s= %20s" % kv).ljust(80) for kv in cards) + "END".ljust(80)
+    hdr = hdr.ljust((len(hdr) + 2879) // 2880 * 2880)
+    data = img.astype(">f4").tobytes()
+    data += b"\0" * (-len(data) % 2880)
+    with open(path, "wb") as f:
+        f.write(hdr.encode("ascii") + data)
+    return path
+
+
 COMMON = ["ExposureTime=0", "Verbose=0", "SourceFlux=0.003", "TStart=2023.5", "SpectrumType=FLAT"]
 CONFIGS = {
     # BASELINE.json configs[0]
@@ -34,13 +54,24 @@ CONFIGS = {
     "c4_beta_acis_i": dict(args=["SourceType=BETA", "S-BetaCoreRadius=10", "S-BetaBeta=0.7", "SourceDEC=-53.92410480125",
                                  "MinEnergy=0.5", "MaxEnergy=7.0", "GratingType=NONE", "DetectorType=ACIS-I",
                                  "DitherModel=INTERNAL"], nrays=16384, seed=13),
+    # the IMAGE flavour of configs[3]: synthetic 256^2 beta-model FITS image (0.5 arcsec pixels), same pointing offset
+    "c4_image_acis_i": dict(args=["SourceType=IMAGE", "S-ImageFile=" + IMAGE_FITS, "SourceDEC=-53.92410480125",
+                                  "MinEnergy=0.5", "MaxEnergy=7.0", "GratingType=NONE", "DetectorType=ACIS-I",
+                                  "DitherModel=INTERNAL"], nrays=16384, seed=14),
+    # LINE source (s-line.c), no grating, ACIS-S, no dither
+    "c1_line_acis_s": dict(args=["SourceType=LINE", "S-LinePhi=30", "S-LineTheta=60", "MinEnergy=1.0", "MaxEnergy=2.0",
+                                 "GratingType=NONE", "DetectorType=ACIS-S", "DitherModel=NONE"], nrays=8192, seed=15),
 }
 
 
 def main():
     par = "@@" + os.path.join(REF, "par", "marx.par")
     env = dict(os.environ, MARX_DATA_DIR=os.path.join(REF, "data"))
+    write_beta_image_fits()
+    only = sys.argv[1:]
     for name, cfg in CONFIGS.items():
+        if only and name not in only:
+            continue
         pack = os.path.join(ROOT, "marx_b200", "caldata", name + ".calpack")
         subprocess.check_call([os.path.join(REF, "calpack_dump"), pack, par] + COMMON + cfg["args"], env=env)
         tmp = os.path.join("/tmp", name + "_replay.bin")

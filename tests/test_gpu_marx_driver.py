@@ -18,7 +18,7 @@ import pytest
 
 import marx_b200
 from marx_b200 import HISTORY, read_marx_column
-from tests.golden.make_golden import COMMON, CONFIGS
+from tests.golden.make_golden import COMMON, CONFIGS, write_beta_image_fits
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MARX_GPU = os.path.join(ROOT, "integration", "_build", "marx_gpu")
@@ -58,9 +58,11 @@ def test_marx_gpu_fails_loudly_without_a_gpu(tmp_path):
 
 @pytest.mark.gpu
 @needs_driver
-@pytest.mark.parametrize("config", ["c1_acis_s", "c2_hetg_acis_s", "c3_letg_hrc_s", "c4_beta_acis_i"])
+@pytest.mark.parametrize("config", ["c1_acis_s", "c2_hetg_acis_s", "c3_letg_hrc_s", "c4_beta_acis_i", "c4_image_acis_i", "c1_line_acis_s"])
 def test_marx_gpu_output_equals_c_abi(config, tmp_path):
     cfg = CONFIGS[config]
+    if config == "c4_image_acis_i":
+        write_beta_image_fits()           # the synthetic S-ImageFile the calibration pack was made from
     # the reference's loop always collects whole batches (marx.c:545-608): NumRays=250000 -> 3 x 100000 rays
     n_par, dn, seed = 250000, 100000, 5
     n = 3 * dn

@@ -28,6 +28,8 @@ def _gpu_all_stages(config, seed, first, n, compact):
     ("c1_acis_s", 99, 7 * 65536, 1 << 19),
     ("c3_letg_hrc_s", 5, 0, 1 << 20),
     ("c4_beta_acis_i", 6, 65536, 1 << 19),
+    ("c4_image_acis_i", 8, 0, 1 << 19),
+    ("c1_line_acis_s", 9, 4096, 1 << 18),
 ])
 def test_cuda_matches_oracle_slot_by_slot(config, seed, first, n):
     from tests.oracle_lib import Oracle
