@@ -28,6 +28,7 @@ int calpack_is_disk (void *st, double *shape);
 int calpack_is_point (void *st);
 int calpack_dump_acis_i (mxcp_writer *w, int detector_module);
 int calpack_dump_hrc_s (mxcp_writer *w, int detector_module);
+int calpack_dump_hrc_i (mxcp_writer *w, int detector_module);
 int calpack_dump_hrma (mxcp_writer *w);
 int calpack_dump_wfold (mxcp_writer *w, const char *prefix, void *table);
 int calpack_dump_grating (mxcp_writer *w, int grating_module);

@@ -83,8 +83,8 @@ static int gpu_init (Marx_Source_Type *st, Marx_Photon_Type *pt)
    if ((Grating_Id != 0) && (Grating_Id != MARX_GRATING_HETG) && (Grating_Id != MARX_GRATING_LETG))
      { marx_error ("marxb200: GratingType must be NONE, HETG or LETG for the GPU path"); return -1; }
    if ((Detector_Id != 0) && (Detector_Id != MARX_DETECTOR_ACIS_S) && (Detector_Id != MARX_DETECTOR_ACIS_I)
-       && (Detector_Id != MARX_DETECTOR_HRC_S))
-     { marx_error ("marxb200: DetectorType must be NONE, ACIS-S, ACIS-I or HRC-S for the GPU path"); return -1; }
+       && (Detector_Id != MARX_DETECTOR_HRC_S) && (Detector_Id != MARX_DETECTOR_HRC_I))
+     { marx_error ("marxb200: DetectorType must be NONE, ACIS-S, ACIS-I, HRC-S or HRC-I for the GPU path"); return -1; }
 
    if (-1 == marxb200_create (&Ctx, dev ? atoi (dev) : 0, (uint64_t) Seed))
      return gpu_error ("marxb200_create");
@@ -103,6 +103,7 @@ static int gpu_init (Marx_Source_Type *st, Marx_Photon_Type *pt)
 	    || (-1 == calpack_dump_hrma (&w))
 	    || (-1 == calpack_dump_grating (&w, Grating_Id))
 	    || (-1 == ((Detector_Id == MARX_DETECTOR_HRC_S) ? calpack_dump_hrc_s (&w, Detector_Id)
+		       : (Detector_Id == MARX_DETECTOR_HRC_I) ? calpack_dump_hrc_i (&w, Detector_Id)
 		       : calpack_dump_acis_s (&w, Detector_Id))))
      marx_error ("marxb200: could not serialise the module tables");
    else status = 0;
@@ -208,6 +209,8 @@ int __wrap_marx_detect (Marx_Photon_Type *pt, int verbose)
      {
 	if (Detector_Id == MARX_DETECTOR_HRC_S)
 	  pt->history |= (MARX_DET_REGION_OK | MARX_PULSEHEIGHT_OK | MARX_DET_PIXEL_OK | MARX_DET_NUM_OK | MARX_DET_UV_PIXEL_OK);
+	else if (Detector_Id == MARX_DETECTOR_HRC_I)          /* hrc-i.c:125-129 */
+	  pt->history |= (MARX_DET_REGION_OK | MARX_PULSEHEIGHT_OK | MARX_DET_PIXEL_OK | MARX_DET_NUM_OK);
 	else
 	  pt->history |= (MARX_DET_PIXEL_OK | MARX_DET_NUM_OK | MARX_PULSEHEIGHT_OK | MARX_PI_OK);
 	if (verbose > 0) marx_message ("Detecting [B200]\n");

@@ -154,20 +154,43 @@ MX_HD uint32_t hrc_s_detect (const HrcDev &D, double energy, Vec3 &x, Vec3 &p, i
         double qe = interp_f (ef, d.qe_energies, d.qe, d.qe_num);
         if (rng.uniform () >= qe) { ccd = -1; return flags | UNDETECTED; }
      }
-   {
-      double t = (D.shield_x - x.x) / p.x;
-      double y = x.y + t * p.y, z = x.z + t * p.z;
-      region = hrc_filter_region (D, y, z);
-      if (region < 0) { ccd = -1; return flags | UNDETECTED; }
-      if (D.filter_num[region] != 0)
-        {
-           double qe = interp_f (ef, D.filter_energies[region], D.filter_qe[region], D.filter_num[region]);
-           if (rng.uniform () >= qe) { ccd = -1; return flags | UNDETECTED; }
-        }
-   }
+   const bool hrc_i = (D.detector_type == 2);      // MARX_DETECTOR_HRC_I: one MCP, one UVIS filter, no shield regions
+   if (hrc_i)
+     {
+        // apply_hrc_qe, hrc-i.c:88-117: Filter_QEs[mcp_id] with mcp_id == 0
+        region = 0;
+        if (D.filter_num[0] != 0)
+          {
+             double qe = interp_f (ef, D.filter_energies[0], D.filter_qe[0], D.filter_num[0]);
+             if (rng.uniform () >= qe) { ccd = -1; return flags | UNDETECTED; }
+          }
+     }
+   else
+     {
+        double t = (D.shield_x - x.x) / p.x;
+        double y = x.y + t * p.y, z = x.z + t * p.z;
+        region = hrc_filter_region (D, y, z);
+        if (region < 0) { ccd = -1; return flags | UNDETECTED; }
+        if (D.filter_num[region] != 0)
+          {
+             double qe = interp_f (ef, D.filter_energies[region], D.filter_qe[region], D.filter_num[region]);
+             if (rng.uniform () >= qe) { ccd = -1; return flags | UNDETECTED; }
+          }
+     }
    pha = hrc_pha (energy, rng);
    hrc_blur (D, dx, dy, rng);
    ccd = d.id;
+   if (hrc_i)
+     {
+        // _marx_hrc_i_compute_pixel, hrc_i_geom.c:146-156: LL_CXCY + d / pixel size (u_start, v_start hold LL_CXCY)
+        ypix = (float) (d.u_start + dx / D.u_pixel_size);
+        zpix = (float) (d.v_start + dy / D.v_pixel_size);
+        upix = 0.f; vpix = 0.f;
+        p = m3_mul_t (D.det_matrix, p);
+        x = m3_mul_t (D.det_matrix, x);
+        x.x += D.det_offset[0]; x.y += D.det_offset[1]; x.z += D.det_offset[2];
+        return flags;
+     }
    // _marx_hrc_s_compute_pixel, hrc_s_geom.c:344-394
    double u = d.u_start + dx / D.u_pixel_size;
    double v = d.v_start + dy / D.v_pixel_size;

@@ -915,11 +915,12 @@ static int plane_hit (const double *g, const double *x0, const double *p, double
    *dx = rx; *dy = ry;
    return 1;
 }
-/* stage 3 (HRC-S): _marx_drake_reflect (drake.c:317-372) + _marx_hrc_s_detect (hrc-s.c:236-312) */
+/* stage 3 (HRC-S / HRC-I): _marx_drake_reflect (drake.c:317-372) + _marx_hrc_s_detect (hrc-s.c:236-312) / _marx_hrc_i_detect (hrc-i.c:119-186) */
 static void stage_detect_hrc (oracle_t *o, uint64_t n, oracle_photon *ph)
 {
    const double *H = o->hrc; const double *off = H + 2, *M = H + 5, *S = H + 16, *B = H + 26;
    int ideal = (int) H[14], extend = (int) H[15], use_hesf = (int) H[41], nplates = (int) H[42];
+   int hrc_i = ((int) H[0] == 2);                                       /* MARX_DETECTOR_HRC_I (hrc-i.c:119-186) */
    double upix = H[39], vpix = H[40], crw = H[43];
    uint64_t i;
    for (i = 0; i < n; i++)
@@ -961,6 +962,9 @@ static void stage_detect_hrc (oracle_t *o, uint64_t n, oracle_photon *ph)
         at->x[0] = xh[0]; at->x[1] = xh[1]; at->x[2] = xh[2];
         /* apply_hrc_qe, hrc-s.c:192-234 */
         if (m->nqe && (rng_uniform (&r) >= interp_f ((float) at->energy, m->qe_e, m->qe, m->nqe))) { at->flags |= F_UNDETECTED; at->ccd_num = -1; continue; }
+        if (hrc_i) region = 0;                                                                           /* hrc-i.c:88-117: one UVIS filter */
+        else
+        {
         t = (S[3] - at->x[0]) / at->p[0]; y = at->x[1] + t * at->p[1]; z = at->x[2] + t * at->p[2];
         y -= S[8]; z -= S[9];                                                                            /* get_filter_region :136-188 */
         {
@@ -970,6 +974,7 @@ static void stage_detect_hrc (oracle_t *o, uint64_t n, oracle_photon *ph)
            else if (y < sl) region = (z >= S[0]) ? 0 : 1;
            else if (y >= slg) region = (z >= S[0]) ? 2 : 3;
            else region = -1;
+        }
         }
         if (region < 0) { at->flags |= F_UNDETECTED; at->ccd_num = -1; continue; }
         if (o->nfilt[region] && (rng_uniform (&r) >= interp_f ((float) at->energy, o->filt_e[region], o->filt_q[region], o->nfilt[region])))
@@ -993,9 +998,14 @@ static void stage_detect_hrc (oracle_t *o, uint64_t n, oracle_photon *ph)
              if (!extend) { if (dx < 0.0) dx = 0.0; if (dy < 0.0) dy = 0.0; }
           }
         at->ccd_num = (int8_t) g[0];
+        if (hrc_i)                                                                                       /* hrc_i_geom.c:146-156 */
+          { double px = dx / upix, py = dy / vpix; at->y_pixel = g[15] + px; at->z_pixel = g[16] + py; }
+        else
+          {
         u = g[15] + dx / upix; v = g[16] + dy / vpix;                                                    /* hrc_s_geom.c:344-394 */
         at->u_pixel = u; at->v_pixel = v;
         at->y_pixel = g[19] + (u - g[17]); at->z_pixel = g[20] + (v - g[18]);
+          }
         mat3t (M, at->p); mat3t (M, at->x);
         at->x[0] += off[0]; at->x[1] += off[1]; at->x[2] += off[2];
      }

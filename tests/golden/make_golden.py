@@ -58,6 +58,9 @@ CONFIGS = {
     "c4_image_acis_i": dict(args=["SourceType=IMAGE", "S-ImageFile=" + IMAGE_FITS, "SourceDEC=-53.92410480125",
                                   "MinEnergy=0.5", "MaxEnergy=7.0", "GratingType=NONE", "DetectorType=ACIS-I",
                                   "DitherModel=INTERNAL"], nrays=16384, seed=14),
+    # HRC-I (hrc-i.c), no grating
+    "c3_hrc_i": dict(args=["SourceType=POINT", "MinEnergy=0.1", "MaxEnergy=2.0", "GratingType=NONE", "DetectorType=HRC-I",
+                           "DitherModel=INTERNAL"], nrays=8192, seed=16),
     # LINE source (s-line.c), no grating, ACIS-S, no dither
     "c1_line_acis_s": dict(args=["SourceType=LINE", "S-LinePhi=30", "S-LineTheta=60", "MinEnergy=1.0", "MaxEnergy=2.0",
                                  "GratingType=NONE", "DetectorType=ACIS-S", "DitherModel=NONE"], nrays=8192, seed=15),

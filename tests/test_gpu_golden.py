@@ -15,7 +15,7 @@ def _load(name):
     return int(z["seed"]), int(z["first_ray"]), z["stages"], z["start_time"]
 
 
-@pytest.mark.parametrize("config", ["c1_acis_s", "c2_hetg_acis_s", "c3_letg_hrc_s", "c4_beta_acis_i", "c4_image_acis_i", "c1_line_acis_s"])
+@pytest.mark.parametrize("config", ["c1_acis_s", "c2_hetg_acis_s", "c3_letg_hrc_s", "c4_beta_acis_i", "c4_image_acis_i", "c1_line_acis_s", "c3_hrc_i"])
 def test_replay_parity_in_place(config):
     """compaction off: every ray keeps its slot, so each stage is compared ray by ray, dead rays included."""
     import marx_b200
@@ -40,7 +40,7 @@ def test_replay_parity_in_place(config):
             assert_stage_ok(f, stage)
 
 
-@pytest.mark.parametrize("config", ["c1_acis_s", "c2_hetg_acis_s", "c3_letg_hrc_s", "c4_beta_acis_i", "c4_image_acis_i", "c1_line_acis_s"])
+@pytest.mark.parametrize("config", ["c1_acis_s", "c2_hetg_acis_s", "c3_letg_hrc_s", "c4_beta_acis_i", "c4_image_acis_i", "c1_line_acis_s", "c3_hrc_i"])
 def test_replay_parity_compacted(config):
     """the product path: fused compaction; survivors must be the reference's survivors in arrival order."""
     import marx_b200

@@ -58,7 +58,7 @@ def test_marx_gpu_fails_loudly_without_a_gpu(tmp_path):
 
 @pytest.mark.gpu
 @needs_driver
-@pytest.mark.parametrize("config", ["c1_acis_s", "c2_hetg_acis_s", "c3_letg_hrc_s", "c4_beta_acis_i", "c4_image_acis_i", "c1_line_acis_s"])
+@pytest.mark.parametrize("config", ["c1_acis_s", "c2_hetg_acis_s", "c3_letg_hrc_s", "c4_beta_acis_i", "c4_image_acis_i", "c1_line_acis_s", "c3_hrc_i"])
 def test_marx_gpu_output_equals_c_abi(config, tmp_path):
     cfg = CONFIGS[config]
     if config == "c4_image_acis_i":

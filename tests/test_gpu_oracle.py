@@ -30,6 +30,7 @@ def _gpu_all_stages(config, seed, first, n, compact):
     ("c4_beta_acis_i", 6, 65536, 1 << 19),
     ("c4_image_acis_i", 8, 0, 1 << 19),
     ("c1_line_acis_s", 9, 4096, 1 << 18),
+    ("c3_hrc_i", 10, 0, 1 << 19),
 ])
 def test_cuda_matches_oracle_slot_by_slot(config, seed, first, n):
     from tests.oracle_lib import Oracle

@@ -44,7 +44,7 @@ def check_bit_exact(mine, ref_stages, start_times):
     assert n == len(ref_stages)
 
 
-@pytest.mark.parametrize("config", ["c1_acis_s", "c2_hetg_acis_s", "c3_letg_hrc_s", "c4_beta_acis_i", "c4_image_acis_i", "c1_line_acis_s"])
+@pytest.mark.parametrize("config", ["c1_acis_s", "c2_hetg_acis_s", "c3_letg_hrc_s", "c4_beta_acis_i", "c4_image_acis_i", "c1_line_acis_s", "c3_hrc_i"])
 def test_oracle_matches_committed_reference_replay(config):
     z = np.load(os.path.join(GOLDEN, config + "_replay.npz"))
     o = Oracle(config, int(z["seed"]))
