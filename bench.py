@@ -323,7 +323,7 @@ def cuda_arm(args):
         except Exception:  # noqa: BLE001
             fp64_peak, fp64_src = 37.0, "datasheet (measurement failed)"
     names = ["K0 time pre-pass (k0_time_sums+k0_time_scan)", "K0+K1a fused (k01_source_hrma)", "K1b (k1_hrma<1>)", "K1c (k1_hrma<2>)",
-             "K2 (k2_grating)", "K3 (k3_acis)", "order restore (4 kernels)"]
+             "K2 (k2_grating)", "K3 (k3_acis)", "order restore (5 kernels)"]
     kernels = {}
     for k, name in enumerate(names):
         kernels[name] = {"ms": stage_ms[k], "share": stage_ms[k] / sum(stage_ms)}

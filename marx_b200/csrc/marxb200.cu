@@ -54,7 +54,7 @@ struct marxb200_ctx
    // device scalars: counts[0..3] + ticket + total_time
    unsigned long long *d_counts = nullptr;      // [8]: generated, after mirror, after grating, detected, after k1a, after k1b
    unsigned long long *d_ticket = nullptr;      // [4]: one ticket counter per kernel of a stage call
-   uint32_t *d_bitmap = nullptr, *d_word_prefix = nullptr, *d_block_prefix = nullptr;   // order restoration scratch
+   uint32_t *d_bitmap = nullptr, *d_word_prefix = nullptr, *d_block_prefix = nullptr, *d_perm = nullptr;   // order restoration scratch
    uint64_t n_words = 0;
    bool ordered = true;                          // live list is in arrival order
    double *d_tile_sums = nullptr, *d_tile_base = nullptr, *d_super_sums = nullptr, *d_times = nullptr;   // d_times: [batch start, running end]
@@ -222,6 +222,7 @@ extern "C" int marxb200_destroy (marxb200_ctx *c)
    if (c->d_bitmap) cudaFree (c->d_bitmap);
    if (c->d_word_prefix) cudaFree (c->d_word_prefix);
    if (c->d_block_prefix) cudaFree (c->d_block_prefix);
+   if (c->d_perm) cudaFree (c->d_perm);
    if (c->d_tile_sums) cudaFree (c->d_tile_sums);
    if (c->d_tile_base) cudaFree (c->d_tile_base);
    if (c->d_super_sums) cudaFree (c->d_super_sums);
@@ -432,6 +433,7 @@ extern "C" int marxb200_alloc_photons (marxb200_ctx *c, uint64_t max_photons)
    if (c->d_bitmap) cudaFree (c->d_bitmap);
    if (c->d_word_prefix) cudaFree (c->d_word_prefix);
    if (c->d_block_prefix) cudaFree (c->d_block_prefix);
+   if (c->d_perm) cudaFree (c->d_perm);
    if (c->d_tile_sums) cudaFree (c->d_tile_sums);
    if (c->d_tile_base) cudaFree (c->d_tile_base);
    if (c->d_super_sums) cudaFree (c->d_super_sums);
@@ -449,6 +451,7 @@ extern "C" int marxb200_alloc_photons (marxb200_ctx *c, uint64_t max_photons)
    CUDA_OK (cudaMalloc (&c->d_bitmap, c->n_words * sizeof (uint32_t)));
    CUDA_OK (cudaMalloc (&c->d_word_prefix, c->n_words * sizeof (uint32_t)));
    CUDA_OK (cudaMalloc (&c->d_block_prefix, (c->n_words / 1024 + 2) * sizeof (uint32_t)));
+   CUDA_OK (cudaMalloc (&c->d_perm, (max_photons + 1) * sizeof (uint32_t)));
    CUDA_OK (cudaMalloc (&c->d_tile_sums, n_tiles * sizeof (double)));
    CUDA_OK (cudaMalloc (&c->d_tile_base, n_tiles * sizeof (double)));
    CUDA_OK (cudaMalloc (&c->d_super_sums, n_super * sizeof (double)));
@@ -592,7 +595,7 @@ static int ensure_order (marxb200_ctx *c)
    o.in = c->buf[c->cur]; o.out = c->buf[1 - c->cur];
    o.n_live = c->d_counts + c->stage_done;
    o.n_slots = c->n_generated;
-   o.bitmap = c->d_bitmap; o.word_prefix = c->d_word_prefix; o.block_prefix = c->d_block_prefix;
+   o.bitmap = c->d_bitmap; o.word_prefix = c->d_word_prefix; o.block_prefix = c->d_block_prefix; o.perm = c->d_perm;
    CUDA_OK (cudaMemsetAsync (c->d_bitmap, 0, (c->n_generated / 32 + 1) * sizeof (uint32_t), c->stream));
    int nl = 0;
    prof_begin (c);

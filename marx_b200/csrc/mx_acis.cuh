@@ -82,7 +82,6 @@ MX_HD double acis_contamination (const AcisChipDev &c, double en, double cx, dou
    return exp (-v);
 }
 
-struct GaussParm { float amp, center, sigma, cum_area; int use_tail_dist; };   // acis_fef.c:87-96
 
 // fmod(t, T) for t >= 0, T > 0 -- EXACT, like the libm routine, without its bit-serial long division:
 // with q = floor(t/T) (possibly off by one) the remainder t - q*T is a multiple of ulp(T) smaller than 2T in
@@ -98,40 +97,69 @@ MX_HD double fmod_pos (double t, double T)
    return r;
 }
 
+// One FEF row pair bracketing the photon energy: the gaussians of the event are linear interpolations between the two
+// rows (acis_fef.c:1011-1032).  The reference materialises them in an array; here gaussian k is re-interpolated (same
+// operations, same float roundings) wherever it is needed, so that no per-thread array -- local memory on the device,
+// 320 B per ray that ncu showed spilling to DRAM -- is required.  Only the cumulative areas are kept: kMaxGauss floats
+// per thread in SHARED memory (`cum`, element k at cum[k * stride]) plus a bit mask for use_tail_dist.
+struct FefRows { const float *g0, *g1; double t; uint32_t ng; };
+struct GaussParm { float amp, center, sigma; };   // acis_fef.c:87-96 (cum_area, use_tail_dist live in cum[] / tail_mask)
+
+MX_HD GaussParm fef_gauss (const FefRows &R, uint32_t k)
+{
+   GaussParm G;
+   const double t = R.t;
+   float a0 = R.g0[3 * k], c0 = R.g0[3 * k + 1], s0 = R.g0[3 * k + 2];
+   float a1 = R.g1[3 * k], c1 = R.g1[3 * k + 1], s1 = R.g1[3 * k + 2];
+   G.center = (float) (c0 + t * (c1 - c0));
+   double v = s0 + t * (s1 - s0);
+   if (v <= 0.0) { G.sigma = 0.0f; G.amp = 0.0f; }
+   else
+     {
+        G.sigma = (float) v;
+        v = a0 + t * (a1 - a0);
+        if ((v < 0.0) && ((a1 > 0.0f) || (a0 > 0.0f))) v = 0.0;
+        G.amp = (float) v;
+     }
+   return G;
+}
+
 // normalize_gaussians, acis_fef.c:509-579.  gaussian_integral(0,+inf) and (-inf,0) share one erf:
 // erf((+-1e37 - x0)/sigma) is exactly +-1 for every representable table value.
-MX_HD int fef_normalize (GaussParm *g, uint32_t num)
+MX_HD int fef_normalize (const FefRows &R, float *cum, uint32_t stride, uint32_t &tail_mask)
 {
    const double SQRT_2 = 1.4142135623730951, SQRT_2PI = 2.5066282746310002;
+   const uint32_t num = R.ng;
    double total_pos_area = 0.0, total_neg_area = 0.0;
    int flags = 0;
+   tail_mask = 0;
    for (uint32_t k = 0; k < num; k++)
      {
+        const GaussParm g = fef_gauss (R, k);
         double area1 = 0.0, area2 = 0.0;
-        double sigma = g[k].sigma * SQRT_2;
+        double sigma = g.sigma * SQRT_2;
         // amp == 0 makes both areas exactly zero whatever erf returns: skip the erf (identical results)
-        if ((sigma != 0.0) && (g[k].amp != 0.0f))
+        if ((sigma != 0.0) && (g.amp != 0.0f))
           {
-             double x0 = g[k].center;
+             double x0 = g.center;
              double e0 = erf ((0 - x0) / sigma);
-             area1 = 0.5 * g[k].amp * (1.0 - e0) * (SQRT_2PI * g[k].sigma);
-             area2 = 0.5 * g[k].amp * (e0 - (-1.0)) * (SQRT_2PI * g[k].sigma);
+             area1 = 0.5 * g.amp * (1.0 - e0) * (SQRT_2PI * g.sigma);
+             area2 = 0.5 * g.amp * (e0 - (-1.0)) * (SQRT_2PI * g.sigma);
           }
-        g[k].use_tail_dist = 0;
         if (area2 > area1)
           {
              double ratio = area1 / area2;
-             if (ratio < 0.1) g[k].use_tail_dist = 1;
+             if (ratio < 0.1) tail_mask |= (1u << k);
           }
         if (area1 >= 0) total_pos_area += area1;
         else total_neg_area -= area1;
-        g[k].cum_area = (float) total_pos_area;
+        cum[k * stride] = (float) total_pos_area;
      }
    if (total_pos_area <= total_neg_area) flags |= 4;      // HAS_TOTAL_NEG_AREA
    if (total_neg_area != 0.0) flags |= 1;                 // HAS_NEG_AMP_GAUSSIANS
    if (total_pos_area > 0)
      for (uint32_t k = 0; k < num; k++)
-       g[k].cum_area = (float) (g[k].cum_area / total_pos_area);
+       cum[k * stride] = (float) (cum[k * stride] / total_pos_area);
    return flags;
 }
 
@@ -139,17 +167,19 @@ MX_HD int fef_normalize (GaussParm *g, uint32_t num)
 // component search is separated from the sampling so that the lanes of a warp reconverge before the
 // expensive part (in the reference's loop shape every lane would sample inside a different iteration).
 // The reference loops until a value is found; the cap only bounds pathological tables.
-MX_HD int fef_pha_pos (const GaussParm *g, uint32_t num, double &phap, Rng &rng)
+MX_HD int fef_pha_pos (const FefRows &R, const float *cum, uint32_t stride, uint32_t tail_mask, double &phap, Rng &rng)
 {
+   const uint32_t num = R.ng;
    for (int guard = 0; guard < 4096; guard++)
      {
         double r = rng.uniform ();
         uint32_t k = 0;
-        while ((k < num) && (g[k].cum_area <= r)) k++;
+        while ((k < num) && (cum[k * stride] <= r)) k++;
         if (k == num) continue;                  // r above every cumulative area: draw again (acis_fef.c:411-424)
-        const float center = g[k].center, sigma = g[k].sigma;
+        const GaussParm g = fef_gauss (R, k);
+        const float center = g.center, sigma = g.sigma;
         double pha;
-        if (g[k].use_tail_dist == 0)
+        if (0 == ((tail_mask >> k) & 1u))
           {
              unsigned int count = 0;
              do
@@ -181,21 +211,22 @@ MX_HD int fef_pha_pos (const GaussParm *g, uint32_t num, double &phap, Rng &rng)
 }
 
 // compute_pha_with_neg_amps, acis_fef.c:471-503
-MX_HD int fef_pha_neg (const GaussParm *g, uint32_t num, double &phap, Rng &rng)
+MX_HD int fef_pha_neg (const FefRows &R, const float *cum, uint32_t stride, uint32_t tail_mask, double &phap, Rng &rng)
 {
    int count = 0;
    while (count < 100)
      {
         double pha;
-        if (-1 == fef_pha_pos (g, num, pha, rng)) return -1;
+        if (-1 == fef_pha_pos (R, cum, stride, tail_mask, pha, rng)) return -1;
         double pos_sum = 0.0, sum = 0.0;
-        for (uint32_t k = 0; k < num; k++)
+        for (uint32_t k = 0; k < R.ng; k++)
           {
-             double sigma = g[k].sigma, dsum = 0.0;
+             const GaussParm g = fef_gauss (R, k);
+             double sigma = g.sigma, dsum = 0.0;
              if (sigma != 0.0)
                {
-                  double xx = (pha - g[k].center) / sigma;
-                  dsum = g[k].amp * exp (-0.5 * xx * xx);
+                  double xx = (pha - g.center) / sigma;
+                  dsum = g.amp * exp (-0.5 * xx * xx);
                }
              sum += dsum;
              if (dsum > 0) pos_sum += dsum;
@@ -207,8 +238,9 @@ MX_HD int fef_pha_neg (const GaussParm *g, uint32_t num, double &phap, Rng &rng)
 }
 
 // marx_apply_acis_rmf, acis_fef.c:967-1079 (+ find_fef :910-965).  x, y are the float chip pixels.
+// cum: kMaxGauss floats of scratch for this ray, element k at cum[k * stride] (shared memory on the device).
 MX_HD int acis_apply_fef (const AcisDev &A, const AcisChipDev &chip, float x, float y, double energy,
-                          float &pi, int16_t &pha_out, Rng &rng)
+                          float &pi, int16_t &pha_out, Rng &rng, float *cum, uint32_t stride)
 {
    if ((x < 0) || (x >= 1024) || (y < 0) || (y >= 1024)) return -1;    // DetExtendFlag=no
    uint32_t i = (uint32_t) (x / 32), j = (uint32_t) (y / 32);
@@ -222,29 +254,16 @@ MX_HD int acis_apply_fef (const AcisDev &A, const AcisChipDev &chip, float x, fl
    i = bsearch_f ((float) energy, f.energies, ne);
    if (i == 0) i++;
    if (i == ne) i--;
-   double t = (energy - f.energies[i - 1]) / (f.energies[i] - f.energies[i - 1]);
-   const float *g0 = f.gauss + (size_t) (i - 1) * ng * 3;
-   const float *g1 = g0 + (size_t) ng * 3;
-   GaussParm G[kMaxGauss];
-   for (uint32_t k = 0; k < ng; k++)
-     {
-        float a0 = g0[3 * k], c0 = g0[3 * k + 1], s0 = g0[3 * k + 2];
-        float a1 = g1[3 * k], c1 = g1[3 * k + 1], s1 = g1[3 * k + 2];
-        G[k].center = (float) (c0 + t * (c1 - c0));
-        double v = s0 + t * (s1 - s0);
-        if (v <= 0.0) { G[k].sigma = 0.0f; G[k].amp = 0.0f; }
-        else
-          {
-             G[k].sigma = (float) v;
-             v = a0 + t * (a1 - a0);
-             if ((v < 0.0) && ((a1 > 0.0f) || (a0 > 0.0f))) v = 0.0;
-             G[k].amp = (float) v;
-          }
-     }
-   int flags = fef_normalize (G, ng);
+   FefRows R;
+   R.t = (energy - f.energies[i - 1]) / (f.energies[i] - f.energies[i - 1]);
+   R.g0 = f.gauss + (size_t) (i - 1) * ng * 3;
+   R.g1 = R.g0 + (size_t) ng * 3;
+   R.ng = ng;
+   uint32_t tail_mask;
+   int flags = fef_normalize (R, cum, stride, tail_mask);
    if (flags & 4) return -1;
    double pha;
-   int status = (flags == 0) ? fef_pha_pos (G, ng, pha, rng) : fef_pha_neg (G, ng, pha, rng);
+   int status = (flags == 0) ? fef_pha_pos (R, cum, stride, tail_mask, pha, rng) : fef_pha_neg (R, cum, stride, tail_mask, pha, rng);
    if (status == -1) return -1;
    int16_t ipha = (int16_t) pha;                   // truncation, acis_fef.c:1065
    pha_out = ipha;
@@ -257,7 +276,8 @@ MX_HD int acis_apply_fef (const AcisDev &A, const AcisChipDev &chip, float x, fl
 // _marx_acis_s_detect for one ray.  t_abs = pt->start_time + arrival_time.  Returns flags (0 alive,
 // possibly with PHOTON_ACIS_STREAKED set, which is not a "dead" bit).
 MX_HD uint32_t acis_detect (const AcisDev &A, double energy, double t_abs, Vec3 &x, Vec3 &p,
-                            int &ccd, float &chipx, float &chipy, int16_t &pha, float &pi, Rng &rng)
+                            int &ccd, float &chipx, float &chipy, int16_t &pha, float &pi, Rng &rng,
+                            float *fef_cum, uint32_t fef_stride)
 {
    const uint32_t UNDETECTED = 0x01, MISSED = 0x08, STREAKED = 0x200;
    uint32_t flags = 0;
@@ -292,7 +312,7 @@ MX_HD uint32_t acis_detect (const AcisDev &A, double energy, double t_abs, Vec3 
         double qe_contam = acis_contamination (d, energy, chipx, chipy);
         if (r >= qe * qe_filter * qe_contam) return UNDETECTED;
      }
-   if (-1 == acis_apply_fef (A, d, chipx, chipy, energy, pi, pha, rng))
+   if (-1 == acis_apply_fef (A, d, chipx, chipy, energy, pi, pha, rng, fef_cum, fef_stride))
      {
         pha = -1; pi = 0;
         return UNDETECTED;

@@ -104,7 +104,7 @@ int stage_grid_size (int stage, int num_sms, uint32_t blob_bytes);
 uint32_t stage_smem_bytes (int stage, uint32_t blob_bytes);
 
 // arrival-order restoration of an unordered live list (DESIGN.md "compaction"): bitmap over batch slots ->
-// popcount prefix -> scatter
+// popcount prefix -> rank (inverse permutation) -> gather
 struct OrderArgs
 {
    PhotonSoA in, out;
@@ -113,6 +113,7 @@ struct OrderArgs
    uint32_t *bitmap;                     // [n_slots/32 + 1], zeroed before launch
    uint32_t *word_prefix;                // [n_words]
    uint32_t *block_prefix;               // [n_words/1024 + 1]
+   uint32_t *perm;                       // [n_slots]: position in the unordered list of the photon with arrival rank j
 };
 void launch_restore_order (const OrderArgs &a, int num_sms, cudaStream_t s, int *n_launches);
 

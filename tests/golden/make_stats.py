@@ -18,12 +18,11 @@ REF = os.path.join(ROOT, "oracle", "_ref")
 sys.path.insert(0, ROOT)
 from tests.stats_bins import summarize  # noqa: E402
 
-COMMON = ["ExposureTime=0", "Verbose=0", "SourceFlux=0.003", "TStart=2023.5", "SourceType=POINT", "SpectrumType=FLAT",
-          "dNumRays=1000000"]
-CONFIGS = {
-    "c1_acis_s": ["MinEnergy=1.5", "MaxEnergy=1.5", "GratingType=NONE", "DetectorType=ACIS-S", "DitherModel=NONE"],
-    "c2_hetg_acis_s": ["MinEnergy=0.3", "MaxEnergy=8.0", "GratingType=HETG", "DetectorType=ACIS-S", "DitherModel=INTERNAL"],
-}
+from tests.golden.make_golden import COMMON as GOLDEN_COMMON, CONFIGS as GOLDEN_CONFIGS  # noqa: E402
+
+# the same parameter sets the calibration packs / replay fixtures were made with (tests/golden/make_golden.py)
+COMMON = GOLDEN_COMMON + ["dNumRays=1000000"]
+CONFIGS = {k: GOLDEN_CONFIGS[k]["args"] for k in ("c1_acis_s", "c2_hetg_acis_s", "c3_letg_hrc_s", "c4_beta_acis_i")}
 TYPES = {"E": ">f4", "I": ">i2", "J": ">i4", "A": "i1", "D": ">f8"}
 
 
@@ -52,8 +51,11 @@ def run_marx(args, seed, nrays, outdir):
 
 
 def main():
-    nrays, seeds = 4000000, [101, 102, 103, 104]
+    nrays, seeds = 2000000, [101, 102, 103, 104, 105, 106, 107, 108]
+    only = sys.argv[1:]
     for name, args in CONFIGS.items():
+        if only and name not in only:
+            continue
         acc = None
         n_gen = 0
         for seed in seeds:

@@ -25,8 +25,12 @@ def summarize(cols):
     if order is None:
         order = np.zeros(len(cols["energy"]), dtype=np.int64)
     out["h_order"] = np.histogram(np.asarray(order, dtype=np.float64), BINS["order"])[0].astype(np.int64)
-    # PSF of the undispersed image on the aim-point chip (S3, ccd 7): radius about the image centre (median)
-    sel = (np.asarray(order) == 0) & (np.asarray(cols["ccd"]) == 7)
+    # PSF of the undispersed image on the aim-point chip (the chip with most zeroth-order events: S3 = ccd 7 for
+    # ACIS-S, I3 for ACIS-I, the middle MCP for HRC-S): radius about the image centre (median)
+    ccd = np.asarray(cols["ccd"]).astype(np.int64)
+    zero = np.asarray(order) == 0
+    aim = np.bincount(ccd[zero & (ccd >= 0)]).argmax() if (zero & (ccd >= 0)).any() else 7
+    sel = zero & (ccd == aim)
     y, z = np.asarray(cols["ypos"], dtype=np.float64)[sel], np.asarray(cols["zpos"], dtype=np.float64)[sel]
     r = np.hypot(y - np.median(y), z - np.median(z)) if sel.any() else np.zeros(0)
     out["h_psf_r"] = np.histogram(r, BINS["psf_r"])[0].astype(np.int64)
