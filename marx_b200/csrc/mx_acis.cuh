@@ -38,6 +38,27 @@ MX_HD int chip_intersect (const AcisChipDev &g, const Vec3 &x0, const Vec3 &p, V
    return 1;
 }
 
+// Code-size control for k3_acis: the kernel is ~90 KB of SASS executed by warps that sit in different phases (geometry,
+// QE, contamination, FEF normalisation, sampling), and ncu showed "no instruction" (I-cache miss) as its largest stall.
+// With MX_K3_OUTLINE the table interpolation and the libm bodies used by this stage exist once, as real functions.
+#if defined(__CUDA_ARCH__) && defined(MX_K3_OUTLINE)
+__device__ __noinline__ float acis_interp_f (float x, const float *xp, const float *yp, uint32_t n) { return interp_f (x, xp, yp, n); }
+#if MX_K3_OUTLINE > 1
+__device__ __noinline__ double acis_exp (double x) { return exp (x); }
+__device__ __noinline__ double acis_erf (double x) { return erf (x); }
+__device__ __noinline__ double acis_pow (double x, double y) { return pow (x, y); }
+#else
+#define acis_exp exp
+#define acis_erf erf
+#define acis_pow pow
+#endif
+#else
+#define acis_interp_f interp_f
+#define acis_exp exp
+#define acis_erf erf
+#define acis_pow pow
+#endif
+
 // compute_contamination, aciscontam.c:93-136, with the analytic f(x,y) of :141-187
 MX_HD double acis_contamination (const AcisChipDev &c, double en, double cx, double cy)
 {
@@ -57,12 +78,14 @@ MX_HD double acis_contamination (const AcisChipDev &c, double en, double cx, dou
         else
           {
              const double y_0 = 512.0;
-             if (cy <= 512.0) fxy = pow (fabs ((cy - y_0) / (64.0 - y_0)), 5.5);
-             else fxy = pow (fabs ((cy - y_0) / (964.0 - y_0)), 4.5);
+             // aciscontam.c:141-187: two branches with different constants; one pow body serves both
+             const bool low = (cy <= 512.0);
+             const double den = low ? (64.0 - y_0) : (964.0 - y_0), ex = low ? 5.5 : 4.5;
+             fxy = acis_pow (fabs ((cy - y_0) / den), ex);
           }
         for (uint32_t i = 0; i < c.contam_num_layers; i++)
           {
-             double mu = interp_f (ef, c.contam_energies[i], c.contam_mus[i], c.contam_num_mu[i]);
+             double mu = acis_interp_f (ef, c.contam_energies[i], c.contam_mus[i], c.contam_num_mu[i]);
              v += mu * (c.contam_tau0[i] + c.contam_tau1[i] * fxy);
           }
      }
@@ -74,12 +97,12 @@ MX_HD double acis_contamination (const AcisChipDev &c, double en, double cx, dou
         uint32_t ofs = (1024 / c.contam_blocking) * (uint32_t) cy + (uint32_t) cx;
         for (uint32_t i = 0; i < c.contam_num_layers; i++)
           {
-             double mu = interp_f (ef, c.contam_energies[i], c.contam_mus[i], c.contam_num_mu[i]);
+             double mu = acis_interp_f (ef, c.contam_energies[i], c.contam_mus[i], c.contam_num_mu[i]);
              double fxy = c.contam_fxy[i][ofs];
              v += mu * (c.contam_tau0[i] + c.contam_tau1[i] * fxy);
           }
      }
-   return exp (-v);
+   return acis_exp (-v);
 }
 
 
@@ -142,7 +165,7 @@ MX_HD int fef_normalize (const FefRows &R, float *cum, uint32_t stride, uint32_t
         if ((sigma != 0.0) && (g.amp != 0.0f))
           {
              double x0 = g.center;
-             double e0 = erf ((0 - x0) / sigma);
+             double e0 = acis_erf ((0 - x0) / sigma);
              area1 = 0.5 * g.amp * (1.0 - e0) * (SQRT_2PI * g.sigma);
              area2 = 0.5 * g.amp * (e0 - (-1.0)) * (SQRT_2PI * g.sigma);
           }
@@ -226,7 +249,7 @@ MX_HD int fef_pha_neg (const FefRows &R, const float *cum, uint32_t stride, uint
              if (sigma != 0.0)
                {
                   double xx = (pha - g.center) / sigma;
-                  dsum = g.amp * exp (-0.5 * xx * xx);
+                  dsum = g.amp * acis_exp (-0.5 * xx * xx);
                }
              sum += dsum;
              if (dsum > 0) pos_sum += dsum;
@@ -268,7 +291,7 @@ MX_HD int acis_apply_fef (const AcisDev &A, const AcisChipDev &chip, float x, fl
    int16_t ipha = (int16_t) pha;                   // truncation, acis_fef.c:1065
    pha_out = ipha;
    pha = ipha - rng.uniform ();
-   pi = interp_f ((float) pha, f.channels, f.energies, ne);
+   pi = acis_interp_f ((float) pha, f.channels, f.energies, ne);
    if (pi < 0) return -1;
    return 0;
 }
@@ -307,8 +330,8 @@ MX_HD uint32_t acis_detect (const AcisDev &A, double energy, double t_abs, Vec3 
      {
         double r = rng.uniform ();
         float ef = (float) energy;
-        double qe = (d.qe_num != 0) ? (double) interp_f (ef, d.qe_energies, d.qe, d.qe_num) : 1.0;
-        double qe_filter = (d.filter_num != 0) ? (double) interp_f (ef, d.filter_energies, d.filter_qe, d.filter_num) : 1.0;
+        double qe = (d.qe_num != 0) ? (double) acis_interp_f (ef, d.qe_energies, d.qe, d.qe_num) : 1.0;
+        double qe_filter = (d.filter_num != 0) ? (double) acis_interp_f (ef, d.filter_energies, d.filter_qe, d.filter_num) : 1.0;
         double qe_contam = acis_contamination (d, energy, chipx, chipy);
         if (r >= qe * qe_filter * qe_contam) return UNDETECTED;
      }

@@ -53,7 +53,7 @@ def test_distributions_match_stock_marx(config):
     for key in ("h_energy", "h_order", "h_ccd", "h_shell", "h_pha", "h_pi", "h_chipx", "h_chipy", "h_psf_r"):
         if key == "h_energy" and config.startswith("c1"):
             continue                                     # monoenergetic
-        if acc[key].sum() == 0 and ref[key].sum() == 0:
+        if key not in ref.files or (acc[key].sum() == 0 and ref[key].sum() == 0):
             continue                                     # column absent for this detector (PI for the HRC)
         chi2, dof, p = two_sample_chi2(acc[key], ref[key])
         report[key] = (round(float(chi2), 1), dof, float(p))
