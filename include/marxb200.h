@@ -330,7 +330,7 @@ int marxb200_trace_from (marxb200_ctx *ctx, uint64_t first_ray, uint64_t n, doub
 /* Per-kernel device times (CUDA events on the launching stream), for roofline bookkeeping.  When enabled, an
  * event is recorded after every kernel launch; marxb200_get_kernel_ms synchronises, returns the accumulated
  * milliseconds and launch counts per kernel class since the last call, and resets them.  Classes:
- * 0 k0_time_sums, 1 k0_time_scan, 2 k0_source, 3 k01_source_hrma (fused), 4 k1_hrma<0>, 5 k1_hrma<1>, 6 k1_hrma<2>,
+ * 0 k0_time_sums, 1 k0_time_scan (k0_time_super + k0_time_bases + k0_time_tiles), 2 k0_source, 3 k01_source_hrma (fused), 4 k1_hrma<0>, 5 k1_hrma<1>, 6 k1_hrma<2>,
  * 7 k2_grating, 8 k3 (acis or hrc), 9 order restoration (5 kernels). */
 #define MARXB200_NUM_KERNEL_CLASSES 10
 int marxb200_set_profiling (marxb200_ctx *ctx, int on);

@@ -135,46 +135,75 @@ __global__ void __launch_bounds__ (kTile) k0_time_sums (const __grid_constant__ 
    if (threadIdx.x == 0) a.tile_sums[blockIdx.x] = total;
 }
 
-// pass 2 (one CTA): canonical order = sequential over tiles inside a super-tile, sequential over
-// super-tiles; results do not depend on how a run is split into batches or GPUs as long as the
-// splits are super-tile aligned (DESIGN.md "arrival times").
-__global__ void __launch_bounds__ (kTile) k0_time_scan (const __grid_constant__ SourceArgs a)
+// pass 2: canonical order = sequential over tiles inside a super-tile, sequential over super-tiles; results do
+// not depend on how a run is split into batches or GPUs as long as the splits are super-tile aligned (DESIGN.md
+// "arrival times").  Three small kernels perform exactly the additions the original single-CTA kernel did (which spent
+// 0.13 ms per 2^24-ray batch on uncoalesced, latency-bound loops): the sequential chains run out of shared memory, one
+// chain per CTA, all super-tiles in parallel.
+//   k0_time_super: super-tile s -> sum of its tile sums, left to right from 0
+//   k0_time_bases: (one CTA) running base of every super-tile, left to right from the batch's time base
+//   k0_time_tiles: super-tile s -> base of each of its tiles, left to right from the super-tile base
+__global__ void __launch_bounds__ (kSuperTile) k0_time_super (const __grid_constant__ SourceArgs a)
 {
+   __shared__ double v[kSuperTile];
    const uint64_t n_tiles = (a.n + kTile - 1) / kTile;
-   const uint64_t n_super = (n_tiles + kSuperTile - 1) / kSuperTile;
-   for (uint64_t s = threadIdx.x; s < n_super; s += blockDim.x)
-     {
-        double acc = 0.0;
-        uint64_t t0 = s * kSuperTile, t1 = min (t0 + (uint64_t) kSuperTile, n_tiles);
-        for (uint64_t t = t0; t < t1; t++) acc += a.tile_sums[t];
-        a.supertile_sums[s] = acc;
-     }
+   const uint64_t t0 = (uint64_t) blockIdx.x * kSuperTile, t = t0 + threadIdx.x;
+   v[threadIdx.x] = (t < n_tiles) ? a.tile_sums[t] : 0.0;
    __syncthreads ();
    if (threadIdx.x == 0)
      {
-        double acc = a.use_dev_base ? a.dev_times[1] : a.time_base;
-        a.dev_times[0] = acc;
-        for (uint64_t s = 0; s < n_super; s++)
+        const int cnt = (int) min ((uint64_t) kSuperTile, n_tiles - t0);
+        double acc = 0.0;
+        for (int k = 0; k < cnt; k++) acc += v[k];
+        a.supertile_sums[blockIdx.x] = acc;
+     }
+}
+__global__ void __launch_bounds__ (kSuperTile) k0_time_bases (const __grid_constant__ SourceArgs a)
+{
+   __shared__ double v[kSuperTile];
+   __shared__ double carry;
+   const uint64_t n_tiles = (a.n + kTile - 1) / kTile;
+   const uint64_t n_super = (n_tiles + kSuperTile - 1) / kSuperTile;
+   if (threadIdx.x == 0)
+     {
+        carry = a.use_dev_base ? a.dev_times[1] : a.time_base;
+        a.dev_times[0] = carry;
+        *a.n_out = a.n;
+     }
+   for (uint64_t s0 = 0; s0 < n_super; s0 += kSuperTile)
+     {
+        const uint64_t sidx = s0 + threadIdx.x;
+        __syncthreads ();
+        v[threadIdx.x] = (sidx < n_super) ? a.supertile_sums[sidx] : 0.0;
+        __syncthreads ();
+        if (threadIdx.x == 0)
           {
-             double v = a.supertile_sums[s];
-             a.tile_base[s * kSuperTile] = acc;          // base of the first tile of the super-tile
-             acc += v;
+             const int cnt = (int) min ((uint64_t) kSuperTile, n_super - s0);
+             double acc = carry;
+             for (int k = 0; k < cnt; k++) { const double x = v[k]; v[k] = acc; acc += x; }
+             carry = acc;
           }
-        a.dev_times[1] = acc;
+        __syncthreads ();
+        if (sidx < n_super) a.tile_base[sidx * kSuperTile] = v[threadIdx.x];      // base of the first tile of the super-tile
      }
    __syncthreads ();
-   for (uint64_t s = threadIdx.x; s < n_super; s += blockDim.x)
+   if (threadIdx.x == 0) a.dev_times[1] = carry;
+}
+__global__ void __launch_bounds__ (kSuperTile) k0_time_tiles (const __grid_constant__ SourceArgs a)
+{
+   __shared__ double v[kSuperTile];
+   const uint64_t n_tiles = (a.n + kTile - 1) / kTile;
+   const uint64_t t0 = (uint64_t) blockIdx.x * kSuperTile, t = t0 + threadIdx.x;
+   v[threadIdx.x] = (t < n_tiles) ? a.tile_sums[t] : 0.0;
+   __syncthreads ();
+   if (threadIdx.x == 0)
      {
-        uint64_t t0 = s * kSuperTile, t1 = min (t0 + (uint64_t) kSuperTile, n_tiles);
+        const int cnt = (int) min ((uint64_t) kSuperTile, n_tiles - t0);
         double acc = a.tile_base[t0];
-        for (uint64_t t = t0; t < t1; t++)
-          {
-             double v = a.tile_sums[t];
-             a.tile_base[t] = acc;
-             acc += v;
-          }
+        for (int k = 0; k < cnt; k++) { const double x = v[k]; v[k] = acc; acc += x; }
      }
-   if (threadIdx.x == 0) *a.n_out = a.n;
+   __syncthreads ();
+   if (t < n_tiles) a.tile_base[t] = v[threadIdx.x];
 }
 
 // pass 3: marx_create_photons for one ray per thread
@@ -925,7 +954,10 @@ void launch_time_sums (const SourceArgs &a, cudaStream_t s)
 }
 void launch_time_scan (const SourceArgs &a, cudaStream_t s)
 {
-   k0_time_scan<<<1, kTile, 0, s>>> (a);
+   const unsigned int n_super = (unsigned int) ((n_tiles_of (a.n) + kSuperTile - 1) / kSuperTile);
+   if (n_super) k0_time_super<<<n_super, kSuperTile, 0, s>>> (a);
+   k0_time_bases<<<1, kSuperTile, 0, s>>> (a);
+   if (n_super) k0_time_tiles<<<n_super, kSuperTile, 0, s>>> (a);
 }
 void launch_source (const SourceArgs &a, cudaStream_t s)
 {

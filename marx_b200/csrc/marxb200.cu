@@ -489,7 +489,7 @@ extern "C" int marxb200_create_photons (marxb200_ctx *c, uint64_t first_ray, uin
    launch_time_sums (a, c->stream); prof_mark (c, 0);
    launch_time_scan (a, c->stream); prof_mark (c, 1);
    launch_source (a, c->stream); prof_mark (c, 2);
-   c->launches += 3;
+   c->launches += 5;                     // k0_time_sums, k0_time_super/_bases/_tiles, k0_source
    CUDA_OK (cudaGetLastError ());
    c->cur = 0; c->stage_done = 0; c->n_generated = n; c->ordered = true; c->first_mirror_kernel = 0;
    return 0;
@@ -526,7 +526,7 @@ extern "C" int marxb200_time_sums (marxb200_ctx *c, uint64_t first_ray, uint64_t
    CUDA_OK (cudaMemcpyAsync (saved, c->d_times, sizeof (saved), cudaMemcpyDeviceToHost, c->stream));
    launch_time_sums (a, c->stream);
    launch_time_scan (a, c->stream);
-   c->launches += 2;
+   c->launches += 4;
    CUDA_OK (cudaStreamSynchronize (c->stream));
    CUDA_OK (cudaMemcpyAsync (c->d_times, saved, sizeof (saved), cudaMemcpyHostToDevice, c->stream));
    uint64_t n_tiles = (n + kTile - 1) / kTile, ns = (n_tiles + kSuperTile - 1) / kSuperTile;
@@ -674,7 +674,7 @@ static int create_and_enter_mirror (marxb200_ctx *c, uint64_t first_ray, uint64_
    CUDA_OK (cudaMemsetAsync (c->d_counts + 4, 0, sizeof (unsigned long long), c->stream));
    prof_begin (c);
    launch_source_hrma (a, st, c->grid01, c->stream); prof_mark (c, 3);
-   c->launches += 3;
+   c->launches += 5;                     // k0_time_sums, k0_time_super/_bases/_tiles, k01_source_hrma
    CUDA_OK (cudaGetLastError ());
    c->cur = 1; c->stage_done = 0; c->n_generated = n; c->ordered = false;
    c->first_mirror_kernel = 1;

@@ -12,10 +12,8 @@
 namespace mx {
 
 // rotate about the x axis, diffract.c:689-700
-MX_HD Vec3 rotate_x (Vec3 a, double theta)
+MX_HD Vec3 rotate_x (Vec3 a, double c, double s)
 {
-   double c, s;
-   sin_cos (theta, s, c);
    double ay = a.y, az = a.z;
    a.y = c * ay - s * az;
    a.z = s * ay + c * az;
@@ -185,9 +183,10 @@ MX_HD uint32_t grating_diffract (const GratingDev &G, uint32_t shell, double ene
    const GratingShellDev &g = G.shell[shell];
    // vignetting (flagged MIRROR_VBLOCKED by the reference, diffract.c:999-1000)
    if (rng.uniform () > g.vig) return VBLOCKED;
-   double theta = -1 * g.dispersion_angle;        // rotate_photons(pt, -1), diffract.c:854-875
-   x = rotate_x (x, theta);
-   p = rotate_x (p, theta);
+   // rotate_photons(pt, -1), diffract.c:854-875: the angle is a per-shell constant, its cosine and sine are tabulated
+   // by the host (tables_build.hpp, the reference's own libm); cos(-t) = cos(t), sin(-t) = -sin(t) exactly
+   x = rotate_x (x, g.cos_dispersion, -g.sin_dispersion);
+   p = rotate_x (p, g.cos_dispersion, -g.sin_dispersion);
    if (-1 == torus_intersect (x, p, g.rowland)) return UNDIFFRACTED;
    if (-1 == diffract_from_grating (g, 0.0, energy, x, p, order_out, g.num_sectors != 0, rng)) return UNDIFFRACTED;
    support_orders = 0;
@@ -204,9 +203,8 @@ MX_HD uint32_t grating_diffract (const GratingDev &G, uint32_t shell, double ene
              if (rc == -1) return UNDIFFRACTED;
           }
      }
-   theta = 1 * g.dispersion_angle;
-   x = rotate_x (x, theta);
-   p = rotate_x (p, theta);
+   x = rotate_x (x, g.cos_dispersion, g.sin_dispersion);
+   p = rotate_x (p, g.cos_dispersion, g.sin_dispersion);
    return 0;
 }
 

@@ -211,8 +211,9 @@ MX_HD_BIG double wfold_interp (const WfoldDev &w, double energy, double sin_alph
 // intersects_struts, hrma.c:928-968.  struts = {xpos0, half_width0, xpos1, half_width1}
 MX_HD_BIG int intersects_struts (const Vec3 &x0, const Vec3 &p0, double cap_position, const double *struts)
 {
-   const double theta = 30.0 * (kPI / 180.0);
-   const double cos_theta = cos (theta), sin_theta = sin (theta);
+   // cos and sin of 30 degrees as the reference's libm returns them for theta = 30.0*(PI/180.0) = 0x1.0c152382d7365p-1
+   // (hrma.c:930-932); spelled out so that no thread evaluates two trigonometric functions of a constant
+   const double cos_theta = 0x1.bb67ae8584cabp-1, sin_theta = 0x1.fffffffffffffp-2;
    for (int s = 0; s < 2; s++)
      {
         double half_width = struts[2 * s + 1];

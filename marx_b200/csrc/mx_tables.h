@@ -78,6 +78,7 @@ struct GratingShellDev
    const float *cum_eff;           // [num_orders][num_energies]
    const double *sectors;          // [num_sectors][6]: min, max, dtheta, dtheta_blur, dpp, dpp_blur
    double dispersion_angle, period, dp_over_p, theta_blur, vig, rowland;
+   double cos_dispersion, sin_dispersion;   // of dispersion_angle, evaluated on the host (diffract.c:689-700 uses libm per photon)
 };
 
 struct GratingDev

@@ -117,6 +117,7 @@ template <class Up> int build_grating_shell (Up &up, const marxb200_grating_shel
        t[(size_t) e * s.num_orders + o] = s.cum_eff[(size_t) o * s.num_energies + e];
    if (-1 == tb_up (up, t.data (), t.size (), &g.cum_eff, err)) return -1;
    g.dispersion_angle = s.dispersion_angle; g.period = s.period; g.dp_over_p = s.dp_over_p;
+   g.cos_dispersion = cos (s.dispersion_angle); g.sin_dispersion = sin (s.dispersion_angle);
    g.theta_blur = s.theta_blur; g.vig = s.vig; g.rowland = rowland;
    g.sectors = nullptr;
    return 0;

@@ -1,6 +1,6 @@
 set -x
 cd /root/repo
-timeout 900 python -m pytest tests/test_gpu_statistics.py -q -m gpu 2>&1 | tail -4
+timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -6
 python bench.py --steps 100 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_r01_final2.json; cut -c1-300 gpurun_out/bench_r01_final2.json
 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1 > gpurun_out/bench_r01_reference.json; cat gpurun_out/bench_r01_reference.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_r01_final2.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/b2.log 2>&1
