@@ -74,6 +74,34 @@ def run_reference_sample(nrays_per_proc, nprocs, seed0=1):
     return rays, secs, wall
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's host threads to the CPUs local to its GPU (sysfs local_cpulist of the GPU's PCI device), so that
+    the pinned egress buffers are first-touched on that NUMA node and the D2H copies of 8 ranks do not all cross the
+    socket interconnect.  Returns a short description for the JSON line (None if the topology is not exposed)."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(index)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]                      # sysfs uses a 4-digit PCI domain
+        base = "/sys/bus/pci/devices/" + bus
+        cpus = open(base + "/local_cpulist").read().strip()
+        node = open(base + "/numa_node").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                ids.update(range(int(a), int(b) + 1))
+            elif part:
+                ids.add(int(part))
+        ids &= set(os.sched_getaffinity(0))
+        if not ids:
+            return None
+        os.sched_setaffinity(0, ids)
+        return "gpu %d: numa node %s, %d cpus" % (index, node, len(ids))
+    except Exception:  # noqa: BLE001
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -172,6 +200,7 @@ def cuda_arm(args):
         raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)      # before any pinned allocation: first touch decides the node
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -181,16 +210,18 @@ def cuda_arm(args):
     stream = torch.cuda.Stream(device=dev)
     m = marx_b200.MarxB200(args.calpack, device=local_rank, seed=args.seed, max_photons=n, stream=stream.cuda_stream)
 
-    # pinned host buffers for the e2e leg: event columns of marxio.c:292-322 (E T x y z cosines chip pha pi order ...)
-    col_names = ("energy", "time", "xpos", "ypos", "zpos", "xcos", "ycos", "zcos", "chipx", "chipy", "pi", "pha",
-                 "ccd", "order", "shell", "ray")
+    # e2e leg: the event list of every step lands in pinned host memory as the column set the reference writes for this
+    # configuration by default (marx.par OutputVectors "ETXYZ123DxyMPOabcdSrB" ANDed with the photon history,
+    # marxio.c:409-414): 17 float32 + 2 int16 + 2 int8 columns = 74 B per event, in the reference's file encoding
+    # (marxb200_egress_begin_packed/_end_packed: converted on the device, copied on a private stream while the next
+    # batch is traced).  Two pinned buffers: the host side is double-buffered as well.
+    from marx_b200 import HISTORY
+    e2e_mask = sum(HISTORY[k] for k in ("ENERGY", "TIME", "X_VECTOR", "P_VECTOR", "DET_NUM", "DET_PIXEL", "MIRROR_SHELL",
+                                        "PULSEHEIGHT", "ORDER", "PI", "SKY_DITHER", "DET_DITHER"))
+    bytes_per_event = 17 * 4 + 2 * 2 + 2 * 1
     cap = n // 8
-    from marx_b200.api import _COLUMN_DTYPES
-    tdt = {"<f8": "float64", "<f4": "float32", "<i2": "int16", "i1": "int8", "<u8": "int64"}
-    pinned = [{k: torch.empty(cap, dtype=getattr(torch, tdt[_COLUMN_DTYPES[k]]), pin_memory=True) for k in col_names}
-              for _ in range(2)]                                    # double-buffered host side
-    pinned_np = [{k: v.numpy().view(_COLUMN_DTYPES[k]) for k, v in p.items()} for p in pinned]
-    bytes_per_event = sum(np.dtype(_COLUMN_DTYPES[k]).itemsize for k in col_names)
+    pinned = [torch.empty(cap * (bytes_per_event + 2) + 4096, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    pinned_np = [p.numpy() for p in pinned]
 
     bases = {}
 
@@ -241,10 +272,10 @@ def cuda_arm(args):
             if e2e:
                 # pipelined egress: the D2H copy of batch s-1 overlaps the kernels of batch s
                 if s > 0:
-                    n_events += len(m.egress_end(pinned_np[(s - 1) & 1])["energy"])
-                m.egress_begin(cap)
+                    n_events += len(m.egress_end_packed(pinned_np[(s - 1) & 1])["energy.dat"])
+                m.egress_begin_packed(e2e_mask, 0.0, cap)
         if e2e:
-            n_events += len(m.egress_end(pinned_np[(K - 1) & 1])["energy"])
+            n_events += len(m.egress_end_packed(pinned_np[(K - 1) & 1])["energy.dat"])
         t1.record(stream)
         barrier()
         ms = t0.elapsed_time(t1)
@@ -336,13 +367,14 @@ def cuda_arm(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": n, "calpack": args.calpack, "seed": args.seed,
                    "l2": "inputs (1.7 GB photon SoA per batch) exceed the 126 MB L2; no flush needed",
-                   "stage_counts_last_step_rank0": counts},
+                   "stage_counts_last_step_rank0": counts, "host_affinity_rank0": numa},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 24,
                 "d2h_bytes_per_step": int(bytes_per_event * n_events / args.steps) + 8,
-                "note": "C ABI marxb200_trace_from + marxb200_egress_begin/_end: every step's event list (16 columns) is copied "
-                        "to pinned host memory inside the timed region, overlapped with the next batch; the only per-step "
-                        "host input of this path is the batch descriptor (first ray, count, time base)"},
+                "note": "C ABI marxb200_trace_from + marxb200_egress_begin_packed/_end_packed: every step's event list (the 21 "
+                        "columns the reference writes for this configuration, in its float32/int16/int8 file encoding, 74 B per "
+                        "event) is copied to pinned host memory inside the timed region, overlapped with the next batch; the "
+                        "only per-step host input of this path is the batch descriptor (first ray, count, time base)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k1_hrma<1>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,

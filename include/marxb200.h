@@ -402,6 +402,24 @@ int marxb200_egress_end (marxb200_ctx *ctx, const marxb200_columns *cols, uint64
 #define MARXB200_ORDER4_OK        0x01000000
 int marxb200_write_photons (marxb200_ctx *ctx, const char *dir, uint64_t write_mask, int open_mode, double total_time);
 
+/* Pipelined form of the same egress without the file system: _begin_packed converts the selected columns of the live list
+ * to their file images (the bytes marxb200_write_photons would append, big endian) in a device staging area and returns
+ * at once; _end_packed copies them into the caller's (ideally pinned) host buffer on the private copy stream --
+ * overlapping the next batch's kernels -- and describes where each column landed. */
+typedef struct
+{
+   uint32_t num_cols;
+   uint64_t n_rows;
+   uint64_t mask[32];              /* the MARXB200_*_OK bit of each column */
+   char file[32][16];              /* its file name in a MARX output directory (marxio.c:292-322) */
+   char type[32];                  /* 'E' float32, 'I' int16, 'J' int32, 'A' int8 */
+   uint32_t elem_size[32];
+   uint64_t offset[32];            /* byte offset of the column in the host buffer; n_rows * elem_size bytes each */
+}
+marxb200_packed_layout;
+int marxb200_egress_begin_packed (marxb200_ctx *ctx, uint64_t write_mask, double total_time, uint64_t max_out);
+int marxb200_egress_end_packed (marxb200_ctx *ctx, void *host, uint64_t host_bytes, marxb200_packed_layout *layout);
+
 /* FP64 roofline denominator measured on this GPU: best of 5 runs of a DFMA-chain kernel (8 independent chains per
  * thread, 8 x 256-thread CTAs per SM), in TFLOP/s counting an FMA as 2 flops.  Diagnostic; leaves the photon list alone. */
 int marxb200_measure_fp64_peak (marxb200_ctx *ctx, double *tflops);

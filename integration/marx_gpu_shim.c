@@ -30,6 +30,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
+#include <time.h>
 #include <marx.h>
 #include <marxb200.h>
 
@@ -54,6 +55,15 @@ static int Host_Is_Stale;              /* photons of the current batch live in H
 static int Have_Support_Orders;
 static int Stock_Egress;               /* MARXB200_EGRESS=stock */
 static int Bulk_Written;               /* the current batch went to the output directory straight from the device */
+
+/* MARXB200_TIMING=1: host wall time spent in each wrapped call, printed when the driver frees its photon buffer */
+static double T_Init, T_Create, T_Stages, T_Write, T_Sync;
+static double now (void)
+{
+   struct timespec ts;
+   clock_gettime (CLOCK_MONOTONIC, &ts);
+   return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
 
 static int gpu_error (const char *what)
 {
@@ -128,6 +138,7 @@ static int sync_host (Marx_Photon_Type *pt)
    uint64_t n_live = 0, i;
    unsigned int *idx;
 
+   double t0 = now ();
    if (Host_Is_Stale == 0) return 0;
    if (-1 == marxb200_download (Ctx, (marxb200_photon_attr *) pt->attributes, pt->max_n_photons, &n_live))
      return gpu_error ("marxb200_download");
@@ -143,6 +154,7 @@ static int sync_host (Marx_Photon_Type *pt)
    pt->sorted_index = idx;
    pt->n_photons = pt->num_sorted = (unsigned int) n_live;
    Host_Is_Stale = 0;
+   T_Sync += now () - t0;
    return 0;
 }
 
@@ -154,7 +166,12 @@ int __wrap_marx_create_photons (Marx_Source_Type *st, Marx_Photon_Type *pt, unsi
 
    *num_collected = 0;
    if ((st == NULL) || (pt == NULL)) return -1;
-   if ((Ctx == NULL) && (-1 == gpu_init (st, pt))) return -1;
+   if (Ctx == NULL)
+     {
+	double t0 = now ();
+	if (-1 == gpu_init (st, pt)) return -1;
+	T_Init += now () - t0;
+     }
    if (num > pt->max_n_photons)
      { marx_error ("marxb200: batch of %u rays exceeds the photon buffer", num); return -1; }
 
@@ -162,6 +179,7 @@ int __wrap_marx_create_photons (Marx_Source_Type *st, Marx_Photon_Type *pt, unsi
    pt->history = 0;
    pt->start_time += pt->total_time;
 
+   double t0 = now ();
    /* time base < 0: the running sum of arrival times continues on the device (source.c:285,326) */
    if (-1 == marxb200_create_photons (Ctx, Next_Ray, n, -1.0))
      return gpu_error ("marxb200_create_photons");
@@ -179,6 +197,7 @@ int __wrap_marx_create_photons (Marx_Source_Type *st, Marx_Photon_Type *pt, unsi
    *num_collected = (unsigned int) n;
    Host_Is_Stale = 1;
    Bulk_Written = 0;
+   T_Create += now () - t0;
    return 0;
 }
 
@@ -187,7 +206,7 @@ int __wrap_marx_mirror_reflect (Marx_Photon_Type *pt, int verbose)
    if (pt->history & MARX_MIRROR_SHELL_OK) return 0;      /* hrma.c:1171-1173 */
    pt->history |= MARX_MIRROR_SHELL_OK;
    if (verbose > 0) marx_message ("Reflecting from HRMA [B200]\n");
-   if (-1 == marxb200_mirror_reflect (Ctx)) return gpu_error ("marxb200_mirror_reflect");
+   { double t0 = now (); if (-1 == marxb200_mirror_reflect (Ctx)) return gpu_error ("marxb200_mirror_reflect"); T_Stages += now () - t0; }
    return 0;
 }
 
@@ -199,7 +218,7 @@ int __wrap_marx_grating_diffract (Marx_Photon_Type *pt, int verbose)
    if (Have_Support_Orders)                               /* diffract.c:1098-1118 */
      pt->history |= (MARX_ORDER1_OK | MARX_ORDER2_OK | MARX_ORDER3_OK | MARX_ORDER4_OK);
    if (verbose > 0) marx_message ("Diffracting from %s [B200]\n", (Grating_Id == MARX_GRATING_LETG) ? "LETG" : "HETG");
-   if (-1 == marxb200_grating_diffract (Ctx)) return gpu_error ("marxb200_grating_diffract");
+   { double t0 = now (); if (-1 == marxb200_grating_diffract (Ctx)) return gpu_error ("marxb200_grating_diffract"); T_Stages += now () - t0; }
    return 0;
 }
 
@@ -214,7 +233,7 @@ int __wrap_marx_detect (Marx_Photon_Type *pt, int verbose)
 	else
 	  pt->history |= (MARX_DET_PIXEL_OK | MARX_DET_NUM_OK | MARX_PULSEHEIGHT_OK | MARX_PI_OK);
 	if (verbose > 0) marx_message ("Detecting [B200]\n");
-	if (-1 == marxb200_detect (Ctx)) return gpu_error ("marxb200_detect");
+	{ double t0 = now (); if (-1 == marxb200_detect (Ctx)) return gpu_error ("marxb200_detect"); T_Stages += now () - t0; }
      }
    return 0;
 }
@@ -231,8 +250,12 @@ int __wrap_marx_write_photons (Marx_Photon_Type *pt, unsigned long write_mask, c
      write_mask &= (pt->history | MARX_SKY_DITHER_OK | MARX_DET_DITHER_OK);
    else
      write_mask &= pt->history;
-   if (-1 == marxb200_write_photons (Ctx, dir, (uint64_t) write_mask, open_mode, total_time))
-     return gpu_error ("marxb200_write_photons");
+   {
+      double t0 = now ();
+      if (-1 == marxb200_write_photons (Ctx, dir, (uint64_t) write_mask, open_mode, total_time))
+	return gpu_error ("marxb200_write_photons");
+      T_Write += now () - t0;
+   }
    Bulk_Written = 1;
    return 0;
 }
@@ -267,6 +290,9 @@ int __wrap_marx_dealloc_photon_type (Marx_Photon_Type *pt)
 	if (0 == marxb200_get_stage_counts (Ctx, stage))
 	  marx_message ("marxb200: last batch: %lu generated, %lu reflected, %lu diffracted, %lu detected\n",
 			(unsigned long) stage[0], (unsigned long) stage[1], (unsigned long) stage[2], (unsigned long) stage[3]);
+	if (getenv ("MARXB200_TIMING") != NULL)
+	  fprintf (stderr, "marxb200: host seconds in the wrapped calls: init+upload %.3f, create_photons %.3f, stages %.3f, "
+		   "write_photons %.3f, download %.3f\n", T_Init, T_Create, T_Stages, T_Write, T_Sync);
 	(void) marxb200_destroy (Ctx);
 	Ctx = NULL;
      }

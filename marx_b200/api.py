@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = [
     "marxb200_set_grating", "marxb200_set_acis", "marxb200_set_hrc_s", "marxb200_load_calpack", "marxb200_alloc_photons",
     "marxb200_create_photons", "marxb200_truncate_exposure", "marxb200_time_sums", "marxb200_mirror_reflect", "marxb200_grating_diffract",
     "marxb200_detect", "marxb200_restore_order", "marxb200_trace", "marxb200_trace_from", "marxb200_set_profiling", "marxb200_get_kernel_ms", "marxb200_get_counts", "marxb200_get_stage_counts", "marxb200_get_internal_counts", "marxb200_download",
-    "marxb200_upload", "marxb200_download_all", "marxb200_download_columns", "marxb200_egress_begin", "marxb200_egress_end", "marxb200_write_photons", "marxb200_measure_fp64_peak", "marxb200_get_launch_count",
+    "marxb200_upload", "marxb200_download_all", "marxb200_download_columns", "marxb200_egress_begin", "marxb200_egress_end", "marxb200_write_photons", "marxb200_egress_begin_packed", "marxb200_egress_end_packed", "marxb200_measure_fp64_peak", "marxb200_get_launch_count",
 ]
 
 # Marx_Photon_Attr_Type, marx/libsrc/marx.h:51-100 (136 bytes; offsets probed in SURVEY.md 8a1)
@@ -122,6 +122,8 @@ def load_library():
         "marxb200_egress_end": [vp, vp, C.POINTER(u64)],
         "marxb200_write_photons": [vp, C.c_char_p, u64, i32, dbl],
         "marxb200_measure_fp64_peak": [vp, C.POINTER(dbl)],
+        "marxb200_egress_begin_packed": [vp, u64, dbl, u64],
+        "marxb200_egress_end_packed": [vp, vp, u64, vp],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -129,6 +131,11 @@ def load_library():
         fn.restype = i32
     _LIB = lib
     return lib
+
+
+class _PackedLayout(C.Structure):
+    _fields_ = [("num_cols", C.c_uint32), ("n_rows", C.c_uint64), ("mask", C.c_uint64 * 32), ("file", (C.c_char * 16) * 32),
+                ("type", C.c_char * 32), ("elem_size", C.c_uint32 * 32), ("offset", C.c_uint64 * 32)]
 
 
 class _Columns(C.Structure):
@@ -293,6 +300,22 @@ class MarxB200:
         got = C.c_uint64()
         self._check(self._lib.marxb200_egress_end(self._ctx, C.byref(cols), C.byref(got)))
         return {k: v[:got.value] for k, v in out.items()}
+
+    def egress_begin_packed(self, write_mask, total_time, max_out):
+        """pack the selected columns into their MARX file images on the device and return at once (include/marxb200.h)"""
+        self._check(self._lib.marxb200_egress_begin_packed(self._ctx, int(write_mask), float(total_time), int(max_out)))
+
+    def egress_end_packed(self, host):
+        """host: (pinned) uint8 numpy array; blocks until the packed columns have landed.  Returns {file name: big-endian
+        numpy view into `host`}."""
+        lay = _PackedLayout()
+        self._check(self._lib.marxb200_egress_end_packed(self._ctx, host.ctypes.data_as(C.c_void_p), host.nbytes, C.byref(lay)))
+        dts = {b"E": ">f4", b"I": ">i2", b"J": ">i4", b"A": "i1"}
+        out = {}
+        for j in range(lay.num_cols):
+            dt = np.dtype(dts[lay.type[j:j + 1]])
+            out[lay.file[j].value.decode()] = host[lay.offset[j]:lay.offset[j] + lay.n_rows * dt.itemsize].view(dt)
+        return out
 
     def write_photons(self, directory, write_mask, open_mode, total_time):
         """marx_write_photons (marxio.c:403-476): create/append the column files of an output directory from the

@@ -85,7 +85,8 @@ struct marxb200_ctx
    cudaEvent_t ev_staged = nullptr, ev_copied = nullptr;
    void *egress_slab = nullptr; uint64_t egress_cap = 0; PhotonSoA egress;
    unsigned long long *h_egress_count = nullptr;      // pinned
-   bool egress_pending = false;
+   bool egress_pending = false, egress_is_packed = false;
+   EgressPlan packed_plan; int packed_which[kMaxEgressCols]; uint64_t packed_cap = 0;
 
    // optional per-kernel timing
    bool profiling = false;
@@ -160,6 +161,7 @@ static size_t align16 (size_t x) { return (x + 15) & ~(size_t) 15; }
 static int ensure_pinned (marxb200_ctx *c, size_t bytes)
 {
    if (c->h_pinned_bytes >= bytes) return 0;
+   bytes += bytes / 4 + 65536;          // event counts fluctuate from batch to batch: grow with headroom, not every time
    if (c->h_pinned) cudaFreeHost (c->h_pinned);
    c->h_pinned = nullptr; c->h_pinned_bytes = 0;
    CUDA_OK (cudaMallocHost (&c->h_pinned, bytes));
@@ -169,6 +171,7 @@ static int ensure_pinned (marxb200_ctx *c, size_t bytes)
 static int ensure_aos (marxb200_ctx *c, uint64_t n)
 {
    if (c->d_aos_cap >= n) return 0;
+   n += n / 4 + 1024;
    if (c->d_aos) cudaFree (c->d_aos);
    c->d_aos = nullptr; c->d_aos_cap = 0;
    CUDA_OK (cudaMalloc (&c->d_aos, (size_t) n * sizeof (marxb200_photon_attr)));
@@ -990,14 +993,14 @@ extern "C" int marxb200_egress_begin (marxb200_ctx *c, uint64_t max_out)
 #undef STAGE
    CUDA_OK (cudaMemcpyAsync (c->h_egress_count, c->d_counts + c->stage_done, sizeof (unsigned long long), cudaMemcpyDeviceToHost, c->stream));
    CUDA_OK (cudaEventRecord (c->ev_staged, c->stream));
-   c->egress_pending = true;
+   c->egress_pending = true; c->egress_is_packed = false;
    return 0;
 }
 
 extern "C" int marxb200_egress_end (marxb200_ctx *c, const marxb200_columns *cols, uint64_t *n_out)
 {
    if ((c == nullptr) || (cols == nullptr)) return fail ("marxb200_egress_end: NULL argument");
-   if (!c->egress_pending) return fail ("marxb200_egress_end: no egress in flight");
+   if (!c->egress_pending || c->egress_is_packed) return fail ("marxb200_egress_end: no (unpacked) egress in flight");
    CUDA_OK (cudaSetDevice (c->device));
    CUDA_OK (cudaEventSynchronize (c->ev_staged));
    unsigned long long n = *c->h_egress_count;
@@ -1015,6 +1018,89 @@ extern "C" int marxb200_egress_end (marxb200_ctx *c, const marxb200_columns *col
    CUDA_OK (cudaStreamSynchronize (c->copy_stream));
    c->egress_pending = false;
    if (n_out) *n_out = n;
+   return 0;
+}
+
+// Pipelined PACKED egress: the column-file images marxb200_write_photons appends, produced on the device and landed in
+// the caller's (pinned) host buffer while the next batch is being traced.  Staging reuses the egress slab; every column
+// has a fixed region of align16 (max_out * size) bytes there, so the pack kernel needs no host knowledge of the count.
+extern "C" int marxb200_egress_begin_packed (marxb200_ctx *c, uint64_t write_mask, double total_time, uint64_t max_out)
+{
+   if (c == nullptr) return fail ("NULL ctx");
+   if (c->stage_done < 0) return fail ("marxb200_egress_begin_packed: no photons");
+   if (max_out == 0) return fail ("marxb200_egress_begin_packed: max_out must be > 0");
+   if (c->egress_pending) return fail ("marxb200_egress_begin_packed: the previous egress was not ended");
+   CUDA_OK (cudaSetDevice (c->device));
+   if (c->copy_stream == nullptr)
+     {
+        CUDA_OK (cudaStreamCreateWithFlags (&c->copy_stream, cudaStreamNonBlocking));
+        CUDA_OK (cudaEventCreateWithFlags (&c->ev_staged, cudaEventDisableTiming));
+        CUDA_OK (cudaEventCreateWithFlags (&c->ev_copied, cudaEventDisableTiming));
+        CUDA_OK (cudaMallocHost (&c->h_egress_count, sizeof (unsigned long long)));
+     }
+   if (max_out > c->capacity) max_out = c->capacity;
+   if (c->egress_cap < max_out)
+     {
+        CUDA_OK (cudaStreamSynchronize (c->copy_stream));
+        if (c->egress_slab) cudaFree (c->egress_slab);
+        PhotonSoA tmp;
+        size_t bytes = carve (tmp, nullptr, max_out);       // 126 B per row: more than any packed row (<= 116 B)
+        CUDA_OK (cudaMalloc (&c->egress_slab, bytes));
+        carve (c->egress, (unsigned char *) c->egress_slab, max_out);
+        c->egress_cap = max_out;
+     }
+   if (-1 == ensure_order (c)) return -1;
+   EgressPlan &plan = c->packed_plan;
+   memset (&plan, 0, sizeof (plan));
+   uint64_t total = 0;
+   for (int k = 0; k < kNumEgressCols; k++)
+     {
+        if (0 == (kEgressCols[k].mask & write_mask)) continue;
+        c->packed_which[plan.num_cols] = k;
+        plan.kind[plan.num_cols] = kEgressCols[k].kind;
+        plan.offset[plan.num_cols] = total;
+        plan.num_cols++;
+        total += (uint64_t) align16 ((size_t) max_out * kEgressCols[k].size);
+     }
+   CUDA_OK (cudaStreamWaitEvent (c->stream, c->ev_copied, 0));      // the slab may still be read by the previous copy
+   launch_egress_pack (c->buf[c->cur], c->d_counts + c->stage_done, max_out, plan, c->egress_slab, c->d_times, total_time, c->stream);
+   c->launches += 1;
+   CUDA_OK (cudaMemcpyAsync (c->h_egress_count, c->d_counts + c->stage_done, sizeof (unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+   CUDA_OK (cudaEventRecord (c->ev_staged, c->stream));
+   CUDA_OK (cudaGetLastError ());
+   c->packed_cap = max_out;
+   c->egress_pending = true; c->egress_is_packed = true;
+   return 0;
+}
+
+extern "C" int marxb200_egress_end_packed (marxb200_ctx *c, void *host, uint64_t host_bytes, marxb200_packed_layout *layout)
+{
+   if ((c == nullptr) || (host == nullptr) || (layout == nullptr)) return fail ("marxb200_egress_end_packed: NULL argument");
+   if (!c->egress_pending || !c->egress_is_packed) return fail ("marxb200_egress_end_packed: no packed egress in flight");
+   CUDA_OK (cudaSetDevice (c->device));
+   CUDA_OK (cudaEventSynchronize (c->ev_staged));
+   unsigned long long n = *c->h_egress_count;
+   if (n > c->packed_cap) n = c->packed_cap;
+   const EgressPlan &plan = c->packed_plan;
+   memset (layout, 0, sizeof (*layout));
+   layout->num_cols = (uint32_t) plan.num_cols;
+   layout->n_rows = n;
+   uint64_t off = 0;
+   for (int j = 0; j < plan.num_cols; j++)
+     {
+        const EgressCol &col = kEgressCols[c->packed_which[j]];
+        layout->mask[j] = col.mask; layout->type[j] = col.type; layout->elem_size[j] = (uint32_t) col.size;
+        strncpy (layout->file[j], col.file, sizeof (layout->file[j]) - 1);
+        layout->offset[j] = off;
+        off += (uint64_t) align16 ((size_t) n * col.size);
+     }
+   c->egress_pending = false; c->egress_is_packed = false;
+   if (off > host_bytes) return fail ("marxb200_egress_end_packed: the host buffer holds %llu bytes, %llu are needed", (unsigned long long) host_bytes, (unsigned long long) off);
+   for (int j = 0; j < plan.num_cols; j++)
+     if (n) CUDA_OK (cudaMemcpyAsync ((unsigned char *) host + layout->offset[j], (const unsigned char *) c->egress_slab + plan.offset[j],
+                                      (size_t) n * layout->elem_size[j], cudaMemcpyDeviceToHost, c->copy_stream));
+   CUDA_OK (cudaEventRecord (c->ev_copied, c->copy_stream));
+   CUDA_OK (cudaStreamSynchronize (c->copy_stream));
    return 0;
 }
 
