@@ -71,14 +71,17 @@ __device__ __forceinline__ void st_relaxed (unsigned long long *p, unsigned long
 
 // Stage a table blob into dynamic shared memory with ONE TMA bulk copy; every thread waits on the
 // mbarrier.  blob_bytes is a multiple of 16 and both addresses are 16-byte aligned.
-__device__ __forceinline__ void stage_blob (unsigned char *smem, const void *blob, uint32_t blob_bytes, unsigned long long *bar)
+__device__ __forceinline__ void stage_blob (unsigned char *smem, const void *blob, uint32_t blob_bytes, unsigned long long *bar,
+                                            uint32_t seg2_off = 0, uint32_t seg2_bytes = 0)
 {
    if (threadIdx.x == 0) mbar_init (bar, 1);
    __syncthreads ();
    if (threadIdx.x == 0)
      {
-        mbar_expect_tx (bar, blob_bytes);
+        mbar_expect_tx (bar, blob_bytes + seg2_bytes);
         tma_bulk_g2s (smem, blob, blob_bytes, bar);
+        // optional second byte range of the blob, placed behind the first (128-byte aligned)
+        if (seg2_bytes) tma_bulk_g2s (smem + ((blob_bytes + 127u) & ~127u), (const unsigned char *) blob + seg2_off, seg2_bytes, bar);
      }
    mbar_wait (bar, 0);
 }
@@ -262,11 +265,13 @@ __device__ __forceinline__ void run_stage (const StageArgs &a, WarpQueue<ND, NU>
         __syncwarp ();
      };
 
+   // (drawing the NEXT chunk's ticket before tracing the current one, to hide the atomic's round trip, was measured
+   // 2 % slower: the extra live registers spill)
+   unsigned long long chunk = 0;
+   if (lane == 0) chunk = atomicAdd (a.ticket, 1ULL);
+   chunk = __shfl_sync (0xffffffffu, chunk, 0);
    while (true)
      {
-        unsigned long long chunk = 0;
-        if (lane == 0) chunk = atomicAdd (a.ticket, 1ULL);
-        chunk = __shfl_sync (0xffffffffu, chunk, 0);
         const unsigned long long base0 = chunk * (unsigned long long) (a.chunk_tiles * kWarpTile);
         if (base0 >= n_in)
           {
@@ -303,6 +308,9 @@ __device__ __forceinline__ void run_stage (const StageArgs &a, WarpQueue<ND, NU>
                }
              else if (active) store_in_place (i, d, u, flags);
           }
+        unsigned long long next_chunk = 0;
+        if (lane == 0) next_chunk = atomicAdd (a.ticket, 1ULL);
+        chunk = __shfl_sync (0xffffffffu, next_chunk, 0);
      }
    if (a.compact && (count > 0)) flush (count);
 }
@@ -338,11 +346,20 @@ __global__ void __launch_bounds__ (kStageThreads, 3) k1_hrma (const __grid_const
    constexpr int ND = K1Shape<PHASE>::ND, NU = K1Shape<PHASE>::NU;
    extern __shared__ __align__ (128) unsigned char smem[];
    __shared__ __align__ (8) unsigned long long bar;
-   // only phase B needs the optical-constant tables behind the header
-   const uint32_t staged = (PHASE == 1) ? a.blob_bytes : (uint32_t) sizeof (K1Blob);
-   stage_blob (smem, a.blob, staged, &bar);
+   // only phase B needs the optical-constant tables behind the header; B and C also stage the WFOLD search keys of
+   // their conic (B: contiguous with the tables, C: as a second segment behind the header)
+   const uint32_t seg1 = (PHASE == 1) ? a.blob_bytes : (uint32_t) sizeof (K1Blob);
+   const uint32_t seg2 = (PHASE == 2) ? a.seg2_bytes : 0u;
+   stage_blob (smem, a.blob, seg1, &bar, a.seg2_off, seg2);
    const K1Blob &B = *reinterpret_cast<const K1Blob *> (smem);
    const HrmaDev &H = B.H;
+   const uint32_t staged = seg2 ? (((seg1 + 127u) & ~127u) + seg2) : seg1;
+#ifdef MX_NO_WFOLD_KEYS_SMEM
+   const unsigned char *wkeys = nullptr;
+#else
+   const unsigned char *wkeys = (B.wkeys_bytes == 0) ? nullptr
+                                : ((PHASE == 1) ? smem + B.off_wkeys_p : ((PHASE == 2 && seg2) ? smem + ((seg1 + 127u) & ~127u) : nullptr));
+#endif
    WarpQueue<ND, NU> &q = my_queue<ND, NU> (smem, staged);
    const PhotonSoA &in = a.in, &out = a.out;
 
@@ -371,12 +388,14 @@ __global__ void __launch_bounds__ (kStageThreads, 3) k1_hrma (const __grid_const
                                           reinterpret_cast<const float *> (smem + B.off_corr_e),
                                           reinterpret_cast<const float *> (smem + B.off_corr_f),
                                           energy, beta, delta, corr);
-                  flags = hrma_phase_b (H, shell, energy, beta, delta, corr, x, p, rng);
+                  flags = hrma_phase_b (H, shell, energy, beta, delta, corr, x, p, rng,
+                                        wkeys ? reinterpret_cast<const double *> (wkeys + shell * B.wkeys_stride) : nullptr);
                }
              else
                {
                   beta = in.chipx[i]; delta = in.chipy[i]; corr = in.pi[i];
-                  flags = hrma_phase_c (H, shell, energy, beta, delta, corr, x, p, rng);
+                  flags = hrma_phase_c (H, shell, energy, beta, delta, corr, x, p, rng,
+                                        wkeys ? reinterpret_cast<const double *> (wkeys + shell * B.wkeys_stride) : nullptr);
                }
           }
         d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = p.x; d[4] = p.y; d[5] = p.z;
@@ -965,7 +984,7 @@ void launch_source (const SourceArgs &a, cudaStream_t s)
    k0_source<<<n_tiles_of (a.n), kTile, 0, s>>> (a);
 }
 
-uint32_t stage_smem_bytes (int stage, uint32_t blob_bytes)
+uint32_t stage_smem_bytes (int stage, uint32_t blob_bytes, uint32_t seg2_bytes)
 {
    const uint32_t warps = kStageThreads / 32, base = (blob_bytes + 127u) & ~127u;
    const uint32_t hdr = ((uint32_t) sizeof (K1Blob) + 127u) & ~127u;
@@ -973,7 +992,7 @@ uint32_t stage_smem_bytes (int stage, uint32_t blob_bytes)
      {
       case 10: return hdr + warps * (uint32_t) sizeof (WarpQueue<K1Shape<0>::ND, K1Shape<0>::NU>);
       case 11: return base + warps * (uint32_t) sizeof (WarpQueue<K1Shape<1>::ND, K1Shape<1>::NU>);
-      case 12: return hdr + warps * (uint32_t) sizeof (WarpQueue<K1Shape<2>::ND, K1Shape<2>::NU>);
+      case 12: return hdr + ((seg2_bytes + 127u) & ~127u) + warps * (uint32_t) sizeof (WarpQueue<K1Shape<2>::ND, K1Shape<2>::NU>);
       case 13: return hdr + (kTile / 32) * (uint32_t) sizeof (WarpQueue<8, 5>);
       case 2: return base + warps * (uint32_t) sizeof (WarpQueue<6, 3>);
       case 3: return base + warps * (uint32_t) sizeof (WarpQueue<6, 6>) + (uint32_t) (kMaxGauss * kStageThreads * sizeof (float));
@@ -990,9 +1009,9 @@ static int occupancy_grid (K kernel, int num_sms, uint32_t smem_bytes)
    if (per_sm < 1) per_sm = 1;
    return per_sm * num_sms;
 }
-int stage_grid_size (int stage, int num_sms, uint32_t blob_bytes)
+int stage_grid_size (int stage, int num_sms, uint32_t blob_bytes, uint32_t seg2_bytes)
 {
-   const uint32_t smem = stage_smem_bytes (stage, blob_bytes);
+   const uint32_t smem = stage_smem_bytes (stage, blob_bytes, seg2_bytes);
    switch (stage)
      {
       case 10: return occupancy_grid (k1_hrma<0>, num_sms, smem);
@@ -1019,7 +1038,7 @@ void launch_source_hrma (const SourceArgs &a, const StageArgs &st, int grid, cud
 }
 void launch_hrma (const StageArgs &a, int phase, int grid, cudaStream_t s)
 {
-   const uint32_t smem = stage_smem_bytes (10 + phase, a.blob_bytes);
+   const uint32_t smem = stage_smem_bytes (10 + phase, a.blob_bytes, (phase == 2) ? a.seg2_bytes : 0u);
    switch (phase)
      {
       case 0: k1_hrma<0><<<grid, kStageThreads, smem, s>>> (a); break;

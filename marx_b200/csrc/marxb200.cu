@@ -69,6 +69,7 @@ struct marxb200_ctx
    double source_distance = 0.0;
    void *blob1 = nullptr, *blob2 = nullptr, *blob3 = nullptr;
    uint32_t blob1_bytes = 0, blob2_bytes = 0, blob3_bytes = 0;
+   uint32_t k1b_bytes = 0, k1c_seg2_off = 0, k1c_seg2_bytes = 0;
    int grid1[3] = {0, 0, 0}, grid2 = 0, grid3 = 0, grid01 = 0;
    bool detector_is_hrc = false;
    int first_mirror_kernel = 0;                  // 1: phase A already ran fused with the source (marxb200_trace)
@@ -342,7 +343,16 @@ extern "C" int marxb200_set_hrma (marxb200_ctx *c, const marxb200_hrma_desc *d)
    if (-1 == mx::build_hrma_blob (up, d, blob, err)) return fail ("marxb200_set_hrma: %s", err.c_str ());
    if (-1 == dev_upload (c, blob.data (), blob.size (), &c->blob1)) return -1;
    c->blob1_bytes = (uint32_t) blob.size ();
-   for (int ph = 0; ph < 3; ph++) c->grid1[ph] = stage_grid_size (10 + ph, c->num_sms, c->blob1_bytes);
+   {
+      // what each HRMA phase stages into shared memory (mx_kernels.cuh K1Blob): A the header; B everything up to and
+      // including the P-conic WFOLD search keys; C the header plus the H-conic keys as a second segment
+      const K1Blob *B = reinterpret_cast<const K1Blob *> (blob.data ());
+      c->k1b_bytes = B->off_wkeys_p + B->wkeys_bytes;
+      c->k1c_seg2_off = B->off_wkeys_h; c->k1c_seg2_bytes = B->wkeys_bytes;
+   }
+   c->grid1[0] = stage_grid_size (10, c->num_sms, c->blob1_bytes);
+   c->grid1[1] = stage_grid_size (11, c->num_sms, c->k1b_bytes);
+   c->grid1[2] = stage_grid_size (12, c->num_sms, c->blob1_bytes, c->k1c_seg2_bytes);
    c->grid01 = fused_source_grid (c->num_sms);
    c->have_hrma = true;
    return 0;
@@ -572,7 +582,9 @@ static int run_stage (marxb200_ctx *c, int stage)
         prof_begin (c);
         switch (stage)
           {
-           case 1: a.blob = c->blob1; a.blob_bytes = c->blob1_bytes; launch_hrma (a, k, c->grid1[k], c->stream); prof_mark (c, 4 + k); break;
+           case 1: a.blob = c->blob1; a.blob_bytes = (k == 1) ? c->k1b_bytes : c->blob1_bytes;
+                   a.seg2_off = c->k1c_seg2_off; a.seg2_bytes = (k == 2) ? c->k1c_seg2_bytes : 0;
+                   launch_hrma (a, k, c->grid1[k], c->stream); prof_mark (c, 4 + k); break;
            case 2: a.blob = c->blob2; a.blob_bytes = c->blob2_bytes; launch_grating (a, c->grid2, c->stream); prof_mark (c, 7); break;
            case 3: a.blob = c->blob3; a.blob_bytes = c->blob3_bytes;
                    if (c->detector_is_hrc) launch_hrc (a, c->grid3, c->stream); else launch_acis (a, c->grid3, c->stream);

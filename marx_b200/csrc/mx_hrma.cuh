@@ -177,19 +177,22 @@ MX_HD double wfold_theta (const WfoldDev &w, uint32_t k, double p)
    return (1.0 - delta_i) * t[i] + delta_i * t[i + 1];
 }
 // marx_wfold_table_interp, wfold.c:334-369
-MX_HD_BIG double wfold_interp (const WfoldDev &w, double energy, double sin_alpha, double r)
+MX_HD_BIG double wfold_interp (const WfoldDev &w, double energy, double sin_alpha, double r, const double *keys = nullptr)
 {
    if (w.num_arrays == 0) return 0.0;
    // (An early-out for r below every array's p_min -- 94 % of the draws -- was measured SLOWER: with 32 lanes per
    // warp some lane nearly always needs the full path, so the warp executes both.)
    if (w.num_arrays == 1) return wfold_theta (w, 0, r);
    double e_alpha = energy * sin_alpha;
-   // JDMbinary_search_d over the e_alpha column (stride 6 doubles)
+   // JDMbinary_search_d over the e_alpha column: a contiguous copy staged in shared memory (`keys`, k1_hrma<1|2>) or
+   // column 0 of the header rows in global memory (stride 6 doubles).  The search is a chain of 8 dependent loads.
+   const int ks = (keys != nullptr) ? 1 : 6;
+   if (keys == nullptr) keys = w.hdr;
    uint32_t n = w.num_arrays, n0 = 0, n1 = n, n2, i;
    while (n1 > n0 + 1)
      {
         n2 = (n0 + n1) / 2;
-        double v = w.hdr[6 * n2];
+        double v = keys[ks * n2];
         if (v >= e_alpha)
           {
              if (v == e_alpha) { n1 = n2; n0 = n2; break; }
@@ -198,13 +201,13 @@ MX_HD_BIG double wfold_interp (const WfoldDev &w, double energy, double sin_alph
         else n0 = n2;
      }
    if (n0 == n1) i = n1;                       // equality short-circuit
-   else if (e_alpha >= w.hdr[6 * n0]) i = n1;
+   else if (e_alpha >= keys[ks * n0]) i = n1;
    else i = n0;
    if (i == n) i--;
    if (i == 0) i++;
    double theta_0 = wfold_theta (w, i - 1, r);
    double theta_1 = wfold_theta (w, i, r);
-   double e0 = w.hdr[6 * (i - 1)], e1 = w.hdr[6 * i];
+   double e0 = keys[ks * (i - 1)], e1 = keys[ks * i];
    return theta_0 + (theta_1 - theta_0) * (e_alpha - e0) / (e1 - e0);
 }
 
@@ -264,7 +267,7 @@ MX_HD Vec3 conic_normal (const double *conic, const Vec3 &x)
 // reflect_from_conic after the intersection test, hrma.c:499-544.  returns 0 ok, -1 absorbed
 MX_HD int reflect_at_point (const HrmaDev &H, const double *conic, const WfoldDev &wfold, double scat_factor,
                             double blur, double energy, double beta, double delta, double corr,
-                            const Vec3 &x, Vec3 &p, Rng &rng)
+                            const Vec3 &x, Vec3 &p, Rng &rng, const double *wfold_keys = nullptr)
 {
    Vec3 normal = conic_normal (conic, x);
    if (H.use_blur) blur_normal (normal, blur, rng);
@@ -279,7 +282,7 @@ MX_HD int reflect_at_point (const HrmaDev &H, const double *conic, const WfoldDe
    if (H.use_wfold == 0) return 0;
    double sin_grazing = -p_dot_n;
    double r = rng.uniform ();
-   double delta_grazing = wfold_interp (wfold, energy, sin_grazing, r);
+   double delta_grazing = wfold_interp (wfold, energy, sin_grazing, r, wfold_keys);
    delta_grazing *= scat_factor;
    if (delta_grazing > kPI / 4) return -1;
    if (rng.uniform () < 0.5) delta_grazing = -delta_grazing;
@@ -363,12 +366,12 @@ MX_HD void hrma_optical_constants (const HrmaDev &H, const HrmaShellDev &h, cons
 
 // phase B.  In: x, p at the P intersection (OSAC-P frame).  Out: x, p at the H intersection (OSAC-H frame).
 MX_HD uint32_t hrma_phase_b (const HrmaDev &H, uint32_t shell, double energy, float beta, float delta, float corr_f32,
-                             Vec3 &x, Vec3 &p, Rng &rng)
+                             Vec3 &x, Vec3 &p, Rng &rng, const double *wfold_keys = nullptr)
 {
    const uint32_t VBLOCKED = 0x10, UNREFLECTED = 0x02;
    const HrmaShellDev &h = H.shell[shell];
    double corr = (H.num_opt != 0 && H.use_scale) ? sqrt ((double) corr_f32) : 1.0;
-   if (0 != reflect_at_point (H, h.conic_p, h.wfold_p, h.p_scat, h.p_blur, energy, beta, delta, corr, x, p, rng))
+   if (0 != reflect_at_point (H, h.conic_p, h.wfold_p, h.p_scat, h.p_blur, energy, beta, delta, corr, x, p, rng, wfold_keys))
      return UNREFLECTED;
    const Vec3 to_p = v_make (h.to_osac_p[0], h.to_osac_p[1], h.to_osac_p[2]);
    const Vec3 to_h = v_make (h.to_osac_h[0], h.to_osac_h[1], h.to_osac_h[2]);
@@ -390,12 +393,12 @@ MX_HD uint32_t hrma_phase_b (const HrmaDev &H, uint32_t shell, double energy, fl
 
 // phase C.  In: x, p at the H intersection (OSAC-H frame).  Out: x, p in MARX coordinates behind the mirror.
 MX_HD uint32_t hrma_phase_c (const HrmaDev &H, uint32_t shell, double energy, float beta, float delta, float corr_f32,
-                             Vec3 &x, Vec3 &p, Rng &rng)
+                             Vec3 &x, Vec3 &p, Rng &rng, const double *wfold_keys = nullptr)
 {
    const uint32_t VBLOCKED = 0x10, UNREFLECTED = 0x02;
    const HrmaShellDev &h = H.shell[shell];
    double corr = (H.num_opt != 0 && H.use_scale) ? sqrt ((double) corr_f32) : 1.0;
-   if (0 != reflect_at_point (H, h.conic_h, h.wfold_h, h.h_scat, h.h_blur, energy, beta, delta, corr, x, p, rng))
+   if (0 != reflect_at_point (H, h.conic_h, h.wfold_h, h.h_scat, h.h_blur, energy, beta, delta, corr, x, p, rng, wfold_keys))
      return UNREFLECTED;
    p = m3_mul (h.bwd_h, p);
    x = m3_mul (h.bwd_h, x);

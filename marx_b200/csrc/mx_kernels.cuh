@@ -40,6 +40,10 @@ struct alignas (16) K1Blob
 {
    HrmaDev H;
    uint32_t off_opt_e, off_opt_b, off_opt_d, off_corr_e, off_corr_f, total_bytes, pad0, pad1;
+   // contiguous copies of the WFOLD e_alpha search keys (column 0 of the header rows), one block of wkeys_stride bytes per
+   // shell: [.. off_wkeys_p ..] directly behind the correction tables (staged by k1_hrma<1> together with them),
+   // [.. off_wkeys_h ..] behind that (staged by k1_hrma<2> as a second segment).  0 bytes when WFOLD is off.
+   uint32_t off_wkeys_p, off_wkeys_h, wkeys_stride, wkeys_bytes;
 };
 struct alignas (16) K2Blob
 {
@@ -71,7 +75,8 @@ struct StageArgs
    int compact;                          // 1: order-preserving compaction into `out`; 0: in place, dead rays kept
    double source_distance;
    const void *blob;                     // K1Blob / K2Blob / K3Blob in global memory
-   uint32_t blob_bytes;
+   uint32_t blob_bytes;                  // bytes staged into shared memory from the start of the blob
+   uint32_t seg2_off, seg2_bytes;        // optional second staged segment (byte range of the blob), placed behind the first
 };
 
 struct SourceArgs
@@ -100,8 +105,8 @@ void launch_source_hrma (const SourceArgs &a, const StageArgs &st, int grid, cud
 void launch_grating (const StageArgs &a, int grid, cudaStream_t s);
 void launch_acis (const StageArgs &a, int grid, cudaStream_t s);
 void launch_hrc (const StageArgs &a, int grid, cudaStream_t s);
-int stage_grid_size (int stage, int num_sms, uint32_t blob_bytes);
-uint32_t stage_smem_bytes (int stage, uint32_t blob_bytes);
+int stage_grid_size (int stage, int num_sms, uint32_t blob_bytes, uint32_t seg2_bytes = 0);
+uint32_t stage_smem_bytes (int stage, uint32_t blob_bytes, uint32_t seg2_bytes = 0);
 
 // arrival-order restoration of an unordered live list (DESIGN.md "compaction"): bitmap over batch slots ->
 // popcount prefix -> rank (inverse permutation) -> gather

@@ -53,6 +53,16 @@ template <class Up> int build_hrma_blob (Up &up, const marxb200_hrma_desc *d, st
    const size_t off_opt_d = off; off = tb_align16 (off + 4 * (size_t) d->num_opt);
    const size_t off_corr_e = off; off = tb_align16 (off + 4 * ncorr_total);
    const size_t off_corr_f = off; off = tb_align16 (off + 4 * ncorr_total);
+   uint32_t max_arrays = 0;
+   if (d->use_wfold)
+     for (int k = 0; k < kNumShells; k++)
+       {
+          if (d->shells[k].p_wfold.num_arrays > max_arrays) max_arrays = d->shells[k].p_wfold.num_arrays;
+          if (d->shells[k].h_wfold.num_arrays > max_arrays) max_arrays = d->shells[k].h_wfold.num_arrays;
+       }
+   const size_t wkeys_stride = tb_align16 (8 * (size_t) max_arrays), wkeys_bytes = kNumShells * wkeys_stride;
+   const size_t off_wkeys_p = off; off += wkeys_bytes;
+   const size_t off_wkeys_h = off; off += wkeys_bytes;
    const size_t total = off;
    if (total > 200 * 1024) { err = "HRMA tables do not fit in shared memory"; return -1; }
    blob.assign (total, 0);
@@ -101,6 +111,15 @@ template <class Up> int build_hrma_blob (Up &up, const marxb200_hrma_desc *d, st
    if (!d->use_scale_factors || (ncorr_total == 0)) H.use_scale = 0;
    B->off_opt_e = (uint32_t) off_opt_e; B->off_opt_b = (uint32_t) off_opt_b; B->off_opt_d = (uint32_t) off_opt_d;
    B->off_corr_e = (uint32_t) off_corr_e; B->off_corr_f = (uint32_t) off_corr_f; B->total_bytes = (uint32_t) total;
+   B->off_wkeys_p = (uint32_t) off_wkeys_p; B->off_wkeys_h = (uint32_t) off_wkeys_h;
+   B->wkeys_stride = (uint32_t) wkeys_stride; B->wkeys_bytes = (uint32_t) wkeys_bytes;
+   if (d->use_wfold)
+     for (int k = 0; k < kNumShells; k++)
+       {
+          const marxb200_hrma_shell &s = d->shells[k];
+          if (s.p_wfold.num_arrays) memcpy (blob.data () + off_wkeys_p + k * wkeys_stride, s.p_wfold.e_alpha, 8 * (size_t) s.p_wfold.num_arrays);
+          if (s.h_wfold.num_arrays) memcpy (blob.data () + off_wkeys_h + k * wkeys_stride, s.h_wfold.e_alpha, 8 * (size_t) s.h_wfold.num_arrays);
+       }
    return 0;
 }
 
