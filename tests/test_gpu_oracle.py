@@ -33,9 +33,14 @@ def _gpu_all_stages(config, seed, first, n, compact):
     ("c3_hrc_i", 10, 0, 1 << 19),
 ])
 def test_cuda_matches_oracle_slot_by_slot(config, seed, first, n):
-    from tests.oracle_lib import Oracle
     if first >= (1 << 32):
         pytest.skip("the restatement keys draws on the 32-bit tag; 64-bit ray ids are covered by the invariance tests")
+    check_cuda_against_oracle(config, seed, first, n)
+
+
+def check_cuda_against_oracle(config, seed, first, n):
+    """config: a shipped calibration pack name or the path of one; all four stages, every ray slot"""
+    from tests.oracle_lib import Oracle
     o = Oracle(config, seed)
     ref, t_end, n_det = o.trace(first, n)
     got, counts = _gpu_all_stages(config, seed, first, n, compact=False)
@@ -57,6 +62,7 @@ def test_cuda_matches_oracle_slot_by_slot(config, seed, first, n):
     assert rel(got[0]["arrival_time"], ref[0]["arrival_time"]).max() <= 1e-12
     alive = (got[3]["flags"] & 0xFF) == 0
     assert int(alive.sum()) == n_det
+    return counts
 
 
 @pytest.mark.parametrize("config,seed,n", [("c2_hetg_acis_s", 31, 1 << 19), ("c1_acis_s", 32, 1 << 18), ("c4_beta_acis_i", 33, 1 << 18), ("c3_letg_hrc_s", 34, 1 << 19)])

@@ -75,6 +75,15 @@ CASES = [
     ("letg_acis_s", ["MinEnergy=0.3", "MaxEnergy=4.0", "GratingType=LETG", "DetectorType=ACIS-S", "DitherModel=INTERNAL"], 22, 0, 10000),
     ("letg_computed_efficiencies", ["MinEnergy=0.2", "MaxEnergy=2.0", "GratingType=LETG", "DetectorType=HRC-S", "DitherModel=INTERNAL",
                                     "UseGratingEffFiles=no"], 23, 0, 10000),
+    ("det_ideal", ["MinEnergy=0.5", "MaxEnergy=6.0", "GratingType=HETG", "DetectorType=ACIS-S", "DitherModel=INTERNAL", "DetIdeal=yes"], 31, 0, 8000),
+    ("no_blur_vignetting", ["MinEnergy=0.5", "MaxEnergy=6.0", "GratingType=NONE", "DetectorType=ACIS-S", "DitherModel=INTERNAL",
+                            "HRMA_Use_Blur=no", "HRMAVig=0.8"], 32, 0, 8000),
+    ("no_scale_factors_big_blurs", ["MinEnergy=1.0", "MaxEnergy=7.0", "GratingType=HETG", "DetectorType=ACIS-S", "DitherModel=INTERNAL",
+                                    "HRMA_Use_Scale_Factors=no", "AspectBlur=1.5", "P1Blur=0.6", "H6Blur=0.2"], 33, 65536, 8000),
+    ("roll_dither_off_axis", ["MinEnergy=0.5", "MaxEnergy=4.0", "GratingType=NONE", "DetectorType=ACIS-S", "DitherModel=INTERNAL",
+                              "DitherAmp_Roll=30", "DitherPeriod_Roll=700", "SourceRA=250.05", "Roll_Nom=17.0"], 34, 0, 8000),
+    ("hrc_i_letg", ["MinEnergy=0.1", "MaxEnergy=1.5", "GratingType=LETG", "DetectorType=HRC-I", "DitherModel=INTERNAL"], 37, 0, 8000),
+    ("detector_none", ["MinEnergy=0.5", "MaxEnergy=4.0", "GratingType=HETG", "DetectorType=NONE", "DitherModel=NONE"], 38, 0, 8000),
     ("sector_files_off_unit_order", ["MinEnergy=0.8", "MaxEnergy=3.0", "GratingType=HETG", "DetectorType=ACIS-S", "DitherModel=INTERNAL",
                                      "Use_HETG_Sector_Files=no"], 8, 1000, 10000),
 ]
