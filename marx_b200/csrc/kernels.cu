@@ -230,6 +230,9 @@ __global__ void __launch_bounds__ (kTile) k0_source (const __grid_constant__ Sou
    o.flags[i] = 0;
    o.order[i] = 0; o.sorders[i] = 0;      // stay 0 when GratingType=NONE (memset of source.c:287)
    o.dra[i] = dra; o.ddec[i] = ddec; o.droll[i] = droll;
+   const RayConst &rc = a.rc;           // slot == i
+   rc.energy[i] = energy; rc.time[i] = t; rc.ray[i] = a.first_ray + i;
+   rc.dra[i] = dra; rc.ddec[i] = ddec; rc.droll[i] = droll;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -315,16 +318,6 @@ __device__ __forceinline__ void run_stage (const StageArgs &a, WarpQueue<ND, NU>
    if (a.compact && (count > 0)) flush (count);
 }
 
-// columns a stage does not touch, gathered from the input list when a queue row is flushed
-__device__ __forceinline__ void copy_carried (const PhotonSoA &in, uint32_t src, const PhotonSoA &out, unsigned long long j)
-{
-   out.energy[j] = in.energy[src];
-   out.time[j] = in.time[src];
-   out.ray[j] = in.ray[src];
-   out.slot[j] = in.slot[src];
-   out.dra[j] = in.dra[src]; out.ddec[j] = in.ddec[src]; out.droll[j] = in.droll[src];
-}
-
 template <int ND, int NU>
 __device__ __forceinline__ WarpQueue<ND, NU> &my_queue (unsigned char *smem, uint32_t blob_bytes)
 {
@@ -369,13 +362,14 @@ __global__ void __launch_bounds__ (kStageThreads, 3) k1_hrma (const __grid_const
         uint32_t shell = 0, flags;
         float beta = 0.f, delta = 1.f, corr = 1.f;
         Rng rng;
-        rng.init (a.seed, in.ray[i], MARXB200_STAGE_MIRROR);
+        const uint32_t slot = in.slot[i];
+        rng.init (a.seed, a.rc.ray[slot], MARXB200_STAGE_MIRROR);
         if (PHASE == 0)
           flags = hrma_phase_a (H, a.source_distance, x, p, shell, rng);
         else
           {
              x = v_make (in.x0[i], in.x1[i], in.x2[i]);
-             const double energy = in.energy[i];
+             const double energy = a.rc.energy[slot];
              shell = in.shell[i];
              const int st = in.pha[i];
              rng.resume ((uint32_t) (st & 0x3FFF), (st & 0x4000) ? 1 : 0, (st & 0x4000) ? in.aux[i] : 0.0);
@@ -399,7 +393,7 @@ __global__ void __launch_bounds__ (kStageThreads, 3) k1_hrma (const __grid_const
                }
           }
         d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = p.x; d[4] = p.y; d[5] = p.z;
-        u[0] = (uint32_t) i;
+        u[0] = slot;
         u[1] = shell | (((rng.draw & 0x3FFFu) | (rng.have_spare ? 0x4000u : 0u)) << 8);
         if (PHASE == 1)
           {
@@ -435,7 +429,7 @@ __global__ void __launch_bounds__ (kStageThreads, 3) k1_hrma (const __grid_const
 #pragma unroll
         for (int k = 0; k < NU; k++) u[k] = q.u[k][pos];
         write_row (j, d, u, 0);
-        copy_carried (in, u[0], out, j);
+        out.slot[j] = u[0];
      };
    auto in_place = [&] (unsigned long long i, const double *d, const uint32_t *u, uint32_t flags) { write_row (i, d, u, flags); };
    run_stage<ND, NU> (a, q, trace, flush_entry, in_place);
@@ -463,11 +457,12 @@ __global__ void __launch_bounds__ (kStageThreads, 3) k2_grating (const __grid_co
         int order = 0;
         uint32_t sorders = 0;
         Rng rng;
-        rng.init (a.seed, in.ray[i], MARXB200_STAGE_GRATING);
-        uint32_t flags = grating_diffract (G, in.shell[i], in.energy[i], x, p, order, sorders, rng);
+        const uint32_t slot = in.slot[i], shell = in.shell[i];
+        rng.init (a.seed, a.rc.ray[slot], MARXB200_STAGE_GRATING);
+        uint32_t flags = grating_diffract (G, shell, a.rc.energy[slot], x, p, order, sorders, rng);
         d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = p.x; d[4] = p.y; d[5] = p.z;
-        u[0] = (uint32_t) i;
-        u[1] = (uint32_t) (order & 0xFF);
+        u[0] = slot;
+        u[1] = (uint32_t) (order & 0xFF) | (shell << 8);
         u[2] = sorders;
         return flags;
      };
@@ -487,8 +482,8 @@ __global__ void __launch_bounds__ (kStageThreads, 3) k2_grating (const __grid_co
 #pragma unroll
         for (int k = 0; k < NU; k++) u[k] = q.u[k][pos];
         write_row (j, d, u, 0);
-        copy_carried (in, u[0], out, j);
-        out.shell[j] = in.shell[u[0]];
+        out.slot[j] = u[0];
+        out.shell[j] = (uint8_t) (u[1] >> 8);
      };
    auto in_place = [&] (unsigned long long i, const double *d, const uint32_t *u, uint32_t flags) { write_row (i, d, u, flags); };
    run_stage<ND, NU> (a, q, trace, flush_entry, in_place);
@@ -516,8 +511,9 @@ __global__ void __launch_bounds__ (kStageThreads, MX_K3_MINBLOCKS) k3_acis (cons
         Vec3 x = v_make (in.x0[i], in.x1[i], in.x2[i]), p = v_make (in.p0[i], in.p1[i], in.p2[i]);
         int ccd = -1; float chipx = 0, chipy = 0, pi = 0; int16_t pha = 0;
         Rng rng;
-        rng.init (a.seed, in.ray[i], MARXB200_STAGE_DETECTOR);
-        uint32_t flags = acis_detect (A, in.energy[i], in.time[i], x, p, ccd, chipx, chipy, pha, pi, rng, fef_cum, kStageThreads);
+        const uint32_t slot = in.slot[i];
+        rng.init (a.seed, a.rc.ray[slot], MARXB200_STAGE_DETECTOR);
+        uint32_t flags = acis_detect (A, a.rc.energy[slot], a.rc.time[slot], x, p, ccd, chipx, chipy, pha, pi, rng, fef_cum, kStageThreads);
         d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = p.x; d[4] = p.y; d[5] = p.z;
         u[0] = (uint32_t) i;
         u[1] = flags;
@@ -543,7 +539,7 @@ __global__ void __launch_bounds__ (kStageThreads, MX_K3_MINBLOCKS) k3_acis (cons
 #pragma unroll
         for (int k = 0; k < NU; k++) u[k] = q.u[k][pos];
         write_row (j, d, u);
-        copy_carried (in, u[0], out, j);
+        out.slot[j] = in.slot[u[0]];          // ids produced by earlier stages travel with the list
         out.shell[j] = in.shell[u[0]];
         out.order[j] = in.order[u[0]];
         out.sorders[j] = in.sorders[u[0]];
@@ -568,8 +564,9 @@ __global__ void __launch_bounds__ (kStageThreads) k3_hrc (const __grid_constant_
         Vec3 x = v_make (in.x0[i], in.x1[i], in.x2[i]), p = v_make (in.p0[i], in.p1[i], in.p2[i]);
         int ccd = -1, region = 0; float ypix = 0, zpix = 0, upix = 0, vpix = 0; int16_t pha = 0;
         Rng rng;
-        rng.init (a.seed, in.ray[i], MARXB200_STAGE_DETECTOR);
-        uint32_t flags = hrc_s_detect (D, in.energy[i], x, p, ccd, region, ypix, zpix, upix, vpix, pha, rng);
+        const uint32_t slot = in.slot[i];
+        rng.init (a.seed, a.rc.ray[slot], MARXB200_STAGE_DETECTOR);
+        uint32_t flags = hrc_s_detect (D, a.rc.energy[slot], x, p, ccd, region, ypix, zpix, upix, vpix, pha, rng);
         d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = p.x; d[4] = p.y; d[5] = p.z;
         u[0] = (uint32_t) i;
         u[1] = flags;
@@ -598,7 +595,7 @@ __global__ void __launch_bounds__ (kStageThreads) k3_hrc (const __grid_constant_
 #pragma unroll
         for (int k = 0; k < NU; k++) u[k] = q.u[k][pos];
         write_row (j, d, u);
-        copy_carried (in, u[0], out, j);
+        out.slot[j] = in.slot[u[0]];          // ids produced by earlier stages travel with the list
         out.shell[j] = in.shell[u[0]];
         out.order[j] = in.order[u[0]];
         out.sorders[j] = in.sorders[u[0]];
@@ -615,7 +612,7 @@ __global__ void __launch_bounds__ (kStageThreads) k3_hrc (const __grid_constant_
 // warp-private re-packing queue straight into the list that k1_hrma<1> consumes.
 __global__ void __launch_bounds__ (kTile, 3) k01_source_hrma (const __grid_constant__ SourceArgs a, const __grid_constant__ StageArgs st)
 {
-   constexpr int ND = 8, NU = 5;
+   constexpr int ND = 6, NU = 2;
    extern __shared__ __align__ (128) unsigned char smem[];
    __shared__ __align__ (8) unsigned long long bar;
    stage_blob (smem, st.blob, (uint32_t) sizeof (K1Blob), &bar);
@@ -636,11 +633,9 @@ __global__ void __launch_bounds__ (kTile, 3) k01_source_hrma (const __grid_const
              const unsigned long long j = base + lane;
              out.x0[j] = q.d[0][pos]; out.x1[j] = q.d[1][pos]; out.x2[j] = q.d[2][pos];
              out.p0[j] = q.d[3][pos]; out.p1[j] = q.d[4][pos]; out.p2[j] = q.d[5][pos];
-             out.energy[j] = q.d[6][pos]; out.time[j] = q.d[7][pos];
              const uint32_t slot = q.u[0][pos], pk = q.u[1][pos];
-             out.slot[j] = slot; out.ray[j] = a.first_ray + slot;
+             out.slot[j] = slot;
              out.shell[j] = (uint8_t) (pk & 0xFFu); out.pha[j] = (int16_t) (pk >> 8);
-             out.dra[j] = __uint_as_float (q.u[2][pos]); out.ddec[j] = __uint_as_float (q.u[3][pos]); out.droll[j] = __uint_as_float (q.u[4][pos]);
              out.flags[j] = 0; out.order[j] = 0; out.sorders[j] = 0;
           }
         head = (head + n_flush) & (kQueueCap - 1);
@@ -676,10 +671,12 @@ __global__ void __launch_bounds__ (kTile, 3) k01_source_hrma (const __grid_const
              const uint32_t pos = (head + count + __popc (ballot & ((1u << lane) - 1u))) & (kQueueCap - 1);
              q.d[0][pos] = x.x; q.d[1][pos] = x.y; q.d[2][pos] = x.z;
              q.d[3][pos] = p.x; q.d[4][pos] = p.y; q.d[5][pos] = p.z;
-             q.d[6][pos] = energy; q.d[7][pos] = t;
              q.u[0][pos] = (uint32_t) i;
              q.u[1][pos] = shell | ((rng.draw & 0x3FFFu) << 8);
-             q.u[2][pos] = __float_as_uint (dra); q.u[3][pos] = __float_as_uint (ddec); q.u[4][pos] = __float_as_uint (droll);
+             // the per-ray constants go straight to their slot (slot == i: the surviving lanes of a warp store into
+             // one 256-byte span per column)
+             a.rc.energy[i] = energy; a.rc.time[i] = t; a.rc.ray[i] = a.first_ray + i;
+             a.rc.dra[i] = dra; a.rc.ddec[i] = ddec; a.rc.droll[i] = droll;
           }
         count += __popc (ballot);
         __syncwarp ();
@@ -760,13 +757,14 @@ __global__ void __launch_bounds__ (256) order_gather (OrderArgs a)
    const PhotonSoA &in = a.in, &out = a.out;
    for (unsigned long long j = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (unsigned long long) gridDim.x * blockDim.x)
      {
-        const uint32_t s = a.perm[j];
-        out.energy[j] = in.energy[s];
+        const uint32_t s = a.perm[j], key = in.slot[s];
+        const RayConst &rc = a.rc;
+        out.energy[j] = rc.energy[key];
         out.x0[j] = in.x0[s]; out.x1[j] = in.x1[s]; out.x2[j] = in.x2[s];
         out.p0[j] = in.p0[s]; out.p1[j] = in.p1[s]; out.p2[j] = in.p2[s];
-        out.time[j] = in.time[s]; out.aux[j] = in.aux[s];
-        out.ray[j] = in.ray[s]; out.slot[j] = in.slot[s]; out.flags[j] = in.flags[s];
-        out.dra[j] = in.dra[s]; out.ddec[j] = in.ddec[s]; out.droll[j] = in.droll[s];
+        out.time[j] = rc.time[key]; out.aux[j] = in.aux[s];
+        out.ray[j] = rc.ray[key]; out.slot[j] = key; out.flags[j] = in.flags[s];
+        out.dra[j] = rc.dra[key]; out.ddec[j] = rc.ddec[key]; out.droll[j] = rc.droll[key];
         out.chipx[j] = in.chipx[s]; out.chipy[j] = in.chipy[s]; out.pi[j] = in.pi[s];
         out.pha[j] = in.pha[s]; out.shell[j] = in.shell[s]; out.order[j] = in.order[s]; out.ccd[j] = in.ccd[s];
         out.upix[j] = in.upix[s]; out.vpix[j] = in.vpix[s]; out.sorders[j] = in.sorders[s]; out.region[j] = in.region[s];
@@ -822,7 +820,7 @@ __global__ void __launch_bounds__ (256) soa_to_aos (PhotonSoA in, const unsigned
 }
 
 __global__ void __launch_bounds__ (256) aos_to_soa (const marxb200_photon_attr *aos, const uint64_t *ray_ids, uint64_t n,
-                                                    PhotonSoA out, double start_time)
+                                                    PhotonSoA out, RayConst rc, double start_time)
 {
    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x)
      {
@@ -839,6 +837,8 @@ __global__ void __launch_bounds__ (256) aos_to_soa (const marxb200_photon_attr *
         out.slot[i] = (uint32_t) i;
         out.flags[i] = r.flags;
         out.dra[i] = r.dither_ra; out.ddec[i] = r.dither_dec; out.droll[i] = r.dither_roll;
+        rc.energy[i] = r.energy; rc.time[i] = r.arrival_time + start_time; rc.ray[i] = ray_ids ? ray_ids[i] : (uint64_t) r.tag;
+        rc.dra[i] = r.dither_ra; rc.ddec[i] = r.dither_dec; rc.droll[i] = r.dither_roll;
         out.chipx[i] = r.y_pixel; out.chipy[i] = r.z_pixel; out.pi[i] = r.pi;
         out.pha[i] = r.pulse_height;
         out.shell[i] = (uint8_t) r.mirror_shell;
@@ -999,7 +999,7 @@ uint32_t stage_smem_bytes (int stage, uint32_t blob_bytes, uint32_t seg2_bytes)
       case 10: return hdr + warps * (uint32_t) sizeof (WarpQueue<K1Shape<0>::ND, K1Shape<0>::NU>);
       case 11: return base + warps * (uint32_t) sizeof (WarpQueue<K1Shape<1>::ND, K1Shape<1>::NU>);
       case 12: return hdr + ((seg2_bytes + 127u) & ~127u) + warps * (uint32_t) sizeof (WarpQueue<K1Shape<2>::ND, K1Shape<2>::NU>);
-      case 13: return hdr + (kTile / 32) * (uint32_t) sizeof (WarpQueue<8, 5>);
+      case 13: return hdr + (kTile / 32) * (uint32_t) sizeof (WarpQueue<6, 2>);
       case 2: return base + warps * (uint32_t) sizeof (WarpQueue<6, 3>);
       case 3: return base + warps * (uint32_t) sizeof (WarpQueue<6, 6>) + (uint32_t) (kMaxGauss * kStageThreads * sizeof (float));
       case 4: return base + warps * (uint32_t) sizeof (WarpQueue<6, 7>);
@@ -1063,12 +1063,12 @@ void launch_soa_to_aos (const PhotonSoA &in, const unsigned long long *n, uint64
    unsigned int grid = (unsigned int) min ((uint64_t) 148 * 8, (max_n + 255) / 256);
    soa_to_aos<<<grid, 256, 0, s>>> (in, n, max_n, (marxb200_photon_attr *) aos, dev_start_time);
 }
-void launch_aos_to_soa (const void *aos, const uint64_t *ray_ids, uint64_t n, const PhotonSoA &out, double start_time,
-                        cudaStream_t s)
+void launch_aos_to_soa (const void *aos, const uint64_t *ray_ids, uint64_t n, const PhotonSoA &out, const RayConst &rc,
+                        double start_time, cudaStream_t s)
 {
    if (n == 0) return;
    unsigned int grid = (unsigned int) min ((uint64_t) 148 * 8, (n + 255) / 256);
-   aos_to_soa<<<grid, 256, 0, s>>> ((const marxb200_photon_attr *) aos, ray_ids, n, out, start_time);
+   aos_to_soa<<<grid, 256, 0, s>>> ((const marxb200_photon_attr *) aos, ray_ids, n, out, rc, start_time);
 }
 
 }  // namespace mx

@@ -49,6 +49,8 @@ struct marxb200_ctx
    uint64_t capacity = 0;
    void *slab[2] = {nullptr, nullptr};
    PhotonSoA buf[2];
+   void *rc_slab = nullptr;
+   RayConst rc;                                  // per-ray constants, indexed by batch slot (mx_kernels.cuh)
    int cur = 0;
 
    // device scalars: counts[0..3] + ticket + total_time
@@ -222,6 +224,7 @@ extern "C" int marxb200_destroy (marxb200_ctx *c)
    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy (e);
    for (void *p : c->allocs) cudaFree (p);
    for (int i = 0; i < 2; i++) if (c->slab[i]) cudaFree (c->slab[i]);
+   if (c->rc_slab) cudaFree (c->rc_slab);
    cudaFree (c->d_counts); cudaFree (c->d_ticket); cudaFree (c->d_times);
    if (c->d_bitmap) cudaFree (c->d_bitmap);
    if (c->d_word_prefix) cudaFree (c->d_word_prefix);
@@ -458,6 +461,16 @@ extern "C" int marxb200_alloc_photons (marxb200_ctx *c, uint64_t max_photons)
         CUDA_OK (cudaMemsetAsync (c->slab[i], 0, bytes, c->stream));
         carve (c->buf[i], (unsigned char *) c->slab[i], max_photons);
      }
+   {
+      // per-ray constants: energy, time (f64), ray (u64), dither ra/dec/roll (f32), each column 256-byte aligned
+      if (c->rc_slab) { cudaFree (c->rc_slab); c->rc_slab = nullptr; }
+      const size_t c8 = (8 * (size_t) max_photons + 255) & ~(size_t) 255, c4 = (4 * (size_t) max_photons + 255) & ~(size_t) 255;
+      CUDA_OK (cudaMalloc (&c->rc_slab, 3 * c8 + 3 * c4));
+      CUDA_OK (cudaMemsetAsync (c->rc_slab, 0, 3 * c8 + 3 * c4, c->stream));
+      unsigned char *b = (unsigned char *) c->rc_slab;
+      c->rc.energy = (double *) b; c->rc.time = (double *) (b + c8); c->rc.ray = (uint64_t *) (b + 2 * c8);
+      c->rc.dra = (float *) (b + 3 * c8); c->rc.ddec = (float *) (b + 3 * c8 + c4); c->rc.droll = (float *) (b + 3 * c8 + 2 * c4);
+   }
    uint64_t n_tiles = (max_photons + kTile - 1) / kTile + 1;
    uint64_t n_super = (n_tiles + kSuperTile - 1) / kSuperTile + 1;
    c->n_words = max_photons / 32 + 1;
@@ -480,6 +493,7 @@ extern "C" int marxb200_alloc_photons (marxb200_ctx *c, uint64_t max_photons)
 static void fill_source_args (marxb200_ctx *c, SourceArgs &a, uint64_t first_ray, uint64_t n, double time_base)
 {
    a.out = c->buf[0];
+   a.rc = c->rc;
    a.first_ray = first_ray; a.n = n; a.seed = c->seed;
    a.S = c->S; a.D = c->D;
    a.time_base = (time_base >= 0.0) ? time_base : 0.0;
@@ -558,6 +572,7 @@ static int run_stage (marxb200_ctx *c, int stage)
    a.seed = c->seed;
    a.compact = c->compact;
    a.source_distance = c->source_distance;
+   a.rc = c->rc;
    // the mirror stage runs as three kernels (HRMA phases A, B, C, mx_hrma.cuh), each re-packing its survivors
    const int n_kernels = (stage == 1) ? 3 : 1;
    const int k_first = (stage == 1) ? c->first_mirror_kernel : 0;
@@ -607,7 +622,7 @@ static int ensure_order (marxb200_ctx *c)
 {
    if (c->ordered || (c->stage_done <= 0)) { c->ordered = true; return 0; }
    OrderArgs o;
-   o.in = c->buf[c->cur]; o.out = c->buf[1 - c->cur];
+   o.in = c->buf[c->cur]; o.out = c->buf[1 - c->cur]; o.rc = c->rc;
    o.n_live = c->d_counts + c->stage_done;
    o.n_slots = c->n_generated;
    o.bitmap = c->d_bitmap; o.word_prefix = c->d_word_prefix; o.block_prefix = c->d_block_prefix; o.perm = c->d_perm;
@@ -817,7 +832,7 @@ extern "C" int marxb200_upload (marxb200_ctx *c, const marxb200_photon_attr *in,
      }
    c->cur = 0;
    CUDA_OK (cudaMemsetAsync (c->d_times, 0, sizeof (double), c->stream));   // uploaded arrival times are absolute
-   launch_aos_to_soa (c->d_aos, d_ids, n, c->buf[0], 0.0, c->stream);
+   launch_aos_to_soa (c->d_aos, d_ids, n, c->buf[0], c->rc, 0.0, c->stream);
    c->launches += 1;
    unsigned long long nn = n;
    CUDA_OK (cudaMemcpyAsync (c->d_counts + 0, &nn, sizeof (nn), cudaMemcpyHostToDevice, c->stream));

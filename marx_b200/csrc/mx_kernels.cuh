@@ -35,6 +35,18 @@ struct PhotonSoA
    int8_t *order, *ccd, *region;
 };
 
+// Per-ray quantities that no stage changes after the source has set them.  They are written ONCE, at the ray's batch
+// slot, and read through the `slot` key of a list entry; the compacting stage kernels therefore move only what they
+// produce (x, p, flags, ids) plus the 4-byte slot.  (The first version carried these 36 bytes from list to list in every
+// stage: 7 dependent gathers + 7 stores per survivor per stage, 13 % of k1_hrma<1>'s stall samples.)  The arrival-order
+// restoration materialises them into the list's own columns, which is what the host boundary reads.
+struct RayConst
+{
+   double *energy, *time;
+   uint64_t *ray;
+   float *dra, *ddec, *droll;
+};
+
 // Blob staged into shared memory by K1 with one TMA bulk copy.
 struct alignas (16) K1Blob
 {
@@ -67,6 +79,7 @@ static_assert (sizeof (K1Blob) % 16 == 0, "TMA bulk copies move multiples of 16 
 struct StageArgs
 {
    PhotonSoA in, out;
+   RayConst rc;                          // indexed by in.slot[i]
    const unsigned long long *n_in;       // device: number of input slots
    unsigned long long *n_out;            // device: number of output photons; compact: zeroed before launch, grown by atomics
    unsigned long long *ticket;           // device: chunk ticket counter (zeroed before launch)
@@ -82,6 +95,7 @@ struct StageArgs
 struct SourceArgs
 {
    PhotonSoA out;
+   RayConst rc;                          // written at the batch slot of every generated (k0_source) / surviving (k01) ray
    uint64_t first_ray, n;
    uint64_t seed;
    SourceDev S;
@@ -113,6 +127,7 @@ uint32_t stage_smem_bytes (int stage, uint32_t blob_bytes, uint32_t seg2_bytes =
 struct OrderArgs
 {
    PhotonSoA in, out;
+   RayConst rc;
    const unsigned long long *n_live;
    uint64_t n_slots;                     // slots of the batch (= generated rays)
    uint32_t *bitmap;                     // [n_slots/32 + 1], zeroed before launch
@@ -125,8 +140,8 @@ void launch_restore_order (const OrderArgs &a, int num_sms, cudaStream_t s, int 
 // host boundary helpers (AoS <-> SoA); `aos` is a device buffer of 136-byte records
 void launch_soa_to_aos (const PhotonSoA &in, const unsigned long long *n, uint64_t max_n, void *aos,
                         const double *dev_start_time, cudaStream_t s);
-void launch_aos_to_soa (const void *aos, const uint64_t *ray_ids, uint64_t n, const PhotonSoA &out, double start_time,
-                        cudaStream_t s);
+void launch_aos_to_soa (const void *aos, const uint64_t *ray_ids, uint64_t n, const PhotonSoA &out, const RayConst &rc,
+                        double start_time, cudaStream_t s);
 
 // bulk egress in the reference's column-file format (marxio.c:292-322): which packed columns to produce
 enum EgressKind
