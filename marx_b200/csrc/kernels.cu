@@ -64,6 +64,7 @@ __device__ __forceinline__ unsigned long long ld_relaxed (const unsigned long lo
    asm volatile ("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
    return v;
 }
+__device__ __forceinline__ void prefetch_l2 (const void *p) { asm volatile ("prefetch.global.L2 [%0];" :: "l"(p)); }
 __device__ __forceinline__ void st_relaxed (unsigned long long *p, unsigned long long v)
 {
    asm volatile ("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
@@ -290,6 +291,16 @@ __device__ __forceinline__ void run_stage (const StageArgs &a, WarpQueue<ND, NU>
              const unsigned long long i = base + lane;
              bool active = i < n_in;
              if (active && !a.compact) active = ((a.in.flags[i] & 0xFFu) == 0);
+#ifdef MX_PREFETCH
+             // the next tile of this chunk: pull its position/direction/slot columns towards L2 while this one is traced
+             if ((t + 1 < a.chunk_tiles) && (i + kWarpTile < n_in))
+               {
+                  const unsigned long long k = i + kWarpTile;
+                  prefetch_l2 (a.in.x0 + k); prefetch_l2 (a.in.x1 + k); prefetch_l2 (a.in.x2 + k);
+                  prefetch_l2 (a.in.p0 + k); prefetch_l2 (a.in.p1 + k); prefetch_l2 (a.in.p2 + k);
+                  prefetch_l2 (a.in.slot + k);
+               }
+#endif
              double d[ND]; uint32_t u[NU];
              uint32_t flags = 0xFFu;
              if (active) flags = trace (i, d, u);
@@ -495,7 +506,7 @@ __global__ void __launch_bounds__ (kStageThreads, 3) k2_grating (const __grid_co
 #endif
 __global__ void __launch_bounds__ (kStageThreads, MX_K3_MINBLOCKS) k3_acis (const __grid_constant__ StageArgs a)
 {
-   constexpr int ND = 6, NU = 6;
+   constexpr int ND = 6, NU = 7;
    extern __shared__ __align__ (128) unsigned char smem[];
    __shared__ __align__ (8) unsigned long long bar;
    stage_blob (smem, a.blob, a.blob_bytes, &bar);
@@ -515,17 +526,20 @@ __global__ void __launch_bounds__ (kStageThreads, MX_K3_MINBLOCKS) k3_acis (cons
         rng.init (a.seed, a.rc.ray[slot], MARXB200_STAGE_DETECTOR);
         uint32_t flags = acis_detect (A, a.rc.energy[slot], a.rc.time[slot], x, p, ccd, chipx, chipy, pha, pi, rng, fef_cum, kStageThreads);
         d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = p.x; d[4] = p.y; d[5] = p.z;
-        u[0] = (uint32_t) i;
-        u[1] = flags;
+        // ids produced by the earlier stages travel through the queue (coalesced loads here instead of dependent
+        // gathers when a row is flushed): flags use bits 0..9, shell and order ride in the upper half
+        u[0] = slot;
+        u[1] = flags | ((uint32_t) in.shell[i] << 16) | (((uint32_t) (uint8_t) in.order[i]) << 24);
         u[2] = ((uint32_t) (ccd & 0xFF)) | (((uint32_t) (uint16_t) pha) << 8);
         u[3] = __float_as_uint (chipx); u[4] = __float_as_uint (chipy); u[5] = __float_as_uint (pi);
+        u[6] = in.sorders[i];
         return flags;
      };
    auto write_row = [&] (unsigned long long j, const double *d, const uint32_t *u)
      {
         out.x0[j] = d[0]; out.x1[j] = d[1]; out.x2[j] = d[2];
         out.p0[j] = d[3]; out.p1[j] = d[4]; out.p2[j] = d[5];
-        out.flags[j] = u[1];
+        out.flags[j] = u[1] & 0xFFFFu;
         out.ccd[j] = (int8_t) (u[2] & 0xFFu);
         out.pha[j] = (int16_t) (uint16_t) (u[2] >> 8);
         out.region[j] = 0; out.upix[j] = 0.f; out.vpix[j] = 0.f;
@@ -539,10 +553,10 @@ __global__ void __launch_bounds__ (kStageThreads, MX_K3_MINBLOCKS) k3_acis (cons
 #pragma unroll
         for (int k = 0; k < NU; k++) u[k] = q.u[k][pos];
         write_row (j, d, u);
-        out.slot[j] = in.slot[u[0]];          // ids produced by earlier stages travel with the list
-        out.shell[j] = in.shell[u[0]];
-        out.order[j] = in.order[u[0]];
-        out.sorders[j] = in.sorders[u[0]];
+        out.slot[j] = u[0];
+        out.shell[j] = (uint8_t) ((u[1] >> 16) & 0xFFu);
+        out.order[j] = (int8_t) (u[1] >> 24);
+        out.sorders[j] = u[NU - 1];
      };
    auto in_place = [&] (unsigned long long i, const double *d, const uint32_t *u, uint32_t) { write_row (i, d, u); };
    run_stage<ND, NU> (a, q, trace, flush_entry, in_place);
@@ -551,7 +565,7 @@ __global__ void __launch_bounds__ (kStageThreads, MX_K3_MINBLOCKS) k3_acis (cons
 // K3 (HRC-S) -----------------------------------------------------------------------------------
 __global__ void __launch_bounds__ (kStageThreads) k3_hrc (const __grid_constant__ StageArgs a)
 {
-   constexpr int ND = 6, NU = 7;
+   constexpr int ND = 6, NU = 8;
    extern __shared__ __align__ (128) unsigned char smem[];
    __shared__ __align__ (8) unsigned long long bar;
    stage_blob (smem, a.blob, a.blob_bytes, &bar);
@@ -568,18 +582,19 @@ __global__ void __launch_bounds__ (kStageThreads) k3_hrc (const __grid_constant_
         rng.init (a.seed, a.rc.ray[slot], MARXB200_STAGE_DETECTOR);
         uint32_t flags = hrc_s_detect (D, a.rc.energy[slot], x, p, ccd, region, ypix, zpix, upix, vpix, pha, rng);
         d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = p.x; d[4] = p.y; d[5] = p.z;
-        u[0] = (uint32_t) i;
-        u[1] = flags;
+        u[0] = slot;
+        u[1] = flags | ((uint32_t) in.shell[i] << 16) | (((uint32_t) (uint8_t) in.order[i]) << 24);
         u[2] = ((uint32_t) (ccd & 0xFF)) | (((uint32_t) (uint16_t) pha) << 8) | (((uint32_t) (region & 0xFF)) << 24);
         u[3] = __float_as_uint (ypix); u[4] = __float_as_uint (zpix);
         u[5] = __float_as_uint (upix); u[6] = __float_as_uint (vpix);
+        u[7] = in.sorders[i];
         return flags;
      };
    auto write_row = [&] (unsigned long long j, const double *d, const uint32_t *u)
      {
         out.x0[j] = d[0]; out.x1[j] = d[1]; out.x2[j] = d[2];
         out.p0[j] = d[3]; out.p1[j] = d[4]; out.p2[j] = d[5];
-        out.flags[j] = u[1];
+        out.flags[j] = u[1] & 0xFFFFu;
         out.ccd[j] = (int8_t) (u[2] & 0xFFu);
         out.pha[j] = (int16_t) (uint16_t) ((u[2] >> 8) & 0xFFFFu);
         out.region[j] = (int8_t) (u[2] >> 24);
@@ -595,10 +610,10 @@ __global__ void __launch_bounds__ (kStageThreads) k3_hrc (const __grid_constant_
 #pragma unroll
         for (int k = 0; k < NU; k++) u[k] = q.u[k][pos];
         write_row (j, d, u);
-        out.slot[j] = in.slot[u[0]];          // ids produced by earlier stages travel with the list
-        out.shell[j] = in.shell[u[0]];
-        out.order[j] = in.order[u[0]];
-        out.sorders[j] = in.sorders[u[0]];
+        out.slot[j] = u[0];
+        out.shell[j] = (uint8_t) ((u[1] >> 16) & 0xFFu);
+        out.order[j] = (int8_t) (u[1] >> 24);
+        out.sorders[j] = u[NU - 1];
      };
    auto in_place = [&] (unsigned long long i, const double *d, const uint32_t *u, uint32_t) { write_row (i, d, u); };
    run_stage<ND, NU> (a, q, trace, flush_entry, in_place);
@@ -1001,8 +1016,8 @@ uint32_t stage_smem_bytes (int stage, uint32_t blob_bytes, uint32_t seg2_bytes)
       case 12: return hdr + ((seg2_bytes + 127u) & ~127u) + warps * (uint32_t) sizeof (WarpQueue<K1Shape<2>::ND, K1Shape<2>::NU>);
       case 13: return hdr + (kTile / 32) * (uint32_t) sizeof (WarpQueue<6, 2>);
       case 2: return base + warps * (uint32_t) sizeof (WarpQueue<6, 3>);
-      case 3: return base + warps * (uint32_t) sizeof (WarpQueue<6, 6>) + (uint32_t) (kMaxGauss * kStageThreads * sizeof (float));
-      case 4: return base + warps * (uint32_t) sizeof (WarpQueue<6, 7>);
+      case 3: return base + warps * (uint32_t) sizeof (WarpQueue<6, 7>) + (uint32_t) (kMaxGauss * kStageThreads * sizeof (float));
+      case 4: return base + warps * (uint32_t) sizeof (WarpQueue<6, 8>);
      }
    return base;
 }
