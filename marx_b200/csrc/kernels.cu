@@ -64,7 +64,6 @@ __device__ __forceinline__ unsigned long long ld_relaxed (const unsigned long lo
    asm volatile ("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
    return v;
 }
-__device__ __forceinline__ void prefetch_l2 (const void *p) { asm volatile ("prefetch.global.L2 [%0];" :: "l"(p)); }
 __device__ __forceinline__ void st_relaxed (unsigned long long *p, unsigned long long v)
 {
    asm volatile ("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
@@ -269,8 +268,9 @@ __device__ __forceinline__ void run_stage (const StageArgs &a, WarpQueue<ND, NU>
         __syncwarp ();
      };
 
-   // (drawing the NEXT chunk's ticket before tracing the current one, to hide the atomic's round trip, was measured
-   // 2 % slower: the extra live registers spill)
+   // (measured without effect or slower: drawing the NEXT chunk's ticket before tracing the current one -- the extra
+   // live registers spill, -2 %; prefetch.global.L2 of the next tile's columns -- 0 %; 4-tile chunks for every stage --
+   // load imbalance in the detector kernel, -2 %)
    unsigned long long chunk = 0;
    if (lane == 0) chunk = atomicAdd (a.ticket, 1ULL);
    chunk = __shfl_sync (0xffffffffu, chunk, 0);
@@ -291,16 +291,6 @@ __device__ __forceinline__ void run_stage (const StageArgs &a, WarpQueue<ND, NU>
              const unsigned long long i = base + lane;
              bool active = i < n_in;
              if (active && !a.compact) active = ((a.in.flags[i] & 0xFFu) == 0);
-#ifdef MX_PREFETCH
-             // the next tile of this chunk: pull its position/direction/slot columns towards L2 while this one is traced
-             if ((t + 1 < a.chunk_tiles) && (i + kWarpTile < n_in))
-               {
-                  const unsigned long long k = i + kWarpTile;
-                  prefetch_l2 (a.in.x0 + k); prefetch_l2 (a.in.x1 + k); prefetch_l2 (a.in.x2 + k);
-                  prefetch_l2 (a.in.p0 + k); prefetch_l2 (a.in.p1 + k); prefetch_l2 (a.in.p2 + k);
-                  prefetch_l2 (a.in.slot + k);
-               }
-#endif
              double d[ND]; uint32_t u[NU];
              uint32_t flags = 0xFFu;
              if (active) flags = trace (i, d, u);

@@ -593,11 +593,7 @@ static int run_stage (marxb200_ctx *c, int stage)
         a.n_out = (k == n_kernels - 1) ? c->d_counts + stage : c->d_counts + 4 + k;
         a.ticket = c->d_ticket + k;
         // big inputs amortise the ticket atomic over several tiles; small ones need fine-grained balancing
-#ifdef MX_CHUNK_TILES
-        a.chunk_tiles = MX_CHUNK_TILES;
-#else
         a.chunk_tiles = (stage == 1 && k == 0) ? 4 : ((stage == 1 && k == 1) ? 2 : 1);
-#endif
         prof_begin (c);
         switch (stage)
           {

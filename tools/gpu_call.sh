@@ -1,7 +1,3 @@
 set -x
 cd /root/repo
-for v in "" pf pf2 pf4 c4; do
-  if [ -z "$v" ]; then unset MARXB200_LIB; else export MARXB200_LIB=/root/repo/build/variants/libmarxb200_$v.so; fi
-  echo "=== variant [$v]"
-  timeout 300 python tools/trace_probe.py 16777216 c2_hetg_acis_s 20 2>&1 | tail -1
-done
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k3_acis|k01_source_hrma" -s 2 -c 2 -o gpurun_out/prof_r01_k3 python tools/ncu_probe.py 16777216 c2_hetg_acis_s 2 2>&1 | tail -3
