@@ -1,16 +1,20 @@
 // kernels.cu -- the sm_100a stage kernels over the HBM photon SoA.
 //
-//   K0  source + arrival times + aspect dither      (k0_time_sums, k0_time_scan, k0_source)
-//   K1  HRMA shell pair                             (k1_hrma)
-//   K2  HETG facet diffraction                      (k2_grating)
-//   K3  ACIS-S detection                            (k3_acis)
+//   K0   source + arrival times + aspect dither      k0_time_sums, k0_time_super/_bases/_tiles, k0_source
+//   K01  K0 fused with HRMA phase A                  k01_source_hrma      (marxb200_trace)
+//   K1   HRMA shell pair, phases A / B / C           k1_hrma<0|1|2>
+//   K2   HETG / LETG facet diffraction               k2_grating
+//   K3   ACIS-S / ACIS-I, HRC-S / HRC-I detection     k3_acis, k3_hrc
+//        arrival-order restoration                   order_mark, order_scan_words, order_scan_blocks, order_rank, order_gather
+//        host boundary                               soa_to_aos, aos_to_soa, egress_pack, exposure_truncate
 //
-// K1..K3 are persistent kernels: a grid of (SM count x resident CTAs) blocks pulls 256-ray tiles from a
-// ticket counter, stages the stage's small tables into shared memory with one TMA bulk copy
-// (cp.async.bulk + mbarrier), traces one ray per thread, and compacts survivors into the output SoA in
-// arrival order with warp ballots + a block prefix + a decoupled look-back over tile aggregates (the
-// GPU form of marx_prune_photons, marx/libsrc/photon.c:40-63).  All loads/stores of the SoA columns are
-// unit-stride across the warp.
+// K1..K3 are persistent kernels (grid = SM count x resident CTAs).  Every WARP pulls chunks of 32-ray tiles from a
+// ticket counter, stages the stage's small tables into shared memory with one TMA bulk copy (cp.async.bulk + mbarrier),
+// traces one ray per lane, and re-packs survivors through a warp-private queue in shared memory into full, coalesced
+// rows of the output list (ballot + popc ranks; the GPU form of marx_prune_photons, marx/libsrc/photon.c:40-63).
+// Per-ray constants (energy, time, ray id, dither angles) are written once at the ray's batch slot (RayConst) and
+// reached through the 4-byte slot key, so a compaction moves only what the stage produced.  The list is put back
+// into arrival order once per batch (order_*).  All loads/stores of list columns are unit-stride across the warp.
 //
 // No tensor cores: nothing on this path is a dense contraction (BASELINE.json north_star).
 // Compiled with -fmad=false: see mx_common.cuh.
@@ -669,6 +673,12 @@ __global__ void __launch_bounds__ (kTile, 3) k01_source_hrma (const __grid_const
              dither_ray (a.D, rng, t, p, dra, ddec, droll, const_roll ? &rolled : nullptr);
              rng.init (a.seed, a.first_ray + i, MARXB200_STAGE_MIRROR);
              alive = (0 == hrma_phase_a (H, st.source_distance, x, p, shell, rng));
+             // the per-ray constants go straight to their slot (slot == i).  They are stored for EVERY ray, dead ones
+             // included: full, coalesced 256-byte rows per column (36 B per generated ray), whereas storing only the
+             // survivors' made every sector a partial write that the L2 had to fill from DRAM first (ncu: 539 MB of
+             // reads in a kernel that reads nothing)
+             a.rc.energy[i] = energy; a.rc.time[i] = t; a.rc.ray[i] = a.first_ray + i;
+             a.rc.dra[i] = dra; a.rc.ddec[i] = ddec; a.rc.droll[i] = droll;
           }
         const uint32_t ballot = __ballot_sync (0xffffffffu, alive);
         if (alive)
@@ -678,10 +688,7 @@ __global__ void __launch_bounds__ (kTile, 3) k01_source_hrma (const __grid_const
              q.d[3][pos] = p.x; q.d[4][pos] = p.y; q.d[5][pos] = p.z;
              q.u[0][pos] = (uint32_t) i;
              q.u[1][pos] = shell | ((rng.draw & 0x3FFFu) << 8);
-             // the per-ray constants go straight to their slot (slot == i: the surviving lanes of a warp store into
-             // one 256-byte span per column)
-             a.rc.energy[i] = energy; a.rc.time[i] = t; a.rc.ray[i] = a.first_ray + i;
-             a.rc.dra[i] = dra; a.rc.ddec[i] = ddec; a.rc.droll[i] = droll;
+
           }
         count += __popc (ballot);
         __syncwarp ();

@@ -20,22 +20,53 @@ MX_HD Vec3 m3_mul_t (const double *m, const Vec3 &v)
    return b;
 }
 
-// intersect_with_detector_plane (must_hit = 1), detector.c:56-109
-MX_HD int chip_intersect (const AcisChipDev &g, const Vec3 &x0, const Vec3 &p, Vec3 &x, double &dx, double &dy)
+// intersect_with_detector_plane, detector.c:56-109.  must_hit: return 0 as soon as the point is off the chip;
+// otherwise (second pass of DetExtendFlag=yes) report the point anyway and return whether it was on the chip.
+// Plain-array form so that ACIS chips and HRC MCPs share it.
+MX_HD int plane_intersect (const double *g_normal, const double *g_x_ll, const double *g_xhat, const double *g_yhat,
+                           double xlen, double ylen, const Vec3 &x0, const Vec3 &p, Vec3 &x, double &dx, double &dy, bool must_hit)
 {
-   Vec3 normal = v_make (g.normal[0], g.normal[1], g.normal[2]);
+   Vec3 normal = v_make (g_normal[0], g_normal[1], g_normal[2]);
    double pdotn = v_dot (p, normal);
    if (pdotn == 0) return -1;
-   Vec3 x_ll = v_make (g.x_ll[0], g.x_ll[1], g.x_ll[2]);
+   Vec3 x_ll = v_make (g_x_ll[0], g_x_ll[1], g_x_ll[2]);
    Vec3 r = v_diff (x0, x_ll);
    r = v_ax1_bx2 (1.0, r, -1.0 * v_dot (r, normal) / pdotn, p);
-   double rx = v_dot (r, v_make (g.xhat[0], g.xhat[1], g.xhat[2]));
-   if ((rx < 0.0) || (rx >= g.xlen)) return 0;
-   double ry = v_dot (r, v_make (g.yhat[0], g.yhat[1], g.yhat[2]));
-   if ((ry < 0.0) || (ry >= g.ylen)) return 0;
+   int hit = 1;
+   double rx = v_dot (r, v_make (g_xhat[0], g_xhat[1], g_xhat[2]));
+   if ((rx < 0.0) || (rx >= xlen)) { if (must_hit) return 0; hit = 0; }
+   double ry = v_dot (r, v_make (g_yhat[0], g_yhat[1], g_yhat[2]));
+   if ((ry < 0.0) || (ry >= ylen)) { if (must_hit) return 0; hit = 0; }
    x = v_sum (r, x_ll);
    dx = rx; dy = ry;
-   return 1;
+   return hit;
+}
+MX_HD int chip_intersect (const AcisChipDev &g, const Vec3 &x0, const Vec3 &p, Vec3 &x, double &dx, double &dy, bool must_hit = true)
+{
+   return plane_intersect (g.normal, g.x_ll, g.xhat, g.yhat, g.xlen, g.ylen, x0, p, x, dx, dy, must_hit);
+}
+// _marx_intersect_with_detector, detector.c:111-168, over n facets accessed through `facet(k)`.  First facet hit wins;
+// with extend_flag the ray is otherwise assigned to the facet whose CENTRE is closest to its plane intersection.
+template <class Facets>
+MX_HD int detector_intersect (const Facets &F, int n, const Vec3 &x0, const Vec3 &p, Vec3 &xh, double &dx, double &dy, int extend_flag)
+{
+   for (int k = 0; k < n; k++)
+     if (1 == plane_intersect (F[k].normal, F[k].x_ll, F[k].xhat, F[k].yhat, F[k].xlen, F[k].ylen, x0, p, xh, dx, dy, true)) return k;
+   if (extend_flag == 0) return -1;
+   int best = -1;
+   double best_r2 = -1, bdx = 0, bdy = 0;
+   Vec3 bx = x0;
+   for (int k = 0; k < n; k++)
+     {
+        Vec3 x; double ddx, ddy;
+        if (-1 == plane_intersect (F[k].normal, F[k].x_ll, F[k].xhat, F[k].yhat, F[k].xlen, F[k].ylen, x0, p, x, ddx, ddy, false)) continue;
+        double deltax = ddx - 0.5 * F[k].xlen, deltay = ddy - 0.5 * F[k].ylen;
+        double r2 = deltax * deltax + deltay * deltay;
+        if ((r2 < best_r2) || (best < 0)) { best = k; bx = x; bdx = ddx; bdy = ddy; best_r2 = r2; }
+     }
+   if (best < 0) return -1;
+   xh = bx; dx = bdx; dy = bdy;
+   return best;
 }
 
 // Code-size control for k3_acis: the kernel is ~90 KB of SASS executed by warps that sit in different phases (geometry,
@@ -265,7 +296,13 @@ MX_HD int fef_pha_neg (const FefRows &R, const float *cum, uint32_t stride, uint
 MX_HD int acis_apply_fef (const AcisDev &A, const AcisChipDev &chip, float x, float y, double energy,
                           float &pi, int16_t &pha_out, Rng &rng, float *cum, uint32_t stride)
 {
-   if ((x < 0) || (x >= 1024) || (y < 0) || (y >= 1024)) return -1;    // DetExtendFlag=no
+   // find_fef, acis_fef.c:910-965: off-chip pixels are an error unless DetExtendFlag=yes, which clamps them
+   if ((x < 0) || (x >= 1024) || (y < 0) || (y >= 1024))
+     {
+        if (A.det_extend == 0) return -1;
+        if (x < 0) x = 0; else if (x >= 1024) x = 1023;
+        if (y < 0) y = 0; else if (y >= 1024) y = 1023;
+     }
    uint32_t i = (uint32_t) (x / 32), j = (uint32_t) (y / 32);
    if ((i >= 32) || (j >= 32)) return -1;
    int fi = chip.fef_map[i * 32 + j];
@@ -309,11 +346,9 @@ MX_HD uint32_t acis_detect (const AcisDev &A, double energy, double t_abs, Vec3 
    x = m3_mul (A.det_matrix, x);
    p = m3_mul (A.det_matrix, p);
 
-   int hit = -1;
    double dx = 0, dy = 0;
    Vec3 xh = x;
-   for (int k = 0; k < A.num_chips; k++)
-     if (1 == chip_intersect (A.chip[k], x, p, xh, dx, dy)) { hit = k; break; }
+   const int hit = detector_intersect (A.chip, A.num_chips, x, p, xh, dx, dy, A.det_extend);
    if (hit < 0)
      {
         ccd = -1;

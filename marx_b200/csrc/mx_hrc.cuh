@@ -124,26 +124,9 @@ MX_HD uint32_t hrc_s_detect (const HrcDev &D, double energy, Vec3 &x, Vec3 &p, i
    x = m3_mul (D.det_matrix, x);
    p = m3_mul (D.det_matrix, p);
 
-   int hit = -1;
    double dx = 0, dy = 0;
    Vec3 xh = x;
-   for (int k = 0; k < D.num_mcps; k++)
-     {
-        const HrcMcpDev &g = D.mcp[k];
-        // intersect_with_detector_plane (must_hit), detector.c:56-109
-        Vec3 normal = v_make (g.normal[0], g.normal[1], g.normal[2]);
-        double pdotn = v_dot (p, normal);
-        if (pdotn == 0) continue;
-        Vec3 x_ll = v_make (g.x_ll[0], g.x_ll[1], g.x_ll[2]);
-        Vec3 r = v_diff (x, x_ll);
-        r = v_ax1_bx2 (1.0, r, -1.0 * v_dot (r, normal) / pdotn, p);
-        double rx = v_dot (r, v_make (g.xhat[0], g.xhat[1], g.xhat[2]));
-        if ((rx < 0.0) || (rx >= g.xlen)) continue;
-        double ry = v_dot (r, v_make (g.yhat[0], g.yhat[1], g.yhat[2]));
-        if ((ry < 0.0) || (ry >= g.ylen)) continue;
-        xh = v_sum (r, x_ll); dx = rx; dy = ry; hit = k;
-        break;
-     }
+   const int hit = detector_intersect (D.mcp, D.num_mcps, x, p, xh, dx, dy, D.det_extend);   // detector.c:111-168
    if (hit < 0) { ccd = -1; return flags | MISSED; }
    const HrcMcpDev &d = D.mcp[hit];
    x = xh;

@@ -182,7 +182,6 @@ template <class Up> int build_grating_blob (Up &up, const marxb200_grating_desc 
 template <class Up> int build_hrc_blob (Up &up, const marxb200_hrc_s_desc *d, std::vector<unsigned char> &blob, std::string &err)
 {
    if ((d->num_mcps < 1) || (d->num_mcps > 3)) { err = "bad MCP count"; return -1; }
-   if (d->det_extend) { err = "DetExtendFlag=yes is not implemented"; return -1; }
    if ((d->hesf_num_plates < 0) || (d->hesf_num_plates > 4)) { err = "bad HESF plate count"; return -1; }
    const size_t total = tb_align16 (sizeof (K3HrcBlob));
    blob.assign (total, 0);
@@ -233,7 +232,6 @@ template <class Up> int build_hrc_blob (Up &up, const marxb200_hrc_s_desc *d, st
 template <class Up> int build_acis_blob (Up &up, const marxb200_acis_desc *d, std::vector<unsigned char> &blob, std::string &err)
 {
    if ((d->num_chips < 1) || (d->num_chips > kMaxChips)) { err = "bad chip count"; return -1; }
-   if (d->det_extend) { err = "DetExtendFlag=yes is not implemented"; return -1; }
    const size_t total = tb_align16 (sizeof (K3Blob));
    blob.assign (total, 0);
    K3Blob *B = reinterpret_cast<K3Blob *> (blob.data ());

@@ -872,7 +872,12 @@ static int pha_neg (const gauss_t *g, uint32_t num, double *phap, rng_t *r)     
 static int apply_fef (oracle_t *o, const chip_t *ch, float x, float y, double energy, float *pip, int16_t *phap, rng_t *r)   /* acis_fef.c:910-1079 */
 {
    unsigned int i, j, k; const fef_t *f; int fi, flags, status; double t, pha; const float *g0, *g1; gauss_t G[MAX_GAUSS];
-   if ((x < 0) || (x >= 1024) || (y < 0) || (y >= 1024)) return -1;
+   if ((x < 0) || (x >= 1024) || (y < 0) || (y >= 1024))                 /* find_fef :917-941: clamp with DetExtendFlag=yes */
+     {
+        if (0 == (int) o->acis[15]) return -1;
+        if (x < 0) x = 0; else if (x >= 1024) x = 1023;
+        if (y < 0) y = 0; else if (y >= 1024) y = 1023;
+     }
    i = (unsigned int) (x / 32); j = (unsigned int) (y / 32);
    if ((i >= 32) || (j >= 32)) return -1;
    fi = ch->fef_map[i * 32 + j];
@@ -902,18 +907,36 @@ static int apply_fef (oracle_t *o, const chip_t *ch, float x, float y, double en
    if (*pip < 0) return -1;
    return 0;
 }
-static int plane_hit (const double *g, const double *x0, const double *p, double *x, double *dx, double *dy)   /* detector.c:56-109 */
+static int plane_hit (const double *g, const double *x0, const double *p, double *x, double *dx, double *dy, int must_hit)   /* detector.c:56-109 */
 {
-   const double *xll = g + 1, *xhat = g + 4, *yhat = g + 7, *nrm = g + 10; double pdn = dot3 (p, nrm), r[3], f, rx, ry;
+   const double *xll = g + 1, *xhat = g + 4, *yhat = g + 7, *nrm = g + 10; double pdn = dot3 (p, nrm), r[3], f, rx, ry; int hit = 1;
    if (pdn == 0) return -1;
    r[0] = x0[0] - xll[0]; r[1] = x0[1] - xll[1]; r[2] = x0[2] - xll[2];
    f = -1.0 * dot3 (r, nrm) / pdn;
    r[0] = 1.0 * r[0] + f * p[0]; r[1] = 1.0 * r[1] + f * p[1]; r[2] = 1.0 * r[2] + f * p[2];
-   rx = dot3 (r, xhat); if ((rx < 0.0) || (rx >= g[13])) return 0;
-   ry = dot3 (r, yhat); if ((ry < 0.0) || (ry >= g[14])) return 0;
+   rx = dot3 (r, xhat); if ((rx < 0.0) || (rx >= g[13])) { if (must_hit) return 0; hit = 0; }
+   ry = dot3 (r, yhat); if ((ry < 0.0) || (ry >= g[14])) { if (must_hit) return 0; hit = 0; }
    x[0] = r[0] + xll[0]; x[1] = r[1] + xll[1]; x[2] = r[2] + xll[2];
    *dx = rx; *dy = ry;
-   return 1;
+   return hit;
+}
+/* _marx_intersect_with_detector, detector.c:111-168; geom[k] = the packed facet k (stride in doubles via accessor) */
+static int detector_hit (const double *const *geom, int n, const double *x0, const double *p, double *xh, double *dx, double *dy, int extend)
+{
+   int k, best = -1; double best_r2 = -1, bx[3] = {0, 0, 0}, bdx = 0, bdy = 0;
+   for (k = 0; k < n; k++) if (1 == plane_hit (geom[k], x0, p, xh, dx, dy, 1)) return k;
+   if (!extend) return -1;
+   for (k = 0; k < n; k++)
+     {
+        double x[3], ddx, ddy, deltax, deltay, r2;
+        if (-1 == plane_hit (geom[k], x0, p, x, &ddx, &ddy, 0)) continue;
+        deltax = ddx - 0.5 * geom[k][13]; deltay = ddy - 0.5 * geom[k][14];
+        r2 = deltax * deltax + deltay * deltay;
+        if ((r2 < best_r2) || (best < 0)) { best = k; bx[0] = x[0]; bx[1] = x[1]; bx[2] = x[2]; bdx = ddx; bdy = ddy; best_r2 = r2; }
+     }
+   if (best < 0) return -1;
+   xh[0] = bx[0]; xh[1] = bx[1]; xh[2] = bx[2]; *dx = bdx; *dy = bdy;
+   return best;
 }
 /* stage 3 (HRC-S / HRC-I): _marx_drake_reflect (drake.c:317-372) + _marx_hrc_s_detect (hrc-s.c:236-312) / _marx_hrc_i_detect (hrc-i.c:119-186) */
 static void stage_detect_hrc (oracle_t *o, uint64_t n, oracle_photon *ph)
@@ -956,7 +979,7 @@ static void stage_detect_hrc (oracle_t *o, uint64_t n, oracle_photon *ph)
         if (at->flags & 0xFF) continue;
         at->x[0] -= off[0]; at->x[1] -= off[1]; at->x[2] -= off[2];
         mat3 (M, at->x); mat3 (M, at->p);
-        for (k = 0; k < o->nmcps; k++) if (1 == plane_hit (o->mcp[k].geom, at->x, at->p, xh, &dx, &dy)) { hit = k; break; }
+        { const double *gg[3]; for (k = 0; k < o->nmcps; k++) gg[k] = o->mcp[k].geom; hit = detector_hit (gg, o->nmcps, at->x, at->p, xh, &dx, &dy, extend); }
         if (hit < 0) { at->flags |= F_MISSED; at->ccd_num = -1; continue; }
         m = &o->mcp[hit]; g = m->geom;
         at->x[0] = xh[0]; at->x[1] = xh[1]; at->x[2] = xh[2];
@@ -1014,7 +1037,7 @@ static void stage_detect_hrc (oracle_t *o, uint64_t n, oracle_photon *ph)
 static void stage_detect (oracle_t *o, uint64_t n, oracle_photon *ph)
 {
    const double *A = o->acis; const double *off = A + 2, *M = A + 5;
-   int ideal = (int) A[14]; double focal = A[16], texp = A[17], tft = A[18], tframe = A[19];
+   int ideal = (int) A[14], extend = (int) A[15]; double focal = A[16], texp = A[17], tft = A[18], tframe = A[19];
    uint64_t i;
    if ((int) A[0] == 0) return;
    for (i = 0; i < n; i++)
@@ -1024,7 +1047,7 @@ static void stage_detect (oracle_t *o, uint64_t n, oracle_photon *ph)
         rng_set (&r, o->seed, at->tag, 3);
         at->x[0] -= off[0]; at->x[1] -= off[1]; at->x[2] -= off[2];                                      /* trans.c:66-77 */
         mat3 (M, at->x); mat3 (M, at->p);
-        for (k = 0; k < o->nchips; k++) if (1 == plane_hit (o->chip[k].geom, at->x, at->p, xh, &dx, &dy)) { hit = k; break; }
+        { const double *gg[MAX_CHIPS]; for (k = 0; k < o->nchips; k++) gg[k] = o->chip[k].geom; hit = detector_hit (gg, o->nchips, at->x, at->p, xh, &dx, &dy, extend); }
         if (hit < 0) { at->flags |= F_MISSED; at->ccd_num = -1; continue; }
         ch = &o->chip[hit]; g = ch->geom;
         at->x[0] = xh[0]; at->x[1] = xh[1]; at->x[2] = xh[2];

@@ -84,6 +84,12 @@ CASES = [
                               "DitherAmp_Roll=30", "DitherPeriod_Roll=700", "SourceRA=250.05", "Roll_Nom=17.0"], 34, 0, 8000),
     ("hrc_i_letg", ["MinEnergy=0.1", "MaxEnergy=1.5", "GratingType=LETG", "DetectorType=HRC-I", "DitherModel=INTERNAL"], 37, 0, 8000),
     ("detector_none", ["MinEnergy=0.5", "MaxEnergy=4.0", "GratingType=HETG", "DetectorType=NONE", "DitherModel=NONE"], 38, 0, 8000),
+    ("det_extend_acis_s_off_axis", ["MinEnergy=0.5", "MaxEnergy=6.0", "GratingType=HETG", "DetectorType=ACIS-S", "DitherModel=INTERNAL",
+                                    "DetExtendFlag=yes", "SourceDEC=-53.45"], 41, 0, 12000),
+    ("det_extend_hrc_s_letg", ["MinEnergy=0.07", "MaxEnergy=1.0", "GratingType=LETG", "DetectorType=HRC-S", "DitherModel=INTERNAL",
+                               "DetExtendFlag=yes", "SourceRA=250.6"], 42, 0, 12000),
+    ("det_extend_acis_i", ["MinEnergy=0.5", "MaxEnergy=6.0", "GratingType=NONE", "DetectorType=ACIS-I", "DitherModel=NONE",
+                           "DetExtendFlag=yes", "SourceRA=250.35"], 43, 0, 12000),
     ("sector_files_off_unit_order", ["MinEnergy=0.8", "MaxEnergy=3.0", "GratingType=HETG", "DetectorType=ACIS-S", "DitherModel=INTERNAL",
                                      "Use_HETG_Sector_Files=no"], 8, 1000, 10000),
 ]
