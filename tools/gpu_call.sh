@@ -1,6 +1,5 @@
 set -x
 cd /root/repo
 timeout 1700 python -m pytest tests -q -m gpu 2>&1 | tail -6
-python bench.py --steps 100 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_r01_final3.json; cut -c1-200 gpurun_out/bench_r01_final3.json
-ncu --metrics gpu__time_duration.sum --clock-control none -c 90 --csv --log-file gpurun_out/launches_r01_final3.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/b3.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k1_hrma|k01_source_hrma|k3_acis|k2_grating|order_|k0_time" -s 15 -c 15 -o gpurun_out/prof_r01_final3 python tools/ncu_probe.py 16777216 c2_hetg_acis_s 2 2>&1 | tail -3
+timeout 300 python tools/trace_probe.py 16777216 c2_hetg_acis_s 20 2>&1 | tail -1
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"k01_source_hrma" -s 1 -c 1 python tools/ncu_probe.py 16777216 c2_hetg_acis_s 2 2>&1 | grep -E "dram__|gpu__time" 
