@@ -349,6 +349,9 @@ int marxb200_get_internal_counts (marxb200_ctx *ctx, uint64_t counts[8]);
  * (the reference's RAYFILE channel, s-rayfile.c:188-221); tags are the ray indices used for draws. */
 int marxb200_download (marxb200_ctx *ctx, marxb200_photon_attr *out, uint64_t max_out, uint64_t *n_out);
 int marxb200_upload (marxb200_ctx *ctx, const marxb200_photon_attr *in, uint64_t n, const uint64_t *ray_ids);
+/* same for records whose arrival_time counts from the start of their batch, as in a Marx_Photon_Type filled by the
+ * RAYFILE source (s-rayfile.c:188-221): start_time = pt->start_time */
+int marxb200_upload_from (marxb200_ctx *ctx, const marxb200_photon_attr *in, uint64_t n, const uint64_t *ray_ids, double start_time);
 /* debug/parity: download EVERY photon slot of the last stage call, dead ones included (flags say why) */
 int marxb200_download_all (marxb200_ctx *ctx, marxb200_photon_attr *out, uint64_t max_out, uint64_t *n_out);
 

@@ -26,6 +26,7 @@ int calpack_is_gauss (void *st, double *shape);
 int calpack_is_beta (void *st, double *shape);
 int calpack_is_disk (void *st, double *shape);
 int calpack_is_point (void *st);
+int calpack_is_rayfile (void *st);
 int calpack_dump_acis_i (mxcp_writer *w, int detector_module);
 int calpack_dump_hrc_s (mxcp_writer *w, int detector_module);
 int calpack_dump_hrc_i (mxcp_writer *w, int detector_module);

@@ -21,15 +21,22 @@ int calpack_dump_source (mxcp_writer *w, void *marx_source)
    double v[16], rot[4], img[4];
    int type;
    memset (v, 0, sizeof (v));
+   int rayfile = 0;
    type = calpack_source_shape (st, v + 13, rot, img);       /* 0 POINT, 1 GAUSS, 2 BETA, 3 DISK, 4 LINE, 5 IMAGE, -1 unsupported */
+   if ((type < 0) && calpack_is_rayfile (st))
+     {
+	/* RAYFILE: the stock host code reads the photons and the caller injects them (marxb200_upload_from); the device
+	 * source is never used and is packed as an inert POINT source.  Return value 1 tells the caller. */
+	type = 0; rayfile = 1;
+     }
    if (type < 0) return -1;
    v[0] = type;
-   v[1] = st->spectrum.type;
+   v[1] = rayfile ? MARX_FLAT_SPECTRUM : st->spectrum.type;
    v[2] = st->p.x; v[3] = st->p.y; v[4] = st->p.z;
    v[5] = st->p_normal.x; v[6] = st->p_normal.y; v[7] = st->p_normal.z;
    v[8] = st->distance;
    v[9] = v[10] = 0.0;
-   if (st->spectrum.type == MARX_FLAT_SPECTRUM)
+   if (!rayfile && (st->spectrum.type == MARX_FLAT_SPECTRUM))
      { v[9] = st->spectrum.s.flat.emin; v[10] = st->spectrum.s.flat.emax; }
    v[11] = st->spectrum.total_flux;
    v[12] = Marx_Mirror_Geometric_Area;
@@ -40,10 +47,10 @@ int calpack_dump_source (mxcp_writer *w, void *marx_source)
 	CP_F64 (w, "source.image_params", img, 4);           /* nx, ny, rad per x pixel, rad per y pixel */
 	calpack_dump_image (w);
      }
-   if (st->spectrum.type == MARX_FILE_SPECTRUM)
+   if (!rayfile && (st->spectrum.type == MARX_FILE_SPECTRUM))
      {
 	CP_F64 (w, "source.spec_energies", st->spectrum.s.file.energies, st->spectrum.s.file.num);
 	CP_F64 (w, "source.spec_cum_flux", st->spectrum.s.file.cum_flux, st->spectrum.s.file.num);
      }
-   return 0;
+   return rayfile;
 }

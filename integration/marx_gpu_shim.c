@@ -2,7 +2,7 @@
  *
  * The stock marx/src/marx.c is linked with
  *    -Wl,--wrap=JDMsrandom,--wrap=marx_mirror_init,--wrap=marx_grating_init,--wrap=marx_detector_init,
- *        --wrap=marx_create_photons,--wrap=marx_mirror_reflect,--wrap=marx_grating_diffract,--wrap=marx_detect,
+ *        --wrap=marx_create_photons (RAYFILE sources keep the stock one and inject its photons),--wrap=marx_mirror_reflect,--wrap=marx_grating_diffract,--wrap=marx_detect,
  *        --wrap=marx_write_photons,--wrap=marx_prune_photons,--wrap=marx_dump_to_rayfile,--wrap=marx_dealloc_photon_type
  * so that its calls (marx.c:245,254,263,569) reach the __wrap_* functions below while pfile parameter handling,
  * the stock *_init functions (calibration file readers), obs.par and the marxio/jdfits writers stay what they are
@@ -39,6 +39,7 @@ extern int _Marx_Dither_Mode;          /* marx/libsrc/_marx.h:144-145 (library-p
 #include "calpack_io.h"
 
 extern void __real_JDMsrandom (unsigned long);
+extern int __real_marx_create_photons (Marx_Source_Type *, Marx_Photon_Type *, unsigned int, unsigned int *, double *);
 extern int __real_marx_mirror_init (Param_File_Type *);
 extern int __real_marx_grating_init (Param_File_Type *);
 extern int __real_marx_detector_init (Param_File_Type *);
@@ -54,6 +55,7 @@ static uint64_t Next_Ray;              /* 64-bit global ray index = RNG counter;
 static int Host_Is_Stale;              /* photons of the current batch live in HBM only */
 static int Have_Support_Orders;
 static int Stock_Egress;               /* MARXB200_EGRESS=stock */
+static int Source_Is_Rayfile;          /* SourceType=RAYFILE: the stock host code reads the photons, the GPU traces them */
 static int Bulk_Written;               /* the current batch went to the output directory straight from the device */
 
 /* MARXB200_TIMING=1: host wall time spent in each wrapped call, printed when the driver frees its photon buffer */
@@ -107,8 +109,8 @@ static int gpu_init (Marx_Source_Type *st, Marx_Photon_Type *pt)
    memset (meta, 0, sizeof (meta));
    meta[0] = Mirror_Id; meta[1] = Grating_Id; meta[2] = Detector_Id; meta[5] = (double) Seed;
    CP_F64 (&w, "meta", meta, 8);
-   if (-1 == calpack_dump_source (&w, st))
-     marx_error ("marxb200: SourceType must be POINT, GAUSS, BETA or DISK for the GPU path");
+   if (-1 == (Source_Is_Rayfile = calpack_dump_source (&w, st)))
+     marx_error ("marxb200: SourceType must be POINT, GAUSS, BETA, DISK, LINE, IMAGE or RAYFILE for the GPU path");
    else if ((-1 == calpack_dump_dither (&w))
 	    || (-1 == calpack_dump_hrma (&w))
 	    || (-1 == calpack_dump_grating (&w, Grating_Id))
@@ -174,6 +176,24 @@ int __wrap_marx_create_photons (Marx_Source_Type *st, Marx_Photon_Type *pt, unsi
      }
    if (num > pt->max_n_photons)
      { marx_error ("marxb200: batch of %u rays exceeds the photon buffer", num); return -1; }
+
+   if (Source_Is_Rayfile)
+     {
+	/* RAYFILE re-entry (s-rayfile.c:188-221): the stock host code reads the records, fixes up their times, tags and
+	 * (record-only) dither state and sets pt->history from the file; the list is then injected into HBM and the
+	 * stage wrappers skip what the history says was already done (hrma.c:1171, diffract.c:982, acis-s.c:186). */
+	unsigned int got = 0;
+	double t0 = now ();
+	if (-1 == __real_marx_create_photons (st, pt, num, &got, exposure_time)) return -1;
+	if (-1 == marxb200_upload_from (Ctx, (marxb200_photon_attr *) pt->attributes, got, NULL, pt->start_time))
+	  return gpu_error ("marxb200_upload_from");
+	*num_collected = got;
+	Next_Ray += got;
+	Host_Is_Stale = (got != 0);
+	Bulk_Written = 0;
+	T_Create += now () - t0;
+	return 0;
+     }
 
    pt->source_distance = st->distance;                    /* source.c:282-285 */
    pt->history = 0;

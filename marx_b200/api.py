@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = [
     "marxb200_set_grating", "marxb200_set_acis", "marxb200_set_hrc_s", "marxb200_load_calpack", "marxb200_alloc_photons",
     "marxb200_create_photons", "marxb200_truncate_exposure", "marxb200_time_sums", "marxb200_mirror_reflect", "marxb200_grating_diffract",
     "marxb200_detect", "marxb200_restore_order", "marxb200_trace", "marxb200_trace_from", "marxb200_set_profiling", "marxb200_get_kernel_ms", "marxb200_get_counts", "marxb200_get_stage_counts", "marxb200_get_internal_counts", "marxb200_download",
-    "marxb200_upload", "marxb200_download_all", "marxb200_download_columns", "marxb200_egress_begin", "marxb200_egress_end", "marxb200_write_photons", "marxb200_egress_begin_packed", "marxb200_egress_end_packed", "marxb200_measure_fp64_peak", "marxb200_get_launch_count",
+    "marxb200_upload", "marxb200_upload_from", "marxb200_download_all", "marxb200_download_columns", "marxb200_egress_begin", "marxb200_egress_end", "marxb200_write_photons", "marxb200_egress_begin_packed", "marxb200_egress_end_packed", "marxb200_measure_fp64_peak", "marxb200_get_launch_count",
 ]
 
 # Marx_Photon_Attr_Type, marx/libsrc/marx.h:51-100 (136 bytes; offsets probed in SURVEY.md 8a1)
@@ -116,6 +116,7 @@ def load_library():
         "marxb200_download": [vp, vp, u64, C.POINTER(u64)],
         "marxb200_download_all": [vp, vp, u64, C.POINTER(u64)],
         "marxb200_upload": [vp, vp, u64, vp],
+        "marxb200_upload_from": [vp, vp, u64, vp, dbl],
         "marxb200_download_columns": [vp, vp, u64, C.POINTER(u64)],
         "marxb200_get_launch_count": [vp, C.POINTER(u64)],
         "marxb200_egress_begin": [vp, u64],
@@ -279,14 +280,15 @@ class MarxB200:
         self._check(fn(self._ctx, out.ctypes.data_as(C.c_void_p), len(out), C.byref(got)))
         return out[:got.value]
 
-    def upload(self, photons, ray_ids=None):
-        """Inject photons at a stage boundary (the reference's RAYFILE channel, s-rayfile.c:188-221)."""
+    def upload(self, photons, ray_ids=None, start_time=0.0):
+        """Inject photons at a stage boundary (the reference's RAYFILE channel, s-rayfile.c:188-221); start_time is
+        added to their arrival times (0: they are absolute)."""
         photons = np.ascontiguousarray(photons, dtype=PHOTON_DTYPE)
         ids = None
         if ray_ids is not None:
             ids = np.ascontiguousarray(ray_ids, dtype=np.uint64)
-        self._check(self._lib.marxb200_upload(self._ctx, photons.ctypes.data_as(C.c_void_p), len(photons),
-                                              ids.ctypes.data_as(C.c_void_p) if ids is not None else None))
+        self._check(self._lib.marxb200_upload_from(self._ctx, photons.ctypes.data_as(C.c_void_p), len(photons),
+                                                   ids.ctypes.data_as(C.c_void_p) if ids is not None else None, float(start_time)))
 
     def egress_begin(self, max_out):
         """snapshot the ordered live list on the device and return at once (see include/marxb200.h)"""

@@ -819,6 +819,11 @@ extern "C" int marxb200_download_all (marxb200_ctx *c, marxb200_photon_attr *out
 
 extern "C" int marxb200_upload (marxb200_ctx *c, const marxb200_photon_attr *in, uint64_t n, const uint64_t *ray_ids)
 {
+   return marxb200_upload_from (c, in, n, ray_ids, 0.0);      // arrival times are absolute
+}
+
+extern "C" int marxb200_upload_from (marxb200_ctx *c, const marxb200_photon_attr *in, uint64_t n, const uint64_t *ray_ids, double start_time)
+{
    if ((c == nullptr) || (in == nullptr)) return fail ("marxb200_upload: NULL argument");
    if (n > c->capacity) return fail ("marxb200_upload: n exceeds capacity");
    CUDA_OK (cudaSetDevice (c->device));
@@ -831,8 +836,9 @@ extern "C" int marxb200_upload (marxb200_ctx *c, const marxb200_photon_attr *in,
         CUDA_OK (cudaMemcpyAsync (d_ids, ray_ids, n * sizeof (uint64_t), cudaMemcpyHostToDevice, c->stream));
      }
    c->cur = 0;
-   CUDA_OK (cudaMemsetAsync (c->d_times, 0, sizeof (double), c->stream));   // uploaded arrival times are absolute
-   launch_aos_to_soa (c->d_aos, d_ids, n, c->buf[0], c->rc, 0.0, c->stream);
+   // the list keeps absolute times (pt->start_time + arrival_time); d_times[0] = the batch start the AoS download subtracts
+   CUDA_OK (cudaMemcpyAsync (c->d_times, &start_time, sizeof (double), cudaMemcpyHostToDevice, c->stream));
+   launch_aos_to_soa (c->d_aos, d_ids, n, c->buf[0], c->rc, start_time, c->stream);
    c->launches += 1;
    unsigned long long nn = n;
    CUDA_OK (cudaMemcpyAsync (c->d_counts + 0, &nn, sizeof (nn), cudaMemcpyHostToDevice, c->stream));

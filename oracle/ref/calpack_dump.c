@@ -30,7 +30,7 @@ int main (int argc, char **argv)
    meta[6] = rs.num_rays; meta[7] = rs.exposure_time;
    CP_F64 (&w, "meta", meta, 8);
 
-   if ((-1 == calpack_dump_source (&w, rs.source))
+   if ((0 != calpack_dump_source (&w, rs.source))      /* -1 unsupported, 1 RAYFILE (host-read photons: nothing to pack) */
        || (-1 == calpack_dump_dither (&w))
        || (rs.mirror_module != MARX_MIRROR_HRMA) || (-1 == calpack_dump_hrma (&w))
        || (-1 == calpack_dump_grating (&w, rs.grating_module))

@@ -182,3 +182,42 @@ def test_marx_gpu_exposure_time_cut(tmp_path):
     n_cpu = len(read_dir(tmp_path / "cpu")["energy.dat"])
     n_gpu = len(got["energy.dat"])
     assert abs(n_cpu - n_gpu) < 5.0 * np.sqrt(n_cpu + n_gpu), (n_cpu, n_gpu)
+
+
+@pytest.mark.gpu
+@needs_driver
+def test_rayfile_dump_and_reentry(tmp_path):
+    """DumpToRayFile=yes writes the generated photons from the device list through the stock rayfile writer; a second run
+    with SourceType=RAYFILE lets the stock host code read them back, injects them into HBM and traces them.  The history
+    word of the file decides which stages still run (hrma.c:1171-1173 etc.)."""
+    cfg = CONFIGS["c2_hetg_acis_s"]
+    rays = str(tmp_path / "rays.dat")
+    n, dn = 300000, 100000
+    base = COMMON + cfg["args"] + ["NumRays=%d" % n, "dNumRays=%d" % dn, "RandomSeed=6", "Verbose=1", "RayFile=" + rays]
+    run_marx(MARX_GPU, tmp_path / "dump", base + ["DumpToRayFile=yes"])
+    assert os.path.getsize(rays) == 16 + 136 * n                      # magic + history + every generated photon
+    raw = np.fromfile(rays, dtype=marx_b200.PHOTON_DTYPE, offset=16)
+    assert (raw["tag"] == np.arange(n, dtype=np.uint32)).all() and (np.diff(raw["arrival_time"]) >= 0).all()
+    assert ((raw["energy"] >= 0.3) & (raw["energy"] <= 8.0)).all()
+    # re-entry
+    args = [a for a in base if not a.startswith("SourceType=")] + ["SourceType=RAYFILE"]
+    p = run_marx(MARX_GPU, tmp_path / "reentry", args)
+    assert "Reflecting from HRMA [B200]" in p.stdout and "Detecting [B200]" in p.stdout
+    got = read_dir(tmp_path / "reentry")
+    # the same rays traced directly
+    q = run_marx(MARX_GPU, tmp_path / "direct", base)
+    ref = read_dir(tmp_path / "direct")
+    n_a, n_b = len(got["energy.dat"]), len(ref["energy.dat"])
+    assert n_a > 0 and abs(n_a - n_b) < 5.0 * np.sqrt(n_a + n_b), (n_a, n_b)
+    # every event of the re-entry run is one of the file's photons, with its energy
+    tags = got["tag.dat"].astype(np.int64)
+    assert (np.diff(tags) > 0).all() and tags.max() < n
+    assert (got["energy.dat"] == raw["energy"][tags].astype(np.float32)).all()
+    # a file whose history says the mirror was already applied: the mirror stage must be skipped
+    hist = np.fromfile(rays, dtype=np.uint64, count=2)
+    patched = str(tmp_path / "rays_mirror_done.dat")
+    data = bytearray(open(rays, "rb").read())
+    data[8:16] = np.uint64(int(hist[1]) | 0x800).tobytes()
+    open(patched, "wb").write(bytes(data))
+    r = run_marx(MARX_GPU, tmp_path / "skip", [a for a in args if not a.startswith("RayFile=")] + ["RayFile=" + patched])
+    assert "Reflecting from HRMA [B200]" not in r.stdout and "Diffracting from HETG [B200]" in r.stdout

@@ -1,5 +1,6 @@
 set -x
 cd /root/repo
-timeout 1700 python -m pytest tests -q -m gpu 2>&1 | tail -6
-timeout 300 python tools/trace_probe.py 16777216 c2_hetg_acis_s 20 2>&1 | tail -1
-timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"k01_source_hrma" -s 1 -c 1 python tools/ncu_probe.py 16777216 c2_hetg_acis_s 2 2>&1 | grep -E "dram__|gpu__time" 
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_probe.py 20000 > gpurun_out/san_mem.log 2>&1; echo "memcheck rc=$?"; tail -12 gpurun_out/san_mem.log
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/sanitize_probe.py 6000 > gpurun_out/san_race.log 2>&1; echo "racecheck rc=$?"; tail -8 gpurun_out/san_race.log
+timeout 900 compute-sanitizer --tool initcheck --error-exitcode 9 python tools/sanitize_probe.py 6000 > gpurun_out/san_init.log 2>&1; echo "initcheck rc=$?"; tail -8 gpurun_out/san_init.log
+timeout 600 compute-sanitizer --tool synccheck --error-exitcode 9 python tools/sanitize_probe.py 6000 > gpurun_out/san_sync.log 2>&1; echo "synccheck rc=$?"; tail -5 gpurun_out/san_sync.log

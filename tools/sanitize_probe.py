@@ -1,0 +1,27 @@
+#!/usr/bin/env python3
+"""Developer probe for compute-sanitizer: small batches of every configuration through the staged and the fused path,
+downloads, the file writer and the packed egress."""
+import os
+import sys
+import tempfile
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import marx_b200
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
+for cfg in ("c2_hetg_acis_s", "c3_letg_hrc_s", "c4_image_acis_i", "c3_hrc_i", "c1_line_acis_s"):
+    with marx_b200.MarxB200(cfg, seed=3, max_photons=n) as m:
+        m.create_photons(0, n); m.mirror_reflect(); m.grating_diffract(); m.detect()
+        a = m.download().copy()
+        m.trace(n, n - 7)
+        b = m.download().copy()
+        d = tempfile.mkdtemp()
+        m.write_photons(d, 0x1F01FFF, True, 0.0)
+        m.egress_begin_packed(0x1F01FFF, 0.0, n)
+        host = np.zeros(n * 120, dtype=np.uint8)
+        cols = m.egress_end_packed(host)
+        m.set_compaction(False)
+        m.create_photons(0, 1000); m.mirror_reflect(); m.grating_diffract(); m.detect()
+        c = m.download(all_slots=True)
+        m.upload(c); m.detect()
+        print(cfg, len(a), len(b), len(cols), len(c), m.stage_counts())
