@@ -107,12 +107,18 @@ marxb200_source_desc;
 /* aspect dither: marx/libsrc/dither.c:50-72,167-182,508-547 (angles already in radians) */
 typedef struct
 {
-   int32_t mode;                   /* 0 = NONE, 1 = INTERNAL */
+   int32_t mode;                   /* 0 = NONE, 1 = INTERNAL, 2 = ASPSOL (DitherModel=FILE, dither.c:288-500) */
    double ra_amp, dec_amp, roll_amp;
    double ra_period, dec_period, roll_period;
    double ra_phase, dec_phase, roll_phase;
    double nominal_roll;
    double aspect_blur;
+   /* ASPSOL: the states the stock reader steps through (get_single_aspsol_point, dither.c:288-359), in file order,
+    * state 0 being the one init_aspsol_dither leaves behind: [num_aspsol][7] = t (s since TSTART), ra, dec, roll (rad,
+    * unrolled offsets), dy, dz (mm), dtheta (rad).  A ray at time t uses the first state k >= 1 with t < t_k and its
+    * predecessor; rays at or beyond the last state end the simulation (the reference stops at the end of the file). */
+   const double *aspsol;
+   uint32_t num_aspsol;
 }
 marxb200_dither_desc;
 

@@ -3,6 +3,39 @@
 #include <dither.c>
 #include "calpack_io.h"
 
+/* ASPSOL (DitherModel=FILE): the stock reader walks the file forward while the photons arrive (dither.c:288-377) and
+ * converts every row on the way (spherical -> unrolled offsets, :331-350).  Here all rows are harvested through that
+ * very function, so the table holds exactly the states the stock code would step through -- including the state left
+ * by init_aspsol_dither, whose t1 has TSTART subtracted twice (:353 and :487).  Afterwards the reader is re-initialised
+ * so that the stock obs.par code (get_aspsol_dither_mean, :420-440) still finds an open file. */
+static int harvest_aspsol (mxcp_writer *w)
+{
+   unsigned int n = 0, cap = 4096;
+   int record_only = (Get_Dither_Function == get_aspsol_dither_record_only);
+   double *tab = (double *) malloc (cap * 7 * sizeof (double));
+   if (tab == NULL) return -1;
+   while (1)
+     {
+	double *r;
+	if (n == cap)
+	  {
+	     cap *= 2;
+	     if (NULL == (tab = (double *) realloc (tab, cap * 7 * sizeof (double)))) return -1;
+	  }
+	r = tab + 7 * n;
+	r[0] = Aspsol.t1; r[1] = Aspsol.ra1; r[2] = Aspsol.dec1; r[3] = Aspsol.roll1;
+	r[4] = Aspsol.dy1; r[5] = Aspsol.dz1; r[6] = Aspsol.dtheta1;
+	n++;
+	if (Aspsol.bt == NULL) break;                       /* cannot happen: init leaves the file open */
+	if (-1 == get_single_aspsol_point ()) break;        /* end of file: the reader has closed it */
+     }
+   CP_F64 (w, "dither.aspsol", tab, 7 * (uint64_t) n);
+   free (tab);
+   memset ((char *) &Aspsol, 0, sizeof (Aspsol));
+   if (-1 == init_aspsol_dither (record_only ? _MARX_DITHER_RECORD_ONLY : 0)) return -1;
+   return 0;
+}
+
 int calpack_dump_dither (mxcp_writer *w)
 {
    double v[12];
@@ -12,7 +45,9 @@ int calpack_dump_dither (mxcp_writer *w)
    v[7] = Ra_Phase; v[8] = Dec_Phase; v[9] = Roll_Phase;
    v[10] = Nominal_Roll; v[11] = Aspect_Blur;
    if (Get_Dither_Function == get_zeroamp_internal_dither) v[1] = v[2] = v[3] = 0.0;
-   return CP_F64 (w, "dither.params", v, 12);
+   if (-1 == CP_F64 (w, "dither.params", v, 12)) return -1;
+   if (_Marx_Dither_Mode == _MARX_DITHER_MODE_ASPSOL) return harvest_aspsol (w);
+   return 0;
 }
 
 int calpack_dump_source (mxcp_writer *w, void *marx_source)

@@ -206,8 +206,14 @@ int __wrap_marx_create_photons (Marx_Source_Type *st, Marx_Photon_Type *pt, unsi
    if ((exposure_time != NULL)                            /* source.c:323-334 */
        && (-1 == marxb200_truncate_exposure (Ctx, *exposure_time, &n)))
      return gpu_error ("marxb200_truncate_exposure");
-   if (-1 == marxb200_get_counts (Ctx, NULL, NULL, &t_end))
-     return gpu_error ("marxb200_get_counts");
+   {
+      /* DitherModel=FILE: the batch ends with the last ray the ASPSOL file still brackets (dither.c:296-301, 630-658;
+       * source.c:355 passes the shortened count on), and marx.c:577-606 ends the run on a short or empty batch */
+      uint64_t generated = n;
+      if (-1 == marxb200_get_counts (Ctx, &generated, NULL, &t_end))
+	return gpu_error ("marxb200_get_counts");
+      if (generated < n) n = generated;
+   }
 
    pt->history |= (MARX_ENERGY_OK | MARX_TIME_OK | MARX_X_VECTOR_OK | MARX_P_VECTOR_OK | MARX_TAG_OK);
    pt->tag_start += (unsigned int) n;                     /* source.c:346-355 */

@@ -8,6 +8,7 @@
 //   source.rotation           f64[4]  LINE / IMAGE: axis[3] + angle of the rotation taking (-1,0,0) to p
 //   source.image_params       f64[4]  IMAGE: nx, ny, rad per x pixel, rad per y pixel;  source.image_cdf f32[ny*nx]
 //   dither.params             f64[12] mode, amp ra/dec/roll, period ra/dec/roll, phase ra/dec/roll, nominal_roll, aspect_blur
+//   dither.aspsol             f64[n][7] (mode 2) t, ra, dec, roll, dy, dz, dtheta of every ASPSOL reader state
 //   hrma.params               f64[7]  vig, cap_position, is_ideal, use_blur, use_wfold, use_struts, use_scale_factors
 //   hrma.opt_energies/.opt_betas/.opt_deltas  f32[n]
 //   hrma.shell<k>.params      f64[62] (order: see set_hrma_from_pack)
@@ -142,6 +143,11 @@ extern "C" int marxb200_load_calpack_impl (marxb200_ctx *ctx, const char *path, 
       d.ra_period = v[4]; d.dec_period = v[5]; d.roll_period = v[6];
       d.ra_phase = v[7]; d.dec_phase = v[8]; d.roll_phase = v[9];
       d.nominal_roll = v[10]; d.aspect_blur = v[11];
+      if (d.mode == 2)
+        {
+           GET (a, "dither.aspsol", MXCP_F64, 14);
+           d.aspsol = (const double *) a->data; d.num_aspsol = (uint32_t) (a->count / 7);
+        }
       if (-1 == marxb200_set_dither (ctx, &d)) return bail (marxb200_last_error ());
    }
    // ---- HRMA ----

@@ -223,8 +223,8 @@ __global__ void __launch_bounds__ (kTile) k0_source (const __grid_constant__ Sou
    double total;
    double t = tile_inclusive_scan (dt, total) + a.tile_base[blockIdx.x];
    if (!valid) return;
-   float dra, ddec, droll;
-   dither_ray (a.D, rng, t, p, dra, ddec, droll);
+   float dra, ddec, droll, det[3];
+   dither_ray (a.D, rng, t, p, dra, ddec, droll, nullptr, det);
    const PhotonSoA &o = a.out;
    o.energy[i] = energy;
    o.p0[i] = p.x; o.p1[i] = p.y; o.p2[i] = p.z;
@@ -234,9 +234,11 @@ __global__ void __launch_bounds__ (kTile) k0_source (const __grid_constant__ Sou
    o.flags[i] = 0;
    o.order[i] = 0; o.sorders[i] = 0;      // stay 0 when GratingType=NONE (memset of source.c:287)
    o.dra[i] = dra; o.ddec[i] = ddec; o.droll[i] = droll;
+   o.ddy[i] = det[0]; o.ddz[i] = det[1]; o.ddth[i] = det[2];
    const RayConst &rc = a.rc;           // slot == i
    rc.energy[i] = energy; rc.time[i] = t; rc.ray[i] = a.first_ray + i;
    rc.dra[i] = dra; rc.ddec[i] = ddec; rc.droll[i] = droll;
+   rc.ddy[i] = det[0]; rc.ddz[i] = det[1]; rc.ddth[i] = det[2];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -518,7 +520,9 @@ __global__ void __launch_bounds__ (kStageThreads, MX_K3_MINBLOCKS) k3_acis (cons
         Rng rng;
         const uint32_t slot = in.slot[i];
         rng.init (a.seed, a.rc.ray[slot], MARXB200_STAGE_DETECTOR);
-        uint32_t flags = acis_detect (A, a.rc.energy[slot], a.rc.time[slot], x, p, ccd, chipx, chipy, pha, pi, rng, fef_cum, kStageThreads);
+        DetDither dd = {0.0, 0.0, 0.0};
+        if (a.det_dither) { dd.dy = a.rc.ddy[slot]; dd.dz = a.rc.ddz[slot]; dd.dtheta = a.rc.ddth[slot]; }
+        uint32_t flags = acis_detect (A, a.rc.energy[slot], a.rc.time[slot], x, p, ccd, chipx, chipy, pha, pi, rng, fef_cum, kStageThreads, dd);
         d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = p.x; d[4] = p.y; d[5] = p.z;
         // ids produced by the earlier stages travel through the queue (coalesced loads here instead of dependent
         // gathers when a row is flushed): flags use bits 0..9, shell and order ride in the upper half
@@ -574,7 +578,9 @@ __global__ void __launch_bounds__ (kStageThreads) k3_hrc (const __grid_constant_
         Rng rng;
         const uint32_t slot = in.slot[i];
         rng.init (a.seed, a.rc.ray[slot], MARXB200_STAGE_DETECTOR);
-        uint32_t flags = hrc_s_detect (D, a.rc.energy[slot], x, p, ccd, region, ypix, zpix, upix, vpix, pha, rng);
+        DetDither dd = {0.0, 0.0, 0.0};
+        if (a.det_dither) { dd.dy = a.rc.ddy[slot]; dd.dz = a.rc.ddz[slot]; dd.dtheta = a.rc.ddth[slot]; }
+        uint32_t flags = hrc_s_detect (D, a.rc.energy[slot], x, p, ccd, region, ypix, zpix, upix, vpix, pha, rng, dd);
         d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = p.x; d[4] = p.y; d[5] = p.z;
         u[0] = slot;
         u[1] = flags | ((uint32_t) in.shell[i] << 16) | (((uint32_t) (uint8_t) in.order[i]) << 24);
@@ -777,6 +783,7 @@ __global__ void __launch_bounds__ (256) order_gather (OrderArgs a)
         out.time[j] = rc.time[key]; out.aux[j] = in.aux[s];
         out.ray[j] = rc.ray[key]; out.slot[j] = key; out.flags[j] = in.flags[s];
         out.dra[j] = rc.dra[key]; out.ddec[j] = rc.ddec[key]; out.droll[j] = rc.droll[key];
+        out.ddy[j] = rc.ddy[key]; out.ddz[j] = rc.ddz[key]; out.ddth[j] = rc.ddth[key];
         out.chipx[j] = in.chipx[s]; out.chipy[j] = in.chipy[s]; out.pi[j] = in.pi[s];
         out.pha[j] = in.pha[s]; out.shell[j] = in.shell[s]; out.order[j] = in.order[s]; out.ccd[j] = in.ccd[s];
         out.upix[j] = in.upix[s]; out.vpix[j] = in.vpix[s]; out.sorders[j] = in.sorders[s]; out.region[j] = in.region[s];
@@ -812,7 +819,7 @@ __global__ void __launch_bounds__ (256) soa_to_aos (PhotonSoA in, const unsigned
         r.flags = in.flags[i];
         r.y_pixel = in.chipx[i]; r.z_pixel = in.chipy[i]; r.u_pixel = in.upix[i]; r.v_pixel = in.vpix[i];
         r.dither_ra = in.dra[i]; r.dither_dec = in.ddec[i]; r.dither_roll = in.droll[i];
-        r.dither_dy = 0.f; r.dither_dz = 0.f; r.dither_dtheta = 0.f;
+        r.dither_dy = in.ddy[i]; r.dither_dz = in.ddz[i]; r.dither_dtheta = in.ddth[i];
         r.pi = in.pi[i];
         r.pulse_height = in.pha[i];
         r.mirror_shell = in.shell[i];
@@ -851,6 +858,8 @@ __global__ void __launch_bounds__ (256) aos_to_soa (const marxb200_photon_attr *
         out.dra[i] = r.dither_ra; out.ddec[i] = r.dither_dec; out.droll[i] = r.dither_roll;
         rc.energy[i] = r.energy; rc.time[i] = r.arrival_time + start_time; rc.ray[i] = ray_ids ? ray_ids[i] : (uint64_t) r.tag;
         rc.dra[i] = r.dither_ra; rc.ddec[i] = r.dither_dec; rc.droll[i] = r.dither_roll;
+        out.ddy[i] = r.dither_dy; out.ddz[i] = r.dither_dz; out.ddth[i] = r.dither_dtheta;
+        rc.ddy[i] = r.dither_dy; rc.ddz[i] = r.dither_dz; rc.ddth[i] = r.dither_dtheta;
         out.chipx[i] = r.y_pixel; out.chipy[i] = r.z_pixel; out.pi[i] = r.pi;
         out.pha[i] = r.pulse_height;
         out.shell[i] = (uint8_t) r.mirror_shell;
@@ -868,25 +877,28 @@ __global__ void __launch_bounds__ (256) aos_to_soa (const marxb200_photon_attr *
 // counted from the batch start, reaches the exposure left.  Arrival times are a running sum, hence monotone: one
 // thread bisects.  Updates the generated count and the running end time (pt->total_time, source.c:377-381).
 // ---------------------------------------------------------------------------------------------
-__global__ void exposure_truncate (const double *time, unsigned long long *n_ptr, double *dev_times, double exposure_left)
+// inclusive = 1: the ExposureTime cut (keep the crossing ray; times counted from the batch start);
+// inclusive = 0: the end of an ASPSOL file (dither.c:296-301, 361-369: the first ray at or beyond the last state is not
+// dithered and ends the batch; `limit` is an absolute time)
+__global__ void exposure_truncate (const double *time, unsigned long long *n_ptr, double *dev_times, double limit, int inclusive)
 {
    if ((blockIdx.x != 0) || (threadIdx.x != 0)) return;
    const unsigned long long n = *n_ptr;
    if (n == 0) return;
-   const double start = dev_times[0];
-   unsigned long long lo = 0, hi = n;            // first index with time - start >= exposure_left, or n
+   const double start = inclusive ? dev_times[0] : 0.0;
+   unsigned long long lo = 0, hi = n;            // first index with time - start >= limit, or n
    while (lo < hi)
      {
         const unsigned long long mid = lo + (hi - lo) / 2;
-        if (time[mid] - start >= exposure_left) hi = mid; else lo = mid + 1;
+        if (time[mid] - start >= limit) hi = mid; else lo = mid + 1;
      }
-   const unsigned long long keep = (lo < n) ? lo + 1 : n;
+   const unsigned long long keep = inclusive ? ((lo < n) ? lo + 1 : n) : lo;
    *n_ptr = keep;
-   dev_times[1] = time[keep - 1];
+   if (keep < n) dev_times[1] = (keep > 0) ? time[keep - 1] : dev_times[0];
 }
-void launch_exposure_truncate (const PhotonSoA &buf, unsigned long long *n, double *dev_times, double exposure_left, cudaStream_t s)
+void launch_exposure_truncate (const PhotonSoA &buf, unsigned long long *n, double *dev_times, double limit, int inclusive, cudaStream_t s)
 {
-   exposure_truncate<<<1, 32, 0, s>>> (buf.time, n, dev_times, exposure_left);
+   exposure_truncate<<<1, 32, 0, s>>> (buf.time, n, dev_times, limit, inclusive);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -930,7 +942,9 @@ __global__ void __launch_bounds__ (256) egress_pack (PhotonSoA in, const unsigne
                 case EGRESS_SKY_RA: f = in.dra[i]; break;
                 case EGRESS_SKY_DEC: f = in.ddec[i]; break;
                 case EGRESS_SKY_ROLL: f = in.droll[i]; break;
-                case EGRESS_ZERO_F32: f = 0.0f; break;
+                case EGRESS_DET_DY: f = in.ddy[i]; break;
+                case EGRESS_DET_DZ: f = in.ddz[i]; break;
+                case EGRESS_DET_THETA: f = in.ddth[i]; break;
                 case EGRESS_TAG:
                   reinterpret_cast<uint32_t *> (base)[i] = bswap32 ((uint32_t) in.ray[i]); continue;
                 case EGRESS_PHA:

@@ -72,6 +72,8 @@ struct marxb200_ctx
    void *blob1 = nullptr, *blob2 = nullptr, *blob3 = nullptr;
    uint32_t blob1_bytes = 0, blob2_bytes = 0, blob3_bytes = 0;
    uint32_t k1b_bytes = 0, k1c_seg2_off = 0, k1c_seg2_bytes = 0;
+   bool det_dither_dirty = false;                // uploaded photons may carry detector dither: the per-ray columns are live
+   double aspsol_t_last = 0.0;                   // ASPSOL dither: time of the last state (rays at or beyond it end the run)
    int grid1[3] = {0, 0, 0}, grid2 = 0, grid3 = 0, grid01 = 0;
    bool detector_is_hrc = false;
    int first_mirror_kernel = 0;                  // 1: phase A already ran fused with the source (marxb200_trace)
@@ -313,8 +315,18 @@ extern "C" int marxb200_set_source (marxb200_ctx *c, const marxb200_source_desc 
 extern "C" int marxb200_set_dither (marxb200_ctx *c, const marxb200_dither_desc *d)
 {
    if ((c == nullptr) || (d == nullptr)) return fail ("marxb200_set_dither: NULL argument");
-   if ((d->mode != 0) && (d->mode != 1)) return fail ("marxb200_set_dither: only NONE and INTERNAL models are implemented (mode %d)", d->mode);
+   if ((d->mode < 0) || (d->mode > 2)) return fail ("marxb200_set_dither: unknown dither model %d", d->mode);
    DitherDev &D = c->D;
+   if ((D.mode == 2) && (d->mode != 2)) c->det_dither_dirty = true;   // the per-ray detector-dither columns hold an ASPSOL run's values
+   D.aspsol = nullptr; D.num_aspsol = 0;
+   if (d->mode == 2)
+     {
+        if ((d->num_aspsol < 2) || (d->aspsol == nullptr)) return fail ("marxb200_set_dither: the ASPSOL model needs at least two states");
+        CUDA_OK (cudaSetDevice (c->device));
+        if (-1 == dev_upload_t (c, d->aspsol, 7 * (size_t) d->num_aspsol, &D.aspsol)) return -1;
+        D.num_aspsol = d->num_aspsol;
+        c->aspsol_t_last = d->aspsol[7 * (size_t) (d->num_aspsol - 1)];
+     }
    D.mode = d->mode;
    D.ra_amp = d->ra_amp; D.dec_amp = d->dec_amp; D.roll_amp = d->roll_amp;
    D.ra_period = d->ra_period; D.dec_period = d->dec_period; D.roll_period = d->roll_period;
@@ -430,6 +442,7 @@ static size_t carve (PhotonSoA &b, unsigned char *base, uint64_t n)
    b.slot = (uint32_t *) take (4);
    b.flags = (uint32_t *) take (4);
    b.dra = (float *) take (4); b.ddec = (float *) take (4); b.droll = (float *) take (4);
+   b.ddy = (float *) take (4); b.ddz = (float *) take (4); b.ddth = (float *) take (4);
    b.chipx = (float *) take (4); b.chipy = (float *) take (4); b.pi = (float *) take (4);
    b.upix = (float *) take (4); b.vpix = (float *) take (4);
    b.sorders = (uint32_t *) take (4);
@@ -465,11 +478,12 @@ extern "C" int marxb200_alloc_photons (marxb200_ctx *c, uint64_t max_photons)
       // per-ray constants: energy, time (f64), ray (u64), dither ra/dec/roll (f32), each column 256-byte aligned
       if (c->rc_slab) { cudaFree (c->rc_slab); c->rc_slab = nullptr; }
       const size_t c8 = (8 * (size_t) max_photons + 255) & ~(size_t) 255, c4 = (4 * (size_t) max_photons + 255) & ~(size_t) 255;
-      CUDA_OK (cudaMalloc (&c->rc_slab, 3 * c8 + 3 * c4));
-      CUDA_OK (cudaMemsetAsync (c->rc_slab, 0, 3 * c8 + 3 * c4, c->stream));
+      CUDA_OK (cudaMalloc (&c->rc_slab, 3 * c8 + 6 * c4));
+      CUDA_OK (cudaMemsetAsync (c->rc_slab, 0, 3 * c8 + 6 * c4, c->stream));
       unsigned char *b = (unsigned char *) c->rc_slab;
       c->rc.energy = (double *) b; c->rc.time = (double *) (b + c8); c->rc.ray = (uint64_t *) (b + 2 * c8);
       c->rc.dra = (float *) (b + 3 * c8); c->rc.ddec = (float *) (b + 3 * c8 + c4); c->rc.droll = (float *) (b + 3 * c8 + 2 * c4);
+      c->rc.ddy = (float *) (b + 3 * c8 + 3 * c4); c->rc.ddz = (float *) (b + 3 * c8 + 4 * c4); c->rc.ddth = (float *) (b + 3 * c8 + 5 * c4);
    }
    uint64_t n_tiles = (max_photons + kTile - 1) / kTile + 1;
    uint64_t n_super = (n_tiles + kSuperTile - 1) / kSuperTile + 1;
@@ -512,13 +526,30 @@ extern "C" int marxb200_create_photons (marxb200_ctx *c, uint64_t first_ray, uin
    SourceArgs a;
    // time_base_in < 0: continue the running sum from the device scalar (no host round trip)
    fill_source_args (c, a, first_ray, n, time_base_in);
+   if (c->det_dither_dirty)
+     {
+        // an upload left detector-dither values in the per-ray columns: clear all slots once (the fused path never writes them)
+        const size_t c4 = (4 * (size_t) c->capacity + 255) & ~(size_t) 255;
+        CUDA_OK (cudaMemsetAsync (c->rc.ddy, 0, 3 * c4, c->stream));
+     }
    prof_begin (c);
    launch_time_sums (a, c->stream); prof_mark (c, 0);
    launch_time_scan (a, c->stream); prof_mark (c, 1);
    launch_source (a, c->stream); prof_mark (c, 2);
    c->launches += 5;                     // k0_time_sums, k0_time_super/_bases/_tiles, k0_source
-   CUDA_OK (cudaGetLastError ());
+   c->det_dither_dirty = false;          // k0_source rewrote the detector-dither columns of every slot it generated
    c->cur = 0; c->stage_done = 0; c->n_generated = n; c->ordered = true; c->first_mirror_kernel = 0;
+   if (c->D.mode == 2)
+     {
+        // the stock reader ends the simulation at the first ray it cannot bracket (end of the ASPSOL file)
+        launch_exposure_truncate (c->buf[0], c->d_counts + 0, c->d_times, c->aspsol_t_last, 0, c->stream);
+        c->launches += 1;
+        unsigned long long kept = 0;
+        CUDA_OK (cudaMemcpyAsync (&kept, c->d_counts + 0, sizeof (kept), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK (cudaStreamSynchronize (c->stream));
+        c->n_generated = kept;
+     }
+   CUDA_OK (cudaGetLastError ());
    return 0;
 }
 
@@ -528,7 +559,7 @@ extern "C" int marxb200_truncate_exposure (marxb200_ctx *c, double exposure_left
    if (c == nullptr) return fail ("NULL ctx");
    if (c->stage_done != 0) return fail ("marxb200_truncate_exposure: call it directly after marxb200_create_photons");
    CUDA_OK (cudaSetDevice (c->device));
-   launch_exposure_truncate (c->buf[c->cur], c->d_counts + 0, c->d_times, exposure_left, c->stream);
+   launch_exposure_truncate (c->buf[c->cur], c->d_counts + 0, c->d_times, exposure_left, 1, c->stream);
    c->launches += 1;
    unsigned long long n = 0;
    CUDA_OK (cudaMemcpyAsync (&n, c->d_counts + 0, sizeof (n), cudaMemcpyDeviceToHost, c->stream));
@@ -573,6 +604,8 @@ static int run_stage (marxb200_ctx *c, int stage)
    a.compact = c->compact;
    a.source_distance = c->source_distance;
    a.rc = c->rc;
+   // _marx_dither_detector is a no-op when DitherModel=NONE (detector.c:277-278), whatever the records carry
+   a.det_dither = ((c->D.mode == 2) || (c->det_dither_dirty && (c->D.mode != 0))) ? 1 : 0;
    // the mirror stage runs as three kernels (HRMA phases A, B, C, mx_hrma.cuh), each re-packing its survivors
    const int n_kernels = (stage == 1) ? 3 : 1;
    const int k_first = (stage == 1) ? c->first_mirror_kernel : 0;
@@ -737,7 +770,9 @@ extern "C" int marxb200_trace (marxb200_ctx *c, uint64_t first_ray, uint64_t n) 
 extern "C" int marxb200_trace_from (marxb200_ctx *c, uint64_t first_ray, uint64_t n, double time_base_in)
 {
    if (c == nullptr) return fail ("NULL ctx");
-   if (c->compact)
+   // the fused source + HRMA-A kernel serves the compacting path of the NONE / INTERNAL dither models; the ASPSOL model
+   // (end-of-file cut, detector dither columns) and lists that follow an upload carrying detector dither go stage by stage
+   if (c->compact && (c->D.mode != 2) && !c->det_dither_dirty)
      {
         if (-1 == create_and_enter_mirror (c, first_ray, n, time_base_in)) return -1;
      }
@@ -845,6 +880,7 @@ extern "C" int marxb200_upload_from (marxb200_ctx *c, const marxb200_photon_attr
    CUDA_OK (cudaStreamSynchronize (c->stream));
    if (d_ids) cudaFree (d_ids);
    c->stage_done = 0; c->n_generated = n; c->ordered = true; c->first_mirror_kernel = 0;
+   c->det_dither_dirty = true;           // the records may carry dy, dz, dtheta (an ASPSOL run dumped to a rayfile)
    return 0;
 }
 
@@ -908,9 +944,9 @@ const EgressCol kEgressCols[] = {
    {MARXB200_SKY_DITHER_OK, "sky_ra.dat", "RA", 'E', EGRESS_SKY_RA, 4},
    {MARXB200_SKY_DITHER_OK, "sky_dec.dat", "DEC", 'E', EGRESS_SKY_DEC, 4},
    {MARXB200_SKY_DITHER_OK, "sky_roll.dat", "ROLL", 'E', EGRESS_SKY_ROLL, 4},
-   {MARXB200_DET_DITHER_OK, "det_dy.dat", "DET_DY", 'E', EGRESS_ZERO_F32, 4},     // 0 for INTERNAL dither (dither.c:167-182)
-   {MARXB200_DET_DITHER_OK, "det_dz.dat", "DET_DZ", 'E', EGRESS_ZERO_F32, 4},
-   {MARXB200_DET_DITHER_OK, "det_theta.dat", "DET_THETA", 'E', EGRESS_ZERO_F32, 4},
+   {MARXB200_DET_DITHER_OK, "det_dy.dat", "DET_DY", 'E', EGRESS_DET_DY, 4},        // 0 for INTERNAL dither (dither.c:167-182)
+   {MARXB200_DET_DITHER_OK, "det_dz.dat", "DET_DZ", 'E', EGRESS_DET_DZ, 4},
+   {MARXB200_DET_DITHER_OK, "det_theta.dat", "DET_THETA", 'E', EGRESS_DET_THETA, 4},
 };
 constexpr int kNumEgressCols = (int) (sizeof (kEgressCols) / sizeof (kEgressCols[0]));
 static_assert (kNumEgressCols <= kMaxEgressCols, "EgressPlan too small");

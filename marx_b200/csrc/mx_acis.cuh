@@ -20,6 +20,22 @@ MX_HD Vec3 m3_mul_t (const double *m, const Vec3 &v)
    return b;
 }
 
+// Detector dither of one ray (Marx_Dither_Type dy, dz, dtheta; zero for the NONE and INTERNAL models).
+// _marx_dither_detector, detector.c:275-284: the SIM offset moves by (dy, dz) and the detector matrix is rotated about
+// x by dtheta (rotate_matrix :240-266) for this ray.  The reference applies and removes it on its one global matrix, ray
+// after ray, so its matrix drifts by rounding (~1e-16 per ray); here every ray starts from the pristine matrix.
+struct DetDither { double dy, dz, dtheta; };
+MX_HD void det_dither_frame (const double *offset, const double *matrix, const DetDither &dd, double *off, double *M)
+{
+   off[0] = offset[0]; off[1] = offset[1] + dd.dy; off[2] = offset[2] + dd.dz;
+   for (int k = 0; k < 9; k++) M[k] = matrix[k];
+   double s = 0, c = 1;
+   if (dd.dtheta != 0) { s = sin (dd.dtheta); c = cos (dd.dtheta); }
+   const double m00 = M[4], m01 = M[5], m10 = M[7], m11 = M[8];
+   M[4] = m00 * c - m01 * s; M[5] = m00 * s + m01 * c;
+   M[7] = m10 * c - m11 * s; M[8] = m10 * s + m11 * c;
+}
+
 // intersect_with_detector_plane, detector.c:56-109.  must_hit: return 0 as soon as the point is off the chip;
 // otherwise (second pass of DetExtendFlag=yes) report the point anyway and return whether it was on the chip.
 // Plain-array form so that ACIS chips and HRC MCPs share it.
@@ -337,14 +353,22 @@ MX_HD int acis_apply_fef (const AcisDev &A, const AcisChipDev &chip, float x, fl
 // possibly with PHOTON_ACIS_STREAKED set, which is not a "dead" bit).
 MX_HD uint32_t acis_detect (const AcisDev &A, double energy, double t_abs, Vec3 &x, Vec3 &p,
                             int &ccd, float &chipx, float &chipy, int16_t &pha, float &pi, Rng &rng,
-                            float *fef_cum, uint32_t fef_stride)
+                            float *fef_cum, uint32_t fef_stride, const DetDither &dd = DetDither {0.0, 0.0, 0.0})
 {
    const uint32_t UNDETECTED = 0x01, MISSED = 0x08, STREAKED = 0x200;
    uint32_t flags = 0;
-   // _marx_transform_ray, trans.c:66-77 (detector dither offsets are zero for the INTERNAL model, dither.c:177-179)
-   x.x -= A.det_offset[0]; x.y -= A.det_offset[1]; x.z -= A.det_offset[2];
-   x = m3_mul (A.det_matrix, x);
-   p = m3_mul (A.det_matrix, p);
+   // _marx_dither_detector + _marx_transform_ray, detector.c:275-284, trans.c:66-77 (the detector dither is zero for the
+   // INTERNAL model, dither.c:177-179: the frame is then the table's)
+   const double *det_off = A.det_offset, *det_mat = A.det_matrix;
+   double off_l[3], mat_l[9];
+   if ((A.dither_mode != 0) && ((dd.dy != 0) || (dd.dz != 0) || (dd.dtheta != 0)))
+     {
+        det_dither_frame (A.det_offset, A.det_matrix, dd, off_l, mat_l);
+        det_off = off_l; det_mat = mat_l;
+     }
+   x.x -= det_off[0]; x.y -= det_off[1]; x.z -= det_off[2];
+   x = m3_mul (det_mat, x);
+   p = m3_mul (det_mat, p);
 
    double dx = 0, dy = 0;
    Vec3 xh = x;
@@ -392,9 +416,9 @@ MX_HD uint32_t acis_detect (const AcisDev &A, double energy, double t_abs, Vec3 
           }
      }
    // _marx_transform_ray_reverse, trans.c:79-90
-   p = m3_mul_t (A.det_matrix, p);
-   x = m3_mul_t (A.det_matrix, x);
-   x.x += A.det_offset[0]; x.y += A.det_offset[1]; x.z += A.det_offset[2];
+   p = m3_mul_t (det_mat, p);
+   x = m3_mul_t (det_mat, x);
+   x.x += det_off[0]; x.y += det_off[1]; x.z += det_off[2];
    return flags;
 }
 

@@ -110,7 +110,8 @@ MX_HD void hrc_blur (const HrcDev &D, double &dx, double &dy, Rng &rng)
 
 // _marx_hrc_s_detect for one ray (preceded by _marx_drake_reflect when HRC-HESF=yes).  Returns flags.
 MX_HD uint32_t hrc_s_detect (const HrcDev &D, double energy, Vec3 &x, Vec3 &p, int &ccd, int &region,
-                             float &ypix, float &zpix, float &upix, float &vpix, int16_t &pha, Rng &rng)
+                             float &ypix, float &zpix, float &upix, float &vpix, int16_t &pha, Rng &rng,
+                             const DetDither &dd = DetDither {0.0, 0.0, 0.0})
 {
    const uint32_t UNDETECTED = 0x01, MISSED = 0x08, DRAKE_BLOCKED = 0x20, DRAKE_REFLECTED = 0x100;
    uint32_t flags = 0;
@@ -120,9 +121,17 @@ MX_HD uint32_t hrc_s_detect (const HrcDev &D, double energy, Vec3 &x, Vec3 &p, i
         if (h < 0) return DRAKE_BLOCKED;
         if (h > 0) flags |= DRAKE_REFLECTED;
      }
-   x.x -= D.det_offset[0]; x.y -= D.det_offset[1]; x.z -= D.det_offset[2];
-   x = m3_mul (D.det_matrix, x);
-   p = m3_mul (D.det_matrix, p);
+   // _marx_dither_detector + _marx_transform_ray (hrc-s.c:264-270, detector.c:275-284): see det_dither_frame
+   const double *det_off = D.det_offset, *det_mat = D.det_matrix;
+   double off_l[3], mat_l[9];
+   if ((dd.dy != 0) || (dd.dz != 0) || (dd.dtheta != 0))
+     {
+        det_dither_frame (D.det_offset, D.det_matrix, dd, off_l, mat_l);
+        det_off = off_l; det_mat = mat_l;
+     }
+   x.x -= det_off[0]; x.y -= det_off[1]; x.z -= det_off[2];
+   x = m3_mul (det_mat, x);
+   p = m3_mul (det_mat, p);
 
    double dx = 0, dy = 0;
    Vec3 xh = x;
@@ -169,9 +178,9 @@ MX_HD uint32_t hrc_s_detect (const HrcDev &D, double energy, Vec3 &x, Vec3 &p, i
         ypix = (float) (d.u_start + dx / D.u_pixel_size);
         zpix = (float) (d.v_start + dy / D.v_pixel_size);
         upix = 0.f; vpix = 0.f;
-        p = m3_mul_t (D.det_matrix, p);
-        x = m3_mul_t (D.det_matrix, x);
-        x.x += D.det_offset[0]; x.y += D.det_offset[1]; x.z += D.det_offset[2];
+        p = m3_mul_t (det_mat, p);
+        x = m3_mul_t (det_mat, x);
+        x.x += det_off[0]; x.y += det_off[1]; x.z += det_off[2];
         return flags;
      }
    // _marx_hrc_s_compute_pixel, hrc_s_geom.c:344-394
@@ -180,9 +189,9 @@ MX_HD uint32_t hrc_s_detect (const HrcDev &D, double energy, Vec3 &x, Vec3 &p, i
    upix = (float) u; vpix = (float) v;
    ypix = (float) (d.cx_0 + (u - d.u_0));
    zpix = (float) (d.cy_0 + (v - d.v_0));
-   p = m3_mul_t (D.det_matrix, p);
-   x = m3_mul_t (D.det_matrix, x);
-   x.x += D.det_offset[0]; x.y += D.det_offset[1]; x.z += D.det_offset[2];
+   p = m3_mul_t (det_mat, p);
+   x = m3_mul_t (det_mat, x);
+   x.x += det_off[0]; x.y += det_off[1]; x.z += det_off[2];
    return flags;
 }
 

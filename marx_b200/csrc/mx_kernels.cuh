@@ -26,7 +26,8 @@ struct PhotonSoA
    uint64_t *ray;                        // global ray index (RNG counter; low 32 bits = tag)
    uint32_t *slot;                       // index of the ray inside its batch: the key that restores arrival order
    uint32_t *flags;
-   float *dra, *ddec, *droll;            // Marx_Dither_Type ra/dec/roll (dy,dz,dtheta are 0 for INTERNAL)
+   float *dra, *ddec, *droll;            // Marx_Dither_Type ra/dec/roll
+   float *ddy, *ddz, *ddth;              // Marx_Dither_Type dy/dz/dtheta: detector dither (0 unless DitherModel=FILE)
    float *chipx, *chipy, *pi;
    float *upix, *vpix;                   // HRC u/v pixels
    uint32_t *sorders;                    // LETG support-grating orders, one signed byte per pass
@@ -45,6 +46,7 @@ struct RayConst
    double *energy, *time;
    uint64_t *ray;
    float *dra, *ddec, *droll;
+   float *ddy, *ddz, *ddth;
 };
 
 // Blob staged into shared memory by K1 with one TMA bulk copy.
@@ -90,6 +92,7 @@ struct StageArgs
    const void *blob;                     // K1Blob / K2Blob / K3Blob in global memory
    uint32_t blob_bytes;                  // bytes staged into shared memory from the start of the blob
    uint32_t seg2_off, seg2_bytes;        // optional second staged segment (byte range of the blob), placed behind the first
+   int det_dither;                       // detector stage: read the per-ray detector dither (ASPSOL model or uploaded photons)
 };
 
 struct SourceArgs
@@ -112,7 +115,7 @@ struct SourceArgs
 void launch_time_sums (const SourceArgs &a, cudaStream_t s);
 void launch_time_scan (const SourceArgs &a, cudaStream_t s);
 void launch_source (const SourceArgs &a, cudaStream_t s);
-void launch_exposure_truncate (const PhotonSoA &buf, unsigned long long *n, double *dev_times, double exposure_left, cudaStream_t s);
+void launch_exposure_truncate (const PhotonSoA &buf, unsigned long long *n, double *dev_times, double limit, int inclusive, cudaStream_t s);
 void launch_hrma (const StageArgs &a, int phase, int grid, cudaStream_t s);
 int fused_source_grid (int num_sms);
 void launch_source_hrma (const SourceArgs &a, const StageArgs &st, int grid, cudaStream_t s);   // k0_source + k1_hrma<0> in one kernel   // phase 0,1,2 = k1a,k1b,k1c
@@ -149,7 +152,7 @@ enum EgressKind
    EGRESS_PI = 0, EGRESS_ENERGY, EGRESS_TIME, EGRESS_TAG, EGRESS_XPOS, EGRESS_YPOS, EGRESS_ZPOS, EGRESS_XCOS, EGRESS_YCOS,
    EGRESS_ZCOS, EGRESS_PHA, EGRESS_CCD, EGRESS_CHIPX, EGRESS_CHIPY, EGRESS_HRC_U, EGRESS_HRC_V, EGRESS_MIRROR, EGRESS_REGION,
    EGRESS_ORDER, EGRESS_ORDER1, EGRESS_ORDER2, EGRESS_ORDER3, EGRESS_ORDER4, EGRESS_SKY_RA, EGRESS_SKY_DEC, EGRESS_SKY_ROLL,
-   EGRESS_ZERO_F32, EGRESS_NUM_KINDS
+   EGRESS_DET_DY, EGRESS_DET_DZ, EGRESS_DET_THETA, EGRESS_NUM_KINDS
 };
 constexpr int kMaxEgressCols = 32;
 struct EgressPlan

@@ -101,23 +101,53 @@ MX_HD Vec3 apply_dither (double ra, double dec, double roll, Vec3 p)
 }
 MX_HD bool dither_roll_is_constant (const SourceDev &s, const DitherDev &d)
 {
-   return (d.mode != 0) && (d.roll_amp == 0.0) && (s.source_type == 0);
+   return (d.mode == 1) && (d.roll_amp == 0.0) && (s.source_type == 0);
 }
 
 // dither_ray + get_internal_dither.  t is the absolute time (pt->start_time + arrival_time).
 // The three angles are stored through float fields before use (dither.c:173-175); that rounding is
 // part of the result.
 // rolled != nullptr: the caller supplies dither_roll ((float) nominal_roll, source p) (see above)
+// det: optional, receives the detector dither dy, dz, dtheta (0 unless the ASPSOL model supplies them)
 MX_HD void dither_ray (const DitherDev &d, Rng &rng, double t, Vec3 &p, float &f_ra, float &f_dec, float &f_roll,
-                       const Vec3 *rolled = nullptr)
+                       const Vec3 *rolled = nullptr, float *det = nullptr)
 {
+   if (det != nullptr) { det[0] = 0.0f; det[1] = 0.0f; det[2] = 0.0f; }
    if (d.mode == 0) { f_ra = f_dec = f_roll = 0.0f; return; }
-   t = (2.0 * kPI) * t;
-   // amp * sin(..) is exactly +-0 when the amplitude is 0 (default DitherAmp_Roll): skip the sine then
-   f_ra = (d.ra_amp == 0.0) ? 0.0f : (float) (d.ra_amp * sin (t / d.ra_period + d.ra_phase));
-   f_dec = (d.dec_amp == 0.0) ? 0.0f : (float) (d.dec_amp * sin (t / d.dec_period + d.dec_phase));
-   f_roll = (d.roll_amp == 0.0) ? (float) d.nominal_roll
-                                : (float) (d.nominal_roll + d.roll_amp * sin (t / d.roll_period + d.roll_phase));
+   if (d.mode == 2)
+     {
+        // get_aspsol_dither, dither.c:379-400: the stock reader advances `while (t >= t1)`; photon times never decrease,
+        // so its position is the first state k >= 1 with t < t_k.  (t at or beyond the last state: the reference stops
+        // the simulation there; marxb200_create_photons cuts the batch, the clamp only keeps the access in range.)
+        const double *A = d.aspsol;
+        uint32_t lo = 1, hi = d.num_aspsol - 1;
+        while (lo < hi)
+          {
+             const uint32_t mid = lo + (hi - lo) / 2;
+             if (t < A[7 * mid]) hi = mid; else lo = mid + 1;
+          }
+        const double *s0 = A + 7 * (lo - 1), *s1 = A + 7 * lo;
+        double dt = s1[0] - s0[0];
+        if (dt != 0) dt = (t - s0[0]) / dt;
+        f_ra = (float) (s0[1] + dt * (s1[1] - s0[1]));
+        f_dec = (float) (s0[2] + dt * (s1[2] - s0[2]));
+        f_roll = (float) (s0[3] + dt * (s1[3] - s0[3]));
+        if (det != nullptr)
+          {
+             det[0] = (float) (s0[4] + dt * (s1[4] - s0[4]));
+             det[1] = (float) (s0[5] + dt * (s1[5] - s0[5]));
+             det[2] = (float) (s0[6] + dt * (s1[6] - s0[6]));
+          }
+     }
+   else
+     {
+        t = (2.0 * kPI) * t;
+        // amp * sin(..) is exactly +-0 when the amplitude is 0 (default DitherAmp_Roll): skip the sine then
+        f_ra = (d.ra_amp == 0.0) ? 0.0f : (float) (d.ra_amp * sin (t / d.ra_period + d.ra_phase));
+        f_dec = (d.dec_amp == 0.0) ? 0.0f : (float) (d.dec_amp * sin (t / d.dec_period + d.dec_phase));
+        f_roll = (d.roll_amp == 0.0) ? (float) d.nominal_roll
+                                     : (float) (d.nominal_roll + d.roll_amp * sin (t / d.roll_period + d.roll_phase));
+     }
    double ra = f_ra, dec = f_dec, roll = f_roll;
    double delta_ra = d.aspect_blur * rng.gaussian ();
    double delta_dec = d.aspect_blur * rng.gaussian ();

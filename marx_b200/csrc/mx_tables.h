@@ -33,6 +33,8 @@ struct DitherDev
    int mode;
    double ra_amp, dec_amp, roll_amp, ra_period, dec_period, roll_period, ra_phase, dec_phase, roll_phase;
    double nominal_roll, aspect_blur;
+   const double *aspsol;           // mode 2: [num_aspsol][7] t, ra, dec, roll, dy, dz, dtheta (marxb200_dither_desc)
+   uint32_t num_aspsol;
 };
 
 struct WfoldDev

@@ -77,6 +77,9 @@ struct oracle
    const double *src, *dith, *hrma, *grat, *acis;
    const double *spec_e, *spec_c; uint32_t nspec;
    const double *src_rot, *img_prm; const float *img_cdf; uint32_t nimg;   /* LINE / IMAGE sources */
+   const double *asp; uint32_t nasp, asp_pos; uint64_t last_generated;                                  /* ASPSOL states [nasp][7] (dither.c:288-359) */
+   double asp_t_prev;
+   double xf_off[3], xf_m[9]; int xf_init;                                 /* _Marx_Det_XForm_Matrix: dithered and restored photon after photon */
    const float *opt_e, *opt_b, *opt_d; uint32_t nopt;
    shell_t shell[NUM_SHELLS];
    gshell_t gshell[NUM_SHELLS];
@@ -158,6 +161,11 @@ oracle_t *oracle_open (const char *path, uint64_t seed)
      {
         o->spec_e = (const double *) need (o, "source.spec_energies", &c); o->nspec = (uint32_t) c;
         o->spec_c = (const double *) need (o, "source.spec_cum_flux", &c);
+     }
+   if ((int) o->dith[0] == 2)
+     {
+        o->asp = (const double *) need (o, "dither.aspsol", &c); o->nasp = (uint32_t) (c / 7);
+        if (!o->asp || (o->nasp < 2)) { oracle_close (o); return NULL; }
      }
    if ((int) o->src[0] >= 4)
      {
@@ -261,6 +269,9 @@ oracle_t *oracle_open (const char *path, uint64_t seed)
      }
    return o;
 }
+
+/* rays kept by the last oracle_trace: its n, or fewer when the ASPSOL file ended inside the batch */
+uint64_t oracle_last_generated (const oracle_t *o) { return o ? o->last_generated : 0; }
 
 void oracle_close (oracle_t *o)
 {
@@ -402,7 +413,9 @@ static double interp_d (double x, const double *xp, const double *yp, unsigned i
 
 /* ------------------------------------------------------------------------------------------- */
 /* stage 0: marx_create_photons (source.c:268-384) for POINT sources + dither (dither.c:551-628)  */
-static void stage_source (oracle_t *o, uint64_t first, uint64_t n, double *time_base, oracle_photon *ph)
+/* returns the number of rays kept: n, or fewer when the ASPSOL file ends inside the batch (dither.c:296-301, 361-369:
+ * the first ray the reader cannot bracket is not dithered and ends the simulation, source.c:355, marx.c:577-578) */
+static uint64_t stage_source (oracle_t *o, uint64_t first, uint64_t n, double *time_base, oracle_photon *ph)
 {
    const double *s = o->src, *d = o->dith;
    double mt = (s[11] <= 0.0) ? 0.0 : 1.0 / s[11] / s[12];              /* source.c:260-264 */
@@ -466,9 +479,35 @@ static void stage_source (oracle_t *o, uint64_t first, uint64_t n, double *time_
              /* get_internal_dither, dither.c:167-182: angles pass through float fields */
              double tt = (2.0 * PI) * t, ra, dec, roll, dra, ddec, n3[3], xax[3] = {1, 0, 0};
              double cra, sra, cdec, sdec, cth, sth;
+             if ((int) d[0] == 2)
+               {
+                  /* get_aspsol_dither, dither.c:361-400: the forward-only reader stops at the first state k >= 1 with
+                   * t < t_k (times never decrease); the seven values are interpolated between it and its predecessor
+                   * and stored through the float fields of Marx_Dither_Type */
+                  const double *A = o->asp, *s0, *s1; double dt;
+                  while ((o->asp_pos < o->nasp) && (t >= A[7 * o->asp_pos])) o->asp_pos++;
+                  if (o->asp_pos >= o->nasp)
+                    {
+                       memset (at, 0, sizeof (*at));
+                       *time_base = (i == 0) ? *time_base : ph[i - 1].arrival_time;
+                       return i;
+                    }
+                  s1 = A + 7 * o->asp_pos; s0 = s1 - 7;
+                  dt = s1[0] - s0[0];
+                  if (dt != 0) dt = (t - s0[0]) / dt;
+                  at->dither[0] = (float) (s0[1] + dt * (s1[1] - s0[1]));
+                  at->dither[1] = (float) (s0[2] + dt * (s1[2] - s0[2]));
+                  at->dither[2] = (float) (s0[3] + dt * (s1[3] - s0[3]));
+                  at->dither[3] = (float) (s0[4] + dt * (s1[4] - s0[4]));
+                  at->dither[4] = (float) (s0[5] + dt * (s1[5] - s0[5]));
+                  at->dither[5] = (float) (s0[6] + dt * (s1[6] - s0[6]));
+               }
+             else
+               {
              at->dither[0] = (float) (d[1] * sin (tt / d[4] + d[7]));
              at->dither[1] = (float) (d[2] * sin (tt / d[5] + d[8]));
              at->dither[2] = (float) (d[10] + d[3] * sin (tt / d[6] + d[9]));
+               }
              ra = at->dither[0]; dec = at->dither[1]; roll = at->dither[2];
              dra = d[11] * rng_gauss (&r); ddec = d[11] * rng_gauss (&r);                                /* dither.c:623-624 */
              ra += dra; dec += ddec;
@@ -481,6 +520,7 @@ static void stage_source (oracle_t *o, uint64_t first, uint64_t n, double *time_
           }
      }
    *time_base = t;
+   return n;
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -907,6 +947,36 @@ static int apply_fef (oracle_t *o, const chip_t *ch, float x, float y, double en
    if (*pip < 0) return -1;
    return 0;
 }
+/* _marx_dither_detector / _marx_undither_detector, detector.c:240-295: the ONE global transform is modified and restored
+ * for every photon that reaches the detector, so it drifts by rounding exactly as the reference's does */
+static void xf_rotate (double *m, double theta)
+{
+   double m00, m01, m10, m11, c, s;
+   if (theta == 0) { s = 0; c = 1; } else { s = sin (theta); c = cos (theta); }
+   m00 = m[4]; m01 = m[5]; m10 = m[7]; m11 = m[8];
+   m[4] = m00 * c - m01 * s; m[5] = m00 * s + m01 * c;
+   m[7] = m10 * c - m11 * s; m[8] = m10 * s + m11 * c;
+}
+static void xf_begin (oracle_t *o, const double *off, const double *M)
+{
+   int k;
+   if (o->xf_init) return;
+   for (k = 0; k < 3; k++) o->xf_off[k] = off[k];
+   for (k = 0; k < 9; k++) o->xf_m[k] = M[k];
+   o->xf_init = 1;
+}
+static void xf_dither (oracle_t *o, const oracle_photon *at)
+{
+   if ((int) o->dith[0] == 0) return;
+   o->xf_off[1] += at->dither[3]; o->xf_off[2] += at->dither[4];
+   xf_rotate (o->xf_m, at->dither[5]);
+}
+static void xf_undither (oracle_t *o, const oracle_photon *at)
+{
+   if ((int) o->dith[0] == 0) return;
+   o->xf_off[1] -= at->dither[3]; o->xf_off[2] -= at->dither[4];
+   xf_rotate (o->xf_m, -at->dither[5]);
+}
 static int plane_hit (const double *g, const double *x0, const double *p, double *x, double *dx, double *dy, int must_hit)   /* detector.c:56-109 */
 {
    const double *xll = g + 1, *xhat = g + 4, *yhat = g + 7, *nrm = g + 10; double pdn = dot3 (p, nrm), r[3], f, rx, ry; int hit = 1;
@@ -941,11 +1011,12 @@ static int detector_hit (const double *const *geom, int n, const double *x0, con
 /* stage 3 (HRC-S / HRC-I): _marx_drake_reflect (drake.c:317-372) + _marx_hrc_s_detect (hrc-s.c:236-312) / _marx_hrc_i_detect (hrc-i.c:119-186) */
 static void stage_detect_hrc (oracle_t *o, uint64_t n, oracle_photon *ph)
 {
-   const double *H = o->hrc; const double *off = H + 2, *M = H + 5, *S = H + 16, *B = H + 26;
+   const double *H = o->hrc; const double *off = o->xf_off, *M = o->xf_m, *S = H + 16, *B = H + 26;
    int ideal = (int) H[14], extend = (int) H[15], use_hesf = (int) H[41], nplates = (int) H[42];
    int hrc_i = ((int) H[0] == 2);                                       /* MARX_DETECTOR_HRC_I (hrc-i.c:119-186) */
    double upix = H[39], vpix = H[40], crw = H[43];
    uint64_t i;
+   xf_begin (o, H + 2, H + 5);
    for (i = 0; i < n; i++)
      {
         oracle_photon *at = ph + i; rng_t r; int k, hit = -1; double dx = 0, dy = 0, xh[3]; const double *g = NULL; const mcp_t *m;
@@ -977,14 +1048,15 @@ static void stage_detect_hrc (oracle_t *o, uint64_t n, oracle_photon *ph)
                break;
             }
         if (at->flags & 0xFF) continue;
+        xf_dither (o, at);                                                                               /* hrc-s.c:264-270 */
         at->x[0] -= off[0]; at->x[1] -= off[1]; at->x[2] -= off[2];
         mat3 (M, at->x); mat3 (M, at->p);
         { const double *gg[3]; for (k = 0; k < o->nmcps; k++) gg[k] = o->mcp[k].geom; hit = detector_hit (gg, o->nmcps, at->x, at->p, xh, &dx, &dy, extend); }
-        if (hit < 0) { at->flags |= F_MISSED; at->ccd_num = -1; continue; }
+        if (hit < 0) { at->flags |= F_MISSED; at->ccd_num = -1; goto undither; }
         m = &o->mcp[hit]; g = m->geom;
         at->x[0] = xh[0]; at->x[1] = xh[1]; at->x[2] = xh[2];
         /* apply_hrc_qe, hrc-s.c:192-234 */
-        if (m->nqe && (rng_uniform (&r) >= interp_f ((float) at->energy, m->qe_e, m->qe, m->nqe))) { at->flags |= F_UNDETECTED; at->ccd_num = -1; continue; }
+        if (m->nqe && (rng_uniform (&r) >= interp_f ((float) at->energy, m->qe_e, m->qe, m->nqe))) { at->flags |= F_UNDETECTED; at->ccd_num = -1; goto undither; }
         if (hrc_i) region = 0;                                                                           /* hrc-i.c:88-117: one UVIS filter */
         else
         {
@@ -999,9 +1071,9 @@ static void stage_detect_hrc (oracle_t *o, uint64_t n, oracle_photon *ph)
            else region = -1;
         }
         }
-        if (region < 0) { at->flags |= F_UNDETECTED; at->ccd_num = -1; continue; }
+        if (region < 0) { at->flags |= F_UNDETECTED; at->ccd_num = -1; goto undither; }
         if (o->nfilt[region] && (rng_uniform (&r) >= interp_f ((float) at->energy, o->filt_e[region], o->filt_q[region], o->nfilt[region])))
-          { at->flags |= F_UNDETECTED; at->ccd_num = -1; continue; }
+          { at->flags |= F_UNDETECTED; at->ccd_num = -1; goto undither; }
         at->detector_region = (int8_t) region;
         {                                                                                                /* hrc-i.c:66-85 */
            double e = at->energy;
@@ -1031,24 +1103,28 @@ static void stage_detect_hrc (oracle_t *o, uint64_t n, oracle_photon *ph)
           }
         mat3t (M, at->p); mat3t (M, at->x);
         at->x[0] += off[0]; at->x[1] += off[1]; at->x[2] += off[2];
+      undither:
+        xf_undither (o, at);
      }
 }
 
 static void stage_detect (oracle_t *o, uint64_t n, oracle_photon *ph)
 {
-   const double *A = o->acis; const double *off = A + 2, *M = A + 5;
+   const double *A = o->acis; const double *off = o->xf_off, *M = o->xf_m;
    int ideal = (int) A[14], extend = (int) A[15]; double focal = A[16], texp = A[17], tft = A[18], tframe = A[19];
    uint64_t i;
    if ((int) A[0] == 0) return;
+   xf_begin (o, A + 2, A + 5);
    for (i = 0; i < n; i++)
      {
         oracle_photon *at = ph + i; rng_t r; int k, hit = -1; double dx = 0, dy = 0, xh[3]; const chip_t *ch; const double *g;
         if (at->flags & 0xFF) continue;
         rng_set (&r, o->seed, at->tag, 3);
+        xf_dither (o, at);                                                                               /* acis-s.c:209-211 */
         at->x[0] -= off[0]; at->x[1] -= off[1]; at->x[2] -= off[2];                                      /* trans.c:66-77 */
         mat3 (M, at->x); mat3 (M, at->p);
         { const double *gg[MAX_CHIPS]; for (k = 0; k < o->nchips; k++) gg[k] = o->chip[k].geom; hit = detector_hit (gg, o->nchips, at->x, at->p, xh, &dx, &dy, extend); }
-        if (hit < 0) { at->flags |= F_MISSED; at->ccd_num = -1; continue; }
+        if (hit < 0) { at->flags |= F_MISSED; at->ccd_num = -1; goto undither; }
         ch = &o->chip[hit]; g = ch->geom;
         at->x[0] = xh[0]; at->x[1] = xh[1]; at->x[2] = xh[2];
         at->ccd_num = (int8_t) g[0];
@@ -1059,10 +1135,10 @@ static void stage_detect (oracle_t *o, uint64_t n, oracle_photon *ph)
              qe = ch->nqe ? interp_f (at->energy, ch->qe_e, ch->qe, ch->nqe) : 1.0;
              qf = ch->nfl ? interp_f (at->energy, ch->fl_e, ch->fl, ch->nfl) : 1.0;
              qc = contamination (ch, at->energy, at->y_pixel, at->z_pixel);
-             if (u >= qe * qf * qc) { at->flags |= F_UNDETECTED; continue; }
+             if (u >= qe * qf * qc) { at->flags |= F_UNDETECTED; goto undither; }
           }
         if (-1 == apply_fef (o, ch, at->y_pixel, at->z_pixel, at->energy, &at->pi, &at->pulse_height, &r))
-          { at->pulse_height = -1; at->pi = 0; at->flags |= F_UNDETECTED; continue; }
+          { at->pulse_height = -1; at->pi = 0; at->flags |= F_UNDETECTED; goto undither; }
         if (tft > 0.0)                                                                                   /* acis-i.c:60-89 */
           {
              double t = fmod (at->arrival_time, tframe);
@@ -1079,6 +1155,8 @@ static void stage_detect (oracle_t *o, uint64_t n, oracle_photon *ph)
           }
         mat3t (M, at->p); mat3t (M, at->x);                                                              /* trans.c:79-90 */
         at->x[0] += off[0]; at->x[1] += off[1]; at->x[2] += off[2];
+      undither:
+        xf_undither (o, at);
      }
 }
 
@@ -1090,8 +1168,26 @@ long oracle_trace (oracle_t *o, uint64_t first_ray, uint64_t n, double *time_bas
    if ((o == NULL) || (n == 0)) return -1;
    work = (oracle_photon *) malloc (n * sizeof (oracle_photon));
    if (work == NULL) return -1;
-   stage_source (o, first_ray, n, &tb, work);
+   {
+      /* the ASPSOL reader only moves forward (dither.c:361-369); a trace that restarts the clock rewinds it */
+      uint64_t kept;
+      if (o->asp && ((o->asp_pos < 1) || (tb < o->asp_t_prev))) o->asp_pos = 1;
+      kept = stage_source (o, first_ray, n, &tb, work);
+      o->asp_t_prev = tb;
+      o->last_generated = kept;
+      if (kept < n)
+        {
+           /* the slots behind the cut stay zero in every stage record */
+           memset (work + kept, 0, (n - kept) * sizeof (oracle_photon));
+           if (st0) memset (st0 + kept, 0, (n - kept) * sizeof (oracle_photon));
+           if (st1) memset (st1 + kept, 0, (n - kept) * sizeof (oracle_photon));
+           if (st2) memset (st2 + kept, 0, (n - kept) * sizeof (oracle_photon));
+           if (st3) memset (st3 + kept, 0, (n - kept) * sizeof (oracle_photon));
+           n = kept;
+        }
+   }
    if (time_base) *time_base = tb;
+   if (n == 0) { free (work); return 0; }
    if (st0) memcpy (st0, work, n * sizeof (oracle_photon));
    stage_mirror (o, n, work);
    if (st1) memcpy (st1, work, n * sizeof (oracle_photon));

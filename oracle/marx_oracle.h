@@ -51,6 +51,10 @@ const char *oracle_last_error (void);
 long oracle_trace (oracle_t *o, uint64_t first_ray, uint64_t n, double *time_base,
                    oracle_photon *st0, oracle_photon *st1, oracle_photon *st2, oracle_photon *st3);
 
+/* DitherModel=FILE only: the number of rays the last oracle_trace kept -- its n, or fewer when the ASPSOL file ended
+ * inside the batch (dither.c:296-301; the reference ends the simulation there).  Slots behind the cut are zero. */
+uint64_t oracle_last_generated (const oracle_t *o);
+
 #ifdef __cplusplus
 }
 #endif

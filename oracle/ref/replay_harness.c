@@ -66,6 +66,13 @@ int main (int argc, char **argv)
 	replay_rng_set (ray, RNG_STAGE_SOURCE);
 	if (-1 == marx_create_photons (rs.source, pt, 1, &n, NULL))
 	  return 1;
+	if (n == 0)
+	  {
+	     /* DitherModel=FILE: the ASPSOL file ended (dither.c:296-301); the stock driver stops here (marx.c:577-578).
+	      * The header's ray count becomes the number of rays traced. */
+	     nrays = i;
+	     break;
+	  }
 	pt->attributes[0].tag = (unsigned int) ray;
 	draws[0] = replay_rng_draws ();
 	start_time = pt->start_time;
@@ -89,6 +96,7 @@ int main (int argc, char **argv)
 	fwrite (draws, 4, 4, fp);
 	fwrite (&start_time, 8, 1, fp);
      }
+   if (0 == fseek (fp, 8, SEEK_SET)) fwrite (&nrays, 8, 1, fp);
    fclose (fp);
    return 0;
 }

@@ -39,6 +39,33 @@ def write_beta_image_fits(path=IMAGE_FITS, n=256, cdelt_arcsec=0.5, core_arcsec=
     return path
 
 
+def write_aspsol_fits(path, tstart=7.9e8, duration=6000.0, step=2.05, ra_nom=250.2134679741175, dec_nom=-53.75743813458669,
+                      roll_nom=237.36968458476):
+    """synthetic aspect solution for DitherModel=FILE: one BINTABLE 'ASPSOL' with the seven double columns and the four
+    keywords init_aspsol_dither reads (dither.c:432-500); angles in degrees, dy/dz in mm, like a CXC asol1 file.
+    Lissajous pointing dither (16 arcsec), a slow roll drift and a small SIM motion (dy, dz, dtheta all non-zero, so the
+    per-photon detector dither of detector.c:275-295 is exercised)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "ref"))
+    from synth_acis_caldb import bintable_hdu, primary_hdu
+    n = int(duration / step) + 1
+    t = tstart + step * np.arange(n)
+    ph = 2 * np.pi * (t - tstart)
+    asec = 1.0 / 3600.0
+    cols = [
+        ("time", "D", 1, t),
+        ("ra", "D", 1, ra_nom + 16 * asec / np.cos(np.radians(dec_nom)) * np.sin(ph / 1000.0)),
+        ("dec", "D", 1, dec_nom + 16 * asec * np.sin(ph / 707.1 + 0.3)),
+        ("roll", "D", 1, roll_nom + 25 * asec * np.sin(ph / 3100.0 + 1.1)),
+        ("dy", "D", 1, 0.040 * np.sin(ph / 1800.0) + 0.003),
+        ("dz", "D", 1, 0.025 * np.cos(ph / 2600.0) - 0.002),
+        ("dtheta", "D", 1, 2.0e-3 * np.sin(ph / 4100.0 + 0.7)),
+    ]
+    keys = [("RA_NOM", float(ra_nom)), ("DEC_NOM", float(dec_nom)), ("ROLL_NOM", float(roll_nom)), ("TSTART", float(tstart))]
+    with open(path, "wb") as f:
+        f.write(primary_hdu() + bintable_hdu("ASPSOL", cols, n, extra_keys=keys))
+    return path
+
+
 COMMON = ["ExposureTime=0", "Verbose=0", "SourceFlux=0.003", "TStart=2023.5", "SpectrumType=FLAT"]
 CONFIGS = {
     # BASELINE.json configs[0]

@@ -24,6 +24,8 @@ def lib():
         _LIB.oracle_last_error.restype = C.c_char_p
         _LIB.oracle_trace.restype = C.c_long
         _LIB.oracle_trace.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_double)] + [C.c_void_p] * 4
+        _LIB.oracle_last_generated.restype = C.c_uint64
+        _LIB.oracle_last_generated.argtypes = [C.c_void_p]
     return _LIB
 
 
@@ -43,6 +45,7 @@ class Oracle:
                                 *[st[s].ctypes.data_as(C.c_void_p) for s in range(4)])
         if nd < 0:
             raise RuntimeError("oracle_trace failed")
+        self.last_generated = int(lib().oracle_last_generated(self._h))   # < n: the ASPSOL file ended inside the batch
         return st, tb.value, int(nd)
 
     def close(self):

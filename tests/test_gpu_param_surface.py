@@ -8,9 +8,8 @@ import subprocess
 import numpy as np
 import pytest
 
-from tests.golden.make_golden import write_beta_image_fits
 from tests.test_gpu_oracle import check_cuda_against_oracle
-from tests.test_oracle_vs_reference import CASES, HAVE_REF, REF
+from tests.test_oracle_vs_reference import CASES, HAVE_REF, REF, expand_args
 
 pytestmark = pytest.mark.gpu
 
@@ -39,17 +38,13 @@ def test_cuda_matches_oracle_for_parameter_variation(tmp_path, name, args, seed,
     par = "@@" + os.path.join(REF, "par", "marx.par")
     common = ["ExposureTime=0", "Verbose=0", "SourceFlux=0.003", "TStart=2023.5", "SpectrumType=FLAT"]
     env = dict(os.environ, MARX_DATA_DIR=os.path.join(REF, "data"))
-    if any("%SPECFILE%" in a for a in args):
-        spec = tmp_path / "spec.dat"
-        e = np.linspace(0.4, 9.0, 400)
-        spec.write_text("".join("%.6f %.6e\n" % (x, x ** -1.7 * (1 + 3 * np.exp(-0.5 * ((x - 6.4) / 0.05) ** 2))) for x in e))
-        args = [a.replace("%SPECFILE%", str(spec)) for a in args]
-    if any("%IMAGE%" in a for a in args):
-        args = [a.replace("%IMAGE%", write_beta_image_fits(str(tmp_path / "img.fits"), n=128, cdelt_arcsec=1.0)) for a in args]
-    if not any(a.startswith("SourceType=") for a in args):
-        args = ["SourceType=POINT"] + args
+    # 2^17 rays at the default flux take ~38 ks: stretch the synthetic aspect solution (the ends_early case stays short)
+    args = expand_args(tmp_path, [a.replace("%ASPSOL:6000%", "%ASPSOL:45000%") for a in args])
     pack = str(tmp_path / (name + ".calpack"))
     subprocess.check_call([os.path.join(REF, "calpack_dump"), pack, par] + common + args, env=env, stdout=subprocess.DEVNULL)
     counts = check_cuda_against_oracle(pack, seed, first, 1 << 17)
     print(name, counts)
-    assert counts[0] == 1 << 17 and counts[1] > 0
+    if "ends_early" in name:
+        assert 0 < counts[0] < 1 << 17 and counts[1] > 0
+    else:
+        assert counts[0] == 1 << 17 and counts[1] > 0

@@ -90,9 +90,39 @@ CASES = [
                                "DetExtendFlag=yes", "SourceRA=250.6"], 42, 0, 12000),
     ("det_extend_acis_i", ["MinEnergy=0.5", "MaxEnergy=6.0", "GratingType=NONE", "DetectorType=ACIS-I", "DitherModel=NONE",
                            "DetExtendFlag=yes", "SourceRA=250.35"], 43, 0, 12000),
+    # DitherModel=FILE (dither.c:288-500): synthetic aspect solution with pointing, roll AND SIM motion,
+    # so the per-photon detector dither (detector.c:275-295) is live; the third case ends the file inside the run
+    ("aspsol_hetg_acis_s", ["MinEnergy=0.5", "MaxEnergy=6.0", "GratingType=HETG", "DetectorType=ACIS-S", "DitherModel=FILE",
+                            "DitherFile=%ASPSOL:6000%"], 51, 0, 12000),
+    ("aspsol_letg_hrc_s", ["MinEnergy=0.1", "MaxEnergy=2.0", "GratingType=LETG", "DetectorType=HRC-S", "DitherModel=FILE",
+                           "DitherFile=%ASPSOL:6000%", "AspectBlur=0.2"], 52, 0, 12000),
+    ("aspsol_ends_early_acis_i", ["MinEnergy=0.5", "MaxEnergy=6.0", "GratingType=NONE", "DetectorType=ACIS-I", "DitherModel=FILE",
+                                  "DitherFile=%ASPSOL:1500%"], 53, 0, 12000),
     ("sector_files_off_unit_order", ["MinEnergy=0.8", "MaxEnergy=3.0", "GratingType=HETG", "DetectorType=ACIS-S", "DitherModel=INTERNAL",
                                      "Use_HETG_Sector_Files=no"], 8, 1000, 10000),
 ]
+
+
+def expand_args(tmp_path, args):
+    """materialise the files a case refers to (%SPECFILE%, %IMAGE%, %ASPSOL:<seconds>%) and default the source type"""
+    from tests.golden.make_golden import write_aspsol_fits, write_beta_image_fits
+    if any("%SPECFILE%" in a for a in args):
+        # a FILE spectrum (spectrum.c:214-273): two columns, energy [keV] and flux density
+        spec = tmp_path / "spec.dat"
+        e = np.linspace(0.4, 9.0, 400)
+        spec.write_text("".join("%.6f %.6e\n" % (x, x ** -1.7 * (1 + 3 * np.exp(-0.5 * ((x - 6.4) / 0.05) ** 2))) for x in e))
+        args = [a.replace("%SPECFILE%", str(spec)) for a in args]
+    if any("%IMAGE%" in a for a in args):
+        args = [a.replace("%IMAGE%", write_beta_image_fits(str(tmp_path / "img.fits"), n=128, cdelt_arcsec=1.0)) for a in args]
+    out = []
+    for a in args:
+        if "%ASPSOL:" in a:
+            dur = float(a.split("%ASPSOL:")[1].rstrip("%"))
+            a = a.split("%ASPSOL:")[0] + write_aspsol_fits(str(tmp_path / "asol1.fits"), duration=dur)
+        out.append(a)
+    if not any(a.startswith("SourceType=") for a in out):
+        out = ["SourceType=POINT"] + out
+    return out
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref (compiled reference) not present on this box")
@@ -101,14 +131,7 @@ def test_oracle_matches_fresh_reference_replay(tmp_path, name, args, seed, first
     par = "@@" + os.path.join(REF, "par", "marx.par")
     common = ["ExposureTime=0", "Verbose=0", "SourceFlux=0.003", "TStart=2023.5", "SpectrumType=FLAT"]
     env = dict(os.environ, MARX_DATA_DIR=os.path.join(REF, "data"))
-    if any("%SPECFILE%" in a for a in args):
-        # a FILE spectrum (spectrum.c:214-273): two columns, energy [keV] and flux density
-        spec = tmp_path / "spec.dat"
-        e = np.linspace(0.4, 9.0, 400)
-        spec.write_text("".join("%.6f %.6e\n" % (x, x ** -1.7 * (1 + 3 * np.exp(-0.5 * ((x - 6.4) / 0.05) ** 2))) for x in e))
-        args = [a.replace("%SPECFILE%", str(spec)) for a in args]
-    if not any(a.startswith("SourceType=") for a in args):
-        args = ["SourceType=POINT"] + args
+    args = expand_args(tmp_path, args)
     pack = str(tmp_path / (name + ".calpack"))
     dump = str(tmp_path / (name + ".bin"))
     subprocess.check_call([os.path.join(REF, "calpack_dump"), pack, par] + common + args, env=env,
@@ -118,4 +141,11 @@ def test_oracle_matches_fresh_reference_replay(tmp_path, name, args, seed, first
     hdr, recs = read_replay(dump)
     o = Oracle(pack, seed)
     st, _, _ = o.trace(first, n)
-    check_bit_exact(st, recs["st"], recs["start"])
+    kept = o.last_generated
+    if "ends_early" in name:
+        assert 0 < kept < n, "the ASPSOL file was meant to end inside the run"
+        assert (st[:, kept:].view(np.uint8) == 0).all()
+    else:
+        assert kept == n
+    assert kept == hdr["nrays"] == len(recs)
+    check_bit_exact(st[:, :kept], recs["st"], recs["start"])

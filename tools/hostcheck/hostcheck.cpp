@@ -56,6 +56,13 @@ extern "C" int marxb200_set_dither (marxb200_ctx *, const marxb200_dither_desc *
    gD.ra_period = d->ra_period; gD.dec_period = d->dec_period; gD.roll_period = d->roll_period;
    gD.ra_phase = d->ra_phase; gD.dec_phase = d->dec_phase; gD.roll_phase = d->roll_phase;
    gD.nominal_roll = d->nominal_roll; gD.aspect_blur = d->aspect_blur;
+   gD.aspsol = nullptr; gD.num_aspsol = 0;
+   if (d->mode == 2)
+     {
+        double *t = (double *) malloc (7 * sizeof (double) * d->num_aspsol);
+        memcpy (t, d->aspsol, 7 * sizeof (double) * d->num_aspsol);
+        gD.aspsol = t; gD.num_aspsol = d->num_aspsol;
+     }
    return 0;
 }
 extern "C" int marxb200_set_hrma (marxb200_ctx *, const marxb200_hrma_desc *d)
@@ -124,13 +131,14 @@ int main (int argc, char **argv)
         double dt = source_time_increment (gS, rng);
         double t_abs = t_run + dt;              // reference: start_time (running) + arrival_time
         t_run = t_abs;
-        float dra, ddec, droll;
-        dither_ray (gD, rng, t_abs, p, dra, ddec, droll);
+        float dra, ddec, droll, det[3];
+        dither_ray (gD, rng, t_abs, p, dra, ddec, droll, nullptr, det);
         const marxb200_photon_attr &a0 = r.st[0];
         s_energy.add (relerr (energy, a0.energy), 0);
         s_time.add (relerr (t_abs, r.start + a0.arrival_time), 1e-12);
         for (int k = 0; k < 3; k++) s_p0.add (fabs ((&p.x)[k] - a0.p[k]), tol);
         s_dith.add (fmax (fabs (dra - a0.dither_ra), fmax (fabs (ddec - a0.dither_dec), fabs (droll - a0.dither_roll))), 0);
+        s_dith.add (fmax (fabs (det[0] - a0.dither_dy), fmax (fabs (det[1] - a0.dither_dz), fabs (det[2] - a0.dither_dtheta))), 0);
         if (rng.draw != r.draws[0]) draw_mis[0]++;
         alive[0]++;
         // use the reference's time downstream so that one ulp of time never masks a stage bug
@@ -172,7 +180,8 @@ int main (int argc, char **argv)
              const AcisDev &A = ((const K3Blob *) gB3.data ())->A;
              int ccd = -1; float chipx = 0, chipy = 0, pi = 0; int16_t pha = 0;
              rng.init (seed, ray, 3);
-             { float fef_cum[mx::kMaxGauss]; flags = acis_detect (A, energy, t_abs, x, p, ccd, chipx, chipy, pha, pi, rng, fef_cum, 1); }
+             { float fef_cum[mx::kMaxGauss]; DetDither dd = {a0.dither_dy, a0.dither_dz, a0.dither_dtheta};
+               flags = acis_detect (A, energy, t_abs, x, p, ccd, chipx, chipy, pha, pi, rng, fef_cum, 1, dd); }
              const marxb200_photon_attr &a3 = r.st[3];
              ref_alive = (a3.flags & 0xFF) == 0; my_alive = (flags & 0xFF) == 0;
              if (ref_alive != my_alive || (!my_alive && ((a3.flags & flags) != flags)) || (my_alive && flags != a3.flags))
