@@ -361,6 +361,30 @@ int marxb200_upload_from (marxb200_ctx *ctx, const marxb200_photon_attr *in, uin
 /* debug/parity: download EVERY photon slot of the last stage call, dead ones included (flags say why) */
 int marxb200_download_all (marxb200_ctx *ctx, marxb200_photon_attr *out, uint64_t max_out, uint64_t *n_out);
 
+/* Event tallies: exact integer histograms of the live list, accumulated on the device over any number of batches, so
+ * that per-GPU results are merged with ONE all-reduce (ncclAllReduce sum over the buffer marxb200_tally_device_ptr
+ * returns) instead of moving events.  The reference has no histogram module: these are the tallies its
+ * users derive from the event files (order populations, PHA / PI / energy spectra, chip and focal-plane images), and
+ * the tests check them against the same binning of the downloaded events.
+ * An axis bins column v as floor ((v - lo) * nbins / (hi - lo)); events outside [lo, hi) on any axis are not counted.
+ * Integer-valued columns (PHA, ORDER, CCD, SHELL) bin exactly with unit-width bins, e.g. ORDER lo=-11 hi=12 nbins=23. */
+enum
+{
+   MARXB200_TALLY_ENERGY = 0, MARXB200_TALLY_TIME, MARXB200_TALLY_PHA, MARXB200_TALLY_PI, MARXB200_TALLY_ORDER,
+   MARXB200_TALLY_CCD, MARXB200_TALLY_SHELL, MARXB200_TALLY_CHIPX, MARXB200_TALLY_CHIPY, MARXB200_TALLY_YPOS,
+   MARXB200_TALLY_ZPOS
+};
+typedef struct { int32_t column; uint32_t nbins; double lo, hi; } marxb200_tally_axis;
+/* naxes = 1 or 2 (row-major: bin = bin0 * nbins1 + bin1); returns the tally id (>= 0) or -1 */
+int marxb200_tally_create (marxb200_ctx *ctx, const marxb200_tally_axis *axes, int naxes);
+/* bin the current live list (after whichever stage ran last) into tally `id`; asynchronous on the context's stream */
+int marxb200_tally_accumulate (marxb200_ctx *ctx, int id);
+int marxb200_tally_reset (marxb200_ctx *ctx, int id);
+/* copy the counters (uint64, nbins0 * nbins1 of them) to the host */
+int marxb200_tally_read (marxb200_ctx *ctx, int id, uint64_t *out, uint64_t max_bins);
+/* the device buffer itself, for an in-place all-reduce; synchronises the context's stream first */
+int marxb200_tally_device_ptr (marxb200_ctx *ctx, int id, void **dev_ptr, uint64_t *num_bins);
+
 /* column download of the live list without the AoS detour (bulk egress).
  * Any pointer may be NULL.  Arrays must hold marxb200_get_counts().n_live entries. */
 typedef struct

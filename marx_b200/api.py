@@ -21,7 +21,12 @@ EXPORTED_SYMBOLS = [
     "marxb200_create_photons", "marxb200_truncate_exposure", "marxb200_time_sums", "marxb200_mirror_reflect", "marxb200_grating_diffract",
     "marxb200_detect", "marxb200_restore_order", "marxb200_trace", "marxb200_trace_from", "marxb200_set_profiling", "marxb200_get_kernel_ms", "marxb200_get_counts", "marxb200_get_stage_counts", "marxb200_get_internal_counts", "marxb200_download",
     "marxb200_upload", "marxb200_upload_from", "marxb200_download_all", "marxb200_download_columns", "marxb200_egress_begin", "marxb200_egress_end", "marxb200_write_photons", "marxb200_egress_begin_packed", "marxb200_egress_end_packed", "marxb200_measure_fp64_peak", "marxb200_get_launch_count",
+    "marxb200_tally_create", "marxb200_tally_accumulate", "marxb200_tally_reset", "marxb200_tally_read", "marxb200_tally_device_ptr",
 ]
+
+# marxb200_tally_axis.column (include/marxb200.h)
+TALLY_COLUMNS = {"energy": 0, "time": 1, "pha": 2, "pi": 3, "order": 4, "ccd": 5, "shell": 6, "chipx": 7, "chipy": 8,
+                 "ypos": 9, "zpos": 10}
 
 # Marx_Photon_Attr_Type, marx/libsrc/marx.h:51-100 (136 bytes; offsets probed in SURVEY.md 8a1)
 PHOTON_DTYPE = np.dtype({
@@ -125,6 +130,11 @@ def load_library():
         "marxb200_measure_fp64_peak": [vp, C.POINTER(dbl)],
         "marxb200_egress_begin_packed": [vp, u64, dbl, u64],
         "marxb200_egress_end_packed": [vp, vp, u64, vp],
+        "marxb200_tally_create": [vp, vp, i32],
+        "marxb200_tally_accumulate": [vp, i32],
+        "marxb200_tally_reset": [vp, i32],
+        "marxb200_tally_read": [vp, i32, vp, u64],
+        "marxb200_tally_device_ptr": [vp, i32, C.POINTER(vp), C.POINTER(u64)],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -137,6 +147,38 @@ def load_library():
 class _PackedLayout(C.Structure):
     _fields_ = [("num_cols", C.c_uint32), ("n_rows", C.c_uint64), ("mask", C.c_uint64 * 32), ("file", (C.c_char * 16) * 32),
                 ("type", C.c_char * 32), ("elem_size", C.c_uint32 * 32), ("offset", C.c_uint64 * 32)]
+
+
+class _TallyAxis(C.Structure):
+    _fields_ = [("column", C.c_int32), ("nbins", C.c_uint32), ("lo", C.c_double), ("hi", C.c_double)]
+
+
+class Tally:
+    """a device-resident histogram of the live event list; counts accumulate over batches until reset()"""
+
+    def __init__(self, m, tid, shape):
+        self._m, self.id, self.shape = m, tid, shape
+
+    def accumulate(self):
+        self._m._check(self._m._lib.marxb200_tally_accumulate(self._m._ctx, self.id))
+
+    def reset(self):
+        self._m._check(self._m._lib.marxb200_tally_reset(self._m._ctx, self.id))
+
+    def read(self):
+        out = np.zeros(self.shape, dtype=np.uint64)
+        self._m._check(self._m._lib.marxb200_tally_read(self._m._ctx, self.id, out.ctypes.data_as(C.c_void_p), out.size))
+        return out
+
+    def device_tensor(self):
+        """the counters as a torch int64 tensor ALIASING the device buffer (for an in-place NCCL all-reduce)"""
+        import torch
+        ptr, n = C.c_void_p(), C.c_uint64()
+        self._m._check(self._m._lib.marxb200_tally_device_ptr(self._m._ctx, self.id, C.byref(ptr), C.byref(n)))
+
+        class _Alias:
+            __cuda_array_interface__ = {"shape": (int(n.value),), "typestr": "<i8", "data": (int(ptr.value), False), "version": 2}
+        return torch.as_tensor(_Alias(), device="cuda:%d" % self._m.device).view(self.shape)
 
 
 class _Columns(C.Structure):
@@ -156,6 +198,7 @@ class MarxB200:
     def __init__(self, calpack, device=0, seed=1, max_photons=1 << 20, stream=None):
         self._lib = load_library()
         self._ctx = C.c_void_p()
+        self.device = int(device)
         self._check(self._lib.marxb200_create(C.byref(self._ctx), int(device), int(seed)))
         try:
             if stream is not None:
@@ -223,6 +266,17 @@ class MarxB200:
     def restore_order(self):
         """put the live list back into arrival order (implicit in trace() and download*())"""
         self._check(self._lib.marxb200_restore_order(self._ctx))
+
+    # ---- event tallies: device-resident histograms of the live list (include/marxb200.h, SURVEY 8e) ----
+    def tally_create(self, *axes):
+        """axes: 1 or 2 tuples (column name, nbins, lo, hi); returns a Tally handle"""
+        arr = (_TallyAxis * len(axes))()
+        for k, (col, nbins, lo, hi) in enumerate(axes):
+            arr[k].column, arr[k].nbins, arr[k].lo, arr[k].hi = TALLY_COLUMNS[col], int(nbins), float(lo), float(hi)
+        tid = self._lib.marxb200_tally_create(self._ctx, C.cast(arr, C.c_void_p), len(axes))
+        if tid < 0:
+            raise MarxB200Error(self._lib.marxb200_last_error().decode())
+        return Tally(self, tid, tuple(int(a[1]) for a in axes))
 
     def trace(self, first_ray, n, time_base=-1.0):
         """create -> mirror -> grating -> detect for one batch, device resident (marx.c:569, :240-273)."""

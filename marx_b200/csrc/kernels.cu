@@ -30,6 +30,16 @@
 #include "mx_kernels.cuh"
 #include "../../include/marxb200.h"
 
+// resident CTAs per SM the register allocation is sized for (developer knobs: tools/build_variant.sh)
+#ifndef MX_K1_MINBLOCKS
+#define MX_K1_MINBLOCKS 3
+#endif
+#ifndef MX_K2_MINBLOCKS
+#define MX_K2_MINBLOCKS 3
+#endif
+#ifndef MX_K01_MINBLOCKS
+#define MX_K01_MINBLOCKS 3
+#endif
 namespace mx {
 
 // ---------------------------------------------------------------------------------------------
@@ -341,7 +351,7 @@ __device__ __forceinline__ WarpQueue<ND, NU> &my_queue (unsigned char *smem, uin
 template <int PHASE> struct K1Shape { static constexpr int ND = (PHASE == 1) ? 7 : 6, NU = (PHASE == 1) ? 5 : 2; };
 
 template <int PHASE>
-__global__ void __launch_bounds__ (kStageThreads, 3) k1_hrma (const __grid_constant__ StageArgs a)
+__global__ void __launch_bounds__ (kStageThreads, MX_K1_MINBLOCKS) k1_hrma (const __grid_constant__ StageArgs a)
 {
    constexpr int ND = K1Shape<PHASE>::ND, NU = K1Shape<PHASE>::NU;
    extern __shared__ __align__ (128) unsigned char smem[];
@@ -443,7 +453,7 @@ __global__ void __launch_bounds__ (kStageThreads, 3) k1_hrma (const __grid_const
 }
 
 // K2 ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__ (kStageThreads, 3) k2_grating (const __grid_constant__ StageArgs a)
+__global__ void __launch_bounds__ (kStageThreads, MX_K2_MINBLOCKS) k2_grating (const __grid_constant__ StageArgs a)
 {
    constexpr int ND = 6, NU = 3;
    extern __shared__ __align__ (128) unsigned char smem[];
@@ -500,6 +510,7 @@ __global__ void __launch_bounds__ (kStageThreads, 3) k2_grating (const __grid_co
 #ifndef MX_K3_MINBLOCKS
 #define MX_K3_MINBLOCKS 3
 #endif
+template <bool DET>
 __global__ void __launch_bounds__ (kStageThreads, MX_K3_MINBLOCKS) k3_acis (const __grid_constant__ StageArgs a)
 {
    constexpr int ND = 6, NU = 7;
@@ -521,8 +532,8 @@ __global__ void __launch_bounds__ (kStageThreads, MX_K3_MINBLOCKS) k3_acis (cons
         const uint32_t slot = in.slot[i];
         rng.init (a.seed, a.rc.ray[slot], MARXB200_STAGE_DETECTOR);
         DetDither dd = {0.0, 0.0, 0.0};
-        if (a.det_dither) { dd.dy = a.rc.ddy[slot]; dd.dz = a.rc.ddz[slot]; dd.dtheta = a.rc.ddth[slot]; }
-        uint32_t flags = acis_detect (A, a.rc.energy[slot], a.rc.time[slot], x, p, ccd, chipx, chipy, pha, pi, rng, fef_cum, kStageThreads, dd);
+        if (DET) { dd.dy = a.rc.ddy[slot]; dd.dz = a.rc.ddz[slot]; dd.dtheta = a.rc.ddth[slot]; }
+        uint32_t flags = acis_detect<DET> (A, a.rc.energy[slot], a.rc.time[slot], x, p, ccd, chipx, chipy, pha, pi, rng, fef_cum, kStageThreads, dd);
         d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = p.x; d[4] = p.y; d[5] = p.z;
         // ids produced by the earlier stages travel through the queue (coalesced loads here instead of dependent
         // gathers when a row is flushed): flags use bits 0..9, shell and order ride in the upper half
@@ -561,6 +572,7 @@ __global__ void __launch_bounds__ (kStageThreads, MX_K3_MINBLOCKS) k3_acis (cons
 }
 
 // K3 (HRC-S) -----------------------------------------------------------------------------------
+template <bool DET>
 __global__ void __launch_bounds__ (kStageThreads) k3_hrc (const __grid_constant__ StageArgs a)
 {
    constexpr int ND = 6, NU = 8;
@@ -579,8 +591,8 @@ __global__ void __launch_bounds__ (kStageThreads) k3_hrc (const __grid_constant_
         const uint32_t slot = in.slot[i];
         rng.init (a.seed, a.rc.ray[slot], MARXB200_STAGE_DETECTOR);
         DetDither dd = {0.0, 0.0, 0.0};
-        if (a.det_dither) { dd.dy = a.rc.ddy[slot]; dd.dz = a.rc.ddz[slot]; dd.dtheta = a.rc.ddth[slot]; }
-        uint32_t flags = hrc_s_detect (D, a.rc.energy[slot], x, p, ccd, region, ypix, zpix, upix, vpix, pha, rng, dd);
+        if (DET) { dd.dy = a.rc.ddy[slot]; dd.dz = a.rc.ddz[slot]; dd.dtheta = a.rc.ddth[slot]; }
+        uint32_t flags = hrc_s_detect<DET> (D, a.rc.energy[slot], x, p, ccd, region, ypix, zpix, upix, vpix, pha, rng, dd);
         d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = p.x; d[4] = p.y; d[5] = p.z;
         u[0] = slot;
         u[1] = flags | ((uint32_t) in.shell[i] << 16) | (((uint32_t) (uint8_t) in.order[i]) << 24);
@@ -625,7 +637,7 @@ __global__ void __launch_bounds__ (kStageThreads) k3_hrc (const __grid_constant_
 // pair writes 77 B and re-reads 36 B for every generated ray).  Persistent 256-thread CTAs walk the 256-ray
 // tiles of the canonical time sum (k0_time_sums / k0_time_scan must have run); survivors go through the
 // warp-private re-packing queue straight into the list that k1_hrma<1> consumes.
-__global__ void __launch_bounds__ (kTile, 3) k01_source_hrma (const __grid_constant__ SourceArgs a, const __grid_constant__ StageArgs st)
+__global__ void __launch_bounds__ (kTile, MX_K01_MINBLOCKS) k01_source_hrma (const __grid_constant__ SourceArgs a, const __grid_constant__ StageArgs st)
 {
    constexpr int ND = 6, NU = 2;
    extern __shared__ __align__ (128) unsigned char smem[];
@@ -783,7 +795,7 @@ __global__ void __launch_bounds__ (256) order_gather (OrderArgs a)
         out.time[j] = rc.time[key]; out.aux[j] = in.aux[s];
         out.ray[j] = rc.ray[key]; out.slot[j] = key; out.flags[j] = in.flags[s];
         out.dra[j] = rc.dra[key]; out.ddec[j] = rc.ddec[key]; out.droll[j] = rc.droll[key];
-        out.ddy[j] = rc.ddy[key]; out.ddz[j] = rc.ddz[key]; out.ddth[j] = rc.ddth[key];
+        if (out.ddy != nullptr) { out.ddy[j] = rc.ddy[key]; out.ddz[j] = rc.ddz[key]; out.ddth[j] = rc.ddth[key]; }   // null: detector dither not live
         out.chipx[j] = in.chipx[s]; out.chipy[j] = in.chipy[s]; out.pi[j] = in.pi[s];
         out.pha[j] = in.pha[s]; out.shell[j] = in.shell[s]; out.order[j] = in.order[s]; out.ccd[j] = in.ccd[s];
         out.upix[j] = in.upix[s]; out.vpix[j] = in.vpix[s]; out.sorders[j] = in.sorders[s]; out.region[j] = in.region[s];
@@ -819,7 +831,8 @@ __global__ void __launch_bounds__ (256) soa_to_aos (PhotonSoA in, const unsigned
         r.flags = in.flags[i];
         r.y_pixel = in.chipx[i]; r.z_pixel = in.chipy[i]; r.u_pixel = in.upix[i]; r.v_pixel = in.vpix[i];
         r.dither_ra = in.dra[i]; r.dither_dec = in.ddec[i]; r.dither_roll = in.droll[i];
-        r.dither_dy = in.ddy[i]; r.dither_dz = in.ddz[i]; r.dither_dtheta = in.ddth[i];
+        const bool det = (in.ddy != nullptr);          // null: no detector dither in this run (NONE / INTERNAL models)
+        r.dither_dy = det ? in.ddy[i] : 0.f; r.dither_dz = det ? in.ddz[i] : 0.f; r.dither_dtheta = det ? in.ddth[i] : 0.f;
         r.pi = in.pi[i];
         r.pulse_height = in.pha[i];
         r.mirror_shell = in.shell[i];
@@ -942,9 +955,9 @@ __global__ void __launch_bounds__ (256) egress_pack (PhotonSoA in, const unsigne
                 case EGRESS_SKY_RA: f = in.dra[i]; break;
                 case EGRESS_SKY_DEC: f = in.ddec[i]; break;
                 case EGRESS_SKY_ROLL: f = in.droll[i]; break;
-                case EGRESS_DET_DY: f = in.ddy[i]; break;
-                case EGRESS_DET_DZ: f = in.ddz[i]; break;
-                case EGRESS_DET_THETA: f = in.ddth[i]; break;
+                case EGRESS_DET_DY: f = in.ddy ? in.ddy[i] : 0.0f; break;        // null: 0 for the NONE / INTERNAL models (dither.c:177-179)
+                case EGRESS_DET_DZ: f = in.ddz ? in.ddz[i] : 0.0f; break;
+                case EGRESS_DET_THETA: f = in.ddth ? in.ddth[i] : 0.0f; break;
                 case EGRESS_TAG:
                   reinterpret_cast<uint32_t *> (base)[i] = bswap32 ((uint32_t) in.ray[i]); continue;
                 case EGRESS_PHA:
@@ -970,6 +983,78 @@ void launch_egress_pack (const PhotonSoA &in, const unsigned long long *n, uint6
    if ((max_n == 0) || (plan.num_cols == 0)) return;
    unsigned int grid = (unsigned int) min ((uint64_t) 148 * 8, (max_n + 255) / 256);
    egress_pack<<<grid, 256, 0, s>>> (in, n, max_n, plan, (unsigned char *) dst, dev_start_time, total_time);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Event tallies: exact histograms of the live list (order populations, PHA / PI / energy spectra, chip images ...) kept
+// on the device so that G GPUs merge them with one all-reduce instead of moving events.  Counts are
+// integers: the result does not depend on the order of the list, the grid or the GPU count.  Small histograms are
+// accumulated per CTA in shared memory (u32) and flushed with one 64-bit atomic per non-empty bin; large ones (images)
+// go straight to global atomics, which L2 resolves.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kTallySmemBins = 8192;
+__device__ __forceinline__ bool tally_value (const PhotonSoA &in, int column, unsigned long long i, double &v)
+{
+   switch (column)
+     {
+      case TALLY_ENERGY: v = in.energy[i]; return true;
+      case TALLY_TIME: v = in.time[i]; return true;
+      case TALLY_PHA: v = (double) in.pha[i]; return true;
+      case TALLY_PI: v = (double) in.pi[i]; return true;
+      case TALLY_ORDER: v = (double) in.order[i]; return true;
+      case TALLY_CCD: v = (double) in.ccd[i]; return true;
+      case TALLY_SHELL: v = (double) in.shell[i]; return true;
+      case TALLY_CHIPX: v = (double) in.chipx[i]; return true;
+      case TALLY_CHIPY: v = (double) in.chipy[i]; return true;
+      case TALLY_YPOS: v = in.x1[i]; return true;
+      case TALLY_ZPOS: v = in.x2[i]; return true;
+     }
+   return false;
+}
+__global__ void __launch_bounds__ (256) tally_events (PhotonSoA in, const unsigned long long *n_ptr, uint64_t max_n, TallyPlan plan,
+                                                      unsigned long long *bins, uint32_t total_bins, int use_smem)
+{
+   extern __shared__ uint32_t local[];
+   unsigned long long n = *n_ptr;
+   if (n > max_n) n = max_n;
+   if (use_smem)
+     {
+        for (uint32_t b = threadIdx.x; b < total_bins; b += blockDim.x) local[b] = 0;
+        __syncthreads ();
+     }
+   for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long) gridDim.x * blockDim.x)
+     {
+        if ((in.flags[i] & 0xFFu) != 0) continue;            // in-place lists keep their dead rays
+        uint32_t bin = 0;
+        bool ok = true;
+        for (int a = 0; a < plan.naxes; a++)
+          {
+             double v;
+             ok = ok && tally_value (in, plan.ax[a].column, i, v);
+             const double f = floor ((v - plan.ax[a].lo) * plan.ax[a].scale);
+             ok = ok && (f >= 0.0) && (f < (double) plan.ax[a].nbins);      // NaN fails both
+             if (!ok) break;
+             bin = bin * plan.ax[a].nbins + (uint32_t) f;
+          }
+        if (!ok) continue;
+        if (use_smem) atomicAdd (&local[bin], 1u);
+        else atomicAdd (&bins[bin], 1ULL);
+     }
+   if (use_smem)
+     {
+        __syncthreads ();
+        for (uint32_t b = threadIdx.x; b < total_bins; b += blockDim.x)
+          if (local[b] != 0) atomicAdd (&bins[b], (unsigned long long) local[b]);
+     }
+}
+void launch_tally (const PhotonSoA &in, const unsigned long long *n, uint64_t max_n, const TallyPlan &plan,
+                   unsigned long long *bins, int num_sms, cudaStream_t s)
+{
+   if (max_n == 0) return;
+   uint32_t total = plan.ax[0].nbins * ((plan.naxes > 1) ? plan.ax[1].nbins : 1u);
+   const int use_smem = (total <= kTallySmemBins) ? 1 : 0;
+   unsigned int grid = (unsigned int) min ((uint64_t) num_sms * 4, (max_n + 255) / 256);
+   tally_events<<<grid, 256, use_smem ? total * sizeof (uint32_t) : 0, s>>> (in, n, max_n, plan, bins, total, use_smem);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1050,8 +1135,11 @@ int stage_grid_size (int stage, int num_sms, uint32_t blob_bytes, uint32_t seg2_
       case 11: return occupancy_grid (k1_hrma<1>, num_sms, smem);
       case 12: return occupancy_grid (k1_hrma<2>, num_sms, smem);
       case 2: return occupancy_grid (k2_grating, num_sms, smem);
-      case 3: return occupancy_grid (k3_acis, num_sms, smem);
-      case 4: return occupancy_grid (k3_hrc, num_sms, smem);
+      // the detector-dither variants run on the same grid (ticket-driven persistent kernels: any grid size is correct)
+      case 3: cudaFuncSetAttribute (k3_acis<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+              return occupancy_grid (k3_acis<false>, num_sms, smem);
+      case 4: cudaFuncSetAttribute (k3_hrc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+              return occupancy_grid (k3_hrc<false>, num_sms, smem);
      }
    return num_sms;
 }
@@ -1079,8 +1167,16 @@ void launch_hrma (const StageArgs &a, int phase, int grid, cudaStream_t s)
      }
 }
 void launch_grating (const StageArgs &a, int grid, cudaStream_t s) { k2_grating<<<grid, kStageThreads, stage_smem_bytes (2, a.blob_bytes), s>>> (a); }
-void launch_acis (const StageArgs &a, int grid, cudaStream_t s) { k3_acis<<<grid, kStageThreads, stage_smem_bytes (3, a.blob_bytes), s>>> (a); }
-void launch_hrc (const StageArgs &a, int grid, cudaStream_t s) { k3_hrc<<<grid, kStageThreads, stage_smem_bytes (4, a.blob_bytes), s>>> (a); }
+void launch_acis (const StageArgs &a, int grid, cudaStream_t s)
+{
+   if (a.det_dither) k3_acis<true><<<grid, kStageThreads, stage_smem_bytes (3, a.blob_bytes), s>>> (a);
+   else k3_acis<false><<<grid, kStageThreads, stage_smem_bytes (3, a.blob_bytes), s>>> (a);
+}
+void launch_hrc (const StageArgs &a, int grid, cudaStream_t s)
+{
+   if (a.det_dither) k3_hrc<true><<<grid, kStageThreads, stage_smem_bytes (4, a.blob_bytes), s>>> (a);
+   else k3_hrc<false><<<grid, kStageThreads, stage_smem_bytes (4, a.blob_bytes), s>>> (a);
+}
 
 void launch_soa_to_aos (const PhotonSoA &in, const unsigned long long *n, uint64_t max_n, void *aos,
                         const double *dev_start_time, cudaStream_t s)

@@ -72,6 +72,8 @@ struct marxb200_ctx
    void *blob1 = nullptr, *blob2 = nullptr, *blob3 = nullptr;
    uint32_t blob1_bytes = 0, blob2_bytes = 0, blob3_bytes = 0;
    uint32_t k1b_bytes = 0, k1c_seg2_off = 0, k1c_seg2_bytes = 0;
+   struct Tally { TallyPlan plan; unsigned long long *bins; uint64_t total; };
+   std::vector<Tally> tallies;
    bool det_dither_dirty = false;                // uploaded photons may carry detector dither: the per-ray columns are live
    double aspsol_t_last = 0.0;                   // ASPSOL dither: time of the last state (rays at or beyond it end the run)
    int grid1[3] = {0, 0, 0}, grid2 = 0, grid3 = 0, grid01 = 0;
@@ -595,6 +597,16 @@ extern "C" int marxb200_time_sums (marxb200_ctx *c, uint64_t first_ray, uint64_t
    return 0;
 }
 
+// The detector-dither columns (dy, dz, dtheta) are live only for the ASPSOL model or after an upload that may carry them;
+// otherwise the kernels that move or export whole records see null pointers there and skip / report zeros.
+static bool det_dither_live (const marxb200_ctx *c) { return (c->D.mode == 2) || c->det_dither_dirty; }
+static PhotonSoA observed (const marxb200_ctx *c, const PhotonSoA &b)
+{
+   PhotonSoA v = b;
+   if (!det_dither_live (c)) { v.ddy = nullptr; v.ddz = nullptr; v.ddth = nullptr; }
+   return v;
+}
+
 static int run_stage (marxb200_ctx *c, int stage)
 {
    StageArgs a;
@@ -605,7 +617,7 @@ static int run_stage (marxb200_ctx *c, int stage)
    a.source_distance = c->source_distance;
    a.rc = c->rc;
    // _marx_dither_detector is a no-op when DitherModel=NONE (detector.c:277-278), whatever the records carry
-   a.det_dither = ((c->D.mode == 2) || (c->det_dither_dirty && (c->D.mode != 0))) ? 1 : 0;
+   a.det_dither = (det_dither_live (c) && (c->D.mode != 0)) ? 1 : 0;
    // the mirror stage runs as three kernels (HRMA phases A, B, C, mx_hrma.cuh), each re-packing its survivors
    const int n_kernels = (stage == 1) ? 3 : 1;
    const int k_first = (stage == 1) ? c->first_mirror_kernel : 0;
@@ -655,7 +667,7 @@ static int ensure_order (marxb200_ctx *c)
 {
    if (c->ordered || (c->stage_done <= 0)) { c->ordered = true; return 0; }
    OrderArgs o;
-   o.in = c->buf[c->cur]; o.out = c->buf[1 - c->cur]; o.rc = c->rc;
+   o.in = c->buf[c->cur]; o.out = observed (c, c->buf[1 - c->cur]); o.rc = c->rc;
    o.n_live = c->d_counts + c->stage_done;
    o.n_slots = c->n_generated;
    o.bitmap = c->d_bitmap; o.word_prefix = c->d_word_prefix; o.block_prefix = c->d_block_prefix; o.perm = c->d_perm;
@@ -835,7 +847,7 @@ static int download_impl (marxb200_ctx *c, marxb200_photon_attr *out, uint64_t m
    if (n_out) *n_out = n;
    if (n == 0) return 0;
    if (-1 == ensure_aos (c, n)) return -1;
-   launch_soa_to_aos (c->buf[c->cur], c->d_counts + c->stage_done, n, c->d_aos, c->d_times, c->stream);
+   launch_soa_to_aos (observed (c, c->buf[c->cur]), c->d_counts + c->stage_done, n, c->d_aos, c->d_times, c->stream);
    c->launches += 1;
    CUDA_OK (cudaMemcpyAsync (out, c->d_aos, (size_t) n * sizeof (marxb200_photon_attr), cudaMemcpyDeviceToHost, c->stream));
    CUDA_OK (cudaStreamSynchronize (c->stream));
@@ -906,6 +918,81 @@ extern "C" int marxb200_download_columns (marxb200_ctx *c, const marxb200_column
    COL (ray, ray, uint64_t);
 #undef COL
    CUDA_OK (cudaStreamSynchronize (c->stream));
+   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// event tallies (include/marxb200.h): device-resident histograms of the live list
+// ---------------------------------------------------------------------------------------------
+extern "C" int marxb200_tally_create (marxb200_ctx *c, const marxb200_tally_axis *axes, int naxes)
+{
+   if ((c == nullptr) || (axes == nullptr)) return fail ("marxb200_tally_create: NULL argument");
+   if ((naxes < 1) || (naxes > 2)) return fail ("marxb200_tally_create: 1 or 2 axes, not %d", naxes);
+   marxb200_ctx::Tally t;
+   memset (&t.plan, 0, sizeof (t.plan));
+   t.plan.naxes = naxes;
+   t.total = 1;
+   for (int a = 0; a < naxes; a++)
+     {
+        if ((axes[a].column < 0) || (axes[a].column >= TALLY_NUM_COLUMNS)) return fail ("marxb200_tally_create: unknown column %d", axes[a].column);
+        if ((axes[a].nbins == 0) || !(axes[a].hi > axes[a].lo)) return fail ("marxb200_tally_create: axis %d needs nbins > 0 and hi > lo", a);
+        t.plan.ax[a].column = axes[a].column; t.plan.ax[a].nbins = axes[a].nbins;
+        t.plan.ax[a].lo = axes[a].lo; t.plan.ax[a].scale = (double) axes[a].nbins / (axes[a].hi - axes[a].lo);
+        t.total *= axes[a].nbins;
+     }
+   if (t.total > (1ull << 28)) return fail ("marxb200_tally_create: %llu bins is beyond the 2^28 limit", (unsigned long long) t.total);
+   CUDA_OK (cudaSetDevice (c->device));
+   CUDA_OK (cudaMalloc (&t.bins, t.total * sizeof (unsigned long long)));
+   CUDA_OK (cudaMemsetAsync (t.bins, 0, t.total * sizeof (unsigned long long), c->stream));
+   c->allocs.push_back (t.bins);
+   c->tallies.push_back (t);
+   return (int) c->tallies.size () - 1;
+}
+static marxb200_ctx::Tally *get_tally (marxb200_ctx *c, int id)
+{
+   if (c == nullptr) { fail ("NULL ctx"); return nullptr; }
+   if ((id < 0) || (id >= (int) c->tallies.size ())) { fail ("unknown tally id %d", id); return nullptr; }
+   return &c->tallies[id];
+}
+extern "C" int marxb200_tally_accumulate (marxb200_ctx *c, int id)
+{
+   marxb200_ctx::Tally *t = get_tally (c, id);
+   if (t == nullptr) return -1;
+   if (c->stage_done < 0) return fail ("marxb200_tally_accumulate: no photons");
+   CUDA_OK (cudaSetDevice (c->device));
+   // the compacting kernels leave energy and time in the per-ray constants until the order is restored
+   if (-1 == ensure_order (c)) return -1;
+   launch_tally (c->buf[c->cur], c->d_counts + c->stage_done, c->n_generated, t->plan, t->bins, c->num_sms, c->stream);
+   c->launches += 1;
+   CUDA_OK (cudaGetLastError ());
+   return 0;
+}
+extern "C" int marxb200_tally_reset (marxb200_ctx *c, int id)
+{
+   marxb200_ctx::Tally *t = get_tally (c, id);
+   if (t == nullptr) return -1;
+   CUDA_OK (cudaSetDevice (c->device));
+   CUDA_OK (cudaMemsetAsync (t->bins, 0, t->total * sizeof (unsigned long long), c->stream));
+   return 0;
+}
+extern "C" int marxb200_tally_read (marxb200_ctx *c, int id, uint64_t *out, uint64_t max_bins)
+{
+   marxb200_ctx::Tally *t = get_tally (c, id);
+   if (t == nullptr) return -1;
+   if ((out == nullptr) || (max_bins < t->total)) return fail ("marxb200_tally_read: the buffer must hold %llu counters", (unsigned long long) t->total);
+   CUDA_OK (cudaSetDevice (c->device));
+   CUDA_OK (cudaMemcpyAsync (out, t->bins, t->total * sizeof (unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+   CUDA_OK (cudaStreamSynchronize (c->stream));
+   return 0;
+}
+extern "C" int marxb200_tally_device_ptr (marxb200_ctx *c, int id, void **dev_ptr, uint64_t *num_bins)
+{
+   marxb200_ctx::Tally *t = get_tally (c, id);
+   if (t == nullptr) return -1;
+   CUDA_OK (cudaSetDevice (c->device));
+   CUDA_OK (cudaStreamSynchronize (c->stream));
+   if (dev_ptr) *dev_ptr = t->bins;
+   if (num_bins) *num_bins = t->total;
    return 0;
 }
 
@@ -982,7 +1069,7 @@ extern "C" int marxb200_write_photons (marxb200_ctx *c, const char *dir, uint64_
         // the AoS staging buffer (136 B per photon) is always large enough: at most 29 columns x 4 B = 116 B per row
         if (-1 == ensure_aos (c, n + 16)) return -1;
         if (-1 == ensure_pinned (c, (size_t) total)) return -1;
-        launch_egress_pack (c->buf[c->cur], c->d_counts + c->stage_done, n, plan, c->d_aos, c->d_times, total_time, c->stream);
+        launch_egress_pack (observed (c, c->buf[c->cur]), c->d_counts + c->stage_done, n, plan, c->d_aos, c->d_times, total_time, c->stream);
         c->launches += 1;
         CUDA_OK (cudaMemcpyAsync (c->h_pinned, c->d_aos, (size_t) total, cudaMemcpyDeviceToHost, c->stream));
         CUDA_OK (cudaStreamSynchronize (c->stream));
@@ -1132,7 +1219,7 @@ extern "C" int marxb200_egress_begin_packed (marxb200_ctx *c, uint64_t write_mas
         total += (uint64_t) align16 ((size_t) max_out * kEgressCols[k].size);
      }
    CUDA_OK (cudaStreamWaitEvent (c->stream, c->ev_copied, 0));      // the slab may still be read by the previous copy
-   launch_egress_pack (c->buf[c->cur], c->d_counts + c->stage_done, max_out, plan, c->egress_slab, c->d_times, total_time, c->stream);
+   launch_egress_pack (observed (c, c->buf[c->cur]), c->d_counts + c->stage_done, max_out, plan, c->egress_slab, c->d_times, total_time, c->stream);
    c->launches += 1;
    CUDA_OK (cudaMemcpyAsync (c->h_egress_count, c->d_counts + c->stage_done, sizeof (unsigned long long), cudaMemcpyDeviceToHost, c->stream));
    CUDA_OK (cudaEventRecord (c->ev_staged, c->stream));

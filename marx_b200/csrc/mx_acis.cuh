@@ -351,6 +351,8 @@ MX_HD int acis_apply_fef (const AcisDev &A, const AcisChipDev &chip, float x, fl
 
 // _marx_acis_s_detect for one ray.  t_abs = pt->start_time + arrival_time.  Returns flags (0 alive,
 // possibly with PHOTON_ACIS_STREAKED set, which is not a "dead" bit).
+// DET: the per-ray detector dither is live (ASPSOL model / uploaded records); false compiles the table-frame path only
+template <bool DET = false>
 MX_HD uint32_t acis_detect (const AcisDev &A, double energy, double t_abs, Vec3 &x, Vec3 &p,
                             int &ccd, float &chipx, float &chipy, int16_t &pha, float &pi, Rng &rng,
                             float *fef_cum, uint32_t fef_stride, const DetDither &dd = DetDither {0.0, 0.0, 0.0})
@@ -361,7 +363,7 @@ MX_HD uint32_t acis_detect (const AcisDev &A, double energy, double t_abs, Vec3 
    // INTERNAL model, dither.c:177-179: the frame is then the table's)
    const double *det_off = A.det_offset, *det_mat = A.det_matrix;
    double off_l[3], mat_l[9];
-   if ((A.dither_mode != 0) && ((dd.dy != 0) || (dd.dz != 0) || (dd.dtheta != 0)))
+   if (DET && (A.dither_mode != 0) && ((dd.dy != 0) || (dd.dz != 0) || (dd.dtheta != 0)))
      {
         det_dither_frame (A.det_offset, A.det_matrix, dd, off_l, mat_l);
         det_off = off_l; det_mat = mat_l;

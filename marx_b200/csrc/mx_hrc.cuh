@@ -109,6 +109,7 @@ MX_HD void hrc_blur (const HrcDev &D, double &dx, double &dy, Rng &rng)
 }
 
 // _marx_hrc_s_detect for one ray (preceded by _marx_drake_reflect when HRC-HESF=yes).  Returns flags.
+template <bool DET = false>
 MX_HD uint32_t hrc_s_detect (const HrcDev &D, double energy, Vec3 &x, Vec3 &p, int &ccd, int &region,
                              float &ypix, float &zpix, float &upix, float &vpix, int16_t &pha, Rng &rng,
                              const DetDither &dd = DetDither {0.0, 0.0, 0.0})
@@ -124,7 +125,7 @@ MX_HD uint32_t hrc_s_detect (const HrcDev &D, double energy, Vec3 &x, Vec3 &p, i
    // _marx_dither_detector + _marx_transform_ray (hrc-s.c:264-270, detector.c:275-284): see det_dither_frame
    const double *det_off = D.det_offset, *det_mat = D.det_matrix;
    double off_l[3], mat_l[9];
-   if ((dd.dy != 0) || (dd.dz != 0) || (dd.dtheta != 0))
+   if (DET && ((dd.dy != 0) || (dd.dz != 0) || (dd.dtheta != 0)))
      {
         det_dither_frame (D.det_offset, D.det_matrix, dd, off_l, mat_l);
         det_off = off_l; det_mat = mat_l;

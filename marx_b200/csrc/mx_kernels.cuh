@@ -154,6 +154,17 @@ enum EgressKind
    EGRESS_ORDER, EGRESS_ORDER1, EGRESS_ORDER2, EGRESS_ORDER3, EGRESS_ORDER4, EGRESS_SKY_RA, EGRESS_SKY_DEC, EGRESS_SKY_ROLL,
    EGRESS_DET_DY, EGRESS_DET_DZ, EGRESS_DET_THETA, EGRESS_NUM_KINDS
 };
+// Event tallies (marxb200_tally_*): exact integer histograms of the live list, 1 or 2 axes
+enum TallyColumn
+{
+   TALLY_ENERGY = 0, TALLY_TIME, TALLY_PHA, TALLY_PI, TALLY_ORDER, TALLY_CCD, TALLY_SHELL, TALLY_CHIPX, TALLY_CHIPY,
+   TALLY_YPOS, TALLY_ZPOS, TALLY_NUM_COLUMNS
+};
+struct TallyAxis { int column; uint32_t nbins; double lo, scale; };      // bin = floor ((v - lo) * scale), dropped unless 0 <= bin < nbins
+struct TallyPlan { int naxes; TallyAxis ax[2]; };
+void launch_tally (const PhotonSoA &in, const unsigned long long *n, uint64_t max_n, const TallyPlan &plan,
+                   unsigned long long *bins, int num_sms, cudaStream_t s);
+
 constexpr int kMaxEgressCols = 32;
 struct EgressPlan
 {

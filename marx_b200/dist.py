@@ -8,7 +8,9 @@ identical for any GPU count.  Two small exchanges remain:
   sums of their block (n/65536 doubles) and add the lower ranks' sums sequentially -> `block_time_bases`;
 * the per-GPU event lists are merged on demand: blocks are contiguous in ray index and arrival time, so
   the time-ordered merge the reference's marxcat performs (marx/src/marxcat.c:505-535) degenerates to a
-  concatenation in rank order -> `gather_event_columns`.
+  concatenation in rank order -> `gather_event_columns`;
+* tallies (device-resident histograms, marxb200_tally_*) are summed over the ranks with one all-reduce on the device
+  buffer itself -> `allreduce_tally`.
 """
 import numpy as np
 
@@ -70,3 +72,12 @@ def gather_event_columns(cols, rank, world, dst=0, device=None):
             parts = [bufs[r][:counts[r]].cpu().numpy().reshape(-1).view(a.dtype) for r in range(world)]
             out[name] = np.concatenate(parts)
     return out
+
+
+def allreduce_tally(counts):
+    """counts: an integer torch tensor -- on the GPU box the alias of a tally's device buffer (Tally.device_tensor(),
+    NCCL sums in place over NVLink, no host copy), in the CPU tests a gloo tensor.  After the call every rank holds the
+    sum over all ranks: integer counts, so the merged histogram is exactly what one GPU tracing all rays accumulates."""
+    import torch.distributed as dist
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    return counts

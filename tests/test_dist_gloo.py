@@ -61,3 +61,36 @@ def test_time_base_exchange_and_event_merge(world):
         assert merged[name].dtype == want.dtype and (merged[name] == want).all()
     assert (np.diff(merged["time"]) >= 0).all()          # rank order == arrival order
     assert all(res[r][5] is None for r in range(1, world))
+
+
+def _tally_worker(rank, world, port, q):
+    from marx_b200.dist import allreduce_tally
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(7 + rank)
+    local = rng.integers(0, 1000, size=(10, 7)).astype(np.int64)
+    if rank == 1:
+        local[:] = 0                             # a rank without events
+    merged = allreduce_tally(torch.from_numpy(local.copy()))
+    q.put((rank, local, merged.numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_tally_allreduce(world):
+    """per-rank histograms are summed in place on every rank (the GPU path hands the device buffer itself to NCCL)"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_tally_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    total = sum(r[1] for r in res)
+    for r in res:
+        assert (r[2] == total).all()

@@ -181,7 +181,7 @@ int main (int argc, char **argv)
              int ccd = -1; float chipx = 0, chipy = 0, pi = 0; int16_t pha = 0;
              rng.init (seed, ray, 3);
              { float fef_cum[mx::kMaxGauss]; DetDither dd = {a0.dither_dy, a0.dither_dz, a0.dither_dtheta};
-               flags = acis_detect (A, energy, t_abs, x, p, ccd, chipx, chipy, pha, pi, rng, fef_cum, 1, dd); }
+               flags = acis_detect<true> (A, energy, t_abs, x, p, ccd, chipx, chipy, pha, pi, rng, fef_cum, 1, dd); }
              const marxb200_photon_attr &a3 = r.st[3];
              ref_alive = (a3.flags & 0xFF) == 0; my_alive = (flags & 0xFF) == 0;
              if (ref_alive != my_alive || (!my_alive && ((a3.flags & flags) != flags)) || (my_alive && flags != a3.flags))

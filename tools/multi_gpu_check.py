@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 
 import marx_b200
-from marx_b200.dist import exchange_time_base, gather_event_columns
+from marx_b200.dist import allreduce_tally, exchange_time_base, gather_event_columns
 
 
 def main():
@@ -24,11 +24,16 @@ def main():
     with marx_b200.MarxB200("c2_hetg_acis_s", device=local, seed=77, max_photons=n * world) as m:
         running = 0.0
         merged_steps = []
+        # device-resident tallies, accumulated over the steps and summed over the ranks with one in-place NCCL all-reduce
+        specs = [(("order", 23, -11, 12),), (("pha", 1024, 0, 4096),), (("ccd", 10, 0, 10), ("chipx", 64, 0, 1024))]
+        tallies = [m.tally_create(*sp) for sp in specs]
         for step in range(2):
             first = (step * world + rank) * n
             base, running = exchange_time_base(m.time_sums(first, n), rank, world, running, device=dev)
             m.create_photons(first, n, base)
             m.mirror_reflect(); m.grating_diffract(); m.detect()
+            for t in tallies:
+                t.accumulate()
             cols = m.download_columns(names)
             merged = gather_event_columns(cols, rank, world, dst=0, device=dev)
             if rank == 0:
@@ -36,8 +41,17 @@ def main():
         # stage-count "histogram" merge: all-reduce over NCCL
         cnt = torch.tensor(m.stage_counts(), device=dev, dtype=torch.int64)
         dist.all_reduce(cnt)
+        merged_tallies = [allreduce_tally(t.device_tensor()).cpu().numpy() for t in tallies]
         if rank == 0:
             got = {k: np.concatenate([s[k] for s in merged_steps]) for k in names}
+            # the all-reduced tallies equal the binning of the merged event list (= of the single-GPU trace, checked below)
+            o = got["order"].astype(np.int64)
+            assert (merged_tallies[0] == np.bincount(o + 11, minlength=23)).all()
+            assert (merged_tallies[1] == np.bincount(got["pha"].astype(np.int64) // 4, minlength=1024)).all()
+            img = np.zeros((10, 64), dtype=np.int64)
+            np.add.at(img, (got["ccd"].astype(np.int64), np.floor(got["chipx"].astype(np.float64) * (64 / 1024.0)).astype(np.int64)), 1)
+            assert (merged_tallies[2] == img).all()
+            assert merged_tallies[0].sum() == len(o)
             m.create_photons(0, n * world, 0.0)
             m.mirror_reflect(); m.grating_diffract(); m.detect()
             a = m.download_columns(names)
@@ -51,8 +65,8 @@ def main():
                 else:
                     assert (got[k] == ref[k]).all(), k
             assert (np.diff(got["ray"].astype(np.int64)) > 0).all() and (np.diff(got["time"]) >= 0).all()
-            print("multi_gpu_check OK: world=%d, %d events identical to the single-GPU trace; all-reduced last-step counts %s"
-                  % (world, len(got["ray"]), cnt.tolist()))
+            print("multi_gpu_check OK: world=%d, %d events identical to the single-GPU trace; all-reduced tallies (order, PHA, ccd x chipx) "
+                  "equal the binned merged list; all-reduced last-step counts %s" % (world, len(got["ray"]), cnt.tolist()))
     dist.barrier()
     dist.destroy_process_group()
 
