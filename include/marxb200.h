@@ -337,8 +337,8 @@ int marxb200_trace_from (marxb200_ctx *ctx, uint64_t first_ray, uint64_t n, doub
  * event is recorded after every kernel launch; marxb200_get_kernel_ms synchronises, returns the accumulated
  * milliseconds and launch counts per kernel class since the last call, and resets them.  Classes:
  * 0 k0_time_sums, 1 k0_time_scan (k0_time_super + k0_time_bases + k0_time_tiles), 2 k0_source, 3 k01_source_hrma (fused), 4 k1_hrma<0>, 5 k1_hrma<1>, 6 k1_hrma<2>,
- * 7 k2_grating, 8 k3 (acis or hrc), 9 order restoration (5 kernels). */
-#define MARXB200_NUM_KERNEL_CLASSES 10
+ * 7 k2_grating, 8 k3 (acis or hrc), 9 order restoration (5 kernels), 10 Level-1 transforms (marxb200_level1_transform). */
+#define MARXB200_NUM_KERNEL_CLASSES 11
 int marxb200_set_profiling (marxb200_ctx *ctx, int on);
 int marxb200_get_kernel_ms (marxb200_ctx *ctx, double ms[MARXB200_NUM_KERNEL_CLASSES], uint64_t launches[MARXB200_NUM_KERNEL_CLASSES]);
 
@@ -452,6 +452,88 @@ typedef struct
 marxb200_packed_layout;
 int marxb200_egress_begin_packed (marxb200_ctx *ctx, uint64_t write_mask, double total_time, uint64_t max_out);
 int marxb200_egress_end_packed (marxb200_ctx *ctx, void *host, uint64_t host_bytes, marxb200_packed_layout *layout);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Level-1 event transforms: the per-event part of marx2fits (marx/src/marx2fits.c:3584-3943) for the
+ * device-resident event list, so that `marx` + `marx2fits` need no intermediate column files.  marx2fits reads the
+ * float32/int16/int8 column files of a MARX output directory row by row and derives, per event (compute order = the order
+ * of Data_Def_Table, :274-1252):
+ *   EXPNO      compute_expno :3741-3763        (long) (time / TimeDel); time is the float32 of time.dat
+ *   TDETX/Y    compute_tdetxy :3584-3599       marx_compute_tiled_pixel, detpix.c:151-177 (acis_geom.c:111-143,181-202,
+ *                                              hrc_s_geom.c:477-515, hrc_i_geom.c:216-236)
+ *   (aspect)   read_dither_value :3567-3580    the 6 dither values are only taken over when EXPNO changed (ACIS) -- every
+ *                                              event of an exposure frame carries the aspect of the frame's FIRST event
+ *   FLTGRADE   compute_fltgrade :3854-3866     1 uniform draw per row (ACIS)
+ *   GRADE      compute_grade :3813-3818
+ *   DETX/Y     compute_detxy :3676-3737        pixel adjustment (NONE / RANDOMIZE: 2 draws / EDSER: acis_subpix.c:283-321 /
+ *                                              EXACT), marx_init_chip_to_mnc + marx_chip_to_mnc (pixlib.c:139-225),
+ *                                              marx_mnc_to_fpc (detpix.c:182-209)
+ *   X/Y        compute_xy_sky :3869-3911       marx_undither_mnc (dither.c:583-607,703-707), marx_mnc_to_ra_dec +
+ *                                              marx_compute_ra_dec_offsets (pixlib.c:503-573); roll rotation without dither
+ *   ENERGY     compute_acis_energy :3923-3929, PI compute_pi :3931-3941, NODE_ID :3765-3771, STATUS :3775-3790
+ *   TIME       write_time :3433-3445           TimeDel * EXPNO + TSTART (ACIS), time + TSTART (HRC)
+ * Rows with pha == -1 are computed (they consume their draws) but not written (:2856-2857): `keep` = 0.
+ * Draw d of event row r (r counts ALL rows since marxb200_level1_reset) = lane d&3 of Philox4x32-10 (key = seed, counter =
+ * (r_lo, r_hi, d>>2, MARXB200_STAGE_LEVEL1)) mapped to [0,1] like every other draw of this library.
+ * The descriptor holds what the stock initialisation (main :3200-3310, get_marx_pfile_info :2371-2562, read_obspar_file
+ * :2961-2985) leaves in marx2fits' statics; INTEGRATION.md shows the binding.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define MARXB200_STAGE_LEVEL1 4
+#define MARXB200_L1_MAX_CHIPS 10
+enum { MARXB200_PIXADJ_NONE = 0, MARXB200_PIXADJ_RANDOMIZE = 1, MARXB200_PIXADJ_EDSER = 2, MARXB200_PIXADJ_EXACT = 3 };   /* marx2fits.c:60-63 */
+
+typedef struct
+{
+   int32_t id;                      /* Marx_Detector_Geometry_Type.id (marx.h:397-425) */
+   int32_t subpix_table;            /* EDSER: 0 = front-illuminated table, 1 = back-illuminated (acis_subpix.c:262-268: CCDs 5, 7) */
+   double x_ll[3], xhat[3], yhat[3];
+   double x_pixel_size, y_pixel_size, xpixel_offset, ypixel_offset;
+   float tdet_xoff, tdet_yoff;      /* acis.h:38-40 / hrc.h:38-40 */
+}
+marxb200_level1_chip;
+
+typedef struct
+{
+   int32_t detector_type;           /* MARX_DETECTOR_HRC_S = 1, HRC_I = 2, ACIS_S = 3, ACIS_I = 4 (marx.h:364-367) */
+   int32_t num_chips;
+   marxb200_level1_chip chips[MARXB200_L1_MAX_CHIPS];
+   double fp_delta_s0, fp_x0, fp_y0;   /* Marx_FP_Coord_Type (detpix.c:41-65) */
+   double focal_length;             /* marx2fits Focal_Length (marx.par FocalLength) */
+   double det_offset[3];            /* DetOffsetX/Y/Z */
+   double time_del;                 /* TimeDel: ACIS exposure (+ frame transfer) time, 0 for HRC (:2539-2542) */
+   double time_start;               /* obs.par TSTART */
+   double pi_factor;                /* 1 / ACIS_eV_Per_PI (:2490-2498) */
+   double nominal_roll;             /* obs.par Roll_Nom, degrees */
+   int32_t used_dither;             /* DitherModel != NONE */
+   int32_t pix_adjust;              /* MARXB200_PIXADJ_*; EDSER on HRC means RANDOMIZE (main :3308-3309) */
+   /* EDSER sub-pixel tables (Subpix_CCD_Type, acis_subpix.c:41-60): for table t and flight grade g, subpix_npoints[t*256+g]
+    * points (0: no correction) stored at subpix_data + subpix_offset[t*256+g] as energies[n], dxs[n], dys[n] */
+   const int32_t *subpix_npoints;
+   const uint32_t *subpix_offset;
+   const float *subpix_data;
+   uint64_t subpix_data_len;
+}
+marxb200_level1_desc;
+
+/* Level-1 columns of the live list, in the types marx2fits computes them in (its writers narrow DETX/Y, X/Y to float32, PI and
+ * STATUS widen to int32: write_float64_as_float32 / write_int16_as_int32, :3370-3431).  Any pointer may be NULL. */
+typedef struct
+{
+   double *time, *detx, *dety, *x, *y;
+   int32_t *expno, *tdetx, *tdety, *pha, *hrc_u, *hrc_v;
+   float *energy;
+   int16_t *ccd_id, *node_id, *chipx, *chipy, *pi, *fltgrade, *grade, *status;
+   uint8_t *keep;
+}
+marxb200_level1_columns;
+
+int marxb200_set_level1 (marxb200_ctx *ctx, const marxb200_level1_desc *d);
+/* start of a new event file: row counter 0, no exposure seen yet (the statics of compute_expno / read_dither_value) */
+int marxb200_level1_reset (marxb200_ctx *ctx);
+/* Transform the live list (arrival order is restored first).  total_time as in marxb200_write_photons: the file's TIME column
+ * is (float) (arrival_time + total_time).  Consecutive calls continue one event file (row counter, exposure state). */
+int marxb200_level1_transform (marxb200_ctx *ctx, double total_time);
+int marxb200_level1_download (marxb200_ctx *ctx, const marxb200_level1_columns *cols, uint64_t max_out, uint64_t *n_out);
 
 /* FP64 roofline denominator measured on this GPU: best of 5 runs of a DFMA-chain kernel (8 independent chains per
  * thread, 8 x 256-thread CTAs per SM), in TFLOP/s counting an FMA as 2 flops.  Diagnostic; leaves the photon list alone. */

@@ -22,6 +22,7 @@ EXPORTED_SYMBOLS = [
     "marxb200_detect", "marxb200_restore_order", "marxb200_trace", "marxb200_trace_from", "marxb200_set_profiling", "marxb200_get_kernel_ms", "marxb200_get_counts", "marxb200_get_stage_counts", "marxb200_get_internal_counts", "marxb200_download",
     "marxb200_upload", "marxb200_upload_from", "marxb200_download_all", "marxb200_download_columns", "marxb200_egress_begin", "marxb200_egress_end", "marxb200_write_photons", "marxb200_egress_begin_packed", "marxb200_egress_end_packed", "marxb200_measure_fp64_peak", "marxb200_get_launch_count",
     "marxb200_tally_create", "marxb200_tally_accumulate", "marxb200_tally_reset", "marxb200_tally_read", "marxb200_tally_device_ptr",
+    "marxb200_set_level1", "marxb200_level1_reset", "marxb200_level1_transform", "marxb200_level1_download",
 ]
 
 # marxb200_tally_axis.column (include/marxb200.h)
@@ -135,6 +136,10 @@ def load_library():
         "marxb200_tally_reset": [vp, i32],
         "marxb200_tally_read": [vp, i32, vp, u64],
         "marxb200_tally_device_ptr": [vp, i32, C.POINTER(vp), C.POINTER(u64)],
+        "marxb200_set_level1": [vp, vp],
+        "marxb200_level1_reset": [vp],
+        "marxb200_level1_transform": [vp, dbl],
+        "marxb200_level1_download": [vp, vp, u64, C.POINTER(u64)],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -283,15 +288,15 @@ class MarxB200:
         self._check(self._lib.marxb200_trace_from(self._ctx, int(first_ray), int(n), float(time_base)))
 
     KERNEL_CLASSES = ("k0_time_sums", "k0_time_scan", "k0_source", "k01_source_hrma", "k1_hrma<0>", "k1_hrma<1>",
-                      "k1_hrma<2>", "k2_grating", "k3_detect", "order_restore")
+                      "k1_hrma<2>", "k2_grating", "k3_detect", "order_restore", "level1")
 
     def set_profiling(self, on):
         self._check(self._lib.marxb200_set_profiling(self._ctx, 1 if on else 0))
 
     def kernel_ms(self):
         """accumulated device milliseconds and launch counts per kernel class since the last call"""
-        ms = (C.c_double * 10)()
-        nl = (C.c_uint64 * 10)()
+        ms = (C.c_double * len(self.KERNEL_CLASSES))()
+        nl = (C.c_uint64 * len(self.KERNEL_CLASSES))()
         self._check(self._lib.marxb200_get_kernel_ms(self._ctx, ms, nl))
         return {k: (float(ms[i]), int(nl[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
 
@@ -378,6 +383,26 @@ class MarxB200:
         device-resident live list; write_mask uses the MARX_*_OK bits (HISTORY below)."""
         self._check(self._lib.marxb200_write_photons(self._ctx, os.fsencode(directory), int(write_mask),
                                                      1 if open_mode else 0, float(total_time)))
+
+    # -- Level-1 event transforms (marx2fits.c:3584-3943 on the device-resident list) -------------------------------
+    def set_level1(self, desc):
+        """desc: marx_b200.level1.Level1Desc (the values the stock marx2fits initialisation derives)"""
+        self._level1_desc = desc              # keeps the arrays the descriptor points into alive during the call
+        self._check(self._lib.marxb200_set_level1(self._ctx, desc.byref()))
+
+    def level1_reset(self):
+        self._check(self._lib.marxb200_level1_reset(self._ctx))
+
+    def level1_transform(self, total_time=0.0):
+        self._check(self._lib.marxb200_level1_transform(self._ctx, float(total_time)))
+
+    def level1_download(self, names=None):
+        from .level1 import alloc_columns
+        _, live, _ = self.counts()
+        cols, arrays = alloc_columns(int(live), names)
+        got = C.c_uint64()
+        self._check(self._lib.marxb200_level1_download(self._ctx, C.byref(cols), max(int(live), 1), C.byref(got)))
+        return {k: v[:got.value] for k, v in arrays.items()}
 
     def download_columns(self, names=("energy", "time", "chipx", "chipy", "pha", "ccd", "order", "ray"), out=None):
         _, live, _ = self.counts()

@@ -95,6 +95,15 @@ struct marxb200_ctx
    bool egress_pending = false, egress_is_packed = false;
    EgressPlan packed_plan; int packed_which[kMaxEgressCols]; uint64_t packed_cap = 0;
 
+   // Level-1 event transforms (marxb200_level1_*)
+   bool have_level1 = false;
+   Level1Dev L1;
+   Level1State *d_l1_state = nullptr;
+   void *l1_slab = nullptr; uint64_t l1_cap = 0; Level1Cols l1_cols;
+   uint32_t *d_l1_head = nullptr, *d_l1_tile_head = nullptr;
+   float *d_l1_next_dither = nullptr; long long *d_l1_next_expno = nullptr; unsigned int *d_l1_error = nullptr;
+   uint64_t l1_rows = 0;                         // rows of the last transform (what marxb200_level1_download returns)
+
    // optional per-kernel timing
    bool profiling = false;
    cudaEvent_t ev_prev = nullptr;
@@ -244,6 +253,8 @@ extern "C" int marxb200_destroy (marxb200_ctx *c)
    if (c->ev_copied) cudaEventDestroy (c->ev_copied);
    if (c->copy_stream) cudaStreamDestroy (c->copy_stream);
    if (c->h_pinned) cudaFreeHost (c->h_pinned);
+   if (c->l1_slab) cudaFree (c->l1_slab);
+   if (c->d_l1_state) cudaFree (c->d_l1_state);
    if (c->own_stream && c->stream) cudaStreamDestroy (c->stream);
    delete c;
    return 0;
@@ -1290,6 +1301,167 @@ extern "C" int marxb200_get_launch_count (marxb200_ctx *c, uint64_t *n)
 {
    if ((c == nullptr) || (n == nullptr)) return fail ("NULL argument");
    *n = c->launches;
+   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Level-1 event transforms (include/marxb200.h; kernels in level1_kernels.cu)
+// ---------------------------------------------------------------------------------------------
+extern "C" int marxb200_level1_reset (marxb200_ctx *c)
+{
+   if (c == nullptr) return fail ("marxb200_level1_reset: NULL ctx");
+   if (!c->have_level1) return fail ("marxb200_level1_reset: call marxb200_set_level1 first");
+   CUDA_OK (cudaSetDevice (c->device));
+   Level1State st;
+   memset (&st, 0, sizeof (st));
+   st.last_expno = -1;                          // static long last_expno = -1 (marx2fits.c:3743)
+   CUDA_OK (cudaMemcpyAsync (c->d_l1_state, &st, sizeof (st), cudaMemcpyHostToDevice, c->stream));
+   CUDA_OK (cudaMemsetAsync (c->d_l1_error, 0, sizeof (unsigned int), c->stream));
+   CUDA_OK (cudaStreamSynchronize (c->stream));
+   c->l1_rows = 0;
+   return 0;
+}
+
+extern "C" int marxb200_set_level1 (marxb200_ctx *c, const marxb200_level1_desc *d)
+{
+   if ((c == nullptr) || (d == nullptr)) return fail ("marxb200_set_level1: NULL argument");
+   if ((d->detector_type < 1) || (d->detector_type > 4)) return fail ("marxb200_set_level1: detector type %d is not HRC-S/HRC-I/ACIS-S/ACIS-I", d->detector_type);
+   if ((d->num_chips < 1) || (d->num_chips > MARXB200_L1_MAX_CHIPS)) return fail ("marxb200_set_level1: %d chips", d->num_chips);
+   if ((d->pix_adjust < 0) || (d->pix_adjust > 3)) return fail ("marxb200_set_level1: unknown pixel adjustment %d", d->pix_adjust);
+   const bool acis = (d->detector_type >= 3);
+   int pix_adjust = d->pix_adjust;
+   if (!acis && (pix_adjust == MARXB200_PIXADJ_EDSER)) pix_adjust = MARXB200_PIXADJ_RANDOMIZE;     // marx2fits main :3308-3309
+   if ((pix_adjust == MARXB200_PIXADJ_EDSER) && ((d->subpix_npoints == nullptr) || (d->subpix_offset == nullptr) || (d->subpix_data == nullptr)))
+     return fail ("marxb200_set_level1: EDSER needs the sub-pixel tables");
+   if (!(d->fp_delta_s0 > 0.0)) return fail ("marxb200_set_level1: focal-plane pixel size must be positive");
+   CUDA_OK (cudaSetDevice (c->device));
+   Level1Dev &L = c->L1;
+   memset (&L, 0, sizeof (L));
+   L.detector_type = d->detector_type; L.num_chips = d->num_chips;
+   for (int k = 0; k < d->num_chips; k++)
+     {
+        const marxb200_level1_chip &s = d->chips[k];
+        Level1ChipDev &g = L.chips[k];
+        g.id = s.id; g.subpix_table = s.subpix_table ? 1 : 0;
+        for (int j = 0; j < 3; j++) { g.x_ll[j] = s.x_ll[j]; g.xhat[j] = s.xhat[j]; g.yhat[j] = s.yhat[j]; }
+        g.x_pixel_size = s.x_pixel_size; g.y_pixel_size = s.y_pixel_size;
+        g.xpixel_offset = s.xpixel_offset; g.ypixel_offset = s.ypixel_offset;
+        g.tdet_xoff = s.tdet_xoff; g.tdet_yoff = s.tdet_yoff;
+     }
+   L.fp_delta_s0 = d->fp_delta_s0; L.fp_x0 = d->fp_x0; L.fp_y0 = d->fp_y0;
+   L.focal_length = d->focal_length;
+   for (int j = 0; j < 3; j++) L.det_offset[j] = d->det_offset[j];
+   L.time_del = d->time_del; L.time_start = d->time_start; L.pi_factor = d->pi_factor;
+   // compute_xy_sky :3881-3883 evaluates these per event with the host's libm; the values are constants of the run
+   const double theta = d->nominal_roll * 3.14159265358979323846 / 180.0;
+   L.roll_cos = cos (theta); L.roll_sin = sin (theta);
+   L.used_dither = d->used_dither ? 1 : 0; L.pix_adjust = pix_adjust;
+   if (pix_adjust == MARXB200_PIXADJ_EDSER)
+     {
+        for (int k = 0; k < 2 * 256; k++)
+          {
+             const int32_t np = d->subpix_npoints[k];
+             if ((np > 0) && ((np == 1) || ((uint64_t) d->subpix_offset[k] + 3ull * (uint64_t) np > d->subpix_data_len)))
+               return fail ("marxb200_set_level1: sub-pixel table entry %d is malformed", k);
+          }
+        if (-1 == dev_upload_t (c, d->subpix_npoints, 2 * 256, &L.subpix_npoints)) return -1;
+        if (-1 == dev_upload_t (c, d->subpix_offset, 2 * 256, &L.subpix_offset)) return -1;
+        if (-1 == dev_upload_t (c, d->subpix_data, (size_t) d->subpix_data_len, &L.subpix_data)) return -1;
+     }
+   if (c->d_l1_state == nullptr)
+     {
+        // state + the two hand-over cells + the error flag in one allocation
+        void *p = nullptr;
+        CUDA_OK (cudaMalloc (&p, 256));
+        c->d_l1_state = (Level1State *) p;
+        c->d_l1_next_dither = (float *) ((char *) p + 64);
+        c->d_l1_next_expno = (long long *) ((char *) p + 96);
+        c->d_l1_error = (unsigned int *) ((char *) p + 128);
+     }
+   c->have_level1 = true;
+   return marxb200_level1_reset (c);
+}
+
+static int level1_ensure_columns (marxb200_ctx *c, uint64_t n)
+{
+   if (n <= c->l1_cap) return 0;
+   if (c->l1_slab) { CUDA_OK (cudaStreamSynchronize (c->stream)); cudaFree (c->l1_slab); c->l1_slab = nullptr; c->l1_cap = 0; }
+   const uint64_t cap = ((n + n / 4 + 1023) / 256) * 256;
+   // 5 x f64, 6 x i32, 1 x f32, 8 x i16, 1 x u8, head (u32), tile heads (u32 per 256 events)
+   const size_t bytes = (size_t) cap * (5 * 8 + 6 * 4 + 4 + 8 * 2 + 1 + 4) + (size_t) (cap / 256 + 2) * 4 + 64 * 256;
+   CUDA_OK (cudaMalloc (&c->l1_slab, bytes));
+   char *p = (char *) c->l1_slab;
+   auto take = [&] (size_t elem) { char *q = p; p += ((size_t) cap * elem + 255) & ~(size_t) 255; return (void *) q; };
+   Level1Cols &o = c->l1_cols;
+   o.time = (double *) take (8); o.detx = (double *) take (8); o.dety = (double *) take (8); o.x = (double *) take (8); o.y = (double *) take (8);
+   o.expno = (int32_t *) take (4); o.tdetx = (int32_t *) take (4); o.tdety = (int32_t *) take (4); o.pha = (int32_t *) take (4);
+   o.hrc_u = (int32_t *) take (4); o.hrc_v = (int32_t *) take (4);
+   o.energy = (float *) take (4);
+   o.ccd_id = (int16_t *) take (2); o.node_id = (int16_t *) take (2); o.chipx = (int16_t *) take (2); o.chipy = (int16_t *) take (2);
+   o.pi = (int16_t *) take (2); o.fltgrade = (int16_t *) take (2); o.grade = (int16_t *) take (2); o.status = (int16_t *) take (2);
+   o.keep = (uint8_t *) take (1);
+   c->d_l1_head = (uint32_t *) take (4);
+   c->d_l1_tile_head = (uint32_t *) p;
+   c->l1_cap = cap;
+   return 0;
+}
+
+extern "C" int marxb200_level1_transform (marxb200_ctx *c, double total_time)
+{
+   if (c == nullptr) return fail ("marxb200_level1_transform: NULL ctx");
+   if (!c->have_level1) return fail ("marxb200_level1_transform: call marxb200_set_level1 first");
+   if (c->stage_done < 0) return fail ("marxb200_level1_transform: no events");
+   CUDA_OK (cudaSetDevice (c->device));
+   if (-1 == ensure_order (c)) return -1;
+   unsigned long long n = 0;
+   CUDA_OK (cudaMemcpyAsync (&n, c->d_counts + c->stage_done, sizeof (n), cudaMemcpyDeviceToHost, c->stream));
+   CUDA_OK (cudaStreamSynchronize (c->stream));
+   c->l1_rows = n;
+   if (n == 0) return 0;
+   if (n >= 0xFFFFFFFFull) return fail ("marxb200_level1_transform: %llu events in one batch", n);
+   if (-1 == level1_ensure_columns (c, n)) return -1;
+   Level1Args a;
+   memset (&a, 0, sizeof (a));
+   a.in = observed (c, c->buf[c->cur]);
+   a.n_ptr = c->d_counts + c->stage_done; a.max_n = n;
+   a.dev_start_time = c->d_times; a.total_time = total_time;
+   a.seed = c->seed;
+   a.L = c->L1; a.state = c->d_l1_state; a.out = c->l1_cols;
+   a.head = c->d_l1_head; a.tile_head = c->d_l1_tile_head;
+   a.next_dither = c->d_l1_next_dither; a.next_expno = c->d_l1_next_expno; a.error_flag = c->d_l1_error;
+   int nl = 0;
+   prof_begin (c);
+   launch_level1 (a, c->num_sms, c->stream, &nl);
+   prof_mark (c, 10);
+   c->launches += (uint64_t) nl;
+   CUDA_OK (cudaGetLastError ());
+   return 0;
+}
+
+extern "C" int marxb200_level1_download (marxb200_ctx *c, const marxb200_level1_columns *cols, uint64_t max_out, uint64_t *n_out)
+{
+   if ((c == nullptr) || (cols == nullptr)) return fail ("marxb200_level1_download: NULL argument");
+   if (!c->have_level1) return fail ("marxb200_level1_download: call marxb200_set_level1 first");
+   CUDA_OK (cudaSetDevice (c->device));
+   uint64_t n = c->l1_rows;
+   if (n > max_out) n = max_out;
+   if (n_out) *n_out = n;
+   unsigned int err = 0;
+   CUDA_OK (cudaMemcpyAsync (&err, c->d_l1_error, sizeof (err), cudaMemcpyDeviceToHost, c->stream));
+   const Level1Cols &b = c->l1_cols;
+#define COL(f, T) if (n && cols->f) CUDA_OK (cudaMemcpyAsync (cols->f, b.f, (size_t) n * sizeof (T), cudaMemcpyDeviceToHost, c->stream))
+   COL (time, double); COL (detx, double); COL (dety, double); COL (x, double); COL (y, double);
+   COL (expno, int32_t); COL (tdetx, int32_t); COL (tdety, int32_t); COL (pha, int32_t); COL (hrc_u, int32_t); COL (hrc_v, int32_t);
+   COL (energy, float);
+   COL (ccd_id, int16_t); COL (node_id, int16_t); COL (chipx, int16_t); COL (chipy, int16_t);
+   COL (pi, int16_t); COL (fltgrade, int16_t); COL (grade, int16_t); COL (status, int16_t);
+   COL (keep, uint8_t);
+#undef COL
+   CUDA_OK (cudaStreamSynchronize (c->stream));
+   // the reference stops with an error on these rows (marx_compute_tiled_pixel: "chip = %d is not appropriate for this
+   // detector", detpix.c:174; marx_mnc_to_fpc: "mnc.x is 0", :195)
+   if (err & 1u) return fail ("marxb200_level1: an event's chip id does not belong to this detector");
+   if (err & 2u) return fail ("marxb200_level1: mnc.x is 0");
    return 0;
 }
 

@@ -3,6 +3,7 @@
 #include <stdint.h>
 #include <cuda_runtime.h>
 #include "mx_tables.h"
+#include "mx_level1.cuh"
 
 namespace mx {
 
@@ -175,5 +176,24 @@ struct EgressPlan
 void launch_fp64_peak (double *sink, int grid, int iters, cudaStream_t s);   // 64 DFMA per thread per iteration
 void launch_egress_pack (const PhotonSoA &in, const unsigned long long *n, uint64_t max_n, const EgressPlan &plan, void *dst,
                          const double *dev_start_time, double total_time, cudaStream_t s);
+
+// Level-1 event transforms (level1_kernels.cu)
+struct Level1Args
+{
+   PhotonSoA in;                         // the live list in arrival order
+   const unsigned long long *n_ptr;      // device: number of events
+   uint64_t max_n;
+   const double *dev_start_time;         // device: start time of the batch (time column is absolute)
+   double total_time;                    // TIME of the file = (float) ((time - start) + total_time)
+   uint64_t seed;
+   Level1Dev L;
+   Level1State *state;                   // device
+   Level1Cols out;
+   uint32_t *head, *tile_head;           // [max_n], [max_n / 256 + 1]: frame-head scan scratch
+   float *next_dither;                   // device [6]
+   long long *next_expno;                // device [1]
+   unsigned int *error_flag;             // device
+};
+void launch_level1 (const Level1Args &a, int num_sms, cudaStream_t s, int *n_launches);
 
 }  // namespace mx

@@ -1,7 +1,7 @@
 set -x
 cd /root/repo
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_aspsol.py tests/test_gpu_tally.py tests/test_gpu_marx_driver.py tests/test_gpu_edges.py -q -m gpu 2>&1 | tail -15 | tee gpurun_out/call26.log
-for v in base r64all r64k1 sparse2 k01r2 base; do
-  MARXB200_LIB=/root/repo/build/variants/libmarxb200_$v.so timeout 120 python tools/trace_probe.py 16777216 c2_hetg_acis_s 20 2>&1 | tail -1
-done | tee gpurun_out/variants26.log
+( timeout 600 python -m pytest tests/test_gpu_level1.py -q -m gpu -x 2>&1 | tail -25 ) | tee gpurun_out/call29_tests.log
+( timeout 120 python tools/level1_probe.py 16777216 c2_hetg_acis_s level1_acis_s_hetg_edser;
+  timeout 120 python tools/level1_probe.py 16777216 c1_acis_s level1_acis_s_nodither_none;
+  timeout 120 python tools/level1_probe.py 16777216 c1_acis_s level1_acis_s_hetg_edser ) 2>&1 | grep -v "^+" | tee gpurun_out/call29_probe.log
