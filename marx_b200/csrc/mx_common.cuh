@@ -223,13 +223,13 @@ struct Rng
 // ------------------------------------------------------------------------------------------------
 // JDMbinary_search_f, finterpo.c:37-57: first index with xp[i] >= x (n if none), with the equality
 // short-circuit that matters when the grid holds duplicate abscissae.
-MX_HD uint32_t bsearch_f (float x, const float *xp, uint32_t n)
+template <class T> MX_HD uint32_t bsearch_ref (T x, const T *xp, uint32_t n, uint32_t stride = 1)
 {
    uint32_t n0 = 0, n1 = n, n2;
    while (n1 > n0 + 1)
      {
         n2 = (n0 + n1) / 2;
-        float v = xp[n2];
+        T v = xp[stride * n2];
         if (v >= x)
           {
              if (v == x) return n2;
@@ -237,27 +237,61 @@ MX_HD uint32_t bsearch_f (float x, const float *xp, uint32_t n)
           }
         else n0 = n2;
      }
-   if (x >= xp[n0]) return n1;
+   if (x >= xp[stride * n0]) return n1;
    return n0;
 }
+// Device form.  The bisection above is a chain of log2(n) DEPENDENT loads (11 for the 1426..2000-point energy grids): ncu
+// attributes 10-16 % of the stall samples of k1_hrma<1> and k3_acis to waiting on them.  Unless x equals a grid value, the
+// reference's result does not depend on its probe sequence: it is the lower bound lb = #{i: xp[i] < x} (for lb == 0 it returns
+// 0 when x < xp[0]).  So: find lb with a branch-free binary lower bound (trip count fixed by n, one select per probe: no
+// divergence, no early-exit branch) and hand the rare exact-equality (or NaN) case to the reference loop, whose answer then
+// depends on which duplicate abscissa it happens to probe.  Measured on B200 (C2, 2^24 rays): k3_acis 1.21 -> 1.04 ms,
+// k1_hrma<1> 1.38 -> 1.32 ms.  MX_SEARCH_ARITY = k > 1 selects a k-ary search instead (k-1 independent probes per round,
+// fewer dependent latencies): 2..6 within 1 % of the binary form, 8 and 16 slower (registers) -- the latency chain was not
+// the cost, the divergent loop was.  0 = the reference loop.
+#ifndef MX_SEARCH_ARITY
+#define MX_SEARCH_ARITY 1
+#endif
+template <class T> MX_HD uint32_t bsearch_fast (T x, const T *xp, uint32_t n, uint32_t stride = 1)
+{
+#if defined(__CUDA_ARCH__) && (MX_SEARCH_ARITY == 1)
+   // branch-free binary lower bound: the trip count depends on n only (no divergence), one select per probe
+   uint32_t base = 0, len = n;
+   while (len > 1)
+     {
+        const uint32_t half = len >> 1;
+        base += (xp[stride * (base + half - 1)] < x) ? half : 0u;
+        len -= half;
+     }
+   const uint32_t lb = base + (((n > 0) && (xp[stride * base] < x)) ? 1u : 0u);
+   if (!(x == x) || ((lb < n) && (xp[stride * lb] == x))) return bsearch_ref (x, xp, n, stride);
+   return lb;
+#elif defined(__CUDA_ARCH__) && (MX_SEARCH_ARITY > 1)
+   constexpr uint32_t A = MX_SEARCH_ARITY;
+   uint32_t lo = 0, hi = n;                       // xp[i] < x for i < lo, xp[i] >= x for i >= hi
+   while (hi - lo > A)
+     {
+        const uint32_t step = (hi - lo) / A;
+        uint32_t c = 0;
+#pragma unroll
+        for (uint32_t k = 1; k < A; k++) c += (xp[stride * (lo + step * k)] < x) ? 1u : 0u;
+        const uint32_t base = lo;
+        if (c > 0) lo = base + step * c + 1u;
+        if (c < A - 1u) hi = base + step * (c + 1u);
+     }
+   uint32_t c = 0;
+#pragma unroll
+   for (uint32_t k = 0; k < A; k++) c += ((lo + k < hi) && (xp[stride * (lo + k)] < x)) ? 1u : 0u;
+   const uint32_t lb = lo + c;
+   if (!(x == x) || ((lb < n) && (xp[stride * lb] == x))) return bsearch_ref (x, xp, n, stride);
+   return lb;
+#else
+   return bsearch_ref (x, xp, n, stride);
+#endif
+}
+MX_HD uint32_t bsearch_f (float x, const float *xp, uint32_t n) { return bsearch_fast<float> (x, xp, n); }
 // JDMbinary_search_d, jdmath/src/dinterpo.c (same algorithm on doubles)
-MX_HD uint32_t bsearch_d (double x, const double *xp, uint32_t n)
-{
-   uint32_t n0 = 0, n1 = n, n2;
-   while (n1 > n0 + 1)
-     {
-        n2 = (n0 + n1) / 2;
-        double v = xp[n2];
-        if (v >= x)
-          {
-             if (v == x) return n2;
-             n1 = n2;
-          }
-        else n0 = n2;
-     }
-   if (x >= xp[n0]) return n1;
-   return n0;
-}
+MX_HD uint32_t bsearch_d (double x, const double *xp, uint32_t n) { return bsearch_fast<double> (x, xp, n); }
 // JDMinterpolate_f, finterpo.c:59-85.  x is narrowed to float by the caller's call (the C prototype
 // takes float); (yp[n1]-yp[n0]) is a float subtraction, the rest is double, the result is a float.
 // The reference reads xp[n] one past the end when x exceeds the grid (finterpo.c:68); that compare

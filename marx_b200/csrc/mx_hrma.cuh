@@ -185,24 +185,11 @@ MX_HD_BIG double wfold_interp (const WfoldDev &w, double energy, double sin_alph
    if (w.num_arrays == 1) return wfold_theta (w, 0, r);
    double e_alpha = energy * sin_alpha;
    // JDMbinary_search_d over the e_alpha column: a contiguous copy staged in shared memory (`keys`, k1_hrma<1|2>) or
-   // column 0 of the header rows in global memory (stride 6 doubles).  The search is a chain of 8 dependent loads.
+   // column 0 of the header rows in global memory (stride 6 doubles).
    const int ks = (keys != nullptr) ? 1 : 6;
    if (keys == nullptr) keys = w.hdr;
-   uint32_t n = w.num_arrays, n0 = 0, n1 = n, n2, i;
-   while (n1 > n0 + 1)
-     {
-        n2 = (n0 + n1) / 2;
-        double v = keys[ks * n2];
-        if (v >= e_alpha)
-          {
-             if (v == e_alpha) { n1 = n2; n0 = n2; break; }
-             n1 = n2;
-          }
-        else n0 = n2;
-     }
-   if (n0 == n1) i = n1;                       // equality short-circuit
-   else if (e_alpha >= keys[ks * n0]) i = n1;
-   else i = n0;
+   const uint32_t n = w.num_arrays;
+   uint32_t i = bsearch_fast<double> (e_alpha, keys, n, (uint32_t) ks);
    if (i == n) i--;
    if (i == 0) i++;
    double theta_0 = wfold_theta (w, i - 1, r);

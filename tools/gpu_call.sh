@@ -1,7 +1,8 @@
 set -x
 cd /root/repo
 mkdir -p gpurun_out
-( timeout 600 python -m pytest tests/test_gpu_level1.py -q -m gpu -x 2>&1 | tail -25 ) | tee gpurun_out/call29_tests.log
-( timeout 120 python tools/level1_probe.py 16777216 c2_hetg_acis_s level1_acis_s_hetg_edser;
-  timeout 120 python tools/level1_probe.py 16777216 c1_acis_s level1_acis_s_nodither_none;
-  timeout 120 python tools/level1_probe.py 16777216 c1_acis_s level1_acis_s_hetg_edser ) 2>&1 | grep -v "^+" | tee gpurun_out/call29_probe.log
+( timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -6 ) | tee gpurun_out/call39_tests.log
+for v in A1 cur A1 cur; do
+  if [ $v = cur ]; then L=/root/repo/marx_b200/libmarxb200.so; else L=/root/repo/build/variants/libmarxb200_$v.so; fi
+  MARXB200_LIB=$L timeout 120 python tools/trace_probe.py 16777216 c2_hetg_acis_s 30 2>&1 | tail -1
+done | tee gpurun_out/call39_variants.log
