@@ -74,6 +74,50 @@ def run_reference_sample(nrays_per_proc, nprocs, seed0=1):
     return rays, secs, wall
 
 
+def level1_leg(m, stream, args, reps=20):
+    """marxb200_level1_transform on the event list the last traced batch left on the device (EDSER sub-pixel mode, the
+    marx2fits default), timed with the library's CUDA-event marks; beside it the plain-C restatement of marx2fits' loop
+    (oracle/level1_oracle.c, one core) on the same events -- the `cpu_baseline` of this leg."""
+    import numpy as np
+    import torch
+    from marx_b200.level1 import Level1Desc
+    z = np.load(os.path.join(ROOT, "tests", "golden", "level1_acis_s_hetg_edser.npz"))
+    desc = {k[5:]: z[k] for k in z.files if k.startswith("desc.")}
+    with torch.cuda.stream(stream):
+        m.set_level1(Level1Desc.from_dict(desc))
+        events = int(m.counts()[1])
+        for _ in range(3):
+            m.level1_transform(0.0)
+        m.set_profiling(True)
+        m.kernel_ms()
+        for _ in range(reps):
+            m.level1_transform(0.0)
+        k = m.kernel_ms()["level1"]
+        m.set_profiling(False)
+    ms = k[0] / max(k[1], 1)
+    # algorithmic bytes per event: R time 8 + chip pixels 8 + PI energy 4 + pha 2 + ccd 1 + aspect 12 = 35, W 5 f64 + 6 i32 + f32 +
+    # 8 i16 + keep = 85
+    out = {"events": events, "ms": ms, "events_per_s": events / (ms * 1e-3), "launches_per_transform": 4,
+           "hbm_gbs_at_120B_per_event": 120.0 * events / (ms * 1e-3) / 1e9,
+           "workload": "events of one 2^24-ray C2 batch, ACIS-S, EDSER sub-pixel mode; 3 kernels + state hand-over"}
+    if not args.no_cpu_baseline:
+        try:
+            from tests import level1_lib
+            ph = m.download()
+            cols = {"time": ph["arrival_time"].astype(np.float32), "xpixel": ph["y_pixel"], "ypixel": ph["z_pixel"], "b_energy": ph["pi"],
+                    "pha": ph["pulse_height"], "ccd": ph["ccd_num"],
+                    **{key: np.ascontiguousarray(ph["dither"][:, j]) for j, key in enumerate(level1_lib.DITHER_KEYS)}}
+            o = level1_lib.Level1Oracle(desc, args.seed)
+            t0 = time.time()
+            o.transform(cols)
+            dt = time.time() - t0
+            out["cpu_baseline"] = {"value": events / dt, "unit": "events/s", "cores": 1, "kind": "port",
+                                   "sample": "%d events, oracle/level1_oracle.c (gcc -O2), %.2f s" % (events, dt)}
+        except Exception as e:  # noqa: BLE001
+            out["cpu_baseline"] = {"value": None, "kind": "port", "sample": "unavailable: %s" % str(e)[:120]}
+    return out
+
+
 def bind_to_gpu_numa_node(index):
     """Pin this rank's host threads to the CPUs local to its GPU (sysfs local_cpulist of the GPU's PCI device), so that
     the pinned egress buffers are first-touched on that NUMA node and the D2H copies of 8 ranks do not all cross the
@@ -311,6 +355,15 @@ def cuda_arm(args):
     timed(2, e2e=True)
     ms_e2e, _, n_events = timed(args.steps, e2e=True)
 
+    # Level-1 leg (marx2fits' per-event transforms on the device-resident list): the events of the last batch,
+    # measured on its own after the timed regions above -- it is not part of `value` / `e2e`
+    level1 = None
+    if rank == 0 and not args.no_level1:
+        try:
+            level1 = level1_leg(m, stream, args)
+        except Exception as e:  # noqa: BLE001
+            level1 = {"unavailable": str(e)[:200]}
+
     total_rays = float(n) * world * args.steps
     value = total_rays / (ms * 1e-3)
     e2e_value = total_rays / (ms_e2e * 1e-3)
@@ -388,6 +441,8 @@ def cuda_arm(args):
                      "profiled_ms_per_step": ms_prof / args.steps,
                      "kernels": kernels},
     }
+    if level1 is not None:
+        line["level1"] = level1
     # CPU baseline beside it (N=1 only): the compiled reference on ONE core, bounded sample
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -414,6 +469,7 @@ def main():
     ap.add_argument("--cpu-baseline-rays", type=int, default=6000000)
     ap.add_argument("--ref-rays-per-proc", type=int, default=1000000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-level1", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

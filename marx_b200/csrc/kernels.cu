@@ -510,7 +510,10 @@ __global__ void __launch_bounds__ (kStageThreads, MX_K2_MINBLOCKS) k2_grating (c
 #ifndef MX_K3_MINBLOCKS
 #define MX_K3_MINBLOCKS 3
 #endif
-template <bool DET>
+// PHASE 0: the whole detector stage in one kernel; 1, 2: its two halves (acis_detect_a / _b, mx_acis.cuh) as two kernels with a
+// re-packed list in between.  The chip index found by the first half travels in the pha column (not yet used), the chip
+// pixels in theirs; the QE test is the only draw of the first half, so the second resumes the DETECTOR sub-stream at draw 0 or 1.
+template <bool DET, int PHASE>
 __global__ void __launch_bounds__ (kStageThreads, MX_K3_MINBLOCKS) k3_acis (const __grid_constant__ StageArgs a)
 {
    constexpr int ND = 6, NU = 7;
@@ -533,7 +536,22 @@ __global__ void __launch_bounds__ (kStageThreads, MX_K3_MINBLOCKS) k3_acis (cons
         rng.init (a.seed, a.rc.ray[slot], MARXB200_STAGE_DETECTOR);
         DetDither dd = {0.0, 0.0, 0.0};
         if (DET) { dd.dy = a.rc.ddy[slot]; dd.dz = a.rc.ddz[slot]; dd.dtheta = a.rc.ddth[slot]; }
-        uint32_t flags = acis_detect<DET> (A, a.rc.energy[slot], a.rc.time[slot], x, p, ccd, chipx, chipy, pha, pi, rng, fef_cum, kStageThreads, dd);
+        uint32_t flags;
+        if (PHASE == 0)
+          flags = acis_detect<DET> (A, a.rc.energy[slot], a.rc.time[slot], x, p, ccd, chipx, chipy, pha, pi, rng, fef_cum, kStageThreads, dd);
+        else if (PHASE == 1)
+          {
+             int hit = -1;
+             flags = acis_detect_a<DET> (A, a.rc.energy[slot], x, p, ccd, hit, chipx, chipy, rng, dd);
+             pha = ((flags & 0xFFu) == 0) ? (int16_t) hit : (int16_t) 0;
+          }
+        else
+          {
+             const int hit = (int) in.pha[i];
+             ccd = (int) in.ccd[i]; chipx = in.chipx[i]; chipy = in.chipy[i];
+             rng.resume (A.det_ideal ? 0u : 1u, 0, 0.0);
+             flags = acis_detect_b<DET> (A, a.rc.energy[slot], a.rc.time[slot], x, p, hit, chipx, chipy, pha, pi, rng, fef_cum, kStageThreads, dd);
+          }
         d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = p.x; d[4] = p.y; d[5] = p.z;
         // ids produced by the earlier stages travel through the queue (coalesced loads here instead of dependent
         // gathers when a row is flushed): flags use bits 0..9, shell and order ride in the upper half
@@ -1136,8 +1154,12 @@ int stage_grid_size (int stage, int num_sms, uint32_t blob_bytes, uint32_t seg2_
       case 12: return occupancy_grid (k1_hrma<2>, num_sms, smem);
       case 2: return occupancy_grid (k2_grating, num_sms, smem);
       // the detector-dither variants run on the same grid (ticket-driven persistent kernels: any grid size is correct)
-      case 3: cudaFuncSetAttribute (k3_acis<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-              return occupancy_grid (k3_acis<false>, num_sms, smem);
+      case 3: cudaFuncSetAttribute (k3_acis<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+              cudaFuncSetAttribute (k3_acis<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+              cudaFuncSetAttribute (k3_acis<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+              cudaFuncSetAttribute (k3_acis<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+              cudaFuncSetAttribute (k3_acis<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+              return occupancy_grid (k3_acis<false, 0>, num_sms, smem);
       case 4: cudaFuncSetAttribute (k3_hrc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
               return occupancy_grid (k3_hrc<false>, num_sms, smem);
      }
@@ -1167,10 +1189,23 @@ void launch_hrma (const StageArgs &a, int phase, int grid, cudaStream_t s)
      }
 }
 void launch_grating (const StageArgs &a, int grid, cudaStream_t s) { k2_grating<<<grid, kStageThreads, stage_smem_bytes (2, a.blob_bytes), s>>> (a); }
-void launch_acis (const StageArgs &a, int grid, cudaStream_t s)
+void launch_acis (const StageArgs &a, int grid, cudaStream_t s, int phase)
 {
-   if (a.det_dither) k3_acis<true><<<grid, kStageThreads, stage_smem_bytes (3, a.blob_bytes), s>>> (a);
-   else k3_acis<false><<<grid, kStageThreads, stage_smem_bytes (3, a.blob_bytes), s>>> (a);
+   const uint32_t smem = stage_smem_bytes (3, a.blob_bytes);
+   if (a.det_dither)
+     switch (phase)
+       {
+        case 1: k3_acis<true, 1><<<grid, kStageThreads, smem, s>>> (a); break;
+        case 2: k3_acis<true, 2><<<grid, kStageThreads, smem, s>>> (a); break;
+        default: k3_acis<true, 0><<<grid, kStageThreads, smem, s>>> (a); break;
+       }
+   else
+     switch (phase)
+       {
+        case 1: k3_acis<false, 1><<<grid, kStageThreads, smem, s>>> (a); break;
+        case 2: k3_acis<false, 2><<<grid, kStageThreads, smem, s>>> (a); break;
+        default: k3_acis<false, 0><<<grid, kStageThreads, smem, s>>> (a); break;
+       }
 }
 void launch_hrc (const StageArgs &a, int grid, cudaStream_t s)
 {

@@ -79,6 +79,7 @@ struct marxb200_ctx
    int grid1[3] = {0, 0, 0}, grid2 = 0, grid3 = 0, grid01 = 0;
    bool detector_is_hrc = false;
    int first_mirror_kernel = 0;                  // 1: phase A already ran fused with the source (marxb200_trace)
+   int k3_split = 1;                             // ACIS detector stage as two kernels (MARXB200_K3_SPLIT=0: one kernel)
 
    // host boundary staging
    void *d_aos = nullptr; uint64_t d_aos_cap = 0;
@@ -212,6 +213,7 @@ extern "C" int marxb200_create (marxb200_ctx **ctxp, int device_ordinal, uint64_
    marxb200_ctx *c = new marxb200_ctx ();
    c->device = device_ordinal;
    c->seed = seed;
+   if (const char *e = getenv ("MARXB200_K3_SPLIT")) c->k3_split = atoi (e);      // developer A/B switch
    cudaDeviceProp prop;
    CUDA_OK (cudaGetDeviceProperties (&prop, device_ordinal));
    c->num_sms = prop.multiProcessorCount;
@@ -630,7 +632,9 @@ static int run_stage (marxb200_ctx *c, int stage)
    // _marx_dither_detector is a no-op when DitherModel=NONE (detector.c:277-278), whatever the records carry
    a.det_dither = (det_dither_live (c) && (c->D.mode != 0)) ? 1 : 0;
    // the mirror stage runs as three kernels (HRMA phases A, B, C, mx_hrma.cuh), each re-packing its survivors
-   const int n_kernels = (stage == 1) ? 3 : 1;
+   // ... and the ACIS detector stage as two (geometry + QE, then FEF + streak; mx_acis.cuh)
+   const bool k3_two = (stage == 3) && !c->detector_is_hrc && (c->k3_split != 0);
+   const int n_kernels = (stage == 1) ? 3 : (k3_two ? 2 : 1);
    const int k_first = (stage == 1) ? c->first_mirror_kernel : 0;
    CUDA_OK (cudaMemsetAsync (c->d_ticket, 0, 4 * sizeof (unsigned long long), c->stream));
    if (c->compact)
@@ -638,6 +642,7 @@ static int run_stage (marxb200_ctx *c, int stage)
         // output counters grow by atomics: zero them (d_counts[4], [5] = after k1a, k1b; d_counts[stage] = stage output)
         CUDA_OK (cudaMemsetAsync (c->d_counts + stage, 0, sizeof (unsigned long long), c->stream));
         if (stage == 1) CUDA_OK (cudaMemsetAsync (c->d_counts + 4 + k_first, 0, (2 - k_first) * sizeof (unsigned long long), c->stream));
+        if (k3_two) CUDA_OK (cudaMemsetAsync (c->d_counts + 6, 0, sizeof (unsigned long long), c->stream));
      }
    const unsigned long long *n_in = (k_first == 1) ? c->d_counts + 4 : c->d_counts + c->stage_done;
    c->first_mirror_kernel = 0;
@@ -646,7 +651,7 @@ static int run_stage (marxb200_ctx *c, int stage)
         a.in = c->buf[c->cur];
         a.out = c->compact ? c->buf[1 - c->cur] : c->buf[c->cur];
         a.n_in = n_in;
-        a.n_out = (k == n_kernels - 1) ? c->d_counts + stage : c->d_counts + 4 + k;
+        a.n_out = (k == n_kernels - 1) ? c->d_counts + stage : ((stage == 1) ? c->d_counts + 4 + k : c->d_counts + 6);
         a.ticket = c->d_ticket + k;
         // big inputs amortise the ticket atomic over several tiles; small ones need fine-grained balancing
         a.chunk_tiles = (stage == 1 && k == 0) ? 4 : ((stage == 1 && k == 1) ? 2 : 1);
@@ -658,7 +663,7 @@ static int run_stage (marxb200_ctx *c, int stage)
                    launch_hrma (a, k, c->grid1[k], c->stream); prof_mark (c, 4 + k); break;
            case 2: a.blob = c->blob2; a.blob_bytes = c->blob2_bytes; launch_grating (a, c->grid2, c->stream); prof_mark (c, 7); break;
            case 3: a.blob = c->blob3; a.blob_bytes = c->blob3_bytes;
-                   if (c->detector_is_hrc) launch_hrc (a, c->grid3, c->stream); else launch_acis (a, c->grid3, c->stream);
+                   if (c->detector_is_hrc) launch_hrc (a, c->grid3, c->stream); else launch_acis (a, c->grid3, c->stream, k3_two ? k + 1 : 0);
                    prof_mark (c, 8);
                    break;
           }

@@ -349,32 +349,42 @@ MX_HD int acis_apply_fef (const AcisDev &A, const AcisChipDev &chip, float x, fl
    return 0;
 }
 
-// _marx_acis_s_detect for one ray.  t_abs = pt->start_time + arrival_time.  Returns flags (0 alive,
-// possibly with PHOTON_ACIS_STREAKED set, which is not a "dead" bit).
+// _marx_acis_s_detect for one ray, in two halves so that the detector stage can run as two kernels (k3_acis<DET, 1|2>: the
+// 88 KB single kernel spent 43 % of its stall samples waiting for instruction fetch; each half has half the footprint, and the
+// second starts from full warps).  t_abs = pt->start_time + arrival_time.  Both return flags (0 alive, possibly with
+// PHOTON_ACIS_STREAKED set, which is not a "dead" bit).
 // DET: the per-ray detector dither is live (ASPSOL model / uploaded records); false compiles the table-frame path only
-template <bool DET = false>
-MX_HD uint32_t acis_detect (const AcisDev &A, double energy, double t_abs, Vec3 &x, Vec3 &p,
-                            int &ccd, float &chipx, float &chipy, int16_t &pha, float &pi, Rng &rng,
-                            float *fef_cum, uint32_t fef_stride, const DetDither &dd = DetDither {0.0, 0.0, 0.0})
+struct AcisFrame { const double *off, *mat; double off_l[3], mat_l[9]; };
+template <bool DET>
+MX_HD void acis_frame (const AcisDev &A, const DetDither &dd, AcisFrame &F)
 {
-   const uint32_t UNDETECTED = 0x01, MISSED = 0x08, STREAKED = 0x200;
-   uint32_t flags = 0;
-   // _marx_dither_detector + _marx_transform_ray, detector.c:275-284, trans.c:66-77 (the detector dither is zero for the
-   // INTERNAL model, dither.c:177-179: the frame is then the table's)
-   const double *det_off = A.det_offset, *det_mat = A.det_matrix;
-   double off_l[3], mat_l[9];
+   // _marx_dither_detector, detector.c:275-284 (the detector dither is zero for the INTERNAL model, dither.c:177-179: the
+   // frame is then the table's)
+   F.off = A.det_offset; F.mat = A.det_matrix;
    if (DET && (A.dither_mode != 0) && ((dd.dy != 0) || (dd.dz != 0) || (dd.dtheta != 0)))
      {
-        det_dither_frame (A.det_offset, A.det_matrix, dd, off_l, mat_l);
-        det_off = off_l; det_mat = mat_l;
+        det_dither_frame (A.det_offset, A.det_matrix, dd, F.off_l, F.mat_l);
+        F.off = F.off_l; F.mat = F.mat_l;
      }
-   x.x -= det_off[0]; x.y -= det_off[1]; x.z -= det_off[2];
-   x = m3_mul (det_mat, x);
-   p = m3_mul (det_mat, p);
+}
+
+// first half: _marx_transform_ray (trans.c:66-77), chip-plane intersection (detector.c:111-168), QE x filter x contamination
+// (_marx_acis_apply_qe_and_pha :138-163).  Leaves x (the point on the chip) and p in the DETECTOR frame; hit = index of the chip.
+template <bool DET = false>
+MX_HD uint32_t acis_detect_a (const AcisDev &A, double energy, Vec3 &x, Vec3 &p, int &ccd, int &hit_out, float &chipx, float &chipy,
+                              Rng &rng, const DetDither &dd = DetDither {0.0, 0.0, 0.0})
+{
+   const uint32_t UNDETECTED = 0x01, MISSED = 0x08;
+   AcisFrame F;
+   acis_frame<DET> (A, dd, F);
+   x.x -= F.off[0]; x.y -= F.off[1]; x.z -= F.off[2];
+   x = m3_mul (F.mat, x);
+   p = m3_mul (F.mat, p);
 
    double dx = 0, dy = 0;
    Vec3 xh = x;
    const int hit = detector_intersect (A.chip, A.num_chips, x, p, xh, dx, dy, A.det_extend);
+   hit_out = hit;
    if (hit < 0)
      {
         ccd = -1;
@@ -386,7 +396,6 @@ MX_HD uint32_t acis_detect (const AcisDev &A, double energy, double t_abs, Vec3 
    chipx = (float) (dx / d.x_pixel_size);
    chipy = (float) (dy / d.y_pixel_size);
 
-   // _marx_acis_apply_qe_and_pha, acis-s.c:138-175
    if (A.det_ideal == 0)
      {
         double r = rng.uniform ();
@@ -396,12 +405,24 @@ MX_HD uint32_t acis_detect (const AcisDev &A, double energy, double t_abs, Vec3 
         double qe_contam = acis_contamination (d, energy, chipx, chipy);
         if (r >= qe * qe_filter * qe_contam) return UNDETECTED;
      }
+   return 0;
+}
+
+// second half: FEF pulse height (marx_apply_acis_rmf), streak (_marx_acis_apply_streak, acis-i.c:60-89), and
+// _marx_transform_ray_reverse (trans.c:79-90).  x, p arrive in the detector frame.
+template <bool DET = false>
+MX_HD uint32_t acis_detect_b (const AcisDev &A, double energy, double t_abs, Vec3 &x, Vec3 &p, int hit, float chipx, float &chipy,
+                              int16_t &pha, float &pi, Rng &rng, float *fef_cum, uint32_t fef_stride,
+                              const DetDither &dd = DetDither {0.0, 0.0, 0.0})
+{
+   const uint32_t UNDETECTED = 0x01, STREAKED = 0x200;
+   uint32_t flags = 0;
+   const AcisChipDev &d = A.chip[hit];
    if (-1 == acis_apply_fef (A, d, chipx, chipy, energy, pi, pha, rng, fef_cum, fef_stride))
      {
         pha = -1; pi = 0;
         return UNDETECTED;
      }
-   // _marx_acis_apply_streak, acis-i.c:60-89
    if (A.frame_transfer_time > 0.0)
      {
         double t = fmod_pos (t_abs, A.frame_time);
@@ -417,11 +438,23 @@ MX_HD uint32_t acis_detect (const AcisDev &A, double energy, double t_abs, Vec3 
              flags |= STREAKED;
           }
      }
-   // _marx_transform_ray_reverse, trans.c:79-90
-   p = m3_mul_t (det_mat, p);
-   x = m3_mul_t (det_mat, x);
-   x.x += det_off[0]; x.y += det_off[1]; x.z += det_off[2];
+   AcisFrame F;
+   acis_frame<DET> (A, dd, F);
+   p = m3_mul_t (F.mat, p);
+   x = m3_mul_t (F.mat, x);
+   x.x += F.off[0]; x.y += F.off[1]; x.z += F.off[2];
    return flags;
+}
+
+template <bool DET = false>
+MX_HD uint32_t acis_detect (const AcisDev &A, double energy, double t_abs, Vec3 &x, Vec3 &p,
+                            int &ccd, float &chipx, float &chipy, int16_t &pha, float &pi, Rng &rng,
+                            float *fef_cum, uint32_t fef_stride, const DetDither &dd = DetDither {0.0, 0.0, 0.0})
+{
+   int hit = -1;
+   const uint32_t flags = acis_detect_a<DET> (A, energy, x, p, ccd, hit, chipx, chipy, rng, dd);
+   if (flags != 0) return flags;
+   return acis_detect_b<DET> (A, energy, t_abs, x, p, hit, chipx, chipy, pha, pi, rng, fef_cum, fef_stride, dd);
 }
 
 }  // namespace mx
