@@ -3,6 +3,8 @@
    marx2fits table, float32 columns within 1 ulp (device libm), FP64 columns within 1e-9 relative of the oracle;
  * the device's own traced events (C2, 2^22 rays, two consecutive batches of one event file) against the oracle fed with the
    same column values -- the exposure-frame aspect broadcast crossing tile and batch boundaries."""
+import os
+
 import numpy as np
 import pytest
 
@@ -101,3 +103,44 @@ def test_level1_of_traced_events_matches_the_oracle(pixadj):
     # exposure frames hold several events: the broadcast is exercised (and crosses 256-event tiles)
     e = got[0]["expno"]
     assert (e[1:] == e[:-1]).mean() > 0.3
+
+
+MARX2FITS_GPU = os.path.join(L.ROOT, "integration", "_build", "marx2fits_gpu")
+
+
+@pytest.mark.skipif(not (L.have_reference() and os.path.exists(MARX2FITS_GPU)), reason="oracle/_ref or integration/_build not built")
+@pytest.mark.parametrize("case", ["level1_acis_s_hetg_edser", "level1_acis_i_beta_randomize", "level1_hrc_s_letg"])
+def test_marx2fits_gpu_writes_the_stock_events_table(case, tmp_path):
+    """integration/marx2fits_gpu = the unmodified marx2fits.c (header, readers, jdfits table writer) with its computed columns
+    re-pointed at marxb200_level1_*: its EVENTS table against the stock program's (same per-row draw stream) for a fresh stock
+    marx run -- integers exact, float32 columns within one ulp, Y within the reference formula's conditioning bound."""
+    import subprocess
+    args, pixadj, ndraw = L.LEVEL1_CASES[case]
+    out = tmp_path / "out"
+    L.run_stock_marx(out, args, n_rays=300000, seed=9)
+    ref = L.run_stock_marx2fits(out, tmp_path / "ref.fits", pixadj, ndraw, seed=21)
+    env = dict(os.environ, MARX_DATA_DIR=os.path.join(L.REF, "data"), L1_SEED="21")
+    p = subprocess.run([MARX2FITS_GPU, "--pixadj=" + pixadj, str(out), str(tmp_path / "gpu.fits")], env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:]
+    from tests.fits_table import read_bintable
+    gpu, hdr = read_bintable(str(tmp_path / "gpu.fits"), "EVENTS")
+    assert set(gpu) == set(read_bintable(str(tmp_path / "ref.fits"), "EVENTS")[0])
+    desc = L.dump_descriptor(out, pixadj)
+    ytol = None
+    if int(desc["used_dither"]):
+        ytol = L.sky_y_tolerance(ref["Y"].astype(np.float64), desc) + 2.0 * np.spacing(np.abs(ref["Y"]).astype(np.float32)).astype(np.float64)
+    for name, r in ref.items():
+        g = gpu[name]
+        if name == "STATUS":
+            g = (g.astype(np.uint32) << np.array([24, 16, 8, 0], dtype=np.uint32)).sum(axis=1).astype(np.int64)
+        assert len(g) == len(r) > 5000, name
+        if name == "Y" and ytol is not None:
+            assert (np.abs(g.astype(np.float64) - r.astype(np.float64)) <= ytol).all(), name
+        elif r.dtype.kind == "f" and r.dtype.itemsize == 4:
+            d = np.abs(g.view(np.int32).astype(np.int64) - r.view(np.int32).astype(np.int64))
+            assert d.max() <= 1, (name, int(d.max()))
+        elif r.dtype.kind == "f":
+            assert np.allclose(g, r, rtol=1e-12, atol=0), name
+        else:
+            assert np.array_equal(g.astype(np.int64), r.astype(np.int64)), name
