@@ -337,8 +337,10 @@ int marxb200_trace_from (marxb200_ctx *ctx, uint64_t first_ray, uint64_t n, doub
  * event is recorded after every kernel launch; marxb200_get_kernel_ms synchronises, returns the accumulated
  * milliseconds and launch counts per kernel class since the last call, and resets them.  Classes:
  * 0 k0_time_sums, 1 k0_time_scan (k0_time_super + k0_time_bases + k0_time_tiles), 2 k0_source, 3 k01_source_hrma (fused), 4 k1_hrma<0>, 5 k1_hrma<1>, 6 k1_hrma<2>,
- * 7 k2_grating, 8 k3 (acis or hrc), 9 order restoration (5 kernels), 10 Level-1 transforms (marxb200_level1_transform). */
-#define MARXB200_NUM_KERNEL_CLASSES 11
+ * 7 k2_grating, 8 k3 (acis or hrc), 9 order restoration (5 kernels), 10 Level-1 transforms (marxb200_level1_transform),
+ * 11 k1_hrma<3> (HRMA B1), 12 k1_hrma<4> (B2+C1), 13 k1_hrma<5> (C2): the compacting path's cut of the mirror stage behind the
+ * reflectivity tests (it then runs 3 | 11 | 12 | 13 in place of 3 | 5 | 6). */
+#define MARXB200_NUM_KERNEL_CLASSES 14
 int marxb200_set_profiling (marxb200_ctx *ctx, int on);
 int marxb200_get_kernel_ms (marxb200_ctx *ctx, double ms[MARXB200_NUM_KERNEL_CLASSES], uint64_t launches[MARXB200_NUM_KERNEL_CLASSES]);
 

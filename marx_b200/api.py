@@ -288,7 +288,8 @@ class MarxB200:
         self._check(self._lib.marxb200_trace_from(self._ctx, int(first_ray), int(n), float(time_base)))
 
     KERNEL_CLASSES = ("k0_time_sums", "k0_time_scan", "k0_source", "k01_source_hrma", "k1_hrma<0>", "k1_hrma<1>",
-                      "k1_hrma<2>", "k2_grating", "k3_detect", "order_restore", "level1")
+                      "k1_hrma<2>", "k2_grating", "k3_detect", "order_restore", "level1",
+                      "k1_hrma<B1>", "k1_hrma<B2C1>", "k1_hrma<C2>")
 
     def set_profiling(self, on):
         self._check(self._lib.marxb200_set_profiling(self._ctx, 1 if on else 0))
@@ -312,7 +313,8 @@ class MarxB200:
         return [int(v) for v in a]
 
     def internal_counts(self):
-        """[generated, after mirror, after grating, detected, after HRMA phase A, after HRMA phase B] of the last batch"""
+        """[generated, after mirror, after grating, detected, after HRMA phase A, after HRMA phase B (B1 when the mirror stage
+        runs as A | B1 | B2+C1 | C2), between the ACIS kernels, after HRMA B2+C1] of the last batch"""
         a = (C.c_uint64 * 8)()
         self._check(self._lib.marxb200_get_internal_counts(self._ctx, a))
         return [int(v) for v in a]

@@ -342,24 +342,40 @@ __device__ __forceinline__ WarpQueue<ND, NU> &my_queue (unsigned char *smem, uin
 }
 
 // K1 ------------------------------------------------------------------------------------------
-// The mirror stage is three kernels (HRMA phases A, B, C of mx_hrma.cuh) so that every phase starts with
-// full warps although 52 % / 43 % / 33 % of its rays die.  State handed from phase to phase through
-// otherwise unused SoA columns:
+// The mirror stage is a chain of kernels (HRMA phases of mx_hrma.cuh) so that every phase starts with
+// full warps although most of its rays die.  Two cuts of the same per-ray sequence exist:
+//   PHASE 0 | 1 | 2   = A | B | C: cut at the two conic intersections (in-place parity mode, MARXB200_K1_SPLIT=0)
+//   PHASE 0 | 3 | 4 | 5 = A | B1 | B2+C1 | C2: additionally cut behind the two reflectivity tests, where 35-40 % of the rays
+//                       of B and C are absorbed (the scatter, the frame transforms and the next intersection then run on
+//                       re-packed warps); the compacting path
+// State handed from phase to phase through otherwise unused SoA columns:
 //   pha  (i16)  draws consumed so far on the MIRROR sub-stream | 0x4000 if a Box-Muller spare is cached
 //   aux  (f64)  the cached spare
 //   chipx, chipy, pi (f32)  beta, delta, effective-area correction (float-valued table lookups)
-template <int PHASE> struct K1Shape { static constexpr int ND = (PHASE == 1) ? 7 : 6, NU = (PHASE == 1) ? 5 : 2; };
+//   energy, time, ray (f64 bit patterns; PHASE 3 -> 4 -> 5 only)  the blurred surface normal that passed the reflectivity test.
+//               These list columns are dead between the source and the order restoration: the per-ray constants live in RayConst.
+template <int PHASE> struct K1Shape
+{
+   static constexpr bool kNormalOut = (PHASE == 3) || (PHASE == 4), kNormalIn = (PHASE == 4) || (PHASE == 5);
+   static constexpr bool kSpareOut = (PHASE == 1) || kNormalOut, kOptOut = (PHASE == 1) || (PHASE == 3), kLast = (PHASE == 2) || (PHASE == 5);
+   // B1 leaves x and p as they are: its queue carries the index of the input row instead (x, p and the slot key are copied from
+   // there at flush; 52 instead of 100 bytes per entry keeps three CTAs per SM next to the optical-constant tables)
+   static constexpr bool kCarryXP = (PHASE == 3);
+   static constexpr int XO = kCarryXP ? 0 : 6;     // queue columns [0, XO) = x, p
+   static constexpr int ND = XO + (kNormalOut ? 3 : 0) + (kSpareOut ? 1 : 0), NU = 2 + (kOptOut ? 3 : 0);
+};
 
 template <int PHASE>
 __global__ void __launch_bounds__ (kStageThreads, MX_K1_MINBLOCKS) k1_hrma (const __grid_constant__ StageArgs a)
 {
-   constexpr int ND = K1Shape<PHASE>::ND, NU = K1Shape<PHASE>::NU;
+   using Shape = K1Shape<PHASE>;
+   constexpr int ND = Shape::ND, NU = Shape::NU;
    extern __shared__ __align__ (128) unsigned char smem[];
    __shared__ __align__ (8) unsigned long long bar;
-   // only phase B needs the optical-constant tables behind the header; B and C also stage the WFOLD search keys of
-   // their conic (B: contiguous with the tables, C: as a second segment behind the header)
-   const uint32_t seg1 = (PHASE == 1) ? a.blob_bytes : (uint32_t) sizeof (K1Blob);
-   const uint32_t seg2 = (PHASE == 2) ? a.seg2_bytes : 0u;
+   // only the phases that look up the optical constants (B, B1) need the tables behind the header; phases that scatter stage
+   // the WFOLD search keys of their conic (B: contiguous with the tables; C, B2+C1, C2: as a second segment behind the header)
+   const uint32_t seg1 = (PHASE == 1 || PHASE == 3) ? a.blob_bytes : (uint32_t) sizeof (K1Blob);
+   const uint32_t seg2 = (PHASE == 2 || PHASE == 4 || PHASE == 5) ? a.seg2_bytes : 0u;
    stage_blob (smem, a.blob, seg1, &bar, a.seg2_off, seg2);
    const K1Blob &B = *reinterpret_cast<const K1Blob *> (smem);
    const HrmaDev &H = B.H;
@@ -368,14 +384,14 @@ __global__ void __launch_bounds__ (kStageThreads, MX_K1_MINBLOCKS) k1_hrma (cons
    const unsigned char *wkeys = nullptr;
 #else
    const unsigned char *wkeys = (B.wkeys_bytes == 0) ? nullptr
-                                : ((PHASE == 1) ? smem + B.off_wkeys_p : ((PHASE == 2 && seg2) ? smem + ((seg1 + 127u) & ~127u) : nullptr));
+                                : ((PHASE == 1) ? smem + B.off_wkeys_p : ((PHASE != 3 && seg2) ? smem + ((seg1 + 127u) & ~127u) : nullptr));
 #endif
    WarpQueue<ND, NU> &q = my_queue<ND, NU> (smem, staged);
    const PhotonSoA &in = a.in, &out = a.out;
 
    auto trace = [&] (unsigned long long i, double *d, uint32_t *u) -> uint32_t
      {
-        Vec3 x = v_make (0, 0, 0), p = v_make (in.p0[i], in.p1[i], in.p2[i]);
+        Vec3 x = v_make (0, 0, 0), p = v_make (in.p0[i], in.p1[i], in.p2[i]), normal = v_make (0, 0, 0);
         uint32_t shell = 0, flags;
         float beta = 0.f, delta = 1.f, corr = 1.f;
         Rng rng;
@@ -390,53 +406,59 @@ __global__ void __launch_bounds__ (kStageThreads, MX_K1_MINBLOCKS) k1_hrma (cons
              shell = in.shell[i];
              const int st = in.pha[i];
              rng.resume ((uint32_t) (st & 0x3FFF), (st & 0x4000) ? 1 : 0, (st & 0x4000) ? in.aux[i] : 0.0);
-             if (PHASE == 1)
+             const double *wk = wkeys ? reinterpret_cast<const double *> (wkeys + shell * B.wkeys_stride) : nullptr;
+             if (Shape::kNormalIn)
+               normal = v_make (in.energy[i], in.time[i], __longlong_as_double ((long long) in.ray[i]));
+             if (PHASE == 1 || PHASE == 3)
+               hrma_optical_constants (H, H.shell[shell],
+                                       reinterpret_cast<const float *> (smem + B.off_opt_e),
+                                       reinterpret_cast<const float *> (smem + B.off_opt_b),
+                                       reinterpret_cast<const float *> (smem + B.off_opt_d),
+                                       reinterpret_cast<const float *> (smem + B.off_corr_e),
+                                       reinterpret_cast<const float *> (smem + B.off_corr_f),
+                                       energy, beta, delta, corr);
+             else if (PHASE == 2 || PHASE == 4)
+               { beta = in.chipx[i]; delta = in.chipy[i]; corr = in.pi[i]; }
+             if (PHASE == 1) flags = hrma_phase_b (H, shell, energy, beta, delta, corr, x, p, rng, wk);
+             else if (PHASE == 2) flags = hrma_phase_c (H, shell, energy, beta, delta, corr, x, p, rng, wk);
+             else if (PHASE == 3) flags = hrma_phase_b1 (H, shell, beta, delta, corr, x, p, normal, rng);
+             else if (PHASE == 4)
                {
-                  hrma_optical_constants (H, H.shell[shell],
-                                          reinterpret_cast<const float *> (smem + B.off_opt_e),
-                                          reinterpret_cast<const float *> (smem + B.off_opt_b),
-                                          reinterpret_cast<const float *> (smem + B.off_opt_d),
-                                          reinterpret_cast<const float *> (smem + B.off_corr_e),
-                                          reinterpret_cast<const float *> (smem + B.off_corr_f),
-                                          energy, beta, delta, corr);
-                  flags = hrma_phase_b (H, shell, energy, beta, delta, corr, x, p, rng,
-                                        wkeys ? reinterpret_cast<const double *> (wkeys + shell * B.wkeys_stride) : nullptr);
+                  flags = hrma_phase_b2 (H, shell, energy, normal, x, p, rng, wk);
+                  if (flags == 0) flags = hrma_phase_c1 (H, shell, beta, delta, corr, x, p, normal, rng);
                }
-             else
-               {
-                  beta = in.chipx[i]; delta = in.chipy[i]; corr = in.pi[i];
-                  flags = hrma_phase_c (H, shell, energy, beta, delta, corr, x, p, rng,
-                                        wkeys ? reinterpret_cast<const double *> (wkeys + shell * B.wkeys_stride) : nullptr);
-               }
+             else flags = hrma_phase_c2 (H, shell, energy, normal, x, p, rng, wk);
           }
-        d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = p.x; d[4] = p.y; d[5] = p.z;
-        u[0] = slot;
+        if (!Shape::kCarryXP) { d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = p.x; d[4] = p.y; d[5] = p.z; }
+        u[0] = Shape::kCarryXP ? (uint32_t) i : slot;
         u[1] = shell | (((rng.draw & 0x3FFFu) | (rng.have_spare ? 0x4000u : 0u)) << 8);
-        if (PHASE == 1)
-          {
-             d[ND - 1] = rng.spare;
-             u[NU - 3] = __float_as_uint (beta); u[NU - 2] = __float_as_uint (delta); u[NU - 1] = __float_as_uint (corr);
-          }
+        if (Shape::kNormalOut) { d[Shape::XO] = normal.x; d[Shape::XO + 1] = normal.y; d[Shape::XO + 2] = normal.z; }
+        if (Shape::kSpareOut) d[ND - 1] = rng.spare;
+        if (Shape::kOptOut)
+          { u[NU - 3] = __float_as_uint (beta); u[NU - 2] = __float_as_uint (delta); u[NU - 1] = __float_as_uint (corr); }
         return flags;
      };
    auto write_row = [&] (unsigned long long j, const double *d, const uint32_t *u, uint32_t flags)
      {
-        out.x0[j] = d[0]; out.x1[j] = d[1]; out.x2[j] = d[2];
-        out.p0[j] = d[3]; out.p1[j] = d[4]; out.p2[j] = d[5];
+        if (!Shape::kCarryXP)
+          {
+             out.x0[j] = d[0]; out.x1[j] = d[1]; out.x2[j] = d[2];
+             out.p0[j] = d[3]; out.p1[j] = d[4]; out.p2[j] = d[5];
+          }
         out.flags[j] = flags;
         out.shell[j] = (uint8_t) (u[1] & 0xFFu);
-        if (PHASE < 2) out.pha[j] = (int16_t) (u[1] >> 8);
+        if (!Shape::kLast) out.pha[j] = (int16_t) (u[1] >> 8);
         else
           {
              // the last mirror kernel hands the scratch columns back zeroed, as the reference's memset of the batch
              // (source.c:287) leaves them when no detector follows (DetectorType=NONE)
              out.pha[j] = 0; out.chipx[j] = 0.f; out.chipy[j] = 0.f; out.pi[j] = 0.f;
           }
-        if (PHASE == 1)
-          {
-             out.aux[j] = d[ND - 1];
-             out.chipx[j] = __uint_as_float (u[NU - 3]); out.chipy[j] = __uint_as_float (u[NU - 2]); out.pi[j] = __uint_as_float (u[NU - 1]);
-          }
+        if (Shape::kNormalOut)
+          { out.energy[j] = d[Shape::XO]; out.time[j] = d[Shape::XO + 1]; out.ray[j] = (uint64_t) __double_as_longlong (d[Shape::XO + 2]); }
+        if (Shape::kSpareOut) out.aux[j] = d[ND - 1];
+        if (Shape::kOptOut)
+          { out.chipx[j] = __uint_as_float (u[NU - 3]); out.chipy[j] = __uint_as_float (u[NU - 2]); out.pi[j] = __uint_as_float (u[NU - 1]); }
      };
    auto flush_entry = [&] (uint32_t pos, unsigned long long j)
      {
@@ -446,7 +468,14 @@ __global__ void __launch_bounds__ (kStageThreads, MX_K1_MINBLOCKS) k1_hrma (cons
 #pragma unroll
         for (int k = 0; k < NU; k++) u[k] = q.u[k][pos];
         write_row (j, d, u, 0);
-        out.slot[j] = u[0];
+        if (Shape::kCarryXP)
+          {
+             const uint32_t src = u[0];      // a row this warp read a moment ago: L1/L2 hits
+             out.x0[j] = in.x0[src]; out.x1[j] = in.x1[src]; out.x2[j] = in.x2[src];
+             out.p0[j] = in.p0[src]; out.p1[j] = in.p1[src]; out.p2[j] = in.p2[src];
+             out.slot[j] = in.slot[src];
+          }
+        else out.slot[j] = u[0];
      };
    auto in_place = [&] (unsigned long long i, const double *d, const uint32_t *u, uint32_t flags) { write_row (i, d, u, flags); };
    run_stage<ND, NU> (a, q, trace, flush_entry, in_place);
@@ -1129,6 +1158,9 @@ uint32_t stage_smem_bytes (int stage, uint32_t blob_bytes, uint32_t seg2_bytes)
       case 11: return base + warps * (uint32_t) sizeof (WarpQueue<K1Shape<1>::ND, K1Shape<1>::NU>);
       case 12: return hdr + ((seg2_bytes + 127u) & ~127u) + warps * (uint32_t) sizeof (WarpQueue<K1Shape<2>::ND, K1Shape<2>::NU>);
       case 13: return hdr + (kTile / 32) * (uint32_t) sizeof (WarpQueue<6, 2>);
+      case 14: return base + warps * (uint32_t) sizeof (WarpQueue<K1Shape<3>::ND, K1Shape<3>::NU>);
+      case 15: return hdr + ((seg2_bytes + 127u) & ~127u) + warps * (uint32_t) sizeof (WarpQueue<K1Shape<4>::ND, K1Shape<4>::NU>);
+      case 16: return hdr + ((seg2_bytes + 127u) & ~127u) + warps * (uint32_t) sizeof (WarpQueue<K1Shape<5>::ND, K1Shape<5>::NU>);
       case 2: return base + warps * (uint32_t) sizeof (WarpQueue<6, 3>);
       case 3: return base + warps * (uint32_t) sizeof (WarpQueue<6, 7>) + (uint32_t) (kMaxGauss * kStageThreads * sizeof (float));
       case 4: return base + warps * (uint32_t) sizeof (WarpQueue<6, 8>);
@@ -1152,6 +1184,9 @@ int stage_grid_size (int stage, int num_sms, uint32_t blob_bytes, uint32_t seg2_
       case 10: return occupancy_grid (k1_hrma<0>, num_sms, smem);
       case 11: return occupancy_grid (k1_hrma<1>, num_sms, smem);
       case 12: return occupancy_grid (k1_hrma<2>, num_sms, smem);
+      case 14: return occupancy_grid (k1_hrma<3>, num_sms, smem);
+      case 15: return occupancy_grid (k1_hrma<4>, num_sms, smem);
+      case 16: return occupancy_grid (k1_hrma<5>, num_sms, smem);
       case 2: return occupancy_grid (k2_grating, num_sms, smem);
       // the detector-dither variants run on the same grid (ticket-driven persistent kernels: any grid size is correct)
       case 3: cudaFuncSetAttribute (k3_acis<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
@@ -1180,12 +1215,17 @@ void launch_source_hrma (const SourceArgs &a, const StageArgs &st, int grid, cud
 }
 void launch_hrma (const StageArgs &a, int phase, int grid, cudaStream_t s)
 {
-   const uint32_t smem = stage_smem_bytes (10 + phase, a.blob_bytes, (phase == 2) ? a.seg2_bytes : 0u);
+   // phases 0, 1, 2 = A, B, C; 3, 4, 5 = B1, B2+C1, C2 (the cut behind the reflectivity tests)
+   const bool two_seg = (phase == 2) || (phase == 4) || (phase == 5);
+   const uint32_t smem = stage_smem_bytes ((phase < 3) ? 10 + phase : 11 + phase, a.blob_bytes, two_seg ? a.seg2_bytes : 0u);
    switch (phase)
      {
       case 0: k1_hrma<0><<<grid, kStageThreads, smem, s>>> (a); break;
       case 1: k1_hrma<1><<<grid, kStageThreads, smem, s>>> (a); break;
-      default: k1_hrma<2><<<grid, kStageThreads, smem, s>>> (a); break;
+      case 2: k1_hrma<2><<<grid, kStageThreads, smem, s>>> (a); break;
+      case 3: k1_hrma<3><<<grid, kStageThreads, smem, s>>> (a); break;
+      case 4: k1_hrma<4><<<grid, kStageThreads, smem, s>>> (a); break;
+      default: k1_hrma<5><<<grid, kStageThreads, smem, s>>> (a); break;
      }
 }
 void launch_grating (const StageArgs &a, int grid, cudaStream_t s) { k2_grating<<<grid, kStageThreads, stage_smem_bytes (2, a.blob_bytes), s>>> (a); }

@@ -71,15 +71,17 @@ struct marxb200_ctx
    double source_distance = 0.0;
    void *blob1 = nullptr, *blob2 = nullptr, *blob3 = nullptr;
    uint32_t blob1_bytes = 0, blob2_bytes = 0, blob3_bytes = 0;
-   uint32_t k1b_bytes = 0, k1c_seg2_off = 0, k1c_seg2_bytes = 0;
+   uint32_t k1b_bytes = 0, k1c_seg2_off = 0, k1c_seg2_bytes = 0, k1b1_bytes = 0, k1b2_seg2_off = 0;
    struct Tally { TallyPlan plan; unsigned long long *bins; uint64_t total; };
    std::vector<Tally> tallies;
    bool det_dither_dirty = false;                // uploaded photons may carry detector dither: the per-ray columns are live
    double aspsol_t_last = 0.0;                   // ASPSOL dither: time of the last state (rays at or beyond it end the run)
-   int grid1[3] = {0, 0, 0}, grid2 = 0, grid3 = 0, grid01 = 0;
+   int grid1[6] = {0, 0, 0, 0, 0, 0}, grid2 = 0, grid3 = 0, grid01 = 0;
    bool detector_is_hrc = false;
    int first_mirror_kernel = 0;                  // 1: phase A already ran fused with the source (marxb200_trace)
    int k3_split = 1;                             // ACIS detector stage as two kernels (MARXB200_K3_SPLIT=0: one kernel)
+   int k1_split = 1;                             // compacting mirror stage cut behind the reflectivity tests: A | B1 | B2+C1 | C2
+                                                 // (MARXB200_K1_SPLIT=0: A | B | C, which the in-place parity mode always runs)
 
    // host boundary staging
    void *d_aos = nullptr; uint64_t d_aos_cap = 0;
@@ -214,6 +216,7 @@ extern "C" int marxb200_create (marxb200_ctx **ctxp, int device_ordinal, uint64_
    c->device = device_ordinal;
    c->seed = seed;
    if (const char *e = getenv ("MARXB200_K3_SPLIT")) c->k3_split = atoi (e);      // developer A/B switch
+   if (const char *e = getenv ("MARXB200_K1_SPLIT")) c->k1_split = atoi (e);      // developer A/B switch
    cudaDeviceProp prop;
    CUDA_OK (cudaGetDeviceProperties (&prop, device_ordinal));
    c->num_sms = prop.multiProcessorCount;
@@ -379,10 +382,18 @@ extern "C" int marxb200_set_hrma (marxb200_ctx *c, const marxb200_hrma_desc *d)
       const K1Blob *B = reinterpret_cast<const K1Blob *> (blob.data ());
       c->k1b_bytes = B->off_wkeys_p + B->wkeys_bytes;
       c->k1c_seg2_off = B->off_wkeys_h; c->k1c_seg2_bytes = B->wkeys_bytes;
+      // the other cut (B1 | B2+C1 | C2): B1 the header and the tables, B2+C1 the header plus the P-conic keys, C2 like C
+      c->k1b1_bytes = B->off_wkeys_p; c->k1b2_seg2_off = B->off_wkeys_p;
    }
    c->grid1[0] = stage_grid_size (10, c->num_sms, c->blob1_bytes);
    c->grid1[1] = stage_grid_size (11, c->num_sms, c->k1b_bytes);
    c->grid1[2] = stage_grid_size (12, c->num_sms, c->blob1_bytes, c->k1c_seg2_bytes);
+   c->grid1[3] = stage_grid_size (14, c->num_sms, c->k1b1_bytes);
+   c->grid1[4] = stage_grid_size (15, c->num_sms, c->blob1_bytes, c->k1c_seg2_bytes);
+   c->grid1[5] = stage_grid_size (16, c->num_sms, c->blob1_bytes, c->k1c_seg2_bytes);
+   if (getenv ("MARXB200_VERBOSE"))
+     fprintf (stderr, "marxb200: HRMA grids A %d B %d C %d | B1 %d B2C1 %d C2 %d (x %d threads)\n", c->grid1[0], c->grid1[1], c->grid1[2],
+              c->grid1[3], c->grid1[4], c->grid1[5], kStageThreads);
    c->grid01 = fused_source_grid (c->num_sms);
    c->have_hrma = true;
    return 0;
@@ -634,14 +645,20 @@ static int run_stage (marxb200_ctx *c, int stage)
    // the mirror stage runs as three kernels (HRMA phases A, B, C, mx_hrma.cuh), each re-packing its survivors
    // ... and the ACIS detector stage as two (geometry + QE, then FEF + streak; mx_acis.cuh)
    const bool k3_two = (stage == 3) && !c->detector_is_hrc && (c->k3_split != 0);
-   const int n_kernels = (stage == 1) ? 3 : (k3_two ? 2 : 1);
+   // the mirror stage as A | B | C (in place, or MARXB200_K1_SPLIT=0) or as A | B1 | B2+C1 | C2 (compacting)
+   const bool k1_four = (stage == 1) && c->compact && (c->k1_split != 0);
+   static const int phases3[3] = {0, 1, 2}, phases4[4] = {0, 3, 4, 5};
+   const int *phases = k1_four ? phases4 : phases3;
+   const int n_kernels = (stage == 1) ? (k1_four ? 4 : 3) : (k3_two ? 2 : 1);
    const int k_first = (stage == 1) ? c->first_mirror_kernel : 0;
    CUDA_OK (cudaMemsetAsync (c->d_ticket, 0, 4 * sizeof (unsigned long long), c->stream));
    if (c->compact)
      {
-        // output counters grow by atomics: zero them (d_counts[4], [5] = after k1a, k1b; d_counts[stage] = stage output)
+        // output counters grow by atomics: zero them (d_counts[4], [5], [7] = after the first, second, third mirror kernel;
+        // [6] = between the ACIS kernels; d_counts[stage] = stage output)
         CUDA_OK (cudaMemsetAsync (c->d_counts + stage, 0, sizeof (unsigned long long), c->stream));
         if (stage == 1) CUDA_OK (cudaMemsetAsync (c->d_counts + 4 + k_first, 0, (2 - k_first) * sizeof (unsigned long long), c->stream));
+        if (k1_four) CUDA_OK (cudaMemsetAsync (c->d_counts + 7, 0, sizeof (unsigned long long), c->stream));
         if (k3_two) CUDA_OK (cudaMemsetAsync (c->d_counts + 6, 0, sizeof (unsigned long long), c->stream));
      }
    const unsigned long long *n_in = (k_first == 1) ? c->d_counts + 4 : c->d_counts + c->stage_done;
@@ -651,16 +668,23 @@ static int run_stage (marxb200_ctx *c, int stage)
         a.in = c->buf[c->cur];
         a.out = c->compact ? c->buf[1 - c->cur] : c->buf[c->cur];
         a.n_in = n_in;
-        a.n_out = (k == n_kernels - 1) ? c->d_counts + stage : ((stage == 1) ? c->d_counts + 4 + k : c->d_counts + 6);
+        a.n_out = (k == n_kernels - 1) ? c->d_counts + stage : ((stage == 1) ? c->d_counts + ((k == 2) ? 7 : 4 + k) : c->d_counts + 6);
         a.ticket = c->d_ticket + k;
         // big inputs amortise the ticket atomic over several tiles; small ones need fine-grained balancing
-        a.chunk_tiles = (stage == 1 && k == 0) ? 4 : ((stage == 1 && k == 1) ? 2 : 1);
+        a.chunk_tiles = (stage == 1 && k == 0) ? 4 : ((stage == 1 && k < n_kernels - 1) ? 2 : 1);
         prof_begin (c);
         switch (stage)
           {
-           case 1: a.blob = c->blob1; a.blob_bytes = (k == 1) ? c->k1b_bytes : c->blob1_bytes;
-                   a.seg2_off = c->k1c_seg2_off; a.seg2_bytes = (k == 2) ? c->k1c_seg2_bytes : 0;
-                   launch_hrma (a, k, c->grid1[k], c->stream); prof_mark (c, 4 + k); break;
+           case 1:
+             {
+                const int ph = phases[k];
+                a.blob = c->blob1; a.blob_bytes = (ph == 1) ? c->k1b_bytes : ((ph == 3) ? c->k1b1_bytes : c->blob1_bytes);
+                a.seg2_off = (ph == 4) ? c->k1b2_seg2_off : c->k1c_seg2_off;
+                a.seg2_bytes = (ph == 2 || ph == 4 || ph == 5) ? c->k1c_seg2_bytes : 0;
+                launch_hrma (a, ph, c->grid1[ph], c->stream);
+                prof_mark (c, (ph < 3) ? 4 + ph : 8 + ph);          // classes 4, 5, 6 = A, B, C; 11, 12, 13 = B1, B2+C1, C2
+                break;
+             }
            case 2: a.blob = c->blob2; a.blob_bytes = c->blob2_bytes; launch_grating (a, c->grid2, c->stream); prof_mark (c, 7); break;
            case 3: a.blob = c->blob3; a.blob_bytes = c->blob3_bytes;
                    if (c->detector_is_hrc) launch_hrc (a, c->grid3, c->stream); else launch_acis (a, c->grid3, c->stream, k3_two ? k + 1 : 0);

@@ -251,20 +251,28 @@ MX_HD Vec3 conic_normal (const double *conic, const Vec3 &x)
    return n;
 }
 
-// reflect_from_conic after the intersection test, hrma.c:499-544.  returns 0 ok, -1 absorbed
-MX_HD int reflect_at_point (const HrmaDev &H, const double *conic, const WfoldDev &wfold, double scat_factor,
-                            double blur, double energy, double beta, double delta, double corr,
-                            const Vec3 &x, Vec3 &p, Rng &rng, const double *wfold_keys = nullptr)
+// reflect_from_conic after the intersection test, hrma.c:499-544, in two halves (the mirror kernels can be cut between them:
+// 35-45 % of the rays are absorbed at the reflectivity test, and the scatter + transforms behind it then run on full warps).
+// first half: surface normal, blur, reflectivity test.  returns 0 ok, -1 absorbed; leaves the (blurred) normal in `normal`
+MX_HD int reflect_test (const HrmaDev &H, const double *conic, double blur, double beta, double delta, double corr,
+                        const Vec3 &x, const Vec3 &p, Vec3 &normal, Rng &rng)
 {
-   Vec3 normal = conic_normal (conic, x);
+   normal = conic_normal (conic, x);
    if (H.use_blur) blur_normal (normal, blur, rng);
-   double p_dot_n = v_dot (p, normal);
    if (H.is_ideal == 0)
      {
+        double p_dot_n = v_dot (p, normal);
         double r = rng.uniform ();
         double rfl = reflectivity (fabs (p_dot_n), beta, delta);
         if (r >= rfl * corr) return -1;
      }
+   return 0;
+}
+// second half: specular reflection about `normal`, WFOLD scatter.  p_dot_n is the same dot product the first half formed.
+MX_HD int reflect_scatter (const HrmaDev &H, const WfoldDev &wfold, double scat_factor, double energy, const Vec3 &normal,
+                           Vec3 &p, Rng &rng, const double *wfold_keys = nullptr)
+{
+   double p_dot_n = v_dot (p, normal);
    p = v_ax1_bx2 (1.0, p, -2.0 * p_dot_n, normal);
    if (H.use_wfold == 0) return 0;
    double sin_grazing = -p_dot_n;
@@ -275,6 +283,14 @@ MX_HD int reflect_at_point (const HrmaDev &H, const double *conic, const WfoldDe
    if (rng.uniform () < 0.5) delta_grazing = -delta_grazing;
    p = v_rotate_unit (p, v_cross (p, normal), delta_grazing);
    return 0;
+}
+MX_HD int reflect_at_point (const HrmaDev &H, const double *conic, const WfoldDev &wfold, double scat_factor,
+                            double blur, double energy, double beta, double delta, double corr,
+                            const Vec3 &x, Vec3 &p, Rng &rng, const double *wfold_keys = nullptr)
+{
+   Vec3 normal;
+   if (0 != reflect_test (H, conic, blur, beta, delta, corr, x, p, normal, rng)) return -1;
+   return reflect_scatter (H, wfold, scat_factor, energy, normal, p, rng, wfold_keys);
 }
 
 // phase A.  In: energy-independent; p from the source.  Out: x, p in the OSAC-P frame AT the P-conic
@@ -357,14 +373,23 @@ MX_HD void hrma_optical_constants (const HrmaDev &H, const HrmaShellDev &h, cons
 }
 
 // phase B.  In: x, p at the P intersection (OSAC-P frame).  Out: x, p at the H intersection (OSAC-H frame).
-MX_HD uint32_t hrma_phase_b (const HrmaDev &H, uint32_t shell, double energy, float beta, float delta, float corr_f32,
-                             Vec3 &x, Vec3 &p, Rng &rng, const double *wfold_keys = nullptr)
+// B = B1 (normal, blur, reflectivity test at the P conic; leaves the blurred normal) ; B2 (reflection, scatter, back transform,
+// CAP struts, OSAC-H transform, H-conic intersection)
+MX_HD uint32_t hrma_phase_b1 (const HrmaDev &H, uint32_t shell, float beta, float delta, float corr_f32,
+                              const Vec3 &x, const Vec3 &p, Vec3 &normal, Rng &rng)
+{
+   const uint32_t UNREFLECTED = 0x02;
+   const HrmaShellDev &h = H.shell[shell];
+   double corr = (H.num_opt != 0 && H.use_scale) ? sqrt ((double) corr_f32) : 1.0;
+   if (0 != reflect_test (H, h.conic_p, h.p_blur, beta, delta, corr, x, p, normal, rng)) return UNREFLECTED;
+   return 0;
+}
+MX_HD uint32_t hrma_phase_b2 (const HrmaDev &H, uint32_t shell, double energy, const Vec3 &normal_p,
+                              Vec3 &x, Vec3 &p, Rng &rng, const double *wfold_keys = nullptr)
 {
    const uint32_t VBLOCKED = 0x10, UNREFLECTED = 0x02;
    const HrmaShellDev &h = H.shell[shell];
-   double corr = (H.num_opt != 0 && H.use_scale) ? sqrt ((double) corr_f32) : 1.0;
-   if (0 != reflect_at_point (H, h.conic_p, h.wfold_p, h.p_scat, h.p_blur, energy, beta, delta, corr, x, p, rng, wfold_keys))
-     return UNREFLECTED;
+   if (0 != reflect_scatter (H, h.wfold_p, h.p_scat, energy, normal_p, p, rng, wfold_keys)) return UNREFLECTED;
    const Vec3 to_p = v_make (h.to_osac_p[0], h.to_osac_p[1], h.to_osac_p[2]);
    const Vec3 to_h = v_make (h.to_osac_h[0], h.to_osac_h[1], h.to_osac_h[2]);
    p = m3_mul (h.bwd_p, p);
@@ -382,16 +407,33 @@ MX_HD uint32_t hrma_phase_b (const HrmaDev &H, uint32_t shell, double energy, fl
    if (-1 == conic_intersection_t<false> (h.conic_h, x, p, normal)) return UNREFLECTED;
    return 0;
 }
+MX_HD uint32_t hrma_phase_b (const HrmaDev &H, uint32_t shell, double energy, float beta, float delta, float corr_f32,
+                             Vec3 &x, Vec3 &p, Rng &rng, const double *wfold_keys = nullptr)
+{
+   Vec3 normal;
+   const uint32_t flags = hrma_phase_b1 (H, shell, beta, delta, corr_f32, x, p, normal, rng);
+   if (flags) return flags;
+   return hrma_phase_b2 (H, shell, energy, normal, x, p, rng, wfold_keys);
+}
 
 // phase C.  In: x, p at the H intersection (OSAC-H frame).  Out: x, p in MARX coordinates behind the mirror.
-MX_HD uint32_t hrma_phase_c (const HrmaDev &H, uint32_t shell, double energy, float beta, float delta, float corr_f32,
-                             Vec3 &x, Vec3 &p, Rng &rng, const double *wfold_keys = nullptr)
+// C = C1 (normal, blur, reflectivity test at the H conic; leaves the blurred normal) ; C2 (reflection, scatter, back transform,
+// postcollimator struts)
+MX_HD uint32_t hrma_phase_c1 (const HrmaDev &H, uint32_t shell, float beta, float delta, float corr_f32,
+                              const Vec3 &x, const Vec3 &p, Vec3 &normal, Rng &rng)
+{
+   const uint32_t UNREFLECTED = 0x02;
+   const HrmaShellDev &h = H.shell[shell];
+   double corr = (H.num_opt != 0 && H.use_scale) ? sqrt ((double) corr_f32) : 1.0;
+   if (0 != reflect_test (H, h.conic_h, h.h_blur, beta, delta, corr, x, p, normal, rng)) return UNREFLECTED;
+   return 0;
+}
+MX_HD uint32_t hrma_phase_c2 (const HrmaDev &H, uint32_t shell, double energy, const Vec3 &normal_h,
+                              Vec3 &x, Vec3 &p, Rng &rng, const double *wfold_keys = nullptr)
 {
    const uint32_t VBLOCKED = 0x10, UNREFLECTED = 0x02;
    const HrmaShellDev &h = H.shell[shell];
-   double corr = (H.num_opt != 0 && H.use_scale) ? sqrt ((double) corr_f32) : 1.0;
-   if (0 != reflect_at_point (H, h.conic_h, h.wfold_h, h.h_scat, h.h_blur, energy, beta, delta, corr, x, p, rng, wfold_keys))
-     return UNREFLECTED;
+   if (0 != reflect_scatter (H, h.wfold_h, h.h_scat, energy, normal_h, p, rng, wfold_keys)) return UNREFLECTED;
    p = m3_mul (h.bwd_h, p);
    x = m3_mul (h.bwd_h, x);
    x = v_diff (x, v_make (h.to_osac_h[0], h.to_osac_h[1], h.to_osac_h[2]));
@@ -401,6 +443,14 @@ MX_HD uint32_t hrma_phase_c (const HrmaDev &H, uint32_t shell, double energy, fl
         if (intersects_struts (x, p, H.cap_position, st)) return VBLOCKED;
      }
    return 0;
+}
+MX_HD uint32_t hrma_phase_c (const HrmaDev &H, uint32_t shell, double energy, float beta, float delta, float corr_f32,
+                             Vec3 &x, Vec3 &p, Rng &rng, const double *wfold_keys = nullptr)
+{
+   Vec3 normal;
+   const uint32_t flags = hrma_phase_c1 (H, shell, beta, delta, corr_f32, x, p, normal, rng);
+   if (flags) return flags;
+   return hrma_phase_c2 (H, shell, energy, normal, x, p, rng, wfold_keys);
 }
 
 // the whole stage for one ray (A;B;C) -- used by the developer host check; the kernels call the phases

@@ -8,7 +8,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from tests.test_gpu_oracle import check_cuda_against_oracle
+from tests.test_gpu_oracle import check_compacted_equals_in_place, check_cuda_against_oracle
 from tests.test_oracle_vs_reference import CASES, HAVE_REF, REF, expand_args
 
 pytestmark = pytest.mark.gpu
@@ -48,3 +48,5 @@ def test_cuda_matches_oracle_for_parameter_variation(tmp_path, name, args, seed,
         assert 0 < counts[0] < 1 << 17 and counts[1] > 0
     else:
         assert counts[0] == 1 << 17 and counts[1] > 0
+    # ... and the compacting product path (other kernel cuts, fused entry) leaves exactly those survivors
+    check_compacted_equals_in_place(pack, seed, first, 1 << 17)
