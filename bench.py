@@ -351,8 +351,12 @@ def cuda_arm(args):
     # device time per STEP of each kernel class (a class may hold several launches per step: the time scan is 3 kernels, the
     # ACIS detector stage 2, the order restoration 5)
     per = {k: (v[0] / args.steps) for k, v in kms.items()}
-    stage_ms = [per["k0_time_sums"] + per["k0_time_scan"], per["k01_source_hrma"], per["k1_hrma<1>"], per["k1_hrma<2>"],
-                per["k2_grating"], per["k3_detect"], per["order_restore"]]
+    # the mirror stage behind the fused entry runs as B1 | B2+C1 | C2 (cut behind the reflectivity tests) or, with
+    # MARXB200_K1_SPLIT=0, as B | C
+    k1_four = kms["k1_hrma<B1>"][1] > 0
+    k1_names = ["k1_hrma<B1>", "k1_hrma<B2C1>", "k1_hrma<C2>"] if k1_four else ["k1_hrma<1>", "k1_hrma<2>"]
+    stage_ms = ([per["k0_time_sums"] + per["k0_time_scan"], per["k01_source_hrma"]] + [per[k] for k in k1_names]
+                + [per["k2_grating"], per["k3_detect"], per["order_restore"]])
     # e2e leg
     timed(2, e2e=True)
     ms_e2e, _, n_events = timed(args.steps, e2e=True)
@@ -381,21 +385,25 @@ def cuda_arm(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-    # dominant kernel: k1_hrma<1> (HRMA phase B: P-conic blur, Fresnel reflectivity, scatter, CAP struts, H-conic
-    # intersection).  Algorithmic bytes per INPUT ray of that kernel: R x,p 48 + energy 8 +
-    # shell/state 3 = 59; W (57 % survive) x,p 48 + state 23 -> 59 + 0.57*71 = 100 B.
-    n_k1b = None
+    # dominant kernel among those that read their input from HBM: HRMA phase B1 (optical constants, P-conic normal, blur, Fresnel
+    # reflectivity test) -- or the whole phase B when the mirror stage runs uncut.  Algorithmic bytes per INPUT ray of that kernel
+    # (DESIGN.md section 4): R x,p 48 + energy 8 + shell/state 3 = 59; W per survivor x,p 48 + state 23 = 71 (B), + normal 24 = 95 (B1)
+    ic = None
     try:
-        n_k1b = int(m.internal_counts()[4])
+        ic = [int(v) for v in m.internal_counts()]
     except Exception:
         pass
-    k1b_in = n_k1b if n_k1b else int(0.476 * n)
-    k1b_bytes = 100.0 * k1b_in
-    k1_ms = per["k1_hrma<1>"]
+    roof_kernel = "k1_hrma<3> (B1)" if k1_four else "k1_hrma<1>"
+    k1b_in = ic[4] if ic and ic[4] else int(0.476 * n)
+    k1b_out = ic[5] if ic and ic[5] else int((0.62 if k1_four else 0.573) * k1b_in)
+    k1b_bytes = 59.0 * k1b_in + (95.0 if k1_four else 71.0) * k1b_out
+    k1_ms = per[k1_names[0]]
     achieved = k1b_bytes / (k1_ms * 1e-3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "k1b_traffic.json"))).get("dram_bytes_per_launch")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "k1b_traffic.json")))
+        ent = tj.get("all_kernels", {}).get("k1_hrma<3>" if k1_four else "k1_hrma<1>")
+        traffic = (ent["dram_read_bytes"] + ent["dram_write_bytes"]) if ent else None
     except Exception:
         pass
     # FP64 peak: not in MEASURED_PEAKS.json -> measured live with the library's DFMA-chain microbenchmark
@@ -408,8 +416,9 @@ def cuda_arm(args):
             fp64_src = "measured in this run (marxb200_measure_fp64_peak: DFMA chains, best of 5)"
         except Exception:  # noqa: BLE001
             fp64_peak, fp64_src = 37.0, "datasheet (measurement failed)"
-    names = ["K0 time pre-pass (k0_time_sums+k0_time_scan)", "K0+K1a fused (k01_source_hrma)", "K1b (k1_hrma<1>)", "K1c (k1_hrma<2>)",
-             "K2 (k2_grating)", "K3 (k3_acis<.,1> + k3_acis<.,2>)", "order restore (5 kernels)"]
+    names = (["K0 time pre-pass (k0_time_sums+k0_time_scan)", "K0+K1a fused (k01_source_hrma)"]
+             + (["K1 B1 (k1_hrma<3>)", "K1 B2+C1 (k1_hrma<4>)", "K1 C2 (k1_hrma<5>)"] if k1_four else ["K1b (k1_hrma<1>)", "K1c (k1_hrma<2>)"])
+             + ["K2 (k2_grating)", "K3 (k3_acis<.,1> + k3_acis<.,2>)", "order restore (5 kernels)"])
     kernels = {}
     for k, name in enumerate(names):
         kernels[name] = {"ms": stage_ms[k], "share": stage_ms[k] / sum(stage_ms)}
@@ -431,9 +440,10 @@ def cuda_arm(args):
                         "event) is copied to pinned host memory inside the timed region, overlapped with the next batch; the "
                         "only per-step host input of this path is the batch descriptor (first ray, count, time base)"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k1_hrma<1>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": roof_kernel, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": k1b_bytes, "input_rays_per_launch": k1b_in, "avg_launch_ms": k1_ms,
+                     "algorithmic_bytes_per_launch": k1b_bytes, "input_rays_per_launch": k1b_in, "output_rays_per_launch": k1b_out,
+                     "avg_launch_ms": k1_ms,
                      "note": "every kernel of this path sits above the FP64/HBM ridge (SURVEY 8d): instruction issue, not HBM, "
                              "binds; the HBM fraction is reported because the contract asks for it",
                      "whole_path": {"hbm_gbs_at_179B_per_ray": path_hbm_gbs, "hbm_frac": path_hbm_gbs / hbm_peak,
