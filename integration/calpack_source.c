@@ -58,10 +58,12 @@ int calpack_dump_source (mxcp_writer *w, void *marx_source)
    memset (v, 0, sizeof (v));
    int rayfile = 0;
    type = calpack_source_shape (st, v + 13, rot, img);       /* 0 POINT, 1 GAUSS, 2 BETA, 3 DISK, 4 LINE, 5 IMAGE, -1 unsupported */
-   if ((type < 0) && calpack_is_rayfile (st))
+   if ((type < 0) && (st->create_photons != NULL))
      {
-	/* RAYFILE: the stock host code reads the photons and the caller injects them (marxb200_upload_from); the device
-	 * source is never used and is packed as an inert POINT source.  Return value 1 tells the caller. */
+	/* RAYFILE, and the sources that only exist as host code (USER = a dlopen'ed generator, SAOSAC = a ray file, SIMPUT = an
+	 * external library): the stock host code produces the photons -- energies, directions, times, tags, dither -- and the
+	 * caller injects them (marxb200_upload_from); the device source is never used and is packed as an inert POINT source.
+	 * Return value 1 tells the caller. */
 	type = 0; rayfile = 1;
      }
    if (type < 0) return -1;

@@ -2,7 +2,7 @@
  *
  * The stock marx/src/marx.c is linked with
  *    -Wl,--wrap=JDMsrandom,--wrap=marx_mirror_init,--wrap=marx_grating_init,--wrap=marx_detector_init,
- *        --wrap=marx_create_photons (RAYFILE sources keep the stock one and inject its photons),--wrap=marx_mirror_reflect,--wrap=marx_grating_diffract,--wrap=marx_detect,
+ *        --wrap=marx_create_photons (RAYFILE / USER / SAOSAC / SIMPUT sources keep the stock one and inject its photons),--wrap=marx_mirror_reflect,--wrap=marx_grating_diffract,--wrap=marx_detect,
  *        --wrap=marx_write_photons,--wrap=marx_prune_photons,--wrap=marx_dump_to_rayfile,--wrap=marx_dealloc_photon_type
  * so that its calls (marx.c:245,254,263,569) reach the __wrap_* functions below while pfile parameter handling,
  * the stock *_init functions (calibration file readers), obs.par and the marxio/jdfits writers stay what they are
@@ -55,7 +55,7 @@ static uint64_t Next_Ray;              /* 64-bit global ray index = RNG counter;
 static int Host_Is_Stale;              /* photons of the current batch live in HBM only */
 static int Have_Support_Orders;
 static int Stock_Egress;               /* MARXB200_EGRESS=stock */
-static int Source_Is_Rayfile;          /* SourceType=RAYFILE: the stock host code reads the photons, the GPU traces them */
+static int Source_Is_Rayfile;          /* SourceType=RAYFILE, USER, SAOSAC, SIMPUT: the stock host code produces the photons, the GPU traces them */
 static int Bulk_Written;               /* the current batch went to the output directory straight from the device */
 
 /* MARXB200_TIMING=1: host wall time spent in each wrapped call, printed when the driver frees its photon buffer */
@@ -110,7 +110,7 @@ static int gpu_init (Marx_Source_Type *st, Marx_Photon_Type *pt)
    meta[0] = Mirror_Id; meta[1] = Grating_Id; meta[2] = Detector_Id; meta[5] = (double) Seed;
    CP_F64 (&w, "meta", meta, 8);
    if (-1 == (Source_Is_Rayfile = calpack_dump_source (&w, st)))
-     marx_error ("marxb200: SourceType must be POINT, GAUSS, BETA, DISK, LINE, IMAGE or RAYFILE for the GPU path");
+     marx_error ("marxb200: this SourceType has neither a device kernel nor a stock host generator");
    else if ((-1 == calpack_dump_dither (&w))
 	    || (-1 == calpack_dump_hrma (&w))
 	    || (-1 == calpack_dump_grating (&w, Grating_Id))
@@ -179,7 +179,8 @@ int __wrap_marx_create_photons (Marx_Source_Type *st, Marx_Photon_Type *pt, unsi
 
    if (Source_Is_Rayfile)
      {
-	/* RAYFILE re-entry (s-rayfile.c:188-221): the stock host code reads the records, fixes up their times, tags and
+	/* host-generated sources (USER s-user.c:189-236, SAOSAC s-saosac.c, SIMPUT s-simput.c) go the same way as the
+	 * RAYFILE re-entry (s-rayfile.c:188-221): the stock host code reads the records, fixes up their times, tags and
 	 * (record-only) dither state and sets pt->history from the file; the list is then injected into HBM and the
 	 * stage wrappers skip what the history says was already done (hrma.c:1171, diffract.c:982, acis-s.c:186). */
 	unsigned int got = 0;

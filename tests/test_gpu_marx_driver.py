@@ -221,3 +221,52 @@ def test_rayfile_dump_and_reentry(tmp_path):
     open(patched, "wb").write(bytes(data))
     r = run_marx(MARX_GPU, tmp_path / "skip", [a for a in args if not a.startswith("RayFile=")] + ["RayFile=" + patched])
     assert "Reflecting from HRMA [B200]" not in r.stdout and "Diffracting from HETG [B200]" in r.stdout
+
+
+@pytest.mark.gpu
+@needs_driver
+def test_user_source_is_generated_by_the_stock_host_code_and_traced_on_the_gpu(tmp_path):
+    """SourceType=USER (s-user.c:160-236: a dlopen'ed generator; likewise SAOSAC and SIMPUT) has no device kernel: the unmodified
+    host code produces the photons -- energies, directions, arrival times, tags, dither -- and the shim injects every batch into
+    HBM (marxb200_upload_from), exactly like the RAYFILE re-entry.  The generator is the reference's own example
+    (marx/doc/examples/user-source/point.c, built into oracle/_ref by oracle/ref/Makefile).
+      * the STOCK CPU marx, told to dump instead of trace (DumpToRayFile=yes, marx.c:583-588), writes the very photons marx_gpu
+        generates (the stages draw nothing from JDMrandom on the GPU path, the dump run skips them);
+      * those records pushed through the C ABI batch by batch must give marx_gpu's event files, value for value;
+      * the detected fraction agrees with the stock CPU run (own RNG in the stages) within Poisson noise."""
+    user_so = os.path.join(REF, "user_point.so")
+    if not os.path.exists(user_so):
+        pytest.skip("oracle/_ref/user_point.so not built")
+    cfg = CONFIGS["c2_hetg_acis_s"]
+    n, dn, seed = 200000, 100000, 7
+    base = (COMMON + [a for a in cfg["args"] if not a.startswith("SourceType=")]
+            + ["SourceType=USER", "UserSourceFile=" + user_so, "NumRays=%d" % n, "dNumRays=%d" % dn, "RandomSeed=%d" % seed, "Verbose=1"])
+    rays = str(tmp_path / "rays.dat")
+    run_marx(os.path.join(REF, "marx"), tmp_path / "dump", base + ["DumpToRayFile=yes", "RayFile=" + rays])
+    raw = np.fromfile(rays, dtype=marx_b200.PHOTON_DTYPE, offset=16)
+    assert len(raw) == n and (raw["tag"] == np.arange(n, dtype=np.uint32)).all()
+    p = run_marx(MARX_GPU, tmp_path / "out", base)
+    assert "marxb200: ray trace on CUDA device" in p.stdout and "Reflecting from HRMA [B200]" in p.stdout
+    got = read_dir(tmp_path / "out")
+    want = []
+    with marx_b200.MarxB200("c2_hetg_acis_s", seed=seed, max_photons=dn) as m:
+        for first in range(0, n, dn):
+            m.upload(raw[first:first + dn])           # the dump holds absolute arrival times (s-rayfile.c:145)
+            m.mirror_reflect(); m.grating_diffract(); m.detect()
+            want.append(m.download().copy())
+    ph = np.concatenate(want)
+    assert len(got["energy.dat"]) == len(ph) > 5000
+    assert (got["tag.dat"].astype(np.uint32) == ph["tag"]).all()
+    assert (got["energy.dat"] == ph["energy"].astype(np.float32)).all()
+    for k, f in enumerate(("ypos.dat", "zpos.dat")):
+        assert (got[f] == ph["x"][:, k + 1].astype(np.float32)).all(), f
+    assert (got["mirror.dat"] == ph["mirror_shell"].astype(np.int16)).all()
+    assert (got["detector.dat"] == ph["ccd_num"]).all() and (got["order.dat"] == ph["order"]).all()
+    assert (got["xpixel.dat"] == ph["y_pixel"]).all() and (got["ypixel.dat"] == ph["z_pixel"]).all()
+    assert (got["pha.dat"] == ph["pulse_height"]).all()
+    assert (got["sky_ra.dat"] == ph["dither"][:, 0]).all() and (got["sky_dec.dat"] == ph["dither"][:, 1]).all()
+    assert (np.diff(got["time.dat"].astype(np.float64)) >= 0).all()
+    # statistics against the stock CPU run of the same parameters
+    q = run_marx(os.path.join(REF, "marx"), tmp_path / "cpu", base)
+    n_cpu, n_gpu = len(read_dir(tmp_path / "cpu")["energy.dat"]), len(ph)
+    assert abs(n_cpu - n_gpu) < 5.0 * np.sqrt(n_cpu + n_gpu), (n_cpu, n_gpu)

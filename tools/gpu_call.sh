@@ -1,11 +1,3 @@
 cd /root/repo
 mkdir -p gpurun_out
-( timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -5 ) | tee gpurun_out/call50_tests.log
-timeout 600 python bench.py > gpurun_out/r01_final6_bench_line.json 2> gpurun_out/call50_bench.err
-tail -c 600 gpurun_out/r01_final6_bench_line.json
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 140 --csv --log-file gpurun_out/r01_final6_launches_bench.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/call50_ncu_bench.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k0_time|k1_hrma|k01_source_hrma|k3_acis|k2_grating|order_|l1_" \
-    -s 20 -c 20 -f -o gpurun_out/prof_r01_final6 python tools/ncu_probe.py 16777216 c2_hetg_acis_s 2 > gpurun_out/call50_ncu_full.log 2>&1
-tail -3 gpurun_out/call50_ncu_full.log
-( timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 ) | tee gpurun_out/call50_smoke.log
+( timeout 600 python -m pytest tests/test_gpu_marx_driver.py -q -m gpu -x -k "user_source or rayfile" 2>&1 | tail -25 ) | tee gpurun_out/call51_tests.log
