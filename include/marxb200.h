@@ -537,6 +537,31 @@ int marxb200_level1_reset (marxb200_ctx *ctx);
 int marxb200_level1_transform (marxb200_ctx *ctx, double total_time);
 int marxb200_level1_download (marxb200_ctx *ctx, const marxb200_level1_columns *cols, uint64_t max_out, uint64_t *n_out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Aspect-solution table: the row loop of marxasp, marx/src/marxasp.c:996-1027 (compute_dither :814-884,
+ * compute_quaternion :886-903).  Row i holds the pointing of the INTERNAL dither model at time i * delta_time: TIME, RA, DEC, ROLL
+ * (degrees), dy = dz = dtheta = 0, and the attitude quaternion.  The descriptor is what marxasp's own initialisation derives from the
+ * simulation directory (marx.par / obs.par; setup_dither :387-410: amplitudes in radians, the nominal pointing and its RA / Dec
+ * unit vectors); marxasp.c keeps its parameter handling and its jdfits header writing and hands the row loop to this call.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct
+{
+   double time_start, delta_time;                                  /* TSTART (s), TimeDel */
+   double ra_amp, dec_amp, roll_amp;                               /* radians */
+   double ra_period, dec_period, roll_period;                      /* s */
+   double ra_phase, dec_phase, roll_phase;                         /* radians */
+   double nominal_roll;                                            /* radians */
+   double pointing[3], ra_hat[3], dec_hat[3];
+}
+marxb200_aspsol_desc;
+#define MARXB200_ASPSOL_ROW_BYTES 76
+/* Rows [first_row, first_row + n) computed on the device.  cols_host (or NULL): 8 arrays of n doubles -- time, ra, dec, roll,
+ * q0..q3.  fits_rows_host (or NULL): n * 76 bytes, the binary-table rows exactly as jdfits_write_float64 / _float32 lay them out
+ * (big endian: time, ra, dec, roll, dy, dz, dtheta, q_att[4]), ready for one fwrite behind the header.  device_ms (or NULL):
+ * duration of the kernel from CUDA events on the context's stream. */
+int marxb200_aspsol_rows (marxb200_ctx *ctx, const marxb200_aspsol_desc *desc, uint64_t first_row, uint64_t n,
+                          double *cols_host, void *fits_rows_host, double *device_ms);
+
 /* FP64 roofline denominator measured on this GPU: best of 5 runs of a DFMA-chain kernel (8 independent chains per
  * thread, 8 x 256-thread CTAs per SM), in TFLOP/s counting an FMA as 2 flops.  Diagnostic; leaves the photon list alone. */
 int marxb200_measure_fp64_peak (marxb200_ctx *ctx, double *tflops);

@@ -23,6 +23,7 @@ EXPORTED_SYMBOLS = [
     "marxb200_upload", "marxb200_upload_from", "marxb200_download_all", "marxb200_download_columns", "marxb200_egress_begin", "marxb200_egress_end", "marxb200_write_photons", "marxb200_egress_begin_packed", "marxb200_egress_end_packed", "marxb200_measure_fp64_peak", "marxb200_get_launch_count",
     "marxb200_tally_create", "marxb200_tally_accumulate", "marxb200_tally_reset", "marxb200_tally_read", "marxb200_tally_device_ptr",
     "marxb200_set_level1", "marxb200_level1_reset", "marxb200_level1_transform", "marxb200_level1_download",
+    "marxb200_aspsol_rows",
 ]
 
 # marxb200_tally_axis.column (include/marxb200.h)
@@ -125,6 +126,7 @@ def load_library():
         "marxb200_upload_from": [vp, vp, u64, vp, dbl],
         "marxb200_download_columns": [vp, vp, u64, C.POINTER(u64)],
         "marxb200_get_launch_count": [vp, C.POINTER(u64)],
+        "marxb200_aspsol_rows": [vp, vp, u64, u64, vp, vp, C.POINTER(dbl)],
         "marxb200_egress_begin": [vp, u64],
         "marxb200_egress_end": [vp, vp, C.POINTER(u64)],
         "marxb200_write_photons": [vp, C.c_char_p, u64, i32, dbl],
@@ -405,6 +407,21 @@ class MarxB200:
         got = C.c_uint64()
         self._check(self._lib.marxb200_level1_download(self._ctx, C.byref(cols), max(int(live), 1), C.byref(got)))
         return {k: v[:got.value] for k, v in arrays.items()}
+
+    ASPSOL_COLUMNS = ("time", "ra", "dec", "roll", "q0", "q1", "q2", "q3")
+
+    def aspsol_rows(self, desc, first_row, n, fits_rows=False):
+        """Rows of the aspect-solution table (marxasp's row loop, marxasp.c:996-1027).  desc: the 21 doubles of
+        marxb200_aspsol_desc.  -> (dict of the 8 f64 columns, the n*76-byte FITS row image or None, kernel milliseconds)"""
+        d = np.ascontiguousarray(desc, dtype=np.float64)
+        assert d.shape == (21,)
+        cols = np.zeros((8, int(n)), dtype=np.float64)
+        img = np.zeros(int(n) * 76, dtype=np.uint8) if fits_rows else None
+        ms = C.c_double()
+        self._check(self._lib.marxb200_aspsol_rows(self._ctx, d.ctypes.data_as(C.c_void_p), int(first_row), int(n),
+                                                   cols.ctypes.data_as(C.c_void_p),
+                                                   img.ctypes.data_as(C.c_void_p) if img is not None else None, C.byref(ms)))
+        return {k: cols[j] for j, k in enumerate(self.ASPSOL_COLUMNS)}, img, ms.value
 
     def download_columns(self, names=("energy", "time", "chipx", "chipy", "pha", "ccd", "order", "ray"), out=None):
         _, live, _ = self.counts()

@@ -13,6 +13,7 @@
 #include "../../include/marxb200_calpack.h"
 #include "mx_tables.h"
 #include "mx_kernels.cuh"
+#include "mx_aspsol.cuh"
 #include "tables_build.hpp"
 
 static_assert (sizeof (marxb200_photon_attr) == 136, "must match sizeof(Marx_Photon_Attr_Type), SURVEY.md 8a1");
@@ -1491,6 +1492,44 @@ extern "C" int marxb200_level1_download (marxb200_ctx *c, const marxb200_level1_
    // detector", detpix.c:174; marx_mnc_to_fpc: "mnc.x is 0", :195)
    if (err & 1u) return fail ("marxb200_level1: an event's chip id does not belong to this detector");
    if (err & 2u) return fail ("marxb200_level1: mnc.x is 0");
+   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// aspect-solution table (marxasp's row loop, marxasp.c:996-1027)
+// ---------------------------------------------------------------------------------------------
+extern "C" int marxb200_aspsol_rows (marxb200_ctx *c, const marxb200_aspsol_desc *d, uint64_t first_row, uint64_t n,
+                                     double *cols_host, void *fits_rows_host, double *device_ms)
+{
+   if ((c == nullptr) || (d == nullptr)) return fail ("marxb200_aspsol_rows: NULL argument");
+   if (!(d->delta_time > 0.0) || (d->ra_period == 0.0) || (d->dec_period == 0.0) || (d->roll_period == 0.0))
+     return fail ("marxb200_aspsol_rows: delta_time must be positive and the dither periods non-zero");
+   // the reference counts rows in an unsigned int (marxasp.c:907,943)
+   if (first_row + n > 0xFFFFFFFFull) return fail ("marxb200_aspsol_rows: row numbers beyond 2^32");
+   if (device_ms) *device_ms = 0.0;
+   if (n == 0) return 0;
+   CUDA_OK (cudaSetDevice (c->device));
+   static_assert (sizeof (AspsolDev) == sizeof (marxb200_aspsol_desc), "descriptor layouts must agree");
+   AspsolDev D;
+   memcpy (&D, d, sizeof (D));
+   double *d_cols = nullptr; uint32_t *d_rows = nullptr;
+   if (cols_host) CUDA_OK (cudaMallocAsync ((void **) &d_cols, (size_t) n * 8 * sizeof (double), c->stream));
+   if (fits_rows_host) CUDA_OK (cudaMallocAsync ((void **) &d_rows, (size_t) n * MARXB200_ASPSOL_ROW_BYTES, c->stream));
+   cudaEvent_t e0 = prof_event (c), e1 = prof_event (c);
+   CUDA_OK (cudaEventRecord (e0, c->stream));
+   launch_aspsol_rows (D, first_row, n, d_cols, d_rows, c->num_sms, c->stream);
+   CUDA_OK (cudaEventRecord (e1, c->stream));
+   c->launches += 1;
+   CUDA_OK (cudaGetLastError ());
+   if (cols_host) CUDA_OK (cudaMemcpyAsync (cols_host, d_cols, (size_t) n * 8 * sizeof (double), cudaMemcpyDeviceToHost, c->stream));
+   if (fits_rows_host) CUDA_OK (cudaMemcpyAsync (fits_rows_host, d_rows, (size_t) n * MARXB200_ASPSOL_ROW_BYTES, cudaMemcpyDeviceToHost, c->stream));
+   if (d_cols) CUDA_OK (cudaFreeAsync (d_cols, c->stream));
+   if (d_rows) CUDA_OK (cudaFreeAsync (d_rows, c->stream));
+   CUDA_OK (cudaStreamSynchronize (c->stream));
+   float ms = 0.f;
+   CUDA_OK (cudaEventElapsedTime (&ms, e0, e1));
+   if (device_ms) *device_ms = ms;
+   c->ev_pool.push_back (e0); c->ev_pool.push_back (e1);
    return 0;
 }
 
