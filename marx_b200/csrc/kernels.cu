@@ -482,6 +482,40 @@ __global__ void __launch_bounds__ (kStageThreads, MX_K1_MINBLOCKS) k1_hrma (cons
 }
 
 // K2 ------------------------------------------------------------------------------------------
+// The compacting path runs the grating stage as two kernels (mx_grating.cuh: grating_select, grating_diffract_selected).
+// k2_select needs neither x nor p: it reads a row's slot key and shell, draws the vignetting and order-selection deviates and
+// appends (row index | order index << 32) of the ~half of the rays that leave the primary grating in an order to the `ray` column
+// of the OUTPUT buffer (dead until the order restoration, and not written by k2_grating).  k2_grating<1> then walks that list:
+// the facet rotation, the Rowland-torus intersection, the diffraction and the support gratings run on full warps.  Warps are
+// uniform here (one table search + five interpolations per ray), so a grid-stride loop with warp-aggregated appends suffices.
+__global__ void __launch_bounds__ (256) k2_select (const __grid_constant__ StageArgs a)
+{
+   const K2Blob *B = reinterpret_cast<const K2Blob *> (a.blob);          // header fields through L1; the tables live in L2
+   const unsigned long long n_in = *a.n_in;
+   const uint32_t lane = threadIdx.x & 31;
+   const unsigned long long n_warps = ((unsigned long long) gridDim.x * blockDim.x) >> 5;
+   for (unsigned long long tile = ((unsigned long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile * 32 < n_in; tile += n_warps)
+     {
+        const unsigned long long i = tile * 32 + lane;
+        int lo = -1;
+        if (i < n_in)
+          {
+             const uint32_t slot = a.in.slot[i], shell = a.in.shell[i];
+             Rng rng;
+             rng.init (a.seed, a.rc.ray[slot], MARXB200_STAGE_GRATING);
+             lo = grating_select (B->G.shell[shell], a.rc.energy[slot], rng);
+          }
+        const uint32_t ballot = __ballot_sync (0xffffffffu, lo >= 0);
+        unsigned long long base = 0;
+        if ((lane == 0) && ballot) base = atomicAdd (a.n_out, (unsigned long long) __popc (ballot));
+        base = __shfl_sync (0xffffffffu, base, 0);
+        if (lo >= 0)
+          a.out.ray[base + __popc (ballot & ((1u << lane) - 1u))] = (unsigned long long) i | ((unsigned long long) (uint32_t) lo << 32);
+     }
+}
+
+// PHASE 0: the whole stage for the rows of `in`; PHASE 1: the second half for the rows k2_select listed in out.ray
+template <int PHASE>
 __global__ void __launch_bounds__ (kStageThreads, MX_K2_MINBLOCKS) k2_grating (const __grid_constant__ StageArgs a)
 {
    constexpr int ND = 6, NU = 3;
@@ -499,13 +533,26 @@ __global__ void __launch_bounds__ (kStageThreads, MX_K2_MINBLOCKS) k2_grating (c
 
    auto trace = [&] (unsigned long long i, double *d, uint32_t *u) -> uint32_t
      {
-        Vec3 x = v_make (in.x0[i], in.x1[i], in.x2[i]), p = v_make (in.p0[i], in.p1[i], in.p2[i]);
+        unsigned long long src = i;
+        int lo = 0;
+        if (PHASE == 1)
+          {
+             const unsigned long long packed = out.ray[i];
+             src = packed & 0xFFFFFFFFull; lo = (int) (packed >> 32);
+          }
+        Vec3 x = v_make (in.x0[src], in.x1[src], in.x2[src]), p = v_make (in.p0[src], in.p1[src], in.p2[src]);
         int order = 0;
         uint32_t sorders = 0;
         Rng rng;
-        const uint32_t slot = in.slot[i], shell = in.shell[i];
+        const uint32_t slot = in.slot[src], shell = in.shell[src];
         rng.init (a.seed, a.rc.ray[slot], MARXB200_STAGE_GRATING);
-        uint32_t flags = grating_diffract (G, shell, a.rc.energy[slot], x, p, order, sorders, rng);
+        uint32_t flags;
+        if (PHASE == 1)
+          {
+             rng.resume (2, 0, 0.0);            // behind the vignetting and order-selection draws
+             flags = grating_diffract_selected (G, shell, a.rc.energy[slot], x, p, lo, order, sorders, rng);
+          }
+        else flags = grating_diffract (G, shell, a.rc.energy[slot], x, p, order, sorders, rng);
         d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = p.x; d[4] = p.y; d[5] = p.z;
         u[0] = slot;
         u[1] = (uint32_t) (order & 0xFF) | (shell << 8);
@@ -1187,7 +1234,8 @@ int stage_grid_size (int stage, int num_sms, uint32_t blob_bytes, uint32_t seg2_
       case 14: return occupancy_grid (k1_hrma<3>, num_sms, smem);
       case 15: return occupancy_grid (k1_hrma<4>, num_sms, smem);
       case 16: return occupancy_grid (k1_hrma<5>, num_sms, smem);
-      case 2: return occupancy_grid (k2_grating, num_sms, smem);
+      case 2: cudaFuncSetAttribute (k2_grating<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+              return occupancy_grid (k2_grating<0>, num_sms, smem);
       // the detector-dither variants run on the same grid (ticket-driven persistent kernels: any grid size is correct)
       case 3: cudaFuncSetAttribute (k3_acis<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
               cudaFuncSetAttribute (k3_acis<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
@@ -1228,7 +1276,12 @@ void launch_hrma (const StageArgs &a, int phase, int grid, cudaStream_t s)
       default: k1_hrma<5><<<grid, kStageThreads, smem, s>>> (a); break;
      }
 }
-void launch_grating (const StageArgs &a, int grid, cudaStream_t s) { k2_grating<<<grid, kStageThreads, stage_smem_bytes (2, a.blob_bytes), s>>> (a); }
+void launch_grating (const StageArgs &a, int grid, cudaStream_t s, int phase)
+{
+   if (phase == 1) k2_select<<<grid, 256, 0, s>>> (a);                   // grid: any size (grid-stride)
+   else if (phase == 2) k2_grating<1><<<grid, kStageThreads, stage_smem_bytes (2, a.blob_bytes), s>>> (a);
+   else k2_grating<0><<<grid, kStageThreads, stage_smem_bytes (2, a.blob_bytes), s>>> (a);
+}
 void launch_acis (const StageArgs &a, int grid, cudaStream_t s, int phase)
 {
    const uint32_t smem = stage_smem_bytes (3, a.blob_bytes);

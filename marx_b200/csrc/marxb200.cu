@@ -81,6 +81,7 @@ struct marxb200_ctx
    bool detector_is_hrc = false;
    int first_mirror_kernel = 0;                  // 1: phase A already ran fused with the source (marxb200_trace)
    int k3_split = 1;                             // ACIS detector stage as two kernels (MARXB200_K3_SPLIT=0: one kernel)
+   int k2_split = 1;                             // compacting grating stage as k2_select + k2_grating<1> (MARXB200_K2_SPLIT=0: one kernel)
    int k1_split = 1;                             // compacting mirror stage cut behind the reflectivity tests: A | B1 | B2+C1 | C2
                                                  // (MARXB200_K1_SPLIT=0: A | B | C, which the in-place parity mode always runs)
 
@@ -218,15 +219,16 @@ extern "C" int marxb200_create (marxb200_ctx **ctxp, int device_ordinal, uint64_
    c->seed = seed;
    if (const char *e = getenv ("MARXB200_K3_SPLIT")) c->k3_split = atoi (e);      // developer A/B switch
    if (const char *e = getenv ("MARXB200_K1_SPLIT")) c->k1_split = atoi (e);      // developer A/B switch
+   if (const char *e = getenv ("MARXB200_K2_SPLIT")) c->k2_split = atoi (e);      // developer A/B switch
    cudaDeviceProp prop;
    CUDA_OK (cudaGetDeviceProperties (&prop, device_ordinal));
    c->num_sms = prop.multiProcessorCount;
    CUDA_OK (cudaStreamCreateWithFlags (&c->stream, cudaStreamNonBlocking));
    c->own_stream = true;
-   CUDA_OK (cudaMalloc (&c->d_counts, 8 * sizeof (unsigned long long)));
+   CUDA_OK (cudaMalloc (&c->d_counts, 12 * sizeof (unsigned long long)));
    CUDA_OK (cudaMalloc (&c->d_ticket, 4 * sizeof (unsigned long long)));
    CUDA_OK (cudaMalloc (&c->d_times, 2 * sizeof (double)));
-   CUDA_OK (cudaMemset (c->d_counts, 0, 8 * sizeof (unsigned long long)));
+   CUDA_OK (cudaMemset (c->d_counts, 0, 12 * sizeof (unsigned long long)));
    CUDA_OK (cudaMemset (c->d_times, 0, 2 * sizeof (double)));
    memset (&c->S, 0, sizeof (c->S));
    memset (&c->D, 0, sizeof (c->D));
@@ -650,7 +652,9 @@ static int run_stage (marxb200_ctx *c, int stage)
    const bool k1_four = (stage == 1) && c->compact && (c->k1_split != 0);
    static const int phases3[3] = {0, 1, 2}, phases4[4] = {0, 3, 4, 5};
    const int *phases = k1_four ? phases4 : phases3;
-   const int n_kernels = (stage == 1) ? (k1_four ? 4 : 3) : (k3_two ? 2 : 1);
+   // the grating stage as k2_select | k2_grating<1> (compacting) or as one kernel
+   const bool k2_two = (stage == 2) && c->compact && (c->k2_split != 0);
+   const int n_kernels = (stage == 1) ? (k1_four ? 4 : 3) : ((k3_two || k2_two) ? 2 : 1);
    const int k_first = (stage == 1) ? c->first_mirror_kernel : 0;
    CUDA_OK (cudaMemsetAsync (c->d_ticket, 0, 4 * sizeof (unsigned long long), c->stream));
    if (c->compact)
@@ -661,6 +665,7 @@ static int run_stage (marxb200_ctx *c, int stage)
         if (stage == 1) CUDA_OK (cudaMemsetAsync (c->d_counts + 4 + k_first, 0, (2 - k_first) * sizeof (unsigned long long), c->stream));
         if (k1_four) CUDA_OK (cudaMemsetAsync (c->d_counts + 7, 0, sizeof (unsigned long long), c->stream));
         if (k3_two) CUDA_OK (cudaMemsetAsync (c->d_counts + 6, 0, sizeof (unsigned long long), c->stream));
+        if (k2_two) CUDA_OK (cudaMemsetAsync (c->d_counts + 8, 0, sizeof (unsigned long long), c->stream));
      }
    const unsigned long long *n_in = (k_first == 1) ? c->d_counts + 4 : c->d_counts + c->stage_done;
    c->first_mirror_kernel = 0;
@@ -669,7 +674,8 @@ static int run_stage (marxb200_ctx *c, int stage)
         a.in = c->buf[c->cur];
         a.out = c->compact ? c->buf[1 - c->cur] : c->buf[c->cur];
         a.n_in = n_in;
-        a.n_out = (k == n_kernels - 1) ? c->d_counts + stage : ((stage == 1) ? c->d_counts + ((k == 2) ? 7 : 4 + k) : c->d_counts + 6);
+        a.n_out = (k == n_kernels - 1) ? c->d_counts + stage
+                  : ((stage == 1) ? c->d_counts + ((k == 2) ? 7 : 4 + k) : ((stage == 2) ? c->d_counts + 8 : c->d_counts + 6));
         a.ticket = c->d_ticket + k;
         // big inputs amortise the ticket atomic over several tiles; small ones need fine-grained balancing
         a.chunk_tiles = (stage == 1 && k == 0) ? 4 : ((stage == 1 && k < n_kernels - 1) ? 2 : 1);
@@ -686,7 +692,12 @@ static int run_stage (marxb200_ctx *c, int stage)
                 prof_mark (c, (ph < 3) ? 4 + ph : 8 + ph);          // classes 4, 5, 6 = A, B, C; 11, 12, 13 = B1, B2+C1, C2
                 break;
              }
-           case 2: a.blob = c->blob2; a.blob_bytes = c->blob2_bytes; launch_grating (a, c->grid2, c->stream); prof_mark (c, 7); break;
+           case 2: a.blob = c->blob2; a.blob_bytes = c->blob2_bytes;
+                   // k2_select lists (row, order) of the rays that leave the primary grating in out.ray; k2_grating<1> reads the
+                   // rows of the SAME input list through it (no buffer swap in between)
+                   launch_grating (a, (k2_two && k == 0) ? c->num_sms * 8 : c->grid2, c->stream, k2_two ? k + 1 : 0);
+                   prof_mark (c, 7);
+                   break;
            case 3: a.blob = c->blob3; a.blob_bytes = c->blob3_bytes;
                    if (c->detector_is_hrc) launch_hrc (a, c->grid3, c->stream); else launch_acis (a, c->grid3, c->stream, k3_two ? k + 1 : 0);
                    prof_mark (c, 8);
@@ -694,7 +705,7 @@ static int run_stage (marxb200_ctx *c, int stage)
           }
         c->launches += 1;
         CUDA_OK (cudaGetLastError ());
-        if (c->compact) c->cur = 1 - c->cur;
+        if (c->compact && !(k2_two && k == 0)) c->cur = 1 - c->cur;
         n_in = a.n_out;
      }
    if (c->compact) c->ordered = false;

@@ -135,14 +135,12 @@ MX_HD uint32_t nfvector_bracket (double x, const float *xp, uint32_t n)
    return lo;
 }
 
-// order selection + diffraction from one grating (diffract_photon_from_grating, diffract.c:828-849, with
-// the per-photon row of cumulative efficiencies produced as in finterpo.c:166-186: double arithmetic,
-// stored to float).  cum_eff_t is TRANSPOSED on upload to [energy][order] so that the order scan reads
-// two contiguous rows.
-MX_HD int diffract_from_grating (const GratingShellDev &g, double theta, double energy, const Vec3 &x, Vec3 &p,
-                                 int &order_out, bool use_sectors, Rng &rng)
+// order selection of one grating (diffract_photon_from_grating, diffract.c:828-849, with the per-photon row of cumulative
+// efficiencies produced as in finterpo.c:166-186: double arithmetic, stored to float) for the uniform deviate r.
+// cum_eff_t is TRANSPOSED on upload to [energy][order] so that the order scan reads two contiguous rows.
+// Returns the index into order_list, or -1 when the photon leaves in none of the tabulated orders (absorbed).
+MX_HD int select_order (const GratingShellDev &g, double energy, double r)
 {
-   double r = rng.uniform ();
    double xe = (double) (float) energy;           // tmp_energies[] is float (diffract.c:1047)
    uint32_t c = nfvector_bracket (xe, g.energies, g.num_energies);
    double x_0 = g.energies[c - 1], x_1 = g.energies[c];
@@ -166,7 +164,15 @@ MX_HD int diffract_from_grating (const GratingShellDev &g, double theta, double 
           }
         if (r <= ce) hi = k; else lo = k + 1;
      }
-   if (lo == g.num_orders) return -1;
+   return (lo == g.num_orders) ? -1 : (int) lo;
+}
+
+// order selection + diffraction from one grating
+MX_HD int diffract_from_grating (const GratingShellDev &g, double theta, double energy, const Vec3 &x, Vec3 &p,
+                                 int &order_out, bool use_sectors, Rng &rng)
+{
+   const int lo = select_order (g, energy, rng.uniform ());
+   if (lo < 0) return -1;
    int order = g.order_list[lo];
    order_out = order;
    return diffract_photon (g, theta, energy, x, p, order, use_sectors, rng);
@@ -175,20 +181,18 @@ MX_HD int diffract_from_grating (const GratingShellDev &g, double theta, double 
 // diffract() for one ray of shell `shell`.  HETG: the primary grating; LETG: the primary grating followed by the
 // fine support grating (facet rotated by pi/2) and three passes through the coarse support grating (pi/3,
 // 2pi/3, 0), diffract.c:1098-1118.  support_orders packs the four support orders (one signed byte each).
+// The stage for one ray is  vignetting test (draw 1) ; facet frame + Rowland torus ; order selection of the primary grating
+// (draw 2) ; diffraction, support gratings, back rotation.  The two tests absorb half of the rays and need neither x nor p, so
+// the compacting path runs them first, as a kernel of their own (grating_select), and the geometry on re-packed warps
+// (grating_diffract_selected); a survivor sees the same draws either way (the torus takes none).
 // Returns flags (0 alive).
-MX_HD uint32_t grating_diffract (const GratingDev &G, uint32_t shell, double energy, Vec3 &x, Vec3 &p,
-                                 int &order_out, uint32_t &support_orders, Rng &rng)
+MX_HD uint32_t grating_finish (const GratingDev &G, const GratingShellDev &g, double energy, Vec3 &x, Vec3 &p, int lo,
+                               int &order_out, uint32_t &support_orders, Rng &rng)
 {
-   const uint32_t VBLOCKED = 0x10, UNDIFFRACTED = 0x04;
-   const GratingShellDev &g = G.shell[shell];
-   // vignetting (flagged MIRROR_VBLOCKED by the reference, diffract.c:999-1000)
-   if (rng.uniform () > g.vig) return VBLOCKED;
-   // rotate_photons(pt, -1), diffract.c:854-875: the angle is a per-shell constant, its cosine and sine are tabulated
-   // by the host (tables_build.hpp, the reference's own libm); cos(-t) = cos(t), sin(-t) = -sin(t) exactly
-   x = rotate_x (x, g.cos_dispersion, -g.sin_dispersion);
-   p = rotate_x (p, g.cos_dispersion, -g.sin_dispersion);
-   if (-1 == torus_intersect (x, p, g.rowland)) return UNDIFFRACTED;
-   if (-1 == diffract_from_grating (g, 0.0, energy, x, p, order_out, g.num_sectors != 0, rng)) return UNDIFFRACTED;
+   const uint32_t UNDIFFRACTED = 0x04;
+   const int order = g.order_list[lo];
+   order_out = order;
+   if (-1 == diffract_photon (g, 0.0, energy, x, p, order, g.num_sectors != 0, rng)) return UNDIFFRACTED;
    support_orders = 0;
    if (G.type == 2)
      {
@@ -206,6 +210,39 @@ MX_HD uint32_t grating_diffract (const GratingDev &G, uint32_t shell, double ene
    x = rotate_x (x, g.cos_dispersion, g.sin_dispersion);
    p = rotate_x (p, g.cos_dispersion, g.sin_dispersion);
    return 0;
+}
+MX_HD uint32_t grating_diffract (const GratingDev &G, uint32_t shell, double energy, Vec3 &x, Vec3 &p,
+                                 int &order_out, uint32_t &support_orders, Rng &rng)
+{
+   const uint32_t VBLOCKED = 0x10, UNDIFFRACTED = 0x04;
+   const GratingShellDev &g = G.shell[shell];
+   // vignetting (flagged MIRROR_VBLOCKED by the reference, diffract.c:999-1000)
+   if (rng.uniform () > g.vig) return VBLOCKED;
+   // rotate_photons(pt, -1), diffract.c:854-875: the angle is a per-shell constant, its cosine and sine are tabulated
+   // by the host (tables_build.hpp, the reference's own libm); cos(-t) = cos(t), sin(-t) = -sin(t) exactly
+   x = rotate_x (x, g.cos_dispersion, -g.sin_dispersion);
+   p = rotate_x (p, g.cos_dispersion, -g.sin_dispersion);
+   if (-1 == torus_intersect (x, p, g.rowland)) return UNDIFFRACTED;
+   const int lo = select_order (g, energy, rng.uniform ());
+   if (lo < 0) return UNDIFFRACTED;
+   return grating_finish (G, g, energy, x, p, lo, order_out, support_orders, rng);
+}
+// first half on the compacting path: draws 1 and 2 of the GRATING sub-stream.  -> index into order_list, or -1 (vignetted / absorbed)
+MX_HD int grating_select (const GratingShellDev &g, double energy, Rng &rng)
+{
+   if (rng.uniform () > g.vig) return -1;
+   return select_order (g, energy, rng.uniform ());
+}
+// second half: rng resumed behind draw 2
+MX_HD uint32_t grating_diffract_selected (const GratingDev &G, uint32_t shell, double energy, Vec3 &x, Vec3 &p, int lo,
+                                          int &order_out, uint32_t &support_orders, Rng &rng)
+{
+   const uint32_t UNDIFFRACTED = 0x04;
+   const GratingShellDev &g = G.shell[shell];
+   x = rotate_x (x, g.cos_dispersion, -g.sin_dispersion);
+   p = rotate_x (p, g.cos_dispersion, -g.sin_dispersion);
+   if (-1 == torus_intersect (x, p, g.rowland)) return UNDIFFRACTED;
+   return grating_finish (G, g, energy, x, p, lo, order_out, support_orders, rng);
 }
 
 }  // namespace mx

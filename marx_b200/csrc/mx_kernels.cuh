@@ -120,7 +120,7 @@ void launch_exposure_truncate (const PhotonSoA &buf, unsigned long long *n, doub
 void launch_hrma (const StageArgs &a, int phase, int grid, cudaStream_t s);
 int fused_source_grid (int num_sms);
 void launch_source_hrma (const SourceArgs &a, const StageArgs &st, int grid, cudaStream_t s);   // k0_source + k1_hrma<0> in one kernel   // phase 0,1,2 = k1a,k1b,k1c
-void launch_grating (const StageArgs &a, int grid, cudaStream_t s);
+void launch_grating (const StageArgs &a, int grid, cudaStream_t s, int phase = 0);   // phase 0: one kernel; 1: k2_select, 2: k2_grating<1>
 void launch_acis (const StageArgs &a, int grid, cudaStream_t s, int phase = 0);   // phase 0: one kernel; 1, 2: the two halves
 void launch_hrc (const StageArgs &a, int grid, cudaStream_t s);
 int stage_grid_size (int stage, int num_sms, uint32_t blob_bytes, uint32_t seg2_bytes = 0);
