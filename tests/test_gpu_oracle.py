@@ -89,7 +89,8 @@ def test_stage_injection_parity(config, seed, n):
 
 
 def check_compacted_equals_in_place(config, seed, first, n):
-    """The product path (compacting kernels: mirror stage cut as A | B1 | B2+C1 | C2, ACIS stage as two kernels; stage by stage and
+    """The product path (compacting kernels: mirror stage cut as A | B1 | B2+C1 | C2, grating stage as order selection | geometry,
+    ACIS stage as two kernels; stage by stage and
     through the fused marxb200_trace) must leave exactly the survivors of the in-place parity path (A | B | C, one ray per slot),
     bit for bit, in arrival order.  Together with the slot-by-slot oracle comparison of the in-place path this pins the product path."""
     import marx_b200
