@@ -947,6 +947,27 @@ static int apply_fef (oracle_t *o, const chip_t *ch, float x, float y, double en
    if (*pip < 0) return -1;
    return 0;
 }
+/* marx_map_energy_to_acis_pha, acis_fef.c:1087-1096 (find_fef :910-966 + JDMinterpolate_f): the deterministic energy -> PHA map
+ * marxpileup uses for its summed island energies (oracle/pileup_oracle.c).  x, y arrive as ints (the prototype truncates). */
+int oracle_map_energy_to_acis_pha (oracle_t *o, int ccd_id, int xi, int yi, double energy, short *phap)
+{
+   float x = (float) xi, y = (float) yi; unsigned int i, j; int k, fi; const chip_t *ch = NULL; const fef_t *f;
+   if ((x < 0) || (x >= 1024) || (y < 0) || (y >= 1024))
+     {
+        if (0 == (int) o->acis[15]) return -1;
+        if (x < 0) x = 0; else if (x >= 1024) x = 1023;
+        if (y < 0) y = 0; else if (y >= 1024) y = 1023;
+     }
+   i = (unsigned int) (x / 32); j = (unsigned int) (y / 32);
+   if ((i >= 32) || (j >= 32)) return -1;
+   for (k = 0; k < o->nchips; k++) if ((int) o->chip[k].geom[0] == ccd_id) ch = &o->chip[k];
+   if (ch == NULL) return -1;
+   fi = ch->fef_map[i * 32 + j];
+   if (fi < 0) return -1;
+   f = &o->fefs[fi];
+   *phap = (short) interp_f ((float) energy, f->energies, f->channels, f->ne);
+   return 0;
+}
 /* _marx_dither_detector / _marx_undither_detector, detector.c:240-295: the ONE global transform is modified and restored
  * for every photon that reaches the detector, so it drifts by rounding exactly as the reference's does */
 static void xf_rotate (double *m, double theta)

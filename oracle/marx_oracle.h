@@ -42,6 +42,8 @@ typedef struct oracle oracle_t;
 /* load the calibration pack (the post-init tables of the reference modules) */
 oracle_t *oracle_open (const char *calpack_path, uint64_t seed);
 void oracle_close (oracle_t *o);
+/* marx_map_energy_to_acis_pha, acis_fef.c:1087-1096 */
+int oracle_map_energy_to_acis_pha (oracle_t *o, int ccd_id, int x, int y, double energy, short *phap);
 const char *oracle_last_error (void);
 
 /* Trace rays [first_ray, first_ray + n).  st[s] (s = 0..3, each n records or NULL) receives the photon
