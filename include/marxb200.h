@@ -562,6 +562,39 @@ marxb200_aspsol_desc;
 int marxb200_aspsol_rows (marxb200_ctx *ctx, const marxb200_aspsol_desc *desc, uint64_t first_row, uint64_t n,
                           double *cols_host, void *fits_rows_host, double *device_ms);
 
+/* ------------------------------------------------------------------------------------------------
+ * ACIS pile-up: the frame loop of marxpileup, marx/src/marxpileup.c:main :1121-1213 (process_frame :890-922:
+ * store_event :754-812, collect_charge :814-845, event_detect :676-752, will_grade_migrate :668-674, write_event :622-666).
+ * The input columns are the event files of a simulation directory as read_input_event :573-620 reads them (detector.dat,
+ * xpixel.dat, ypixel.dat, time.dat, b_energy.dat and the six dither files sky_ra ... det_theta, in that order in dither[]; a NULL
+ * dither pointer drops that column), n rows in file order.  The output columns are those write_event writes; within an exposure
+ * frame the rows come out in the reference's order (reverse file order).  alpha = the Alpha parameter; frame_time = FrameTime +
+ * FrameTransferTime (initialize :1083-1084).  The PHA of an island's summed energy comes from the FEF tables of the ACIS detector
+ * the context was set up with (marx_map_energy_to_acis_pha, acis_fef.c:1087-1096): marxb200_set_acis / a calibration pack first.
+ *
+ * Random draws: the reference draws from its one global generator once per island of >= 2 photons that passed the local-maximum
+ * tests, in list order.  Here draw k (0, 1, ...) of exposure frame F is lane k&3 of Philox4x32-10 (key = seed, counter =
+ * (F, 0, k >> 2, 5)) mapped to [0,1] as jdmath/src/random.c:151-154, so frames are independent.
+ *
+ * All pointers are HOST pointers; any output pointer may be NULL.  At most max_out rows are written (more rows than that: error).
+ * A frame longer than 65536 events is refused (every event walks its own frame's run of the list).  device_ms (or NULL): duration
+ * of the eight kernels from CUDA events on the context's stream.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct
+{
+   const int8_t *ccd; const float *x, *y, *t, *benergy;
+   const float *dither[6];
+}
+marxb200_pileup_in;
+typedef struct
+{
+   int8_t *ccd; float *x, *y, *t, *benergy; int32_t *frame; int16_t *nphotons, *pha;
+   float *dither[6];
+}
+marxb200_pileup_out;
+int marxb200_pileup_run (marxb200_ctx *ctx, uint64_t n, const marxb200_pileup_in *in, double alpha, double frame_time, uint64_t seed,
+                         uint64_t max_out, const marxb200_pileup_out *out, uint64_t *n_out, double *device_ms);
+
 /* FP64 roofline denominator measured on this GPU: best of 5 runs of a DFMA-chain kernel (8 independent chains per
  * thread, 8 x 256-thread CTAs per SM), in TFLOP/s counting an FMA as 2 flops.  Diagnostic; leaves the photon list alone. */
 int marxb200_measure_fp64_peak (marxb200_ctx *ctx, double *tflops);

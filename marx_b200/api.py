@@ -24,6 +24,7 @@ EXPORTED_SYMBOLS = [
     "marxb200_tally_create", "marxb200_tally_accumulate", "marxb200_tally_reset", "marxb200_tally_read", "marxb200_tally_device_ptr",
     "marxb200_set_level1", "marxb200_level1_reset", "marxb200_level1_transform", "marxb200_level1_download",
     "marxb200_aspsol_rows",
+    "marxb200_pileup_run",
 ]
 
 # marxb200_tally_axis.column (include/marxb200.h)
@@ -127,6 +128,7 @@ def load_library():
         "marxb200_download_columns": [vp, vp, u64, C.POINTER(u64)],
         "marxb200_get_launch_count": [vp, C.POINTER(u64)],
         "marxb200_aspsol_rows": [vp, vp, u64, u64, vp, vp, C.POINTER(dbl)],
+        "marxb200_pileup_run": [vp, u64, vp, dbl, dbl, u64, u64, vp, C.POINTER(u64), C.POINTER(dbl)],
         "marxb200_egress_begin": [vp, u64],
         "marxb200_egress_end": [vp, vp, C.POINTER(u64)],
         "marxb200_write_photons": [vp, C.c_char_p, u64, i32, dbl],
@@ -422,6 +424,32 @@ class MarxB200:
                                                    cols.ctypes.data_as(C.c_void_p),
                                                    img.ctypes.data_as(C.c_void_p) if img is not None else None, C.byref(ms)))
         return {k: cols[j] for j, k in enumerate(self.ASPSOL_COLUMNS)}, img, ms.value
+
+    PILEUP_DITHER = ("sky_ra", "sky_dec", "sky_roll", "det_dy", "det_dz", "det_theta")
+
+    def pileup(self, cols, alpha, frame_time, seed, max_out=None):
+        """ACIS pile-up on the event columns of a simulation (marxpileup's frame loop, marxpileup.c:1121-1213).  cols: dict with
+        ccd (i8), x, y, t, benergy (f32) and optionally the six dither columns, in file order; frame_time = FrameTime +
+        FrameTransferTime.  -> (dict of the output columns write_event :622-666 writes, milliseconds of the device kernels)"""
+        n = len(cols["t"])
+        keep = {"ccd": np.ascontiguousarray(cols["ccd"], dtype=np.int8)}
+        for k in ("x", "y", "t", "benergy") + tuple(d for d in self.PILEUP_DITHER if d in cols):
+            keep[k] = np.ascontiguousarray(cols[k], dtype=np.float32)
+            assert len(keep[k]) == n
+        ptr = lambda a: a.ctypes.data if a is not None else None  # noqa: E731
+        pin = (C.c_void_p * 11)(*[ptr(keep.get(k)) for k in ("ccd", "x", "y", "t", "benergy") + self.PILEUP_DITHER])
+        cap = n if max_out is None else int(max_out)
+        out = {"ccd": np.zeros(cap, np.int8), "x": np.zeros(cap, np.float32), "y": np.zeros(cap, np.float32), "t": np.zeros(cap, np.float32),
+               "benergy": np.zeros(cap, np.float32), "frame": np.zeros(cap, np.int32), "nphotons": np.zeros(cap, np.int16),
+               "pha": np.zeros(cap, np.int16)}
+        for d in self.PILEUP_DITHER:
+            if d in keep:
+                out[d] = np.zeros(cap, np.float32)
+        pout = (C.c_void_p * 14)(*[ptr(out.get(k)) for k in ("ccd", "x", "y", "t", "benergy", "frame", "nphotons", "pha") + self.PILEUP_DITHER])
+        got, ms = C.c_uint64(), C.c_double()
+        self._check(self._lib.marxb200_pileup_run(self._ctx, n, pin, float(alpha), float(frame_time), int(seed), cap, pout,
+                                                  C.byref(got), C.byref(ms)))
+        return {k: v[:got.value] for k, v in out.items()}, ms.value
 
     def download_columns(self, names=("energy", "time", "chipx", "chipy", "pha", "ccd", "order", "ray"), out=None):
         _, live, _ = self.counts()

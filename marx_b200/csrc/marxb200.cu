@@ -14,6 +14,7 @@
 #include "mx_tables.h"
 #include "mx_kernels.cuh"
 #include "mx_aspsol.cuh"
+#include "mx_pileup.cuh"
 #include "tables_build.hpp"
 
 static_assert (sizeof (marxb200_photon_attr) == 136, "must match sizeof(Marx_Photon_Attr_Type), SURVEY.md 8a1");
@@ -1542,6 +1543,123 @@ extern "C" int marxb200_aspsol_rows (marxb200_ctx *c, const marxb200_aspsol_desc
    if (device_ms) *device_ms = ms;
    c->ev_pool.push_back (e0); c->ev_pool.push_back (e1);
    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ACIS pile-up (marxpileup's frame loop, marxpileup.c:1121-1213; kernels in pileup_kernels.cu)
+// ---------------------------------------------------------------------------------------------
+extern "C" int marxb200_pileup_run (marxb200_ctx *c, uint64_t n, const marxb200_pileup_in *in, double alpha, double frame_time, uint64_t seed,
+                                    uint64_t max_out, const marxb200_pileup_out *out, uint64_t *n_out, double *device_ms)
+{
+   if ((c == nullptr) || (in == nullptr) || (out == nullptr) || (n_out == nullptr)) return fail ("marxb200_pileup_run: NULL argument");
+   *n_out = 0;
+   if (device_ms) *device_ms = 0.0;
+   if (!c->have_acis || c->detector_is_hrc || (c->detector_type == 0) || (c->blob3 == nullptr))
+     return fail ("marxb200_pileup_run: the context has no ACIS detector (the PHA of an island comes from its FEF tables)");
+   if (!(frame_time > 0.0)) return fail ("marxb200_pileup_run: frame_time must be positive");
+   if (n >= 0xFFFFFFFFull) return fail ("marxb200_pileup_run: %llu events in one call", (unsigned long long) n);
+   if (n == 0) return 0;
+   if ((in->ccd == nullptr) || (in->x == nullptr) || (in->y == nullptr) || (in->t == nullptr) || (in->benergy == nullptr))
+     return fail ("marxb200_pileup_run: the detector, pixel, time and energy columns are required");
+   CUDA_OK (cudaSetDevice (c->device));
+   const uint64_t cap_out = (max_out < n) ? max_out : n;
+   const uint64_t n_tiles = n / 256 + 2;
+   // one slab: inputs (41 B/event), scratch (59 B/event), outputs (49 B/row), every column rounded up to 256 bytes
+   auto rounded = [] (uint64_t rows, size_t elem) { return ((size_t) rows * elem + 255) & ~(size_t) 255; };
+   size_t bytes = rounded (n, 1) + 10 * rounded (n, 4)                                         // inputs
+     + 8 * rounded (n, 4) + 6 * rounded (n, 4) + rounded (n, 1) + rounded (n, 2) + rounded (n_tiles, 4)   // scratch
+     + rounded (cap_out + 1, 1) + 11 * rounded (cap_out + 1, 4) + 2 * rounded (cap_out + 1, 2)  // outputs
+     + 256;                                                                                    // n_out, error
+   char *slab = nullptr;
+   CUDA_OK (cudaMallocAsync ((void **) &slab, bytes, c->stream));
+   char *p = slab;
+   auto take = [&] (uint64_t rows, size_t elem) { char *q = p; p += rounded (rows, elem); return (void *) q; };
+   mx::PileupArgs a;
+   memset (&a, 0, sizeof (a));
+   int8_t *d_ccd = (int8_t *) take (n, 1);
+   float *d_in[10];
+   for (int k = 0; k < 10; k++) d_in[k] = (float *) take (n, 4);
+   const float *h_in[10] = {in->x, in->y, in->t, in->benergy, in->dither[0], in->dither[1], in->dither[2], in->dither[3], in->dither[4], in->dither[5]};
+   a.ccd = d_ccd; a.x = d_in[0]; a.y = d_in[1]; a.t = d_in[2]; a.benergy = d_in[3];
+   for (int k = 0; k < 6; k++) a.dither[k] = (h_in[4 + k] != nullptr) ? d_in[4 + k] : nullptr;
+   a.n = n; a.alpha = alpha; a.frame_time = frame_time; a.seed = seed;
+   for (int k = 0; k < mx::kPuProbTable; k++) a.prob[k] = pow (alpha, (double) k);
+   a.max_frame_events = 1u << 16;
+   a.A = &((const mx::K3Blob *) c->blob3)->A;
+   a.frame = (uint32_t *) take (n, 4); a.key = (uint32_t *) take (n, 4); a.lo = (uint32_t *) take (n, 4); a.hi = (uint32_t *) take (n, 4);
+   a.pn = (uint32_t *) take (n, 4); a.in = (uint32_t *) take (n, 4); a.emit = (uint32_t *) take (n, 4); a.cum = (uint32_t *) take (n, 4);
+   a.pb = (float *) take (n, 4); a.px = (float *) take (n, 4); a.py = (float *) take (n, 4); a.ib = (float *) take (n, 4);
+   a.sx = (float *) take (n, 4); a.sy = (float *) take (n, 4);
+   a.flag = (uint8_t *) take (n, 1); a.spha = (int16_t *) take (n, 2); a.tile_sum = (uint32_t *) take (n_tiles, 4);
+   a.o_ccd = (int8_t *) take (cap_out + 1, 1);
+   a.o_x = (float *) take (cap_out + 1, 4); a.o_y = (float *) take (cap_out + 1, 4); a.o_t = (float *) take (cap_out + 1, 4);
+   a.o_benergy = (float *) take (cap_out + 1, 4); a.o_frame = (int32_t *) take (cap_out + 1, 4);
+   for (int k = 0; k < 6; k++) { float *q = (float *) take (cap_out + 1, 4); a.o_dither[k] = (a.dither[k] && out->dither[k]) ? q : nullptr; }
+   a.o_nphotons = (int16_t *) take (cap_out + 1, 2); a.o_pha = (int16_t *) take (cap_out + 1, 2);
+   a.max_out = cap_out;
+   a.n_out = (unsigned long long *) p; a.error = (unsigned int *) (p + 8);
+   int status = 0;
+   unsigned long long rows = 0; unsigned int err = 0;
+   cudaEvent_t e0 = prof_event (c), e1 = prof_event (c);
+   do
+     {
+#define PU_OK(expr) { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { status = fail ("%s: %s", #expr, cudaGetErrorString (e_)); break; } }
+        PU_OK (cudaMemsetAsync (p, 0, 16, c->stream));
+        PU_OK (cudaMemcpyAsync (d_ccd, in->ccd, (size_t) n, cudaMemcpyHostToDevice, c->stream));
+        bool copied = true;
+        for (int k = 0; k < 10; k++)
+          if (h_in[k] != nullptr)
+            {
+               cudaError_t e_ = cudaMemcpyAsync (d_in[k], h_in[k], (size_t) n * 4, cudaMemcpyHostToDevice, c->stream);
+               if (e_ != cudaSuccess) { status = fail ("marxb200_pileup_run: upload: %s", cudaGetErrorString (e_)); copied = false; break; }
+            }
+        if (!copied) break;
+        PU_OK (cudaEventRecord (e0, c->stream));
+        int nl = 0;
+        mx::launch_pileup (a, c->num_sms, c->stream, &nl);
+        PU_OK (cudaEventRecord (e1, c->stream));
+        c->launches += (uint64_t) nl;
+        PU_OK (cudaGetLastError ());
+        PU_OK (cudaMemcpyAsync (&rows, a.n_out, 8, cudaMemcpyDeviceToHost, c->stream));
+        PU_OK (cudaMemcpyAsync (&err, a.error, 4, cudaMemcpyDeviceToHost, c->stream));
+        PU_OK (cudaStreamSynchronize (c->stream));
+        if (err & mx::kPuErrCcd) { status = fail ("marxb200_pileup_run: an event's CCD id is outside 0..9"); break; }
+        if (err & mx::kPuErrCorrupt) { status = fail ("marxb200_pileup_run: pixel coordinate beyond the chip (corrupt file?)"); break; }
+        if (err & mx::kPuErrFrameTooLong) { status = fail ("marxb200_pileup_run: an exposure frame holds more than 65536 events"); break; }
+        if (err & mx::kPuErrPha) { status = fail ("marxb200_pileup_run: no FEF for an island's chip region"); break; }
+        if ((err & mx::kPuErrOverflow) || (rows > cap_out)) { status = fail ("marxb200_pileup_run: more than max_out = %llu rows", (unsigned long long) max_out); break; }
+        const size_t r = (size_t) rows;
+        if (r > 0)
+          {
+             if (out->ccd) PU_OK (cudaMemcpyAsync (out->ccd, a.o_ccd, r, cudaMemcpyDeviceToHost, c->stream));
+             if (out->x) PU_OK (cudaMemcpyAsync (out->x, a.o_x, r * 4, cudaMemcpyDeviceToHost, c->stream));
+             if (out->y) PU_OK (cudaMemcpyAsync (out->y, a.o_y, r * 4, cudaMemcpyDeviceToHost, c->stream));
+             if (out->t) PU_OK (cudaMemcpyAsync (out->t, a.o_t, r * 4, cudaMemcpyDeviceToHost, c->stream));
+             if (out->benergy) PU_OK (cudaMemcpyAsync (out->benergy, a.o_benergy, r * 4, cudaMemcpyDeviceToHost, c->stream));
+             if (out->frame) PU_OK (cudaMemcpyAsync (out->frame, a.o_frame, r * 4, cudaMemcpyDeviceToHost, c->stream));
+             if (out->nphotons) PU_OK (cudaMemcpyAsync (out->nphotons, a.o_nphotons, r * 2, cudaMemcpyDeviceToHost, c->stream));
+             if (out->pha) PU_OK (cudaMemcpyAsync (out->pha, a.o_pha, r * 2, cudaMemcpyDeviceToHost, c->stream));
+             bool ok = true;
+             for (int k = 0; k < 6; k++)
+               if (a.o_dither[k])
+                 {
+                    cudaError_t e_ = cudaMemcpyAsync (out->dither[k], a.o_dither[k], r * 4, cudaMemcpyDeviceToHost, c->stream);
+                    if (e_ != cudaSuccess) { status = fail ("marxb200_pileup_run: download: %s", cudaGetErrorString (e_)); ok = false; break; }
+                 }
+             if (!ok) break;
+             PU_OK (cudaStreamSynchronize (c->stream));
+          }
+        float ms = 0.f;
+        PU_OK (cudaEventElapsedTime (&ms, e0, e1));
+        if (device_ms) *device_ms = ms;
+        *n_out = rows;
+#undef PU_OK
+     }
+   while (0);
+   cudaFreeAsync (slab, c->stream);
+   cudaStreamSynchronize (c->stream);
+   c->ev_pool.push_back (e0); c->ev_pool.push_back (e1);
+   return status;
 }
 
 extern "C" int marxb200_load_calpack_impl (marxb200_ctx *ctx, const char *path, char *errbuf, size_t errlen);

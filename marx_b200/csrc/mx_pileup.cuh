@@ -121,7 +121,11 @@ MX_HD void pu_hood (const PileupArgs &a, uint64_t e, PuHood &h)
         if ((int) (k >> 20) != ccd) continue;
         const int dy = (int) ((k >> 10) & 1023u) - iy, dx = (int) (k & 1023u) - ix;
         if ((dy < -1) || (dy > 1) || (dx < -1) || (dx > 1)) continue;
-        h.at[dy + 1][dx + 1] = (int64_t) j;
+        const int slot = (dy + 1) * 3 + (dx + 1);              // compile-time slots: the table stays in registers on the device
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int q = 0; q < 9; q++) if (q == slot) h.at[q / 3][q % 3] = (int64_t) j;
      }
 }
 
@@ -132,7 +136,13 @@ MX_HD void pu_island (const PileupArgs &a, uint64_t e)
    PuHood h; pu_hood (a, e, h);
    double s = 0.0; uint32_t np = 0;
    bool first = true;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
    for (int r = 0; r < 3; r++)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
      for (int c = 0; c < 3; c++)
        {
           const int64_t j = h.at[r][c];
@@ -151,7 +161,13 @@ MX_HD void pu_detect (const PileupArgs &a, uint64_t e)
    if (a.pn[e] == 0) return;
    PuHood h; pu_hood (a, e, h);
    float pb[3][3], ib[3][3];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
    for (int r = 0; r < 3; r++)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
      for (int c = 0; c < 3; c++)
        {
           const int64_t j = h.at[r][c];
@@ -210,7 +226,13 @@ MX_HD void pu_emit (const PileupArgs &a, uint64_t e)
         if (rng.uniform () >= prob) return;
         PuHood h; pu_hood (a, e, h);
         x = 0; y = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
         for (int c = 0; c < 3; c++)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
           for (int r = 0; r < 3; r++)
             {
                const int64_t j = h.at[r][c];
@@ -243,6 +265,11 @@ MX_HD void pu_scatter (const PileupArgs &a, uint64_t e)
    a.o_nphotons[pos] = (int16_t) a.in[e]; a.o_pha[pos] = a.spha[e]; a.o_benergy[pos] = a.ib[e];
    for (int d = 0; d < 6; d++) if (a.dither[d] && a.o_dither[d]) a.o_dither[d][pos] = a.dither[d][e];
 }
+
+#if defined(__CUDACC__)
+// pileup_kernels.cu: the eight launches on stream s (5 steps, 2 scan kernels, scatter)
+void launch_pileup (const PileupArgs &a, int num_sms, cudaStream_t s, int *n_launches);
+#endif
 
 }  // namespace mx
 #endif
