@@ -118,6 +118,46 @@ def level1_leg(m, stream, args, reps=20):
     return out
 
 
+def pileup_leg(m, stream, args, n=1 << 22, reps=5):
+    """marxb200_pileup_run (marxpileup's frame loop) on a synthetic bright-source event list: ~32 events per
+    3.241 s exposure frame on a spot of sigma 3 pixels.  `ms` = the eight kernels (CUDA events inside the library), `e2e_ms` = the
+    whole call with HOST columns in and out.  Beside it the pinned plain-C oracle (oracle/pileup_oracle.c, one core) on the same list."""
+    import numpy as np
+    import torch
+    r = np.random.default_rng(args.seed)
+    alpha, ft, rate = 0.5, 3.241, 10.0
+    cols = {"ccd": np.full(n, 7, np.int8), "t": np.cumsum(r.exponential(1.0 / rate, n)).astype(np.float32),
+            "x": (512.0 + r.normal(0.0, 3.0, n)).astype(np.float32), "y": (300.0 + r.normal(0.0, 3.0, n)).astype(np.float32),
+            "benergy": r.uniform(0.4, 7.0, n).astype(np.float32)}
+    for k in ("sky_ra", "sky_dec", "sky_roll", "det_dy", "det_dz", "det_theta"):
+        cols[k] = r.normal(0.0, 1e-3, n).astype(np.float32)
+    with torch.cuda.stream(stream):
+        got, _ = m.pileup(cols, alpha, ft, args.seed)
+        ms, wall = [], []
+        for _ in range(reps):
+            t0 = time.time()
+            got, k = m.pileup(cols, alpha, ft, args.seed)
+            wall.append((time.time() - t0) * 1e3)
+            ms.append(k)
+    ms, wall, rows = float(np.median(ms)), float(np.median(wall)), len(got["t"])
+    # algorithmic bytes: R 41 per event (ccd 1, pixel/time/energy 16, aspect 24), W 49 per output row
+    out = {"events": n, "rows": rows, "ms": ms, "events_per_s": n / (ms * 1e-3), "e2e_ms": wall, "e2e_events_per_s": n / (wall * 1e-3),
+           "launches_per_call": 8, "hbm_gbs_algorithmic": (41.0 * n + 49.0 * rows) / (ms * 1e-3) / 1e9,
+           "workload": "synthetic list, %d events, %.0f events/s, frame %.3f s, alpha %.1f, one chip" % (n, rate, ft, alpha)}
+    if not args.no_cpu_baseline:
+        try:
+            from tests import pileup_lib
+            t0 = time.time()
+            ref = pileup_lib.oracle_pileup(cols, ["Alpha=%r" % alpha, "FrameTime=%r" % ft, "FrameTransferTime=0.0"], args.calpack, args.seed)
+            dt = time.time() - t0
+            out["parity"] = bool(all(got[k].tobytes() == ref[k].tobytes() for k in ref))
+            out["cpu_baseline"] = {"value": n / dt, "unit": "events/s", "cores": 1, "kind": "port",
+                                   "sample": "%d events, oracle/pileup_oracle.c (gcc -O2), %.2f s" % (n, dt)}
+        except Exception as e:  # noqa: BLE001
+            out["cpu_baseline"] = {"value": None, "kind": "port", "sample": "unavailable: %s" % str(e)[:120]}
+    return out
+
+
 def bind_to_gpu_numa_node(index):
     """Pin this rank's host threads to the CPUs local to its GPU (sysfs local_cpulist of the GPU's PCI device), so that
     the pinned egress buffers are first-touched on that NUMA node and the D2H copies of 8 ranks do not all cross the
@@ -370,6 +410,14 @@ def cuda_arm(args):
         except Exception as e:  # noqa: BLE001
             level1 = {"unavailable": str(e)[:200]}
 
+    # pile-up leg, likewise on its own after the timed regions
+    pileup = None
+    if rank == 0 and not args.no_pileup:
+        try:
+            pileup = pileup_leg(m, stream, args)
+        except Exception as e:  # noqa: BLE001
+            pileup = {"unavailable": str(e)[:200]}
+
     total_rays = float(n) * world * args.steps
     value = total_rays / (ms * 1e-3)
     e2e_value = total_rays / (ms_e2e * 1e-3)
@@ -455,6 +503,8 @@ def cuda_arm(args):
     }
     if level1 is not None:
         line["level1"] = level1
+    if pileup is not None:
+        line["pileup"] = pileup
     # CPU baseline beside it (N=1 only): the compiled reference on ONE core, bounded sample
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -482,6 +532,7 @@ def main():
     ap.add_argument("--ref-rays-per-proc", type=int, default=1000000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-level1", action="store_true")
+    ap.add_argument("--no-pileup", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -1,6 +1,7 @@
 /* pileup_oracle.c -- TEST INFRASTRUCTURE: plain-C restatement of marxpileup's frame loop (marx/src/marxpileup.c; SURVEY.md 8f
  * rank 4), the ACIS pile-up model applied to the event list of a simulation.  Only tests/ (and later smoke / bench's cpu_baseline)
- * may use it; the product (marx_b200/) never does.  There is no CUDA implementation of this row yet (plan).
+ * may use it; the product (marx_b200/) never does.  The device implementation is marx_b200/csrc/mx_pileup.cuh + pileup_kernels.cu
+ * behind marxb200_pileup_run (tests/test_gpu_zz_pileup.py compares the two).
  *
  * Parity PINNED: tests/test_pileup_oracle_vs_reference.py requires this file to reproduce the output directory of the stock program
  * run with counter-based draws (oracle/_ref/marxpileup_replay = the unmodified marxpileup.c + oracle/ref/pileup_replay.c) bit for bit

@@ -1,8 +1,8 @@
 """Pins oracle/pileup_oracle.c (the plain-C restatement of marxpileup's frame loop, marx/src/marxpileup.c:573-922,1121-1213) to the
 UNMODIFIED reference: bit for bit -- every output column, every row -- against the committed output of the stock program run with
 counter-based draws (tests/golden/pileup_*.npz, made by oracle/_ref/marxpileup_replay), on fresh simulations where oracle/_ref
-exists, and statistically against the stock program with its own RNG.  (The CUDA implementation of this row is the next step,
-DESIGN.md section 8: this file is its oracle.)"""
+exists, and statistically against the stock program with its own RNG.  (The CUDA implementation, marxb200_pileup_run, is compared with this oracle and with
+the same fixtures in tests/test_gpu_zz_pileup.py.)"""
 import numpy as np
 import pytest
 
