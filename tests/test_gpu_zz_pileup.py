@@ -1,8 +1,7 @@
 """ACIS pile-up on the GPU (marxb200_pileup_run; marx/src/marxpileup.c:573-922,1121-1213) against the stock
 program's committed output (tests/golden/pileup_*.npz, bit for bit, every column and row) and against the pinned plain-C oracle
-(oracle/pileup_oracle.c) on larger and on adversarial event lists.  (The file sorts last on purpose: the device path of this row
-was first verified by stepping its per-event functions on the host -- tools/pileup_hostcheck.py, bit-identical on the three
-fixtures -- in a session whose GPU budget was spent, so its first run on a B200 must not mask the other GPU tests under `-x`.)"""
+(oracle/pileup_oracle.c) on larger and on adversarial event lists.  (The file sorts last on purpose: it was written in a session with one GPU-minute left.  tools/pileup_gpu_probe.py made the same
+calls on a B200 -- profiles/r01_pileup_first_contact.txt, r01_pileup_edges.txt: all identical -- but this file itself had not run there.)"""
 import numpy as np
 import pytest
 
