@@ -186,6 +186,104 @@ def bind_to_gpu_numa_node(index):
         return None
 
 
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def d2h_probe(m, rank, world, dev, barrier, nbytes=128 << 20, reps=6):
+    """marxb200_probe_d2h: pinned device-to-host copies of 128 MB; every rank alone in turn, then all ranks together."""
+    import torch
+    import torch.distributed as dist
+    alone = 0.0
+    for r in range(world):
+        barrier()
+        if r == rank:
+            alone = m.probe_d2h(nbytes, reps)
+    barrier()
+    together = m.probe_d2h(nbytes, reps, together=(world > 1))
+    barrier()
+    if world > 1:
+        t = torch.tensor([alone, together], device=dev, dtype=torch.float64)
+        parts = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        alone_all = [float(p[0]) for p in parts]
+        tog_all = [float(p[1]) for p in parts]
+    else:
+        alone_all, tog_all = [alone], [together]
+    return {"bytes_per_copy": nbytes, "copies": reps, "alone_gbs_per_rank": alone_all, "concurrent_gbs_per_rank": tog_all,
+            "concurrent_gbs_total": sum(tog_all),
+            "note": "cudaHostAlloc'ed buffer, one cudaMemcpyAsync per copy on a private stream, CUDA-event timed; `e2e` moves 74 B per "
+                    "event per step per rank through the same path"}
+
+
+def sweep_leg(m, stream, n, rank, world, dev, barrier, args):
+    """BASELINE.json configs[4] (C5): 1e7 ... 1e11 generated rays of the C2 set-up in steps of `world` blocks of n rays (the last step
+    short), ray indices 64 bit, arrival times continued on the device; detected events counted by a device-resident tally that the
+    ranks sum with ONE marxb200_tally_allreduce at the end of each size.  Device timed, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    sizes = [s for s in (10**7, 10**8, 10**9, 10**10, 10**11) if s <= args.sweep_max]
+    tally = m.tally_create(("ccd", 10, 0, 10))
+    out = []
+    for total in sizes:
+        tally.reset()
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record(stream)
+        first, steps, base = 0, 0, 0.0
+        with torch.cuda.stream(stream):
+            while first < total:
+                cnt = min(n * world, total - first)
+                if world == 1:
+                    m.trace(first, cnt, base)
+                else:
+                    m.trace_sharded(first, cnt, base)
+                tally.accumulate()
+                first += cnt
+                steps += 1
+                base = -1.0                        # continue the running arrival-time sum on the device
+            if world > 1:
+                tally.allreduce()
+        t1.record(stream)
+        barrier()
+        ms = t0.elapsed_time(t1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        events = int(tally.read().sum())
+        out.append({"rays": total, "steps": steps, "seconds": ms * 1e-3, "rays_per_s": total / (ms * 1e-3), "events": events,
+                    "ray_index_bits": 64 if total > (1 << 32) else 32})
+    return {"sizes": out, "note": "device resident; the reference counts rays in an int (marx.c:86-87,789) and tags in 32 bits "
+                                  "(marx.h:98): beyond 2^32 rays only the 64-bit ray index keys the draws"}
+
+
+def config_leg(pack, n, stream, dev, args, steps=10):
+    """device-resident rays/s of another BASELINE.json configuration at the bench's step size (rank 0, N = 1)"""
+    import torch
+    import marx_b200
+    with marx_b200.MarxB200(pack, device=dev.index, seed=args.seed, max_photons=n, stream=stream.cuda_stream) as c:
+        with torch.cuda.stream(stream):
+            for k in range(3):
+                c.trace(k * n, n)
+            torch.cuda.synchronize(dev)
+            t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+            t0.record(stream)
+            for k in range(steps):
+                c.trace((3 + k) * n, n)
+            t1.record(stream)
+            torch.cuda.synchronize(dev)
+        ms = t0.elapsed_time(t1)
+        return {"calpack": pack, "rays_per_s": float(n) * steps / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps,
+                "stage_counts_last_step": c.stage_counts()}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -307,35 +405,24 @@ def cuda_arm(args):
     pinned = [torch.empty(cap * (bytes_per_event + 2) + 4096, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
     pinned_np = [p.numpy() for p in pinned]
 
-    bases = {}
-
-    def plan_time_bases(step0, K):
-        """multi-GPU: arrival times are one running sum over ALL rays (source.c:326).  Each rank reduces the time
-        increments of its K blocks to super-tile sums (marxb200_time_sums), ONE all-gather over NCCL exchanges them,
-        and every rank adds them up in global ray order -- exactly the additions a single GPU performs -- to get the
-        absolute time base of each of its blocks.  Single GPU: the running sum simply continues on the device."""
-        if world == 1:
-            for s in range(step0, step0 + K):
-                bases[s] = -1.0
-            return
-        from marx_b200.dist import block_time_bases
-        mine = np.stack([m.time_sums((s * world + rank) * n, n) for s in range(step0, step0 + K)])      # [K, n_super]
-        t = torch.from_numpy(mine).to(dev)
-        gathered = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(gathered, t)
-        allsums = torch.stack(gathered).cpu().numpy()                                                      # [world, K, n_super]
-        for k in range(K):
-            b, plan_time_bases.running = block_time_bases([allsums[r, k] for r in range(world)], plan_time_bases.running)
-            bases[step0 + k] = b[rank]
-    plan_time_bases.running = 0.0
-
-    def time_base_for(step):
-        return (step * world + rank) * n, bases[step]
+    # multi-GPU: the exchanges run inside the library (comm.cu): NCCL communicator from an id rank 0 creates and the launcher's
+    # process group hands over; marxb200_trace_sharded all-gathers the time bases on the device; the event lists are merged
+    # on rank 0 over NVLink (marxb200_merge_events_begin/_end) while the next step is traced
+    if world > 1:
+        from marx_b200.api import comm_unique_id, COMM_ID_BYTES
+        idt = torch.zeros(COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, src=0)
+        m.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+    merge_log = []
 
     def one_step(step):
-        first, base = time_base_for(step)
         with torch.cuda.stream(stream):
-            m.trace(first, n, base)            # fused source+HRMA-A, HRMA-B, HRMA-C, grating, detector, order restore
+            if world == 1:
+                m.trace(step * n, n)           # fused source+HRMA-A, HRMA B1 | B2C1 | C2, grating, detector, order restore
+            else:
+                m.trace_sharded(step * n * world, n * world)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -343,12 +430,13 @@ def cuda_arm(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    def timed(K, e2e):
+    def timed(K, e2e, merge=False):
+        """K steps.  e2e: every step's event list lands in this rank's pinned host memory (pipelined packed egress).  merge (N>1):
+        every step's event lists are merged on rank 0's HBM in arrival order; the transfers of step s run while step s+1 is traced."""
         barrier()
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
         launches0 = m.launch_count()
         t0.record(stream)
-        plan_time_bases(timed.step, K)        # inside the timed region
         n_events = 0
         for s in range(K):
             one_step(timed.step)
@@ -358,8 +446,15 @@ def cuda_arm(args):
                 if s > 0:
                     n_events += len(m.egress_end_packed(pinned_np[(s - 1) & 1])["energy.dat"])
                 m.egress_begin_packed(e2e_mask, 0.0, cap)
+            if merge:
+                with torch.cuda.stream(stream):
+                    if s > 0:
+                        merge_log.append(m.merge_events_end())
+                    m.merge_events_begin(e2e_mask, 0.0, cap, 0)
         if e2e:
             n_events += len(m.egress_end_packed(pinned_np[(K - 1) & 1])["energy.dat"])
+        if merge:
+            merge_log.append(m.merge_events_end())
         t1.record(stream)
         barrier()
         ms = t0.elapsed_time(t1)
@@ -374,13 +469,18 @@ def cuda_arm(args):
     if rank == 0:
         sampler.start()
         time.sleep(1.0)                       # let nvidia-smi come up; it samples every 100 ms from then on
-    plan_time_bases(timed.step, max(args.warmup, 3))
     for _ in range(max(args.warmup, 3)):
         one_step(timed.step); timed.step += 1
+    if world > 1:
+        timed(2, e2e=False, merge=True)       # sets up the merge buffers (collective: IPC mapping of rank 0's buffer)
+        merge_log.clear()
     if rank == 0:
         sampler.mark()                        # only samples taken from here on count
-    ms, launches, _ = timed(args.steps, e2e=False)
+    # `value`: at N > 1 the NVLink merge of every step's event lists is inside the timed region
+    ms, launches, _ = timed(args.steps, e2e=False, merge=(world > 1))
     clocks = sampler.stop() if rank == 0 else None
+    merge_steps = list(merge_log)
+    ms_nomerge = timed(args.steps, e2e=False)[0] if world > 1 else ms
     counts = m.stage_counts()
     # per-kernel durations: the same K steps once more with the library's CUDA-event marks switched on (events
     # recorded on the launching stream after every kernel; the marks cost ~1 % so `value` is timed without them)
@@ -401,8 +501,23 @@ def cuda_arm(args):
     timed(2, e2e=True)
     ms_e2e, _, n_events = timed(args.steps, e2e=True)
 
+    # host-copy ceiling of this box (collective): 128 MB pinned D2H copies, every rank alone in turn, then all ranks at once --
+    # the bound of `e2e` when 8 ranks land 89 MB per step each in host memory
+    d2h = None
+    if not args.no_probe:
+        try:
+            d2h = d2h_probe(m, rank, world, dev, barrier)
+        except Exception as e:  # noqa: BLE001
+            d2h = {"unavailable": str(e)[:200]}
+
+    # C5: throughput sweep 1e7 ... 1e11 generated rays (collective)
+    sweep = None
+    if not args.no_sweep:
+        sweep = sweep_leg(m, stream, n, rank, world, dev, barrier, args)
+
     # Level-1 leg (marx2fits' per-event transforms on the device-resident list): the events of the last batch,
     # measured on its own after the timed regions above -- it is not part of `value` / `e2e`
+    one_step(timed.step); timed.step += 1     # a full batch again (the sweep ends on a short one); collective at N > 1
     level1 = None
     if rank == 0 and not args.no_level1:
         try:
@@ -417,6 +532,33 @@ def cuda_arm(args):
             pileup = pileup_leg(m, stream, args)
         except Exception as e:  # noqa: BLE001
             pileup = {"unavailable": str(e)[:200]}
+
+    ic = None
+    try:
+        ic = [int(v) for v in m.internal_counts()]
+    except Exception:
+        pass
+    fp64_peak, fp64_src = None, None
+    if rank == 0:
+        try:
+            fp64_peak = float(m.measure_fp64_peak())
+            fp64_src = "measured in this run (marxb200_measure_fp64_peak: DFMA chains, best of 5)"
+        except Exception:  # noqa: BLE001
+            fp64_peak, fp64_src = 37.0, "datasheet (measurement failed)"
+    comm_info = m.comm_info() if world > 1 else None
+    m.close()
+
+    # the other BASELINE.json configurations (C1, C3, C4), device resident, same step size: driver-visible numbers
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        configs = {}
+        for name, pack in (("C1 point 1.5 keV HRMA+ACIS-S no grating no dither", "c1_acis_s"),
+                           ("C3 LETG+HRC-S 0.1-2 keV dither", "c3_letg_hrc_s"),
+                           ("C4 BETA source 10' off axis ACIS-I dither", "c4_beta_acis_i")):
+            try:
+                configs[name] = config_leg(pack, n, stream, dev, args)
+            except Exception as e:  # noqa: BLE001
+                configs[name] = {"unavailable": str(e)[:200]}
 
     total_rays = float(n) * world * args.steps
     value = total_rays / (ms * 1e-3)
@@ -433,43 +575,49 @@ def cuda_arm(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-    # dominant kernel among those that read their input from HBM: HRMA phase B1 (optical constants, P-conic normal, blur, Fresnel
-    # reflectivity test) -- or the whole phase B when the mirror stage runs uncut.  Algorithmic bytes per INPUT ray of that kernel
-    # (DESIGN.md section 4): R x,p 48 + energy 8 + shell/state 3 = 59; W per survivor x,p 48 + state 23 = 71 (B), + normal 24 = 95 (B1)
-    ic = None
-    try:
-        ic = [int(v) for v in m.internal_counts()]
-    except Exception:
-        pass
-    roof_kernel = "k1_hrma<3> (B1)" if k1_four else "k1_hrma<1>"
-    k1b_in = ic[4] if ic and ic[4] else int(0.476 * n)
-    k1b_out = ic[5] if ic and ic[5] else int((0.62 if k1_four else 0.573) * k1b_in)
-    k1b_bytes = 59.0 * k1b_in + (95.0 if k1_four else 71.0) * k1b_out
-    k1_ms = per[k1_names[0]]
-    achieved = k1b_bytes / (k1_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "k1b_traffic.json")))
-        ent = tj.get("all_kernels", {}).get("k1_hrma<3>" if k1_four else "k1_hrma<1>")
-        traffic = (ent["dram_read_bytes"] + ent["dram_write_bytes"]) if ent else None
-    except Exception:
-        pass
-    # FP64 peak: not in MEASURED_PEAKS.json -> measured live with the library's DFMA-chain microbenchmark
-    fp64_src = "measured (MEASURED_PEAKS.json)"
     if "fp64_tflops" in peaks:
-        fp64_peak = float(peaks["fp64_tflops"])
-    else:
-        try:
-            fp64_peak = float(m.measure_fp64_peak())
-            fp64_src = "measured in this run (marxb200_measure_fp64_peak: DFMA chains, best of 5)"
-        except Exception:  # noqa: BLE001
-            fp64_peak, fp64_src = 37.0, "datasheet (measurement failed)"
-    names = (["K0 time pre-pass (k0_time_sums+k0_time_scan)", "K0+K1a fused (k01_source_hrma)"]
-             + (["K1 B1 (k1_hrma<3>)", "K1 B2+C1 (k1_hrma<4>)", "K1 C2 (k1_hrma<5>)"] if k1_four else ["K1b (k1_hrma<1>)", "K1c (k1_hrma<2>)"])
-             + ["K2 (k2_grating)", "K3 (k3_acis<.,1> + k3_acis<.,2>)", "order restore (5 kernels)"])
+        fp64_peak, fp64_src = float(peaks["fp64_tflops"]), "measured (MEASURED_PEAKS.json)"
+
+    # per-kernel roofline table: input rays of each kernel from the device counters of the last step, algorithmic bytes and
+    # contract FP64 flop-equivalents per input ray, executed FP64 flops and DRAM bytes per input
+    # ray from the committed ncu capture (profiles/r02_kernel_counters.json, tools/ncu_counters.py)
+    prof = {}
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r02_kernel_counters.json")))
+    except Exception:
+        pass
+    n_in = {"K0": n, "K01": n, "B1": ic[4] if ic else 0, "B2C1": ic[5] if ic else 0, "C2": ic[7] if ic else 0,
+            "K2": ic[1] if ic else 0, "K3": ic[2] if ic else 0, "ORDER": ic[3] if ic else 0}
+    if not k1_four and ic:
+        n_in["B"], n_in["C"] = ic[4], ic[5]
+    rows = ([("K0", "K0 time pre-pass (k0_time_sums + scan)", 0.0, 60.0), ("K01", "K0+K1a fused (k01_source_hrma)", 56.0, 530.0 + 280.0)]
+            + ([("B1", "K1 B1 (k1_hrma<3>)", 116.0, 530.0), ("B2C1", "K1 B2+C1 (k1_hrma<4>)", 166.0, 440.0 + 530.0 * 0.96), ("C2", "K1 C2 (k1_hrma<5>)", 166.0, 243.0)]
+               if k1_four else [("B", "K1b (k1_hrma<1>)", 116.0, 970.0), ("C", "K1c (k1_hrma<2>)", 166.0, 773.0)])
+            + [("K2", "K2 (k2_select + k2_grating<1>)", 114.0, 700.0), ("K3", "K3 (k3_acis<.,1> + k3_acis<.,2>)", 147.0, 850.0),
+               ("ORDER", "order restore (5 kernels)", 252.0, 0.0)])
     kernels = {}
-    for k, name in enumerate(names):
-        kernels[name] = {"ms": stage_ms[k], "share": stage_ms[k] / sum(stage_ms)}
+    for k, (key, name, bytes_per, flopeq_per) in enumerate(rows):
+        t = stage_ms[k] * 1e-3
+        ent = {"ms": stage_ms[k], "share": stage_ms[k] / sum(stage_ms), "input_rays": n_in.get(key, 0),
+               "algorithmic_bytes_per_input_ray": bytes_per, "contract_flopeq_per_input_ray": flopeq_per}
+        if t > 0 and n_in.get(key):
+            ent["hbm_frac"] = bytes_per * n_in[key] / t / 1e9 / hbm_peak
+            ent["fp64_frac_contract"] = flopeq_per * n_in[key] / t / 1e12 / fp64_peak
+            pk = prof.get(key)
+            if pk:
+                ent["executed_fp64_flop_per_input_ray"] = pk["fp64_flop_per_input_ray"]
+                ent["fp64_frac_executed"] = pk["fp64_flop_per_input_ray"] * n_in[key] / t / 1e12 / fp64_peak
+                ent["dram_bytes_per_input_ray_ncu"] = pk["dram_bytes_per_input_ray"]
+                ent["traffic_over_algorithmic"] = pk["dram_bytes_per_input_ray"] / bytes_per if bytes_per else None
+        kernels[name] = ent
+    # the dominant kernel by time and its binding roof: every kernel of this path sits above the FP64 / HBM ridge, so
+    # the roof is the FP64 pipe; `achieved` counts the FP64 flops the kernel EXECUTES (2 per DFMA, 1 per DMUL / DADD, from the ncu
+    # counters of the committed capture) per launch over its CUDA-event time
+    top_key, top_name = max(((r[0], r[1]) for r in rows), key=lambda kn: kernels[kn[1]]["ms"])
+    top = kernels[top_name]
+    flop_per = top.get("executed_fp64_flop_per_input_ray", top["contract_flopeq_per_input_ray"])
+    achieved = flop_per * top["input_rays"] / (top["ms"] * 1e-3) / 1e12
+    tp = prof.get(top_key)
     # SURVEY 8d contract figures for the whole staged path: 179 B and 1.6e3 FP64 flop-equivalents per generated ray
     path_hbm_gbs = 179.0 * n / (sum(stage_ms) * 1e-3) / 1e9
     path_tflopeq = 1600.0 * n / (sum(stage_ms) * 1e-3) / 1e12
@@ -483,24 +631,45 @@ def cuda_arm(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 24,
                 "d2h_bytes_per_step": int(bytes_per_event * n_events / args.steps) + 8,
-                "note": "C ABI marxb200_trace_from + marxb200_egress_begin_packed/_end_packed: every step's event list (the 21 "
+                "note": "C ABI marxb200_trace(_sharded) + marxb200_egress_begin_packed/_end_packed: every step's event list (the 21 "
                         "columns the reference writes for this configuration, in its float32/int16/int8 file encoding, 74 B per "
-                        "event) is copied to pinned host memory inside the timed region, overlapped with the next batch; the "
-                        "only per-step host input of this path is the batch descriptor (first ray, count, time base)"},
+                        "event) is copied to this rank's pinned host memory inside the timed region, overlapped with the next "
+                        "batch; the only per-step host input of this path is the batch descriptor (first ray, count, time base)"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": roof_kernel, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": k1b_bytes, "input_rays_per_launch": k1b_in, "output_rays_per_launch": k1b_out,
-                     "avg_launch_ms": k1_ms,
-                     "note": "every kernel of this path sits above the FP64/HBM ridge (SURVEY 8d): instruction issue, not HBM, "
-                             "binds; the HBM fraction is reported because the contract asks for it",
+        "roofline": {"bound": "fp64", "kernel": top_name, "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                     "frac": achieved / fp64_peak, "peak_source": fp64_src,
+                     "traffic": (tp["dram_bytes_per_input_ray"] * top["input_rays"]) if tp else None,
+                     "flop_per_input_ray": flop_per, "input_rays_per_launch": top["input_rays"], "avg_launch_ms": top["ms"],
+                     "hbm": {"achieved_gbs": top["algorithmic_bytes_per_input_ray"] * top["input_rays"] / (top["ms"] * 1e-3) / 1e9,
+                             "peak_gbs": hbm_peak, "frac": top.get("hbm_frac"), "peak_source": peak_src},
+                     "note": "dominant kernel by time, on the roof that binds it: arithmetic intensity of every kernel of this path is "
+                             "above the FP64/HBM ridge of 5.2 flop/B (SURVEY 8d); both fractions per kernel in `kernels`",
                      "whole_path": {"hbm_gbs_at_179B_per_ray": path_hbm_gbs, "hbm_frac": path_hbm_gbs / hbm_peak,
                                     "fp64_tflopeq_at_1600_per_ray": path_tflopeq, "fp64_peak_tflops": fp64_peak,
-                                    "fp64_frac": path_tflopeq / fp64_peak,
-                                    "fp64_peak_source": fp64_src},
+                                    "fp64_frac": path_tflopeq / fp64_peak},
                      "profiled_ms_per_step": ms_prof / args.steps,
                      "kernels": kernels},
     }
+    if world > 1:
+        recv = [x for x in merge_steps if x["nvlink_bytes"] > 0 and x["transfer_ms"] > 0]
+        tot_b = sum(x["nvlink_bytes"] for x in recv)
+        tot_ms = sum(x["transfer_ms"] for x in recv)
+        line["merge"] = {"what": "every step's per-GPU event lists concatenated in arrival order in rank 0's HBM (marxb200_merge_events_begin/"
+                                 "_end, reference analogue marxcat.c:505-535), inside the timed region of `value`, overlapped with the next step",
+                         "transport": comm_info["merge_transport"], "nccl_version": comm_info["nccl_version"],
+                         "steps": len(merge_steps), "rows_per_step": (sum(x["n_rows"] for x in merge_steps) / max(len(merge_steps), 1)),
+                         "nvlink_bytes_per_step_into_rank0": tot_b / max(len(recv), 1),
+                         "transfer_ms_per_step": tot_ms / max(len(recv), 1),
+                         "achieved_nvlink_gbs_into_rank0": (tot_b / (tot_ms * 1e-3) / 1e9) if tot_ms > 0 else None,
+                         "value_without_merge": total_rays / (ms_nomerge * 1e-3),
+                         "time_base_exchange": "ncclAllGather of the pre-pass's per-65536-ray sums inside marxb200_trace_sharded, added in "
+                                               "global ray order on every GPU (no host round trip)"}
+    if d2h is not None:
+        line["e2e"]["d2h_ceiling"] = d2h
+    if sweep is not None:
+        line["sweep"] = sweep
+    if configs is not None:
+        line["configs"] = configs
     if level1 is not None:
         line["level1"] = level1
     if pileup is not None:
@@ -509,7 +678,7 @@ def cuda_arm(args):
     if world == 1 and not args.no_cpu_baseline:
         try:
             rays, secs, _ = run_reference_sample(args.cpu_baseline_rays, 1)
-            line["cpu_baseline"] = {"value": rays / secs, "unit": UNIT, "cores": 1, "kind": "reference",
+            line["cpu_baseline"] = {"value": rays / secs, "unit": UNIT, "cores": 1, "kind": "reference", "cpu": cpu_model(),
                                     "sample": "%d rays, stock MARX 5.5.3 stages + stock RNG, trace loop only "
                                               "(oracle/_ref/marx_trace_bench, gcc -O2), %.1f s" % (rays, secs)}
         except Exception as e:  # noqa: BLE001
@@ -533,6 +702,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-level1", action="store_true")
     ap.add_argument("--no-pileup", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-probe", action="store_true")
+    ap.add_argument("--no-configs", action="store_true")
+    ap.add_argument("--sweep-max", type=float, default=1e11)
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

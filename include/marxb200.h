@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MARXB200_ABI_VERSION 1
+#define MARXB200_ABI_VERSION 2
 #define MARXB200_NUM_SHELLS 4          /* MARX_NUM_MIRRORS, marx/libsrc/_marx.h:46 */
 #define MARXB200_MAX_CHIPS 6           /* _MARX_NUM_ACIS_S_CHIPS, _marx.h:41 */
 #define MARXB200_MAX_CONTAM_LAYERS 5   /* MAX_LAYERS, marx/libsrc/aciscontam.c:76 */
@@ -594,6 +594,68 @@ typedef struct
 marxb200_pileup_out;
 int marxb200_pileup_run (marxb200_ctx *ctx, uint64_t n, const marxb200_pileup_in *in, double alpha, double frame_time, uint64_t seed,
                          uint64_t max_out, const marxb200_pileup_out *out, uint64_t *n_out, double *device_ms);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU: one process per GPU, the exchanges run on device buffers over NVLink / NVSwitch inside this library
+ * (NCCL, opened at run time with dlopen: a single-GPU caller needs none).  The reference's analogue is N independent `marx`
+ * processes whose output directories marxcat merges in time order (marx/src/marxcat.c:491-535); here the ranks trace
+ * contiguous blocks of ONE simulation, so that rays, draws, arrival times and events are identical for any number of GPUs.
+ *
+ *   communicator   rank 0 obtains an id (marxb200_comm_get_unique_id), hands it to the other ranks by whatever the launcher
+ *                  offers (MPI_Bcast, a torch.distributed broadcast, an environment variable, a file), and every rank calls
+ *                  marxb200_comm_init.  marxb200_comm_init_file does the hand-over through a file for launcher-less runs.
+ *   trace          marxb200_trace_sharded (collective): rays [first_ray, first_ray + n_total) are split into `world` contiguous
+ *                  blocks of ceil (n_total / world) rays rounded up to a multiple of 65536 (marxb200_shard_of); rank r traces
+ *                  block r.  The running arrival-time sum (source.c:326) is continued across the blocks on the device: the
+ *                  ranks all-gather the per-65536-ray sums their own pre-pass produced and add them in global ray order, so
+ *                  every event carries the time one GPU tracing all blocks would give it, and every rank ends with the same
+ *                  running time.  time_base_in as in marxb200_trace_from (< 0: continue).
+ *   merge          marxb200_merge_events_begin / _end (collective): the ranks' event lists, converted on the device to the
+ *                  column-file images marx_write_photons appends (marxio.c:217-322; the columns write_mask selects), are
+ *                  concatenated in rank order -- arrival order -- in a buffer of the destination GPU.  _begin packs and returns
+ *                  at once, so the next block can be launched; _end moves the columns (peer writes by the copy engines into the
+ *                  destination's buffer, or ncclSend / ncclRecv) on a private stream while that block is traced.  TIME of the
+ *                  merged list = (float) (arrival time since the start of the simulation + total_time).
+ *   tallies        marxb200_tally_allreduce: the histograms of all ranks summed in place (ncclAllReduce on the context's stream).
+ * ------------------------------------------------------------------------------------------------ */
+#define MARXB200_COMM_ID_BYTES 128     /* sizeof (ncclUniqueId) */
+#define MARXB200_MAX_RANKS 64
+int marxb200_comm_get_unique_id (void *id /* MARXB200_COMM_ID_BYTES bytes */);
+int marxb200_comm_init (marxb200_ctx *ctx, const void *id, int rank, int world);
+int marxb200_comm_init_file (marxb200_ctx *ctx, const char *path, int rank, int world, double timeout_s);
+/* merge_transport: 0 = ncclSend / ncclRecv, 1 = peer writes into the destination's buffer (valid after the first merge) */
+int marxb200_comm_info (marxb200_ctx *ctx, int *rank, int *world, int *nccl_version, int *merge_transport);
+int marxb200_comm_destroy (marxb200_ctx *ctx);
+/* the block of rank `rank`: *my_n may be short or 0 at the end of the range */
+int marxb200_shard_of (uint64_t first_ray, uint64_t n_total, int rank, int world, uint64_t *my_first_ray, uint64_t *my_n);
+int marxb200_trace_sharded (marxb200_ctx *ctx, uint64_t first_ray, uint64_t n_total, double time_base_in,
+                            uint64_t *my_first_ray, uint64_t *my_n);
+int marxb200_tally_allreduce (marxb200_ctx *ctx, int id);
+
+typedef struct
+{
+   uint32_t num_cols, world, dst_rank, transport;
+   uint64_t n_rows;                         /* rows of the merged list = sum of rows_of_rank */
+   uint64_t rows_of_rank[MARXB200_MAX_RANKS];
+   void *device_base;                       /* destination rank: the merged columns in HBM (NULL elsewhere); valid until the next _end */
+   uint64_t device_offset[32];              /* byte offset of column j from device_base; n_rows * elem_size[j] bytes */
+   uint64_t mask[32];
+   char file[32][16];
+   char type[32];
+   uint32_t elem_size[32];
+   double transfer_ms;                      /* this rank's transfers + the closing barrier, CUDA events on the merge stream */
+   uint64_t nvlink_bytes;                   /* bytes this rank moved over NVLink: received (destination) or sent */
+}
+marxb200_merged_layout;
+int marxb200_merge_events_begin (marxb200_ctx *ctx, uint64_t write_mask, double total_time, uint64_t max_rows_per_rank, int dst_rank);
+int marxb200_merge_events_end (marxb200_ctx *ctx, marxb200_merged_layout *layout);
+/* destination rank: copy the merged columns to the host, laid out like marxb200_egress_end_packed's buffer */
+int marxb200_merge_download (marxb200_ctx *ctx, void *host, uint64_t host_bytes, marxb200_packed_layout *layout);
+
+/* Device-to-host copy rate into pinned memory (GB/s): `reps` copies of `bytes` on a private stream, CUDA-event timed.
+ * flags & 1: cudaHostAllocWriteCombined.  flags & 2 (collective, needs a communicator): the ranks start together, so that the
+ * call measures the box's CONCURRENT ceiling -- the bound of the end-to-end event egress with 8 GPUs. */
+int marxb200_probe_d2h (marxb200_ctx *ctx, uint64_t bytes, int reps, int flags, double *gb_per_s);
 
 /* FP64 roofline denominator measured on this GPU: best of 5 runs of a DFMA-chain kernel (8 independent chains per
  * thread, 8 x 256-thread CTAs per SM), in TFLOP/s counting an FMA as 2 flops.  Diagnostic; leaves the photon list alone. */

@@ -25,6 +25,9 @@ EXPORTED_SYMBOLS = [
     "marxb200_set_level1", "marxb200_level1_reset", "marxb200_level1_transform", "marxb200_level1_download",
     "marxb200_aspsol_rows",
     "marxb200_pileup_run",
+    "marxb200_comm_get_unique_id", "marxb200_comm_init", "marxb200_comm_init_file", "marxb200_comm_info", "marxb200_comm_destroy",
+    "marxb200_shard_of", "marxb200_trace_sharded", "marxb200_tally_allreduce",
+    "marxb200_merge_events_begin", "marxb200_merge_events_end", "marxb200_merge_download", "marxb200_probe_d2h",
 ]
 
 # marxb200_tally_axis.column (include/marxb200.h)
@@ -144,6 +147,18 @@ def load_library():
         "marxb200_level1_reset": [vp],
         "marxb200_level1_transform": [vp, dbl],
         "marxb200_level1_download": [vp, vp, u64, C.POINTER(u64)],
+        "marxb200_comm_get_unique_id": [vp],
+        "marxb200_comm_init": [vp, vp, i32, i32],
+        "marxb200_comm_init_file": [vp, C.c_char_p, i32, i32, dbl],
+        "marxb200_comm_info": [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
+        "marxb200_comm_destroy": [vp],
+        "marxb200_shard_of": [u64, u64, i32, i32, C.POINTER(u64), C.POINTER(u64)],
+        "marxb200_trace_sharded": [vp, u64, u64, dbl, C.POINTER(u64), C.POINTER(u64)],
+        "marxb200_tally_allreduce": [vp, i32],
+        "marxb200_merge_events_begin": [vp, u64, dbl, u64, i32],
+        "marxb200_merge_events_end": [vp, vp],
+        "marxb200_merge_download": [vp, vp, u64, vp],
+        "marxb200_probe_d2h": [vp, u64, i32, i32, C.POINTER(dbl)],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -156,6 +171,34 @@ def load_library():
 class _PackedLayout(C.Structure):
     _fields_ = [("num_cols", C.c_uint32), ("n_rows", C.c_uint64), ("mask", C.c_uint64 * 32), ("file", (C.c_char * 16) * 32),
                 ("type", C.c_char * 32), ("elem_size", C.c_uint32 * 32), ("offset", C.c_uint64 * 32)]
+
+
+class _MergedLayout(C.Structure):
+    _fields_ = [("num_cols", C.c_uint32), ("world", C.c_uint32), ("dst_rank", C.c_uint32), ("transport", C.c_uint32),
+                ("n_rows", C.c_uint64), ("rows_of_rank", C.c_uint64 * 64), ("device_base", C.c_void_p),
+                ("device_offset", C.c_uint64 * 32), ("mask", C.c_uint64 * 32), ("file", (C.c_char * 16) * 32),
+                ("type", C.c_char * 32), ("elem_size", C.c_uint32 * 32), ("transfer_ms", C.c_double), ("nvlink_bytes", C.c_uint64)]
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """rank 0: a fresh NCCL id (128 bytes) to hand to the other ranks (marxb200_comm_get_unique_id)"""
+    lib = load_library()
+    buf = (C.c_ubyte * COMM_ID_BYTES)()
+    if lib.marxb200_comm_get_unique_id(buf) != 0:
+        raise MarxB200Error(lib.marxb200_last_error().decode(errors="replace"))
+    return bytes(buf)
+
+
+def shard_of(first_ray, n_total, rank, world):
+    """(first ray, count) of rank's block in a sharded trace of rays [first_ray, first_ray + n_total)"""
+    lib = load_library()
+    f, n = C.c_uint64(), C.c_uint64()
+    if lib.marxb200_shard_of(int(first_ray), int(n_total), int(rank), int(world), C.byref(f), C.byref(n)) != 0:
+        raise MarxB200Error(lib.marxb200_last_error().decode(errors="replace"))
+    return f.value, n.value
 
 
 class _TallyAxis(C.Structure):
@@ -178,6 +221,10 @@ class Tally:
         out = np.zeros(self.shape, dtype=np.uint64)
         self._m._check(self._m._lib.marxb200_tally_read(self._m._ctx, self.id, out.ctypes.data_as(C.c_void_p), out.size))
         return out
+
+    def allreduce(self):
+        """sum the counters over all ranks of the context's communicator, in place (marxb200_tally_allreduce)"""
+        self._m._check(self._m._lib.marxb200_tally_allreduce(self._m._ctx, self.id))
 
     def device_tensor(self):
         """the counters as a torch int64 tensor ALIASING the device buffer (for an in-place NCCL all-reduce)"""
@@ -290,6 +337,56 @@ class MarxB200:
     def trace(self, first_ray, n, time_base=-1.0):
         """create -> mirror -> grating -> detect for one batch, device resident (marx.c:569, :240-273)."""
         self._check(self._lib.marxb200_trace_from(self._ctx, int(first_ray), int(n), float(time_base)))
+
+    # -- multi-GPU: NCCL inside the library (include/marxb200.h "Multi-GPU") ----------------------------------------
+    def comm_init(self, unique_id, rank, world):
+        buf = (C.c_ubyte * COMM_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        self._check(self._lib.marxb200_comm_init(self._ctx, buf, int(rank), int(world)))
+
+    def comm_init_file(self, path, rank, world, timeout_s=120.0):
+        self._check(self._lib.marxb200_comm_init_file(self._ctx, os.fsencode(path), int(rank), int(world), float(timeout_s)))
+
+    def comm_info(self):
+        r, w, v, t = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self._check(self._lib.marxb200_comm_info(self._ctx, C.byref(r), C.byref(w), C.byref(v), C.byref(t)))
+        return {"rank": r.value, "world": w.value, "nccl_version": v.value,
+                "merge_transport": "peer writes (CUDA IPC, copy engines)" if t.value == 1 else "ncclSend/ncclRecv"}
+
+    def comm_destroy(self):
+        self._check(self._lib.marxb200_comm_destroy(self._ctx))
+
+    def trace_sharded(self, first_ray, n_total, time_base=-1.0):
+        """collective: this rank traces its block of rays [first_ray, first_ray + n_total); -> (first ray, count) of the block"""
+        f, n = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.marxb200_trace_sharded(self._ctx, int(first_ray), int(n_total), float(time_base), C.byref(f), C.byref(n)))
+        return f.value, n.value
+
+    def merge_events_begin(self, write_mask, total_time, max_rows_per_rank, dst_rank=0):
+        self._check(self._lib.marxb200_merge_events_begin(self._ctx, int(write_mask), float(total_time), int(max_rows_per_rank), int(dst_rank)))
+
+    def merge_events_end(self):
+        lay = _MergedLayout()
+        self._check(self._lib.marxb200_merge_events_end(self._ctx, C.byref(lay)))
+        return {"n_rows": int(lay.n_rows), "rows_of_rank": [int(lay.rows_of_rank[r]) for r in range(lay.world)],
+                "transport": int(lay.transport), "transfer_ms": float(lay.transfer_ms), "nvlink_bytes": int(lay.nvlink_bytes),
+                "device_base": lay.device_base, "columns": [lay.file[j].value.decode() for j in range(lay.num_cols)]}
+
+    def merge_download(self, host):
+        """destination rank: the merged columns -> {file name: big-endian numpy view into `host`}"""
+        lay = _PackedLayout()
+        self._check(self._lib.marxb200_merge_download(self._ctx, host.ctypes.data_as(C.c_void_p), host.nbytes, C.byref(lay)))
+        dts = {b"E": ">f4", b"I": ">i2", b"J": ">i4", b"A": "i1"}
+        out = {}
+        for j in range(lay.num_cols):
+            dt = np.dtype(dts[lay.type[j:j + 1]])
+            out[lay.file[j].value.decode()] = host[lay.offset[j]:lay.offset[j] + lay.n_rows * dt.itemsize].view(dt)
+        return out
+
+    def probe_d2h(self, nbytes, reps=8, write_combined=False, together=False):
+        """device-to-host copy rate into pinned memory in GB/s (marxb200_probe_d2h); together: collective, all ranks start at once"""
+        g = C.c_double()
+        self._check(self._lib.marxb200_probe_d2h(self._ctx, int(nbytes), int(reps), (1 if write_combined else 0) | (2 if together else 0), C.byref(g)))
+        return g.value
 
     KERNEL_CLASSES = ("k0_time_sums", "k0_time_scan", "k0_source", "k01_source_hrma", "k1_hrma<0>", "k1_hrma<1>",
                       "k1_hrma<2>", "k2_grating", "k3_detect", "order_restore", "level1",

@@ -206,6 +206,48 @@ __global__ void __launch_bounds__ (kSuperTile) k0_time_bases (const __grid_const
    __syncthreads ();
    if (threadIdx.x == 0) a.dev_times[1] = carry;
 }
+// Multi-GPU form of k0_time_bases (marxb200_trace_sharded, comm.cu): the rays of one collective step are split into
+// `world` contiguous blocks of ns_blk super-tiles, rank r traces block r.  all_sums = [world][ns_blk] holds the super-tile
+// sums of EVERY rank's block (ncclAllGather of the vectors k0_time_super produced; short or empty blocks are zero padded,
+// and acc + 0.0 == acc).  One thread adds them in global ray order from the running end time of the previous step --
+// exactly the additions k0_time_bases performs when one GPU traces the same blocks one after the other -- and notes the
+// bases of this rank's super-tiles on the way.  Every rank ends with the same running end time: no host round trip, no
+// second pass over the increments.
+__global__ void __launch_bounds__ (kSuperTile) k0_time_bases_sharded (const __grid_constant__ SourceArgs a, const double *all_sums,
+                                                                      int rank, int world, uint32_t ns_blk)
+{
+   __shared__ double v[kSuperTile];
+   __shared__ double carry;
+   const uint64_t n_tiles = (a.n + kTile - 1) / kTile;
+   const uint64_t n_super = (n_tiles + kSuperTile - 1) / kSuperTile;      // super-tiles of this rank's block (<= ns_blk)
+   if (threadIdx.x == 0) carry = a.use_dev_base ? a.dev_times[1] : a.time_base;
+   for (int r = 0; r < world; r++)
+     {
+        if ((r == rank) && (threadIdx.x == 0))
+          {
+             a.dev_times[0] = carry;               // `carry` is only ever written by this thread
+             *a.n_out = a.n;
+          }
+        for (uint32_t s0 = 0; s0 < ns_blk; s0 += kSuperTile)
+          {
+             const uint32_t sidx = s0 + threadIdx.x;
+             __syncthreads ();
+             v[threadIdx.x] = (sidx < ns_blk) ? all_sums[(size_t) r * ns_blk + sidx] : 0.0;
+             __syncthreads ();
+             if (threadIdx.x == 0)
+               {
+                  const int cnt = (int) min ((uint32_t) kSuperTile, ns_blk - s0);
+                  double acc = carry;
+                  for (int k = 0; k < cnt; k++) { const double x = v[k]; v[k] = acc; acc += x; }
+                  carry = acc;
+               }
+             __syncthreads ();
+             if ((r == rank) && (sidx < n_super)) a.tile_base[(uint64_t) sidx * kSuperTile] = v[threadIdx.x];
+          }
+     }
+   __syncthreads ();
+   if (threadIdx.x == 0) a.dev_times[1] = carry;
+}
 __global__ void __launch_bounds__ (kSuperTile) k0_time_tiles (const __grid_constant__ SourceArgs a)
 {
    __shared__ double v[kSuperTile];
@@ -1026,7 +1068,7 @@ __global__ void __launch_bounds__ (256) egress_pack (PhotonSoA in, const unsigne
                                                      unsigned char *dst, const double *dev_start_time, double total_time)
 {
    const uint64_t n = min ((uint64_t) *n_ptr, max_n);
-   const double start_time = *dev_start_time;
+   const double start_time = (dev_start_time != nullptr) ? *dev_start_time : 0.0;     // null: TIME = absolute time + total_time
    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x)
      {
         for (int c = 0; c < plan.num_cols; c++)
@@ -1190,6 +1232,18 @@ void launch_time_scan (const SourceArgs &a, cudaStream_t s)
    const unsigned int n_super = (unsigned int) ((n_tiles_of (a.n) + kSuperTile - 1) / kSuperTile);
    if (n_super) k0_time_super<<<n_super, kSuperTile, 0, s>>> (a);
    k0_time_bases<<<1, kSuperTile, 0, s>>> (a);
+   if (n_super) k0_time_tiles<<<n_super, kSuperTile, 0, s>>> (a);
+}
+// the sharded scan in two halves around the all-gather of the super-tile sums (comm.cu)
+void launch_time_super (const SourceArgs &a, cudaStream_t s)
+{
+   const unsigned int n_super = (unsigned int) ((n_tiles_of (a.n) + kSuperTile - 1) / kSuperTile);
+   if (n_super) k0_time_super<<<n_super, kSuperTile, 0, s>>> (a);
+}
+void launch_time_bases_sharded (const SourceArgs &a, const double *all_sums, int rank, int world, uint32_t ns_blk, cudaStream_t s)
+{
+   const unsigned int n_super = (unsigned int) ((n_tiles_of (a.n) + kSuperTile - 1) / kSuperTile);
+   k0_time_bases_sharded<<<1, kSuperTile, 0, s>>> (a, all_sums, rank, world, ns_blk);
    if (n_super) k0_time_tiles<<<n_super, kSuperTile, 0, s>>> (a);
 }
 void launch_source (const SourceArgs &a, cudaStream_t s)

@@ -13,6 +13,7 @@
 #include "../../include/marxb200_calpack.h"
 #include "mx_tables.h"
 #include "mx_kernels.cuh"
+#include "mx_context.hpp"
 #include "mx_aspsol.cuh"
 #include "mx_pileup.cuh"
 #include "tables_build.hpp"
@@ -28,7 +29,7 @@ static_assert (offsetof (marxb200_photon_attr, tag) == 128, "layout");
 using namespace mx;
 
 static thread_local char g_err[512] = "";
-static int fail (const char *fmt, ...)
+int mxb_fail (const char *fmt, ...)
 {
    va_list ap;
    va_start (ap, fmt);
@@ -36,88 +37,7 @@ static int fail (const char *fmt, ...)
    va_end (ap);
    return -1;
 }
-#define CUDA_OK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return fail ("%s: %s", #expr, cudaGetErrorString (e_)); } while (0)
-
-struct marxb200_ctx
-{
-   int device = 0;
-   int num_sms = 0;
-   uint64_t seed = 0;
-   cudaStream_t stream = nullptr;
-   bool own_stream = false;
-   int compact = 1;
-
-   // photon buffers
-   uint64_t capacity = 0;
-   void *slab[2] = {nullptr, nullptr};
-   PhotonSoA buf[2];
-   void *rc_slab = nullptr;
-   RayConst rc;                                  // per-ray constants, indexed by batch slot (mx_kernels.cuh)
-   int cur = 0;
-
-   // device scalars: counts[0..3] + ticket + total_time
-   unsigned long long *d_counts = nullptr;      // [8]: generated, after mirror, after grating, detected, after k1a, after k1b
-   unsigned long long *d_ticket = nullptr;      // [4]: one ticket counter per kernel of a stage call
-   uint32_t *d_bitmap = nullptr, *d_word_prefix = nullptr, *d_block_prefix = nullptr, *d_perm = nullptr;   // order restoration scratch
-   uint64_t n_words = 0;
-   bool ordered = true;                          // live list is in arrival order
-   double *d_tile_sums = nullptr, *d_tile_base = nullptr, *d_super_sums = nullptr, *d_times = nullptr;   // d_times: [batch start, running end]
-   int stage_done = -1;                          // index into d_counts of the latest valid count
-   uint64_t n_generated = 0;
-
-   // tables
-   std::vector<void *> allocs;                   // every cudaMalloc'd table (freed in destroy)
-   SourceDev S; DitherDev D;
-   bool have_source = false, have_dither = false, have_hrma = false, have_grating = false, have_acis = false;
-   int grating_type = 0, detector_type = 0;
-   double source_distance = 0.0;
-   void *blob1 = nullptr, *blob2 = nullptr, *blob3 = nullptr;
-   uint32_t blob1_bytes = 0, blob2_bytes = 0, blob3_bytes = 0;
-   uint32_t k1b_bytes = 0, k1c_seg2_off = 0, k1c_seg2_bytes = 0, k1b1_bytes = 0, k1b2_seg2_off = 0;
-   struct Tally { TallyPlan plan; unsigned long long *bins; uint64_t total; };
-   std::vector<Tally> tallies;
-   bool det_dither_dirty = false;                // uploaded photons may carry detector dither: the per-ray columns are live
-   double aspsol_t_last = 0.0;                   // ASPSOL dither: time of the last state (rays at or beyond it end the run)
-   int grid1[6] = {0, 0, 0, 0, 0, 0}, grid2 = 0, grid3 = 0, grid01 = 0;
-   bool detector_is_hrc = false;
-   int first_mirror_kernel = 0;                  // 1: phase A already ran fused with the source (marxb200_trace)
-   int k3_split = 1;                             // ACIS detector stage as two kernels (MARXB200_K3_SPLIT=0: one kernel)
-   int k2_split = 1;                             // compacting grating stage as k2_select + k2_grating<1> (MARXB200_K2_SPLIT=0: one kernel)
-   int k1_split = 1;                             // compacting mirror stage cut behind the reflectivity tests: A | B1 | B2+C1 | C2
-                                                 // (MARXB200_K1_SPLIT=0: A | B | C, which the in-place parity mode always runs)
-
-   // host boundary staging
-   void *d_aos = nullptr; uint64_t d_aos_cap = 0;
-   void *h_pinned = nullptr; size_t h_pinned_bytes = 0;
-
-   uint64_t launches = 0;
-   uint64_t egress_rows[32] = {0};               // cumulative rows per column file (marxio.c File_Pointers[].num_rows)
-
-   // pipelined egress
-   cudaStream_t copy_stream = nullptr;
-   cudaEvent_t ev_staged = nullptr, ev_copied = nullptr;
-   void *egress_slab = nullptr; uint64_t egress_cap = 0; PhotonSoA egress;
-   unsigned long long *h_egress_count = nullptr;      // pinned
-   bool egress_pending = false, egress_is_packed = false;
-   EgressPlan packed_plan; int packed_which[kMaxEgressCols]; uint64_t packed_cap = 0;
-
-   // Level-1 event transforms (marxb200_level1_*)
-   bool have_level1 = false;
-   Level1Dev L1;
-   Level1State *d_l1_state = nullptr;
-   void *l1_slab = nullptr; uint64_t l1_cap = 0; Level1Cols l1_cols;
-   uint32_t *d_l1_head = nullptr, *d_l1_tile_head = nullptr;
-   float *d_l1_next_dither = nullptr; long long *d_l1_next_expno = nullptr; unsigned int *d_l1_error = nullptr;
-   uint64_t l1_rows = 0;                         // rows of the last transform (what marxb200_level1_download returns)
-
-   // optional per-kernel timing
-   bool profiling = false;
-   cudaEvent_t ev_prev = nullptr;
-   std::vector<std::pair<cudaEvent_t, int>> ev_marks;   // (event recorded after a kernel, class)
-   std::vector<cudaEvent_t> ev_pool;
-   double prof_ms[MARXB200_NUM_KERNEL_CLASSES] = {0};
-   uint64_t prof_n[MARXB200_NUM_KERNEL_CLASSES] = {0};
-};
+#define fail mxb_fail
 
 static cudaEvent_t prof_event (marxb200_ctx *c)
 {
@@ -242,6 +162,7 @@ extern "C" int marxb200_destroy (marxb200_ctx *c)
    if (c == nullptr) return -1;
    cudaSetDevice (c->device);
    cudaDeviceSynchronize ();
+   mxb_comm_release (c);
    prof_collect (c);
    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy (e);
    for (void *p : c->allocs) cudaFree (p);
@@ -782,6 +703,7 @@ extern "C" int marxb200_restore_order (marxb200_ctx *c)
 
 // marx_create_photons + HRMA phase A in one kernel (only the compacting path; the in-place parity mode and the
 // stage-by-stage API keep the separate kernels)
+static int enter_mirror_after_scan (marxb200_ctx *c, const SourceArgs &a);
 static int create_and_enter_mirror (marxb200_ctx *c, uint64_t first_ray, uint64_t n, double time_base_in)
 {
    if (!c->have_source) return fail ("marxb200_trace: no source set");
@@ -793,6 +715,14 @@ static int create_and_enter_mirror (marxb200_ctx *c, uint64_t first_ray, uint64_
    prof_begin (c);
    launch_time_sums (a, c->stream); prof_mark (c, 0);
    launch_time_scan (a, c->stream); prof_mark (c, 1);    // also sets d_counts[0] = n
+   c->launches += 4;                     // k0_time_sums, k0_time_super/_bases/_tiles
+   return enter_mirror_after_scan (c, a);
+}
+
+// k01_source_hrma behind a finished arrival-time scan (tile bases, batch start and count on the device)
+static int enter_mirror_after_scan (marxb200_ctx *c, const SourceArgs &a)
+{
+   const uint64_t n = a.n;
    StageArgs st;
    memset (&st, 0, sizeof (st));
    st.out = c->buf[1];
@@ -802,7 +732,7 @@ static int create_and_enter_mirror (marxb200_ctx *c, uint64_t first_ray, uint64_
    CUDA_OK (cudaMemsetAsync (c->d_counts + 4, 0, sizeof (unsigned long long), c->stream));
    prof_begin (c);
    launch_source_hrma (a, st, c->grid01, c->stream); prof_mark (c, 3);
-   c->launches += 5;                     // k0_time_sums, k0_time_super/_bases/_tiles, k01_source_hrma
+   c->launches += (n != 0) ? 1 : 0;      // k01_source_hrma
    CUDA_OK (cudaGetLastError ());
    c->cur = 1; c->stage_done = 0; c->n_generated = n; c->ordered = false;
    c->first_mirror_kernel = 1;
@@ -1054,10 +984,9 @@ extern "C" int marxb200_tally_device_ptr (marxb200_ctx *c, int id, void **dev_pt
 // the reference's (32-byte header marxio.c:151-205 + big-endian column data), without the AoS detour and without one
 // fwrite per photon per column.
 // ---------------------------------------------------------------------------------------------
-namespace {
-struct EgressCol { uint64_t mask; const char *file, *colname; char type; int kind; int size; };
+typedef MxEgressCol EgressCol;
 // Outfile_Info_Table, marxio.c:292-322 (same files, names, type letters)
-const EgressCol kEgressCols[] = {
+extern const MxEgressCol kMxEgressCols[] = {
    {MARXB200_PI_OK, "b_energy.dat", "B_ENERGY", 'E', EGRESS_PI, 4},
    {MARXB200_ENERGY_OK, "energy.dat", "ENERGY", 'E', EGRESS_ENERGY, 4},
    {MARXB200_TIME_OK, "time.dat", "TIME", 'E', EGRESS_TIME, 4},
@@ -1088,8 +1017,11 @@ const EgressCol kEgressCols[] = {
    {MARXB200_DET_DITHER_OK, "det_dz.dat", "DET_DZ", 'E', EGRESS_DET_DZ, 4},
    {MARXB200_DET_DITHER_OK, "det_theta.dat", "DET_THETA", 'E', EGRESS_DET_THETA, 4},
 };
-constexpr int kNumEgressCols = (int) (sizeof (kEgressCols) / sizeof (kEgressCols[0]));
+#define kEgressCols kMxEgressCols
+constexpr int kNumEgressCols = (int) (sizeof (kMxEgressCols) / sizeof (kMxEgressCols[0]));
+extern const int kMxNumEgressCols = kNumEgressCols;
 static_assert (kNumEgressCols <= kMaxEgressCols, "EgressPlan too small");
+namespace {
 
 void put_be32 (unsigned char *b, uint32_t v) { b[0] = (unsigned char) (v >> 24); b[1] = (unsigned char) (v >> 16); b[2] = (unsigned char) (v >> 8); b[3] = (unsigned char) v; }
 }
@@ -1660,6 +1592,39 @@ extern "C" int marxb200_pileup_run (marxb200_ctx *c, uint64_t n, const marxb200_
    cudaStreamSynchronize (c->stream);
    c->ev_pool.push_back (e0); c->ev_pool.push_back (e1);
    return status;
+}
+
+// ---------------------------------------------------------------------------------------------
+// helpers shared with comm.cu (mx_context.hpp)
+// ---------------------------------------------------------------------------------------------
+void mxb_prof_begin (marxb200_ctx *c) { prof_begin (c); }
+void mxb_prof_mark (marxb200_ctx *c, int cls) { prof_mark (c, cls); }
+int mxb_ensure_order (marxb200_ctx *c) { return ensure_order (c); }
+PhotonSoA mxb_observed (const marxb200_ctx *c, const PhotonSoA &b) { return observed (c, b); }
+void mxb_fill_source_args (marxb200_ctx *c, SourceArgs &a, uint64_t first_ray, uint64_t n, double time_base) { fill_source_args (c, a, first_ray, n, time_base); }
+int mxb_enter_mirror_after_scan (marxb200_ctx *c, const SourceArgs &a) { return enter_mirror_after_scan (c, a); }
+int mxb_finish_trace (marxb200_ctx *c)
+{
+   if (-1 == marxb200_mirror_reflect (c)) return -1;
+   if (-1 == marxb200_grating_diffract (c)) return -1;
+   if (-1 == marxb200_detect (c)) return -1;
+   return ensure_order (c);
+}
+// every selected column in a fixed region of align16 (rows_per_col * size) bytes; returns the total size
+uint64_t mxb_build_egress_plan (uint64_t write_mask, uint64_t rows_per_col, EgressPlan &plan, int *which)
+{
+   memset (&plan, 0, sizeof (plan));
+   uint64_t total = 0;
+   for (int k = 0; k < kNumEgressCols; k++)
+     {
+        if (0 == (kEgressCols[k].mask & write_mask)) continue;
+        if (which) which[plan.num_cols] = k;
+        plan.kind[plan.num_cols] = kEgressCols[k].kind;
+        plan.offset[plan.num_cols] = total;
+        plan.num_cols++;
+        total += (uint64_t) align16 ((size_t) rows_per_col * kEgressCols[k].size);
+     }
+   return total;
 }
 
 extern "C" int marxb200_load_calpack_impl (marxb200_ctx *ctx, const char *path, char *errbuf, size_t errlen);

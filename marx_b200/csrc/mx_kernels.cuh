@@ -115,6 +115,9 @@ struct SourceArgs
 
 void launch_time_sums (const SourceArgs &a, cudaStream_t s);
 void launch_time_scan (const SourceArgs &a, cudaStream_t s);
+void launch_time_super (const SourceArgs &a, cudaStream_t s);                 // multi-GPU scan, first half: k0_time_super
+// second half, behind the all-gather of the super-tile sums: k0_time_bases_sharded + k0_time_tiles
+void launch_time_bases_sharded (const SourceArgs &a, const double *all_sums, int rank, int world, uint32_t ns_blk, cudaStream_t s);
 void launch_source (const SourceArgs &a, cudaStream_t s);
 void launch_exposure_truncate (const PhotonSoA &buf, unsigned long long *n, double *dev_times, double limit, int inclusive, cudaStream_t s);
 void launch_hrma (const StageArgs &a, int phase, int grid, cudaStream_t s);

@@ -28,7 +28,37 @@ def test_library_exports_every_declared_symbol():
     lib = C.CDLL(marx_b200.lib_path())
     for name in EXPORTED_SYMBOLS:
         assert hasattr(lib, name), name
-    assert marx_b200.load_library().marxb200_abi_version() == 1
+    assert marx_b200.load_library().marxb200_abi_version() == 2
+
+
+@pytest.mark.skipif(not _built(), reason="libmarxb200.so not built")
+def test_shard_of_partitions_the_ray_range():
+    """marxb200_shard_of (the block rule of marxb200_trace_sharded): contiguous, super-tile aligned, ragged/empty at the end"""
+    from marx_b200.api import shard_of
+    for first, n_total, world in [(0, 1 << 24, 8), (12345 * 65536, 10**7, 8), (7, 1000, 2), (0, 65536 * 3 + 5, 4), (1 << 40, 10**9, 3),
+                                  (0, 1, 8), (0, 65536 * 8, 8), (0, 65536 * 8 + 1, 8)]:
+        blocks = [shard_of(first, n_total, r, world) for r in range(world)]
+        pos = first
+        for f, n in blocks:
+            assert f >= pos and (f == pos or n == 0)          # contiguous; empty blocks sit at the end
+            assert (f - first) % 65536 == 0                    # blocks start on super-tile boundaries of the step
+            pos = f + n if n else pos
+        assert sum(n for _, n in blocks) == n_total and pos == first + n_total
+        sizes = [n for _, n in blocks if n]
+        assert all(s == sizes[0] for s in sizes[:-1]) and sizes[-1] <= sizes[0] and sizes[0] % 65536 == 0 or len(sizes) == 1
+    with pytest.raises(marx_b200.MarxB200Error):
+        shard_of(0, 10, 3, 2)
+
+
+@pytest.mark.skipif(not _built(), reason="libmarxb200.so not built")
+def test_comm_unique_id_needs_no_gpu():
+    """the id hand-over half of marxb200_comm_init works on a CPU box (NCCL is opened with dlopen at run time)"""
+    from marx_b200.api import comm_unique_id, COMM_ID_BYTES
+    try:
+        a, b = comm_unique_id(), comm_unique_id()
+    except marx_b200.MarxB200Error as e:
+        pytest.skip("no NCCL library on this box: %s" % e)
+    assert len(a) == len(b) == COMM_ID_BYTES and a != b
 
 
 @pytest.mark.skipif(not _built(), reason="libmarxb200.so not built")

@@ -1,15 +1,6 @@
-cd /root/repo
 mkdir -p gpurun_out
-L=gpurun_out/call55_k2sel_variants.log
-: > $L
-for v in default MB8 ILP2 ILP2MB6; do
-  lib=/root/repo/build/variants/libmarxb200_$v.so
-  [ "$v" = default ] && lib=/root/repo/marx_b200/libmarxb200.so
-  for cfg in c2_hetg_acis_s c3_letg_hrc_s; do
-    MARXB200_LIB=$lib timeout 60 python tools/trace_probe.py 16777216 $cfg 6 2>&1 | cut -c1-330 >> $L
-  done
-done
-for v in ILP2 ILP2MB6; do
-  ( MARXB200_LIB=/root/repo/build/variants/libmarxb200_$v.so timeout 120 python -m pytest tests/test_gpu_golden.py tests/test_gpu_oracle.py -q -m gpu -x -k "compacted" 2>&1 | tail -3 ) >> gpurun_out/call55_tests.log
-done
-cat gpurun_out/call55_tests.log
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/c1_smi.txt 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k01_source_hrma|k1_hrma|k2_select|k2_grating|k3_acis" -s 7 -c 7 -o gpurun_out/prof_r02a python tools/ncu_probe.py 16777216 c2_hetg_acis_s 2 > gpurun_out/c1_ncu.log 2>&1
+ls -la gpurun_out/ >> gpurun_out/c1_ncu.log
+timeout 300 python bench.py --steps 20 --warmup 3 --no-pileup --no-level1 > gpurun_out/c1_bench.json 2> gpurun_out/c1_bench.err
+tail -c 600 gpurun_out/c1_bench.json
