@@ -367,8 +367,21 @@ def reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def phase(msg):
+    """progress marker on stderr (MARXB200_BENCH_TRACE=1): where a multi-rank run stands if it ever stalls"""
+    if os.environ.get("MARXB200_BENCH_TRACE"):
+        sys.stderr.write("[bench rank %s %.1fs] %s\n" % (os.environ.get("RANK", "0"), time.time() - phase.t0, msg))
+        sys.stderr.flush()
+
+
+phase.t0 = time.time()
+
+
 def cuda_arm(args):
+    import faulthandler
     import numpy as np
+    if os.environ.get("MARXB200_BENCH_HANG_S"):
+        faulthandler.dump_traceback_later(float(os.environ["MARXB200_BENCH_HANG_S"]), exit=True)
     import torch
     import torch.distributed as dist
     import marx_b200
@@ -414,7 +427,9 @@ def cuda_arm(args):
         if rank == 0:
             idt.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, src=0)
+        phase("id broadcast done")
         m.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+        phase("comm_init done")
     merge_log = []
 
     def one_step(step):
@@ -471,13 +486,16 @@ def cuda_arm(args):
         time.sleep(1.0)                       # let nvidia-smi come up; it samples every 100 ms from then on
     for _ in range(max(args.warmup, 3)):
         one_step(timed.step); timed.step += 1
+    phase("warm-up steps launched")
     if world > 1:
         timed(2, e2e=False, merge=True)       # sets up the merge buffers (collective: IPC mapping of rank 0's buffer)
         merge_log.clear()
     if rank == 0:
         sampler.mark()                        # only samples taken from here on count
     # `value`: at N > 1 the NVLink merge of every step's event lists is inside the timed region
+    phase("merge set up")
     ms, launches, _ = timed(args.steps, e2e=False, merge=(world > 1))
+    phase("value timed")
     clocks = sampler.stop() if rank == 0 else None
     merge_steps = list(merge_log)
     ms_nomerge = timed(args.steps, e2e=False)[0] if world > 1 else ms
@@ -498,8 +516,10 @@ def cuda_arm(args):
     stage_ms = ([per["k0_time_sums"] + per["k0_time_scan"], per["k01_source_hrma"]] + [per[k] for k in k1_names]
                 + [per["k2_grating"], per["k3_detect"], per["order_restore"]])
     # e2e leg
+    phase("profiled run done")
     timed(2, e2e=True)
     ms_e2e, _, n_events = timed(args.steps, e2e=True)
+    phase("e2e timed")
 
     # host-copy ceiling of this box (collective): 128 MB pinned D2H copies, every rank alone in turn, then all ranks at once --
     # the bound of `e2e` when 8 ranks land 89 MB per step each in host memory
@@ -510,6 +530,7 @@ def cuda_arm(args):
         except Exception as e:  # noqa: BLE001
             d2h = {"unavailable": str(e)[:200]}
 
+    phase("d2h probe done")
     # C5: throughput sweep 1e7 ... 1e11 generated rays (collective)
     sweep = None
     if not args.no_sweep:
@@ -517,6 +538,7 @@ def cuda_arm(args):
 
     # Level-1 leg (marx2fits' per-event transforms on the device-resident list): the events of the last batch,
     # measured on its own after the timed regions above -- it is not part of `value` / `e2e`
+    phase("sweep done")
     one_step(timed.step); timed.step += 1     # a full batch again (the sweep ends on a short one); collective at N > 1
     level1 = None
     if rank == 0 and not args.no_level1:
@@ -546,7 +568,17 @@ def cuda_arm(args):
         except Exception:  # noqa: BLE001
             fp64_peak, fp64_src = 37.0, "datasheet (measurement failed)"
     comm_info = m.comm_info() if world > 1 else None
+    push_rates = None
+    if world > 1:
+        mine = [x for x in merge_steps if x["copy_ms"] > 0 and x["nvlink_bytes"] > 0]
+        rate = (sum(x["nvlink_bytes"] for x in mine) / (sum(x["copy_ms"] for x in mine) * 1e-3) / 1e9) if (mine and rank != 0) else None
+        push_rates = [None] * world
+        dist.all_gather_object(push_rates, rate)
+    phase("legs done")
+    if world > 1:
+        barrier()                             # every rank leaves the communicator together
     m.close()
+    phase("context closed")
 
     # the other BASELINE.json configurations (C1, C3, C4), device resident, same step size: driver-visible numbers
     configs = None
@@ -654,6 +686,7 @@ def cuda_arm(args):
         recv = [x for x in merge_steps if x["nvlink_bytes"] > 0 and x["transfer_ms"] > 0]
         tot_b = sum(x["nvlink_bytes"] for x in recv)
         tot_ms = sum(x["transfer_ms"] for x in recv)
+        src = [g for g in push_rates[1:] if g]
         line["merge"] = {"what": "every step's per-GPU event lists concatenated in arrival order in rank 0's HBM (marxb200_merge_events_begin/"
                                  "_end, reference analogue marxcat.c:505-535), inside the timed region of `value`, overlapped with the next step",
                          "transport": comm_info["merge_transport"], "nccl_version": comm_info["nccl_version"],
@@ -661,6 +694,12 @@ def cuda_arm(args):
                          "nvlink_bytes_per_step_into_rank0": tot_b / max(len(recv), 1),
                          "transfer_ms_per_step": tot_ms / max(len(recv), 1),
                          "achieved_nvlink_gbs_into_rank0": (tot_b / (tot_ms * 1e-3) / 1e9) if tot_ms > 0 else None,
+                         "transfer_ms_note": "rank 0's merge-stream time from the start of its own copy to the end of the closing barrier: "
+                                             "includes waiting for the slowest source rank",
+                         "source_push_gbs_per_rank": src,
+                         "source_push_gbs_sum": sum(src) if src else None,
+                         "source_push_note": "each source rank's bytes / the CUDA-event time of its own copy-engine writes into rank 0's "
+                                             "buffer (21 columns, one cudaMemcpyAsync each); measured peer-copy reference 770 GB/s per direction",
                          "value_without_merge": total_rays / (ms_nomerge * 1e-3),
                          "time_base_exchange": "ncclAllGather of the pre-pass's per-65536-ray sums inside marxb200_trace_sharded, added in "
                                                "global ray order on every GPU (no host round trip)"}

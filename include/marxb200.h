@@ -576,9 +576,12 @@ int marxb200_aspsol_rows (marxb200_ctx *ctx, const marxb200_aspsol_desc *desc, u
  * tests, in list order.  Here draw k (0, 1, ...) of exposure frame F is lane k&3 of Philox4x32-10 (key = seed, counter =
  * (F, 0, k >> 2, 5)) mapped to [0,1] as jdmath/src/random.c:151-154, so frames are independent.
  *
- * All pointers are HOST pointers; any output pointer may be NULL.  At most max_out rows are written (more rows than that: error).
- * A frame longer than 65536 events is refused (every event walks its own frame's run of the list).  device_ms (or NULL): duration
- * of the eight kernels from CUDA events on the context's stream.
+ * All pointers are HOST pointers (pinned memory makes the copies run at the PCIe rate); any output pointer may be NULL.  At most
+ * max_out rows are written (more rows than that: error).  Lists whose exposure frames hold up to 513 events run as ONE kernel with
+ * the frames staged in shared memory; longer frames take the eight step kernels (every event walks its own frame's run of the list,
+ * O(frame length) each), and a frame longer than 65536 events is refused -- a limit the reference does not have (its per-CCD pixel
+ * maps make a frame O(events)), stated here because a source that bright is outside the model's validity anyway.  Lists of 2^32 - 1
+ * or more events are refused.  device_ms (or NULL): duration of the kernels from CUDA events on the context's stream.
  * ------------------------------------------------------------------------------------------------ */
 typedef struct
 {
@@ -594,6 +597,12 @@ typedef struct
 marxb200_pileup_out;
 int marxb200_pileup_run (marxb200_ctx *ctx, uint64_t n, const marxb200_pileup_in *in, double alpha, double frame_time, uint64_t seed,
                          uint64_t max_out, const marxb200_pileup_out *out, uint64_t *n_out, double *device_ms);
+/* The same for the event list the detector stage left on the device (behind marxb200_detect / marxb200_trace): `marx` followed by
+ * `marxpileup` without the column files in between.  The input columns are what marx_write_photons would have written for that
+ * list -- chip id, chip pixels, TIME = (float) (arrival_time + total_time), the PI energy of b_energy.dat, the six dither values
+ * (marxio.c:217-290) -- gathered on the device; results are identical to marxb200_pileup_run on those files' contents. */
+int marxb200_pileup_events (marxb200_ctx *ctx, double total_time, double alpha, double frame_time, uint64_t seed,
+                            uint64_t max_out, const marxb200_pileup_out *out, uint64_t *n_out, double *device_ms);
 
 /* ------------------------------------------------------------------------------------------------
  * Multi-GPU: one process per GPU, the exchanges run on device buffers over NVLink / NVSwitch inside this library
@@ -643,7 +652,8 @@ typedef struct
    char file[32][16];
    char type[32];
    uint32_t elem_size[32];
-   double transfer_ms;                      /* this rank's transfers + the closing barrier, CUDA events on the merge stream */
+   double transfer_ms;                      /* this rank's transfers + the closing barrier (waits for the slowest rank), CUDA events on the merge stream */
+   double copy_ms;                          /* this rank's transfers alone: a source rank's nvlink_bytes / copy_ms is its achieved NVLink rate */
    uint64_t nvlink_bytes;                   /* bytes this rank moved over NVLink: received (destination) or sent */
 }
 marxb200_merged_layout;

@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "marxb200_tally_create", "marxb200_tally_accumulate", "marxb200_tally_reset", "marxb200_tally_read", "marxb200_tally_device_ptr",
     "marxb200_set_level1", "marxb200_level1_reset", "marxb200_level1_transform", "marxb200_level1_download",
     "marxb200_aspsol_rows",
-    "marxb200_pileup_run",
+    "marxb200_pileup_run", "marxb200_pileup_events",
     "marxb200_comm_get_unique_id", "marxb200_comm_init", "marxb200_comm_init_file", "marxb200_comm_info", "marxb200_comm_destroy",
     "marxb200_shard_of", "marxb200_trace_sharded", "marxb200_tally_allreduce",
     "marxb200_merge_events_begin", "marxb200_merge_events_end", "marxb200_merge_download", "marxb200_probe_d2h",
@@ -132,6 +132,7 @@ def load_library():
         "marxb200_get_launch_count": [vp, C.POINTER(u64)],
         "marxb200_aspsol_rows": [vp, vp, u64, u64, vp, vp, C.POINTER(dbl)],
         "marxb200_pileup_run": [vp, u64, vp, dbl, dbl, u64, u64, vp, C.POINTER(u64), C.POINTER(dbl)],
+        "marxb200_pileup_events": [vp, dbl, dbl, dbl, u64, u64, vp, C.POINTER(u64), C.POINTER(dbl)],
         "marxb200_egress_begin": [vp, u64],
         "marxb200_egress_end": [vp, vp, C.POINTER(u64)],
         "marxb200_write_photons": [vp, C.c_char_p, u64, i32, dbl],
@@ -177,7 +178,8 @@ class _MergedLayout(C.Structure):
     _fields_ = [("num_cols", C.c_uint32), ("world", C.c_uint32), ("dst_rank", C.c_uint32), ("transport", C.c_uint32),
                 ("n_rows", C.c_uint64), ("rows_of_rank", C.c_uint64 * 64), ("device_base", C.c_void_p),
                 ("device_offset", C.c_uint64 * 32), ("mask", C.c_uint64 * 32), ("file", (C.c_char * 16) * 32),
-                ("type", C.c_char * 32), ("elem_size", C.c_uint32 * 32), ("transfer_ms", C.c_double), ("nvlink_bytes", C.c_uint64)]
+                ("type", C.c_char * 32), ("elem_size", C.c_uint32 * 32), ("transfer_ms", C.c_double), ("copy_ms", C.c_double),
+                ("nvlink_bytes", C.c_uint64)]
 
 
 COMM_ID_BYTES = 128
@@ -368,7 +370,8 @@ class MarxB200:
         lay = _MergedLayout()
         self._check(self._lib.marxb200_merge_events_end(self._ctx, C.byref(lay)))
         return {"n_rows": int(lay.n_rows), "rows_of_rank": [int(lay.rows_of_rank[r]) for r in range(lay.world)],
-                "transport": int(lay.transport), "transfer_ms": float(lay.transfer_ms), "nvlink_bytes": int(lay.nvlink_bytes),
+                "transport": int(lay.transport), "transfer_ms": float(lay.transfer_ms), "copy_ms": float(lay.copy_ms),
+                "nvlink_bytes": int(lay.nvlink_bytes),
                 "device_base": lay.device_base, "columns": [lay.file[j].value.decode() for j in range(lay.num_cols)]}
 
     def merge_download(self, host):
@@ -524,28 +527,48 @@ class MarxB200:
 
     PILEUP_DITHER = ("sky_ra", "sky_dec", "sky_roll", "det_dy", "det_dz", "det_theta")
 
-    def pileup(self, cols, alpha, frame_time, seed, max_out=None):
+    def pileup(self, cols, alpha, frame_time, seed, max_out=None, out=None):
         """ACIS pile-up on the event columns of a simulation (marxpileup's frame loop, marxpileup.c:1121-1213).  cols: dict with
         ccd (i8), x, y, t, benergy (f32) and optionally the six dither columns, in file order; frame_time = FrameTime +
         FrameTransferTime.  -> (dict of the output columns write_event :622-666 writes, milliseconds of the device kernels)"""
         n = len(cols["t"])
-        keep = {"ccd": np.ascontiguousarray(cols["ccd"], dtype=np.int8)}
+        keep = {"ccd": np.ascontiguousarray(cols["ccd"], dtype=np.int8)}     # no copy when the caller's (pinned) array already fits
         for k in ("x", "y", "t", "benergy") + tuple(d for d in self.PILEUP_DITHER if d in cols):
             keep[k] = np.ascontiguousarray(cols[k], dtype=np.float32)
             assert len(keep[k]) == n
         ptr = lambda a: a.ctypes.data if a is not None else None  # noqa: E731
         pin = (C.c_void_p * 11)(*[ptr(keep.get(k)) for k in ("ccd", "x", "y", "t", "benergy") + self.PILEUP_DITHER])
         cap = n if max_out is None else int(max_out)
-        out = {"ccd": np.zeros(cap, np.int8), "x": np.zeros(cap, np.float32), "y": np.zeros(cap, np.float32), "t": np.zeros(cap, np.float32),
-               "benergy": np.zeros(cap, np.float32), "frame": np.zeros(cap, np.int32), "nphotons": np.zeros(cap, np.int16),
-               "pha": np.zeros(cap, np.int16)}
-        for d in self.PILEUP_DITHER:
-            if d in keep:
-                out[d] = np.zeros(cap, np.float32)
+        if out is None:
+            out = {"ccd": np.zeros(cap, np.int8), "x": np.zeros(cap, np.float32), "y": np.zeros(cap, np.float32), "t": np.zeros(cap, np.float32),
+                   "benergy": np.zeros(cap, np.float32), "frame": np.zeros(cap, np.int32), "nphotons": np.zeros(cap, np.int16),
+                   "pha": np.zeros(cap, np.int16)}
+            for d in self.PILEUP_DITHER:
+                if d in keep:
+                    out[d] = np.zeros(cap, np.float32)
         pout = (C.c_void_p * 14)(*[ptr(out.get(k)) for k in ("ccd", "x", "y", "t", "benergy", "frame", "nphotons", "pha") + self.PILEUP_DITHER])
         got, ms = C.c_uint64(), C.c_double()
         self._check(self._lib.marxb200_pileup_run(self._ctx, n, pin, float(alpha), float(frame_time), int(seed), cap, pout,
                                                   C.byref(got), C.byref(ms)))
+        return {k: v[:got.value] for k, v in out.items()}, ms.value
+
+    def pileup_events(self, total_time, alpha, frame_time, seed, max_out=None, out=None):
+        """marxb200_pileup_events: the pile-up model on the event list the detector stage left on the device (no column files in
+        between).  -> (dict of output columns incl. the six dither columns, milliseconds of the device kernels)"""
+        _, live, _ = self.counts()
+        cap = int(live) if max_out is None else int(max_out)
+        cap = max(cap, 1)
+        if out is None:
+            out = {"ccd": np.zeros(cap, np.int8), "x": np.zeros(cap, np.float32), "y": np.zeros(cap, np.float32), "t": np.zeros(cap, np.float32),
+                   "benergy": np.zeros(cap, np.float32), "frame": np.zeros(cap, np.int32), "nphotons": np.zeros(cap, np.int16),
+                   "pha": np.zeros(cap, np.int16)}
+            for d in self.PILEUP_DITHER:
+                out[d] = np.zeros(cap, np.float32)
+        ptr = lambda a: a.ctypes.data if a is not None else None  # noqa: E731
+        pout = (C.c_void_p * 14)(*[ptr(out.get(k)) for k in ("ccd", "x", "y", "t", "benergy", "frame", "nphotons", "pha") + self.PILEUP_DITHER])
+        got, ms = C.c_uint64(), C.c_double()
+        self._check(self._lib.marxb200_pileup_events(self._ctx, float(total_time), float(alpha), float(frame_time), int(seed), cap, pout,
+                                                     C.byref(got), C.byref(ms)))
         return {k: v[:got.value] for k, v in out.items()}, ms.value
 
     def download_columns(self, names=("energy", "time", "chipx", "chipy", "pha", "ccd", "order", "ray"), out=None):

@@ -6,6 +6,7 @@
 //               that the 19 words of 256 rows leave the CTA as one contiguous, coalesced store.
 //   The kernel is compute bound by construction (76 B written per ~1.2e3 FP64 operations); it is sized like the stage kernels
 //   (grid = SMs x resident CTAs, grid-stride over 256-row tiles).
+#define MX_MATH 0      // the aspect-solution rows keep libdevice sin / cos (tests/test_gpu_marxasp.py pins them at 3e-13 deg)
 #include <cuda_runtime.h>
 #include "mx_aspsol.cuh"
 

@@ -48,8 +48,9 @@ struct Pack
       FILE *fp = fopen (path, "rb");
       if (!fp) { err = std::string ("cannot open ") + path; return false; }
       fseek (fp, 0, SEEK_END); long sz = ftell (fp); fseek (fp, 0, SEEK_SET);
+      if (sz < 16) { fclose (fp); err = (sz < 0) ? "cannot determine the file size" : "file too short"; return false; }
       bytes.resize ((size_t) sz);
-      if (sz < 16 || fread (bytes.data (), 1, (size_t) sz, fp) != (size_t) sz) { fclose (fp); err = "short read"; return false; }
+      if (fread (bytes.data (), 1, (size_t) sz, fp) != (size_t) sz) { fclose (fp); err = "short read"; return false; }
       fclose (fp);
       if (memcmp (bytes.data (), MARXB200_CALPACK_MAGIC, 8)) { err = "bad magic"; return false; }
       uint32_t n; memcpy (&n, bytes.data () + 8, 4);
@@ -61,8 +62,9 @@ struct Pack
            Entry e; memcpy (&e.dtype, bytes.data () + off + MARXB200_CALPACK_NAMELEN, 4);
            memcpy (&e.count, bytes.data () + off + MARXB200_CALPACK_NAMELEN + 8, 8);
            off += MARXB200_CALPACK_NAMELEN + 16;
-           size_t nb = (size_t) e.count * mxcp_dtype_size (e.dtype);
-           if (off + nb > bytes.size ()) { err = "truncated data"; return false; }
+           const size_t esz = mxcp_dtype_size (e.dtype);
+           if ((esz == 0) || (e.count > (bytes.size () - off) / esz)) { err = "truncated data"; return false; }   // no count * size overflow
+           size_t nb = (size_t) e.count * esz;
            e.data = bytes.data () + off;
            off += (nb + 7) & ~(size_t) 7;
            entries[name] = e;
@@ -193,6 +195,12 @@ extern "C" int marxb200_load_calpack_impl (marxb200_ctx *ctx, const char *path, 
                 GET (wt, std::string (base) + ".theta", MXCP_F32, 0);
                 marxb200_wfold_table &w = ph ? h.h_wfold : h.p_wfold;
                 uint32_t na = (uint32_t) wn->count;
+                if (wh->count < 6ull * na) return bail (std::string (base) + ".hdr holds fewer than 6 values per array");
+                {
+                   uint64_t total = 0;
+                   for (uint32_t i = 0; i < na; i++) total += ((const uint32_t *) wn->data)[i];
+                   if (total > wt->count) return bail (std::string (base) + ".theta is shorter than the sum of num_theta");
+                }
                 const double *hdr = (const double *) wh->data;
                 size_t c0 = wf_cols.size ();
                 for (int col = 0; col < 6; col++)
@@ -236,6 +244,7 @@ extern "C" int marxb200_load_calpack_impl (marxb200_ctx *ctx, const char *path, 
              s.num_orders = (uint32_t) ol->count; s.order_list = (const int32_t *) ol->data;
              s.num_energies = (uint32_t) en->count; s.energies = (const float *) en->data;
              s.cum_eff = (const float *) ce->data;
+             if (sc->count % 6 != 0) return bail (nm ("grating.shell%d.sectors is not a multiple of 6 values", k));
              uint32_t ns = (uint32_t) (sc->count / 6);
              const double *sec = (const double *) sc->data;
              size_t c0 = sec_cols.size ();

@@ -106,7 +106,7 @@ struct MxComm
    double *d_all_sums = nullptr; uint64_t all_sums_cap = 0;        // [world][ns_blk]
    // event merge
    cudaStream_t merge_stream = nullptr;
-   cudaEvent_t ev_packed = nullptr, ev_counts = nullptr, ev_pushed = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+   cudaEvent_t ev_packed = nullptr, ev_counts = nullptr, ev_pushed = nullptr, ev_t0 = nullptr, ev_tc = nullptr, ev_t1 = nullptr;
    unsigned long long *d_all_counts = nullptr, *h_all_counts = nullptr;     // [world]; pinned host copy
    int *d_flag = nullptr;                                                   // barrier / agreement scratch
    int dst = -1; uint64_t max_rows = 0, mask = 0;
@@ -119,7 +119,7 @@ struct MxComm
    bool pending = false;
    uint64_t total_rows = 0;                   // of the last finished merge
    uint64_t counts[64];
-   float last_ms = 0.f; uint64_t last_bytes = 0;
+   float last_ms = 0.f, last_copy_ms = 0.f; uint64_t last_bytes = 0;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -146,7 +146,7 @@ void mxb_comm_release (marxb200_ctx *c)
    NcclApi *N = nccl_api ();
    merge_release (c);
    if (m->merge_stream) cudaStreamDestroy (m->merge_stream);
-   for (cudaEvent_t e : {m->ev_packed, m->ev_counts, m->ev_pushed, m->ev_t0, m->ev_t1}) if (e) cudaEventDestroy (e);
+   for (cudaEvent_t e : {m->ev_packed, m->ev_counts, m->ev_pushed, m->ev_t0, m->ev_tc, m->ev_t1}) if (e) cudaEventDestroy (e);
    if (m->d_all_sums) cudaFree (m->d_all_sums);
    if (m->d_all_counts) cudaFree (m->d_all_counts);
    if (m->h_all_counts) cudaFreeHost (m->h_all_counts);
@@ -197,6 +197,7 @@ extern "C" int marxb200_comm_init (marxb200_ctx *c, const void *id, int rank, in
         INIT_OK (cudaEventCreateWithFlags (&m->ev_counts, cudaEventDisableTiming), "event");
         INIT_OK (cudaEventCreateWithFlags (&m->ev_pushed, cudaEventDisableTiming), "event");
         INIT_OK (cudaEventCreate (&m->ev_t0), "event");
+        INIT_OK (cudaEventCreate (&m->ev_tc), "event");
         INIT_OK (cudaEventCreate (&m->ev_t1), "event");
         INIT_OK (cudaMalloc (&m->d_all_counts, 64 * sizeof (unsigned long long)), "cudaMalloc");
         INIT_OK (cudaMallocHost (&m->h_all_counts, 64 * sizeof (unsigned long long)), "cudaMallocHost");
@@ -486,6 +487,7 @@ extern "C" int marxb200_merge_events_end (marxb200_ctx *c, marxb200_merged_layou
              CUDA_OK (cudaMemcpyAsync (target + m->merged_off[j] + row0[m->rank] * sz, (const unsigned char *) m->stage + m->plan.offset[j],
                                        (size_t) (n_mine * sz), cudaMemcpyDefault, m->merge_stream));
           }
+        CUDA_OK (cudaEventRecord (m->ev_tc, m->merge_stream));
         // stream-ordered barrier: the destination's all-reduce completes only after every rank's, which follow their copies
         NCCL_OK (N->AllReduce (m->d_flag + 1, m->d_flag + 1, 1, NCCL_INT32, NCCL_MIN, m->comm_merge, m->merge_stream));
      }
@@ -517,6 +519,7 @@ extern "C" int marxb200_merge_events_end (marxb200_ctx *c, marxb200_merged_layou
                CUDA_OK (cudaMemcpyAsync (target + m->merged_off[j] + row0[dst] * sz, (const unsigned char *) m->stage + m->plan.offset[j],
                                          (size_t) (n_mine * sz), cudaMemcpyDeviceToDevice, m->merge_stream));
             }
+        CUDA_OK (cudaEventRecord (m->ev_tc, m->merge_stream));
      }
    CUDA_OK (cudaEventRecord (m->ev_t1, m->merge_stream));
    CUDA_OK (cudaEventRecord (m->ev_pushed, m->merge_stream));
@@ -524,6 +527,7 @@ extern "C" int marxb200_merge_events_end (marxb200_ctx *c, marxb200_merged_layou
    CUDA_OK (cudaStreamSynchronize (m->merge_stream));
    CUDA_OK (cudaGetLastError ());
    CUDA_OK (cudaEventElapsedTime (&m->last_ms, m->ev_t0, m->ev_t1));
+   CUDA_OK (cudaEventElapsedTime (&m->last_copy_ms, m->ev_t0, m->ev_tc));
    m->total_rows = row0[m->world];
    uint64_t row_bytes = 0;
    for (int j = 0; j < m->plan.num_cols; j++) row_bytes += (uint64_t) kMxEgressCols[m->which[j]].size;
@@ -545,7 +549,7 @@ extern "C" int marxb200_merge_events_end (marxb200_ctx *c, marxb200_merged_layou
              strncpy (layout->file[j], col.file, sizeof (layout->file[j]) - 1);
              layout->device_offset[j] = m->merged_off[j];
           }
-        layout->transfer_ms = m->last_ms; layout->nvlink_bytes = m->last_bytes;
+        layout->transfer_ms = m->last_ms; layout->copy_ms = m->last_copy_ms; layout->nvlink_bytes = m->last_bytes;
      }
    return 0;
 }

@@ -11,6 +11,7 @@
 // The reference walks the rows sequentially because "take the aspect over only when EXPNO changed" (marx2fits.c:3567-3580)
 // is a running state; on the device that state is the segmented broadcast above.  HRC data and --pixadj=exact take every
 // row's own aspect and skip the two scan kernels.  All loads and stores are unit-stride over the SoA columns.
+#define MX_MATH 0      // Level-1 keeps libdevice sin / cos: its sky-coordinate checks are pinned at the libdevice-vs-glibc level (tests/test_gpu_level1.py)
 #include <cuda_runtime.h>
 #include "mx_level1.cuh"
 #include "mx_kernels.cuh"

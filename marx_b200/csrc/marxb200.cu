@@ -87,7 +87,7 @@ static int dev_upload (marxb200_ctx *c, const void *host, size_t bytes, void **o
    CUDA_OK (cudaMemsetAsync (d, 0, padded, c->stream));
    if (host != nullptr) CUDA_OK (cudaMemcpyAsync (d, host, bytes, cudaMemcpyHostToDevice, c->stream));
    CUDA_OK (cudaStreamSynchronize (c->stream));
-   c->allocs.push_back (d);
+   c->allocs.push_back (std::make_pair (d, c->alloc_tag));
    *out = d;
    return 0;
 }
@@ -97,6 +97,24 @@ template <class T> static int dev_upload_t (marxb200_ctx *c, const T *host, size
    if (-1 == dev_upload (c, host, n * sizeof (T), &d)) return -1;
    *out = (const T *) d;
    return 0;
+}
+// a module's setter runs again: release the tables of its previous call (the stream is drained first)
+static void begin_module (marxb200_ctx *c, int tag)
+{
+   bool any = false;
+   for (auto &p : c->allocs) if (p.second == tag) any = true;
+   if (any)
+     {
+        cudaStreamSynchronize (c->stream);
+        size_t k = 0;
+        for (size_t i = 0; i < c->allocs.size (); i++)
+          {
+             if (c->allocs[i].second == tag) cudaFree (c->allocs[i].first);
+             else c->allocs[k++] = c->allocs[i];
+          }
+        c->allocs.resize (k);
+     }
+   c->alloc_tag = tag;
 }
 static size_t align16 (size_t x) { return (x + 15) & ~(size_t) 15; }
 
@@ -136,6 +154,7 @@ extern "C" int marxb200_create (marxb200_ctx **ctxp, int device_ordinal, uint64_
    if ((device_ordinal < 0) || (device_ordinal >= ndev)) return fail ("marxb200_create: bad device ordinal %d", device_ordinal);
    CUDA_OK (cudaSetDevice (device_ordinal));
    marxb200_ctx *c = new marxb200_ctx ();
+   struct Guard { marxb200_ctx *c; ~Guard () { if (c) marxb200_destroy (c); } } guard{c};     // a failing CUDA call below frees what exists
    c->device = device_ordinal;
    c->seed = seed;
    if (const char *e = getenv ("MARXB200_K3_SPLIT")) c->k3_split = atoi (e);      // developer A/B switch
@@ -153,6 +172,7 @@ extern "C" int marxb200_create (marxb200_ctx **ctxp, int device_ordinal, uint64_
    CUDA_OK (cudaMemset (c->d_times, 0, 2 * sizeof (double)));
    memset (&c->S, 0, sizeof (c->S));
    memset (&c->D, 0, sizeof (c->D));
+   guard.c = nullptr;
    *ctxp = c;
    return 0;
 }
@@ -165,7 +185,8 @@ extern "C" int marxb200_destroy (marxb200_ctx *c)
    mxb_comm_release (c);
    prof_collect (c);
    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy (e);
-   for (void *p : c->allocs) cudaFree (p);
+   for (auto &p : c->allocs) cudaFree (p.first);
+   if (c->d_upload_ids) cudaFree (c->d_upload_ids);
    for (int i = 0; i < 2; i++) if (c->slab[i]) cudaFree (c->slab[i]);
    if (c->rc_slab) cudaFree (c->rc_slab);
    cudaFree (c->d_counts); cudaFree (c->d_ticket); cudaFree (c->d_times);
@@ -225,6 +246,7 @@ extern "C" int marxb200_set_source (marxb200_ctx *c, const marxb200_source_desc 
    if ((d->source_type < 0) || (d->source_type > 5)) return fail ("marxb200_set_source: source type %d is not implemented (POINT, GAUSS, BETA, DISK, LINE, IMAGE are)", d->source_type);
    if ((d->spectrum_type != 1) && (d->spectrum_type != 2)) return fail ("marxb200_set_source: unknown spectrum type %d", d->spectrum_type);
    CUDA_OK (cudaSetDevice (c->device));
+   begin_module (c, marxb200_ctx::TAG_SOURCE);
    SourceDev &S = c->S;
    memset (&S, 0, sizeof (S));
    S.source_type = d->source_type; S.spectrum_type = d->spectrum_type;
@@ -260,6 +282,8 @@ extern "C" int marxb200_set_dither (marxb200_ctx *c, const marxb200_dither_desc 
    if ((c == nullptr) || (d == nullptr)) return fail ("marxb200_set_dither: NULL argument");
    if ((d->mode < 0) || (d->mode > 2)) return fail ("marxb200_set_dither: unknown dither model %d", d->mode);
    DitherDev &D = c->D;
+   CUDA_OK (cudaSetDevice (c->device));
+   begin_module (c, marxb200_ctx::TAG_DITHER);
    if ((D.mode == 2) && (d->mode != 2)) c->det_dither_dirty = true;   // the per-ray detector-dither columns hold an ASPSOL run's values
    D.aspsol = nullptr; D.num_aspsol = 0;
    if (d->mode == 2)
@@ -295,6 +319,7 @@ extern "C" int marxb200_set_hrma (marxb200_ctx *c, const marxb200_hrma_desc *d)
 {
    if ((c == nullptr) || (d == nullptr)) return fail ("marxb200_set_hrma: NULL argument");
    CUDA_OK (cudaSetDevice (c->device));
+   begin_module (c, marxb200_ctx::TAG_HRMA);
    CudaUploader up{c};
    std::vector<unsigned char> blob;
    std::string err;
@@ -328,6 +353,7 @@ extern "C" int marxb200_set_grating (marxb200_ctx *c, const marxb200_grating_des
 {
    if ((c == nullptr) || (d == nullptr)) return fail ("marxb200_set_grating: NULL argument");
    CUDA_OK (cudaSetDevice (c->device));
+   begin_module (c, marxb200_ctx::TAG_GRATING);
    c->grating_type = d->type;
    c->have_grating = true;
    if (d->type == 0) return 0;
@@ -345,6 +371,7 @@ extern "C" int marxb200_set_acis (marxb200_ctx *c, const marxb200_acis_desc *d)
 {
    if ((c == nullptr) || (d == nullptr)) return fail ("marxb200_set_acis: NULL argument");
    CUDA_OK (cudaSetDevice (c->device));
+   begin_module (c, marxb200_ctx::TAG_DETECTOR);
    c->detector_type = d->detector_type;
    c->have_acis = true;
    if (d->detector_type == 0) return 0;
@@ -363,6 +390,7 @@ extern "C" int marxb200_set_hrc_s (marxb200_ctx *c, const marxb200_hrc_s_desc *d
 {
    if ((c == nullptr) || (d == nullptr)) return fail ("marxb200_set_hrc_s: NULL argument");
    CUDA_OK (cudaSetDevice (c->device));
+   begin_module (c, marxb200_ctx::TAG_DETECTOR);
    c->detector_type = d->detector_type;
    c->have_acis = true;
    if (d->detector_type == 0) return 0;
@@ -862,7 +890,15 @@ extern "C" int marxb200_upload_from (marxb200_ctx *c, const marxb200_photon_attr
    uint64_t *d_ids = nullptr;
    if (ray_ids)
      {
-        CUDA_OK (cudaMalloc (&d_ids, (n ? n : 1) * sizeof (uint64_t)));
+        if (c->upload_ids_cap < n)
+          {
+             CUDA_OK (cudaStreamSynchronize (c->stream));
+             if (c->d_upload_ids) cudaFree (c->d_upload_ids);
+             c->d_upload_ids = nullptr; c->upload_ids_cap = 0;
+             CUDA_OK (cudaMalloc (&c->d_upload_ids, (n + n / 4 + 1024) * sizeof (uint64_t)));
+             c->upload_ids_cap = n + n / 4 + 1024;
+          }
+        d_ids = c->d_upload_ids;
         CUDA_OK (cudaMemcpyAsync (d_ids, ray_ids, n * sizeof (uint64_t), cudaMemcpyHostToDevice, c->stream));
      }
    c->cur = 0;
@@ -873,7 +909,6 @@ extern "C" int marxb200_upload_from (marxb200_ctx *c, const marxb200_photon_attr
    unsigned long long nn = n;
    CUDA_OK (cudaMemcpyAsync (c->d_counts + 0, &nn, sizeof (nn), cudaMemcpyHostToDevice, c->stream));
    CUDA_OK (cudaStreamSynchronize (c->stream));
-   if (d_ids) cudaFree (d_ids);
    c->stage_done = 0; c->n_generated = n; c->ordered = true; c->first_mirror_kernel = 0;
    c->det_dither_dirty = true;           // the records may carry dy, dz, dtheta (an ASPSOL run dumped to a rayfile)
    return 0;
@@ -927,7 +962,7 @@ extern "C" int marxb200_tally_create (marxb200_ctx *c, const marxb200_tally_axis
    CUDA_OK (cudaSetDevice (c->device));
    CUDA_OK (cudaMalloc (&t.bins, t.total * sizeof (unsigned long long)));
    CUDA_OK (cudaMemsetAsync (t.bins, 0, t.total * sizeof (unsigned long long), c->stream));
-   c->allocs.push_back (t.bins);
+   c->allocs.push_back (std::make_pair ((void *) t.bins, (int) marxb200_ctx::TAG_MISC));
    c->tallies.push_back (t);
    return (int) c->tallies.size () - 1;
 }
@@ -1309,6 +1344,7 @@ extern "C" int marxb200_set_level1 (marxb200_ctx *c, const marxb200_level1_desc 
      return fail ("marxb200_set_level1: EDSER needs the sub-pixel tables");
    if (!(d->fp_delta_s0 > 0.0)) return fail ("marxb200_set_level1: focal-plane pixel size must be positive");
    CUDA_OK (cudaSetDevice (c->device));
+   begin_module (c, marxb200_ctx::TAG_LEVEL1);
    Level1Dev &L = c->L1;
    memset (&L, 0, sizeof (L));
    L.detector_type = d->detector_type; L.num_chips = d->num_chips;
@@ -1434,6 +1470,12 @@ extern "C" int marxb200_level1_download (marxb200_ctx *c, const marxb200_level1_
    CUDA_OK (cudaStreamSynchronize (c->stream));
    // the reference stops with an error on these rows (marx_compute_tiled_pixel: "chip = %d is not appropriate for this
    // detector", detpix.c:174; marx_mnc_to_fpc: "mnc.x is 0", :195)
+   if (err != 0)
+     {
+        // reported once: later batches of the same file are not failed by this one
+        CUDA_OK (cudaMemsetAsync (c->d_l1_error, 0, sizeof (unsigned int), c->stream));
+        CUDA_OK (cudaStreamSynchronize (c->stream));
+     }
    if (err & 1u) return fail ("marxb200_level1: an event's chip id does not belong to this detector");
    if (err & 2u) return fail ("marxb200_level1: mnc.x is 0");
    return 0;
@@ -1480,10 +1522,13 @@ extern "C" int marxb200_aspsol_rows (marxb200_ctx *c, const marxb200_aspsol_desc
 // ---------------------------------------------------------------------------------------------
 // ACIS pile-up (marxpileup's frame loop, marxpileup.c:1121-1213; kernels in pileup_kernels.cu)
 // ---------------------------------------------------------------------------------------------
-extern "C" int marxb200_pileup_run (marxb200_ctx *c, uint64_t n, const marxb200_pileup_in *in, double alpha, double frame_time, uint64_t seed,
-                                    uint64_t max_out, const marxb200_pileup_out *out, uint64_t *n_out, double *device_ms)
+// in == NULL: the input columns are gathered on the device from the context's live event list (marxb200_pileup_events)
+static int pileup_impl (marxb200_ctx *c, uint64_t n, const marxb200_pileup_in *in, double total_time, double alpha, double frame_time, uint64_t seed,
+                        uint64_t max_out, const marxb200_pileup_out *out, uint64_t *n_out, double *device_ms)
 {
-   if ((c == nullptr) || (in == nullptr) || (out == nullptr) || (n_out == nullptr)) return fail ("marxb200_pileup_run: NULL argument");
+   static const marxb200_pileup_in no_host_columns = {nullptr, nullptr, nullptr, nullptr, nullptr, {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}};
+   const bool from_list = (in == nullptr);
+   if (from_list) in = &no_host_columns;
    *n_out = 0;
    if (device_ms) *device_ms = 0.0;
    if (!c->have_acis || c->detector_is_hrc || (c->detector_type == 0) || (c->blob3 == nullptr))
@@ -1491,7 +1536,7 @@ extern "C" int marxb200_pileup_run (marxb200_ctx *c, uint64_t n, const marxb200_
    if (!(frame_time > 0.0)) return fail ("marxb200_pileup_run: frame_time must be positive");
    if (n >= 0xFFFFFFFFull) return fail ("marxb200_pileup_run: %llu events in one call", (unsigned long long) n);
    if (n == 0) return 0;
-   if ((in->ccd == nullptr) || (in->x == nullptr) || (in->y == nullptr) || (in->t == nullptr) || (in->benergy == nullptr))
+   if (!from_list && ((in->ccd == nullptr) || (in->x == nullptr) || (in->y == nullptr) || (in->t == nullptr) || (in->benergy == nullptr)))
      return fail ("marxb200_pileup_run: the detector, pixel, time and energy columns are required");
    CUDA_OK (cudaSetDevice (c->device));
    const uint64_t cap_out = (max_out < n) ? max_out : n;
@@ -1501,7 +1546,8 @@ extern "C" int marxb200_pileup_run (marxb200_ctx *c, uint64_t n, const marxb200_
    size_t bytes = rounded (n, 1) + 10 * rounded (n, 4)                                         // inputs
      + 8 * rounded (n, 4) + 6 * rounded (n, 4) + rounded (n, 1) + rounded (n, 2) + rounded (n_tiles, 4)   // scratch
      + rounded (cap_out + 1, 1) + 11 * rounded (cap_out + 1, 4) + 2 * rounded (cap_out + 1, 2)  // outputs
-     + 256;                                                                                    // n_out, error
+     + 256                                                                                     // n_out, error
+     + ((mx::pileup_fused_scratch_bytes (n) + 255) & ~(size_t) 255);                           // fused kernel: ticket + tile states
    char *slab = nullptr;
    CUDA_OK (cudaMallocAsync ((void **) &slab, bytes, c->stream));
    char *p = slab;
@@ -1513,7 +1559,7 @@ extern "C" int marxb200_pileup_run (marxb200_ctx *c, uint64_t n, const marxb200_
    for (int k = 0; k < 10; k++) d_in[k] = (float *) take (n, 4);
    const float *h_in[10] = {in->x, in->y, in->t, in->benergy, in->dither[0], in->dither[1], in->dither[2], in->dither[3], in->dither[4], in->dither[5]};
    a.ccd = d_ccd; a.x = d_in[0]; a.y = d_in[1]; a.t = d_in[2]; a.benergy = d_in[3];
-   for (int k = 0; k < 6; k++) a.dither[k] = (h_in[4 + k] != nullptr) ? d_in[4 + k] : nullptr;
+   for (int k = 0; k < 6; k++) a.dither[k] = (from_list || (h_in[4 + k] != nullptr)) ? d_in[4 + k] : nullptr;
    a.n = n; a.alpha = alpha; a.frame_time = frame_time; a.seed = seed;
    for (int k = 0; k < mx::kPuProbTable; k++) a.prob[k] = pow (alpha, (double) k);
    a.max_frame_events = 1u << 16;
@@ -1530,6 +1576,11 @@ extern "C" int marxb200_pileup_run (marxb200_ctx *c, uint64_t n, const marxb200_
    a.o_nphotons = (int16_t *) take (cap_out + 1, 2); a.o_pha = (int16_t *) take (cap_out + 1, 2);
    a.max_out = cap_out;
    a.n_out = (unsigned long long *) p; a.error = (unsigned int *) (p + 8);
+   void *fused_scratch = (void *) (p + 256);
+   // the fused single-kernel form serves lists whose exposure frames fit its shared-memory window (<= 513 events guaranteed);
+   // a longer frame makes it raise a flag and the step kernels run instead (MARXB200_PILEUP_FUSED=0: always the step kernels)
+   bool fused = true;
+   if (const char *e = getenv ("MARXB200_PILEUP_FUSED")) fused = (atoi (e) != 0);
    int status = 0;
    unsigned long long rows = 0; unsigned int err = 0;
    cudaEvent_t e0 = prof_event (c), e1 = prof_event (c);
@@ -1537,10 +1588,18 @@ extern "C" int marxb200_pileup_run (marxb200_ctx *c, uint64_t n, const marxb200_
      {
 #define PU_OK(expr) { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { status = fail ("%s: %s", #expr, cudaGetErrorString (e_)); break; } }
         PU_OK (cudaMemsetAsync (p, 0, 16, c->stream));
-        PU_OK (cudaMemcpyAsync (d_ccd, in->ccd, (size_t) n, cudaMemcpyHostToDevice, c->stream));
+        if (from_list)
+          {
+             // the columns marx_write_photons would put into detector.dat, xpixel.dat, ypixel.dat, time.dat, b_energy.dat and the six
+             // dither files (marxio.c:217-290: TIME = (float) (arrival_time + total_time)), straight from the list in HBM
+             mx::launch_pileup_gather (mxb_observed (c, c->buf[c->cur]), c->d_counts + c->stage_done, n, c->d_times, total_time,
+                                       d_ccd, d_in, c->stream);
+             c->launches += 1;
+          }
+        else PU_OK (cudaMemcpyAsync (d_ccd, in->ccd, (size_t) n, cudaMemcpyHostToDevice, c->stream));
         bool copied = true;
         for (int k = 0; k < 10; k++)
-          if (h_in[k] != nullptr)
+          if (!from_list && (h_in[k] != nullptr))
             {
                cudaError_t e_ = cudaMemcpyAsync (d_in[k], h_in[k], (size_t) n * 4, cudaMemcpyHostToDevice, c->stream);
                if (e_ != cudaSuccess) { status = fail ("marxb200_pileup_run: upload: %s", cudaGetErrorString (e_)); copied = false; break; }
@@ -1548,13 +1607,26 @@ extern "C" int marxb200_pileup_run (marxb200_ctx *c, uint64_t n, const marxb200_
         if (!copied) break;
         PU_OK (cudaEventRecord (e0, c->stream));
         int nl = 0;
-        mx::launch_pileup (a, c->num_sms, c->stream, &nl);
+        if (fused) mx::launch_pileup_fused (a, fused_scratch, c->num_sms, c->stream, &nl);
+        else mx::launch_pileup (a, c->num_sms, c->stream, &nl);
         PU_OK (cudaEventRecord (e1, c->stream));
         c->launches += (uint64_t) nl;
         PU_OK (cudaGetLastError ());
         PU_OK (cudaMemcpyAsync (&rows, a.n_out, 8, cudaMemcpyDeviceToHost, c->stream));
         PU_OK (cudaMemcpyAsync (&err, a.error, 4, cudaMemcpyDeviceToHost, c->stream));
         PU_OK (cudaStreamSynchronize (c->stream));
+        if (fused && (err & mx::kPuErrFallback))
+          {
+             PU_OK (cudaMemsetAsync (p, 0, 16, c->stream));
+             PU_OK (cudaEventRecord (e0, c->stream));
+             mx::launch_pileup (a, c->num_sms, c->stream, &nl);
+             PU_OK (cudaEventRecord (e1, c->stream));
+             c->launches += (uint64_t) nl;
+             PU_OK (cudaGetLastError ());
+             PU_OK (cudaMemcpyAsync (&rows, a.n_out, 8, cudaMemcpyDeviceToHost, c->stream));
+             PU_OK (cudaMemcpyAsync (&err, a.error, 4, cudaMemcpyDeviceToHost, c->stream));
+             PU_OK (cudaStreamSynchronize (c->stream));
+          }
         if (err & mx::kPuErrCcd) { status = fail ("marxb200_pileup_run: an event's CCD id is outside 0..9"); break; }
         if (err & mx::kPuErrCorrupt) { status = fail ("marxb200_pileup_run: pixel coordinate beyond the chip (corrupt file?)"); break; }
         if (err & mx::kPuErrFrameTooLong) { status = fail ("marxb200_pileup_run: an exposure frame holds more than 65536 events"); break; }
@@ -1592,6 +1664,28 @@ extern "C" int marxb200_pileup_run (marxb200_ctx *c, uint64_t n, const marxb200_
    cudaStreamSynchronize (c->stream);
    c->ev_pool.push_back (e0); c->ev_pool.push_back (e1);
    return status;
+}
+
+extern "C" int marxb200_pileup_run (marxb200_ctx *c, uint64_t n, const marxb200_pileup_in *in, double alpha, double frame_time, uint64_t seed,
+                                    uint64_t max_out, const marxb200_pileup_out *out, uint64_t *n_out, double *device_ms)
+{
+   if ((c == nullptr) || (in == nullptr) || (out == nullptr) || (n_out == nullptr)) return fail ("marxb200_pileup_run: NULL argument");
+   return pileup_impl (c, n, in, 0.0, alpha, frame_time, seed, max_out, out, n_out, device_ms);
+}
+
+// the same for the event list the detector stage left on the device: marx -> marxpileup without the column files in between
+extern "C" int marxb200_pileup_events (marxb200_ctx *c, double total_time, double alpha, double frame_time, uint64_t seed,
+                                       uint64_t max_out, const marxb200_pileup_out *out, uint64_t *n_out, double *device_ms)
+{
+   if ((c == nullptr) || (out == nullptr) || (n_out == nullptr)) return fail ("marxb200_pileup_events: NULL argument");
+   *n_out = 0;
+   if (c->stage_done != 3) return fail ("marxb200_pileup_events: the live list must be behind marxb200_detect");
+   CUDA_OK (cudaSetDevice (c->device));
+   if (-1 == ensure_order (c)) return -1;
+   unsigned long long n = 0;
+   CUDA_OK (cudaMemcpyAsync (&n, c->d_counts + 3, sizeof (n), cudaMemcpyDeviceToHost, c->stream));
+   CUDA_OK (cudaStreamSynchronize (c->stream));
+   return pileup_impl (c, n, nullptr, total_time, alpha, frame_time, seed, max_out, out, n_out, device_ms);
 }
 
 // ---------------------------------------------------------------------------------------------

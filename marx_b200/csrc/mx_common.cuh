@@ -13,6 +13,7 @@
 #pragma once
 #include <stdint.h>
 #include <math.h>
+#include "mx_math.cuh"
 
 #if defined(__CUDACC__)
 #define MX_HD __host__ __device__ __forceinline__
@@ -114,11 +115,7 @@ MX_HD Vec3 v_rotate_unit1 (const Vec3 &p, const Vec3 &n, double cos_theta, doubl
 // of its sin and cos), the two libm calls of the reference on the host
 MX_HD void sin_cos (double theta, double &s, double &c)
 {
-#if defined(__CUDA_ARCH__)
-   sincos (theta, &s, &c);
-#else
-   s = sin (theta); c = cos (theta);
-#endif
+   mx_sincos (theta, s, c);          // mx_math.cuh: one argument reduction, coefficients in constant memory; libm on the host
 }
 // JDMv_rotate_unit_vector, vector.c:204-208
 MX_HD_BIG Vec3 v_rotate_unit (const Vec3 &p, const Vec3 &n, double theta)
@@ -212,7 +209,7 @@ struct Rng
            g = g1 * g1 + g2 * g2;
         }
       while ((g >= 1.0) || (g == 0.0));
-      double s = sqrt (-2.0 * log (g) / g);
+      double s = sqrt (-2.0 * mx_log (g) / g);
       spare = g2 * s; have_spare = 1;
       return g1 * s;
    }
@@ -221,7 +218,7 @@ struct Rng
    {
       double r;
       do r = uniform (); while (r == 0.0);
-      return -log (r);
+      return -mx_log (r);
    }
 };
 

@@ -41,7 +41,11 @@ struct marxb200_ctx
    uint64_t n_generated = 0;
 
    // tables
-   std::vector<void *> allocs;                   // every cudaMalloc'd table (freed in destroy)
+   // every cudaMalloc'd table with the module that owns it (freed in destroy, or when the module's setter runs again)
+   enum { TAG_MISC = 0, TAG_SOURCE, TAG_DITHER, TAG_HRMA, TAG_GRATING, TAG_DETECTOR, TAG_LEVEL1 };
+   std::vector<std::pair<void *, int>> allocs;
+   int alloc_tag = TAG_MISC;
+   uint64_t *d_upload_ids = nullptr; uint64_t upload_ids_cap = 0;      // ray ids of marxb200_upload
    SourceDev S; DitherDev D;
    bool have_source = false, have_dither = false, have_hrma = false, have_grating = false, have_acis = false;
    int grating_type = 0, detector_type = 0;

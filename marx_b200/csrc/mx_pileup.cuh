@@ -31,7 +31,7 @@ namespace mx {
 
 constexpr uint32_t kPuNoKey = 0xFFFFFFFFu;
 constexpr int kPuProbTable = 64;
-constexpr uint32_t kPuErrCcd = 1u, kPuErrCorrupt = 2u, kPuErrFrameTooLong = 4u, kPuErrPha = 8u, kPuErrOverflow = 16u;
+constexpr uint32_t kPuErrCcd = 1u, kPuErrCorrupt = 2u, kPuErrFrameTooLong = 4u, kPuErrPha = 8u, kPuErrOverflow = 16u, kPuErrFallback = 0x100u;
 
 struct PileupArgs
 {
@@ -107,7 +107,7 @@ MX_HD void pu_store (const PileupArgs &a, uint64_t e)
 }
 
 // the occupied pixels of e's 3 x 3 neighbourhood: slot [r][c] = representative event of pixel (y - 1 + r, x - 1 + c), or -1
-struct PuHood { int64_t at[3][3]; };
+struct PuHood { int32_t at[3][3]; };           // event indices stay below 2^32 - 1 (marxb200_pileup_run refuses longer lists)
 MX_HD void pu_hood (const PileupArgs &a, uint64_t e, PuHood &h)
 {
    const uint32_t key = a.key[e];
@@ -125,7 +125,7 @@ MX_HD void pu_hood (const PileupArgs &a, uint64_t e, PuHood &h)
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int q = 0; q < 9; q++) if (q == slot) h.at[q / 3][q % 3] = (int64_t) j;
+        for (int q = 0; q < 9; q++) if (q == slot) h.at[q / 3][q % 3] = (int32_t) j;
      }
 }
 
@@ -145,7 +145,7 @@ MX_HD void pu_island (const PileupArgs &a, uint64_t e)
 #endif
      for (int c = 0; c < 3; c++)
        {
-          const int64_t j = h.at[r][c];
+          const int32_t j = h.at[r][c];
           const float b = (j < 0) ? 0.0f : a.pb[j];
           const double term = (((r == 1) && (c == 1)) ? (1.0) : (9.0 / 9.0)) * (double) b;
           s = first ? term : s + term;
@@ -170,7 +170,7 @@ MX_HD void pu_detect (const PileupArgs &a, uint64_t e)
 #endif
      for (int c = 0; c < 3; c++)
        {
-          const int64_t j = h.at[r][c];
+          const int32_t j = h.at[r][c];
           pb[r][c] = (j < 0) ? 0.0f : a.pb[j];
           ib[r][c] = (j < 0) ? 0.0f : a.ib[j];
        }
@@ -235,7 +235,7 @@ MX_HD void pu_emit (const PileupArgs &a, uint64_t e)
 #endif
           for (int r = 0; r < 3; r++)
             {
-               const int64_t j = h.at[r][c];
+               const int32_t j = h.at[r][c];
                const float qx = (j < 0) ? 0.0f : a.px[j], qy = (j < 0) ? 0.0f : a.py[j], qb = (j < 0) ? 0.0f : a.pb[j];
                x += (double) (qx * qb); y += (double) (qy * qb);
             }
@@ -269,6 +269,13 @@ MX_HD void pu_scatter (const PileupArgs &a, uint64_t e)
 #if defined(__CUDACC__)
 // pileup_kernels.cu: the eight launches on stream s (5 steps, 2 scan kernels, scatter)
 void launch_pileup (const PileupArgs &a, int num_sms, cudaStream_t s, int *n_launches);
+// the fused single-kernel form (frames staged in shared memory); sets kPuErrFallback in *a.error when a frame does not fit
+size_t pileup_fused_scratch_bytes (uint64_t n);
+struct PhotonSoA;
+// cols: x, y, t, benergy, then the six dither columns
+void launch_pileup_gather (const PhotonSoA &in, const unsigned long long *n_ptr, uint64_t max_n, const double *dev_start_time, double total_time,
+                           int8_t *ccd, float *const cols[10], cudaStream_t s);
+void launch_pileup_fused (const PileupArgs &a, void *scratch, int num_sms, cudaStream_t s, int *n_launches);
 #endif
 
 }  // namespace mx

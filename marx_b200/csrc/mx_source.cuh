@@ -86,8 +86,7 @@ MX_HD Vec3 dither_roll (double roll, const Vec3 &p) { return v_rotate_unit (p, v
 MX_HD Vec3 apply_dither_rolled (double ra, double dec, Vec3 p)
 {
    double cos_ra, sin_ra, cos_dec, sin_dec;
-   sin_cos (ra, sin_ra, cos_ra);
-   sin_cos (dec, sin_dec, cos_dec);
+   mx_sincos_pair (ra, dec, sin_ra, cos_ra, sin_dec, cos_dec);      // dither angles: a few 1e-5 rad
    double cos_theta = cos_dec * cos_ra;
    Vec3 n = v_make (0, sin_dec, -cos_dec * sin_ra);
    double sin_theta = v_length (n);
@@ -143,10 +142,10 @@ MX_HD void dither_ray (const DitherDev &d, Rng &rng, double t, Vec3 &p, float &f
      {
         t = (2.0 * kPI) * t;
         // amp * sin(..) is exactly +-0 when the amplitude is 0 (default DitherAmp_Roll): skip the sine then
-        f_ra = (d.ra_amp == 0.0) ? 0.0f : (float) (d.ra_amp * sin (t / d.ra_period + d.ra_phase));
-        f_dec = (d.dec_amp == 0.0) ? 0.0f : (float) (d.dec_amp * sin (t / d.dec_period + d.dec_phase));
+        f_ra = (d.ra_amp == 0.0) ? 0.0f : (float) (d.ra_amp * mx_sin (t / d.ra_period + d.ra_phase));
+        f_dec = (d.dec_amp == 0.0) ? 0.0f : (float) (d.dec_amp * mx_sin (t / d.dec_period + d.dec_phase));
         f_roll = (d.roll_amp == 0.0) ? (float) d.nominal_roll
-                                     : (float) (d.nominal_roll + d.roll_amp * sin (t / d.roll_period + d.roll_phase));
+                                     : (float) (d.nominal_roll + d.roll_amp * mx_sin (t / d.roll_period + d.roll_phase));
      }
    double ra = f_ra, dec = f_dec, roll = f_roll;
    double delta_ra = d.aspect_blur * rng.gaussian ();

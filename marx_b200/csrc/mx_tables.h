@@ -10,7 +10,7 @@ namespace mx {
 constexpr int kNumShells = 4;
 constexpr int kMaxChips = 6;
 constexpr int kMaxContamLayers = 5;
-constexpr int kMaxGauss = 16;          // gaussians per FEF row kept in registers/local (reference: <= 18)
+constexpr int kMaxGauss = 18;          // gaussians per FEF row: (MAX_FEF_COLUMNS - FWHM1_COLUMN) / 3 of the reference (acis_fef.c:328-338)
 
 struct SourceDev
 {

@@ -14,6 +14,17 @@ namespace mx {
 
 constexpr int kPuTile = 256;            // pu_rows_through (mx_pileup.cuh) shifts by 8
 
+__device__ __forceinline__ unsigned long long ld_relaxed (const unsigned long long *p)
+{
+   unsigned long long v;
+   asm volatile ("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+   return v;
+}
+__device__ __forceinline__ void st_relaxed (unsigned long long *p, unsigned long long v)
+{
+   asm volatile ("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
 template <int STEP>
 __global__ void __launch_bounds__ (kPuTile) pu_step (const __grid_constant__ PileupArgs a)
 {
@@ -84,6 +95,208 @@ __global__ void __launch_bounds__ (1024) pu_scan_totals (const __grid_constant__
         if (threadIdx.x == 1023) carry_s = incl;
         __syncthreads ();
      }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Fused form: ONE persistent kernel.  A CTA takes tiles of kFuTile consecutive events from a ticket counter, stages the input
+// columns of a window of up to kFuCap events (the tile plus what the tile's last frame needs beyond it) in shared memory and
+// runs the same per-event functions on the window -- the walks over an event's frame run, the 3 x 3 neighbourhoods, the
+// pixel and island sums never leave the SM, and no per-event scratch goes to HBM.  A tile OWNS the frames whose first event
+// lies in it, so every frame is processed exactly once.  Output rows (reference order: frames ascending, reverse file order
+// inside a frame) are placed with a block scan over the window's emit flags and a decoupled look-back over the tiles' row
+// counts (tiles are ticketed in order, so a predecessor is always running or done).  A frame that does not fit the window
+// (more than kFuCap - kFuTile + 1 events is the guaranteed size) raises kPuErrFallback: the host then runs the step kernels above.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int kFuTile = 512, kFuCap = 1024, kFuThreads = 512;
+constexpr unsigned long long kFuAggregate = 1ull << 62, kFuPrefix = 2ull << 62, kFuValueMask = (1ull << 62) - 1ull;
+
+struct FuSmem
+{
+   uint32_t frame[kFuCap], key[kFuCap], lo[kFuCap], hi[kFuCap], pn[kFuCap], in[kFuCap], emit[kFuCap], cum[kFuCap];
+   float x[kFuCap], y[kFuCap], t[kFuCap], benergy[kFuCap], pb[kFuCap], px[kFuCap], py[kFuCap], ib[kFuCap], sx[kFuCap], sy[kFuCap];
+   int16_t spha[kFuCap];
+   int8_t ccd[kFuCap];
+   uint8_t flag[kFuCap];
+   uint32_t warp_sum[kFuThreads / 32];
+   PileupArgs args;                         // the argument block with its per-event columns re-pointed at this window
+   unsigned long long tile;
+   uint32_t own_lo, own_hi, total;
+   unsigned long long base;
+};
+
+__global__ void __launch_bounds__ (kFuThreads, 2) pu_fused (const __grid_constant__ PileupArgs g, unsigned long long *ticket,
+                                                        unsigned long long *tile_state)
+{
+   extern __shared__ __align__ (16) unsigned char fu_raw[];
+   FuSmem &S = *reinterpret_cast<FuSmem *> (fu_raw);
+   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+   // the per-event functions see the window through the same argument block, its columns pointing into shared memory
+   PileupArgs &a = S.args;
+   if (tid == 0)
+     {
+        a = g;
+        a.ccd = S.ccd; a.x = S.x; a.y = S.y; a.t = S.t; a.benergy = S.benergy;
+        a.frame = S.frame; a.key = S.key; a.lo = S.lo; a.hi = S.hi; a.pn = S.pn; a.in = S.in; a.emit = S.emit; a.cum = S.cum;
+        a.pb = S.pb; a.px = S.px; a.py = S.py; a.ib = S.ib; a.sx = S.sx; a.sy = S.sy; a.spha = S.spha; a.flag = S.flag;
+     }
+   const uint64_t n_tiles = (g.n + kFuTile - 1) / kFuTile;
+   while (true)
+     {
+        __syncthreads ();
+        if (tid == 0) S.tile = atomicAdd (ticket, 1ull);
+        __syncthreads ();
+        const uint64_t tile = S.tile;
+        if (tile >= n_tiles) break;
+        const uint64_t t0 = tile * kFuTile;
+        const uint32_t cnt = (uint32_t) min ((uint64_t) kFuCap, g.n - t0);
+        const uint32_t in_tile = min ((uint32_t) kFuTile, cnt);
+        for (uint32_t e = tid; e < cnt; e += kFuThreads)
+          {
+             S.ccd[e] = g.ccd[t0 + e]; S.x[e] = g.x[t0 + e]; S.y[e] = g.y[t0 + e]; S.t[e] = g.t[t0 + e]; S.benergy[e] = g.benergy[t0 + e];
+          }
+        if (tid == 0) { S.own_lo = cnt; S.own_hi = cnt; a.n = cnt; }
+        __syncthreads ();
+        for (uint32_t e = tid; e < cnt; e += kFuThreads) pu_frames (a, e);
+        __syncthreads ();
+        // the frames this tile owns: from the first frame head inside the tile to the end of the frame of the tile's last event
+        const uint32_t prev_frame = (t0 == 0) ? 0u : (unsigned int) ((double) g.t[t0 - 1] / g.frame_time);
+        for (uint32_t e = tid; e < cnt; e += kFuThreads)
+          {
+             if (e < in_tile)
+               {
+                  const bool head = (e == 0) ? ((t0 == 0) || (S.frame[0] != prev_frame)) : (S.frame[e] != S.frame[e - 1]);
+                  if (head) atomicMin (&S.own_lo, e);
+               }
+             else if (S.frame[e] != S.frame[in_tile - 1]) atomicMin (&S.own_hi, e);
+          }
+        __syncthreads ();
+        uint32_t own_lo = S.own_lo, own_hi = S.own_hi;
+        if (own_lo >= in_tile) { own_lo = 0; own_hi = 0; }          // no frame starts here: an earlier tile owns all of it
+        else if ((own_hi == cnt) && (t0 + cnt < g.n) && (S.frame[cnt - 1] == S.frame[in_tile - 1]))
+          {
+             // the last owned frame runs past the window: the step kernels take over (host side)
+             if (tid == 0) atomicOr (g.error, kPuErrFallback);
+             own_hi = own_lo;
+          }
+        if (tid == 0) a.n = own_hi;                                 // walks stop at the end of the owned frames
+        __syncthreads ();
+        for (uint32_t e = own_lo + tid; e < own_hi; e += kFuThreads) pu_store (a, e);
+        __syncthreads ();
+        for (uint32_t e = own_lo + tid; e < own_hi; e += kFuThreads) pu_island (a, e);
+        __syncthreads ();
+        for (uint32_t e = own_lo + tid; e < own_hi; e += kFuThreads) pu_detect (a, e);
+        __syncthreads ();
+        for (uint32_t e = own_lo + tid; e < own_hi; e += kFuThreads) pu_emit (a, e);
+        __syncthreads ();
+        // inclusive prefix sum of the emit flags over the window (two entries per thread)
+        {
+           const uint32_t i0 = 2u * tid, i1 = i0 + 1u;
+           const uint32_t v0 = ((i0 >= own_lo) && (i0 < own_hi)) ? S.emit[i0] : 0u, v1 = ((i1 >= own_lo) && (i1 < own_hi)) ? S.emit[i1] : 0u;
+           uint32_t s = v0 + v1;
+#pragma unroll
+           for (int d = 1; d < 32; d <<= 1)
+             {
+                const uint32_t o = __shfl_up_sync (0xFFFFFFFFu, s, d);
+                if (lane >= (uint32_t) d) s += o;
+             }
+           if (lane == 31u) S.warp_sum[warp] = s;
+           __syncthreads ();
+           uint32_t before = 0;
+           for (uint32_t k = 0; k < warp; k++) before += S.warp_sum[k];
+           s += before;
+           S.cum[i0] = s - v1; S.cum[i1] = s;
+           if (tid == kFuThreads - 1) S.total = s;
+        }
+        __syncthreads ();
+        // decoupled look-back over the tiles' row counts
+        if (warp == 0)
+          {
+             const unsigned long long total = S.total;
+             unsigned long long excl = 0;
+             if (lane == 0)
+               {
+                  if (tile == 0) st_relaxed (tile_state, kFuPrefix | total);
+                  else
+                    {
+                       st_relaxed (tile_state + tile, kFuAggregate | total);
+                       long long p = (long long) tile - 1;
+                       while (true)
+                         {
+                            const unsigned long long w = ld_relaxed (tile_state + p);
+                            if ((w & ~kFuValueMask) == 0ull) continue;          // predecessor not published yet
+                            excl += (w & kFuValueMask);
+                            if ((w & ~kFuValueMask) == kFuPrefix) break;
+                            p--;
+                         }
+                       st_relaxed (tile_state + tile, kFuPrefix | (excl + total));
+                    }
+                  S.base = excl;
+                  if (tile + 1 == n_tiles) *g.n_out = excl + total;
+               }
+          }
+        __syncthreads ();
+        const unsigned long long base = S.base;
+        for (uint32_t e = own_lo + tid; e < own_hi; e += kFuThreads)
+          {
+             if (S.emit[e] == 0) continue;
+             const uint32_t lo = S.lo[e], hi = S.hi[e];
+             const unsigned long long before = (lo == 0) ? 0ull : S.cum[lo - 1];
+             const unsigned long long pos = base + before + (S.cum[hi - 1] - S.cum[e]);
+             if (pos >= g.max_out) { atomicOr (g.error, kPuErrOverflow); continue; }
+             const uint32_t f = S.frame[e];
+             g.o_ccd[pos] = S.ccd[e]; g.o_x[pos] = S.sx[e]; g.o_y[pos] = S.sy[e];
+             g.o_frame[pos] = (int32_t) f; g.o_t[pos] = (float) ((int32_t) f * g.frame_time);
+             g.o_nphotons[pos] = (int16_t) S.in[e]; g.o_pha[pos] = S.spha[e]; g.o_benergy[pos] = S.ib[e];
+             for (int d = 0; d < 6; d++) if (g.dither[d] && g.o_dither[d]) g.o_dither[d][pos] = g.dither[d][t0 + e];
+          }
+     }
+}
+
+// scratch: [0] the ticket, [1 ..] one status word per tile (zeroed here)
+size_t pileup_fused_scratch_bytes (uint64_t n) { return (size_t) ((n + kFuTile - 1) / kFuTile + 2) * sizeof (unsigned long long); }
+void launch_pileup_fused (const PileupArgs &a, void *scratch, int num_sms, cudaStream_t s, int *n_launches)
+{
+   *n_launches = 0;
+   if (a.n == 0) return;
+   static int per_sm = 0;
+   if (per_sm == 0)
+     {
+        cudaFuncSetAttribute (pu_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof (FuSmem));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, pu_fused, kFuThreads, sizeof (FuSmem));
+        if (per_sm < 1) per_sm = 1;
+     }
+   cudaMemsetAsync (scratch, 0, pileup_fused_scratch_bytes (a.n), s);
+   const uint64_t tiles = (a.n + kFuTile - 1) / kFuTile;
+   const unsigned int grid = (unsigned int) min (tiles, (uint64_t) num_sms * per_sm);
+   unsigned long long *w = (unsigned long long *) scratch;
+   pu_fused<<<grid, kFuThreads, sizeof (FuSmem), s>>> (a, w, w + 1);
+   *n_launches = 1;
+}
+
+// input columns of the pile-up model from the live event list in HBM: what marx_write_photons would have put into the column files
+// marxpileup reads (marxio.c:217-290: chip id, chip pixels, (float) (arrival time + total_time), PI energy, the six dither values)
+__global__ void __launch_bounds__ (256) pu_gather (PhotonSoA in, const unsigned long long *n_ptr, uint64_t max_n, const double *dev_start_time,
+                                                  double total_time, int8_t *ccd, float *x, float *y, float *t, float *b,
+                                                  float *d0, float *d1, float *d2, float *d3, float *d4, float *d5)
+{
+   const uint64_t n = min ((uint64_t) *n_ptr, max_n);
+   const double start = *dev_start_time;
+   for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x)
+     {
+        ccd[i] = in.ccd[i]; x[i] = in.chipx[i]; y[i] = in.chipy[i];
+        t[i] = (float) ((in.time[i] - start) + total_time);
+        b[i] = in.pi[i];
+        d0[i] = in.dra[i]; d1[i] = in.ddec[i]; d2[i] = in.droll[i];
+        d3[i] = in.ddy ? in.ddy[i] : 0.0f; d4[i] = in.ddz ? in.ddz[i] : 0.0f; d5[i] = in.ddth ? in.ddth[i] : 0.0f;
+     }
+}
+void launch_pileup_gather (const PhotonSoA &in, const unsigned long long *n_ptr, uint64_t max_n, const double *dev_start_time, double total_time,
+                           int8_t *ccd, float *const cols[10], cudaStream_t s)
+{
+   if (max_n == 0) return;
+   const unsigned int grid = (unsigned int) min ((uint64_t) 148 * 8, (max_n + 255) / 256);
+   pu_gather<<<grid, 256, 0, s>>> (in, n_ptr, max_n, dev_start_time, total_time, ccd, cols[0], cols[1], cols[2], cols[3],
+                                   cols[4], cols[5], cols[6], cols[7], cols[8], cols[9]);
 }
 
 void launch_pileup (const PileupArgs &a, int num_sms, cudaStream_t s, int *n_launches)

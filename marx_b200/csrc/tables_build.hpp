@@ -277,6 +277,8 @@ template <class Up> int build_acis_blob (Up &up, const marxb200_acis_desc *d, st
                }
           }
         if (s.fef_map == nullptr) { err = "chip without FEF map"; return -1; }
+        for (int i = 0; i < 1024; i++)
+          if ((s.fef_map[i] < -1) || (s.fef_map[i] >= (int32_t) d->num_fefs)) { err = "FEF map entry outside [-1, num_fefs)"; return -1; }
         if (-1 == tb_up (up, s.fef_map, 1024, &g.fef_map, err)) return -1;
      }
    for (int i = 0; i < 3; i++) A.det_offset[i] = d->det_offset[i];

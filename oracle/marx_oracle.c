@@ -77,6 +77,7 @@ struct oracle
    const double *src, *dith, *hrma, *grat, *acis;
    const double *spec_e, *spec_c; uint32_t nspec;
    const double *src_rot, *img_prm; const float *img_cdf; uint32_t nimg;   /* LINE / IMAGE sources */
+   uint64_t batch_first;                                                                              /* global index of the batch's first ray: the records' tags hold the low 32 bits only (marx.h:98) */
    const double *asp; uint32_t nasp, asp_pos; uint64_t last_generated;                                  /* ASPSOL states [nasp][7] (dither.c:288-359) */
    double asp_t_prev;
    double xf_off[3], xf_m[9]; int xf_init;                                 /* _Marx_Det_XForm_Matrix: dithered and restored photon after photon */
@@ -287,6 +288,10 @@ typedef struct { uint64_t seed, ray; uint32_t stage, draw, blk[4]; int have_spar
 
 static void rng_set (rng_t *r, uint64_t seed, uint64_t ray, uint32_t stage)
 { r->seed = seed; r->ray = ray; r->stage = stage; r->draw = 0; r->have_spare = 0; }
+/* The draws are keyed on the 64-bit global ray index; a record only carries its low 32 bits (the reference's tag,
+ * marx.h:98).  Within a batch (< 2^32 rays) the full index is the batch's first ray plus the tag's distance from it. */
+static uint64_t ray_of (const oracle_t *o, uint32_t tag)
+{ return o->batch_first + (uint64_t) (uint32_t) (tag - (uint32_t) o->batch_first); }
 
 static uint32_t rng_u32 (rng_t *r)
 {
@@ -665,7 +670,7 @@ static void stage_mirror (oracle_t *o, uint64_t n, oracle_photon *ph)
         oracle_photon *at = ph + i; rng_t r; const shell_t *sh; const double *s; int k, found = 0, st;
         double radius, theta, beta = 0.0, delta = 1.0, corr = 1.0; uint32_t quad;
         if (at->flags & 0xFF) continue;
-        rng_set (&r, o->seed, at->tag, 1);
+        rng_set (&r, o->seed, ray_of (o, at->tag), 1);
         if (!ideal && (rng_uniform (&r) > H[0])) { at->flags |= F_VBLOCKED; continue; }                /* hrma.c:1185-1192 */
         while (!found)                                                                                  /* :984-1050 */
           {
@@ -795,7 +800,7 @@ static void stage_grating (oracle_t *o, uint64_t n, oracle_photon *ph)
         oracle_photon *at = ph + i; rng_t r; const gshell_t *g; int rc = -1;
         if (at->flags & 0xFF) continue;
         g = &o->gshell[at->mirror_shell];
-        rng_set (&r, o->seed, at->tag, 2);
+        rng_set (&r, o->seed, ray_of (o, at->tag), 2);
         if (rng_uniform (&r) > g->prm[4]) { at->flags |= F_VBLOCKED; continue; }                        /* :994-1001 */
         rot_x (at->x, -1 * g->prm[0]); rot_x (at->p, -1 * g->prm[0]);                                   /* :1013 */
         if (-1 == torus_hit (at->x, at->p, o->grat[1 + at->mirror_shell])) { at->flags |= F_UNDIFFRACTED; continue; }
@@ -1043,7 +1048,7 @@ static void stage_detect_hrc (oracle_t *o, uint64_t n, oracle_photon *ph)
         oracle_photon *at = ph + i; rng_t r; int k, hit = -1; double dx = 0, dy = 0, xh[3]; const double *g = NULL; const mcp_t *m;
         double t, y, z, u, v; int region;
         if (at->flags & 0xFF) continue;
-        rng_set (&r, o->seed, at->tag, 3);
+        rng_set (&r, o->seed, ray_of (o, at->tag), 3);
         if (use_hesf)
           for (k = 0; k < 2 * nplates; k++)                                                              /* drake.c:268-313 */
             {
@@ -1140,7 +1145,7 @@ static void stage_detect (oracle_t *o, uint64_t n, oracle_photon *ph)
      {
         oracle_photon *at = ph + i; rng_t r; int k, hit = -1; double dx = 0, dy = 0, xh[3]; const chip_t *ch; const double *g;
         if (at->flags & 0xFF) continue;
-        rng_set (&r, o->seed, at->tag, 3);
+        rng_set (&r, o->seed, ray_of (o, at->tag), 3);
         xf_dither (o, at);                                                                               /* acis-s.c:209-211 */
         at->x[0] -= off[0]; at->x[1] -= off[1]; at->x[2] -= off[2];                                      /* trans.c:66-77 */
         mat3 (M, at->x); mat3 (M, at->p);
@@ -1193,6 +1198,7 @@ long oracle_trace (oracle_t *o, uint64_t first_ray, uint64_t n, double *time_bas
       /* the ASPSOL reader only moves forward (dither.c:361-369); a trace that restarts the clock rewinds it */
       uint64_t kept;
       if (o->asp && ((o->asp_pos < 1) || (tb < o->asp_t_prev))) o->asp_pos = 1;
+      o->batch_first = first_ray;
       kept = stage_source (o, first_ray, n, &tb, work);
       o->asp_t_prev = tb;
       o->last_generated = kept;

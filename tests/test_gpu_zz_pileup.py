@@ -1,7 +1,8 @@
-"""ACIS pile-up on the GPU (marxb200_pileup_run; marx/src/marxpileup.c:573-922,1121-1213) against the stock
-program's committed output (tests/golden/pileup_*.npz, bit for bit, every column and row) and against the pinned plain-C oracle
-(oracle/pileup_oracle.c) on larger and on adversarial event lists.  (The file sorts last on purpose: it was written in a session with one GPU-minute left.  tools/pileup_gpu_probe.py made the same
-calls on a B200 -- profiles/r01_pileup_first_contact.txt, r01_pileup_edges.txt: all identical -- but this file itself had not run there.)"""
+"""ACIS pile-up on the GPU (marxb200_pileup_run / marxb200_pileup_events; marx/src/marxpileup.c:573-922,1121-1213; SURVEY.md 8f
+rank 4) against the stock program's committed output (tests/golden/pileup_*.npz, bit for bit, every column and row) and against the
+pinned plain-C oracle (oracle/pileup_oracle.c) on larger and on adversarial event lists.  Both device forms are covered: the fused
+single kernel (frames staged in shared memory) and the eight step kernels it falls back to for frames beyond its window."""
+import os
 import numpy as np
 import pytest
 
@@ -26,8 +27,16 @@ def test_device_reproduces_the_committed_stock_output(name):
     with marx_b200.MarxB200(PACK[name], seed=1, max_photons=1024) as m:
         before = m.launch_count()
         got, ms = m.pileup(cols, alpha, ft, seed)
-        assert m.launch_count() - before == 8 and ms > 0.0
+        assert m.launch_count() - before == 1 and ms > 0.0           # the fused kernel
         _same(got, ref, name)
+        os.environ["MARXB200_PILEUP_FUSED"] = "0"                     # the eight step kernels
+        try:
+            before = m.launch_count()
+            steps, _ = m.pileup(cols, alpha, ft, seed)
+            assert m.launch_count() - before == 8
+        finally:
+            del os.environ["MARXB200_PILEUP_FUSED"]
+        _same(steps, ref, name + " step kernels")
         # frames are independent: any split of the list at a frame boundary gives the same rows
         frame = (cols["t"].astype(np.float64) / ft).astype(np.uint32)
         cut = int(np.nonzero(np.diff(frame))[0][len(np.nonzero(np.diff(frame))[0]) // 2]) + 1
@@ -64,7 +73,11 @@ def test_device_equals_the_oracle_on_synthetic_lists(n, rate, alpha, ft, spot, c
     ref = P.oracle_pileup(cols, args, "c1_acis_s", 77)
     assert len(ref["t"]) > 0 and (ref["nphotons"] >= 2).any()
     with marx_b200.MarxB200(PACK["pileup_acis_s_bright"], seed=1, max_photons=1024) as m:
+        before = m.launch_count()
         got, _ = m.pileup(cols, alpha, ft, 77)
+        launches = m.launch_count() - before
+    # frames of up to 513 events stay in the fused kernel; the 10^4-events-per-frame list makes it hand over to the step kernels
+    assert launches == (9 if rate * ft > 600 else 1), launches
     _same(got, ref, "synthetic")
     assert int(got["nphotons"].sum()) <= n and (np.diff(got["frame"]) >= 0).all()
 
@@ -101,3 +114,21 @@ def test_edges_and_errors():
     with marx_b200.MarxB200(marx_b200.caldata_path("c3_letg_hrc_s.calpack"), seed=1, max_photons=1024) as m:
         with pytest.raises(marx_b200.MarxB200Error, match="ACIS"):
             m.pileup(cols, alpha, ft, seed)
+
+
+def test_pileup_of_the_device_resident_event_list():
+    """marxb200_pileup_events: `marx` then `marxpileup` without the column files in between.  The rows must equal
+    marxb200_pileup_run on the columns marx_write_photons would have written for the same list (and so the oracle's)."""
+    n, total_time, alpha, ft = 1 << 21, 1234.5, 0.5, 3.241
+    with marx_b200.MarxB200(PACK["pileup_acis_s_bright"], seed=21, max_photons=n) as m:
+        m.trace(0, n, time_base=0.0)
+        ph = m.download().copy()
+        dev, ms = m.pileup_events(total_time, alpha, ft, 5)
+        cols = {"ccd": ph["ccd_num"].astype(np.int8), "x": ph["y_pixel"].astype(np.float32), "y": ph["z_pixel"].astype(np.float32),
+                "t": (ph["arrival_time"] + total_time).astype(np.float32), "benergy": ph["pi"].astype(np.float32),
+                **{k: np.ascontiguousarray(ph["dither"][:, j]).astype(np.float32) for j, k in enumerate(P.DITHER)}}
+        host, _ = m.pileup(cols, alpha, ft, 5)
+        assert ms > 0.0 and len(dev["t"]) > 0 and (dev["nphotons"] >= 2).any()
+        _same(dev, host, "device-resident list")
+        ref = P.oracle_pileup(cols, ["Alpha=%r" % alpha, "FrameTime=%r" % ft, "FrameTransferTime=0.0"], "c1_acis_s", 5)
+        _same(dev, ref, "device-resident list vs oracle")

@@ -98,6 +98,12 @@ CASES = [
                            "DitherFile=%ASPSOL:6000%", "AspectBlur=0.2"], 52, 0, 12000),
     ("aspsol_ends_early_acis_i", ["MinEnergy=0.5", "MaxEnergy=6.0", "GratingType=NONE", "DetectorType=ACIS-I", "DitherModel=FILE",
                                   "DitherFile=%ASPSOL:1500%"], 53, 0, 12000),
+    # 64-bit ray indices: beyond 2^32 the record's tag (marx.h:98) wraps and only the full index keys the draws; the second
+    # batch straddles the boundary
+    ("ray_index_beyond_2_32", ["MinEnergy=0.3", "MaxEnergy=8.0", "GratingType=HETG", "DetectorType=ACIS-S", "DitherModel=INTERNAL"],
+     3, (1 << 33) + 12345, 12000),
+    ("ray_index_across_2_32", ["MinEnergy=0.3", "MaxEnergy=8.0", "GratingType=HETG", "DetectorType=ACIS-S", "DitherModel=INTERNAL"],
+     3, (1 << 32) - 6000, 12000),
     ("sector_files_off_unit_order", ["MinEnergy=0.8", "MaxEnergy=3.0", "GratingType=HETG", "DetectorType=ACIS-S", "DitherModel=INTERNAL",
                                      "Use_HETG_Sector_Files=no"], 8, 1000, 10000),
 ]
