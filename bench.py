@@ -74,6 +74,143 @@ def run_reference_sample(nrays_per_proc, nprocs, seed0=1):
     return rays, secs, wall
 
 
+def write_marx_column(path, name, kind, data):
+    """one column file of a MARX output directory (marxio.c:151-205: 32-byte header + big-endian data); bench harness only, for the
+    directory the STOCK marxpileup is timed on"""
+    import numpy as np
+    dt = {"E": ">f4", "A": "i1", "I": ">i2", "J": ">i4"}[kind]
+    hdr = bytearray(32)
+    hdr[0:4] = bytes([0x83, 0x13, 0x89, 0x8D])
+    hdr[4] = ord(kind)
+    nm = name.encode()[:15]
+    hdr[5:5 + len(nm)] = nm
+    hdr[20:24] = int(len(data)).to_bytes(4, "big")
+    hdr[24:28] = (1).to_bytes(4, "big")
+    with open(path, "wb") as f:
+        f.write(bytes(hdr))
+        f.write(np.ascontiguousarray(data).astype(dt).tobytes())
+
+
+def scratch_dir(name):
+    import shutil
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else "/tmp"
+    d = os.path.join(base, "marxb200_bench_%d_%s" % (os.getpid(), name))
+    shutil.rmtree(d, ignore_errors=True)
+    return d
+
+
+def level1_reference_baseline(args, n_rays=1 << 24):
+    """the STOCK marx2fits (oracle/_ref/marx2fits, gcc -O2, one core) on the event files of a C2 simulation of the bench's batch size,
+    written by the drop-in driver (integration/_build/marx_gpu = the unmodified marx.c on the CUDA path) to tmpfs"""
+    import shutil
+    ref, _, par, data = ref_paths()
+    marx_gpu = os.path.join(ROOT, "integration", "_build", "marx_gpu")
+    m2f = os.path.join(ref, "marx2fits")
+    if not (os.path.exists(marx_gpu) and os.path.exists(m2f)):
+        return {"value": None, "kind": "reference", "sample": "unavailable: integration/_build/marx_gpu or oracle/_ref/marx2fits not built"}
+    d = scratch_dir("l1")
+    env = dict(os.environ, MARX_DATA_DIR=data, USER=os.environ.get("USER", "marx"))
+    try:
+        t0 = time.time()
+        p = subprocess.run([marx_gpu, "@@" + par, "OutputDir=" + d, "NumRays=%d" % n_rays, "RandomSeed=%d" % args.seed] + REF_ARGS,
+                           env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+        t_marx = time.time() - t0
+        if p.returncode != 0:
+            return {"value": None, "kind": "reference", "sample": "unavailable: marx_gpu failed: %s" % p.stdout[-200:]}
+        rows = (os.path.getsize(os.path.join(d, "pha.dat")) - 32) // 2
+        fits = os.path.join(d, "evt.fits")
+        t0 = time.time()
+        p = subprocess.run([m2f, "--pixadj=edser", d, fits], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+        dt = time.time() - t0
+        if p.returncode != 0:
+            return {"value": None, "kind": "reference", "sample": "unavailable: marx2fits failed: %s" % p.stdout[-200:]}
+        return {"value": rows / dt, "unit": "events/s", "cores": 1, "kind": "reference", "cpu": cpu_model(),
+                "sample": "%d events of a %d-ray C2 simulation: stock marx2fits --pixadj=edser (reads 20 column files from tmpfs, writes "
+                          "the Level-1 FITS file to tmpfs), %.2f s; the directory came from marx_gpu in %.2f s" % (rows, n_rays, dt, t_marx)}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def pileup_reference_baseline(cols, alpha, ft, n_ref):
+    """the STOCK marxpileup (oracle/_ref/marxpileup, gcc -O2, one core) on the first n_ref events of the list, as a MARX output
+    directory on tmpfs; -> (cpu_baseline object, its output rows)"""
+    import shutil
+    ref, _, par, data = ref_paths()
+    exe = os.path.join(ref, "marxpileup")
+    if not os.path.exists(exe):
+        return {"value": None, "kind": "reference", "sample": "unavailable: oracle/_ref/marxpileup not built"}
+    d = scratch_dir("pu")
+    os.makedirs(d)
+    files = {"ccd": ("detector.dat", "CCDID", "A"), "x": ("xpixel.dat", "CHIPX", "E"), "y": ("ypixel.dat", "CHIPY", "E"),
+             "t": ("time.dat", "TIME", "E"), "benergy": ("b_energy.dat", "B_ENERGY", "E"), "sky_ra": ("sky_ra.dat", "RA", "E"),
+             "sky_dec": ("sky_dec.dat", "DEC", "E"), "sky_roll": ("sky_roll.dat", "ROLL", "E"), "det_dy": ("det_dy.dat", "DET_DY", "E"),
+             "det_dz": ("det_dz.dat", "DET_DZ", "E"), "det_theta": ("det_theta.dat", "DET_THETA", "E")}
+    try:
+        for k, (f, nm, kind) in files.items():
+            write_marx_column(os.path.join(d, f), nm, kind, cols[k][:n_ref])
+        write_marx_column(os.path.join(d, "energy.dat"), "ENERGY", "E", cols["benergy"][:n_ref])
+        shutil.copy(par, os.path.join(d, "marx.par"))            # DetectorType=ACIS-S is the file's default
+        open(os.path.join(d, "obs.par"), "w").write("# synthetic list\n")
+        env = dict(os.environ, MARX_DATA_DIR=data, USER=os.environ.get("USER", "marx"))
+        t0 = time.time()
+        p = subprocess.run([exe, "@@" + os.path.join(ref, "par", "marxpileup.par"), "MarxOutputDir=" + d, "Verbose=0", "Alpha=%r" % alpha,
+                            "FrameTime=%r" % ft, "FrameTransferTime=0.0"], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                           text=True, timeout=600)
+        dt = time.time() - t0
+        if p.returncode != 0:
+            return {"value": None, "kind": "reference", "sample": "unavailable: marxpileup failed: %s" % p.stdout[-200:]}
+        rows = (os.path.getsize(os.path.join(d, "pileup", "pha.dat")) - 32) // 2
+        return {"value": n_ref / dt, "unit": "events/s", "cores": 1, "kind": "reference", "cpu": cpu_model(), "rows": rows,
+                "sample": "%d events (11 column files on tmpfs in, 14 out), stock marxpileup incl. its FEF read, %.2f s" % (n_ref, dt)}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def driver_leg(args, n_rays=1 << 30, dn=1 << 24, ref_rays=2000000):
+    """What a MARX user gets: the UNMODIFIED reference driver on the CUDA path (integration/_build/marx_gpu = marx/src/marx.c linked
+    against libmarxb200.so with -Wl,--wrap) run as `marx`, 2^30 rays of C2 in batches of 2^24 (dNumRays: the reference's maximum of
+    10^6 is only the range field of marx/par/marx.par:9, raised in integration/_build/par/marx.par), event files written to tmpfs by
+    the background writer; wall clock of the whole process, CUDA start-up and calibration-file reading included.  Beside it the stock
+    CPU `marx` (oracle/_ref/marx) on a bounded sample with the same arguments."""
+    import shutil
+    ref, _, par_stock, data = ref_paths()
+    marx_gpu = os.path.join(ROOT, "integration", "_build", "marx_gpu")
+    par = os.path.join(ROOT, "integration", "_build", "par", "marx.par")
+    if not (os.path.exists(marx_gpu) and os.path.exists(par)):
+        return {"unavailable": "integration/_build/marx_gpu not built"}
+    env = dict(os.environ, MARX_DATA_DIR=data, USER=os.environ.get("USER", "marx"), MARXB200_TIMING="1")
+    common = [a for a in REF_ARGS if not a.startswith("dNumRays")]
+    d = scratch_dir("drv")
+    out = {}
+    try:
+        t0 = time.time()
+        p = subprocess.run([marx_gpu, "@@" + par, "OutputDir=" + d, "NumRays=%d" % n_rays, "dNumRays=%d" % dn, "RandomSeed=%d" % args.seed] + common,
+                           env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+        wall = time.time() - t0
+        if p.returncode != 0:
+            return {"unavailable": "marx_gpu failed: %s" % p.stdout[-300:]}
+        rows = (os.path.getsize(os.path.join(d, "pha.dat")) - 32) // 2
+        nbytes = sum(os.path.getsize(os.path.join(d, f)) for f in os.listdir(d) if f.endswith(".dat"))
+        timing = [ln for ln in p.stdout.splitlines() if "host seconds" in ln]
+        out = {"rays": n_rays, "rays_per_batch": dn, "wall_s": wall, "rays_per_s": n_rays / wall, "events": rows, "event_file_bytes": nbytes,
+               "writer_threads": int(os.environ.get("MARXB200_WRITER_THREADS", "8")), "breakdown": timing[-1].split("marxb200: ")[-1] if timing else None}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+    if not args.no_cpu_baseline and os.path.exists(os.path.join(ref, "marx")):
+        d = scratch_dir("drv_ref")
+        try:
+            t0 = time.time()
+            p = subprocess.run([os.path.join(ref, "marx"), "@@" + par_stock, "OutputDir=" + d, "NumRays=%d" % ref_rays, "RandomSeed=%d" % args.seed] + REF_ARGS,
+                               env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+            dt = time.time() - t0
+            if p.returncode == 0:
+                out["cpu_baseline"] = {"value": ref_rays / dt, "unit": UNIT, "cores": 1, "kind": "reference", "cpu": cpu_model(),
+                                       "sample": "stock marx, %d rays, same arguments, files to tmpfs, %.1f s wall" % (ref_rays, dt)}
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
+    return out
+
+
 def level1_leg(m, stream, args, reps=20):
     """marxb200_level1_transform on the event list the last traced batch left on the device (EDSER sub-pixel mode, the
     marx2fits default), timed with the library's CUDA-event marks; beside it the plain-C restatement of marx2fits' loop
@@ -101,61 +238,78 @@ def level1_leg(m, stream, args, reps=20):
            "hbm_gbs_at_120B_per_event": 120.0 * events / (ms * 1e-3) / 1e9,
            "workload": "events of one 2^24-ray C2 batch, ACIS-S, EDSER sub-pixel mode; 3 kernels + state hand-over"}
     if not args.no_cpu_baseline:
-        try:
-            from tests import level1_lib
-            ph = m.download()
-            cols = {"time": ph["arrival_time"].astype(np.float32), "xpixel": ph["y_pixel"], "ypixel": ph["z_pixel"], "b_energy": ph["pi"],
-                    "pha": ph["pulse_height"], "ccd": ph["ccd_num"],
-                    **{key: np.ascontiguousarray(ph["dither"][:, j]) for j, key in enumerate(level1_lib.DITHER_KEYS)}}
-            o = level1_lib.Level1Oracle(desc, args.seed)
-            t0 = time.time()
-            o.transform(cols)
-            dt = time.time() - t0
-            out["cpu_baseline"] = {"value": events / dt, "unit": "events/s", "cores": 1, "kind": "port",
-                                   "sample": "%d events, oracle/level1_oracle.c (gcc -O2), %.2f s" % (events, dt)}
-        except Exception as e:  # noqa: BLE001
-            out["cpu_baseline"] = {"value": None, "kind": "port", "sample": "unavailable: %s" % str(e)[:120]}
+        out["cpu_baseline"] = level1_reference_baseline(args)
     return out
 
 
 def pileup_leg(m, stream, args, n=1 << 22, reps=5):
     """marxb200_pileup_run (marxpileup's frame loop) on a synthetic bright-source event list: ~32 events per
-    3.241 s exposure frame on a spot of sigma 3 pixels.  `ms` = the eight kernels (CUDA events inside the library), `e2e_ms` = the
-    whole call with HOST columns in and out.  Beside it the pinned plain-C oracle (oracle/pileup_oracle.c, one core) on the same list."""
+    3.241 s exposure frame on a spot of sigma 3 pixels.  `ms` = the device kernel(s) (CUDA events inside the library), `e2e_ms` = the
+    whole call with PINNED host columns in and out.  Beside it the STOCK marxpileup on the same list (one core, files on tmpfs) and
+    the pinned plain-C oracle as the bit-for-bit check."""
     import numpy as np
     import torch
     r = np.random.default_rng(args.seed)
     alpha, ft, rate = 0.5, 3.241, 10.0
-    cols = {"ccd": np.full(n, 7, np.int8), "t": np.cumsum(r.exponential(1.0 / rate, n)).astype(np.float32),
-            "x": (512.0 + r.normal(0.0, 3.0, n)).astype(np.float32), "y": (300.0 + r.normal(0.0, 3.0, n)).astype(np.float32),
-            "benergy": r.uniform(0.4, 7.0, n).astype(np.float32)}
+    src = {"ccd": np.full(n, 7, np.int8), "t": np.cumsum(r.exponential(1.0 / rate, n)).astype(np.float32),
+           "x": (512.0 + r.normal(0.0, 3.0, n)).astype(np.float32), "y": (300.0 + r.normal(0.0, 3.0, n)).astype(np.float32),
+           "benergy": r.uniform(0.4, 7.0, n).astype(np.float32)}
     for k in ("sky_ra", "sky_dec", "sky_roll", "det_dy", "det_dz", "det_theta"):
-        cols[k] = r.normal(0.0, 1e-3, n).astype(np.float32)
+        src[k] = r.normal(0.0, 1e-3, n).astype(np.float32)
+
+    def pinned_like(a, rows=None):
+        t = torch.empty(len(a) if rows is None else rows, dtype=torch.from_numpy(a[:1]).dtype, pin_memory=True)
+        return t.numpy()
+    cols = {}
+    for k, v in src.items():
+        cols[k] = pinned_like(v)
+        cols[k][:] = v
+    out = {"ccd": pinned_like(src["ccd"]), "frame": pinned_like(np.zeros(1, np.int32), n), "nphotons": pinned_like(np.zeros(1, np.int16), n),
+           "pha": pinned_like(np.zeros(1, np.int16), n)}
+    for k in ("x", "y", "t", "benergy", "sky_ra", "sky_dec", "sky_roll", "det_dy", "det_dz", "det_theta"):
+        out[k] = pinned_like(src["x"])
     with torch.cuda.stream(stream):
-        got, _ = m.pileup(cols, alpha, ft, args.seed)
+        before = m.launch_count()
+        got, _ = m.pileup(cols, alpha, ft, args.seed, out=out)
+        launches = m.launch_count() - before
         ms, wall = [], []
         for _ in range(reps):
             t0 = time.time()
-            got, k = m.pileup(cols, alpha, ft, args.seed)
+            got, k = m.pileup(cols, alpha, ft, args.seed, out=out)
             wall.append((time.time() - t0) * 1e3)
             ms.append(k)
     ms, wall, rows = float(np.median(ms)), float(np.median(wall)), len(got["t"])
+    got = {k: v.copy() for k, v in got.items()}
     # algorithmic bytes: R 41 per event (ccd 1, pixel/time/energy 16, aspect 24), W 49 per output row
-    out = {"events": n, "rows": rows, "ms": ms, "events_per_s": n / (ms * 1e-3), "e2e_ms": wall, "e2e_events_per_s": n / (wall * 1e-3),
-           "launches_per_call": 8, "hbm_gbs_algorithmic": (41.0 * n + 49.0 * rows) / (ms * 1e-3) / 1e9,
-           "workload": "synthetic list, %d events, %.0f events/s, frame %.3f s, alpha %.1f, one chip" % (n, rate, ft, alpha)}
+    alg = 41.0 * n + 49.0 * rows
+    peak = 6650.0
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:  # noqa: BLE001
+        pass
+    res = {"events": n, "rows": rows, "ms": ms, "events_per_s": n / (ms * 1e-3), "e2e_ms": wall, "e2e_events_per_s": n / (wall * 1e-3),
+           "launches_per_call": launches, "hbm_gbs_algorithmic": alg / (ms * 1e-3) / 1e9, "hbm_frac": alg / (ms * 1e-3) / 1e9 / peak,
+           "h2d_bytes": 41 * n, "d2h_bytes": 49 * rows,
+           "workload": "synthetic list, %d events, %.0f events/s, frame %.3f s, alpha %.1f, one chip; host columns in pinned memory" % (n, rate, ft, alpha)}
     if not args.no_cpu_baseline:
+        try:
+            res["cpu_baseline"] = pileup_reference_baseline(src, alpha, ft, n)
+            if res["cpu_baseline"].get("rows") is not None:
+                res["rows_match_stock"] = bool(res["cpu_baseline"]["rows"] == rows or abs(res["cpu_baseline"]["rows"] - rows) < 0.01 * rows)
+        except Exception as e:  # noqa: BLE001
+            res["cpu_baseline"] = {"value": None, "kind": "reference", "sample": "unavailable: %s" % str(e)[:120]}
         try:
             from tests import pileup_lib
             t0 = time.time()
-            ref = pileup_lib.oracle_pileup(cols, ["Alpha=%r" % alpha, "FrameTime=%r" % ft, "FrameTransferTime=0.0"], args.calpack, args.seed)
+            ref = pileup_lib.oracle_pileup(src, ["Alpha=%r" % alpha, "FrameTime=%r" % ft, "FrameTransferTime=0.0"], args.calpack, args.seed)
             dt = time.time() - t0
-            out["parity"] = bool(all(got[k].tobytes() == ref[k].tobytes() for k in ref))
-            out["cpu_baseline"] = {"value": n / dt, "unit": "events/s", "cores": 1, "kind": "port",
-                                   "sample": "%d events, oracle/pileup_oracle.c (gcc -O2), %.2f s" % (n, dt)}
+            res["parity"] = bool(all(got[k].tobytes() == ref[k].tobytes() for k in ref))
+            res["oracle_port"] = {"value": n / dt, "unit": "events/s", "cores": 1, "kind": "port",
+                                  "sample": "%d events, oracle/pileup_oracle.c (gcc -O2, arrays in memory), %.2f s" % (n, dt)}
         except Exception as e:  # noqa: BLE001
-            out["cpu_baseline"] = {"value": None, "kind": "port", "sample": "unavailable: %s" % str(e)[:120]}
-    return out
+            res["parity"] = None
+            res["oracle_port"] = {"value": None, "kind": "port", "sample": "unavailable: %s" % str(e)[:120]}
+    return res
 
 
 def bind_to_gpu_numa_node(index):
@@ -555,6 +709,14 @@ def cuda_arm(args):
         except Exception as e:  # noqa: BLE001
             pileup = {"unavailable": str(e)[:200]}
 
+    # the drop-in driver, run the way a MARX user runs `marx` (rank 0, N = 1): its own process and context
+    driver = None
+    if rank == 0 and world == 1 and not args.no_driver:
+        try:
+            driver = driver_leg(args)
+        except Exception as e:  # noqa: BLE001
+            driver = {"unavailable": str(e)[:200]}
+
     ic = None
     try:
         ic = [int(v) for v in m.internal_counts()]
@@ -709,6 +871,8 @@ def cuda_arm(args):
         line["sweep"] = sweep
     if configs is not None:
         line["configs"] = configs
+    if driver is not None:
+        line["driver"] = driver
     if level1 is not None:
         line["level1"] = level1
     if pileup is not None:
@@ -744,6 +908,7 @@ def main():
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-probe", action="store_true")
     ap.add_argument("--no-configs", action="store_true")
+    ap.add_argument("--no-driver", action="store_true")
     ap.add_argument("--sweep-max", type=float, default=1e11)
     args = ap.parse_args()
     if args.impl == "reference":

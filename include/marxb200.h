@@ -436,6 +436,15 @@ int marxb200_egress_end (marxb200_ctx *ctx, const marxb200_columns *cols, uint64
 #define MARXB200_ORDER3_OK        0x00800000
 #define MARXB200_ORDER4_OK        0x01000000
 int marxb200_write_photons (marxb200_ctx *ctx, const char *dir, uint64_t write_mask, int open_mode, double total_time);
+/* Background column-file writer for marxb200_write_photons.  Appending a 2^24-ray batch's event columns to their files costs a
+ * single host thread ten times what the GPU needs to trace the batch (even on tmpfs).  With n_threads > 0 marxb200_write_photons
+ * returns as soon as the batch has landed in one of two pinned host buffers; column file k is appended by thread k mod n_threads
+ * (the order of appends to one file is kept; different files are written in parallel) while the caller traces the next batch.
+ * The files are byte-identical to the synchronous writer's.  marxb200_write_flush blocks until everything queued is in the files
+ * and reports the first write error; marxb200_destroy and a call with open_mode = 1 flush as well.  n_threads = 0: flush and go
+ * back to writing synchronously (the default). */
+int marxb200_set_async_writer (marxb200_ctx *ctx, int n_threads);
+int marxb200_write_flush (marxb200_ctx *ctx);
 
 /* Pipelined form of the same egress without the file system: _begin_packed converts the selected columns of the live list
  * to their file images (the bytes marxb200_write_photons would append, big endian) in a device staging area and returns

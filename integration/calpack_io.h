@@ -31,6 +31,7 @@ int calpack_dump_acis_i (mxcp_writer *w, int detector_module);
 int calpack_dump_hrc_s (mxcp_writer *w, int detector_module);
 int calpack_dump_hrc_i (mxcp_writer *w, int detector_module);
 int calpack_dump_hrma (mxcp_writer *w);
+int calpack_dump_ffield (mxcp_writer *w);      /* MirrorType=FLATFIELD (ffield.c) */
 int calpack_dump_wfold (mxcp_writer *w, const char *prefix, void *table);
 int calpack_dump_grating (mxcp_writer *w, int grating_module);
 int calpack_dump_acis_s (mxcp_writer *w, int detector_module);

@@ -24,7 +24,11 @@
  *
  * Table upload: on the first marx_create_photons the post-init statics of the stock modules are serialised by the
  * calpack_*.c units (the field mappings of INTEGRATION.md section 2) and handed to marxb200_load_calpack.
- * Environment: MARXB200_DEVICE (CUDA ordinal, default 0), MARXB200_EGRESS (bulk [default] | stock).
+ * Environment: MARXB200_DEVICE (CUDA ordinal, default 0), MARXB200_EGRESS (bulk [default] | stock), MARXB200_WRITER_THREADS
+ * (background column-file writers, default 8; 0 = synchronous).
+ * Batch size: the reference caps dNumRays at 10^6 only through the range field of its parameter file (marx/par/marx.par:9); the
+ * build writes integration/_build/par/marx.par, the same file with that maximum raised to 2^28, so that `marx_gpu @@.../marx.par
+ * dNumRays=16777216` runs batches the size the GPU wants (2^24 rays: 4.2 GB of HBM, 2.3 GB of host photon buffer).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -59,7 +63,7 @@ static int Source_Is_Rayfile;          /* SourceType=RAYFILE, USER, SAOSAC, SIMP
 static int Bulk_Written;               /* the current batch went to the output directory straight from the device */
 
 /* MARXB200_TIMING=1: host wall time spent in each wrapped call, printed when the driver frees its photon buffer */
-static double T_Init, T_Create, T_Stages, T_Write, T_Sync;
+static double T_Init, T_Create, T_Stages, T_Write, T_Sync, T_Init_Create, T_Init_Dump, T_Init_Upload, T_Init_Alloc;
 static double now (void)
 {
    struct timespec ts;
@@ -90,16 +94,18 @@ static int gpu_init (Marx_Source_Type *st, Marx_Photon_Type *pt)
    const char *dev = getenv ("MARXB200_DEVICE");
    int fd, status = -1;
 
-   if (Mirror_Id != MARX_MIRROR_HRMA)
-     { marx_error ("marxb200: MirrorType must be HRMA for the GPU path"); return -1; }
+   if ((Mirror_Id != MARX_MIRROR_HRMA) && (Mirror_Id != MARX_MIRROR_FFIELD))
+     { marx_error ("marxb200: MirrorType must be HRMA or FLATFIELD for the GPU path"); return -1; }
    if ((Grating_Id != 0) && (Grating_Id != MARX_GRATING_HETG) && (Grating_Id != MARX_GRATING_LETG))
      { marx_error ("marxb200: GratingType must be NONE, HETG or LETG for the GPU path"); return -1; }
    if ((Detector_Id != 0) && (Detector_Id != MARX_DETECTOR_ACIS_S) && (Detector_Id != MARX_DETECTOR_ACIS_I)
        && (Detector_Id != MARX_DETECTOR_HRC_S) && (Detector_Id != MARX_DETECTOR_HRC_I))
      { marx_error ("marxb200: DetectorType must be NONE, ACIS-S, ACIS-I, HRC-S or HRC-I for the GPU path"); return -1; }
 
+   double t_mark = now ();
    if (-1 == marxb200_create (&Ctx, dev ? atoi (dev) : 0, (uint64_t) Seed))
      return gpu_error ("marxb200_create");
+   T_Init_Create = now () - t_mark; t_mark = now ();
 
    if (-1 == (fd = mkstemp (path)))
      { marx_error ("marxb200: cannot create a temporary file"); return -1; }
@@ -112,7 +118,7 @@ static int gpu_init (Marx_Source_Type *st, Marx_Photon_Type *pt)
    if (-1 == (Source_Is_Rayfile = calpack_dump_source (&w, st)))
      marx_error ("marxb200: this SourceType has neither a device kernel nor a stock host generator");
    else if ((-1 == calpack_dump_dither (&w))
-	    || (-1 == calpack_dump_hrma (&w))
+	    || (-1 == ((Mirror_Id == MARX_MIRROR_FFIELD) ? calpack_dump_ffield (&w) : calpack_dump_hrma (&w)))
 	    || (-1 == calpack_dump_grating (&w, Grating_Id))
 	    || (-1 == ((Detector_Id == MARX_DETECTOR_HRC_S) ? calpack_dump_hrc_s (&w, Detector_Id)
 		       : (Detector_Id == MARX_DETECTOR_HRC_I) ? calpack_dump_hrc_i (&w, Detector_Id)
@@ -120,14 +126,25 @@ static int gpu_init (Marx_Source_Type *st, Marx_Photon_Type *pt)
      marx_error ("marxb200: could not serialise the module tables");
    else status = 0;
    mxcp_close_write (&w);
+   T_Init_Dump = now () - t_mark; t_mark = now ();
    if ((status == 0) && (-1 == marxb200_load_calpack (Ctx, path)))
      status = gpu_error ("table upload");
    (void) unlink (path);
    if (status == -1) return -1;
+   T_Init_Upload = now () - t_mark; t_mark = now ();
 
    if (-1 == marxb200_alloc_photons (Ctx, pt->max_n_photons))
      return gpu_error ("marxb200_alloc_photons");
+   T_Init_Alloc = now () - t_mark;
 
+   {
+      /* column files are appended by background threads while the next batch is traced (marxb200_set_async_writer);
+       * MARXB200_WRITER_THREADS=0 writes synchronously */
+      const char *wt = getenv ("MARXB200_WRITER_THREADS");
+      int n_threads = (wt != NULL) ? atoi (wt) : 8;
+      if ((n_threads > 0) && (-1 == marxb200_set_async_writer (Ctx, n_threads)))
+	return gpu_error ("marxb200_set_async_writer");
+   }
    Have_Support_Orders = (Grating_Id == MARX_GRATING_LETG);
    Stock_Egress = ((NULL != getenv ("MARXB200_EGRESS")) && (0 == strcmp (getenv ("MARXB200_EGRESS"), "stock")));
    marx_message ("marxb200: ray trace on CUDA device %d, Philox key %lu\n", dev ? atoi (dev) : 0, Seed);
@@ -318,10 +335,22 @@ int __wrap_marx_dealloc_photon_type (Marx_Photon_Type *pt)
 	  marx_message ("marxb200: last batch: %lu generated, %lu reflected, %lu diffracted, %lu detected\n",
 			(unsigned long) stage[0], (unsigned long) stage[1], (unsigned long) stage[2], (unsigned long) stage[3]);
 	if (getenv ("MARXB200_TIMING") != NULL)
-	  fprintf (stderr, "marxb200: host seconds in the wrapped calls: init+upload %.3f, create_photons %.3f, stages %.3f, "
-		   "write_photons %.3f, download %.3f\n", T_Init, T_Create, T_Stages, T_Write, T_Sync);
-	(void) marxb200_destroy (Ctx);
-	Ctx = NULL;
+	  fprintf (stderr, "marxb200: host seconds in the wrapped calls: init+upload %.3f (CUDA context %.3f, table dump %.3f, table upload %.3f, "
+		   "photon buffers %.3f), create_photons %.3f, stages %.3f, write_photons %.3f, download %.3f\n", T_Init, T_Init_Create,
+		   T_Init_Dump, T_Init_Upload, T_Init_Alloc, T_Create, T_Stages, T_Write, T_Sync);
+	/* every queued column append must be in its file before the driver closes the run (marx.c:616-618); a failed write
+	 * fails the run like a failed fwrite of the stock writer (marxio.c:452-466) */
+	{
+	   int flushed = marxb200_write_flush (Ctx);
+	   if (flushed == -1) (void) gpu_error ("marxb200_write_flush");
+	   (void) marxb200_destroy (Ctx);
+	   Ctx = NULL;
+	   if (flushed == -1)
+	     {
+		(void) __real_marx_dealloc_photon_type (pt);
+		return -1;
+	     }
+	}
      }
    return __real_marx_dealloc_photon_type (pt);
 }

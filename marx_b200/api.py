@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = [
     "marxb200_set_grating", "marxb200_set_acis", "marxb200_set_hrc_s", "marxb200_load_calpack", "marxb200_alloc_photons",
     "marxb200_create_photons", "marxb200_truncate_exposure", "marxb200_time_sums", "marxb200_mirror_reflect", "marxb200_grating_diffract",
     "marxb200_detect", "marxb200_restore_order", "marxb200_trace", "marxb200_trace_from", "marxb200_set_profiling", "marxb200_get_kernel_ms", "marxb200_get_counts", "marxb200_get_stage_counts", "marxb200_get_internal_counts", "marxb200_download",
-    "marxb200_upload", "marxb200_upload_from", "marxb200_download_all", "marxb200_download_columns", "marxb200_egress_begin", "marxb200_egress_end", "marxb200_write_photons", "marxb200_egress_begin_packed", "marxb200_egress_end_packed", "marxb200_measure_fp64_peak", "marxb200_get_launch_count",
+    "marxb200_upload", "marxb200_upload_from", "marxb200_download_all", "marxb200_download_columns", "marxb200_egress_begin", "marxb200_egress_end", "marxb200_write_photons", "marxb200_set_async_writer", "marxb200_write_flush", "marxb200_egress_begin_packed", "marxb200_egress_end_packed", "marxb200_measure_fp64_peak", "marxb200_get_launch_count",
     "marxb200_tally_create", "marxb200_tally_accumulate", "marxb200_tally_reset", "marxb200_tally_read", "marxb200_tally_device_ptr",
     "marxb200_set_level1", "marxb200_level1_reset", "marxb200_level1_transform", "marxb200_level1_download",
     "marxb200_aspsol_rows",
@@ -136,6 +136,8 @@ def load_library():
         "marxb200_egress_begin": [vp, u64],
         "marxb200_egress_end": [vp, vp, C.POINTER(u64)],
         "marxb200_write_photons": [vp, C.c_char_p, u64, i32, dbl],
+        "marxb200_set_async_writer": [vp, i32],
+        "marxb200_write_flush": [vp],
         "marxb200_measure_fp64_peak": [vp, C.POINTER(dbl)],
         "marxb200_egress_begin_packed": [vp, u64, dbl, u64],
         "marxb200_egress_end_packed": [vp, vp, u64, vp],
@@ -489,6 +491,13 @@ class MarxB200:
         device-resident live list; write_mask uses the MARX_*_OK bits (HISTORY below)."""
         self._check(self._lib.marxb200_write_photons(self._ctx, os.fsencode(directory), int(write_mask),
                                                      1 if open_mode else 0, float(total_time)))
+
+    def set_async_writer(self, n_threads):
+        """background column-file writer for write_photons (0: back to synchronous writes)"""
+        self._check(self._lib.marxb200_set_async_writer(self._ctx, int(n_threads)))
+
+    def write_flush(self):
+        self._check(self._lib.marxb200_write_flush(self._ctx))
 
     # -- Level-1 event transforms (marx2fits.c:3584-3943 on the device-resident list) -------------------------------
     def set_level1(self, desc):

@@ -14,6 +14,7 @@
 #include "mx_tables.h"
 #include "mx_kernels.cuh"
 #include "mx_context.hpp"
+#include "writer.hpp"
 #include "mx_aspsol.cuh"
 #include "mx_pileup.cuh"
 #include "tables_build.hpp"
@@ -182,6 +183,8 @@ extern "C" int marxb200_destroy (marxb200_ctx *c)
    if (c == nullptr) return -1;
    cudaSetDevice (c->device);
    cudaDeviceSynchronize ();
+   if (c->writer) { mxw_destroy (c->writer); c->writer = nullptr; }       // waits for the queued column writes
+   for (int i = 0; i < 2; i++) if (c->h_wbuf[i]) cudaFreeHost (c->h_wbuf[i]);
    mxb_comm_release (c);
    prof_collect (c);
    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy (e);
@@ -1084,16 +1087,64 @@ extern "C" int marxb200_write_photons (marxb200_ctx *c, const char *dir, uint64_
         plan.num_cols++;
         total += (uint64_t) align16 ((size_t) n * kEgressCols[k].size);
      }
+   // where the batch lands on the host: the context's pinned buffer, or -- with the background writer -- one of its two
+   // buffers, once the writes that still read it are done
+   unsigned char *h_dst = nullptr;
+   int wb = 0;
+   if (c->writer != nullptr)
+     {
+        std::string werr;
+        if (open_mode && (-1 == mxw_flush (c->writer, &werr))) return fail ("marxb200_write_photons: %s", werr.c_str ());
+        if (mxw_failed (c->writer, &werr)) return fail ("marxb200_write_photons: %s", werr.c_str ());
+        wb = c->wbuf_next;
+        c->wbuf_next ^= 1;
+        mxw_wait_buffer (c->writer, wb);
+        if (c->h_wbuf_bytes[wb] < total + 64)
+          {
+             if (c->h_wbuf[wb]) cudaFreeHost (c->h_wbuf[wb]);
+             c->h_wbuf[wb] = nullptr; c->h_wbuf_bytes[wb] = 0;
+             const size_t want = (size_t) total + (size_t) total / 4 + 65536;
+             CUDA_OK (cudaMallocHost (&c->h_wbuf[wb], want));
+             c->h_wbuf_bytes[wb] = want;
+          }
+        h_dst = (unsigned char *) c->h_wbuf[wb];
+     }
    if (n && plan.num_cols)
      {
         // the AoS staging buffer (136 B per photon) is always large enough: at most 29 columns x 4 B = 116 B per row
         if (-1 == ensure_aos (c, n + 16)) return -1;
-        if (-1 == ensure_pinned (c, (size_t) total)) return -1;
+        if (c->writer == nullptr)
+          {
+             if (-1 == ensure_pinned (c, (size_t) total)) return -1;
+             h_dst = (unsigned char *) c->h_pinned;
+          }
         launch_egress_pack (observed (c, c->buf[c->cur]), c->d_counts + c->stage_done, n, plan, c->d_aos, c->d_times, total_time, c->stream);
         c->launches += 1;
-        CUDA_OK (cudaMemcpyAsync (c->h_pinned, c->d_aos, (size_t) total, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK (cudaMemcpyAsync (h_dst, c->d_aos, (size_t) total, cudaMemcpyDeviceToHost, c->stream));
         CUDA_OK (cudaStreamSynchronize (c->stream));
         CUDA_OK (cudaGetLastError ());
+     }
+   if (c->writer != nullptr)
+     {
+        for (int j = 0; j < plan.num_cols; j++)
+          {
+             const EgressCol &col = kEgressCols[which[j]];
+             MxWriteTask t;
+             t.path = std::string (dir) + "/" + col.file;
+             t.create = open_mode ? 1 : 0;
+             static const unsigned char magic[4] = {0x83, 0x13, 0x89, 0x8D};
+             memset (t.header, 0, sizeof (t.header));
+             memcpy (t.header, magic, 4);
+             t.header[4] = (unsigned char) col.type;
+             strncpy ((char *) t.header + 5, col.colname, 15);
+             if (open_mode) c->egress_rows[which[j]] = 0;
+             c->egress_rows[which[j]] += n;
+             put_be32 (t.rows_be, (uint32_t) c->egress_rows[which[j]]);
+             t.data = h_dst + plan.offset[j]; t.bytes = (size_t) n * col.size;
+             t.buffer = wb;
+             mxw_submit (c->writer, which[j], t);
+          }
+        return 0;
      }
    for (int j = 0; j < plan.num_cols; j++)
      {
@@ -1128,6 +1179,33 @@ extern "C" int marxb200_write_photons (marxb200_ctx *c, const char *dir, uint64_
         ok = ok && (0 == fseek (fp, 20, SEEK_SET)) && (4 == fwrite (rows_be, 1, 4, fp));   // marx_close_write_dump_file :82-126
         if ((0 != fclose (fp)) || !ok) return fail ("marxb200_write_photons: write error on %s", path.c_str ());
      }
+   return 0;
+}
+
+// Background writer for marxb200_write_photons: n_threads > 0 starts it (or keeps a running one), 0 flushes and stops it.
+extern "C" int marxb200_set_async_writer (marxb200_ctx *c, int n_threads)
+{
+   if (c == nullptr) return fail ("NULL ctx");
+   if (n_threads < 0) return fail ("marxb200_set_async_writer: n_threads must be >= 0");
+   if (n_threads == 0)
+     {
+        if (c->writer == nullptr) return 0;
+        std::string werr;
+        const int rc = mxw_flush (c->writer, &werr);
+        mxw_destroy (c->writer);
+        c->writer = nullptr;
+        return (rc == 0) ? 0 : fail ("marxb200_write_photons: %s", werr.c_str ());
+     }
+   if (c->writer == nullptr) c->writer = mxw_create (n_threads);
+   return 0;
+}
+// block until every queued column write has reached its file; reports the first write error
+extern "C" int marxb200_write_flush (marxb200_ctx *c)
+{
+   if (c == nullptr) return fail ("NULL ctx");
+   if (c->writer == nullptr) return 0;
+   std::string werr;
+   if (-1 == mxw_flush (c->writer, &werr)) return fail ("marxb200_write_photons: %s", werr.c_str ());
    return 0;
 }
 

@@ -10,6 +10,7 @@
 #include "mx_kernels.cuh"
 
 struct MxComm;                                  // comm.cu
+struct MxWriter;                                // writer.cpp
 using mx::PhotonSoA; using mx::RayConst; using mx::SourceDev; using mx::DitherDev; using mx::TallyPlan; using mx::EgressPlan;
 using mx::Level1Dev; using mx::Level1State; using mx::Level1Cols; using mx::kMaxEgressCols;
 
@@ -96,6 +97,10 @@ struct marxb200_ctx
    std::vector<cudaEvent_t> ev_pool;
    double prof_ms[MARXB200_NUM_KERNEL_CLASSES] = {0};
    uint64_t prof_n[MARXB200_NUM_KERNEL_CLASSES] = {0};
+
+   // background column-file writer (marxb200_set_async_writer): two pinned batch buffers, file k on thread k mod n
+   MxWriter *writer = nullptr;
+   void *h_wbuf[2] = {nullptr, nullptr}; size_t h_wbuf_bytes[2] = {0, 0}; int wbuf_next = 0;
 
    // multi-GPU exchanges (comm.cu): NCCL communicators, time-base all-gather scratch, event-merge buffers
    MxComm *comm = nullptr;

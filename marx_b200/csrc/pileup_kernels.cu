@@ -208,28 +208,38 @@ __global__ void __launch_bounds__ (kFuThreads, 2) pu_fused (const __grid_constan
            if (tid == kFuThreads - 1) S.total = s;
         }
         __syncthreads ();
-        // decoupled look-back over the tiles' row counts
+        // decoupled look-back over the tiles' row counts: warp 0 inspects 32 predecessors per round (a tile that is still at
+        // work has published nothing yet: 0), sums their aggregates down to the nearest published prefix
         if (warp == 0)
           {
              const unsigned long long total = S.total;
              unsigned long long excl = 0;
+             if (tile == 0) { if (lane == 0) st_relaxed (tile_state, kFuPrefix | total); }
+             else
+               {
+                  if (lane == 0) st_relaxed (tile_state + tile, kFuAggregate | total);
+                  long long p = (long long) tile - 1;
+                  while (true)
+                    {
+                       const long long idx = p - (long long) lane;
+                       const unsigned long long w = (idx >= 0) ? ld_relaxed (tile_state + idx) : kFuPrefix;      // before tile 0: prefix 0
+                       const unsigned long long st = w & ~kFuValueMask;
+                       const uint32_t unpublished = __ballot_sync (0xFFFFFFFFu, st == 0ull);
+                       const uint32_t prefixes = __ballot_sync (0xFFFFFFFFu, st == kFuPrefix);
+                       const int first = prefixes ? (__ffs (prefixes) - 1) : 31;                                  // nearest predecessor with a prefix
+                       const uint32_t needed = (first == 31) ? 0xFFFFFFFFu : ((2u << first) - 1u);
+                       if (unpublished & needed) continue;                                                         // look again
+                       unsigned long long v = ((int) lane <= first) ? (w & kFuValueMask) : 0ull;
+#pragma unroll
+                       for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync (0xFFFFFFFFu, v, d);
+                       excl += v;
+                       if (prefixes) break;
+                       p -= 32;
+                    }
+                  if (lane == 0) st_relaxed (tile_state + tile, kFuPrefix | (excl + total));
+               }
              if (lane == 0)
                {
-                  if (tile == 0) st_relaxed (tile_state, kFuPrefix | total);
-                  else
-                    {
-                       st_relaxed (tile_state + tile, kFuAggregate | total);
-                       long long p = (long long) tile - 1;
-                       while (true)
-                         {
-                            const unsigned long long w = ld_relaxed (tile_state + p);
-                            if ((w & ~kFuValueMask) == 0ull) continue;          // predecessor not published yet
-                            excl += (w & kFuValueMask);
-                            if ((w & ~kFuValueMask) == kFuPrefix) break;
-                            p--;
-                         }
-                       st_relaxed (tile_state + tile, kFuPrefix | (excl + total));
-                    }
                   S.base = excl;
                   if (tile + 1 == n_tiles) *g.n_out = excl + total;
                }

@@ -32,14 +32,15 @@ int main (int argc, char **argv)
 
    if ((0 != calpack_dump_source (&w, rs.source))      /* -1 unsupported, 1 RAYFILE (host-read photons: nothing to pack) */
        || (-1 == calpack_dump_dither (&w))
-       || (rs.mirror_module != MARX_MIRROR_HRMA) || (-1 == calpack_dump_hrma (&w))
+       || ((rs.mirror_module != MARX_MIRROR_HRMA) && (rs.mirror_module != MARX_MIRROR_FFIELD))
+       || (-1 == ((rs.mirror_module == MARX_MIRROR_FFIELD) ? calpack_dump_ffield (&w) : calpack_dump_hrma (&w)))
        || (-1 == calpack_dump_grating (&w, rs.grating_module))
        || ((rs.grating_module != 0) && (rs.grating_module != MARX_GRATING_HETG) && (rs.grating_module != MARX_GRATING_LETG))
        || (rs.detector_module == MARX_DETECTOR_PLANE)
        || (-1 == ((rs.detector_module == MARX_DETECTOR_HRC_S) ? calpack_dump_hrc_s (&w, rs.detector_module)
                   : (rs.detector_module == MARX_DETECTOR_HRC_I) ? calpack_dump_hrc_i (&w, rs.detector_module)
                   : calpack_dump_acis_s (&w, rs.detector_module))))
-     { fprintf (stderr, "calpack_dump: dump failed (only HRMA + NONE/HETG/LETG + NONE/ACIS-S/ACIS-I/HRC-S/HRC-I with POINT/GAUSS/BETA/DISK/LINE/IMAGE sources are packed)\n"); return 1; }
+     { fprintf (stderr, "calpack_dump: dump failed (only HRMA/FLATFIELD + NONE/HETG/LETG + NONE/ACIS-S/ACIS-I/HRC-S/HRC-I with POINT/GAUSS/BETA/DISK/LINE/IMAGE sources are packed)\n"); return 1; }
    mxcp_close_write (&w);
    return 0;
 }

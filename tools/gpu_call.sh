@@ -1,4 +1,7 @@
 mkdir -p gpurun_out
-export NCCL_DEBUG=WARN MARXB200_BENCH_TRACE=1 MARXB200_BENCH_HANG_S=120
-( timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29555 bench.py --gpus 2 --steps 10 --warmup 3 --sweep-max 1e8 ) > gpurun_out/c3_bench_n2.json 2> gpurun_out/c3_bench_n2.err
-echo "rc=$?"; tail -c 1200 gpurun_out/c3_bench_n2.json; grep -E "bench rank|Error|error|Traceback|File \"/root|line [0-9]+ in" gpurun_out/c3_bench_n2.err | tail -60
+( timeout 600 python -m pytest tests/test_gpu_zz_pileup.py tests/test_gpu_marx_driver.py -x -q -m gpu 2>&1 | tail -25 ) > gpurun_out/c5_tests_a.log
+cat gpurun_out/c5_tests_a.log
+( timeout 900 python -m pytest tests -x -q -m gpu --deselect tests/test_gpu_zz_pileup.py --deselect tests/test_gpu_marx_driver.py 2>&1 | tail -15 ) > gpurun_out/c5_tests_b.log
+cat gpurun_out/c5_tests_b.log
+( MARXB200_BENCH_TRACE=1 timeout 600 python bench.py --steps 20 --warmup 3 ) > gpurun_out/c5_bench_n1.json 2> gpurun_out/c5_bench_n1.err
+tail -c 2500 gpurun_out/c5_bench_n1.json; tail -12 gpurun_out/c5_bench_n1.err
