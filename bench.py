@@ -52,12 +52,13 @@ def ref_paths():
     return ref, os.path.join(ref, "marx_trace_bench"), os.path.join(ref, "par", "marx.par"), os.path.join(ref, "data")
 
 
-def run_reference_sample(nrays_per_proc, nprocs, seed0=1):
+def run_reference_sample(nrays_per_proc, nprocs, seed0=1, exe_name="marx_trace_bench"):
     """nprocs concurrent single-threaded reference processes (the reference's own multi-core mode:
     N independent `marx` runs); returns (total rays, wall seconds of the trace loops)."""
     ref, exe, par, data = ref_paths()
+    exe = os.path.join(ref, exe_name)
     if not os.path.exists(exe):
-        raise RuntimeError("oracle/_ref/marx_trace_bench not built (run __graft_entry__.build() where /root/reference exists)")
+        raise RuntimeError("oracle/_ref/%s not built (run __graft_entry__.build() where /root/reference exists)" % exe_name)
     env = dict(os.environ, MARX_DATA_DIR=data)
     t0 = time.time()
     procs = [subprocess.Popen([exe, str(nrays_per_proc), "@@" + par, "RandomSeed=%d" % (seed0 + k)] + REF_ARGS,
@@ -492,6 +493,43 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+def reference_full_program(per_proc, nprocs, seed0=1000):
+    """the reference's own multi-core mode end to end: N independent stock `marx` processes, each writing its output
+    directory (tmpfs), time to the last exit, then `marxcat` merging the N directories in time order (marxcat.c:491-535), timed
+    separately.  -> dict"""
+    import shutil
+    ref, _, par, data = ref_paths()
+    marx, marxcat = os.path.join(ref, "marx"), os.path.join(ref, "marxcat")
+    if not (os.path.exists(marx) and os.path.exists(marxcat)):
+        return {"unavailable": "oracle/_ref/marx or marxcat not built"}
+    base = scratch_dir("refrun")
+    os.makedirs(base)
+    env = dict(os.environ, MARX_DATA_DIR=data, USER=os.environ.get("USER", "marx"))
+    try:
+        t0 = time.time()
+        procs = [subprocess.Popen([marx, "@@" + par, "OutputDir=" + os.path.join(base, "run_%d" % k), "NumRays=%d" % per_proc,
+                                   "RandomSeed=%d" % (seed0 + k)] + REF_ARGS, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env)
+                 for k in range(nprocs)]
+        rcs = [p.wait() for p in procs]
+        wall = time.time() - t0
+        if any(rcs):
+            return {"unavailable": "a stock marx process failed"}
+        t0 = time.time()
+        p = subprocess.run([marxcat] + [os.path.join(base, "run_%d" % k) for k in range(nprocs)] + [os.path.join(base, "merged")],
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+        t_cat = time.time() - t0
+        rows = None
+        f = os.path.join(base, "merged", "pha.dat")
+        if p.returncode == 0 and os.path.exists(f):
+            rows = (os.path.getsize(f) - 32) // 2
+        return {"processes": nprocs, "rays_per_process": per_proc, "wall_s_to_last_exit": wall, "rays_per_s": per_proc * nprocs / wall,
+                "marxcat_s": t_cat, "marxcat_ok": p.returncode == 0, "merged_events": rows,
+                "rays_per_s_including_marxcat": per_proc * nprocs / (wall + t_cat),
+                "note": "whole stock program incl. calibration-file reading and event-file output to tmpfs (default OutputVectors)"}
+    finally:
+        shutil.rmtree(base, ignore_errors=True)
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -512,11 +550,30 @@ def reference_arm(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": "%d rays per process x %d processes per step" % (per_proc, cores)},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "cpu": cpu_model(),
                          "sample": "%d steps x %d processes x %d rays, stock MARX stages + stock RNG, trace loop only "
                                    "(oracle/_ref/marx_trace_bench, gcc -O2)" % (args.steps, cores, per_proc)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    # BASELINE.md 3 extras, reported beside the headline: the -O3 / AVX2+FMA build of the same harness, one core alone, and the whole
+    # stock program (output files + marxcat merge)
+    extras = {}
+    try:
+        rays, secs, _ = run_reference_sample(per_proc, cores, seed0=501, exe_name="marx_trace_bench_o3")
+        extras["O3_x86_64_v3_all_cores"] = {"value": rays / secs, "unit": UNIT, "cores": cores,
+                                            "sample": "same harness, reference compiled gcc -O3 -march=x86-64-v3, %d processes x %d rays" % (cores, per_proc)}
+    except Exception as e:  # noqa: BLE001
+        extras["O3_x86_64_v3_all_cores"] = {"unavailable": str(e)[:160]}
+    try:
+        rays, secs, _ = run_reference_sample(per_proc, 1, seed0=601)
+        extras["O2_one_core"] = {"value": rays / secs, "unit": UNIT, "cores": 1, "sample": "%d rays, gcc -O2" % rays}
+    except Exception as e:  # noqa: BLE001
+        extras["O2_one_core"] = {"unavailable": str(e)[:160]}
+    try:
+        extras["full_program_and_marxcat"] = reference_full_program(max(per_proc // 2, 100000), cores)
+    except Exception as e:  # noqa: BLE001
+        extras["full_program_and_marxcat"] = {"unavailable": str(e)[:160]}
+    line["reference_extras"] = extras
     print(json.dumps(line), flush=True)
 
 

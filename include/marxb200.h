@@ -165,6 +165,11 @@ typedef struct
 }
 marxb200_hrma_desc;
 
+/* MirrorType=FLATFIELD (marx/libsrc/ffield.c:45-108): no optics; every ray starts at a uniformly drawn point of the rectangle
+ * [min_y, max_y] x [min_z, max_z] in the plane x = x_pos (two draws on the MIRROR sub-stream: z first, then y), its direction
+ * re-aimed for a source at finite distance; the mirror shell stays 0 */
+typedef struct { double min_y, min_z, max_y, max_z, x_pos; } marxb200_flatfield_desc;
+
 /* gratings: Grating_Type / Grating_Sector_Type (marx/libsrc/diffract.c:51-91) */
 typedef struct
 {
@@ -294,6 +299,7 @@ int marxb200_set_compaction (marxb200_ctx *ctx, int on);
 int marxb200_set_source (marxb200_ctx *ctx, const marxb200_source_desc *d);
 int marxb200_set_dither (marxb200_ctx *ctx, const marxb200_dither_desc *d);
 int marxb200_set_hrma (marxb200_ctx *ctx, const marxb200_hrma_desc *d);
+int marxb200_set_flatfield (marxb200_ctx *ctx, const marxb200_flatfield_desc *d);      /* instead of marxb200_set_hrma */
 int marxb200_set_grating (marxb200_ctx *ctx, const marxb200_grating_desc *d);
 int marxb200_set_acis (marxb200_ctx *ctx, const marxb200_acis_desc *d);
 int marxb200_set_hrc_s (marxb200_ctx *ctx, const marxb200_hrc_s_desc *d);

@@ -202,8 +202,18 @@ int __wrap_marx_create_photons (Marx_Source_Type *st, Marx_Photon_Type *pt, unsi
 	 * stage wrappers skip what the history says was already done (hrma.c:1171, diffract.c:982, acis-s.c:186). */
 	unsigned int got = 0;
 	double t0 = now ();
+	unsigned int live = 0, i;
 	if (-1 == __real_marx_create_photons (st, pt, num, &got, exposure_time)) return -1;
-	if (-1 == marxb200_upload_from (Ctx, (marxb200_photon_attr *) pt->attributes, got, NULL, pt->start_time))
+	/* a host generator may hand over rays it has already rejected (SAOSAC: the ray-weight test of s-saosac.c:206-211 sets
+	 * PHOTON_MIRROR_VBLOCKED); the stock stages skip them through marx_prune_photons (photon.c:40-63), the device list holds live
+	 * rays only: drop them here, in place and in order (the records are overwritten by the next batch anyway) */
+	for (i = 0; i < got; i++)
+	  if (0 == (pt->attributes[i].flags & BAD_PHOTON_MASK))
+	    {
+	       if (live != i) pt->attributes[live] = pt->attributes[i];
+	       live++;
+	    }
+	if (-1 == marxb200_upload_from (Ctx, (marxb200_photon_attr *) pt->attributes, live, NULL, pt->start_time))
 	  return gpu_error ("marxb200_upload_from");
 	*num_collected = got;
 	Next_Ray += got;

@@ -16,7 +16,7 @@ STAGE_SOURCE, STAGE_MIRROR, STAGE_GRATING, STAGE_DETECTOR = 0, 1, 2, 3
 # every symbol include/marxb200.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
     "marxb200_abi_version", "marxb200_last_error", "marxb200_create", "marxb200_destroy", "marxb200_set_stream",
-    "marxb200_set_compaction", "marxb200_set_source", "marxb200_set_dither", "marxb200_set_hrma",
+    "marxb200_set_compaction", "marxb200_set_source", "marxb200_set_dither", "marxb200_set_hrma", "marxb200_set_flatfield",
     "marxb200_set_grating", "marxb200_set_acis", "marxb200_set_hrc_s", "marxb200_load_calpack", "marxb200_alloc_photons",
     "marxb200_create_photons", "marxb200_truncate_exposure", "marxb200_time_sums", "marxb200_mirror_reflect", "marxb200_grating_diffract",
     "marxb200_detect", "marxb200_restore_order", "marxb200_trace", "marxb200_trace_from", "marxb200_set_profiling", "marxb200_get_kernel_ms", "marxb200_get_counts", "marxb200_get_stage_counts", "marxb200_get_internal_counts", "marxb200_download",

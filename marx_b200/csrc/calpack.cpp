@@ -9,6 +9,7 @@
 //   source.image_params       f64[4]  IMAGE: nx, ny, rad per x pixel, rad per y pixel;  source.image_cdf f32[ny*nx]
 //   dither.params             f64[12] mode, amp ra/dec/roll, period ra/dec/roll, phase ra/dec/roll, nominal_roll, aspect_blur
 //   dither.aspsol             f64[n][7] (mode 2) t, ra, dec, roll, dy, dz, dtheta of every ASPSOL reader state
+//   ffield.params             f64[5]  MirrorType=FLATFIELD instead of the hrma.* entries: min_y, min_z, max_y, max_z, x_pos
 //   hrma.params               f64[7]  vig, cap_position, is_ideal, use_blur, use_wfold, use_struts, use_scale_factors
 //   hrma.opt_energies/.opt_betas/.opt_deltas  f32[n]
 //   hrma.shell<k>.params      f64[62] (order: see set_hrma_from_pack)
@@ -157,6 +158,14 @@ extern "C" int marxb200_load_calpack_impl (marxb200_ctx *ctx, const char *path, 
    theta_offsets.reserve (16);
    std::vector<std::vector<double>> wf_cols;
    wf_cols.reserve (64);
+   if (P.has ("ffield.params"))
+     {
+        GET (e, "ffield.params", MXCP_F64, 5);
+        const double *v = (const double *) e->data;
+        marxb200_flatfield_desc d = {v[0], v[1], v[2], v[3], v[4]};
+        if (-1 == marxb200_set_flatfield (ctx, &d)) return bail (marxb200_last_error ());
+     }
+   else
    {
       GET (e, "hrma.params", MXCP_F64, 7);
       const double *v = (const double *) e->data;

@@ -41,6 +41,26 @@ typedef struct { char internal[MARXB200_COMM_ID_BYTES]; } nccl_unique_id;
 enum { NCCL_CHAR = 0, NCCL_INT32 = 2, NCCL_UINT64 = 5, NCCL_FLOAT64 = 8 };     // ncclDataType_t
 enum { NCCL_SUM = 0, NCCL_MIN = 3 };                                            // ncclRedOp_t
 
+// ncclConfig_t as of NCCL 2.18 (the first release with ncclCommSplit): newer libraries accept an older, shorter struct (they read
+// `size` bytes and default the rest).  Used to cap the collectives of this path -- a few kilobytes each -- at ONE CTA: an NCCL
+// kernel spins while it waits for its peers, and every CTA it holds is a slot the persistent trace kernels cannot use.
+struct nccl_config_v21800
+{
+   size_t size; unsigned int magic; unsigned int version;
+   int blocking, cgaClusterSize, minCTAs, maxCTAs;
+   const char *netName;
+   int splitShare;
+};
+const int kNcclUndefInt = (int) 0x80000000;      // NCCL_CONFIG_UNDEF_INT (INT_MIN)
+nccl_config_v21800 one_cta_config ()
+{
+   nccl_config_v21800 c;
+   c.size = sizeof (c); c.magic = 0xcafebeef; c.version = 21800;
+   c.blocking = kNcclUndefInt; c.cgaClusterSize = kNcclUndefInt; c.minCTAs = 1; c.maxCTAs = 1;
+   c.netName = nullptr; c.splitShare = kNcclUndefInt;
+   return c;
+}
+
 struct NcclApi
 {
    void *handle = nullptr;
@@ -48,6 +68,7 @@ struct NcclApi
    int (*GetVersion) (int *) = nullptr;
    int (*GetUniqueId) (nccl_unique_id *) = nullptr;
    int (*CommInitRank) (nccl_comm_t *, int, nccl_unique_id, int) = nullptr;
+   int (*CommInitRankConfig) (nccl_comm_t *, int, nccl_unique_id, int, void *) = nullptr;
    int (*CommSplit) (nccl_comm_t, int, int, nccl_comm_t *, void *) = nullptr;
    int (*CommDestroy) (nccl_comm_t) = nullptr;
    const char *(*GetErrorString) (int) = nullptr;
@@ -78,7 +99,7 @@ NcclApi *nccl_api ()
         if (api.handle == nullptr) return;
         bool ok = true;
 #define SYM(field, name) do { *(void **) (&api.field) = dlsym (api.handle, name); if (api.field == nullptr) { ok = false; api.error = std::string ("missing symbol ") + name; } } while (0)
-        SYM (GetVersion, "ncclGetVersion"); SYM (GetUniqueId, "ncclGetUniqueId"); SYM (CommInitRank, "ncclCommInitRank");
+        SYM (GetVersion, "ncclGetVersion"); SYM (GetUniqueId, "ncclGetUniqueId"); SYM (CommInitRank, "ncclCommInitRank"); SYM (CommInitRankConfig, "ncclCommInitRankConfig");
         SYM (CommSplit, "ncclCommSplit"); SYM (CommDestroy, "ncclCommDestroy"); SYM (GetErrorString, "ncclGetErrorString");
         SYM (AllGather, "ncclAllGather"); SYM (AllReduce, "ncclAllReduce"); SYM (Broadcast, "ncclBroadcast");
         SYM (Send, "ncclSend"); SYM (Recv, "ncclRecv"); SYM (GroupStart, "ncclGroupStart"); SYM (GroupEnd, "ncclGroupEnd");
@@ -186,11 +207,19 @@ extern "C" int marxb200_comm_init (marxb200_ctx *c, const void *id, int rank, in
    do
      {
 #define INIT_OK(expr, what) { if (0 != (expr)) { status = fail ("marxb200_comm_init: %s failed: %s", what, cudaGetErrorString (cudaGetLastError ())); break; } }
-        int r = N->CommInitRank (&m->comm, world, u, rank);
+        // MARXB200_NCCL_CTAS=0 leaves NCCL's own choice of CTAs per collective (A/B runs); the default caps it at one
+        const char *ctas = getenv ("MARXB200_NCCL_CTAS");
+        const bool cap = (ctas == nullptr) || (atoi (ctas) != 0);
+        nccl_config_v21800 cfg = one_cta_config ();
+        int r = cap ? N->CommInitRankConfig (&m->comm, world, u, rank, &cfg) : N->CommInitRank (&m->comm, world, u, rank);
         if (r != 0) { status = fail ("marxb200_comm_init: ncclCommInitRank: %s", N->GetErrorString (r)); break; }
         // a second communicator for the merge stream: collectives of one communicator must be issued in one order on all ranks,
-        // and the merge of batch k is interleaved with the trace of batch k+1
-        r = N->CommSplit (m->comm, 0, rank, &m->comm_merge, nullptr);
+        // and the merge of batch k is interleaved with the trace of batch k+1.  With the peer-write transport it only carries the
+        // counts and the closing barrier (one CTA); the ncclSend / ncclRecv transport moves the columns with it and keeps NCCL's CTAs.
+        const char *force = getenv ("MARXB200_MERGE_TRANSPORT");
+        const bool merge_moves_data = (force != nullptr) && (0 == strcmp (force, "nccl"));
+        nccl_config_v21800 cfg2 = one_cta_config ();
+        r = N->CommSplit (m->comm, 0, rank, &m->comm_merge, (cap && !merge_moves_data) ? (void *) &cfg2 : nullptr);
         if (r != 0) { status = fail ("marxb200_comm_init: ncclCommSplit: %s", N->GetErrorString (r)); break; }
         INIT_OK (cudaStreamCreateWithFlags (&m->merge_stream, cudaStreamNonBlocking), "stream");
         INIT_OK (cudaEventCreateWithFlags (&m->ev_packed, cudaEventDisableTiming), "event");
@@ -289,6 +318,7 @@ extern "C" int marxb200_trace_sharded (marxb200_ctx *c, uint64_t first_ray, uint
    // the ASPSOL model ends a run at the end of the aspect file (a cut inside one rank's block) and the ExposureTime cut
    // likewise: those runs go block by block through marxb200_create_photons / marxb200_truncate_exposure
    if ((c->D.mode == 2) || c->det_dither_dirty) return fail ("marxb200_trace_sharded: the ASPSOL dither model is not sharded");
+   if (c->mirror_is_flat) return fail ("marxb200_trace_sharded: MirrorType=FLATFIELD is not sharded");
    uint64_t first = 0, n = 0;
    marxb200_shard_of (first_ray, n_total, m->rank, m->world, &first, &n);
    if (n > c->capacity) return fail ("marxb200_trace_sharded: this rank's block of %llu rays exceeds the allocated capacity %llu",

@@ -288,7 +288,7 @@ __global__ void __launch_bounds__ (kTile) k0_source (const __grid_constant__ Sou
    o.dra[i] = dra; o.ddec[i] = ddec; o.droll[i] = droll;
    o.ddy[i] = det[0]; o.ddz[i] = det[1]; o.ddth[i] = det[2];
    const RayConst &rc = a.rc;           // slot == i
-   rc.energy[i] = energy; rc.time[i] = t; rc.ray[i] = a.first_ray + i;
+   rc_store (rc, i, energy, a.first_ray + i); rc.time[i] = t;
    rc.dra[i] = dra; rc.ddec[i] = ddec; rc.droll[i] = droll;
    rc.ddy[i] = det[0]; rc.ddz[i] = det[1]; rc.ddth[i] = det[2];
 }
@@ -438,13 +438,14 @@ __global__ void __launch_bounds__ (kStageThreads, MX_K1_MINBLOCKS) k1_hrma (cons
         float beta = 0.f, delta = 1.f, corr = 1.f;
         Rng rng;
         const uint32_t slot = in.slot[i];
-        rng.init (a.seed, a.rc.ray[slot], MARXB200_STAGE_MIRROR);
+        double energy; uint64_t ray;
+        rc_load (a.rc, slot, energy, ray);
+        rng.init (a.seed, ray, MARXB200_STAGE_MIRROR);
         if (PHASE == 0)
           flags = hrma_phase_a (H, a.source_distance, x, p, shell, rng);
         else
           {
              x = v_make (in.x0[i], in.x1[i], in.x2[i]);
-             const double energy = a.rc.energy[slot];
              shell = in.shell[i];
              const int st = in.pha[i];
              rng.resume ((uint32_t) (st & 0x3FFF), (st & 0x4000) ? 1 : 0, (st & 0x4000) ? in.aux[i] : 0.0);
@@ -523,6 +524,54 @@ __global__ void __launch_bounds__ (kStageThreads, MX_K1_MINBLOCKS) k1_hrma (cons
    run_stage<ND, NU> (a, q, trace, flush_entry, in_place);
 }
 
+// K1 (MirrorType=FLATFIELD) ---------------------------------------------------------------------
+// _marx_ff_mirror_reflect, marx/libsrc/ffield.c:61-108: no optics.  Draw order on the MIRROR sub-stream: z, then y.
+__global__ void __launch_bounds__ (kStageThreads) k1_flatfield (const __grid_constant__ StageArgs a)
+{
+   constexpr int ND = 6, NU = 1;
+   extern __shared__ __align__ (128) unsigned char smem[];
+   WarpQueue<ND, NU> &q = my_queue<ND, NU> (smem, 0);
+   const PhotonSoA &in = a.in, &out = a.out;
+   auto trace = [&] (unsigned long long i, double *d, uint32_t *u) -> uint32_t
+     {
+        Vec3 p = v_make (in.p0[i], in.p1[i], in.p2[i]), x;
+        const uint32_t slot = in.slot[i];
+        Rng rng;
+        double energy; uint64_t ray;
+        rc_load (a.rc, slot, energy, ray);
+        rng.init (a.seed, ray, MARXB200_STAGE_MIRROR);
+        x.z = a.ff[1] + rng.uniform () * (a.ff[3] - a.ff[1]);
+        x.y = a.ff[0] + rng.uniform () * (a.ff[2] - a.ff[0]);
+        x.x = a.ff[4];
+        if (a.source_distance > 0.0)
+          {
+             p = v_ax1_bx2 (1.0, x, a.source_distance, p);
+             v_normalize (p);
+          }
+        d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = p.x; d[4] = p.y; d[5] = p.z;
+        u[0] = slot;
+        return 0u;
+     };
+   auto write_row = [&] (unsigned long long j, const double *d)
+     {
+        out.x0[j] = d[0]; out.x1[j] = d[1]; out.x2[j] = d[2];
+        out.p0[j] = d[3]; out.p1[j] = d[4]; out.p2[j] = d[5];
+        out.flags[j] = 0; out.shell[j] = 0;
+        out.pha[j] = 0; out.chipx[j] = 0.f; out.chipy[j] = 0.f; out.pi[j] = 0.f;
+     };
+   auto flush_entry = [&] (uint32_t pos, unsigned long long j)
+     {
+        double d[ND];
+#pragma unroll
+        for (int k = 0; k < ND; k++) d[k] = q.d[k][pos];
+        write_row (j, d);
+        out.slot[j] = q.u[0][pos];
+        out.order[j] = 0; out.sorders[j] = 0;
+     };
+   auto in_place = [&] (unsigned long long i, const double *d, const uint32_t *, uint32_t) { write_row (i, d); };
+   run_stage<ND, NU> (a, q, trace, flush_entry, in_place);
+}
+
 // K2 ------------------------------------------------------------------------------------------
 // The compacting path runs the grating stage as two kernels (mx_grating.cuh: grating_select, grating_diffract_selected).
 // k2_select needs neither x nor p: it reads a row's slot key and shell, draws the vignetting and order-selection deviates and
@@ -547,8 +596,10 @@ __global__ void __launch_bounds__ (256) k2_select (const __grid_constant__ Stage
           {
              const uint32_t slot = a.in.slot[i], shell = a.in.shell[i];
              Rng rng;
-             rng.init (a.seed, a.rc.ray[slot], MARXB200_STAGE_GRATING);
-             lo = grating_select (B->G.shell[shell], a.rc.energy[slot], rng);
+             double energy; uint64_t ray;
+             rc_load (a.rc, slot, energy, ray);
+             rng.init (a.seed, ray, MARXB200_STAGE_GRATING);
+             lo = grating_select (B->G.shell[shell], energy, rng);
           }
         const uint32_t ballot = __ballot_sync (0xffffffffu, lo >= 0);
         unsigned long long base = 0;
@@ -590,14 +641,16 @@ __global__ void __launch_bounds__ (kStageThreads, MX_K2_MINBLOCKS) k2_grating (c
         uint32_t sorders = 0;
         Rng rng;
         const uint32_t slot = in.slot[src], shell = in.shell[src];
-        rng.init (a.seed, a.rc.ray[slot], MARXB200_STAGE_GRATING);
+        double energy; uint64_t ray;
+        rc_load (a.rc, slot, energy, ray);
+        rng.init (a.seed, ray, MARXB200_STAGE_GRATING);
         uint32_t flags;
         if (PHASE == 1)
           {
              rng.resume (2, 0, 0.0);            // behind the vignetting and order-selection draws
-             flags = grating_diffract_selected (G, shell, a.rc.energy[slot], x, p, lo, order, sorders, rng);
+             flags = grating_diffract_selected (G, shell, energy, x, p, lo, order, sorders, rng);
           }
-        else flags = grating_diffract (G, shell, a.rc.energy[slot], x, p, order, sorders, rng);
+        else flags = grating_diffract (G, shell, energy, x, p, order, sorders, rng);
         d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = p.x; d[4] = p.y; d[5] = p.z;
         u[0] = slot;
         u[1] = (uint32_t) (order & 0xFF) | (shell << 8);
@@ -654,16 +707,18 @@ __global__ void __launch_bounds__ (kStageThreads, MX_K3_MINBLOCKS) k3_acis (cons
         int ccd = -1; float chipx = 0, chipy = 0, pi = 0; int16_t pha = 0;
         Rng rng;
         const uint32_t slot = in.slot[i];
-        rng.init (a.seed, a.rc.ray[slot], MARXB200_STAGE_DETECTOR);
+        double energy; uint64_t ray;
+        rc_load (a.rc, slot, energy, ray);
+        rng.init (a.seed, ray, MARXB200_STAGE_DETECTOR);
         DetDither dd = {0.0, 0.0, 0.0};
         if (DET) { dd.dy = a.rc.ddy[slot]; dd.dz = a.rc.ddz[slot]; dd.dtheta = a.rc.ddth[slot]; }
         uint32_t flags;
         if (PHASE == 0)
-          flags = acis_detect<DET> (A, a.rc.energy[slot], a.rc.time[slot], x, p, ccd, chipx, chipy, pha, pi, rng, fef_cum, kStageThreads, dd);
+          flags = acis_detect<DET> (A, energy, a.rc.time[slot], x, p, ccd, chipx, chipy, pha, pi, rng, fef_cum, kStageThreads, dd);
         else if (PHASE == 1)
           {
              int hit = -1;
-             flags = acis_detect_a<DET> (A, a.rc.energy[slot], x, p, ccd, hit, chipx, chipy, rng, dd);
+             flags = acis_detect_a<DET> (A, energy, x, p, ccd, hit, chipx, chipy, rng, dd);
              pha = ((flags & 0xFFu) == 0) ? (int16_t) hit : (int16_t) 0;
           }
         else
@@ -671,7 +726,7 @@ __global__ void __launch_bounds__ (kStageThreads, MX_K3_MINBLOCKS) k3_acis (cons
              const int hit = (int) in.pha[i];
              ccd = (int) in.ccd[i]; chipx = in.chipx[i]; chipy = in.chipy[i];
              rng.resume (A.det_ideal ? 0u : 1u, 0, 0.0);
-             flags = acis_detect_b<DET> (A, a.rc.energy[slot], a.rc.time[slot], x, p, hit, chipx, chipy, pha, pi, rng, fef_cum, kStageThreads, dd);
+             flags = acis_detect_b<DET> (A, energy, a.rc.time[slot], x, p, hit, chipx, chipy, pha, pi, rng, fef_cum, kStageThreads, dd);
           }
         d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = p.x; d[4] = p.y; d[5] = p.z;
         // ids produced by the earlier stages travel through the queue (coalesced loads here instead of dependent
@@ -728,10 +783,12 @@ __global__ void __launch_bounds__ (kStageThreads) k3_hrc (const __grid_constant_
         int ccd = -1, region = 0; float ypix = 0, zpix = 0, upix = 0, vpix = 0; int16_t pha = 0;
         Rng rng;
         const uint32_t slot = in.slot[i];
-        rng.init (a.seed, a.rc.ray[slot], MARXB200_STAGE_DETECTOR);
+        double energy; uint64_t ray;
+        rc_load (a.rc, slot, energy, ray);
+        rng.init (a.seed, ray, MARXB200_STAGE_DETECTOR);
         DetDither dd = {0.0, 0.0, 0.0};
         if (DET) { dd.dy = a.rc.ddy[slot]; dd.dz = a.rc.ddz[slot]; dd.dtheta = a.rc.ddth[slot]; }
-        uint32_t flags = hrc_s_detect<DET> (D, a.rc.energy[slot], x, p, ccd, region, ypix, zpix, upix, vpix, pha, rng, dd);
+        uint32_t flags = hrc_s_detect<DET> (D, energy, x, p, ccd, region, ypix, zpix, upix, vpix, pha, rng, dd);
         d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = p.x; d[4] = p.y; d[5] = p.z;
         u[0] = slot;
         u[1] = flags | ((uint32_t) in.shell[i] << 16) | (((uint32_t) (uint8_t) in.order[i]) << 24);
@@ -834,7 +891,7 @@ __global__ void __launch_bounds__ (kTile, MX_K01_MINBLOCKS) k01_source_hrma (con
              // included: full, coalesced 256-byte rows per column (36 B per generated ray), whereas storing only the
              // survivors' made every sector a partial write that the L2 had to fill from DRAM first (ncu: 539 MB of
              // reads in a kernel that reads nothing)
-             a.rc.energy[i] = energy; a.rc.time[i] = t; a.rc.ray[i] = a.first_ray + i;
+             rc_store (a.rc, i, energy, a.first_ray + i); a.rc.time[i] = t;
              a.rc.dra[i] = dra; a.rc.ddec[i] = ddec; a.rc.droll[i] = droll;
           }
         const uint32_t ballot = __ballot_sync (0xffffffffu, alive);
@@ -928,11 +985,13 @@ __global__ void __launch_bounds__ (256) order_gather (OrderArgs a)
      {
         const uint32_t s = a.perm[j], key = in.slot[s];
         const RayConst &rc = a.rc;
-        out.energy[j] = rc.energy[key];
+        double rc_energy; uint64_t rc_ray;
+        rc_load (rc, key, rc_energy, rc_ray);
+        out.energy[j] = rc_energy;
         out.x0[j] = in.x0[s]; out.x1[j] = in.x1[s]; out.x2[j] = in.x2[s];
         out.p0[j] = in.p0[s]; out.p1[j] = in.p1[s]; out.p2[j] = in.p2[s];
         out.time[j] = rc.time[key]; out.aux[j] = in.aux[s];
-        out.ray[j] = rc.ray[key]; out.slot[j] = key; out.flags[j] = in.flags[s];
+        out.ray[j] = rc_ray; out.slot[j] = key; out.flags[j] = in.flags[s];
         out.dra[j] = rc.dra[key]; out.ddec[j] = rc.ddec[key]; out.droll[j] = rc.droll[key];
         if (out.ddy != nullptr) { out.ddy[j] = rc.ddy[key]; out.ddz[j] = rc.ddz[key]; out.ddth[j] = rc.ddth[key]; }   // null: detector dither not live
         out.chipx[j] = in.chipx[s]; out.chipy[j] = in.chipy[s]; out.pi[j] = in.pi[s];
@@ -1008,7 +1067,7 @@ __global__ void __launch_bounds__ (256) aos_to_soa (const marxb200_photon_attr *
         out.slot[i] = (uint32_t) i;
         out.flags[i] = r.flags;
         out.dra[i] = r.dither_ra; out.ddec[i] = r.dither_dec; out.droll[i] = r.dither_roll;
-        rc.energy[i] = r.energy; rc.time[i] = r.arrival_time + start_time; rc.ray[i] = ray_ids ? ray_ids[i] : (uint64_t) r.tag;
+        rc_store (rc, i, r.energy, ray_ids ? ray_ids[i] : (uint64_t) r.tag); rc.time[i] = r.arrival_time + start_time;
         rc.dra[i] = r.dither_ra; rc.ddec[i] = r.dither_dec; rc.droll[i] = r.dither_roll;
         out.ddy[i] = r.dither_dy; out.ddz[i] = r.dither_dz; out.ddth[i] = r.dither_dtheta;
         rc.ddy[i] = r.dither_dy; rc.ddz[i] = r.dither_dz; rc.ddth[i] = r.dither_dtheta;
@@ -1332,6 +1391,18 @@ void launch_hrma (const StageArgs &a, int phase, int grid, cudaStream_t s)
       case 4: k1_hrma<4><<<grid, kStageThreads, smem, s>>> (a); break;
       default: k1_hrma<5><<<grid, kStageThreads, smem, s>>> (a); break;
      }
+}
+void launch_flatfield (const StageArgs &a, int num_sms, cudaStream_t s)
+{
+   const uint32_t smem = (kStageThreads / 32) * (uint32_t) sizeof (WarpQueue<6, 1>);
+   static int per_sm = 0;
+   if (per_sm == 0)
+     {
+        cudaFuncSetAttribute (k1_flatfield, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, k1_flatfield, kStageThreads, smem);
+        if (per_sm < 1) per_sm = 1;
+     }
+   k1_flatfield<<<per_sm * num_sms, kStageThreads, smem, s>>> (a);
 }
 void launch_grating (const StageArgs &a, int grid, cudaStream_t s, int phase)
 {

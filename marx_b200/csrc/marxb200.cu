@@ -349,6 +349,19 @@ extern "C" int marxb200_set_hrma (marxb200_ctx *c, const marxb200_hrma_desc *d)
               c->grid1[3], c->grid1[4], c->grid1[5], kStageThreads);
    c->grid01 = fused_source_grid (c->num_sms);
    c->have_hrma = true;
+   c->mirror_is_flat = false;
+   return 0;
+}
+
+extern "C" int marxb200_set_flatfield (marxb200_ctx *c, const marxb200_flatfield_desc *d)
+{
+   if ((c == nullptr) || (d == nullptr)) return fail ("marxb200_set_flatfield: NULL argument");
+   if ((d->max_y <= d->min_y) || (d->max_z <= d->min_z) || (d->x_pos < 0.0)) return fail ("marxb200_set_flatfield: FF_* parameters not physical");   // ffield.c:115-121
+   CUDA_OK (cudaSetDevice (c->device));
+   begin_module (c, marxb200_ctx::TAG_HRMA);
+   c->ff[0] = d->min_y; c->ff[1] = d->min_z; c->ff[2] = d->max_y; c->ff[3] = d->max_z; c->ff[4] = d->x_pos;
+   c->mirror_is_flat = true;
+   c->have_hrma = true;
    return 0;
 }
 
@@ -463,7 +476,7 @@ extern "C" int marxb200_alloc_photons (marxb200_ctx *c, uint64_t max_photons)
       CUDA_OK (cudaMalloc (&c->rc_slab, 3 * c8 + 6 * c4));
       CUDA_OK (cudaMemsetAsync (c->rc_slab, 0, 3 * c8 + 6 * c4, c->stream));
       unsigned char *b = (unsigned char *) c->rc_slab;
-      c->rc.energy = (double *) b; c->rc.time = (double *) (b + c8); c->rc.ray = (uint64_t *) (b + 2 * c8);
+      c->rc.er = (double2 *) b; c->rc.time = (double *) (b + 2 * c8);          // {energy, ray id} records: 16 B per slot
       c->rc.dra = (float *) (b + 3 * c8); c->rc.ddec = (float *) (b + 3 * c8 + c4); c->rc.droll = (float *) (b + 3 * c8 + 2 * c4);
       c->rc.ddy = (float *) (b + 3 * c8 + 3 * c4); c->rc.ddz = (float *) (b + 3 * c8 + 4 * c4); c->rc.ddth = (float *) (b + 3 * c8 + 5 * c4);
    }
@@ -622,6 +635,22 @@ static int run_stage (marxb200_ctx *c, int stage)
      }
    const unsigned long long *n_in = (k_first == 1) ? c->d_counts + 4 : c->d_counts + c->stage_done;
    c->first_mirror_kernel = 0;
+   if ((stage == 1) && c->mirror_is_flat)
+     {
+        // MirrorType=FLATFIELD: the whole stage is one kernel (ffield.c:77-108)
+        a.in = c->buf[c->cur];
+        a.out = c->compact ? c->buf[1 - c->cur] : c->buf[c->cur];
+        a.n_in = c->d_counts + c->stage_done; a.n_out = c->d_counts + 1; a.ticket = c->d_ticket; a.chunk_tiles = 4;
+        for (int k = 0; k < 5; k++) a.ff[k] = c->ff[k];
+        prof_begin (c);
+        launch_flatfield (a, c->num_sms, c->stream);
+        prof_mark (c, 4);
+        c->launches += 1;
+        CUDA_OK (cudaGetLastError ());
+        if (c->compact) { c->cur = 1 - c->cur; c->ordered = false; }
+        c->stage_done = 1;
+        return 0;
+     }
    for (int k = k_first; k < n_kernels; k++)
      {
         a.in = c->buf[c->cur];
@@ -798,7 +827,7 @@ extern "C" int marxb200_trace_from (marxb200_ctx *c, uint64_t first_ray, uint64_
    if (c == nullptr) return fail ("NULL ctx");
    // the fused source + HRMA-A kernel serves the compacting path of the NONE / INTERNAL dither models; the ASPSOL model
    // (end-of-file cut, detector dither columns) and lists that follow an upload carrying detector dither go stage by stage
-   if (c->compact && (c->D.mode != 2) && !c->det_dither_dirty)
+   if (c->compact && (c->D.mode != 2) && !c->det_dither_dirty && !c->mirror_is_flat)
      {
         if (-1 == create_and_enter_mirror (c, first_ray, n, time_base_in)) return -1;
      }

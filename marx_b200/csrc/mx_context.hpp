@@ -60,6 +60,7 @@ struct marxb200_ctx
    double aspsol_t_last = 0.0;                   // ASPSOL dither: time of the last state (rays at or beyond it end the run)
    int grid1[6] = {0, 0, 0, 0, 0, 0}, grid2 = 0, grid3 = 0, grid01 = 0;
    bool detector_is_hrc = false;
+   bool mirror_is_flat = false; double ff[5] = {0, 0, 0, 0, 0};      // MirrorType=FLATFIELD (marxb200_set_flatfield)
    int first_mirror_kernel = 0;                  // 1: phase A already ran fused with the source (marxb200_trace)
    int k3_split = 1;                             // ACIS detector stage as two kernels (MARXB200_K3_SPLIT=0: one kernel)
    int k2_split = 1;                             // compacting grating stage as k2_select + k2_grating<1> (MARXB200_K2_SPLIT=0: one kernel)

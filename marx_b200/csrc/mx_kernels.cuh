@@ -42,13 +42,27 @@ struct PhotonSoA
 // produce (x, p, flags, ids) plus the 4-byte slot.  (The first version carried these 36 bytes from list to list in every
 // stage: 7 dependent gathers + 7 stores per survivor per stage, 13 % of k1_hrma<1>'s stall samples.)  The arrival-order
 // restoration materialises them into the list's own columns, which is what the host boundary reads.
+// energy and ray id share ONE 16-byte record per slot: every stage kernel needs both (the ray id keys its draws), and a gather
+// through the slot key costs a 32-byte DRAM sector per touched array once the list is sparse -- one sector instead of two
+// (k2_select: 102 -> ~70 B of DRAM traffic per input ray).
 struct RayConst
 {
-   double *energy, *time;
-   uint64_t *ray;
+   double2 *er;                          // x = energy, y = the bit pattern of the 64-bit global ray index
+   double *time;
    float *dra, *ddec, *droll;
    float *ddy, *ddz, *ddth;
 };
+#if defined(__CUDACC__)
+__device__ __forceinline__ void rc_load (const RayConst &rc, uint32_t slot, double &energy, uint64_t &ray)
+{
+   const double2 v = rc.er[slot];
+   energy = v.x; ray = (uint64_t) __double_as_longlong (v.y);
+}
+__device__ __forceinline__ void rc_store (const RayConst &rc, uint64_t slot, double energy, uint64_t ray)
+{
+   rc.er[slot] = make_double2 (energy, __longlong_as_double ((long long) ray));
+}
+#endif
 
 // Blob staged into shared memory by K1 with one TMA bulk copy.
 struct alignas (16) K1Blob
@@ -94,6 +108,7 @@ struct StageArgs
    uint32_t blob_bytes;                  // bytes staged into shared memory from the start of the blob
    uint32_t seg2_off, seg2_bytes;        // optional second staged segment (byte range of the blob), placed behind the first
    int det_dither;                       // detector stage: read the per-ray detector dither (ASPSOL model or uploaded photons)
+   double ff[5];                         // MirrorType=FLATFIELD: min_y, min_z, max_y, max_z, x_pos (k1_flatfield)
 };
 
 struct SourceArgs
@@ -121,6 +136,7 @@ void launch_time_bases_sharded (const SourceArgs &a, const double *all_sums, int
 void launch_source (const SourceArgs &a, cudaStream_t s);
 void launch_exposure_truncate (const PhotonSoA &buf, unsigned long long *n, double *dev_times, double limit, int inclusive, cudaStream_t s);
 void launch_hrma (const StageArgs &a, int phase, int grid, cudaStream_t s);
+void launch_flatfield (const StageArgs &a, int num_sms, cudaStream_t s);       // MirrorType=FLATFIELD: the whole mirror stage
 int fused_source_grid (int num_sms);
 void launch_source_hrma (const SourceArgs &a, const StageArgs &st, int grid, cudaStream_t s);   // k0_source + k1_hrma<0> in one kernel   // phase 0,1,2 = k1a,k1b,k1c
 void launch_grating (const StageArgs &a, int grid, cudaStream_t s, int phase = 0);   // phase 0: one kernel; 1: k2_select, 2: k2_grating<1>

@@ -21,6 +21,12 @@
 #define MX_MATH 2
 #endif
 
+#if defined(__CUDACC__)
+#define MXM_HD __host__ __device__ __forceinline__
+#else
+#define MXM_HD inline          // host builds of the MX_HD functions (tools/hostcheck) take libm
+#endif
+
 namespace mx {
 
 #if defined(__CUDACC__)
@@ -67,7 +73,7 @@ static __device__ __noinline__ double log_far (double x) { return log (x); }
 #endif
 
 // sin and cos of one angle
-__host__ __device__ __forceinline__ void mx_sincos (double x, double &s, double &c)
+MXM_HD void mx_sincos (double x, double &s, double &c)
 {
 #if defined(__CUDA_ARCH__) && (MX_MATH >= 1)
    if (fabs (x) <= 1.0e5)
@@ -89,7 +95,7 @@ __host__ __device__ __forceinline__ void mx_sincos (double x, double &s, double 
 }
 // the same for two small angles at once (the dithered pointing offsets): below 2^-10 rad the series needs three terms
 // (the next ones are below 2^-60 relative)
-__host__ __device__ __forceinline__ void mx_sincos_pair (double x, double y, double &sx, double &cx, double &sy, double &cy)
+MXM_HD void mx_sincos_pair (double x, double y, double &sx, double &cx, double &sy, double &cy)
 {
 #if defined(__CUDA_ARCH__) && (MX_MATH >= 1)
    if ((fabs (x) < 0x1p-10) && (fabs (y) < 0x1p-10))
@@ -105,7 +111,7 @@ __host__ __device__ __forceinline__ void mx_sincos_pair (double x, double y, dou
    mx_sincos (x, sx, cx);
    mx_sincos (y, sy, cy);
 }
-__host__ __device__ __forceinline__ double mx_sin (double x)
+MXM_HD double mx_sin (double x)
 {
 #if defined(__CUDA_ARCH__) && (MX_MATH >= 1)
    if (fabs (x) <= 1.0e5)
@@ -124,7 +130,7 @@ __host__ __device__ __forceinline__ double mx_sin (double x)
 // natural logarithm of a positive normal number (the draws: (0, 1]); anything else takes the libdevice function.
 // fdlibm's scheme: x = 2^k (1 + f), sqrt(2)/2 <= 1 + f < sqrt(2); s = f / (2 + f); log (1 + f) = f - f^2/2 + s (f^2/2 + R (s^2)).
 // The quotient comes from the hardware reciprocal seed and two Newton steps (<= 1 ulp; its error enters the result scaled by s^2).
-__host__ __device__ __forceinline__ double mx_log (double x)
+MXM_HD double mx_log (double x)
 {
 #if defined(__CUDA_ARCH__) && (MX_MATH >= 2)
    int hx = __double2hiint (x);

@@ -77,6 +77,27 @@ MX_HD void pu_frames (const PileupArgs &a, uint64_t e)
    a.pn[e] = 0; a.flag[e] = 0; a.emit[e] = 0;
 }
 
+// store_event :754-812 for the pixel whose representative is e (the LAST event of the frame on that pixel), replayed in list order
+// (= reverse file order: e first, then the earlier events of the frame on the same pixel); cent = 1: the neighbours receive + 0.0 * e
+MX_HD void pu_pixel_state (const PileupArgs &a, uint64_t e, uint64_t lo)
+{
+   const uint32_t key = a.key[e];
+   float cb = 0.0f, cx = 0.0f, cy = 0.0f; uint32_t np = 0;
+   for (uint64_t j = e + 1; j-- > lo; )
+     {
+        if (a.key[j] != key) continue;
+        const float ex = a.x[j], ey = a.y[j];
+        const double cent_e = 1.0 * (double) a.benergy[j];
+        np += 1;
+        cx = (float) ((double) (cx * cb) + cent_e * (double) ex);
+        cy = (float) ((double) (cy * cb) + cent_e * (double) ey);
+        cb = (float) ((double) cb + cent_e);
+        cx = cx / cb;
+        cy = cy / cb;
+     }
+   a.pb[e] = cb; a.px[e] = cx; a.py[e] = cy; a.pn[e] = np;
+}
+
 MX_HD void pu_store (const PileupArgs &a, uint64_t e)
 {
    const uint32_t f = a.frame[e];
@@ -88,22 +109,9 @@ MX_HD void pu_store (const PileupArgs &a, uint64_t e)
    a.lo[e] = (uint32_t) lo; a.hi[e] = (uint32_t) hi;
    const uint32_t key = a.key[e];
    if (key == kPuNoKey) return;
-   // store_event :754-812 in list order (= reverse file order); cent = 1: the neighbours receive + 0.0 * e
-   float cb = 0.0f, cx = 0.0f, cy = 0.0f; uint32_t np = 0;
-   for (uint64_t j = hi; j-- > lo; )
-     {
-        if (a.key[j] != key) continue;
-        if ((np == 0) && (j != e)) return;                    // a later event owns this pixel: e left the list (:903-908)
-        const float ex = a.x[j], ey = a.y[j];
-        const double cent_e = 1.0 * (double) a.benergy[j];
-        np += 1;
-        cx = (float) ((double) (cx * cb) + cent_e * (double) ex);
-        cy = (float) ((double) (cy * cb) + cent_e * (double) ey);
-        cb = (float) ((double) cb + cent_e);
-        cx = cx / cb;
-        cy = cy / cb;
-     }
-   a.pb[e] = cb; a.px[e] = cx; a.py[e] = cy; a.pn[e] = np;
+   // a later event of the frame on the same pixel owns it: e left the list (:903-908)
+   for (uint64_t j = e + 1; j < hi; j++) if (a.key[j] == key) return;
+   pu_pixel_state (a, e, lo);
 }
 
 // the occupied pixels of e's 3 x 3 neighbourhood: slot [r][c] = representative event of pixel (y - 1 + r, x - 1 + c), or -1
@@ -129,11 +137,9 @@ MX_HD void pu_hood (const PileupArgs &a, uint64_t e, PuHood &h)
      }
 }
 
-// collect_charge :814-845
-MX_HD void pu_island (const PileupArgs &a, uint64_t e)
+// collect_charge :814-845, for the neighbourhood h of representative e
+MX_HD void pu_island_from (const PileupArgs &a, uint64_t e, const PuHood &h)
 {
-   if (a.pn[e] == 0) return;
-   PuHood h; pu_hood (a, e, h);
    double s = 0.0; uint32_t np = 0;
    bool first = true;
 #if defined(__CUDA_ARCH__)
@@ -154,12 +160,16 @@ MX_HD void pu_island (const PileupArgs &a, uint64_t e)
        }
    a.ib[e] = (float) s; a.in[e] = np;
 }
-
-// event_detect :676-752, the two local-maximum tests
-MX_HD void pu_detect (const PileupArgs &a, uint64_t e)
+MX_HD void pu_island (const PileupArgs &a, uint64_t e)
 {
    if (a.pn[e] == 0) return;
    PuHood h; pu_hood (a, e, h);
+   pu_island_from (a, e, h);
+}
+
+// event_detect :676-752, the two local-maximum tests
+MX_HD void pu_detect_from (const PileupArgs &a, uint64_t e, const PuHood &h)
+{
    float pb[3][3], ib[3][3];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -185,6 +195,12 @@ MX_HD void pu_detect (const PileupArgs &a, uint64_t e)
      return;
    a.flag[e] = (a.in[e] >= 2) ? 2 : 1;
 }
+MX_HD void pu_detect (const PileupArgs &a, uint64_t e)
+{
+   if (a.pn[e] == 0) return;
+   PuHood h; pu_hood (a, e, h);
+   pu_detect_from (a, e, h);
+}
 
 // marx_map_energy_to_acis_pha, acis_fef.c:1087-1096 (find_fef :910-966 + JDMinterpolate_f); x, y arrive as ints
 MX_HD int pu_energy_to_pha (const AcisDev &A, int ccd_id, int xi, int yi, double energy, int16_t &pha)
@@ -208,23 +224,19 @@ MX_HD int pu_energy_to_pha (const AcisDev &A, int ccd_id, int xi, int yi, double
    return 0;
 }
 
-// the rest of event_detect (grade migration draw, centroid) and write_event's PHA
-MX_HD void pu_emit (const PileupArgs &a, uint64_t e)
+// the rest of event_detect (grade migration draw, centroid) and write_event's PHA.  k: number of islands of the frame that drew before
+// this one (list order = reverse file order); h: the neighbourhood (read for flag == 2 only)
+MX_HD void pu_emit_from (const PileupArgs &a, uint64_t e, uint32_t k, const PuHood &h)
 {
    const uint32_t flag = a.flag[e];
-   if (flag == 0) return;
    double x = a.x[e], y = a.y[e];
    const uint32_t np = a.in[e];
    if (flag == 2)
      {
-        uint32_t k = 0;                                        // islands that drew before this one (list order = reverse file order)
-        const uint64_t hi = a.hi[e];
-        for (uint64_t j = e + 1; j < hi; j++) k += (a.flag[j] == 2) ? 1u : 0u;
         const uint32_t m = np - 1u;
         const double prob = (m < (uint32_t) kPuProbTable) ? a.prob[m] : pow (a.alpha, (double) m);
         Rng rng; rng.init (a.seed, (uint64_t) a.frame[e], 5u); rng.resume (k, 0, 0.0);
         if (rng.uniform () >= prob) return;
-        PuHood h; pu_hood (a, e, h);
         x = 0; y = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -246,6 +258,21 @@ MX_HD void pu_emit (const PileupArgs &a, uint64_t e)
    int16_t pha = 0;
    if (-1 == pu_energy_to_pha (*a.A, (int) (a.key[e] >> 20), (int) xpix, (int) ypix, (double) a.ib[e], pha)) { pu_error (a, kPuErrPha); return; }
    a.sx[e] = xpix; a.sy[e] = ypix; a.spha[e] = pha; a.emit[e] = 1;
+}
+MX_HD void pu_emit (const PileupArgs &a, uint64_t e)
+{
+   const uint32_t flag = a.flag[e];
+   if (flag == 0) return;
+   uint32_t k = 0;
+   PuHood h;
+   for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) h.at[r][c] = -1;
+   if (flag == 2)
+     {
+        const uint64_t hi = a.hi[e];
+        for (uint64_t j = e + 1; j < hi; j++) k += (a.flag[j] == 2) ? 1u : 0u;
+        pu_hood (a, e, h);
+     }
+   pu_emit_from (a, e, k, h);
 }
 
 // inclusive count of emitted rows up to and including event i (cum: inclusive inside the 256-event tile; tile_sum: exclusive over tiles)

@@ -100,20 +100,32 @@ __global__ void __launch_bounds__ (1024) pu_scan_totals (const __grid_constant__
 // ---------------------------------------------------------------------------------------------------------------------------
 // Fused form: ONE persistent kernel.  A CTA takes tiles of kFuTile consecutive events from a ticket counter, stages the input
 // columns of a window of up to kFuCap events (the tile plus what the tile's last frame needs beyond it) in shared memory and
-// runs the same per-event functions on the window -- the walks over an event's frame run, the 3 x 3 neighbourhoods, the
-// pixel and island sums never leave the SM, and no per-event scratch goes to HBM.  A tile OWNS the frames whose first event
-// lies in it, so every frame is processed exactly once.  Output rows (reference order: frames ascending, reverse file order
-// inside a frame) are placed with a block scan over the window's emit flags and a decoupled look-back over the tiles' row
-// counts (tiles are ticketed in order, so a predecessor is always running or done).  A frame that does not fit the window
-// (more than kFuCap - kFuTile + 1 events is the guaranteed size) raises kPuErrFallback: the host then runs the step kernels above.
+// runs the per-event functions of mx_pileup.cuh on the window -- no per-event scratch goes to HBM.  A tile OWNS the frames
+// whose first event lies in it, so every frame is processed exactly once.
+//
+// What the step kernels do by walking an event's whole frame run (O(frame length) per event and step) is done here with
+//   * block scans over the window: the start / end of every event's frame (segmented max / min of the frame-head positions),
+//     the number of drawing islands behind an event, the output row of an event;
+//   * a hash table in shared memory keyed by (frame, pixel): one pass inserts every event and keeps the LAST event of a
+//     pixel (atomicMax on the stored index = the pixel's representative, marxpileup.c:903-908) and the pixel's event count;
+//     the 3 x 3 neighbourhood of a representative is nine probes.  Only pixels hit more than once replay their events.
+// Output rows (reference order: frames ascending, reverse file order inside a frame) are placed with a decoupled look-back over
+// the tiles' row counts (tiles are ticketed in order, so a predecessor is always running or done).  A frame that does not fit
+// the window (more than kFuCap - kFuTile + 1 events is the guaranteed size) raises kPuErrFallback: the host then runs the step
+// kernels above.  Same arithmetic, same order of operations: the rows are bit-identical to the step kernels' (tests).
 // ---------------------------------------------------------------------------------------------------------------------------
-constexpr int kFuTile = 512, kFuCap = 1024, kFuThreads = 512;
+constexpr int kFuTile = 512, kFuCap = 1024, kFuThreads = 512, kFuHash = 2048;
 constexpr unsigned long long kFuAggregate = 1ull << 62, kFuPrefix = 2ull << 62, kFuValueMask = (1ull << 62) - 1ull;
+constexpr uint32_t kFuEmpty = 0xFFFFFFFFu;
 
 struct FuSmem
 {
    uint32_t frame[kFuCap], key[kFuCap], lo[kFuCap], hi[kFuCap], pn[kFuCap], in[kFuCap], emit[kFuCap], cum[kFuCap];
    float x[kFuCap], y[kFuCap], t[kFuCap], benergy[kFuCap], pb[kFuCap], px[kFuCap], py[kFuCap], ib[kFuCap], sx[kFuCap], sy[kFuCap];
+   uint32_t table[kFuHash];                 // (frame, pixel) -> index of the pixel's last event
+   uint32_t count[kFuHash];                 // events on that pixel
+   uint32_t draws[kFuCap];                  // inclusive prefix of (flag == 2)
+   uint16_t slot[kFuCap];                   // where an event's pixel sits in the table
    int16_t spha[kFuCap];
    int8_t ccd[kFuCap];
    uint8_t flag[kFuCap];
@@ -124,8 +136,71 @@ struct FuSmem
    unsigned long long base;
 };
 
+// block-wide inclusive scan of two consecutive window entries per thread (v0 at 2 tid, v1 at 2 tid + 1) with operator OP;
+// returns the scanned values in v0, v1 and leaves the block total in S.total
+template <class OP>
+__device__ __forceinline__ void fu_scan2 (FuSmem &S, uint32_t &v0, uint32_t &v1, uint32_t identity, OP op)
+{
+   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+   v1 = op (v0, v1);
+   uint32_t s = v1;
+#pragma unroll
+   for (int d = 1; d < 32; d <<= 1)
+     {
+        const uint32_t o = __shfl_up_sync (0xFFFFFFFFu, s, d);
+        if (lane >= (uint32_t) d) s = op (o, s);
+     }
+   __syncthreads ();                        // the previous user of warp_sum is done
+   if (lane == 31u) S.warp_sum[warp] = s;
+   __syncthreads ();
+   uint32_t before = identity;
+   for (uint32_t k = 0; k < warp; k++) before = op (before, S.warp_sum[k]);
+   const uint32_t excl = op (before, __shfl_up_sync (0xFFFFFFFFu, s, 1));
+   const uint32_t left = (lane == 0u) ? before : excl;          // everything before this thread's pair
+   v0 = op (left, v0);
+   v1 = op (left, v1);
+   if (tid == kFuThreads - 1) S.total = v1;
+}
+
+__device__ __forceinline__ uint32_t fu_hash (uint32_t key, uint32_t frame_id)
+{
+   return ((key * 2654435761u) ^ (frame_id * 0x9E3779B1u) ^ (key >> 13)) & (uint32_t) (kFuHash - 1);
+}
+// the table slot of pixel (frame_id, key), or kFuHash if the pixel is empty
+__device__ __forceinline__ uint32_t fu_find (const FuSmem &S, uint32_t key, uint32_t frame_id)
+{
+   uint32_t s = fu_hash (key, frame_id);
+   while (true)
+     {
+        const uint32_t j = S.table[s];
+        if (j == kFuEmpty) return (uint32_t) kFuHash;
+        if ((S.key[j] == key) && (S.lo[j] == frame_id)) return s;
+        s = (s + 1u) & (uint32_t) (kFuHash - 1);
+     }
+}
+
+// the 3 x 3 neighbourhood of representative e by nine probes: slot [r][c] = last event on pixel (y - 1 + r, x - 1 + c) of e's frame
+__device__ __forceinline__ void fu_hood (const FuSmem &S, uint32_t e, PuHood &h)
+{
+   const uint32_t key = S.key[e], fid = S.lo[e];
+#pragma unroll
+   for (int r = 0; r < 3; r++)
+#pragma unroll
+     for (int c = 0; c < 3; c++)
+       {
+          int32_t j = (int32_t) e;
+          if ((r != 1) || (c != 1))
+            {
+               const uint32_t nk = key + (uint32_t) ((r - 1) * 1024 + (c - 1));        // x, y of a keyed event lie in [1, 1022]
+               const uint32_t s = fu_find (S, nk, fid);
+               j = (s == (uint32_t) kFuHash) ? -1 : (int32_t) S.table[s];
+            }
+          h.at[r][c] = j;
+       }
+}
+
 __global__ void __launch_bounds__ (kFuThreads, 2) pu_fused (const __grid_constant__ PileupArgs g, unsigned long long *ticket,
-                                                        unsigned long long *tile_state)
+                                                           unsigned long long *tile_state)
 {
    extern __shared__ __align__ (16) unsigned char fu_raw[];
    FuSmem &S = *reinterpret_cast<FuSmem *> (fu_raw);
@@ -140,6 +215,8 @@ __global__ void __launch_bounds__ (kFuThreads, 2) pu_fused (const __grid_constan
         a.pb = S.pb; a.px = S.px; a.py = S.py; a.ib = S.ib; a.sx = S.sx; a.sy = S.sy; a.spha = S.spha; a.flag = S.flag;
      }
    const uint64_t n_tiles = (g.n + kFuTile - 1) / kFuTile;
+   auto op_max = [] (uint32_t p, uint32_t q) { return max (p, q); };
+   auto op_add = [] (uint32_t p, uint32_t q) { return p + q; };
    while (true)
      {
         __syncthreads ();
@@ -154,21 +231,24 @@ __global__ void __launch_bounds__ (kFuThreads, 2) pu_fused (const __grid_constan
           {
              S.ccd[e] = g.ccd[t0 + e]; S.x[e] = g.x[t0 + e]; S.y[e] = g.y[t0 + e]; S.t[e] = g.t[t0 + e]; S.benergy[e] = g.benergy[t0 + e];
           }
+        for (uint32_t k = tid; k < (uint32_t) kFuHash; k += kFuThreads) { S.table[k] = kFuEmpty; S.count[k] = 0; }
         if (tid == 0) { S.own_lo = cnt; S.own_hi = cnt; a.n = cnt; }
         __syncthreads ();
         for (uint32_t e = tid; e < cnt; e += kFuThreads) pu_frames (a, e);
         __syncthreads ();
         // the frames this tile owns: from the first frame head inside the tile to the end of the frame of the tile's last event
         const uint32_t prev_frame = (t0 == 0) ? 0u : (unsigned int) ((double) g.t[t0 - 1] / g.frame_time);
-        for (uint32_t e = tid; e < cnt; e += kFuThreads)
+        const uint32_t i0 = 2u * tid, i1 = i0 + 1u;
+        auto is_head = [&] (uint32_t e) -> bool
           {
-             if (e < in_tile)
-               {
-                  const bool head = (e == 0) ? ((t0 == 0) || (S.frame[0] != prev_frame)) : (S.frame[e] != S.frame[e - 1]);
-                  if (head) atomicMin (&S.own_lo, e);
-               }
-             else if (S.frame[e] != S.frame[in_tile - 1]) atomicMin (&S.own_hi, e);
-          }
+             if (e >= cnt) return false;
+             return (e == 0) ? ((t0 == 0) || (S.frame[0] != prev_frame)) : (S.frame[e] != S.frame[e - 1]);
+          };
+        const bool h0 = is_head (i0), h1 = is_head (i1);
+        if (h0 && (i0 < in_tile)) atomicMin (&S.own_lo, i0);
+        if (h1 && (i1 < in_tile)) atomicMin (&S.own_lo, i1);
+        if ((i0 >= in_tile) && (i0 < cnt) && (S.frame[i0] != S.frame[in_tile - 1])) atomicMin (&S.own_hi, i0);
+        if ((i1 >= in_tile) && (i1 < cnt) && (S.frame[i1] != S.frame[in_tile - 1])) atomicMin (&S.own_hi, i1);
         __syncthreads ();
         uint32_t own_lo = S.own_lo, own_hi = S.own_hi;
         if (own_lo >= in_tile) { own_lo = 0; own_hi = 0; }          // no frame starts here: an earlier tile owns all of it
@@ -178,34 +258,103 @@ __global__ void __launch_bounds__ (kFuThreads, 2) pu_fused (const __grid_constan
              if (tid == 0) atomicOr (g.error, kPuErrFallback);
              own_hi = own_lo;
           }
-        if (tid == 0) a.n = own_hi;                                 // walks stop at the end of the owned frames
-        __syncthreads ();
-        for (uint32_t e = own_lo + tid; e < own_hi; e += kFuThreads) pu_store (a, e);
-        __syncthreads ();
-        for (uint32_t e = own_lo + tid; e < own_hi; e += kFuThreads) pu_island (a, e);
-        __syncthreads ();
-        for (uint32_t e = own_lo + tid; e < own_hi; e += kFuThreads) pu_detect (a, e);
-        __syncthreads ();
-        for (uint32_t e = own_lo + tid; e < own_hi; e += kFuThreads) pu_emit (a, e);
-        __syncthreads ();
-        // inclusive prefix sum of the emit flags over the window (two entries per thread)
+        // frame start of every event: running maximum of the head positions (+ 1, so that 0 can be the identity)
         {
-           const uint32_t i0 = 2u * tid, i1 = i0 + 1u;
-           const uint32_t v0 = ((i0 >= own_lo) && (i0 < own_hi)) ? S.emit[i0] : 0u, v1 = ((i1 >= own_lo) && (i1 < own_hi)) ? S.emit[i1] : 0u;
-           uint32_t s = v0 + v1;
+           uint32_t v0 = h0 ? i0 + 1u : 0u, v1 = h1 ? i1 + 1u : 0u;
+           fu_scan2 (S, v0, v1, 0u, op_max);
+           S.lo[i0] = (v0 > 0u) ? v0 - 1u : 0u;
+           S.lo[i1] = (v1 > 0u) ? v1 - 1u : 0u;
+        }
+        __syncthreads ();
+        // frame end: the first head position above the event.  Scan the window backwards: scan index i stands for event
+        // kFuCap - 1 - i, a head at event q contributes kFuCap - q (0: no head), the running maximum is the NEAREST head at or
+        // above the event
+        {
+           const uint32_t q0 = (uint32_t) kFuCap - 1u - i0, q1 = (uint32_t) kFuCap - 1u - i1;
+           uint32_t v0 = is_head (q0) ? (uint32_t) kFuCap - q0 : 0u, v1 = is_head (q1) ? (uint32_t) kFuCap - q1 : 0u;
+           fu_scan2 (S, v0, v1, 0u, op_max);
+           S.hi[q0] = v0; S.hi[q1] = v1;                                // "first head at a position >= the event", encoded
+        }
+        __syncthreads ();
+        // the value at e + 1 is "first head at a position > e": decode it (no head: the window end)
+        for (uint32_t e = tid; e < cnt; e += kFuThreads)
+          {
+             const uint32_t v = (e + 1u < (uint32_t) kFuCap) ? S.hi[e + 1u] : 0u;
+             S.cum[e] = (v > 0u) ? (uint32_t) kFuCap - v : cnt;
+          }
+        __syncthreads ();
+        for (uint32_t e = tid; e < cnt; e += kFuThreads) S.hi[e] = min (S.cum[e], max (own_hi, e + 1u));
+        if (tid == 0) a.n = own_hi;
+        __syncthreads ();
+        // one pass over the owned events: (frame, pixel) -> last event of the pixel, and the pixel's event count
+        for (uint32_t e = own_lo + tid; e < own_hi; e += kFuThreads)
+          {
+             const uint32_t key = S.key[e];
+             if (key == kPuNoKey) continue;
+             const uint32_t fid = S.lo[e];
+             uint32_t s = fu_hash (key, fid);
+             while (true)
+               {
+                  const uint32_t old = atomicCAS (&S.table[s], kFuEmpty, e);
+                  if (old == kFuEmpty) break;
+                  // the slot's pixel is identified by any of its events: key and frame start
+                  if ((S.key[old] == key) && (S.lo[old] == fid)) { atomicMax (&S.table[s], e); break; }
+                  s = (s + 1u) & (uint32_t) (kFuHash - 1);
+               }
+             atomicAdd (&S.count[s], 1u);
+             S.slot[e] = (uint16_t) s;
+          }
+        __syncthreads ();
+        // pixel state at the representatives (store_event): a pixel hit once needs no walk
+        for (uint32_t e = own_lo + tid; e < own_hi; e += kFuThreads)
+          {
+             if ((S.key[e] == kPuNoKey) || (S.table[S.slot[e]] != e)) continue;
+             pu_pixel_state (a, e, (S.count[S.slot[e]] == 1u) ? e : S.lo[e]);
+          }
+        __syncthreads ();
+        // neighbourhoods by nine probes, island sums (collect_charge)
+        for (uint32_t e = own_lo + tid; e < own_hi; e += kFuThreads)
+          {
+             if (S.pn[e] == 0) continue;
+             PuHood h;
+             fu_hood (S, e, h);
+             pu_island_from (a, e, h);
+          }
+        __syncthreads ();
+        for (uint32_t e = own_lo + tid; e < own_hi; e += kFuThreads)
+          {
+             if (S.pn[e] == 0) continue;
+             PuHood h;
+             fu_hood (S, e, h);
+             pu_detect_from (a, e, h);
+          }
+        __syncthreads ();
+        // draw index of an island = number of drawing islands of its frame behind it in file order
+        {
+           uint32_t v0 = ((i0 >= own_lo) && (i0 < own_hi) && (S.flag[i0] == 2)) ? 1u : 0u;
+           uint32_t v1 = ((i1 >= own_lo) && (i1 < own_hi) && (S.flag[i1] == 2)) ? 1u : 0u;
+           fu_scan2 (S, v0, v1, 0u, op_add);
+           S.draws[i0] = v0; S.draws[i1] = v1;
+        }
+        __syncthreads ();
+        for (uint32_t e = own_lo + tid; e < own_hi; e += kFuThreads)
+          {
+             if (S.flag[e] == 0) continue;
+             PuHood h;
+             if (S.flag[e] == 2) fu_hood (S, e, h);
+             else
+               {
 #pragma unroll
-           for (int d = 1; d < 32; d <<= 1)
-             {
-                const uint32_t o = __shfl_up_sync (0xFFFFFFFFu, s, d);
-                if (lane >= (uint32_t) d) s += o;
-             }
-           if (lane == 31u) S.warp_sum[warp] = s;
-           __syncthreads ();
-           uint32_t before = 0;
-           for (uint32_t k = 0; k < warp; k++) before += S.warp_sum[k];
-           s += before;
-           S.cum[i0] = s - v1; S.cum[i1] = s;
-           if (tid == kFuThreads - 1) S.total = s;
+                  for (int q = 0; q < 9; q++) h.at[q / 3][q % 3] = -1;
+               }
+             pu_emit_from (a, e, S.draws[S.hi[e] - 1u] - S.draws[e], h);
+          }
+        __syncthreads ();
+        // inclusive prefix sum of the emit flags over the window
+        {
+           uint32_t v0 = ((i0 >= own_lo) && (i0 < own_hi)) ? S.emit[i0] : 0u, v1 = ((i1 >= own_lo) && (i1 < own_hi)) ? S.emit[i1] : 0u;
+           fu_scan2 (S, v0, v1, 0u, op_add);
+           S.cum[i0] = v0; S.cum[i1] = v1;
         }
         __syncthreads ();
         // decoupled look-back over the tiles' row counts: warp 0 inspects 32 predecessors per round (a tile that is still at

@@ -77,6 +77,7 @@ struct oracle
    const double *src, *dith, *hrma, *grat, *acis;
    const double *spec_e, *spec_c; uint32_t nspec;
    const double *src_rot, *img_prm; const float *img_cdf; uint32_t nimg;   /* LINE / IMAGE sources */
+   const double *ffield;                                                                              /* MirrorType=FLATFIELD: min_y, min_z, max_y, max_z, x_pos (ffield.c:45-49) */
    uint64_t batch_first;                                                                              /* global index of the batch's first ray: the records' tags hold the low 32 bits only (marx.h:98) */
    const double *asp; uint32_t nasp, asp_pos; uint64_t last_generated;                                  /* ASPSOL states [nasp][7] (dither.c:288-359) */
    double asp_t_prev;
@@ -153,7 +154,8 @@ oracle_t *oracle_open (const char *path, uint64_t seed)
    o->seed = seed;
    o->src = (const double *) need (o, "source.params", NULL);
    o->dith = (const double *) need (o, "dither.params", NULL);
-   o->hrma = (const double *) need (o, "hrma.params", NULL);
+   o->ffield = find (o, "ffield.params") ? (const double *) need (o, "ffield.params", NULL) : NULL;
+   o->hrma = o->ffield ? o->ffield : (const double *) need (o, "hrma.params", NULL);
    o->grat = (const double *) need (o, "grating.params", NULL);
    o->hrc = find (o, "hrc.params") ? (const double *) need (o, "hrc.params", NULL) : NULL;
    o->acis = o->hrc ? NULL : (const double *) need (o, "acis.params", NULL);
@@ -179,10 +181,13 @@ oracle_t *oracle_open (const char *path, uint64_t seed)
         o->img_cdf = (const float *) need (o, "source.image_cdf", &c); o->nimg = (uint32_t) c;
         if (!o->img_prm || !o->img_cdf) { oracle_close (o); return NULL; }
      }
-   o->opt_e = (const float *) need (o, "hrma.opt_energies", &c); o->nopt = (uint32_t) c;
-   o->opt_b = (const float *) need (o, "hrma.opt_betas", &c);
-   o->opt_d = (const float *) need (o, "hrma.opt_deltas", &c);
-   for (k = 0; k < NUM_SHELLS; k++)
+   if (!o->ffield)
+     {
+        o->opt_e = (const float *) need (o, "hrma.opt_energies", &c); o->nopt = (uint32_t) c;
+        o->opt_b = (const float *) need (o, "hrma.opt_betas", &c);
+        o->opt_d = (const float *) need (o, "hrma.opt_deltas", &c);
+     }
+   for (k = 0; (k < NUM_SHELLS) && !o->ffield; k++)
      {
         shell_t *s = &o->shell[k];
         s->s = (const double *) needf (o, &c, "hrma.shell%d.params", k, 0);
@@ -665,6 +670,23 @@ static void stage_mirror (oracle_t *o, uint64_t n, oracle_photon *ph)
    const double *H = o->hrma; double dist = o->src[8], cap = H[1];
    int ideal = (int) H[2], struts = (int) H[5], scale = (int) H[6];
    uint64_t i;
+   if (o->ffield)
+     {
+        /* _marx_ff_mirror_reflect / project_photon, ffield.c:61-108: no optics, the ray starts on a rectangle at x = FF_XPos */
+        const double *F = o->ffield;
+        for (i = 0; i < n; i++)
+          {
+             oracle_photon *at = ph + i; rng_t r;
+             if (at->flags & 0xFF) continue;
+             rng_set (&r, o->seed, ray_of (o, at->tag), 1);
+             at->x[2] = F[1] + rng_uniform (&r) * (F[3] - F[1]);
+             at->x[1] = F[0] + rng_uniform (&r) * (F[2] - F[0]);
+             at->x[0] = F[4];
+             if (dist > 0.0)
+               { at->p[0] = 1.0 * at->x[0] + dist * at->p[0]; at->p[1] = 1.0 * at->x[1] + dist * at->p[1]; at->p[2] = 1.0 * at->x[2] + dist * at->p[2]; norm3 (at->p); }
+          }
+        return;
+     }
    for (i = 0; i < n; i++)
      {
         oracle_photon *at = ph + i; rng_t r; const shell_t *sh; const double *s; int k, found = 0, st;

@@ -306,3 +306,61 @@ def test_marx_gpu_big_batches_background_writer_equals_synchronous_writer(tmp_pa
             assert np.allclose(a, b, rtol=1e-5, atol=1e-6), f
         else:
             assert (a == b).mean() > 0.9999, f
+
+
+def write_saosac_fits(path, n, seed=3):
+    """a synthetic SAOSAC ray file (s-saosac.c:95-140: BINTABLE 'RAYTRACE', double columns RT_X ... RT_KEV, RT_WGHT, RT_TIME): rays
+    behind the mirror, on the four shells' radii at the file's x = 0 plane, converging on the focus with a small scatter"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "ref"))
+    from synth_acis_caldb import bintable_hdu, primary_hdu
+    r = np.random.default_rng(seed)
+    cap = 10079.77                                            # mm in front of the focus (the CAP; the source projects to it)
+    radius = r.choice(np.array([600.0, 483.0, 426.0, 317.0]), n) + r.normal(0.0, 2.0, n)
+    phi = r.uniform(0.0, 2 * np.pi, n)
+    y, z = radius * np.cos(phi), radius * np.sin(phi)
+    target = r.normal(0.0, 0.02, (n, 2))                      # mm at the focal plane
+    d = np.stack([-cap * np.ones(n), target[:, 0] - y, target[:, 1] - z], axis=1)
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    cols = [("RT_X", "D", 1, np.zeros(n)), ("RT_Y", "D", 1, y), ("RT_Z", "D", 1, z), ("RT_COSX", "D", 1, d[:, 0]), ("RT_COSY", "D", 1, d[:, 1]),
+            ("RT_COSZ", "D", 1, d[:, 2]), ("RT_KEV", "D", 1, r.uniform(0.5, 6.0, n)), ("RT_WGHT", "D", 1, r.uniform(0.2, 1.0, n)),
+            ("RT_TIME", "D", 1, 1000.0 + np.cumsum(r.exponential(0.3, n)))]
+    with open(path, "wb") as f:
+        f.write(primary_hdu() + bintable_hdu("RAYTRACE", cols, n))
+    return path
+
+
+@pytest.mark.gpu
+@needs_driver
+def test_saosac_rays_are_read_by_the_stock_host_code_and_traced_on_the_gpu(tmp_path):
+    """SourceType=SAOSAC (s-saosac.c): rays of an external mirror ray trace, read by the UNMODIFIED host code (jdfits), weighted
+    (JDMrandom >= RT_WGHT rejects a ray at the source, :206-211), assigned a mirror shell, and handed to the device with the mirror
+    stage marked done.  Same three checks as for the USER source; a synthetic ray file stands in for a real SAOSAC product."""
+    cfg = CONFIGS["c2_hetg_acis_s"]
+    n, dn, seed = 120000, 60000, 11
+    fits = write_saosac_fits(str(tmp_path / "saosac.fits"), n)
+    base = (COMMON + [a for a in cfg["args"] if not a.startswith("SourceType=")]
+            + ["SourceType=SAOSAC", "SAOSACFile=" + fits, "NumRays=%d" % n, "dNumRays=%d" % dn, "RandomSeed=%d" % seed, "Verbose=1"])
+    rays = str(tmp_path / "rays.dat")
+    run_marx(os.path.join(REF, "marx"), tmp_path / "dump", base + ["DumpToRayFile=yes", "RayFile=" + rays])
+    raw = np.fromfile(rays, dtype=marx_b200.PHOTON_DTYPE, offset=16)
+    assert 0.3 * n < len(raw) <= n                              # the weight test removed ~40 % of the rays at the source
+    p = run_marx(MARX_GPU, tmp_path / "out", base)
+    assert "marxb200: ray trace on CUDA device" in p.stdout and "Reflecting from HRMA [B200]" not in p.stdout
+    assert "Diffracting from HETG [B200]" in p.stdout
+    got = read_dir(tmp_path / "out")
+    live = raw[(raw["flags"] & 0xFF) == 0]
+    with marx_b200.MarxB200("c2_hetg_acis_s", seed=seed, max_photons=len(live) + 16) as m:
+        m.upload(live)
+        m.grating_diffract(); m.detect()
+        ph = m.download().copy()
+    assert len(got["energy.dat"]) == len(ph) > 2000
+    assert (got["tag.dat"].astype(np.uint32) == ph["tag"]).all()
+    assert (got["energy.dat"] == ph["energy"].astype(np.float32)).all()
+    assert (got["mirror.dat"] == ph["mirror_shell"].astype(np.int16)).all() and len(np.unique(ph["mirror_shell"])) == 4
+    assert (got["detector.dat"] == ph["ccd_num"]).all() and (got["order.dat"] == ph["order"]).all()
+    assert (got["xpixel.dat"] == ph["y_pixel"]).all() and (got["ypixel.dat"] == ph["z_pixel"]).all()
+    assert (got["pha.dat"] == ph["pulse_height"]).all()
+    q = run_marx(os.path.join(REF, "marx"), tmp_path / "cpu", base)
+    n_cpu, n_gpu = len(read_dir(tmp_path / "cpu")["energy.dat"]), len(ph)
+    assert abs(n_cpu - n_gpu) < 5.0 * np.sqrt(n_cpu + n_gpu), (n_cpu, n_gpu)

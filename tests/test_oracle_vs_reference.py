@@ -104,6 +104,12 @@ CASES = [
      3, (1 << 33) + 12345, 12000),
     ("ray_index_across_2_32", ["MinEnergy=0.3", "MaxEnergy=8.0", "GratingType=HETG", "DetectorType=ACIS-S", "DitherModel=INTERNAL"],
      3, (1 << 32) - 6000, 12000),
+    # MirrorType=FLATFIELD (ffield.c): no optics, rays start on a rectangle in front of the detector (24 cm^2 instead of the HRMA's
+    # 1145: the flux is raised so that arrival times stay in the range of the other cases)
+    ("flatfield_acis_s", ["MirrorType=FLATFIELD", "FF_MinY=-30", "FF_MaxY=45", "FF_MinZ=-20", "FF_MaxZ=12", "FF_XPos=9000", "MinEnergy=0.5",
+                          "MaxEnergy=7.0", "GratingType=NONE", "DetectorType=ACIS-S", "DitherModel=INTERNAL", "SourceFlux=0.15"], 61, 0, 10000),
+    ("flatfield_finite_distance_hetg_hrc_s", ["MirrorType=FLATFIELD", "SourceDistance=537.0", "MinEnergy=0.5", "MaxEnergy=3.0",
+                                              "GratingType=HETG", "DetectorType=HRC-S", "DitherModel=NONE"], 62, 4096, 10000),
     ("sector_files_off_unit_order", ["MinEnergy=0.8", "MaxEnergy=3.0", "GratingType=HETG", "DetectorType=ACIS-S", "DitherModel=INTERNAL",
                                      "Use_HETG_Sector_Files=no"], 8, 1000, 10000),
 ]

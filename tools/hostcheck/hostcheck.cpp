@@ -65,6 +65,7 @@ extern "C" int marxb200_set_dither (marxb200_ctx *, const marxb200_dither_desc *
      }
    return 0;
 }
+extern "C" int marxb200_set_flatfield (marxb200_ctx *, const marxb200_flatfield_desc *) { return 0; }
 extern "C" int marxb200_set_hrma (marxb200_ctx *, const marxb200_hrma_desc *d)
 { HostUploader up; std::string e; int r = build_hrma_blob (up, d, gB1, e); snprintf (gErr, sizeof gErr, "%s", e.c_str ()); return r; }
 extern "C" int marxb200_set_grating (marxb200_ctx *, const marxb200_grating_desc *d)

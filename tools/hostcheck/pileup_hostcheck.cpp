@@ -37,6 +37,7 @@ extern "C" const char *marxb200_last_error (void) { return gErr; }
 extern "C" int marxb200_set_source (marxb200_ctx *, const marxb200_source_desc *) { return 0; }
 extern "C" int marxb200_set_dither (marxb200_ctx *, const marxb200_dither_desc *) { return 0; }
 extern "C" int marxb200_set_hrma (marxb200_ctx *, const marxb200_hrma_desc *) { return 0; }
+extern "C" int marxb200_set_flatfield (marxb200_ctx *, const marxb200_flatfield_desc *) { return 0; }
 extern "C" int marxb200_set_grating (marxb200_ctx *, const marxb200_grating_desc *) { return 0; }
 extern "C" int marxb200_set_hrc_s (marxb200_ctx *, const marxb200_hrc_s_desc *) { snprintf (gErr, sizeof gErr, "pile-up is an ACIS model"); return -1; }
 extern "C" int marxb200_set_acis (marxb200_ctx *, const marxb200_acis_desc *d)
