@@ -195,6 +195,17 @@ def driver_leg(args, n_rays=1 << 30, dn=1 << 24, ref_rays=2000000):
         timing = [ln for ln in p.stdout.splitlines() if "host seconds" in ln]
         out = {"rays": n_rays, "rays_per_batch": dn, "wall_s": wall, "rays_per_s": n_rays / wall, "events": rows, "event_file_bytes": nbytes,
                "writer_threads": int(os.environ.get("MARXB200_WRITER_THREADS", "8")), "breakdown": timing[-1].split("marxb200: ")[-1] if timing else None}
+        if timing:
+            import re
+            f = {k: float(v) for k, v in re.findall(r"(init\+upload|CUDA context|create_photons|stages|write_photons) ([0-9.]+)", timing[-1])}
+            if {"create_photons", "stages", "write_photons"} <= set(f):
+                loop = f["create_photons"] + f["stages"] + f["write_photons"]
+                out["loop_s"] = loop
+                out["loop_rays_per_s"] = n_rays / loop
+                out["cuda_context_s"] = f.get("CUDA context")
+                out["note"] = ("wall_s is the whole process: CUDA context creation on this box (cuda_context_s) dominates a run the int NumRays of "
+                               "marx.c:86-87 caps at 2^31 rays; loop_s = host seconds inside the wrapped per-batch calls (create, stages, write) = "
+                               "the rate of the collection loop itself, files written to tmpfs by the background writer")
     finally:
         shutil.rmtree(d, ignore_errors=True)
     if not args.no_cpu_baseline and os.path.exists(os.path.join(ref, "marx")):

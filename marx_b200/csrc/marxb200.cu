@@ -1712,28 +1712,25 @@ static int pileup_impl (marxb200_ctx *c, uint64_t n, const marxb200_pileup_in *i
                if (e_ != cudaSuccess) { status = fail ("marxb200_pileup_run: upload: %s", cudaGetErrorString (e_)); copied = false; break; }
             }
         if (!copied) break;
-        PU_OK (cudaEventRecord (e0, c->stream));
+        // the fused kernel (window of 1024 events: frames of up to 513), then the step kernels.  (A 256-event window -- eight small
+        // CTAs per SM -- measured slower: four times the tiles, and the look-back over the tiles' row counts grows with the tiles in flight)
         int nl = 0;
-        if (fused) mx::launch_pileup_fused (a, fused_scratch, c->num_sms, c->stream, &nl);
-        else mx::launch_pileup (a, c->num_sms, c->stream, &nl);
-        PU_OK (cudaEventRecord (e1, c->stream));
-        c->launches += (uint64_t) nl;
-        PU_OK (cudaGetLastError ());
-        PU_OK (cudaMemcpyAsync (&rows, a.n_out, 8, cudaMemcpyDeviceToHost, c->stream));
-        PU_OK (cudaMemcpyAsync (&err, a.error, 4, cudaMemcpyDeviceToHost, c->stream));
-        PU_OK (cudaStreamSynchronize (c->stream));
-        if (fused && (err & mx::kPuErrFallback))
+        const int attempts[3] = {256, 1024, 0};
+        for (int k = fused ? 1 : 2; k < 3; k++)
           {
              PU_OK (cudaMemsetAsync (p, 0, 16, c->stream));
              PU_OK (cudaEventRecord (e0, c->stream));
-             mx::launch_pileup (a, c->num_sms, c->stream, &nl);
+             if (attempts[k]) mx::launch_pileup_fused (a, fused_scratch, attempts[k], c->num_sms, c->stream, &nl);
+             else mx::launch_pileup (a, c->num_sms, c->stream, &nl);
              PU_OK (cudaEventRecord (e1, c->stream));
              c->launches += (uint64_t) nl;
              PU_OK (cudaGetLastError ());
              PU_OK (cudaMemcpyAsync (&rows, a.n_out, 8, cudaMemcpyDeviceToHost, c->stream));
              PU_OK (cudaMemcpyAsync (&err, a.error, 4, cudaMemcpyDeviceToHost, c->stream));
              PU_OK (cudaStreamSynchronize (c->stream));
+             if (0 == (err & mx::kPuErrFallback)) break;
           }
+        if (status != 0) break;
         if (err & mx::kPuErrCcd) { status = fail ("marxb200_pileup_run: an event's CCD id is outside 0..9"); break; }
         if (err & mx::kPuErrCorrupt) { status = fail ("marxb200_pileup_run: pixel coordinate beyond the chip (corrupt file?)"); break; }
         if (err & mx::kPuErrFrameTooLong) { status = fail ("marxb200_pileup_run: an exposure frame holds more than 65536 events"); break; }

@@ -302,7 +302,7 @@ struct PhotonSoA;
 // cols: x, y, t, benergy, then the six dither columns
 void launch_pileup_gather (const PhotonSoA &in, const unsigned long long *n_ptr, uint64_t max_n, const double *dev_start_time, double total_time,
                            int8_t *ccd, float *const cols[10], cudaStream_t s);
-void launch_pileup_fused (const PileupArgs &a, void *scratch, int num_sms, cudaStream_t s, int *n_launches);
+void launch_pileup_fused (const PileupArgs &a, void *scratch, int window, int num_sms, cudaStream_t s, int *n_launches);
 #endif
 
 }  // namespace mx

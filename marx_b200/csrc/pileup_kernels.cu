@@ -14,17 +14,6 @@ namespace mx {
 
 constexpr int kPuTile = 256;            // pu_rows_through (mx_pileup.cuh) shifts by 8
 
-__device__ __forceinline__ unsigned long long ld_relaxed (const unsigned long long *p)
-{
-   unsigned long long v;
-   asm volatile ("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-   return v;
-}
-__device__ __forceinline__ void st_relaxed (unsigned long long *p, unsigned long long v)
-{
-   asm volatile ("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-}
-
 template <int STEP>
 __global__ void __launch_bounds__ (kPuTile) pu_step (const __grid_constant__ PileupArgs a)
 {
@@ -107,23 +96,27 @@ __global__ void __launch_bounds__ (1024) pu_scan_totals (const __grid_constant__
 //   * block scans over the window: the start / end of every event's frame (segmented max / min of the frame-head positions),
 //     the number of drawing islands behind an event, the output row of an event;
 //   * a hash table in shared memory keyed by (frame, pixel): one pass inserts every event and keeps the LAST event of a
-//     pixel (atomicMax on the stored index = the pixel's representative, marxpileup.c:903-908) and the pixel's event count;
+//     pixel (atomicMax on the stored index = the pixel's representative, marxpileup.c:903-908) and marks pixels hit more than once;
 //     the 3 x 3 neighbourhood of a representative is nine probes.  Only pixels hit more than once replay their events.
-// Output rows (reference order: frames ascending, reverse file order inside a frame) are placed with a decoupled look-back over
-// the tiles' row counts (tiles are ticketed in order, so a predecessor is always running or done).  A frame that does not fit
+// Output rows (reference order: frames ascending, reverse file order inside a frame) are placed by the step path's three small
+// kernels (prefix sum over the emit flags + scatter) from the rows this kernel stages at the events' own slots.  A frame that does not fit
 // the window (more than kFuCap - kFuTile + 1 events is the guaranteed size) raises kPuErrFallback: the host then runs the step
 // kernels above.  Same arithmetic, same order of operations: the rows are bit-identical to the step kernels' (tests).
 // ---------------------------------------------------------------------------------------------------------------------------
-constexpr int kFuTile = 512, kFuCap = 1024, kFuThreads = 512, kFuHash = 2048;
-constexpr unsigned long long kFuAggregate = 1ull << 62, kFuPrefix = 2ull << 62, kFuValueMask = (1ull << 62) - 1ull;
 constexpr uint32_t kFuEmpty = 0xFFFFFFFFu;
 
-struct FuSmem
+// W = window capacity in events (tile = W / 2 events, W / 2 threads, 2 W hash slots: load <= 0.5): <256> keeps eight 128-thread CTAs per SM in
+// flight -- the phases below are short and separated by block barriers, so it is the number of independent CTAs that hides the
+// barrier waits (ncu: with one 512-thread CTA pair per SM 33 % of the stall samples sat on barriers) -- and serves frames of up to
+// 129 events; <1024> serves frames of up to 513 events.
+template <int W> struct FuSmem
 {
+   static constexpr int kFuCap = W, kFuTile = W / 2, kFuThreads = W / 2, kFuHash = 2 * W;
    uint32_t frame[kFuCap], key[kFuCap], lo[kFuCap], hi[kFuCap], pn[kFuCap], in[kFuCap], emit[kFuCap], cum[kFuCap];
    float x[kFuCap], y[kFuCap], t[kFuCap], benergy[kFuCap], pb[kFuCap], px[kFuCap], py[kFuCap], ib[kFuCap], sx[kFuCap], sy[kFuCap];
    uint32_t table[kFuHash];                 // (frame, pixel) -> index of the pixel's last event
-   uint32_t count[kFuHash];                 // events on that pixel
+   uint8_t multi[kFuHash];                  // the pixel was hit more than once: its events are replayed in order
+   uint32_t occupied[kFuHash / 4];          // one bit per second-hash value of an inserted (frame, pixel): 8 bits per window slot
    uint32_t draws[kFuCap];                  // inclusive prefix of (flag == 2)
    uint16_t slot[kFuCap];                   // where an event's pixel sits in the table
    int16_t spha[kFuCap];
@@ -138,8 +131,8 @@ struct FuSmem
 
 // block-wide inclusive scan of two consecutive window entries per thread (v0 at 2 tid, v1 at 2 tid + 1) with operator OP;
 // returns the scanned values in v0, v1 and leaves the block total in S.total
-template <class OP>
-__device__ __forceinline__ void fu_scan2 (FuSmem &S, uint32_t &v0, uint32_t &v1, uint32_t identity, OP op)
+template <int W, class OP>
+__device__ __forceinline__ void fu_scan2 (FuSmem<W> &S, uint32_t &v0, uint32_t &v1, uint32_t identity, OP op)
 {
    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
    v1 = op (v0, v1);
@@ -159,17 +152,30 @@ __device__ __forceinline__ void fu_scan2 (FuSmem &S, uint32_t &v0, uint32_t &v1,
    const uint32_t left = (lane == 0u) ? before : excl;          // everything before this thread's pair
    v0 = op (left, v0);
    v1 = op (left, v1);
-   if (tid == kFuThreads - 1) S.total = v1;
+   if (tid == (uint32_t) FuSmem<W>::kFuThreads - 1u) S.total = v1;
 }
 
-__device__ __forceinline__ uint32_t fu_hash (uint32_t key, uint32_t frame_id)
+template <int W> __device__ __forceinline__ uint32_t fu_hash (uint32_t key, uint32_t frame_id)
 {
-   return ((key * 2654435761u) ^ (frame_id * 0x9E3779B1u) ^ (key >> 13)) & (uint32_t) (kFuHash - 1);
+   return ((key * 2654435761u) ^ (frame_id * 0x9E3779B1u) ^ (key >> 13)) & (uint32_t) (FuSmem<W>::kFuHash - 1);
 }
 // the table slot of pixel (frame_id, key), or kFuHash if the pixel is empty
-__device__ __forceinline__ uint32_t fu_find (const FuSmem &S, uint32_t key, uint32_t frame_id)
+// second, independent hash into the occupancy bitmap (8 * kFuHash bits)
+template <int W> __device__ __forceinline__ uint32_t fu_hash2 (uint32_t key, uint32_t frame_id)
 {
-   uint32_t s = fu_hash (key, frame_id);
+   uint32_t h = key * 0x85EBCA6Bu + frame_id * 0xC2B2AE35u;
+   h ^= h >> 15;
+   return h & (uint32_t) (8 * FuSmem<W>::kFuHash - 1);
+}
+// the table slot of pixel (frame_id, key), or kFuHash if the pixel is empty
+template <int W> __device__ __forceinline__ uint32_t fu_find (const FuSmem<W> &S, uint32_t key, uint32_t frame_id)
+{
+   constexpr int kFuHash = FuSmem<W>::kFuHash;
+   // an empty pixel is recognised by one bit test in most cases (<= 1024 pixels in 16384 bits: 6 % false positives), without
+   // entering the probe loop, whose trip counts differ from lane to lane
+   const uint32_t b = fu_hash2<W> (key, frame_id);
+   if (0u == (S.occupied[b >> 5] & (1u << (b & 31u)))) return (uint32_t) kFuHash;
+   uint32_t s = fu_hash<W> (key, frame_id);
    while (true)
      {
         const uint32_t j = S.table[s];
@@ -178,10 +184,12 @@ __device__ __forceinline__ uint32_t fu_find (const FuSmem &S, uint32_t key, uint
         s = (s + 1u) & (uint32_t) (kFuHash - 1);
      }
 }
-
-// the 3 x 3 neighbourhood of representative e by nine probes: slot [r][c] = last event on pixel (y - 1 + r, x - 1 + c) of e's frame
-__device__ __forceinline__ void fu_hood (const FuSmem &S, uint32_t e, PuHood &h)
+// the 3 x 3 neighbourhood of representative e by eight probes: slot [r][c] = last event on pixel (y - 1 + r, x - 1 + c) of e's frame.
+// (Advancing the eight probe sequences of a thread together, one slot each per round, measured SLOWER -- 1.23 against 1.04 ms for
+// the whole call: the probe state of eight sequences costs more than the divergence it removes.)
+template <int W> __device__ __forceinline__ void fu_hood (const FuSmem<W> &S, uint32_t e, PuHood &h)
 {
+   constexpr int kFuHash = FuSmem<W>::kFuHash;
    const uint32_t key = S.key[e], fid = S.lo[e];
 #pragma unroll
    for (int r = 0; r < 3; r++)
@@ -199,12 +207,13 @@ __device__ __forceinline__ void fu_hood (const FuSmem &S, uint32_t e, PuHood &h)
        }
 }
 
-__global__ void __launch_bounds__ (kFuThreads, 2) pu_fused (const __grid_constant__ PileupArgs g, unsigned long long *ticket,
-                                                           unsigned long long *tile_state)
+template <int W>
+__global__ void __launch_bounds__ (W / 2, (W <= 256) ? 8 : 2) pu_fused (const __grid_constant__ PileupArgs g, unsigned long long *ticket)
 {
+   constexpr int kFuCap = FuSmem<W>::kFuCap, kFuTile = FuSmem<W>::kFuTile, kFuThreads = FuSmem<W>::kFuThreads, kFuHash = FuSmem<W>::kFuHash;
    extern __shared__ __align__ (16) unsigned char fu_raw[];
-   FuSmem &S = *reinterpret_cast<FuSmem *> (fu_raw);
-   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+   FuSmem<W> &S = *reinterpret_cast<FuSmem<W> *> (fu_raw);
+   const uint32_t tid = threadIdx.x;
    // the per-event functions see the window through the same argument block, its columns pointing into shared memory
    PileupArgs &a = S.args;
    if (tid == 0)
@@ -231,7 +240,8 @@ __global__ void __launch_bounds__ (kFuThreads, 2) pu_fused (const __grid_constan
           {
              S.ccd[e] = g.ccd[t0 + e]; S.x[e] = g.x[t0 + e]; S.y[e] = g.y[t0 + e]; S.t[e] = g.t[t0 + e]; S.benergy[e] = g.benergy[t0 + e];
           }
-        for (uint32_t k = tid; k < (uint32_t) kFuHash; k += kFuThreads) { S.table[k] = kFuEmpty; S.count[k] = 0; }
+        for (uint32_t k = tid; k < (uint32_t) kFuHash; k += kFuThreads) { S.table[k] = kFuEmpty; S.multi[k] = 0; }
+        for (uint32_t k = tid; k < (uint32_t) kFuHash / 4u; k += kFuThreads) S.occupied[k] = 0;
         if (tid == 0) { S.own_lo = cnt; S.own_hi = cnt; a.n = cnt; }
         __syncthreads ();
         for (uint32_t e = tid; e < cnt; e += kFuThreads) pu_frames (a, e);
@@ -292,16 +302,20 @@ __global__ void __launch_bounds__ (kFuThreads, 2) pu_fused (const __grid_constan
              const uint32_t key = S.key[e];
              if (key == kPuNoKey) continue;
              const uint32_t fid = S.lo[e];
-             uint32_t s = fu_hash (key, fid);
+             uint32_t s = fu_hash<W> (key, fid);
              while (true)
                {
                   const uint32_t old = atomicCAS (&S.table[s], kFuEmpty, e);
-                  if (old == kFuEmpty) break;
+                  if (old == kFuEmpty)
+                    {
+                       const uint32_t b = fu_hash2<W> (key, fid);
+                       atomicOr (&S.occupied[b >> 5], 1u << (b & 31u));
+                       break;
+                    }
                   // the slot's pixel is identified by any of its events: key and frame start
-                  if ((S.key[old] == key) && (S.lo[old] == fid)) { atomicMax (&S.table[s], e); break; }
+                  if ((S.key[old] == key) && (S.lo[old] == fid)) { atomicMax (&S.table[s], e); S.multi[s] = 1; break; }
                   s = (s + 1u) & (uint32_t) (kFuHash - 1);
                }
-             atomicAdd (&S.count[s], 1u);
              S.slot[e] = (uint16_t) s;
           }
         __syncthreads ();
@@ -309,7 +323,7 @@ __global__ void __launch_bounds__ (kFuThreads, 2) pu_fused (const __grid_constan
         for (uint32_t e = own_lo + tid; e < own_hi; e += kFuThreads)
           {
              if ((S.key[e] == kPuNoKey) || (S.table[S.slot[e]] != e)) continue;
-             pu_pixel_state (a, e, (S.count[S.slot[e]] == 1u) ? e : S.lo[e]);
+             pu_pixel_state (a, e, S.multi[S.slot[e]] ? S.lo[e] : e);
           }
         __syncthreads ();
         // neighbourhoods by nine probes, island sums (collect_charge)
@@ -350,86 +364,56 @@ __global__ void __launch_bounds__ (kFuThreads, 2) pu_fused (const __grid_constan
              pu_emit_from (a, e, S.draws[S.hi[e] - 1u] - S.draws[e], h);
           }
         __syncthreads ();
-        // inclusive prefix sum of the emit flags over the window
-        {
-           uint32_t v0 = ((i0 >= own_lo) && (i0 < own_hi)) ? S.emit[i0] : 0u, v1 = ((i1 >= own_lo) && (i1 < own_hi)) ? S.emit[i1] : 0u;
-           fu_scan2 (S, v0, v1, 0u, op_add);
-           S.cum[i0] = v0; S.cum[i1] = v1;
-        }
-        __syncthreads ();
-        // decoupled look-back over the tiles' row counts: warp 0 inspects 32 predecessors per round (a tile that is still at
-        // work has published nothing yet: 0), sums their aggregates down to the nearest published prefix
-        if (warp == 0)
-          {
-             const unsigned long long total = S.total;
-             unsigned long long excl = 0;
-             if (tile == 0) { if (lane == 0) st_relaxed (tile_state, kFuPrefix | total); }
-             else
-               {
-                  if (lane == 0) st_relaxed (tile_state + tile, kFuAggregate | total);
-                  long long p = (long long) tile - 1;
-                  while (true)
-                    {
-                       const long long idx = p - (long long) lane;
-                       const unsigned long long w = (idx >= 0) ? ld_relaxed (tile_state + idx) : kFuPrefix;      // before tile 0: prefix 0
-                       const unsigned long long st = w & ~kFuValueMask;
-                       const uint32_t unpublished = __ballot_sync (0xFFFFFFFFu, st == 0ull);
-                       const uint32_t prefixes = __ballot_sync (0xFFFFFFFFu, st == kFuPrefix);
-                       const int first = prefixes ? (__ffs (prefixes) - 1) : 31;                                  // nearest predecessor with a prefix
-                       const uint32_t needed = (first == 31) ? 0xFFFFFFFFu : ((2u << first) - 1u);
-                       if (unpublished & needed) continue;                                                         // look again
-                       unsigned long long v = ((int) lane <= first) ? (w & kFuValueMask) : 0ull;
-#pragma unroll
-                       for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync (0xFFFFFFFFu, v, d);
-                       excl += v;
-                       if (prefixes) break;
-                       p -= 32;
-                    }
-                  if (lane == 0) st_relaxed (tile_state + tile, kFuPrefix | (excl + total));
-               }
-             if (lane == 0)
-               {
-                  S.base = excl;
-                  if (tile + 1 == n_tiles) *g.n_out = excl + total;
-               }
-          }
-        __syncthreads ();
-        const unsigned long long base = S.base;
+        // hand the rows to the row-placement kernels (pu_scan_tiles, pu_scan_totals, pu_step<5>): every owned event's emit flag and, for
+        // the emitted ones, the staged row at the event's own slot of the per-event scratch -- frame bounds as GLOBAL indices.  (An
+        // ordered decoupled look-back inside this kernel made every tile wait for the slowest tile in flight: the tiles of a wave
+        // finished together, and a third of the kernel's time -- later, with the whole CTA looking back, 45 % of its instructions --
+        // went into that wait.  The placement needs one 4-byte flag per event and ~30 bytes per row instead.)
         for (uint32_t e = own_lo + tid; e < own_hi; e += kFuThreads)
           {
-             if (S.emit[e] == 0) continue;
-             const uint32_t lo = S.lo[e], hi = S.hi[e];
-             const unsigned long long before = (lo == 0) ? 0ull : S.cum[lo - 1];
-             const unsigned long long pos = base + before + (S.cum[hi - 1] - S.cum[e]);
-             if (pos >= g.max_out) { atomicOr (g.error, kPuErrOverflow); continue; }
-             const uint32_t f = S.frame[e];
-             g.o_ccd[pos] = S.ccd[e]; g.o_x[pos] = S.sx[e]; g.o_y[pos] = S.sy[e];
-             g.o_frame[pos] = (int32_t) f; g.o_t[pos] = (float) ((int32_t) f * g.frame_time);
-             g.o_nphotons[pos] = (int16_t) S.in[e]; g.o_pha[pos] = S.spha[e]; g.o_benergy[pos] = S.ib[e];
-             for (int d = 0; d < 6; d++) if (g.dither[d] && g.o_dither[d]) g.o_dither[d][pos] = g.dither[d][t0 + e];
+             const uint64_t ge = t0 + e;
+             const uint32_t em = S.emit[e];
+             g.emit[ge] = em;
+             if (em == 0) continue;
+             g.lo[ge] = (uint32_t) (t0 + S.lo[e]); g.hi[ge] = (uint32_t) (t0 + S.hi[e]);
+             g.frame[ge] = S.frame[e]; g.in[ge] = S.in[e]; g.ib[ge] = S.ib[e];
+             g.sx[ge] = S.sx[e]; g.sy[ge] = S.sy[e]; g.spha[ge] = S.spha[e];
           }
      }
 }
 
-// scratch: [0] the ticket, [1 ..] one status word per tile (zeroed here)
-size_t pileup_fused_scratch_bytes (uint64_t n) { return (size_t) ((n + kFuTile - 1) / kFuTile + 2) * sizeof (unsigned long long); }
-void launch_pileup_fused (const PileupArgs &a, void *scratch, int num_sms, cudaStream_t s, int *n_launches)
+// scratch: the ticket counter (zeroed here)
+size_t pileup_fused_scratch_bytes (uint64_t) { return 2 * sizeof (unsigned long long); }
+template <int W>
+static void launch_pileup_fused_w (const PileupArgs &a, void *scratch, int num_sms, cudaStream_t s)
 {
-   *n_launches = 0;
-   if (a.n == 0) return;
    static int per_sm = 0;
    if (per_sm == 0)
      {
-        cudaFuncSetAttribute (pu_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof (FuSmem));
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, pu_fused, kFuThreads, sizeof (FuSmem));
+        cudaFuncSetAttribute (pu_fused<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof (FuSmem<W>));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, pu_fused<W>, W / 2, sizeof (FuSmem<W>));
         if (per_sm < 1) per_sm = 1;
      }
    cudaMemsetAsync (scratch, 0, pileup_fused_scratch_bytes (a.n), s);
-   const uint64_t tiles = (a.n + kFuTile - 1) / kFuTile;
+   const uint64_t tiles = (a.n + W / 2 - 1) / (W / 2);
    const unsigned int grid = (unsigned int) min (tiles, (uint64_t) num_sms * per_sm);
    unsigned long long *w = (unsigned long long *) scratch;
-   pu_fused<<<grid, kFuThreads, sizeof (FuSmem), s>>> (a, w, w + 1);
-   *n_launches = 1;
+   pu_fused<W><<<grid, W / 2, sizeof (FuSmem<W>), s>>> (a, w);
+}
+// window: 256 (frames of up to 129 events) or 1024 (up to 513)
+void launch_pileup_fused (const PileupArgs &a, void *scratch, int window, int num_sms, cudaStream_t s, int *n_launches)
+{
+   *n_launches = 0;
+   if (a.n == 0) return;
+   if (window <= 256) launch_pileup_fused_w<256> (a, scratch, num_sms, s);
+   else launch_pileup_fused_w<1024> (a, scratch, num_sms, s);
+   // row placement: prefix sum over the emit flags, then the rows go to their places in the reference's order
+   const unsigned int tiles = (unsigned int) ((a.n + kPuTile - 1) / kPuTile);
+   const unsigned int grid = min (tiles, (unsigned int) num_sms * 8u);
+   pu_scan_tiles<<<grid, kPuTile, 0, s>>> (a);
+   pu_scan_totals<<<1, 1024, 0, s>>> (a);
+   pu_step<5><<<grid, kPuTile, 0, s>>> (a);
+   *n_launches = 4;
 }
 
 // input columns of the pile-up model from the live event list in HBM: what marx_write_photons would have put into the column files
