@@ -125,6 +125,15 @@ struct MxComm
    int rank = 0, world = 1;
    // time-base exchange
    double *d_all_sums = nullptr; uint64_t all_sums_cap = 0;        // [world][ns_blk]
+   // time-base look-ahead: the pre-pass and the all-gather of the NEXT contiguous batch run on their own stream while this
+   // batch is traced, so that neither the collective's latency nor the wait for the slowest rank is on the critical path
+   cudaStream_t ahead_stream = nullptr;
+   cudaEvent_t ev_ahead = nullptr, ev_consumed = nullptr;
+   double *ahead_tile_sums = nullptr, *ahead_super_sums = nullptr, *ahead_all_sums = nullptr;
+   uint64_t ahead_capacity = 0;                                     // rays the look-ahead scratch was sized for
+   bool ahead_on = true, ahead_valid = false;
+   uint64_t ahead_first = 0, ahead_total = 0, ahead_epoch = 0;
+   uint64_t ahead_hits = 0, ahead_misses = 0;
    // event merge
    cudaStream_t merge_stream = nullptr;
    cudaEvent_t ev_packed = nullptr, ev_counts = nullptr, ev_pushed = nullptr, ev_t0 = nullptr, ev_tc = nullptr, ev_t1 = nullptr;
@@ -165,9 +174,14 @@ void mxb_comm_release (marxb200_ctx *c)
    MxComm *m = c->comm;
    if (m == nullptr) return;
    NcclApi *N = nccl_api ();
+   if (getenv ("MARXB200_VERBOSE"))
+     fprintf (stderr, "marxb200: rank %d time-base look-ahead: %llu batches found their sums exchanged ahead, %llu ran the pre-pass themselves\n",
+              m->rank, (unsigned long long) m->ahead_hits, (unsigned long long) m->ahead_misses);
    merge_release (c);
    if (m->merge_stream) cudaStreamDestroy (m->merge_stream);
-   for (cudaEvent_t e : {m->ev_packed, m->ev_counts, m->ev_pushed, m->ev_t0, m->ev_tc, m->ev_t1}) if (e) cudaEventDestroy (e);
+   if (m->ahead_stream) { cudaStreamSynchronize (m->ahead_stream); cudaStreamDestroy (m->ahead_stream); }
+   for (cudaEvent_t e : {m->ev_packed, m->ev_counts, m->ev_pushed, m->ev_t0, m->ev_tc, m->ev_t1, m->ev_ahead, m->ev_consumed}) if (e) cudaEventDestroy (e);
+   for (double *p : {m->ahead_tile_sums, m->ahead_super_sums, m->ahead_all_sums}) if (p) cudaFree (p);
    if (m->d_all_sums) cudaFree (m->d_all_sums);
    if (m->d_all_counts) cudaFree (m->d_all_counts);
    if (m->h_all_counts) cudaFreeHost (m->h_all_counts);
@@ -225,10 +239,14 @@ extern "C" int marxb200_comm_init (marxb200_ctx *c, const void *id, int rank, in
         INIT_OK (cudaEventCreateWithFlags (&m->ev_packed, cudaEventDisableTiming), "event");
         INIT_OK (cudaEventCreateWithFlags (&m->ev_counts, cudaEventDisableTiming), "event");
         INIT_OK (cudaEventCreateWithFlags (&m->ev_pushed, cudaEventDisableTiming), "event");
+        INIT_OK (cudaStreamCreateWithFlags (&m->ahead_stream, cudaStreamNonBlocking), "stream");
+        INIT_OK (cudaEventCreateWithFlags (&m->ev_ahead, cudaEventDisableTiming), "event");
+        INIT_OK (cudaEventCreateWithFlags (&m->ev_consumed, cudaEventDisableTiming), "event");
+        if (const char *e = getenv ("MARXB200_LOOKAHEAD")) m->ahead_on = (atoi (e) != 0);      // A/B switch
         INIT_OK (cudaEventCreate (&m->ev_t0), "event");
         INIT_OK (cudaEventCreate (&m->ev_tc), "event");
         INIT_OK (cudaEventCreate (&m->ev_t1), "event");
-        INIT_OK (cudaMalloc (&m->d_all_counts, 64 * sizeof (unsigned long long)), "cudaMalloc");
+        INIT_OK (cudaMalloc (&m->d_all_counts, 65 * sizeof (unsigned long long)), "cudaMalloc");      // [world] + this rank's own snapshot
         INIT_OK (cudaMallocHost (&m->h_all_counts, 64 * sizeof (unsigned long long)), "cudaMallocHost");
         INIT_OK (cudaMalloc (&m->d_flag, 64 * sizeof (int)), "cudaMalloc");
         INIT_OK (cudaMemset (m->d_flag, 0, 64 * sizeof (int)), "cudaMemset");
@@ -304,6 +322,44 @@ extern "C" int marxb200_shard_of (uint64_t first_ray, uint64_t n_total, int rank
    return 0;
 }
 
+// The pre-pass of the batch a run asks for next -- rays [first_ray, first_ray + n_total) right behind the one just launched -- and the
+// all-gather of its sums, on the look-ahead stream.  The sums depend on the seed, the source and the ray indices only; a call that
+// asks for something else (or follows a marxb200_set_source) finds no match and runs the pre-pass itself.
+static int look_ahead (marxb200_ctx *c, NcclApi *N, uint64_t first_ray, uint64_t n_total, uint32_t ns_blk)
+{
+   MxComm *m = c->comm;
+   if (!m->ahead_on || c->profiling || (first_ray + n_total < first_ray)) return 0;
+   const uint64_t super = (uint64_t) kTile * kSuperTile;
+   if (m->ahead_capacity != c->capacity)
+     {
+        CUDA_OK (cudaStreamSynchronize (m->ahead_stream));
+        CUDA_OK (cudaStreamSynchronize (c->stream));
+        for (double **p : {&m->ahead_tile_sums, &m->ahead_super_sums, &m->ahead_all_sums}) { if (*p) cudaFree (*p); *p = nullptr; }
+        m->ahead_capacity = 0;
+        const uint64_t n_super = (c->capacity + super - 1) / super + 2;
+        CUDA_OK (cudaMalloc (&m->ahead_tile_sums, n_super * kSuperTile * sizeof (double)));
+        CUDA_OK (cudaMalloc (&m->ahead_super_sums, n_super * sizeof (double)));
+        CUDA_OK (cudaMalloc (&m->ahead_all_sums, n_super * m->world * sizeof (double)));
+        m->ahead_capacity = c->capacity;
+     }
+   uint64_t first = 0, n = 0;
+   marxb200_shard_of (first_ray, n_total, m->rank, m->world, &first, &n);
+   SourceArgs b;
+   mxb_fill_source_args (c, b, first, n, 0.0);
+   b.tile_sums = m->ahead_tile_sums; b.supertile_sums = m->ahead_super_sums;
+   // the scratch is free once the bases of the current batch have been formed from it
+   CUDA_OK (cudaStreamWaitEvent (m->ahead_stream, m->ev_consumed, 0));
+   CUDA_OK (cudaMemsetAsync (m->ahead_super_sums, 0, (size_t) ns_blk * sizeof (double), m->ahead_stream));
+   launch_time_sums (b, m->ahead_stream);
+   launch_time_super (b, m->ahead_stream);
+   NCCL_OK (N->AllGather (m->ahead_super_sums, m->ahead_all_sums, ns_blk, NCCL_FLOAT64, m->comm, m->ahead_stream));
+   c->launches += (n != 0) ? 2 : 0;
+   CUDA_OK (cudaGetLastError ());
+   CUDA_OK (cudaEventRecord (m->ev_ahead, m->ahead_stream));
+   m->ahead_valid = true; m->ahead_first = first_ray; m->ahead_total = n_total; m->ahead_epoch = c->source_epoch;
+   return 0;
+}
+
 extern "C" int marxb200_trace_sharded (marxb200_ctx *c, uint64_t first_ray, uint64_t n_total, double time_base_in,
                                        uint64_t *my_first_ray, uint64_t *my_n)
 {
@@ -344,19 +400,40 @@ extern "C" int marxb200_trace_sharded (marxb200_ctx *c, uint64_t first_ray, uint
         CUDA_OK (cudaMalloc (&m->d_all_sums, cap * m->world * sizeof (double)));
         m->all_sums_cap = cap * m->world;
      }
+   // Was this batch's pre-pass already run (and its sums exchanged) behind the previous call?  Every rank sees the same arguments,
+   // hence takes the same branch.  Either way the context's stream waits for the look-ahead: it used the same communicator.
+   if (-1 == mxb_begin_batch (c)) return -1;
+   const bool hit = m->ahead_valid && (m->ahead_first == first_ray) && (m->ahead_total == n_total) && (m->ahead_epoch == c->source_epoch);
+   if (m->ahead_valid) CUDA_OK (cudaStreamWaitEvent (c->stream, m->ev_ahead, 0));
+   m->ahead_valid = false;
    SourceArgs a;
    mxb_fill_source_args (c, a, first, n, time_base_in);
-   // the scratch holds capacity / 65536 + 2 sums, ns_blk <= capacity / 65536 + 1: zero the padding of a short block
-   CUDA_OK (cudaMemsetAsync (c->d_super_sums, 0, (size_t) ns_blk * sizeof (double), c->stream));
    mxb_prof_begin (c);
-   launch_time_sums (a, c->stream); mxb_prof_mark (c, 0);
-   launch_time_super (a, c->stream);
-   NCCL_OK (N->AllGather (c->d_super_sums, m->d_all_sums, ns_blk, NCCL_FLOAT64, m->comm, c->stream));
-   launch_time_bases_sharded (a, m->d_all_sums, m->rank, m->world, ns_blk, c->stream); mxb_prof_mark (c, 1);
-   c->launches += (n != 0) ? 4 : 1;
+   if (hit)
+     {
+        m->ahead_hits++;
+        SourceArgs b = a;
+        b.tile_sums = m->ahead_tile_sums;
+        mxb_prof_mark (c, 0);
+        launch_time_bases_sharded (b, m->ahead_all_sums, m->rank, m->world, ns_blk, c->stream); mxb_prof_mark (c, 1);
+        c->launches += (n != 0) ? 2 : 1;
+     }
+   else
+     {
+        m->ahead_misses++;
+        // the scratch holds capacity / 65536 + 2 sums, ns_blk <= capacity / 65536 + 1: zero the padding of a short block
+        CUDA_OK (cudaMemsetAsync (c->d_super_sums, 0, (size_t) ns_blk * sizeof (double), c->stream));
+        launch_time_sums (a, c->stream); mxb_prof_mark (c, 0);
+        launch_time_super (a, c->stream);
+        NCCL_OK (N->AllGather (c->d_super_sums, m->d_all_sums, ns_blk, NCCL_FLOAT64, m->comm, c->stream));
+        launch_time_bases_sharded (a, m->d_all_sums, m->rank, m->world, ns_blk, c->stream); mxb_prof_mark (c, 1);
+        c->launches += (n != 0) ? 4 : 1;
+     }
    CUDA_OK (cudaGetLastError ());
+   CUDA_OK (cudaEventRecord (m->ev_consumed, c->stream));
    if (-1 == mxb_enter_mirror_after_scan (c, a)) return -1;
    if (-1 == mxb_finish_trace (c)) return -1;
+   if ((first_ray + n_total > first_ray) && (-1 == look_ahead (c, N, first_ray + n_total, n_total, ns_blk))) return -1;
    if (my_first_ray) *my_first_ray = first;
    if (my_n) *my_n = n;
    return 0;
@@ -375,6 +452,7 @@ extern "C" int marxb200_tally_allreduce (marxb200_ctx *c, int id)
    if ((id < 0) || (id >= (int) c->tallies.size ())) return fail ("unknown tally id %d", id);
    CUDA_OK (cudaSetDevice (c->device));
    marxb200_ctx::Tally &t = c->tallies[id];
+   if (m->ahead_valid) CUDA_OK (cudaStreamWaitEvent (c->stream, m->ev_ahead, 0));      // the look-ahead's all-gather uses the same communicator
    NCCL_OK (N->AllReduce (t.bins, t.bins, (size_t) t.total, NCCL_UINT64, NCCL_SUM, m->comm, c->stream));
    return 0;
 }
@@ -470,10 +548,12 @@ extern "C" int marxb200_merge_events_begin (marxb200_ctx *c, uint64_t write_mask
    launch_egress_pack (mxb_observed (c, c->buf[c->cur]), c->d_counts + c->stage_done, m->max_rows, m->plan, m->stage, nullptr, total_time, c->stream);
    c->launches += 1;
    CUDA_OK (cudaGetLastError ());
+   // the count is snapshot in stream order: the next batch clears the context's counters while the merge stream still works
+   CUDA_OK (cudaMemcpyAsync (m->d_all_counts + 64, c->d_counts + c->stage_done, sizeof (unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
    CUDA_OK (cudaEventRecord (m->ev_packed, c->stream));
    // counts of all ranks, on the merge stream (the context's stream goes on with the next batch)
    CUDA_OK (cudaStreamWaitEvent (m->merge_stream, m->ev_packed, 0));
-   NCCL_OK (N->AllGather (c->d_counts + c->stage_done, m->d_all_counts, 1, NCCL_UINT64, m->comm_merge, m->merge_stream));
+   NCCL_OK (N->AllGather (m->d_all_counts + 64, m->d_all_counts, 1, NCCL_UINT64, m->comm_merge, m->merge_stream));
    CUDA_OK (cudaMemcpyAsync (m->h_all_counts, m->d_all_counts, m->world * sizeof (unsigned long long), cudaMemcpyDeviceToHost, m->merge_stream));
    CUDA_OK (cudaEventRecord (m->ev_counts, m->merge_stream));
    m->pending = true;

@@ -166,10 +166,14 @@ extern "C" int marxb200_create (marxb200_ctx **ctxp, int device_ordinal, uint64_
    c->num_sms = prop.multiProcessorCount;
    CUDA_OK (cudaStreamCreateWithFlags (&c->stream, cudaStreamNonBlocking));
    c->own_stream = true;
-   CUDA_OK (cudaMalloc (&c->d_counts, 12 * sizeof (unsigned long long)));
-   CUDA_OK (cudaMalloc (&c->d_ticket, 4 * sizeof (unsigned long long)));
+   CUDA_OK (cudaMalloc (&c->d_counts, (marxb200_ctx::kNumCounts + marxb200_ctx::kNumTickets) * sizeof (unsigned long long)));
+   c->d_ticket = c->d_counts + marxb200_ctx::kNumCounts;
+   CUDA_OK (cudaStreamCreateWithFlags (&c->ahead_stream, cudaStreamNonBlocking));
+   CUDA_OK (cudaEventCreateWithFlags (&c->ev_ahead, cudaEventDisableTiming));
+   CUDA_OK (cudaEventCreateWithFlags (&c->ev_ahead_consumed, cudaEventDisableTiming));
+   if (const char *e = getenv ("MARXB200_LOOKAHEAD")) c->ahead_on = (atoi (e) != 0);          // developer A/B switch
    CUDA_OK (cudaMalloc (&c->d_times, 2 * sizeof (double)));
-   CUDA_OK (cudaMemset (c->d_counts, 0, 12 * sizeof (unsigned long long)));
+   CUDA_OK (cudaMemset (c->d_counts, 0, (marxb200_ctx::kNumCounts + marxb200_ctx::kNumTickets) * sizeof (unsigned long long)));
    CUDA_OK (cudaMemset (c->d_times, 0, 2 * sizeof (double)));
    memset (&c->S, 0, sizeof (c->S));
    memset (&c->D, 0, sizeof (c->D));
@@ -183,6 +187,9 @@ extern "C" int marxb200_destroy (marxb200_ctx *c)
    if (c == nullptr) return -1;
    cudaSetDevice (c->device);
    cudaDeviceSynchronize ();
+   if (getenv ("MARXB200_VERBOSE") && (c->ahead_hits + c->ahead_misses > 0))
+     fprintf (stderr, "marxb200: time pre-pass look-ahead: %llu batches found their sums ready, %llu ran the pre-pass themselves\n",
+              (unsigned long long) c->ahead_hits, (unsigned long long) c->ahead_misses);
    if (c->writer) { mxw_destroy (c->writer); c->writer = nullptr; }       // waits for the queued column writes
    for (int i = 0; i < 2; i++) if (c->h_wbuf[i]) cudaFreeHost (c->h_wbuf[i]);
    mxb_comm_release (c);
@@ -192,7 +199,12 @@ extern "C" int marxb200_destroy (marxb200_ctx *c)
    if (c->d_upload_ids) cudaFree (c->d_upload_ids);
    for (int i = 0; i < 2; i++) if (c->slab[i]) cudaFree (c->slab[i]);
    if (c->rc_slab) cudaFree (c->rc_slab);
-   cudaFree (c->d_counts); cudaFree (c->d_ticket); cudaFree (c->d_times);
+   cudaFree (c->d_counts); cudaFree (c->d_times);
+   if (c->ahead_stream) { cudaStreamSynchronize (c->ahead_stream); cudaStreamDestroy (c->ahead_stream); }
+   if (c->ev_ahead) cudaEventDestroy (c->ev_ahead);
+   if (c->ev_ahead_consumed) cudaEventDestroy (c->ev_ahead_consumed);
+   if (c->ahead_tile_sums) cudaFree (c->ahead_tile_sums);
+   if (c->ahead_super_sums) cudaFree (c->ahead_super_sums);
    if (c->d_bitmap) cudaFree (c->d_bitmap);
    if (c->d_word_prefix) cudaFree (c->d_word_prefix);
    if (c->d_block_prefix) cudaFree (c->d_block_prefix);
@@ -249,6 +261,8 @@ extern "C" int marxb200_set_source (marxb200_ctx *c, const marxb200_source_desc 
    if ((d->source_type < 0) || (d->source_type > 5)) return fail ("marxb200_set_source: source type %d is not implemented (POINT, GAUSS, BETA, DISK, LINE, IMAGE are)", d->source_type);
    if ((d->spectrum_type != 1) && (d->spectrum_type != 2)) return fail ("marxb200_set_source: unknown spectrum type %d", d->spectrum_type);
    CUDA_OK (cudaSetDevice (c->device));
+   if (c->comm != nullptr) CUDA_OK (cudaDeviceSynchronize ());       // a look-ahead pre-pass (comm.cu) may still read the old tables
+   c->source_epoch++;
    begin_module (c, marxb200_ctx::TAG_SOURCE);
    SourceDev &S = c->S;
    memset (&S, 0, sizeof (S));
@@ -453,6 +467,10 @@ extern "C" int marxb200_alloc_photons (marxb200_ctx *c, uint64_t max_photons)
    if (max_photons == 0) return fail ("marxb200_alloc_photons: max_photons must be > 0");
    CUDA_OK (cudaSetDevice (c->device));
    CUDA_OK (cudaStreamSynchronize (c->stream));
+   if (c->ahead_stream) CUDA_OK (cudaStreamSynchronize (c->ahead_stream));
+   c->ahead_valid = false;
+   if (c->ahead_tile_sums) { cudaFree (c->ahead_tile_sums); c->ahead_tile_sums = nullptr; }
+   if (c->ahead_super_sums) { cudaFree (c->ahead_super_sums); c->ahead_super_sums = nullptr; }
    for (int i = 0; i < 2; i++) if (c->slab[i]) { cudaFree (c->slab[i]); c->slab[i] = nullptr; }
    if (c->d_bitmap) cudaFree (c->d_bitmap);
    if (c->d_word_prefix) cudaFree (c->d_word_prefix);
@@ -490,6 +508,8 @@ extern "C" int marxb200_alloc_photons (marxb200_ctx *c, uint64_t max_photons)
    CUDA_OK (cudaMalloc (&c->d_tile_sums, n_tiles * sizeof (double)));
    CUDA_OK (cudaMalloc (&c->d_tile_base, n_tiles * sizeof (double)));
    CUDA_OK (cudaMalloc (&c->d_super_sums, n_super * sizeof (double)));
+   CUDA_OK (cudaMalloc (&c->ahead_tile_sums, n_tiles * sizeof (double)));
+   CUDA_OK (cudaMalloc (&c->ahead_super_sums, n_super * sizeof (double)));
    CUDA_OK (cudaStreamSynchronize (c->stream));
    c->capacity = max_photons;
    c->cur = 0; c->stage_done = -1; c->n_generated = 0; c->ordered = true;
@@ -622,16 +642,20 @@ static int run_stage (marxb200_ctx *c, int stage)
    const bool k2_two = (stage == 2) && c->compact && (c->k2_split != 0);
    const int n_kernels = (stage == 1) ? (k1_four ? 4 : 3) : ((k3_two || k2_two) ? 2 : 1);
    const int k_first = (stage == 1) ? c->first_mirror_kernel : 0;
-   CUDA_OK (cudaMemsetAsync (c->d_ticket, 0, 4 * sizeof (unsigned long long), c->stream));
-   if (c->compact)
+   unsigned long long *const tickets = c->d_ticket + 4 * (stage - 1);
+   if (!c->batch_zeroed)
      {
-        // output counters grow by atomics: zero them (d_counts[4], [5], [7] = after the first, second, third mirror kernel;
-        // [6] = between the ACIS kernels; d_counts[stage] = stage output)
-        CUDA_OK (cudaMemsetAsync (c->d_counts + stage, 0, sizeof (unsigned long long), c->stream));
-        if (stage == 1) CUDA_OK (cudaMemsetAsync (c->d_counts + 4 + k_first, 0, (2 - k_first) * sizeof (unsigned long long), c->stream));
-        if (k1_four) CUDA_OK (cudaMemsetAsync (c->d_counts + 7, 0, sizeof (unsigned long long), c->stream));
-        if (k3_two) CUDA_OK (cudaMemsetAsync (c->d_counts + 6, 0, sizeof (unsigned long long), c->stream));
-        if (k2_two) CUDA_OK (cudaMemsetAsync (c->d_counts + 8, 0, sizeof (unsigned long long), c->stream));
+        CUDA_OK (cudaMemsetAsync (tickets, 0, 4 * sizeof (unsigned long long), c->stream));
+        if (c->compact)
+          {
+             // output counters grow by atomics: zero them (d_counts[4], [5], [7] = after the first, second, third mirror kernel;
+             // [6] = between the ACIS kernels; d_counts[stage] = stage output)
+             CUDA_OK (cudaMemsetAsync (c->d_counts + stage, 0, sizeof (unsigned long long), c->stream));
+             if (stage == 1) CUDA_OK (cudaMemsetAsync (c->d_counts + 4 + k_first, 0, (2 - k_first) * sizeof (unsigned long long), c->stream));
+             if (k1_four) CUDA_OK (cudaMemsetAsync (c->d_counts + 7, 0, sizeof (unsigned long long), c->stream));
+             if (k3_two) CUDA_OK (cudaMemsetAsync (c->d_counts + 6, 0, sizeof (unsigned long long), c->stream));
+             if (k2_two) CUDA_OK (cudaMemsetAsync (c->d_counts + 8, 0, sizeof (unsigned long long), c->stream));
+          }
      }
    const unsigned long long *n_in = (k_first == 1) ? c->d_counts + 4 : c->d_counts + c->stage_done;
    c->first_mirror_kernel = 0;
@@ -640,7 +664,7 @@ static int run_stage (marxb200_ctx *c, int stage)
         // MirrorType=FLATFIELD: the whole stage is one kernel (ffield.c:77-108)
         a.in = c->buf[c->cur];
         a.out = c->compact ? c->buf[1 - c->cur] : c->buf[c->cur];
-        a.n_in = c->d_counts + c->stage_done; a.n_out = c->d_counts + 1; a.ticket = c->d_ticket; a.chunk_tiles = 4;
+        a.n_in = c->d_counts + c->stage_done; a.n_out = c->d_counts + 1; a.ticket = tickets; a.chunk_tiles = 4;
         for (int k = 0; k < 5; k++) a.ff[k] = c->ff[k];
         prof_begin (c);
         launch_flatfield (a, c->num_sms, c->stream);
@@ -658,7 +682,7 @@ static int run_stage (marxb200_ctx *c, int stage)
         a.n_in = n_in;
         a.n_out = (k == n_kernels - 1) ? c->d_counts + stage
                   : ((stage == 1) ? c->d_counts + ((k == 2) ? 7 : 4 + k) : ((stage == 2) ? c->d_counts + 8 : c->d_counts + 6));
-        a.ticket = c->d_ticket + k;
+        a.ticket = tickets + k;
         // big inputs amortise the ticket atomic over several tiles; small ones need fine-grained balancing
         a.chunk_tiles = (stage == 1 && k == 0) ? 4 : ((stage == 1 && k < n_kernels - 1) ? 2 : 1);
         prof_begin (c);
@@ -772,11 +796,49 @@ static int create_and_enter_mirror (marxb200_ctx *c, uint64_t first_ray, uint64_
    CUDA_OK (cudaSetDevice (c->device));
    SourceArgs a;
    fill_source_args (c, a, first_ray, n, time_base_in);
+   // the pre-pass of this batch may have run behind the previous one (look_ahead below)
+   const bool hit = c->ahead_valid && (c->ahead_first == first_ray) && (c->ahead_n == n) && (c->ahead_epoch == c->source_epoch);
+   if (c->ahead_valid) CUDA_OK (cudaStreamWaitEvent (c->stream, c->ev_ahead, 0));
+   c->ahead_valid = false;
    prof_begin (c);
-   launch_time_sums (a, c->stream); prof_mark (c, 0);
-   launch_time_scan (a, c->stream); prof_mark (c, 1);    // also sets d_counts[0] = n
-   c->launches += 4;                     // k0_time_sums, k0_time_super/_bases/_tiles
+   if (hit)
+     {
+        c->ahead_hits++;
+        a.tile_sums = c->ahead_tile_sums; a.supertile_sums = c->ahead_super_sums;
+        prof_mark (c, 0);
+        launch_time_scan (a, c->stream, false); prof_mark (c, 1);       // k0_time_bases/_tiles; also sets d_counts[0] = n
+        c->launches += 2;
+     }
+   else
+     {
+        c->ahead_misses++;
+        launch_time_sums (a, c->stream); prof_mark (c, 0);
+        launch_time_scan (a, c->stream); prof_mark (c, 1);    // also sets d_counts[0] = n
+        c->launches += 4;                     // k0_time_sums, k0_time_super/_bases/_tiles
+     }
+   CUDA_OK (cudaEventRecord (c->ev_ahead_consumed, c->stream));
+   a.tile_sums = c->d_tile_sums; a.supertile_sums = c->d_super_sums;
    return enter_mirror_after_scan (c, a);
+}
+
+// The arrival-time pre-pass (k0_time_sums + k0_time_super: every ray's time increment drawn and summed per tile) of the batch a
+// run asks for next -- the n rays right behind this one -- on the look-ahead stream: it fills the idle SM slots at the kernel
+// boundaries of the batch being traced instead of standing in front of the next one.  The sums depend on the seed, the source
+// and the ray indices only; a call for other rays, or after marxb200_set_source, finds no match and runs the pre-pass itself.
+static int look_ahead (marxb200_ctx *c, uint64_t first_ray, uint64_t n)
+{
+   if (!c->ahead_on || c->profiling || (n == 0) || (first_ray + n < first_ray) || (c->ahead_tile_sums == nullptr)) return 0;
+   SourceArgs b;
+   fill_source_args (c, b, first_ray, n, 0.0);
+   b.tile_sums = c->ahead_tile_sums; b.supertile_sums = c->ahead_super_sums;
+   CUDA_OK (cudaStreamWaitEvent (c->ahead_stream, c->ev_ahead_consumed, 0));      // the scratch is free once this batch's bases exist
+   launch_time_sums (b, c->ahead_stream);
+   launch_time_super (b, c->ahead_stream);
+   c->launches += 2;
+   CUDA_OK (cudaGetLastError ());
+   CUDA_OK (cudaEventRecord (c->ev_ahead, c->ahead_stream));
+   c->ahead_valid = true; c->ahead_first = first_ray; c->ahead_n = n; c->ahead_epoch = c->source_epoch;
+   return 0;
 }
 
 // k01_source_hrma behind a finished arrival-time scan (tile bases, batch start and count on the device)
@@ -789,7 +851,7 @@ static int enter_mirror_after_scan (marxb200_ctx *c, const SourceArgs &a)
    st.n_out = c->d_counts + 4;
    st.seed = c->seed; st.compact = 1; st.source_distance = c->source_distance;
    st.blob = c->blob1; st.blob_bytes = c->blob1_bytes;
-   CUDA_OK (cudaMemsetAsync (c->d_counts + 4, 0, sizeof (unsigned long long), c->stream));
+   if (!c->batch_zeroed) CUDA_OK (cudaMemsetAsync (c->d_counts + 4, 0, sizeof (unsigned long long), c->stream));
    prof_begin (c);
    launch_source_hrma (a, st, c->grid01, c->stream); prof_mark (c, 3);
    c->launches += (n != 0) ? 1 : 0;      // k01_source_hrma
@@ -827,15 +889,29 @@ extern "C" int marxb200_trace_from (marxb200_ctx *c, uint64_t first_ray, uint64_
    if (c == nullptr) return fail ("NULL ctx");
    // the fused source + HRMA-A kernel serves the compacting path of the NONE / INTERNAL dither models; the ASPSOL model
    // (end-of-file cut, detector dither columns) and lists that follow an upload carrying detector dither go stage by stage
-   if (c->compact && (c->D.mode != 2) && !c->det_dither_dirty && !c->mirror_is_flat)
-     {
-        if (-1 == create_and_enter_mirror (c, first_ray, n, time_base_in)) return -1;
-     }
-   else if (-1 == marxb200_create_photons (c, first_ray, n, time_base_in)) return -1;
-   if (-1 == marxb200_mirror_reflect (c)) return -1;
-   if (-1 == marxb200_grating_diffract (c)) return -1;
-   if (-1 == marxb200_detect (c)) return -1;
-   return ensure_order (c);
+   const bool fused = c->compact && (c->D.mode != 2) && !c->det_dither_dirty && !c->mirror_is_flat;
+   CUDA_OK (cudaSetDevice (c->device));
+   if (c->compact && (-1 == mxb_begin_batch (c))) return -1;
+   int status = 0;
+   if (fused) status = create_and_enter_mirror (c, first_ray, n, time_base_in);
+   else status = marxb200_create_photons (c, first_ray, n, time_base_in);
+   if (status == 0) status = marxb200_mirror_reflect (c);
+   if (status == 0) status = marxb200_grating_diffract (c);
+   if (status == 0) status = marxb200_detect (c);
+   c->batch_zeroed = false;
+   if (status != 0) return -1;
+   if (-1 == ensure_order (c)) return -1;
+   if (fused && (first_ray + n > first_ray)) return look_ahead (c, first_ray + n, n);
+   return 0;
+}
+
+// One clear for everything a traced batch counts with atomics: counts[1..] and every kernel's ticket.  counts[0] (rays generated)
+// is written by the time scan; nothing between here and the end of the batch reads a count of the previous batch.
+int mxb_begin_batch (marxb200_ctx *c)
+{
+   CUDA_OK (cudaMemsetAsync (c->d_counts + 1, 0, (marxb200_ctx::kNumCounts - 1 + marxb200_ctx::kNumTickets) * sizeof (unsigned long long), c->stream));
+   c->batch_zeroed = true;
+   return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1803,9 +1879,11 @@ void mxb_fill_source_args (marxb200_ctx *c, SourceArgs &a, uint64_t first_ray, u
 int mxb_enter_mirror_after_scan (marxb200_ctx *c, const SourceArgs &a) { return enter_mirror_after_scan (c, a); }
 int mxb_finish_trace (marxb200_ctx *c)
 {
-   if (-1 == marxb200_mirror_reflect (c)) return -1;
-   if (-1 == marxb200_grating_diffract (c)) return -1;
-   if (-1 == marxb200_detect (c)) return -1;
+   int status = marxb200_mirror_reflect (c);
+   if (status == 0) status = marxb200_grating_diffract (c);
+   if (status == 0) status = marxb200_detect (c);
+   c->batch_zeroed = false;
+   if (status != 0) return -1;
    return ensure_order (c);
 }
 // every selected column in a fixed region of align16 (rows_per_col * size) bytes; returns the total size

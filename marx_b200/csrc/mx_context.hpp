@@ -32,8 +32,18 @@ struct marxb200_ctx
    int cur = 0;
 
    // device scalars: counts[0..3] + ticket + total_time
-   unsigned long long *d_counts = nullptr;      // [8]: generated, after mirror, after grating, detected, after k1a, after k1b
-   unsigned long long *d_ticket = nullptr;      // [4]: one ticket counter per kernel of a stage call
+   // one allocation: counts[12] (generated, after mirror, after grating, detected, after k1a, after k1b, ...) followed by
+   // ticket[12] (stage s, kernel k of its call: slot 4 (s - 1) + k), so that a traced batch clears counts[1..] and all tickets at once
+   unsigned long long *d_counts = nullptr;
+   unsigned long long *d_ticket = nullptr;      // = d_counts + kNumCounts
+   static constexpr int kNumCounts = 12, kNumTickets = 12;
+   bool batch_zeroed = false;                   // inside marxb200_trace(_sharded): the stage calls skip their own clears
+   // time pre-pass of the NEXT contiguous batch, run on its own stream while this one is traced (marxb200_trace)
+   cudaStream_t ahead_stream = nullptr;
+   cudaEvent_t ev_ahead = nullptr, ev_ahead_consumed = nullptr;
+   double *ahead_tile_sums = nullptr, *ahead_super_sums = nullptr;
+   bool ahead_on = true, ahead_valid = false;
+   uint64_t ahead_first = 0, ahead_n = 0, ahead_epoch = 0, ahead_hits = 0, ahead_misses = 0;
    uint32_t *d_bitmap = nullptr, *d_word_prefix = nullptr, *d_block_prefix = nullptr, *d_perm = nullptr;   // order restoration scratch
    uint64_t n_words = 0;
    bool ordered = true;                          // live list is in arrival order
@@ -93,6 +103,7 @@ struct marxb200_ctx
 
    // optional per-kernel timing
    bool profiling = false;
+   uint64_t source_epoch = 0;                 // bumped by marxb200_set_source: invalidates work done ahead for the old source
    cudaEvent_t ev_prev = nullptr;
    std::vector<std::pair<cudaEvent_t, int>> ev_marks;   // (event recorded after a kernel, class)
    std::vector<cudaEvent_t> ev_pool;
@@ -123,6 +134,7 @@ void mxb_fill_source_args (marxb200_ctx *c, mx::SourceArgs &a, uint64_t first_ra
 // the fused source + HRMA phase A entry behind an already computed time scan; then the remaining stages of one batch
 int mxb_enter_mirror_after_scan (marxb200_ctx *c, const mx::SourceArgs &a);
 int mxb_finish_trace (marxb200_ctx *c);
+int mxb_begin_batch (marxb200_ctx *c);          // clears the batch's counters and tickets with one memset
 // the column files of marx_write_photons selected by write_mask, each in a fixed region of rows_per_col rows
 struct MxEgressCol { uint64_t mask; const char *file, *colname; char type; int kind; int size; };
 extern const MxEgressCol kMxEgressCols[];

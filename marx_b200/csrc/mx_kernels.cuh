@@ -129,7 +129,7 @@ struct SourceArgs
 };
 
 void launch_time_sums (const SourceArgs &a, cudaStream_t s);
-void launch_time_scan (const SourceArgs &a, cudaStream_t s);
+void launch_time_scan (const SourceArgs &a, cudaStream_t s, bool with_super = true);   // false: the super-tile sums exist already
 void launch_time_super (const SourceArgs &a, cudaStream_t s);                 // multi-GPU scan, first half: k0_time_super
 // second half, behind the all-gather of the super-tile sums: k0_time_bases_sharded + k0_time_tiles
 void launch_time_bases_sharded (const SourceArgs &a, const double *all_sums, int rank, int world, uint32_t ns_blk, cudaStream_t s);

@@ -4,8 +4,9 @@
 G ranks trace the blocks of a few collective steps with marxb200_trace_sharded (time bases all-gathered on the device), the
 event lists are merged on rank 0 with marxb200_merge_events_begin / _end (interleaved with the next step's trace, as bench.py
 does), tallies are summed with marxb200_tally_allreduce, and rank 0 compares everything with ONE GPU tracing the same rays
-step by step: identical events, identical order, identical times.  Steps: two full ones, one with a short last block, one so
-small that the upper ranks get empty blocks."""
+step by step: identical events, identical order, identical times.  Steps: three full ones, one with a short last block, two so
+small that the upper ranks get empty blocks -- which also walks the time-base look-ahead of marxb200_trace_sharded through
+its hits and misses."""
 import os
 import sys
 
@@ -28,7 +29,7 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("gloo")                # only carries the id and the final barrier: the data path is the library's NCCL
     n = 1 << 20                                    # rays per rank and full step
-    steps = [n * world, n * world, n * world - 12345, 70000]
+    steps = [n * world, n * world, n * world, n * world - 12345, 70000, 70000]      # look-ahead: miss, hit, hit, miss, miss, hit
     cap = n // 4
     with marx_b200.MarxB200("c2_hetg_acis_s", device=local, seed=77, max_photons=n) as m:
         if os.environ.get("MGC_INIT", "bcast") == "file":
