@@ -541,18 +541,20 @@ extern "C" int marxb200_merge_events_begin (marxb200_ctx *c, uint64_t write_mask
    if ((m->stage == nullptr) || (m->mask != write_mask) || (m->max_rows != max_rows_per_rank) || (m->dst != dst_rank))
      if (-1 == merge_setup (c, write_mask, max_rows_per_rank, dst_rank)) return -1;
    if (-1 == mxb_ensure_order (c)) return -1;
-   // the staging area may still be read by the previous merge's transfers
-   CUDA_OK (cudaStreamWaitEvent (c->stream, m->ev_pushed, 0));
+   // The count is snapshot in stream order (the next batch clears the context's counters); the conversion to file images then runs on
+   // the MERGE stream -- behind the previous merge's transfers, which read the same staging area -- while the context's stream goes
+   // straight on with the next batch (its first kernel that writes into the list buffer being read waits, mxb_guard_buffer).
    // TIME of the merged list = (float) (absolute arrival time + total_time): in a sharded run the list's times already count
    // from the start of the simulation on every rank
-   launch_egress_pack (mxb_observed (c, c->buf[c->cur]), c->d_counts + c->stage_done, m->max_rows, m->plan, m->stage, nullptr, total_time, c->stream);
+   CUDA_OK (cudaStreamWaitEvent (c->stream, m->ev_packed, 0));         // the previous conversion has consumed the last snapshot
+   CUDA_OK (cudaMemcpyAsync (m->d_all_counts + 64, c->d_counts + c->stage_done, sizeof (unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
+   if (-1 == mxb_reader_begin (c, 1, m->merge_stream)) return -1;
+   launch_egress_pack (mxb_observed (c, c->buf[c->cur]), m->d_all_counts + 64, m->max_rows, m->plan, m->stage, nullptr, total_time, m->merge_stream);
    c->launches += 1;
    CUDA_OK (cudaGetLastError ());
-   // the count is snapshot in stream order: the next batch clears the context's counters while the merge stream still works
-   CUDA_OK (cudaMemcpyAsync (m->d_all_counts + 64, c->d_counts + c->stage_done, sizeof (unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
-   CUDA_OK (cudaEventRecord (m->ev_packed, c->stream));
+   CUDA_OK (cudaEventRecord (m->ev_packed, m->merge_stream));
+   if (-1 == mxb_reader_end (c, 1, m->merge_stream)) return -1;
    // counts of all ranks, on the merge stream (the context's stream goes on with the next batch)
-   CUDA_OK (cudaStreamWaitEvent (m->merge_stream, m->ev_packed, 0));
    NCCL_OK (N->AllGather (m->d_all_counts + 64, m->d_all_counts, 1, NCCL_UINT64, m->comm_merge, m->merge_stream));
    CUDA_OK (cudaMemcpyAsync (m->h_all_counts, m->d_all_counts, m->world * sizeof (unsigned long long), cudaMemcpyDeviceToHost, m->merge_stream));
    CUDA_OK (cudaEventRecord (m->ev_counts, m->merge_stream));

@@ -871,9 +871,26 @@ __global__ void __launch_bounds__ (kTile, MX_K01_MINBLOCKS) k01_source_hrma (con
    Vec3 rolled = v_make (0, 0, 0);
    if (const_roll) rolled = dither_roll ((double) (float) a.D.nominal_roll, v_make (a.S.p[0], a.S.p[1], a.S.p[2]));
 
+   // Tiles are handed out by a ticket counter (st.ticket, or a static stride when it is null): a CTA that becomes resident late --
+   // an NCCL kernel of the merge stream held its slot, or another stream's kernel did -- finds the work gone instead of running a
+   // full 1/grid share after everybody else has finished.  The next ticket is drawn before the tile is traced, so that the
+   // atomic's round trip is not on the tile's critical path.
+   __shared__ unsigned long long s_tile;
    const uint64_t n_tiles = (a.n + kTile - 1) / kTile;
-   for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+   unsigned long long next_tile = blockIdx.x;
+   if ((st.ticket != nullptr) && (threadIdx.x == 0)) next_tile = atomicAdd (st.ticket, 1ull);
+   for (;;)
      {
+        uint64_t tile = next_tile;
+        if (st.ticket != nullptr)
+          {
+             if (threadIdx.x == 0) s_tile = next_tile;
+             __syncthreads ();              // the scan's barriers separate this read from the next round's write
+             tile = s_tile;
+          }
+        if (tile >= n_tiles) break;
+        if (st.ticket == nullptr) next_tile = tile + gridDim.x;
+        else if (threadIdx.x == 0) next_tile = atomicAdd (st.ticket, 1ull);
         const uint64_t i = tile * kTile + threadIdx.x;
         const bool valid = i < a.n;
         Rng rng; double energy = 0.0, dt = 0.0; Vec3 p = v_make (0, 0, 0);

@@ -144,6 +144,7 @@ static int ensure_aos (marxb200_ctx *c, uint64_t n)
 extern "C" int marxb200_abi_version (void) { return MARXB200_ABI_VERSION; }
 extern "C" const char *marxb200_last_error (void) { return g_err; }
 
+#define GUARD(idx) do { if (-1 == mxb_guard_buffer (c, (idx))) return -1; } while (0)
 extern "C" int marxb200_create (marxb200_ctx **ctxp, int device_ordinal, uint64_t seed)
 {
    if (ctxp == nullptr) return fail ("marxb200_create: NULL ctxp");
@@ -159,6 +160,7 @@ extern "C" int marxb200_create (marxb200_ctx **ctxp, int device_ordinal, uint64_
    c->device = device_ordinal;
    c->seed = seed;
    if (const char *e = getenv ("MARXB200_K3_SPLIT")) c->k3_split = atoi (e);      // developer A/B switch
+   if (const char *e = getenv ("MARXB200_K01_TICKET")) c->k01_ticket = atoi (e);  // developer A/B switch
    if (const char *e = getenv ("MARXB200_K1_SPLIT")) c->k1_split = atoi (e);      // developer A/B switch
    if (const char *e = getenv ("MARXB200_K2_SPLIT")) c->k2_split = atoi (e);      // developer A/B switch
    cudaDeviceProp prop;
@@ -171,6 +173,12 @@ extern "C" int marxb200_create (marxb200_ctx **ctxp, int device_ordinal, uint64_
    CUDA_OK (cudaStreamCreateWithFlags (&c->ahead_stream, cudaStreamNonBlocking));
    CUDA_OK (cudaEventCreateWithFlags (&c->ev_ahead, cudaEventDisableTiming));
    CUDA_OK (cudaEventCreateWithFlags (&c->ev_ahead_consumed, cudaEventDisableTiming));
+   for (int k = 0; k < 2; k++)
+     {
+        CUDA_OK (cudaEventCreateWithFlags (&c->ev_reader_go[k], cudaEventDisableTiming));
+        CUDA_OK (cudaEventCreateWithFlags (&c->ev_reader_done[k], cudaEventDisableTiming));
+     }
+   CUDA_OK (cudaMalloc (&c->d_snap, 2 * sizeof (unsigned long long)));
    if (const char *e = getenv ("MARXB200_LOOKAHEAD")) c->ahead_on = (atoi (e) != 0);          // developer A/B switch
    CUDA_OK (cudaMalloc (&c->d_times, 2 * sizeof (double)));
    CUDA_OK (cudaMemset (c->d_counts, 0, (marxb200_ctx::kNumCounts + marxb200_ctx::kNumTickets) * sizeof (unsigned long long)));
@@ -203,6 +211,8 @@ extern "C" int marxb200_destroy (marxb200_ctx *c)
    if (c->ahead_stream) { cudaStreamSynchronize (c->ahead_stream); cudaStreamDestroy (c->ahead_stream); }
    if (c->ev_ahead) cudaEventDestroy (c->ev_ahead);
    if (c->ev_ahead_consumed) cudaEventDestroy (c->ev_ahead_consumed);
+   for (int k = 0; k < 2; k++) { if (c->ev_reader_go[k]) cudaEventDestroy (c->ev_reader_go[k]); if (c->ev_reader_done[k]) cudaEventDestroy (c->ev_reader_done[k]); }
+   if (c->d_snap) cudaFree (c->d_snap);
    if (c->ahead_tile_sums) cudaFree (c->ahead_tile_sums);
    if (c->ahead_super_sums) cudaFree (c->ahead_super_sums);
    if (c->d_bitmap) cudaFree (c->d_bitmap);
@@ -229,6 +239,7 @@ extern "C" int marxb200_destroy (marxb200_ctx *c)
 extern "C" int marxb200_set_stream (marxb200_ctx *c, void *cuda_stream)
 {
    if (c == nullptr) return fail ("NULL ctx");
+   GUARD (-1);
    CUDA_OK (cudaStreamSynchronize (c->stream));
    if (cuda_stream == nullptr)
      {
@@ -468,6 +479,8 @@ extern "C" int marxb200_alloc_photons (marxb200_ctx *c, uint64_t max_photons)
    CUDA_OK (cudaSetDevice (c->device));
    CUDA_OK (cudaStreamSynchronize (c->stream));
    if (c->ahead_stream) CUDA_OK (cudaStreamSynchronize (c->ahead_stream));
+   GUARD (-1);
+   CUDA_OK (cudaStreamSynchronize (c->stream));
    c->ahead_valid = false;
    if (c->ahead_tile_sums) { cudaFree (c->ahead_tile_sums); c->ahead_tile_sums = nullptr; }
    if (c->ahead_super_sums) { cudaFree (c->ahead_super_sums); c->ahead_super_sums = nullptr; }
@@ -519,6 +532,32 @@ extern "C" int marxb200_alloc_photons (marxb200_ctx *c, uint64_t max_photons)
 // ---------------------------------------------------------------------------------------------
 // stages
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// off-stream readers of the finished list (mx_context.hpp)
+// ---------------------------------------------------------------------------------------------
+int mxb_guard_buffer (marxb200_ctx *c, int idx)
+{
+   for (int k = 0; k < 2; k++)
+     if ((c->reader_buf[k] >= 0) && ((idx < 0) || (c->reader_buf[k] == idx)))
+       {
+          CUDA_OK (cudaStreamWaitEvent (c->stream, c->ev_reader_done[k], 0));
+          c->reader_buf[k] = -1;
+       }
+   return 0;
+}
+int mxb_reader_begin (marxb200_ctx *c, int slot, cudaStream_t reader)
+{
+   CUDA_OK (cudaEventRecord (c->ev_reader_go[slot], c->stream));
+   CUDA_OK (cudaStreamWaitEvent (reader, c->ev_reader_go[slot], 0));
+   return 0;
+}
+int mxb_reader_end (marxb200_ctx *c, int slot, cudaStream_t reader)
+{
+   CUDA_OK (cudaEventRecord (c->ev_reader_done[slot], reader));
+   c->reader_buf[slot] = c->cur;
+   return 0;
+}
+
 static void fill_source_args (marxb200_ctx *c, SourceArgs &a, uint64_t first_ray, uint64_t n, double time_base)
 {
    a.out = c->buf[0];
@@ -547,6 +586,7 @@ extern "C" int marxb200_create_photons (marxb200_ctx *c, uint64_t first_ray, uin
         const size_t c4 = (4 * (size_t) c->capacity + 255) & ~(size_t) 255;
         CUDA_OK (cudaMemsetAsync (c->rc.ddy, 0, 3 * c4, c->stream));
      }
+   GUARD (0);
    prof_begin (c);
    launch_time_sums (a, c->stream); prof_mark (c, 0);
    launch_time_scan (a, c->stream); prof_mark (c, 1);
@@ -664,6 +704,7 @@ static int run_stage (marxb200_ctx *c, int stage)
         // MirrorType=FLATFIELD: the whole stage is one kernel (ffield.c:77-108)
         a.in = c->buf[c->cur];
         a.out = c->compact ? c->buf[1 - c->cur] : c->buf[c->cur];
+        GUARD (c->compact ? 1 - c->cur : c->cur);
         a.n_in = c->d_counts + c->stage_done; a.n_out = c->d_counts + 1; a.ticket = tickets; a.chunk_tiles = 4;
         for (int k = 0; k < 5; k++) a.ff[k] = c->ff[k];
         prof_begin (c);
@@ -679,6 +720,7 @@ static int run_stage (marxb200_ctx *c, int stage)
      {
         a.in = c->buf[c->cur];
         a.out = c->compact ? c->buf[1 - c->cur] : c->buf[c->cur];
+        GUARD (c->compact ? 1 - c->cur : c->cur);
         a.n_in = n_in;
         a.n_out = (k == n_kernels - 1) ? c->d_counts + stage
                   : ((stage == 1) ? c->d_counts + ((k == 2) ? 7 : 4 + k) : ((stage == 2) ? c->d_counts + 8 : c->d_counts + 6));
@@ -726,6 +768,7 @@ static int ensure_order (marxb200_ctx *c)
    if (c->ordered || (c->stage_done <= 0)) { c->ordered = true; return 0; }
    OrderArgs o;
    o.in = c->buf[c->cur]; o.out = observed (c, c->buf[1 - c->cur]); o.rc = c->rc;
+   GUARD (1 - c->cur);
    o.n_live = c->d_counts + c->stage_done;
    o.n_slots = c->n_generated;
    o.bitmap = c->d_bitmap; o.word_prefix = c->d_word_prefix; o.block_prefix = c->d_block_prefix; o.perm = c->d_perm;
@@ -849,9 +892,12 @@ static int enter_mirror_after_scan (marxb200_ctx *c, const SourceArgs &a)
    memset (&st, 0, sizeof (st));
    st.out = c->buf[1];
    st.n_out = c->d_counts + 4;
+   // slot 0 of the mirror stage's tickets: the stage call that follows starts at its kernel 1.  MARXB200_K01_TICKET=0: static stride
+   st.ticket = (c->batch_zeroed && c->k01_ticket) ? c->d_ticket : nullptr;
    st.seed = c->seed; st.compact = 1; st.source_distance = c->source_distance;
    st.blob = c->blob1; st.blob_bytes = c->blob1_bytes;
    if (!c->batch_zeroed) CUDA_OK (cudaMemsetAsync (c->d_counts + 4, 0, sizeof (unsigned long long), c->stream));
+   GUARD (1);
    prof_begin (c);
    launch_source_hrma (a, st, c->grid01, c->stream); prof_mark (c, 3);
    c->launches += (n != 0) ? 1 : 0;      // k01_source_hrma
@@ -1012,6 +1058,7 @@ extern "C" int marxb200_upload_from (marxb200_ctx *c, const marxb200_photon_attr
    c->cur = 0;
    // the list keeps absolute times (pt->start_time + arrival_time); d_times[0] = the batch start the AoS download subtracts
    CUDA_OK (cudaMemcpyAsync (c->d_times, &start_time, sizeof (double), cudaMemcpyHostToDevice, c->stream));
+   GUARD (0);
    launch_aos_to_soa (c->d_aos, d_ids, n, c->buf[0], c->rc, start_time, c->stream);
    c->launches += 1;
    unsigned long long nn = n;
@@ -1421,11 +1468,18 @@ extern "C" int marxb200_egress_begin_packed (marxb200_ctx *c, uint64_t write_mas
         plan.num_cols++;
         total += (uint64_t) align16 ((size_t) max_out * kEgressCols[k].size);
      }
-   CUDA_OK (cudaStreamWaitEvent (c->stream, c->ev_copied, 0));      // the slab may still be read by the previous copy
-   launch_egress_pack (observed (c, c->buf[c->cur]), c->d_counts + c->stage_done, max_out, plan, c->egress_slab, c->d_times, total_time, c->stream);
+   // The conversion runs on the COPY stream (behind the previous batch's copies, which read the same slab), so that the context's
+   // stream goes straight on with the next batch; what the kernel needs from the device scalars -- the event count, the batch
+   // start -- is snapshot in stream order first, because the next batch rewrites both.
+   CUDA_OK (cudaStreamWaitEvent (c->stream, c->ev_staged, 0));      // the previous conversion has consumed the last snapshot
+   CUDA_OK (cudaMemcpyAsync (c->d_snap, c->d_counts + c->stage_done, sizeof (unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
+   CUDA_OK (cudaMemcpyAsync (c->d_snap + 1, c->d_times, sizeof (double), cudaMemcpyDeviceToDevice, c->stream));
+   if (-1 == mxb_reader_begin (c, 0, c->copy_stream)) return -1;
+   launch_egress_pack (observed (c, c->buf[c->cur]), c->d_snap, max_out, plan, c->egress_slab, (const double *) (c->d_snap + 1), total_time, c->copy_stream);
    c->launches += 1;
-   CUDA_OK (cudaMemcpyAsync (c->h_egress_count, c->d_counts + c->stage_done, sizeof (unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-   CUDA_OK (cudaEventRecord (c->ev_staged, c->stream));
+   CUDA_OK (cudaMemcpyAsync (c->h_egress_count, c->d_snap, sizeof (unsigned long long), cudaMemcpyDeviceToHost, c->copy_stream));
+   CUDA_OK (cudaEventRecord (c->ev_staged, c->copy_stream));
+   if (-1 == mxb_reader_end (c, 0, c->copy_stream)) return -1;
    CUDA_OK (cudaGetLastError ());
    c->packed_cap = max_out;
    c->egress_pending = true; c->egress_is_packed = true;

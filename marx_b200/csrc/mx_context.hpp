@@ -37,6 +37,13 @@ struct marxb200_ctx
    unsigned long long *d_counts = nullptr;
    unsigned long long *d_ticket = nullptr;      // = d_counts + kNumCounts
    static constexpr int kNumCounts = 12, kNumTickets = 12;
+   int k01_ticket = 1;
+   // Readers of the finished list on OTHER streams (slot 0: the packed egress on the copy stream, slot 1: the multi-GPU merge on
+   // the merge stream): they convert the list to file images while the next batch starts.  reader_buf = the list buffer being
+   // read (-1: none); the first kernel of the context's stream that writes into that buffer waits for ev_reader_done.
+   cudaEvent_t ev_reader_go[2] = {nullptr, nullptr}, ev_reader_done[2] = {nullptr, nullptr};
+   int reader_buf[2] = {-1, -1};
+   unsigned long long *d_snap = nullptr;        // [0] event count, [1] batch start time (f64 bits): what the egress pack reads, snapshot in stream order
    bool batch_zeroed = false;                   // inside marxb200_trace(_sharded): the stage calls skip their own clears
    // time pre-pass of the NEXT contiguous batch, run on its own stream while this one is traced (marxb200_trace)
    cudaStream_t ahead_stream = nullptr;
@@ -134,7 +141,10 @@ void mxb_fill_source_args (marxb200_ctx *c, mx::SourceArgs &a, uint64_t first_ra
 // the fused source + HRMA phase A entry behind an already computed time scan; then the remaining stages of one batch
 int mxb_enter_mirror_after_scan (marxb200_ctx *c, const mx::SourceArgs &a);
 int mxb_finish_trace (marxb200_ctx *c);
-int mxb_begin_batch (marxb200_ctx *c);          // clears the batch's counters and tickets with one memset
+int mxb_begin_batch (marxb200_ctx *c);
+int mxb_guard_buffer (marxb200_ctx *c, int idx);   // before a kernel of the context's stream writes list buffer idx (-1: any)
+int mxb_reader_begin (marxb200_ctx *c, int slot, cudaStream_t reader);   // reader waits for the list; call mxb_reader_end after its launches
+int mxb_reader_end (marxb200_ctx *c, int slot, cudaStream_t reader);          // clears the batch's counters and tickets with one memset
 // the column files of marx_write_photons selected by write_mask, each in a fixed region of rows_per_col rows
 struct MxEgressCol { uint64_t mask; const char *file, *colname; char type; int kind; int size; };
 extern const MxEgressCol kMxEgressCols[];
