@@ -137,6 +137,35 @@ __device__ __forceinline__ void k0_draw (const SourceArgs &a, uint64_t i, Rng &r
    dt = source_time_increment (a.S, rng);
 }
 
+// the same scan, carrying one 64-bit word from thread 0 to every thread across its first barrier (k01's next tile index)
+__device__ __forceinline__ double tile_inclusive_scan_bcast (double v, double &total, unsigned long long &word)
+{
+   __shared__ double warp_tot[kTile / 32];
+   __shared__ unsigned long long bcast;
+   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+   for (int o = 1; o < 32; o <<= 1)
+     {
+        double u = __shfl_up_sync (0xffffffffu, v, o);
+        if (lane >= (uint32_t) o) v += u;
+     }
+   if (lane == 31) warp_tot[warp] = v;
+   if (threadIdx.x == 0) bcast = word;
+   __syncthreads ();
+   double off = 0.0, tot = 0.0;
+#pragma unroll
+   for (int w = 0; w < kTile / 32; w++)
+     {
+        double c = warp_tot[w];
+        if (w < (int) warp) off += c;
+        tot += c;
+     }
+   word = bcast;
+   __syncthreads ();
+   total = tot;
+   return off + v;
+}
+
 // pass 1: per-tile sums of the arrival-time increments
 __global__ void __launch_bounds__ (kTile) k0_time_sums (const __grid_constant__ SourceArgs a)
 {
@@ -877,26 +906,37 @@ __global__ void __launch_bounds__ (kTile, MX_K01_MINBLOCKS) k01_source_hrma (con
    // atomic's round trip is not on the tile's critical path.
    __shared__ unsigned long long s_tile;
    const uint64_t n_tiles = (a.n + kTile - 1) / kTile;
-   unsigned long long next_tile = blockIdx.x;
-   if ((st.ticket != nullptr) && (threadIdx.x == 0)) next_tile = atomicAdd (st.ticket, 1ull);
-   for (;;)
+   const bool dynamic = (st.ticket != nullptr);
+   // tile: what every thread traces now; upcoming: the tile after it -- known to thread 0 only until the scan's first barrier
+   // hands it to everybody (no barrier of its own)
+   unsigned long long tile = blockIdx.x, upcoming = 0;
+   if (dynamic)
      {
-        uint64_t tile = next_tile;
-        if (st.ticket != nullptr)
-          {
-             if (threadIdx.x == 0) s_tile = next_tile;
-             __syncthreads ();              // the scan's barriers separate this read from the next round's write
-             tile = s_tile;
-          }
-        if (tile >= n_tiles) break;
-        if (st.ticket == nullptr) next_tile = tile + gridDim.x;
-        else if (threadIdx.x == 0) next_tile = atomicAdd (st.ticket, 1ull);
+        if (threadIdx.x == 0) s_tile = atomicAdd (st.ticket, 1ull);
+        __syncthreads ();
+        tile = s_tile;
+        if (threadIdx.x == 0) upcoming = atomicAdd (st.ticket, 1ull);
+     }
+   while (tile < n_tiles)
+     {
         const uint64_t i = tile * kTile + threadIdx.x;
         const bool valid = i < a.n;
         Rng rng; double energy = 0.0, dt = 0.0; Vec3 p = v_make (0, 0, 0);
         if (valid) k0_draw (a, i, rng, energy, p, dt);
         double total;
-        const double t = tile_inclusive_scan (dt, total) + a.tile_base[tile];
+        double t;
+        unsigned long long after = 0;
+        if (dynamic)
+          {
+             t = tile_inclusive_scan_bcast (dt, total, upcoming) + a.tile_base[tile];
+             if (threadIdx.x == 0) after = atomicAdd (st.ticket, 1ull);      // consumed one whole tile from now
+          }
+        else
+          {
+             t = tile_inclusive_scan (dt, total) + a.tile_base[tile];
+             upcoming = tile + gridDim.x;
+          }
+        tile = upcoming; upcoming = after;
         bool alive = false;
         Vec3 x = v_make (0, 0, 0); uint32_t shell = 0; float dra = 0.f, ddec = 0.f, droll = 0.f;
         if (valid)

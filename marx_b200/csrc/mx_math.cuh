@@ -9,7 +9,7 @@
 // instructions per sincos; arguments below 2^-10 (the aspect-dither angles: 16 arcsec = 8e-5 rad) need three terms.
 //
 // Accuracy (tools/math_accuracy.c: the same algorithms in plain C against 80-bit sinl / cosl / logl on 4e6 random arguments per range): sin and cos <= 1.5 ulp
-// for |x| <= 1e5, <= 0.5 ulp below 2^-10; log <= 1 ulp on (0, 1].  libdevice documents 2 ulp (sin, cos) and 1 ulp (log); the
+// for |x| <= 1e9, <= 0.5 ulp below 2^-10; log <= 1 ulp on (0, 1].  libdevice documents 2 ulp (sin, cos) and 1 ulp (log); the
 // reference's glibc is at 0.52 ulp.  Replay parity is judged at 1e-9 relative, integer outputs bit-exact: the differences
 // are of the size the libdevice-vs-glibc differences already were.  Arguments outside the fast range, NaN and Inf take the
 // libdevice function.  -DMX_MATH=0 restores libdevice everywhere (A/B builds, tools/build_variant.sh).
@@ -44,7 +44,7 @@ static __constant__ double kLog[10] = {
    1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01,
    6.93147180369123816490e-01, 1.90821492927058770002e-10, 0.0};
 
-// quadrant k = rint (x * 2/pi), remainder r = x - k pi/2 in [-pi/4, pi/4]; valid for |x| <= 1e5
+// quadrant k = rint (x * 2/pi), remainder r = x - k pi/2 in [-pi/4, pi/4]; valid for |x| <= 1e9 (the quotient fits an int; tools/math_accuracy.c: <= 1.5 ulp up to there)
 __device__ __forceinline__ double trig_reduce (double x, int &k)
 {
    const double q = rint (x * kTrig[15]);
@@ -76,7 +76,7 @@ static __device__ __noinline__ double log_far (double x) { return log (x); }
 MXM_HD void mx_sincos (double x, double &s, double &c)
 {
 #if defined(__CUDA_ARCH__) && (MX_MATH >= 1)
-   if (fabs (x) <= 1.0e5)
+   if (fabs (x) <= 1.0e9)
      {
         int k;
         const double r = trig_reduce (x, k), z = r * r;
@@ -114,7 +114,7 @@ MXM_HD void mx_sincos_pair (double x, double y, double &sx, double &cx, double &
 MXM_HD double mx_sin (double x)
 {
 #if defined(__CUDA_ARCH__) && (MX_MATH >= 1)
-   if (fabs (x) <= 1.0e5)
+   if (fabs (x) <= 1.0e9)
      {
         int k;
         const double r = trig_reduce (x, k), z = r * r;

@@ -86,10 +86,10 @@ static double ulp_err (double got, long double want)
 int main (int argc, char **argv)
 {
    long n = (argc > 1) ? atol (argv[1]) : 4000000;
-   double ranges[] = {0.8, 7.0, 700.0, 1e5};
+   double ranges[] = {0.8, 7.0, 700.0, 1e5, 1e7, 1e9};
    double worst = 0.0;
    srand48 (1);
-   for (int r = 0; r < 4; r++)
+   for (int r = 0; r < 6; r++)
      {
         double ms = 0, mc = 0;
         for (long i = 0; i < n; i++)
