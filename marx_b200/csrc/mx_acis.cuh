@@ -212,7 +212,13 @@ MX_HD int fef_normalize (const FefRows &R, float *cum, uint32_t stride, uint32_t
         if ((sigma != 0.0) && (g.amp != 0.0f))
           {
              double x0 = g.center;
-             double e0 = acis_erf ((0 - x0) / sigma);
+             // erf is exactly -1 / +1 in double beyond |z| = 5.93 (erfc (6) = 2e-17 < 2^-54): the peaks of a response function
+             // sit tens of widths above zero, so almost every component skips the polynomial
+             const double zarg = (0 - x0) / sigma;
+             double e0;
+             if (zarg <= -6.0) e0 = -1.0;
+             else if (zarg >= 6.0) e0 = 1.0;
+             else e0 = acis_erf (zarg);
              area1 = 0.5 * g.amp * (1.0 - e0) * (SQRT_2PI * g.sigma);
              area2 = 0.5 * g.amp * (e0 - (-1.0)) * (SQRT_2PI * g.sigma);
           }

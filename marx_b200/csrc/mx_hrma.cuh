@@ -18,33 +18,29 @@ namespace mx {
 struct Cplx { double r, i; };
 // JDMc_mul / JDMc_div / JDMc_abs / JDMc_sqrt, jdmath/src/complex.c:38-227
 MX_HD Cplx c_mul (Cplx a, Cplx b) { Cplx z; z.r = a.r * b.r - a.i * b.i; z.i = a.r * b.i + a.i * b.r; return z; }
+// The reference branches on |r2| > |i2| and the lanes of a warp split about evenly: both bodies, three FP64 divisions each, ran one
+// after the other.  The two bodies are the same expressions with the roles of the real and imaginary parts exchanged (a + b == b + a
+// and a * b == b * a hold bit for bit), so one copy with selected operands returns identical bits.
 MX_HD Cplx c_div (Cplx z1, Cplx z2)
 {
    Cplx z;
-   double r1 = z1.r, i1 = z1.i, r2 = z2.r, i2 = z2.i, ratio, denom;
-   if (fabs (r2) > fabs (i2))
-     {
-        ratio = i2 / r2;
-        denom = r2 + i2 * ratio;
-        z.r = (r1 + ratio * i1) / denom;
-        z.i = (i1 - r1 * ratio) / denom;
-     }
-   else
-     {
-        ratio = r2 / i2;
-        denom = r2 * ratio + i2;
-        z.r = (r1 * ratio + i1) / denom;
-        z.i = (i1 * ratio - r1) / denom;
-     }
+   const bool big = fabs (z2.r) > fabs (z2.i);
+   const double a = big ? z2.r : z2.i, b = big ? z2.i : z2.r;       // divisor parts: the larger, the smaller
+   const double u = big ? z1.r : z1.i, v = big ? z1.i : z1.r;
+   const double ratio = b / a;
+   const double denom = a + b * ratio;            // r2 + i2 * ratio | r2 * ratio + i2
+   const double w = u * ratio;
+   z.r = (u + ratio * v) / denom;                 // (r1 + ratio * i1) | (r1 * ratio + i1)
+   z.i = (big ? (v - w) : (w - v)) / denom;       // (i1 - r1 * ratio) | (i1 * ratio - r1)
    return z;
 }
 MX_HD double c_abs (Cplx z)
 {
-   double fr = fabs (z.r), fi = fabs (z.i), ratio;
-   if (fr > fi) { ratio = z.i / z.r; return fr * sqrt (1.0 + ratio * ratio); }
-   if (fi == 0.0) return 0.0;
-   ratio = z.r / z.i;
-   return fi * sqrt (1.0 + ratio * ratio);
+   const double fr = fabs (z.r), fi = fabs (z.i);
+   const bool big = fr > fi;
+   if (!big && (fi == 0.0)) return 0.0;
+   const double ratio = (big ? z.i : z.r) / (big ? z.r : z.i);
+   return (big ? fr : fi) * sqrt (1.0 + ratio * ratio);
 }
 MX_HD Cplx c_sqrt (Cplx a)
 {
