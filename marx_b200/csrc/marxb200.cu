@@ -1842,11 +1842,13 @@ static int pileup_impl (marxb200_ctx *c, uint64_t n, const marxb200_pileup_in *i
                if (e_ != cudaSuccess) { status = fail ("marxb200_pileup_run: upload: %s", cudaGetErrorString (e_)); copied = false; break; }
             }
         if (!copied) break;
-        // the fused kernel (window of 1024 events: frames of up to 513), then the step kernels.  (A 256-event window -- eight small
-        // CTAs per SM -- measured slower: four times the tiles, and the look-back over the tiles' row counts grows with the tiles in flight)
+        // the fused kernel with a window of 256, 512 or 1024 events (frames of up to 129 / 257 / 513 events: a longer one raises the
+        // fallback flag and the next size runs), then the step kernels.  MARXB200_PILEUP_WINDOW picks the first size tried.
         int nl = 0;
-        const int attempts[3] = {256, 1024, 0};
-        for (int k = fused ? 1 : 2; k < 3; k++)
+        const int attempts[4] = {256, 512, 1024, 0};
+        int k_first = 2;
+        if (const char *e = getenv ("MARXB200_PILEUP_WINDOW")) { const int w = atoi (e); k_first = (w <= 256) ? 0 : ((w <= 512) ? 1 : 2); }
+        for (int k = fused ? k_first : 3; k < 4; k++)
           {
              PU_OK (cudaMemsetAsync (p, 0, 16, c->stream));
              PU_OK (cudaEventRecord (e0, c->stream));

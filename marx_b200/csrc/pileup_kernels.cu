@@ -146,8 +146,18 @@ __device__ __forceinline__ void fu_scan2 (FuSmem<W> &S, uint32_t &v0, uint32_t &
    __syncthreads ();                        // the previous user of warp_sum is done
    if (lane == 31u) S.warp_sum[warp] = s;
    __syncthreads ();
-   uint32_t before = identity;
-   for (uint32_t k = 0; k < warp; k++) before = op (before, S.warp_sum[k]);
+   // every warp scans the warp totals itself, with shuffles (a loop over S.warp_sum[0 .. warp) was a chain of dependent
+   // shared-memory loads, longest for the last warp: 9 % of the kernel's stall samples)
+   constexpr uint32_t kWarps = (uint32_t) FuSmem<W>::kFuThreads / 32u;
+   uint32_t ws = (lane < kWarps) ? S.warp_sum[lane] : identity;
+#pragma unroll
+   for (uint32_t d = 1; d < kWarps; d <<= 1)
+     {
+        const uint32_t o = __shfl_up_sync (0xFFFFFFFFu, ws, d);
+        if (lane >= d) ws = op (o, ws);
+     }
+   uint32_t before = __shfl_sync (0xFFFFFFFFu, ws, (warp + 31u) & 31u);
+   if (warp == 0u) before = identity;
    const uint32_t excl = op (before, __shfl_up_sync (0xFFFFFFFFu, s, 1));
    const uint32_t left = (lane == 0u) ? before : excl;          // everything before this thread's pair
    v0 = op (left, v0);
@@ -155,17 +165,23 @@ __device__ __forceinline__ void fu_scan2 (FuSmem<W> &S, uint32_t &v0, uint32_t &
    if (tid == (uint32_t) FuSmem<W>::kFuThreads - 1u) S.total = v1;
 }
 
+// key = 1024 y + x: the pixels above and below differ by 1024, and a product with an odd constant keeps the low 10 bits of such
+// keys EQUAL -- taking the slot from the low bits of one product put every column of an event cluster into two slots and made the
+// probe chains as long as the cluster is tall (ncu: 26 % of the kernel's instructions in the probe loop at 3 active lanes).  Both
+// hashes therefore fold the high half into the low one between two multiplications.
+__device__ __forceinline__ uint32_t fu_mix (uint32_t h)
+{
+   h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+   return h;
+}
 template <int W> __device__ __forceinline__ uint32_t fu_hash (uint32_t key, uint32_t frame_id)
 {
-   return ((key * 2654435761u) ^ (frame_id * 0x9E3779B1u) ^ (key >> 13)) & (uint32_t) (FuSmem<W>::kFuHash - 1);
+   return fu_mix (key * 0x9E3779B1u + frame_id) & (uint32_t) (FuSmem<W>::kFuHash - 1);
 }
-// the table slot of pixel (frame_id, key), or kFuHash if the pixel is empty
 // second, independent hash into the occupancy bitmap (8 * kFuHash bits)
 template <int W> __device__ __forceinline__ uint32_t fu_hash2 (uint32_t key, uint32_t frame_id)
 {
-   uint32_t h = key * 0x85EBCA6Bu + frame_id * 0xC2B2AE35u;
-   h ^= h >> 15;
-   return h & (uint32_t) (8 * FuSmem<W>::kFuHash - 1);
+   return fu_mix (key + frame_id * 0xC2B2AE35u + 0x27D4EB2Fu) & (uint32_t) (8 * FuSmem<W>::kFuHash - 1);
 }
 // the table slot of pixel (frame_id, key), or kFuHash if the pixel is empty
 template <int W> __device__ __forceinline__ uint32_t fu_find (const FuSmem<W> &S, uint32_t key, uint32_t frame_id)
@@ -208,7 +224,7 @@ template <int W> __device__ __forceinline__ void fu_hood (const FuSmem<W> &S, ui
 }
 
 template <int W>
-__global__ void __launch_bounds__ (W / 2, (W <= 256) ? 8 : 2) pu_fused (const __grid_constant__ PileupArgs g, unsigned long long *ticket)
+__global__ void __launch_bounds__ (W / 2, (W <= 256) ? 8 : ((W <= 512) ? 4 : 2)) pu_fused (const __grid_constant__ PileupArgs g, unsigned long long *ticket)
 {
    constexpr int kFuCap = FuSmem<W>::kFuCap, kFuTile = FuSmem<W>::kFuTile, kFuThreads = FuSmem<W>::kFuThreads, kFuHash = FuSmem<W>::kFuHash;
    extern __shared__ __align__ (16) unsigned char fu_raw[];
@@ -400,12 +416,13 @@ static void launch_pileup_fused_w (const PileupArgs &a, void *scratch, int num_s
    unsigned long long *w = (unsigned long long *) scratch;
    pu_fused<W><<<grid, W / 2, sizeof (FuSmem<W>), s>>> (a, w);
 }
-// window: 256 (frames of up to 129 events) or 1024 (up to 513)
+// window: 256 (frames of up to 129 events), 512 (up to 257) or 1024 (up to 513)
 void launch_pileup_fused (const PileupArgs &a, void *scratch, int window, int num_sms, cudaStream_t s, int *n_launches)
 {
    *n_launches = 0;
    if (a.n == 0) return;
    if (window <= 256) launch_pileup_fused_w<256> (a, scratch, num_sms, s);
+   else if (window <= 512) launch_pileup_fused_w<512> (a, scratch, num_sms, s);
    else launch_pileup_fused_w<1024> (a, scratch, num_sms, s);
    // row placement: prefix sum over the emit flags, then the rows go to their places in the reference's order
    const unsigned int tiles = (unsigned int) ((a.n + kPuTile - 1) / kPuTile);
