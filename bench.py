@@ -167,9 +167,9 @@ def pileup_reference_baseline(cols, alpha, ft, n_ref):
         shutil.rmtree(d, ignore_errors=True)
 
 
-def driver_leg(args, n_rays=1 << 30, dn=1 << 24, ref_rays=2000000):
+def driver_leg(args, n_rays=127 << 24, dn=1 << 24, ref_rays=2000000):
     """What a MARX user gets: the UNMODIFIED reference driver on the CUDA path (integration/_build/marx_gpu = marx/src/marx.c linked
-    against libmarxb200.so with -Wl,--wrap) run as `marx`, 2^30 rays of C2 in batches of 2^24 (dNumRays: the reference's maximum of
+    against libmarxb200.so with -Wl,--wrap) run as `marx`, 127 x 2^24 rays of C2 in batches of 2^24 (dNumRays: the reference's maximum of
     10^6 is only the range field of marx/par/marx.par:9, raised in integration/_build/par/marx.par), event files written to tmpfs by
     the background writer; wall clock of the whole process, CUDA start-up and calibration-file reading included.  Beside it the stock
     CPU `marx` (oracle/_ref/marx) on a bounded sample with the same arguments."""
@@ -180,6 +180,10 @@ def driver_leg(args, n_rays=1 << 30, dn=1 << 24, ref_rays=2000000):
     if not (os.path.exists(marx_gpu) and os.path.exists(par)):
         return {"unavailable": "integration/_build/marx_gpu not built"}
     env = dict(os.environ, MARX_DATA_DIR=data, USER=os.environ.get("USER", "marx"), MARXB200_TIMING="1")
+    # 127 batches (just under the int NumRays of marx.c:86-87) write 11 GB of event files: fall back to 2^30 / 2^28 rays on a small tmpfs
+    free = shutil.disk_usage(os.path.dirname(scratch_dir("probe"))).free
+    if free < (24 << 30):
+        n_rays = (1 << 30) if free >= (12 << 30) else (1 << 28)
     common = [a for a in REF_ARGS if not a.startswith("dNumRays")]
     d = scratch_dir("drv")
     out = {}
@@ -900,6 +904,11 @@ def cuda_arm(args):
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64", "kernel": top_name, "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak, "peak_source": fp64_src,
+                     "achieved_contract": top["contract_flopeq_per_input_ray"] * top["input_rays"] / (top["ms"] * 1e-3) / 1e12,
+                     "frac_contract": top.get("fp64_frac_contract"),
+                     "achieved_note": "`achieved` counts the FP64 flops the kernel executes (ncu counters of the committed capture: 2 per "
+                                      "DFMA, 1 per DMUL / DADD); `achieved_contract` the SURVEY 8d flop-equivalents per ray (a sqrt, a "
+                                      "division or a sin counted at its published cost)",
                      "traffic": (tp["dram_bytes_per_input_ray"] * top["input_rays"]) if tp else None,
                      "flop_per_input_ray": flop_per, "input_rays_per_launch": top["input_rays"], "avg_launch_ms": top["ms"],
                      "hbm": {"achieved_gbs": top["algorithmic_bytes_per_input_ray"] * top["input_rays"] / (top["ms"] * 1e-3) / 1e9,
@@ -940,7 +949,7 @@ def cuda_arm(args):
         slowest = min(d2h["concurrent_gbs_per_rank"])
         if slowest > 0:
             floor_ms = line["e2e"]["d2h_bytes_per_step"] / (slowest * 1e9) * 1e3
-            e2e_ms = total_rays / line["e2e"]["value"] * 1e3
+            e2e_ms = (total_rays / args.steps) / line["e2e"]["value"] * 1e3
             line["e2e"]["d2h_floor"] = {"ms_per_step": floor_ms, "e2e_ms_per_step": e2e_ms, "device_ms_per_step": line["ms_per_step"],
                                         "bound": "host link" if floor_ms > line["ms_per_step"] else "device",
                                         "e2e_over_floor": e2e_ms / max(floor_ms, line["ms_per_step"]),

@@ -286,6 +286,10 @@ int marxb200_abi_version (void);
 const char *marxb200_last_error (void);
 /* device_ordinal: CUDA device; seed: RandomSeed (marx.c:846-849, JDMsrandom). */
 int marxb200_create (marxb200_ctx **ctxp, int device_ordinal, uint64_t seed);
+/* Optional: create the CUDA context of a device ahead of marxb200_create, e.g. from a helper thread while the host program still
+ * reads its calibration files (marx.c:257-318: the *_init calls of the stock modules).  Context creation costs 0.5 - 3 s of a
+ * process's life; it is the largest fixed cost of a `marx` run on the device.  Safe to call from any thread, any number of times. */
+int marxb200_device_warmup (int device_ordinal);
 int marxb200_destroy (marxb200_ctx *ctx);
 /* use an externally owned cudaStream_t (e.g. the harness's timing stream); NULL = library stream */
 int marxb200_set_stream (marxb200_ctx *ctx, void *cuda_stream);

@@ -24,7 +24,7 @@
  *
  * Table upload: on the first marx_create_photons the post-init statics of the stock modules are serialised by the
  * calpack_*.c units (the field mappings of INTEGRATION.md section 2) and handed to marxb200_load_calpack.
- * Environment: MARXB200_DEVICE (CUDA ordinal, default 0), MARXB200_EGRESS (bulk [default] | stock), MARXB200_WRITER_THREADS
+ * Environment: MARXB200_DEVICE (CUDA ordinal, default 0), MARXB200_WARMUP (1: create the CUDA context in a helper thread at program load), MARXB200_EGRESS (bulk [default] | stock), MARXB200_WRITER_THREADS
  * (background column-file writers, default 8; 0 = synchronous).
  * Batch size: the reference caps dNumRays at 10^6 only through the range field of its parameter file (marx/par/marx.par:9); the
  * build writes integration/_build/par/marx.par, the same file with that maximum raised to 2^28, so that `marx_gpu @@.../marx.par
@@ -35,6 +35,7 @@
 #include <string.h>
 #include <unistd.h>
 #include <time.h>
+#include <pthread.h>
 #include <marx.h>
 #include <marxb200.h>
 
@@ -71,6 +72,26 @@ static double now (void)
    return ts.tv_sec + 1e-9 * ts.tv_nsec;
 }
 
+/* MARXB200_WARMUP=1: the CUDA context is created by a helper thread from the moment the program is loaded, while marx.c still parses
+ * its parameter file and the stock *_init calls read the calibration files.  Off by default: on the B200 boxes measured here the
+ * stock initialisation takes ~0.1 s against 0.5 - 1.3 s of context creation (which varies that much from run to run), so the
+ * overlap was not measurable (tools/driver_startup_probe.sh). */
+static pthread_t Warm_Thread;
+static int Warm_Started;
+static void *warm_main (void *unused)
+{
+   const char *dev = getenv ("MARXB200_DEVICE");
+   (void) unused;
+   (void) marxb200_device_warmup (dev ? atoi (dev) : 0);
+   return NULL;
+}
+__attribute__ ((constructor)) static void warm_start (void)
+{
+   const char *e = getenv ("MARXB200_WARMUP");
+   if ((e == NULL) || (0 == atoi (e))) return;
+   if (0 == pthread_create (&Warm_Thread, NULL, warm_main, NULL)) Warm_Started = 1;
+}
+
 static int gpu_error (const char *what)
 {
    marx_error ("marxb200: %s: %s", what, marxb200_last_error ());
@@ -103,6 +124,7 @@ static int gpu_init (Marx_Source_Type *st, Marx_Photon_Type *pt)
      { marx_error ("marxb200: DetectorType must be NONE, ACIS-S, ACIS-I, HRC-S or HRC-I for the GPU path"); return -1; }
 
    double t_mark = now ();
+   if (Warm_Started) { (void) pthread_join (Warm_Thread, NULL); Warm_Started = 0; }
    if (-1 == marxb200_create (&Ctx, dev ? atoi (dev) : 0, (uint64_t) Seed))
      return gpu_error ("marxb200_create");
    T_Init_Create = now () - t_mark; t_mark = now ();

@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "marxb200_pileup_run", "marxb200_pileup_events",
     "marxb200_comm_get_unique_id", "marxb200_comm_init", "marxb200_comm_init_file", "marxb200_comm_info", "marxb200_comm_destroy",
     "marxb200_shard_of", "marxb200_trace_sharded", "marxb200_tally_allreduce",
-    "marxb200_merge_events_begin", "marxb200_merge_events_end", "marxb200_merge_download", "marxb200_probe_d2h",
+    "marxb200_merge_events_begin", "marxb200_merge_events_end", "marxb200_merge_download", "marxb200_probe_d2h", "marxb200_device_warmup",
 ]
 
 # marxb200_tally_axis.column (include/marxb200.h)
@@ -162,6 +162,7 @@ def load_library():
         "marxb200_merge_events_end": [vp, vp],
         "marxb200_merge_download": [vp, vp, u64, vp],
         "marxb200_probe_d2h": [vp, u64, i32, i32, C.POINTER(dbl)],
+        "marxb200_device_warmup": [i32],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)

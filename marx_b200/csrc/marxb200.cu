@@ -144,6 +144,14 @@ static int ensure_aos (marxb200_ctx *c, uint64_t n)
 extern "C" int marxb200_abi_version (void) { return MARXB200_ABI_VERSION; }
 extern "C" const char *marxb200_last_error (void) { return g_err; }
 
+extern "C" int marxb200_device_warmup (int device_ordinal)
+{
+   cudaError_t e = cudaSetDevice (device_ordinal);
+   if (e == cudaSuccess) e = cudaFree (nullptr);
+   if (e != cudaSuccess) return fail ("marxb200_device_warmup: device %d: %s", device_ordinal, cudaGetErrorString (e));
+   return 0;
+}
+
 #define GUARD(idx) do { if (-1 == mxb_guard_buffer (c, (idx))) return -1; } while (0)
 extern "C" int marxb200_create (marxb200_ctx **ctxp, int device_ordinal, uint64_t seed)
 {
