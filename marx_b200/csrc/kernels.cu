@@ -611,6 +611,9 @@ __global__ void __launch_bounds__ (kStageThreads) k1_flatfield (const __grid_con
 // (measured without effect on B200: 32 registers per thread for 64 resident warps per SM, and two tiles per warp with the two table
 // searches advanced in lockstep -- 0.279 / 0.280 / 0.279 ms for the stage.  The kernel is not short of warps or of independent
 // loads: its 97 B of DRAM traffic per ray are the 32-byte sectors of the two per-ray constants gathered through the slot key.)
+// (Round 2, measured without gain: the four shells' energy grids -- 1408 floats each for the HETG -- copied into shared memory once per
+// CTA, so that the ten probes of the energy bracket stay on the SM: 0.273 against 0.266 ms for the stage.  The bracket's probes hit
+// L1 / L2 lines shared by the whole warp; the kernel waits for the sector-granular gathers through the slot key, see above.)
 __global__ void __launch_bounds__ (256) k2_select (const __grid_constant__ StageArgs a)
 {
    const K2Blob *B = reinterpret_cast<const K2Blob *> (a.blob);          // header fields through L1; the tables live in L2
