@@ -1,4 +1,7 @@
-"""Multi-GPU plumbing (torch.distributed; NCCL over NVLink on the GPU box, gloo in the CPU tests).
+"""Host-side statement of the multi-GPU exchanges (torch.distributed; gloo in the CPU tests).  The product path is
+marx_b200/csrc/comm.cu behind the C ABI (marxb200_trace_sharded, marxb200_merge_events_begin/_end, marxb200_tally_allreduce: NCCL and
+peer writes on device buffers); these functions state the same arithmetic on numpy arrays so that the block rule, the sequential
+time-base additions and the rank-order merge can be tested with world_size 2 on a CPU box (tests/test_dist_gloo.py).
 
 The path shards trivially: rank r traces the contiguous block of global ray indices
 [(step*G + r)*n, (step*G + r + 1)*n) with the same counter-based draw streams, so every event is
@@ -32,12 +35,22 @@ def exchange_time_base(time_sums, rank, world, running, device=None):
     """all-gather the super-tile sums (tiny) and return (time base of this rank's block, new running time)."""
     import torch
     import torch.distributed as dist
-    t = torch.as_tensor(np.asarray(time_sums, dtype=np.float64))
+    mine = np.asarray(time_sums, dtype=np.float64).reshape(-1)
+    # blocks may be ragged (a short or empty last block): agree on the longest, pad with zeros (adding 0.0 changes no sum), trim again
+    cnt = torch.tensor([len(mine)], dtype=torch.int64)
+    if device is not None:
+        cnt = cnt.to(device)
+    counts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(counts, cnt)
+    counts = [int(c.item()) for c in counts]
+    pad = np.zeros(max(max(counts), 1), dtype=np.float64)
+    pad[:len(mine)] = mine
+    t = torch.from_numpy(pad)
     if device is not None:
         t = t.to(device)
     gathered = [torch.empty_like(t) for _ in range(world)]
     dist.all_gather(gathered, t)
-    sums = [g.cpu().numpy() for g in gathered]
+    sums = [g.cpu().numpy()[:counts[r]] for r, g in enumerate(gathered)]
     bases, end = block_time_bases(sums, running)
     return bases[rank], end
 
