@@ -33,12 +33,15 @@
 // resident CTAs per SM the register allocation is sized for (developer knobs: tools/build_variant.sh)
 #ifndef MX_K1_MINBLOCKS
 #define MX_K1_MINBLOCKS 3
+#else
+#define MX_K1_MINBLOCKS_SET 1
 #endif
 #ifndef MX_K2_MINBLOCKS
 #define MX_K2_MINBLOCKS 3
 #endif
+// k01: 4 since its tiles come from a ticket (64 registers, 32 warps per SM: 1.224 -> 1.205 ms; with the static stride 3 was better)
 #ifndef MX_K01_MINBLOCKS
-#define MX_K01_MINBLOCKS 3
+#define MX_K01_MINBLOCKS 4
 #endif
 namespace mx {
 
@@ -436,8 +439,16 @@ template <int PHASE> struct K1Shape
    static constexpr int ND = XO + (kNormalOut ? 3 : 0) + (kSpareOut ? 1 : 0), NU = 2 + (kOptOut ? 3 : 0);
 };
 
+// Resident CTAs per SM by phase: B1 and C2 (phases 3, 5) run faster with four (64 registers, 32 warps: 0.705 -> 0.652 ms and 0.217 ->
+// 0.199 ms per C2 batch), B2+C1 (phase 4: reflection, scatter, two transforms, the H intersection and the second reflectivity test in
+// one kernel) loses 4 % to the spills and keeps three.  -DMX_K1_MINBLOCKS=k forces one value for all phases (A/B builds).
+#ifdef MX_K1_MINBLOCKS_SET
+constexpr int k1_min_blocks (int) { return MX_K1_MINBLOCKS; }
+#else
+constexpr int k1_min_blocks (int phase) { return ((phase == 3) || (phase == 5)) ? 4 : MX_K1_MINBLOCKS; }
+#endif
 template <int PHASE>
-__global__ void __launch_bounds__ (kStageThreads, MX_K1_MINBLOCKS) k1_hrma (const __grid_constant__ StageArgs a)
+__global__ void __launch_bounds__ (kStageThreads, k1_min_blocks (PHASE)) k1_hrma (const __grid_constant__ StageArgs a)
 {
    using Shape = K1Shape<PHASE>;
    constexpr int ND = Shape::ND, NU = Shape::NU;
@@ -719,8 +730,15 @@ __global__ void __launch_bounds__ (kStageThreads, MX_K2_MINBLOCKS) k2_grating (c
 // PHASE 0: the whole detector stage in one kernel; 1, 2: its two halves (acis_detect_a / _b, mx_acis.cuh) as two kernels with a
 // re-packed list in between.  The chip index found by the first half travels in the pha column (not yet used), the chip
 // pixels in theirs; the QE test is the only draw of the first half, so the second resumes the DETECTOR sub-stream at draw 0 or 1.
+#ifndef MX_K3A_MINBLOCKS
+#define MX_K3A_MINBLOCKS MX_K3_MINBLOCKS
+#endif
+#ifndef MX_K3B_MINBLOCKS
+#define MX_K3B_MINBLOCKS MX_K3_MINBLOCKS
+#endif
+constexpr int k3_min_blocks (int phase) { return (phase == 1) ? MX_K3A_MINBLOCKS : ((phase == 2) ? MX_K3B_MINBLOCKS : MX_K3_MINBLOCKS); }
 template <bool DET, int PHASE>
-__global__ void __launch_bounds__ (kStageThreads, MX_K3_MINBLOCKS) k3_acis (const __grid_constant__ StageArgs a)
+__global__ void __launch_bounds__ (kStageThreads, k3_min_blocks (PHASE)) k3_acis (const __grid_constant__ StageArgs a)
 {
    constexpr int ND = 6, NU = 7;
    extern __shared__ __align__ (128) unsigned char smem[];

@@ -67,7 +67,7 @@ __device__ __forceinline__ double cos_kernel (double z)
 }
 // arguments beyond the fast range (never on the benchmark path): ONE out-of-line copy of the libdevice functions per kernel
 // instead of an inlined Payne-Hanek reduction at every call site
-static __device__ __noinline__ void sincos_far (double x, double *s, double *c) { sincos (x, s, c); }
+static __device__ __noinline__ double2 sincos_far (double x) { double2 r; sincos (x, &r.x, &r.y); return r; }   // by value: no stack slot at the call sites
 static __device__ __noinline__ double sin_far (double x) { return sin (x); }
 static __device__ __noinline__ double log_far (double x) { return log (x); }
 #endif
@@ -86,7 +86,7 @@ MXM_HD void mx_sincos (double x, double &s, double &c)
         c = ((k + 1) & 2) ? -b : b;
         return;
      }
-   sincos_far (x, &s, &c);
+   { const double2 r = sincos_far (x); s = r.x; c = r.y; }
 #elif defined(__CUDA_ARCH__)
    sincos (x, &s, &c);
 #else

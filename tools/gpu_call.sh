@@ -1,1 +1,13 @@
-( timeout 600 python -m pytest tests/test_gpu_lookahead.py -x -q -m gpu 2>&1 | tail -3 | cut -c1-300 )
+mkdir -p gpurun_out
+for v in default k3a4 k3b4 k3b2; do
+if [ $v = default ]; then unset MARXB200_LIB; else export MARXB200_LIB=$PWD/build/variants/libmarxb200_$v.so; fi
+timeout 120 python bench.py --steps 40 --warmup 3 --no-sweep --no-probe --no-configs --no-driver --no-cpu-baseline > gpurun_out/bench_v.json 2> /dev/null
+python - <<PY
+import json
+d=json.loads(open("gpurun_out/bench_v.json").read().strip().splitlines()[-1])
+k=d["roofline"]["kernels"]
+print("$v value %.4g ms %.4f | " % (d["value"], d["ms_per_step"]), " ".join("%.4f"%v["ms"] for v in k.values()))
+PY
+done
+unset MARXB200_LIB
+( timeout 900 python -m pytest tests/test_gpu_oracle.py tests/test_gpu_param_surface.py -x -q -m gpu 2>&1 | tail -2 )
