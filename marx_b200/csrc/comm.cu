@@ -141,7 +141,10 @@ struct MxComm
    int *d_flag = nullptr;                                                   // barrier / agreement scratch
    int dst = -1; uint64_t max_rows = 0, mask = 0;
    EgressPlan plan; int which[kMaxEgressCols]; uint64_t stage_bytes = 0;
-   void *stage = nullptr;                     // this rank's packed columns: column c at plan.offset[c], max_rows rows each
+   void *stage = nullptr;                     // this rank's packed columns of the batch being merged: column c at plan.offset[c], max_rows rows each
+   void *stage_bufs[2] = {nullptr, nullptr};  // two staging areas alternate (pre-pack, mx_context.hpp); stage == stage_bufs[stage_k]
+   int stage_k = 0;
+   cudaEvent_t ev_stage_free[2] = {nullptr, nullptr};      // behind the transfers that last read stage_bufs[k]
    void *merged = nullptr;                    // dst: merged columns, column c at merged_off[c], world * max_rows rows each
    void *peer_merged = nullptr;               // other ranks, MERGE_PEER: the destination's buffer mapped with CUDA IPC
    uint64_t merged_off[kMaxEgressCols]; uint64_t merged_bytes = 0;
@@ -182,6 +185,7 @@ void mxb_comm_release (marxb200_ctx *c)
    if (m->ahead_stream) { cudaStreamSynchronize (m->ahead_stream); cudaStreamDestroy (m->ahead_stream); }
    for (cudaEvent_t e : {m->ev_packed, m->ev_counts, m->ev_pushed, m->ev_t0, m->ev_tc, m->ev_t1, m->ev_ahead, m->ev_consumed}) if (e) cudaEventDestroy (e);
    for (double *p : {m->ahead_tile_sums, m->ahead_super_sums, m->ahead_all_sums}) if (p) cudaFree (p);
+   for (int k = 0; k < 2; k++) if (m->ev_stage_free[k]) cudaEventDestroy (m->ev_stage_free[k]);
    if (m->d_all_sums) cudaFree (m->d_all_sums);
    if (m->d_all_counts) cudaFree (m->d_all_counts);
    if (m->h_all_counts) cudaFreeHost (m->h_all_counts);
@@ -467,7 +471,8 @@ static void merge_release (marxb200_ctx *c)
    if (m->merge_stream) cudaStreamSynchronize (m->merge_stream);
    if (m->peer_merged) cudaIpcCloseMemHandle (m->peer_merged);
    if (m->merged) cudaFree (m->merged);
-   if (m->stage) cudaFree (m->stage);
+   if (c->prepack.owner == 1) { c->prepack.armed = false; c->prepack.done = false; }
+   for (int k = 0; k < 2; k++) { if (m->stage_bufs[k]) cudaFree (m->stage_bufs[k]); m->stage_bufs[k] = nullptr; }
    m->peer_merged = m->merged = m->stage = nullptr;
    m->dst = -1; m->max_rows = 0; m->mask = 0; m->pending = false;
 }
@@ -482,7 +487,12 @@ static int merge_setup (marxb200_ctx *c, uint64_t write_mask, uint64_t max_rows,
    merge_release (c);
    m->stage_bytes = mxb_build_egress_plan (write_mask, max_rows, m->plan, m->which);
    if (m->plan.num_cols == 0) return fail ("marxb200_merge_events_begin: the write mask selects no column");
-   CUDA_OK (cudaMalloc (&m->stage, (size_t) m->stage_bytes + 256));
+   for (int k = 0; k < 2; k++)
+     {
+        CUDA_OK (cudaMalloc (&m->stage_bufs[k], (size_t) m->stage_bytes + 256));
+        if (m->ev_stage_free[k] == nullptr) CUDA_OK (cudaEventCreateWithFlags (&m->ev_stage_free[k], cudaEventDisableTiming));
+     }
+   m->stage_k = 0; m->stage = m->stage_bufs[0];
    uint64_t off = 0;
    for (int j = 0; j < m->plan.num_cols; j++)
      {
@@ -548,12 +558,24 @@ extern "C" int marxb200_merge_events_begin (marxb200_ctx *c, uint64_t write_mask
    // from the start of the simulation on every rank
    CUDA_OK (cudaStreamWaitEvent (c->stream, m->ev_packed, 0));         // the previous conversion has consumed the last snapshot
    CUDA_OK (cudaMemcpyAsync (m->d_all_counts + 64, c->d_counts + c->stage_done, sizeof (unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
-   if (-1 == mxb_reader_begin (c, 1, m->merge_stream)) return -1;
-   launch_egress_pack (mxb_observed (c, c->buf[c->cur]), m->d_all_counts + 64, m->max_rows, m->plan, m->stage, nullptr, total_time, m->merge_stream);
-   c->launches += 1;
-   CUDA_OK (cudaGetLastError ());
+   const int k = m->stage_k ^ 1;
+   PackArgs want;
+   memset (&want, 0, sizeof (want));
+   want.plan = m->plan; want.dst = (unsigned char *) m->stage_bufs[k]; want.dev_start_time = nullptr; want.total_time = total_time; want.max_rows = m->max_rows;
+   if (-1 == mxb_reader_begin (c, 1, m->merge_stream)) return -1;            // the merge stream continues behind the list (and the snapshot)
+   if (!mxb_prepack_matches (c, 1, want))
+     {
+        launch_egress_pack (mxb_observed (c, c->buf[c->cur]), m->d_all_counts + 64, m->max_rows, m->plan, m->stage_bufs[k], nullptr, total_time, m->merge_stream);
+        c->launches += 1;
+        CUDA_OK (cudaGetLastError ());
+        if (-1 == mxb_reader_end (c, 1, m->merge_stream)) return -1;
+     }
+   // else: the order restoration at the end of the trace wrote these very images into stage_bufs[k] (pre-pack): nothing to convert
    CUDA_OK (cudaEventRecord (m->ev_packed, m->merge_stream));
-   if (-1 == mxb_reader_end (c, 1, m->merge_stream)) return -1;
+   m->stage_k = k; m->stage = m->stage_bufs[k];
+   // a run that merges every batch the same way: let the next batch's order restoration write the images into the other buffer
+   want.dst = (unsigned char *) m->stage_bufs[k ^ 1];
+   mxb_prepack_arm (c, 1, want, m->ev_stage_free[k ^ 1]);
    // counts of all ranks, on the merge stream (the context's stream goes on with the next batch)
    NCCL_OK (N->AllGather (m->d_all_counts + 64, m->d_all_counts, 1, NCCL_UINT64, m->comm_merge, m->merge_stream));
    CUDA_OK (cudaMemcpyAsync (m->h_all_counts, m->d_all_counts, m->world * sizeof (unsigned long long), cudaMemcpyDeviceToHost, m->merge_stream));
@@ -635,6 +657,7 @@ extern "C" int marxb200_merge_events_end (marxb200_ctx *c, marxb200_merged_layou
      }
    CUDA_OK (cudaEventRecord (m->ev_t1, m->merge_stream));
    CUDA_OK (cudaEventRecord (m->ev_pushed, m->merge_stream));
+   CUDA_OK (cudaEventRecord (m->ev_stage_free[m->stage_k], m->merge_stream));
    // this rank's part is done when its transfers are; the next batch's kernels are already queued on the context's stream
    CUDA_OK (cudaStreamSynchronize (m->merge_stream));
    CUDA_OK (cudaGetLastError ());

@@ -1055,29 +1055,108 @@ __global__ void __launch_bounds__ (256) order_rank (OrderArgs a)
 // permutation of the unordered list (a stage kernel emits survivors in completion order, so neighbours in arrival
 // order sit within a few hundred entries of each other) and are absorbed by L1/L2.  The first version scattered the
 // 23 columns instead: partial-sector writes made it run at 1.1 TB/s (1.15 ms for the 5.1e6 events of a C1 batch).
-__global__ void __launch_bounds__ (256) order_gather (OrderArgs a)
+//
+// PACK: the kernel also emits the file images of the row's columns (what egress_pack would produce from the list it writes) into
+// a staging buffer, straight from the registers that hold the row: the packed egress / the multi-GPU merge of a run that asks for
+// the same columns batch after batch then needs no conversion pass of its own (marxb200.cu "pre-pack").
+__device__ __forceinline__ uint32_t bswap32 (uint32_t v) { return __byte_perm (v, 0u, 0x0123); }
+__device__ __forceinline__ uint16_t bswap16 (uint16_t v) { return (uint16_t) ((v << 8) | (v >> 8)); }
+struct EventRow
+{
+   double energy, x0, x1, x2, p0, p1, p2, time;
+   uint64_t ray;
+   float chipx, chipy, pi, upix, vpix, dra, ddec, droll, ddy, ddz, ddth;
+   uint32_t sorders;
+   int16_t pha; uint8_t shell, region; int8_t order, ccd;
+};
+// the file image of one column of a row: its bits, right-aligned (marxio.c:217-322: the casts of the MAKE_WRITE_*_FUNC macros, big endian)
+__device__ __forceinline__ uint32_t egress_from_row (const EventRow &r, int kind, double start_time, double total_time)
+{
+   float f = 0.0f;
+   switch (kind)
+     {
+      case EGRESS_PI: f = r.pi; break;
+      case EGRESS_ENERGY: f = (float) r.energy; break;
+      case EGRESS_TIME: f = (float) ((r.time - start_time) + total_time); break;
+      case EGRESS_XPOS: f = (float) r.x0; break;
+      case EGRESS_YPOS: f = (float) r.x1; break;
+      case EGRESS_ZPOS: f = (float) r.x2; break;
+      case EGRESS_XCOS: f = (float) r.p0; break;
+      case EGRESS_YCOS: f = (float) r.p1; break;
+      case EGRESS_ZCOS: f = (float) r.p2; break;
+      case EGRESS_CHIPX: f = r.chipx; break;
+      case EGRESS_CHIPY: f = r.chipy; break;
+      case EGRESS_HRC_U: f = r.upix; break;
+      case EGRESS_HRC_V: f = r.vpix; break;
+      case EGRESS_SKY_RA: f = r.dra; break;
+      case EGRESS_SKY_DEC: f = r.ddec; break;
+      case EGRESS_SKY_ROLL: f = r.droll; break;
+      case EGRESS_DET_DY: f = r.ddy; break;
+      case EGRESS_DET_DZ: f = r.ddz; break;
+      case EGRESS_DET_THETA: f = r.ddth; break;
+      case EGRESS_TAG: return bswap32 ((uint32_t) r.ray);
+      case EGRESS_PHA: return bswap16 ((uint16_t) r.pha);
+      case EGRESS_MIRROR: return bswap16 ((uint16_t) r.shell);
+      case EGRESS_CCD: return (unsigned char) r.ccd;
+      case EGRESS_REGION: return (unsigned char) r.region;
+      case EGRESS_ORDER: return (unsigned char) r.order;
+      case EGRESS_ORDER1: return r.sorders & 0xFFu;
+      case EGRESS_ORDER2: return (r.sorders >> 8) & 0xFFu;
+      case EGRESS_ORDER3: return (r.sorders >> 16) & 0xFFu;
+      case EGRESS_ORDER4: return r.sorders >> 24;
+      default: return 0;
+     }
+   return bswap32 (__float_as_uint (f));
+}
+__device__ __forceinline__ void egress_store (unsigned char *base, int kind, uint64_t i, uint32_t v)
+{
+   switch (kind)
+     {
+      case EGRESS_PHA: case EGRESS_MIRROR:
+        reinterpret_cast<uint16_t *> (base)[i] = (uint16_t) v; break;
+      case EGRESS_CCD: case EGRESS_REGION: case EGRESS_ORDER: case EGRESS_ORDER1: case EGRESS_ORDER2: case EGRESS_ORDER3: case EGRESS_ORDER4:
+        base[i] = (unsigned char) v; break;
+      default:
+        reinterpret_cast<uint32_t *> (base)[i] = v; break;
+     }
+}
+template <bool PACK>
+__global__ void __launch_bounds__ (256) order_gather (OrderArgs a, const __grid_constant__ PackArgs pk)
 {
    const unsigned long long n = *a.n_live;
    const PhotonSoA &in = a.in, &out = a.out;
+   double start_time = 0.0;
+   if (PACK && (pk.dev_start_time != nullptr)) start_time = *pk.dev_start_time;
    for (unsigned long long j = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (unsigned long long) gridDim.x * blockDim.x)
      {
         const uint32_t s = a.perm[j], key = in.slot[s];
         const RayConst &rc = a.rc;
-        double rc_energy; uint64_t rc_ray;
-        rc_load (rc, key, rc_energy, rc_ray);
-        out.energy[j] = rc_energy;
-        out.x0[j] = in.x0[s]; out.x1[j] = in.x1[s]; out.x2[j] = in.x2[s];
-        out.p0[j] = in.p0[s]; out.p1[j] = in.p1[s]; out.p2[j] = in.p2[s];
-        out.time[j] = rc.time[key]; out.aux[j] = in.aux[s];
-        out.ray[j] = rc_ray; out.slot[j] = key; out.flags[j] = in.flags[s];
-        out.dra[j] = rc.dra[key]; out.ddec[j] = rc.ddec[key]; out.droll[j] = rc.droll[key];
-        if (out.ddy != nullptr) { out.ddy[j] = rc.ddy[key]; out.ddz[j] = rc.ddz[key]; out.ddth[j] = rc.ddth[key]; }   // null: detector dither not live
-        out.chipx[j] = in.chipx[s]; out.chipy[j] = in.chipy[s]; out.pi[j] = in.pi[s];
-        out.pha[j] = in.pha[s]; out.shell[j] = in.shell[s]; out.order[j] = in.order[s]; out.ccd[j] = in.ccd[s];
-        out.upix[j] = in.upix[s]; out.vpix[j] = in.vpix[s]; out.sorders[j] = in.sorders[s]; out.region[j] = in.region[s];
+        EventRow r;
+        rc_load (rc, key, r.energy, r.ray);
+        r.x0 = in.x0[s]; r.x1 = in.x1[s]; r.x2 = in.x2[s]; r.p0 = in.p0[s]; r.p1 = in.p1[s]; r.p2 = in.p2[s];
+        r.time = rc.time[key];
+        r.dra = rc.dra[key]; r.ddec = rc.ddec[key]; r.droll = rc.droll[key];
+        r.ddy = 0.0f; r.ddz = 0.0f; r.ddth = 0.0f;
+        if (out.ddy != nullptr) { r.ddy = rc.ddy[key]; r.ddz = rc.ddz[key]; r.ddth = rc.ddth[key]; }   // null: detector dither not live
+        r.chipx = in.chipx[s]; r.chipy = in.chipy[s]; r.pi = in.pi[s];
+        r.pha = in.pha[s]; r.shell = in.shell[s]; r.order = in.order[s]; r.ccd = in.ccd[s];
+        r.upix = in.upix[s]; r.vpix = in.vpix[s]; r.sorders = in.sorders[s]; r.region = in.region[s];
+        out.energy[j] = r.energy;
+        out.x0[j] = r.x0; out.x1[j] = r.x1; out.x2[j] = r.x2;
+        out.p0[j] = r.p0; out.p1[j] = r.p1; out.p2[j] = r.p2;
+        out.time[j] = r.time; out.aux[j] = in.aux[s];
+        out.ray[j] = r.ray; out.slot[j] = key; out.flags[j] = in.flags[s];
+        out.dra[j] = r.dra; out.ddec[j] = r.ddec; out.droll[j] = r.droll;
+        if (out.ddy != nullptr) { out.ddy[j] = r.ddy; out.ddz[j] = r.ddz; out.ddth[j] = r.ddth; }
+        out.chipx[j] = r.chipx; out.chipy[j] = r.chipy; out.pi[j] = r.pi;
+        out.pha[j] = r.pha; out.shell[j] = r.shell; out.order[j] = r.order; out.ccd[j] = r.ccd;
+        out.upix[j] = r.upix; out.vpix[j] = r.vpix; out.sorders[j] = r.sorders; out.region[j] = r.region;
+        if (PACK && (j < pk.max_rows))
+          for (int c = 0; c < pk.plan.num_cols; c++)
+            egress_store (pk.dst + pk.plan.offset[c], pk.plan.kind[c], j, egress_from_row (r, pk.plan.kind[c], start_time, pk.total_time));
      }
 }
-void launch_restore_order (const OrderArgs &a, int num_sms, cudaStream_t s, int *n_launches)
+void launch_restore_order (const OrderArgs &a, int num_sms, cudaStream_t s, int *n_launches, const PackArgs *pack)
 {
    const uint32_t n_words = (uint32_t) (a.n_slots / 32 + 1), n_blocks = (n_words + 1023u) / 1024u;
    const int grid = num_sms * 8;
@@ -1085,7 +1164,13 @@ void launch_restore_order (const OrderArgs &a, int num_sms, cudaStream_t s, int 
    order_scan_words<<<n_blocks, 256, 0, s>>> (a, n_words);
    order_scan_blocks<<<1, 1024, 0, s>>> (a, n_blocks);
    order_rank<<<grid, 256, 0, s>>> (a);
-   order_gather<<<grid, 256, 0, s>>> (a);
+   if (pack != nullptr) order_gather<true><<<grid, 256, 0, s>>> (a, *pack);
+   else
+     {
+        PackArgs none;
+        memset (&none, 0, sizeof (none));
+        order_gather<false><<<grid, 256, 0, s>>> (a, none);
+     }
    if (n_launches) *n_launches = 5;
 }
 
@@ -1198,9 +1283,6 @@ void launch_exposure_truncate (const PhotonSoA &buf, unsigned long long *n, doub
 // thread handles one photon and walks the (uniform) column list, so that every store instruction of a warp hits
 // consecutive elements of one packed column.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t bswap32 (uint32_t v) { return __byte_perm (v, 0u, 0x0123); }
-__device__ __forceinline__ uint16_t bswap16 (uint16_t v) { return (uint16_t) ((v << 8) | (v >> 8)); }
-
 // the file image of one (photon, column) element: its bits, right-aligned (4, 2 or 1 bytes wide by kind)
 __device__ __forceinline__ uint32_t egress_load (const PhotonSoA &in, int kind, uint64_t i, double start_time, double total_time)
 {
@@ -1241,19 +1323,6 @@ __device__ __forceinline__ uint32_t egress_load (const PhotonSoA &in, int kind, 
      }
    return bswap32 (__float_as_uint (f));
 }
-__device__ __forceinline__ void egress_store (unsigned char *base, int kind, uint64_t i, uint32_t v)
-{
-   switch (kind)
-     {
-      case EGRESS_PHA: case EGRESS_MIRROR:
-        reinterpret_cast<uint16_t *> (base)[i] = (uint16_t) v; break;
-      case EGRESS_CCD: case EGRESS_REGION: case EGRESS_ORDER: case EGRESS_ORDER1: case EGRESS_ORDER2: case EGRESS_ORDER3: case EGRESS_ORDER4:
-        base[i] = (unsigned char) v; break;
-      default:
-        reinterpret_cast<uint32_t *> (base)[i] = v; break;
-     }
-}
-
 // The column walk is cut into groups of kEgressGroup columns: all loads of a group are issued before its first store (a plain
 // load-store-load-store walk leaves one request in flight per thread and ran at a third of the HBM rate: 0.10 ms per 1.2e6 events).
 constexpr int kEgressGroup = 8;

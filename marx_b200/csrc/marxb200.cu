@@ -232,6 +232,8 @@ extern "C" int marxb200_destroy (marxb200_ctx *c)
    if (c->d_super_sums) cudaFree (c->d_super_sums);
    if (c->d_aos) cudaFree (c->d_aos);
    if (c->egress_slab) cudaFree (c->egress_slab);
+   if (c->packed_slab_b) cudaFree (c->packed_slab_b);
+   for (int k = 0; k < 2; k++) if (c->ev_slab_free[k]) cudaEventDestroy (c->ev_slab_free[k]);
    if (c->h_egress_count) cudaFreeHost (c->h_egress_count);
    if (c->ev_staged) cudaEventDestroy (c->ev_staged);
    if (c->ev_copied) cudaEventDestroy (c->ev_copied);
@@ -533,7 +535,7 @@ extern "C" int marxb200_alloc_photons (marxb200_ctx *c, uint64_t max_photons)
    CUDA_OK (cudaMalloc (&c->ahead_super_sums, n_super * sizeof (double)));
    CUDA_OK (cudaStreamSynchronize (c->stream));
    c->capacity = max_photons;
-   c->cur = 0; c->stage_done = -1; c->n_generated = 0; c->ordered = true;
+   c->cur = 0; c->stage_done = -1; c->n_generated = 0; c->ordered = true; c->prepack.done = false;
    return 0;
 }
 
@@ -552,6 +554,18 @@ int mxb_guard_buffer (marxb200_ctx *c, int idx)
           c->reader_buf[k] = -1;
        }
    return 0;
+}
+bool mxb_prepack_matches (const marxb200_ctx *c, int owner, const mx::PackArgs &want)
+{
+   const marxb200_ctx::Prepack &p = c->prepack;
+   return p.armed && p.done && (p.owner == owner) && (p.args.dst == want.dst) && (p.args.dev_start_time == want.dev_start_time)
+          && (p.args.total_time == want.total_time) && (p.args.max_rows == want.max_rows)
+          && (0 == memcmp (&p.args.plan, &want.plan, sizeof (want.plan)));
+}
+void mxb_prepack_arm (marxb200_ctx *c, int owner, const mx::PackArgs &next, cudaEvent_t ev_free)
+{
+   c->prepack.armed = (getenv ("MARXB200_PREPACK") == nullptr) || (atoi (getenv ("MARXB200_PREPACK")) != 0);      // developer A/B switch
+   c->prepack.done = false; c->prepack.owner = owner; c->prepack.args = next; c->prepack.ev_free = ev_free;
 }
 int mxb_reader_begin (marxb200_ctx *c, int slot, cudaStream_t reader)
 {
@@ -601,7 +615,7 @@ extern "C" int marxb200_create_photons (marxb200_ctx *c, uint64_t first_ray, uin
    launch_source (a, c->stream); prof_mark (c, 2);
    c->launches += 5;                     // k0_time_sums, k0_time_super/_bases/_tiles, k0_source
    c->det_dither_dirty = false;          // k0_source rewrote the detector-dither columns of every slot it generated
-   c->cur = 0; c->stage_done = 0; c->n_generated = n; c->ordered = true; c->first_mirror_kernel = 0;
+   c->cur = 0; c->stage_done = 0; c->n_generated = n; c->ordered = true; c->first_mirror_kernel = 0; c->prepack.done = false;
    if (c->D.mode == 2)
      {
         // the stock reader ends the simulation at the first ray it cannot bracket (end of the ASPSOL file)
@@ -721,6 +735,7 @@ static int run_stage (marxb200_ctx *c, int stage)
         c->launches += 1;
         CUDA_OK (cudaGetLastError ());
         if (c->compact) { c->cur = 1 - c->cur; c->ordered = false; }
+        c->prepack.done = false;
         c->stage_done = 1;
         return 0;
      }
@@ -765,6 +780,7 @@ static int run_stage (marxb200_ctx *c, int stage)
         n_in = a.n_out;
      }
    if (c->compact) c->ordered = false;
+   c->prepack.done = false;
    c->stage_done = stage;
    return 0;
 }
@@ -782,8 +798,11 @@ static int ensure_order (marxb200_ctx *c)
    o.bitmap = c->d_bitmap; o.word_prefix = c->d_word_prefix; o.block_prefix = c->d_block_prefix; o.perm = c->d_perm;
    CUDA_OK (cudaMemsetAsync (c->d_bitmap, 0, (c->n_generated / 32 + 1) * sizeof (uint32_t), c->stream));
    int nl = 0;
+   const bool pack = c->prepack.armed && (c->prepack.args.dst != nullptr);
+   if (pack && (c->prepack.ev_free != nullptr)) CUDA_OK (cudaStreamWaitEvent (c->stream, c->prepack.ev_free, 0));
    prof_begin (c);
-   launch_restore_order (o, c->num_sms, c->stream, &nl);
+   launch_restore_order (o, c->num_sms, c->stream, &nl, pack ? &c->prepack.args : nullptr);
+   c->prepack.done = pack;
    prof_mark (c, 9);
    c->launches += nl;
    CUDA_OK (cudaGetLastError ());
@@ -910,7 +929,7 @@ static int enter_mirror_after_scan (marxb200_ctx *c, const SourceArgs &a)
    launch_source_hrma (a, st, c->grid01, c->stream); prof_mark (c, 3);
    c->launches += (n != 0) ? 1 : 0;      // k01_source_hrma
    CUDA_OK (cudaGetLastError ());
-   c->cur = 1; c->stage_done = 0; c->n_generated = n; c->ordered = false;
+   c->cur = 1; c->stage_done = 0; c->n_generated = n; c->ordered = false; c->prepack.done = false;
    c->first_mirror_kernel = 1;
    return 0;
 }
@@ -1072,7 +1091,7 @@ extern "C" int marxb200_upload_from (marxb200_ctx *c, const marxb200_photon_attr
    unsigned long long nn = n;
    CUDA_OK (cudaMemcpyAsync (c->d_counts + 0, &nn, sizeof (nn), cudaMemcpyHostToDevice, c->stream));
    CUDA_OK (cudaStreamSynchronize (c->stream));
-   c->stage_done = 0; c->n_generated = n; c->ordered = true; c->first_mirror_kernel = 0;
+   c->stage_done = 0; c->n_generated = n; c->ordered = true; c->first_mirror_kernel = 0; c->prepack.done = false;
    c->det_dither_dirty = true;           // the records may carry dy, dz, dtheta (an ASPSOL run dumped to a rayfile)
    return 0;
 }
@@ -1400,6 +1419,7 @@ extern "C" int marxb200_egress_begin (marxb200_ctx *c, uint64_t max_out)
    const uint64_t n = (max_out < c->capacity) ? max_out : c->capacity;
    // the staging area may still be read by the previous copy: make the main stream wait for it
    CUDA_OK (cudaStreamWaitEvent (c->stream, c->ev_copied, 0));
+   if (c->prepack.owner == 0) { c->prepack.armed = false; c->prepack.done = false; }      // this call stages into the packed egress's first buffer
 #define STAGE(col, T) CUDA_OK (cudaMemcpyAsync (e.col, b.col, (size_t) n * sizeof (T), cudaMemcpyDeviceToDevice, c->stream))
    STAGE (energy, double); STAGE (time, double); STAGE (x0, double); STAGE (x1, double); STAGE (x2, double);
    STAGE (p0, double); STAGE (p1, double); STAGE (p2, double); STAGE (chipx, float); STAGE (chipy, float); STAGE (pi, float);
@@ -1453,15 +1473,27 @@ extern "C" int marxb200_egress_begin_packed (marxb200_ctx *c, uint64_t write_mas
         CUDA_OK (cudaMallocHost (&c->h_egress_count, sizeof (unsigned long long)));
      }
    if (max_out > c->capacity) max_out = c->capacity;
-   if (c->egress_cap < max_out)
+   if ((c->egress_cap < max_out) || (c->packed_slab_b == nullptr))
      {
         CUDA_OK (cudaStreamSynchronize (c->copy_stream));
-        if (c->egress_slab) cudaFree (c->egress_slab);
+        CUDA_OK (cudaStreamSynchronize (c->stream));
+        if (c->prepack.owner == 0) c->prepack.armed = false;            // its destination is about to be freed
+        if (c->egress_cap < max_out)
+          {
+             if (c->egress_slab) cudaFree (c->egress_slab);
+             c->egress_slab = nullptr; c->egress_cap = 0;
+             PhotonSoA tmp;
+             size_t bytes = carve (tmp, nullptr, max_out);       // 126 B per row: more than any packed row (<= 116 B)
+             CUDA_OK (cudaMalloc (&c->egress_slab, bytes));
+             carve (c->egress, (unsigned char *) c->egress_slab, max_out);
+             c->egress_cap = max_out;
+          }
+        if (c->packed_slab_b) cudaFree (c->packed_slab_b);
+        c->packed_slab_b = nullptr;
         PhotonSoA tmp;
-        size_t bytes = carve (tmp, nullptr, max_out);       // 126 B per row: more than any packed row (<= 116 B)
-        CUDA_OK (cudaMalloc (&c->egress_slab, bytes));
-        carve (c->egress, (unsigned char *) c->egress_slab, max_out);
-        c->egress_cap = max_out;
+        CUDA_OK (cudaMalloc (&c->packed_slab_b, carve (tmp, nullptr, c->egress_cap)));
+        for (int k = 0; k < 2; k++)
+          if (c->ev_slab_free[k] == nullptr) CUDA_OK (cudaEventCreateWithFlags (&c->ev_slab_free[k], cudaEventDisableTiming));
      }
    if (-1 == ensure_order (c)) return -1;
    EgressPlan &plan = c->packed_plan;
@@ -1476,19 +1508,39 @@ extern "C" int marxb200_egress_begin_packed (marxb200_ctx *c, uint64_t write_mas
         plan.num_cols++;
         total += (uint64_t) align16 ((size_t) max_out * kEgressCols[k].size);
      }
-   // The conversion runs on the COPY stream (behind the previous batch's copies, which read the same slab), so that the context's
-   // stream goes straight on with the next batch; what the kernel needs from the device scalars -- the event count, the batch
-   // start -- is snapshot in stream order first, because the next batch rewrites both.
-   CUDA_OK (cudaStreamWaitEvent (c->stream, c->ev_staged, 0));      // the previous conversion has consumed the last snapshot
-   CUDA_OK (cudaMemcpyAsync (c->d_snap, c->d_counts + c->stage_done, sizeof (unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
-   CUDA_OK (cudaMemcpyAsync (c->d_snap + 1, c->d_times, sizeof (double), cudaMemcpyDeviceToDevice, c->stream));
-   if (-1 == mxb_reader_begin (c, 0, c->copy_stream)) return -1;
-   launch_egress_pack (observed (c, c->buf[c->cur]), c->d_snap, max_out, plan, c->egress_slab, (const double *) (c->d_snap + 1), total_time, c->copy_stream);
-   c->launches += 1;
-   CUDA_OK (cudaMemcpyAsync (c->h_egress_count, c->d_snap, sizeof (unsigned long long), cudaMemcpyDeviceToHost, c->copy_stream));
-   CUDA_OK (cudaEventRecord (c->ev_staged, c->copy_stream));
-   if (-1 == mxb_reader_end (c, 0, c->copy_stream)) return -1;
+   // Two staging buffers alternate (the next batch's images may be written while this batch's are still being copied out).
+   void *slab[2] = {c->egress_slab, c->packed_slab_b};
+   const int k = c->packed_k ^ 1;
+   mx::PackArgs want;
+   memset (&want, 0, sizeof (want));
+   want.plan = plan; want.dst = (unsigned char *) slab[k]; want.dev_start_time = c->d_times; want.total_time = total_time; want.max_rows = max_out;
+   if (mxb_prepack_matches (c, 0, want))
+     {
+        // the order restoration at the end of the trace wrote these very images (pre-pack): only the count travels
+        CUDA_OK (cudaStreamWaitEvent (c->stream, c->ev_staged, 0));
+        CUDA_OK (cudaMemcpyAsync (c->h_egress_count, c->d_counts + c->stage_done, sizeof (unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK (cudaEventRecord (c->ev_staged, c->stream));
+     }
+   else
+     {
+        // The conversion runs on the COPY stream (behind the previous batches' copies), so that the context's stream goes straight on
+        // with the next batch; what the kernel needs from the device scalars -- the event count, the batch start -- is snapshot in
+        // stream order first, because the next batch rewrites both.
+        CUDA_OK (cudaStreamWaitEvent (c->stream, c->ev_staged, 0));      // the previous conversion has consumed the last snapshot
+        CUDA_OK (cudaMemcpyAsync (c->d_snap, c->d_counts + c->stage_done, sizeof (unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_OK (cudaMemcpyAsync (c->d_snap + 1, c->d_times, sizeof (double), cudaMemcpyDeviceToDevice, c->stream));
+        if (-1 == mxb_reader_begin (c, 0, c->copy_stream)) return -1;
+        launch_egress_pack (observed (c, c->buf[c->cur]), c->d_snap, max_out, plan, slab[k], (const double *) (c->d_snap + 1), total_time, c->copy_stream);
+        c->launches += 1;
+        CUDA_OK (cudaMemcpyAsync (c->h_egress_count, c->d_snap, sizeof (unsigned long long), cudaMemcpyDeviceToHost, c->copy_stream));
+        CUDA_OK (cudaEventRecord (c->ev_staged, c->copy_stream));
+        if (-1 == mxb_reader_end (c, 0, c->copy_stream)) return -1;
+     }
    CUDA_OK (cudaGetLastError ());
+   c->packed_k = k;
+   // a run that egresses every batch the same way: let the next batch's order restoration write the images into the other buffer
+   want.dst = (unsigned char *) slab[k ^ 1];
+   mxb_prepack_arm (c, 0, want, c->ev_slab_free[k ^ 1]);
    c->packed_cap = max_out;
    c->egress_pending = true; c->egress_is_packed = true;
    return 0;
@@ -1518,8 +1570,10 @@ extern "C" int marxb200_egress_end_packed (marxb200_ctx *c, void *host, uint64_t
    c->egress_pending = false; c->egress_is_packed = false;
    if (off > host_bytes) return fail ("marxb200_egress_end_packed: the host buffer holds %llu bytes, %llu are needed", (unsigned long long) host_bytes, (unsigned long long) off);
    for (int j = 0; j < plan.num_cols; j++)
-     if (n) CUDA_OK (cudaMemcpyAsync ((unsigned char *) host + layout->offset[j], (const unsigned char *) c->egress_slab + plan.offset[j],
+     if (n) CUDA_OK (cudaMemcpyAsync ((unsigned char *) host + layout->offset[j],
+                                      (const unsigned char *) ((c->packed_k == 0) ? c->egress_slab : c->packed_slab_b) + plan.offset[j],
                                       (size_t) n * layout->elem_size[j], cudaMemcpyDeviceToHost, c->copy_stream));
+   CUDA_OK (cudaEventRecord (c->ev_slab_free[c->packed_k], c->copy_stream));
    CUDA_OK (cudaEventRecord (c->ev_copied, c->copy_stream));
    CUDA_OK (cudaStreamSynchronize (c->copy_stream));
    return 0;

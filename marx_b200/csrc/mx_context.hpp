@@ -43,6 +43,21 @@ struct marxb200_ctx
    // read (-1: none); the first kernel of the context's stream that writes into that buffer waits for ev_reader_done.
    cudaEvent_t ev_reader_go[2] = {nullptr, nullptr}, ev_reader_done[2] = {nullptr, nullptr};
    int reader_buf[2] = {-1, -1};
+   // Pre-pack: a run that converts every batch to the same file images (marxb200_egress_begin_packed or marxb200_merge_events_begin
+   // with the same columns, time offset and row limit as for the previous batch) gets them from the order restoration at the end of
+   // the trace (order_gather<true>), written straight from the registers that hold the row; the begin call then finds them done and
+   // launches no conversion kernel.  Two staging buffers alternate: the next batch's images are written while the previous batch's
+   // are still being copied out.  owner: 0 = packed egress, 1 = merge.
+   struct Prepack
+   {
+      bool armed = false, done = false;
+      int owner = -1;
+      mx::PackArgs args;
+      cudaEvent_t ev_free = nullptr;           // recorded behind the copies that last read args.dst (may be null / never recorded)
+   } prepack;
+   void *packed_slab_b = nullptr;               // second staging buffer of the packed egress (the first is egress_slab)
+   int packed_k = 0;                            // staging buffer of the batch being egressed
+   cudaEvent_t ev_slab_free[2] = {nullptr, nullptr};
    unsigned long long *d_snap = nullptr;        // [0] event count, [1] batch start time (f64 bits): what the egress pack reads, snapshot in stream order
    bool batch_zeroed = false;                   // inside marxb200_trace(_sharded): the stage calls skip their own clears
    // time pre-pass of the NEXT contiguous batch, run on its own stream while this one is traced (marxb200_trace)
@@ -142,6 +157,8 @@ void mxb_fill_source_args (marxb200_ctx *c, mx::SourceArgs &a, uint64_t first_ra
 int mxb_enter_mirror_after_scan (marxb200_ctx *c, const mx::SourceArgs &a);
 int mxb_finish_trace (marxb200_ctx *c);
 int mxb_begin_batch (marxb200_ctx *c);
+bool mxb_prepack_matches (const marxb200_ctx *c, int owner, const mx::PackArgs &want);   // the current list's images exist in want.dst
+void mxb_prepack_arm (marxb200_ctx *c, int owner, const mx::PackArgs &next, cudaEvent_t ev_free);
 int mxb_guard_buffer (marxb200_ctx *c, int idx);   // before a kernel of the context's stream writes list buffer idx (-1: any)
 int mxb_reader_begin (marxb200_ctx *c, int slot, cudaStream_t reader);   // reader waits for the list; call mxb_reader_end after its launches
 int mxb_reader_end (marxb200_ctx *c, int slot, cudaStream_t reader);          // clears the batch's counters and tickets with one memset

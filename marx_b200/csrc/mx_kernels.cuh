@@ -158,7 +158,8 @@ struct OrderArgs
    uint32_t *block_prefix;               // [n_words/1024 + 1]
    uint32_t *perm;                       // [n_slots]: position in the unordered list of the photon with arrival rank j
 };
-void launch_restore_order (const OrderArgs &a, int num_sms, cudaStream_t s, int *n_launches);
+struct PackArgs;
+void launch_restore_order (const OrderArgs &a, int num_sms, cudaStream_t s, int *n_launches, const PackArgs *pack = nullptr);
 
 // host boundary helpers (AoS <-> SoA); `aos` is a device buffer of 136-byte records
 void launch_soa_to_aos (const PhotonSoA &in, const unsigned long long *n, uint64_t max_n, void *aos,
@@ -191,6 +192,15 @@ struct EgressPlan
    int num_cols;
    int kind[kMaxEgressCols];
    uint64_t offset[kMaxEgressCols];      // byte offset of each packed column in the staging buffer (4-byte aligned)
+};
+// file images emitted by the order restoration itself (order_gather<true>): the columns of `plan` for rows [0, max_rows) into dst
+struct PackArgs
+{
+   EgressPlan plan;
+   unsigned char *dst;
+   const double *dev_start_time;         // null: TIME = absolute time + total_time
+   double total_time;
+   uint64_t max_rows;
 };
 void launch_fp64_peak (double *sink, int grid, int iters, cudaStream_t s);   // 64 DFMA per thread per iteration
 void launch_egress_pack (const PhotonSoA &in, const unsigned long long *n, uint64_t max_n, const EgressPlan &plan, void *dst,

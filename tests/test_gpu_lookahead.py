@@ -65,3 +65,44 @@ def test_events_do_not_depend_on_the_look_ahead(script):
     # batch left in whatever rows the compaction happened to use (marx_write_photons does not emit it either, marxio.c:403-476)
     skip = ("order",) if any(step[0] == "load" for step in script) else ()
     _same(_run(True, script), _run(False, script), skip)
+
+
+def _egress_run(prepack, total_times):
+    """three batches, each followed by the pipelined packed egress with the same columns; -> the packed column images per batch"""
+    import marx_b200
+    from marx_b200 import HISTORY
+    mask = sum(HISTORY[k] for k in ("ENERGY", "TIME", "X_VECTOR", "P_VECTOR", "DET_NUM", "DET_PIXEL", "MIRROR_SHELL", "PULSEHEIGHT",
+                                    "ORDER", "PI", "SKY_DITHER", "TAG"))
+    old = os.environ.get("MARXB200_PREPACK")
+    os.environ["MARXB200_PREPACK"] = "1" if prepack else "0"              # read when a begin call arms the next batch
+    out = []
+    try:
+        with marx_b200.MarxB200("c2_hetg_acis_s", seed=99, max_photons=N) as m:
+            host = np.zeros(N // 4 * 96 + 4096, dtype=np.uint8)
+            launches = []
+            for k, tt in enumerate(total_times):
+                m.trace(k * N, N)
+                before = m.launch_count()
+                m.egress_begin_packed(mask, tt, N // 4)
+                launches.append(m.launch_count() - before)
+                cols = m.egress_end_packed(host)
+                out.append({name: v.copy() for name, v in cols.items()})
+    finally:
+        if old is None:
+            del os.environ["MARXB200_PREPACK"]
+        else:
+            os.environ["MARXB200_PREPACK"] = old
+    return out, launches
+
+
+def test_file_images_written_by_the_order_restoration_equal_the_conversion_kernel():
+    """pre-pack: from the second batch on the packed images come from order_gather<true>; a changed time offset
+    falls back to the conversion kernel for that batch"""
+    times = [0.0, 0.0, 0.0, 12.5, 12.5]
+    a, la = _egress_run(True, times)
+    b, lb = _egress_run(False, times)
+    assert la == [1, 0, 0, 1, 0] and lb == [1, 1, 1, 1, 1], (la, lb)      # conversion kernels launched by the begin calls
+    for k, (x, y) in enumerate(zip(a, b)):
+        assert set(x) == set(y) and len(x) >= 12
+        for name in x:
+            assert x[name].tobytes() == y[name].tobytes(), (k, name)
