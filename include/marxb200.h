@@ -693,6 +693,24 @@ int marxb200_measure_fp64_peak (marxb200_ctx *ctx, double *tflops);
 /* kernel launch counter (bench.py "gpu_launches") */
 int marxb200_get_launch_count (marxb200_ctx *ctx, uint64_t *n);
 
+/* ------------------------------------------------------------------------------------------------ */
+/* Work the library does AHEAD of the call that asks for it (results never depend on it):
+ *  - marxb200_trace / marxb200_trace_sharded launch the arrival-time pre-pass (and, sharded, the all-gather of its sums) of the
+ *    next contiguous batch -- the same number of rays right behind the batch just traced -- on a stream of their own.  A call that
+ *    asks for other rays, or follows marxb200_set_source / marxb200_load_calpack, runs the pre-pass itself.
+ *  - after marxb200_egress_begin_packed or marxb200_merge_events_begin, the order restoration of the next traced batch also writes
+ *    the file images of the same columns (same write mask, time offset, row limit); a begin call with exactly those arguments then
+ *    launches no conversion kernel, any other one converts as usual.  Costs one more staging buffer of max_out rows.
+ *
+ * Environment switches (read when a context / communicator is created, or at the call; all default to the fast path):
+ *   MARXB200_VERBOSE=1            grids, merge transport, look-ahead statistics on stderr
+ *   MARXB200_LOOKAHEAD=0          no pre-pass look-ahead              MARXB200_PREPACK=0       conversion kernel for every batch
+ *   MARXB200_K01_TICKET=0         static tile stride in the fused source + HRMA-A kernel
+ *   MARXB200_K1_SPLIT=0 / _K2_SPLIT=0 / _K3_SPLIT=0   the stage as fewer, larger kernels (A/B runs; identical results)
+ *   MARXB200_PILEUP_FUSED=0       pile-up by the step kernels only    MARXB200_PILEUP_WINDOW=256|512|1024  first window size tried
+ *   MARXB200_NCCL_LIB=path        the NCCL library to dlopen (default libnccl.so.2)
+ *   MARXB200_MERGE_TRANSPORT=nccl ncclSend / ncclRecv instead of CUDA-IPC peer writes      MARXB200_NCCL_CTAS=0  NCCL's own CTA count */
+
 #ifdef __cplusplus
 }
 #endif
