@@ -1,14 +1,7 @@
 mkdir -p gpurun_out
-MARXB200_BENCH_HANG_S=300 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 60 --warmup 3 > gpurun_out/r02_bench_n2.json 2> gpurun_out/r02_bench_n2.err
-python - <<PY
-import json
-d=json.loads(open("gpurun_out/r02_bench_n2.json").read().strip().splitlines()[-1])
-print("N=2 value %.4g ms %.4f e2e %.4g nomerge %.4g" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d["merge"]["value_without_merge"]))
-PY
-timeout 900 python bench.py > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err
-python - <<PY
-import json
-d=json.loads(open("gpurun_out/r02_bench_n1.json").read().strip().splitlines()[-1])
-print("N=1 value %.4g ms %.4f e2e %.4g" % (d["value"], d["ms_per_step"], d["e2e"]["value"]))
-PY
-cp gpurun_out/r02_bench_n1.json gpurun_out/r02_bench_n1_samebox_as_n2.json
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 1 python tools/sanitize_probe.py 20000 > gpurun_out/r02_racecheck.txt 2>&1
+echo "racecheck rc=$?"; tail -4 gpurun_out/r02_racecheck.txt | cut -c1-300; grep -c "Race reported\|hazard" gpurun_out/r02_racecheck.txt
+timeout 900 compute-sanitizer --tool synccheck --error-exitcode 1 python tools/sanitize_probe.py 20000 > gpurun_out/r02_synccheck.txt 2>&1
+echo "synccheck rc=$?"; tail -2 gpurun_out/r02_synccheck.txt | cut -c1-300
+timeout 300 compute-sanitizer --tool racecheck --error-exitcode 1 python tools/pileup_ncu_probe.py 200000 > gpurun_out/r02_racecheck_pileup.txt 2>&1
+echo "racecheck pileup rc=$?"; tail -3 gpurun_out/r02_racecheck_pileup.txt | cut -c1-300
