@@ -165,10 +165,18 @@ struct Rng
       b0 = b1 = b2 = b3 = 0;
    }
    // continue a stream that another kernel left after `d` draws (sub-stage kernels of one MARX stage share a stream)
+   // The block is consumed from b0: every draw returns b0 and shifts the rest down (three moves, none when the compiler knows the
+   // draw index; picking word draw & 3 took three compares and three selects per draw: 6 % of k01's instructions).
    MX_HD void resume (uint32_t d, int has_spare, double spare_value)
    {
       draw = d; have_spare = has_spare; spare = spare_value;
-      if ((d & 3u) != 0u) refill (d >> 2);
+      if ((d & 3u) != 0u)
+        {
+           refill (d >> 2);
+#ifndef MX_PHILOX_SELECT
+           for (uint32_t k = 0; k < (d & 3u); k++) { b0 = b1; b1 = b2; b2 = b3; }
+#endif
+        }
    }
    MX_HD void refill (uint32_t block)
    {
@@ -190,10 +198,18 @@ struct Rng
    }
    MX_HD uint32_t next_u32 ()
    {
-      uint32_t lane = draw & 3u;
+#ifdef MX_PHILOX_SELECT            // developer A/B knob: the round-1 form (word draw & 3 of an unshifted block)
+      const uint32_t lane = draw & 3u;
       if (lane == 0u) refill (draw >> 2);
       draw++;
       return lane == 0u ? b0 : (lane == 1u ? b1 : (lane == 2u ? b2 : b3));
+#else
+      if ((draw & 3u) == 0u) refill (draw >> 2);
+      draw++;
+      const uint32_t r = b0;
+      b0 = b1; b1 = b2; b2 = b3;
+      return r;
+#endif
    }
    // JDMrandom, random.c:151-154: uniform on [0,1] inclusive
    MX_HD double uniform () { return (double) next_u32 () * (1.0 / 4294967295.0); }
