@@ -134,6 +134,22 @@ MX_HD Vec3 m3_mul (const double *m, const Vec3 &v)
    return b;
 }
 
+// An FP64 quotient that is exactly zero (0 / x) leaves the fast path of the device's division and runs its ~100-instruction special-case
+// routine.  Three places of this path divide a numerator that is zero for most or all rays (a vector component that is literally 0, the
+// diffraction term of order 0, the scatter-angle interpolation between two zero angles); each now tests for the zero first.  Written as
+// `cond ? 0 : a / b` the compiler evaluates the quotient anyway and selects afterwards, so the division that remains is pinned inside its
+// branch (ncu, round 2: 3 % of k01_source_hrma's instructions, 2-3 % of k1_hrma<4|5> and k2_grating<1>).
+MX_HD double div_in_branch (double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+   double q;
+   asm volatile ("div.rn.f64 %0, %1, %2;" : "=d"(q) : "d"(a), "d"(b));
+   return q;
+#else
+   return a / b;
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10 draw stream (include/marxb200.h, "Random draws").  Replaces JDMrandom
 // (jdmath/src/random.c:100-154) with a per-(ray, stage) counter so photons are independent.

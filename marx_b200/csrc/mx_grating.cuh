@@ -71,7 +71,10 @@ MX_HD Vec3 v_unit (Vec3 a) { v_normalize (a); return a; }
 MX_HD int diffract_photon (const GratingShellDev &g, double theta, double energy, const Vec3 &x, Vec3 &pio,
                            int order, bool use_sectors, Rng &rng)
 {
-   double n_lambda_over_d = order * (2.0 * kPI * kHbarC) / g.period / energy;
+   // order 0 (half of the rays that reach this point): 0 * c / period / energy is +0 for positive period and energy
+   double n_lambda_over_d = 0.0;
+   if (!((order == 0) && (g.period > 0.0) && (energy > 0.0)))
+     n_lambda_over_d = div_in_branch (div_in_branch (order * (2.0 * kPI * kHbarC), g.period), energy);
    Vec3 p = pio;
    Vec3 n = v_unit (x);
    n.x = -n.x; n.y = -n.y; n.z = -n.z;

@@ -191,7 +191,9 @@ MX_HD_BIG double wfold_interp (const WfoldDev &w, double energy, double sin_alph
    double theta_0 = wfold_theta (w, i - 1, r);
    double theta_1 = wfold_theta (w, i, r);
    double e0 = keys[ks * (i - 1)], e1 = keys[ks * i];
-   return theta_0 + (theta_1 - theta_0) * (e_alpha - e0) / (e1 - e0);
+   // 94 % of the draws lie below both arrays' p_min: both angles are 0, the interpolation term is 0 / (e1 - e0) = 0 and the sum theta_0
+   if ((theta_1 == theta_0) && (e1 != e0)) return theta_0;
+   return theta_0 + div_in_branch ((theta_1 - theta_0) * (e_alpha - e0), e1 - e0);
 }
 
 // intersects_struts, hrma.c:928-968.  struts = {xpos0, half_width0, xpos1, half_width1}

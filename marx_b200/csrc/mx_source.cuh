@@ -91,7 +91,8 @@ MX_HD Vec3 apply_dither_rolled (double ra, double dec, Vec3 p)
    Vec3 n = v_make (0, sin_dec, -cos_dec * sin_ra);
    double sin_theta = v_length (n);
    if (sin_theta <= 1e-20) return p;
-   n.x /= sin_theta; n.y /= sin_theta; n.z /= sin_theta;
+   // n.x is +0 and sin_theta > 0: the reference's n.x / sin_theta is +0 again (and a zero quotient is the division's slow case)
+   n.y /= sin_theta; n.z /= sin_theta;
    return v_rotate_unit1 (p, n, cos_theta, sin_theta);
 }
 MX_HD Vec3 apply_dither (double ra, double dec, double roll, Vec3 p)
