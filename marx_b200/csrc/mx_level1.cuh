@@ -158,7 +158,9 @@ MX_HD Vec3 l1_unapply_dither (double ra, double dec, double roll, Vec3 p)
    const double sin_theta = v_length (n);
    if (sin_theta >= 1e-20)
      {
-        n.x /= sin_theta; n.y /= sin_theta; n.z /= sin_theta;
+        // n.x is +0 and sin_theta > 0: n.x / sin_theta is +0 again, and a zero quotient runs the FP64 division's special-case routine
+        // (4.5 % of l1_transform's instructions, tools/ncu_calls.py); see div_in_branch, mx_common.cuh
+        n.y /= sin_theta; n.z /= sin_theta;
         p = v_rotate_unit1 (p, n, cos_theta, sin_theta);
      }
    sin_cos (roll, sr, cr);
