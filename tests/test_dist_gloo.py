@@ -21,11 +21,13 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     rng = np.random.default_rng(100 + rank)
-    sums = rng.random(7) * 3.0 + rank            # this rank's super-tile sums
+    # this rank's super-tile sums; RAGGED: the last block of a step may be short (fewer super-tiles) or empty
+    n_sums = [7, 4, 0][rank] if world == 3 else [7, 3][rank]
+    sums = rng.random(n_sums) * 3.0 + rank
     base, end = exchange_time_base(sums, rank, world, running=10.0)
     # events of this rank: times inside its block, ragged counts (rank 1 has none -> empty-input edge case)
     n_ev = [5, 0, 3][rank] if world == 3 else [5, 0][rank]
-    t = np.sort(base + rng.random(n_ev) * (sums.sum()))
+    t = np.sort(base + rng.random(n_ev) * (sums.sum() if n_sums else 1.0))
     cols = {"time": t, "pha": (np.arange(n_ev) + 100 * rank).astype(np.int16), "ray": (np.arange(n_ev) + 1000 * rank).astype(np.uint64)}
     merged = gather_event_columns(cols, rank, world, dst=0)
     q.put((rank, sums, base, end, cols, merged))
